@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes front end for the two CPU checkers.
+
+  OracleLib("port")       -> oracle/libvbx_oracle.so      (restatement, oracle/vbx_oracle.cc)
+  OracleLib("reference")  -> oracle/_ref/libvbx_ref.so    (the reference's own sources)
+
+Both export oracle/vbo_api.h.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module; the product package
+voxblox_b200 never does (tests/test_layout.py enforces it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libvbx_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libvbx_ref.so")
+
+TSDF_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4"), ("color", "u1", (4,))])
+ESDF_DTYPE = np.dtype([("distance", "<f4"), ("observed", "u1"), ("hallucinated", "u1"),
+                       ("in_queue", "u1"), ("fixed", "u1"), ("parent", "<i4", (3,))])
+assert TSDF_DTYPE.itemsize == 12 and ESDF_DTYPE.itemsize == 20
+
+SIMPLE, MERGED, FAST = 1, 2, 3
+ORDER_REFERENCE, ORDER_CANONICAL = 0, 1
+LAYER_TSDF, LAYER_ESDF = 0, 1
+
+
+class TsdfConfig(C.Structure):
+    """vbo_tsdf_config; defaults = TsdfIntegratorBase::Config (tsdf_integrator.h:56-89)."""
+    _fields_ = [("default_truncation_distance", C.c_float), ("max_weight", C.c_float),
+                ("voxel_carving_enabled", C.c_int32), ("min_ray_length_m", C.c_float),
+                ("max_ray_length_m", C.c_float), ("use_const_weight", C.c_int32),
+                ("allow_clear", C.c_int32), ("use_weight_dropoff", C.c_int32),
+                ("use_sparsity_compensation_factor", C.c_int32),
+                ("sparsity_compensation_factor", C.c_float), ("integrator_threads", C.c_int32),
+                ("integration_order_mode", C.c_int32), ("enable_anti_grazing", C.c_int32),
+                ("start_voxel_subsampling_factor", C.c_float),
+                ("max_consecutive_ray_collisions", C.c_int32),
+                ("clear_checks_every_n_frames", C.c_int32), ("max_integration_time_s", C.c_float)]
+
+    def __init__(self, **kw):
+        d = dict(default_truncation_distance=0.1, max_weight=10000.0, voxel_carving_enabled=1,
+                 min_ray_length_m=0.1, max_ray_length_m=5.0, use_const_weight=0, allow_clear=1,
+                 use_weight_dropoff=1, use_sparsity_compensation_factor=0,
+                 sparsity_compensation_factor=1.0, integrator_threads=1, integration_order_mode=0,
+                 enable_anti_grazing=0, start_voxel_subsampling_factor=2.0,
+                 max_consecutive_ray_collisions=2, clear_checks_every_n_frames=1,
+                 max_integration_time_s=3.4028234663852886e38)
+        d.update(kw)
+        super().__init__(**d)
+
+
+class EsdfConfig(C.Structure):
+    """vbo_esdf_config; defaults = EsdfIntegrator::Config (esdf_integrator.h:29-78)."""
+    _fields_ = [("full_euclidean_distance", C.c_int32), ("max_distance_m", C.c_float),
+                ("min_distance_m", C.c_float), ("default_distance_m", C.c_float),
+                ("min_diff_m", C.c_float), ("min_weight", C.c_float), ("num_buckets", C.c_int32),
+                ("multi_queue", C.c_int32), ("add_occupied_crust", C.c_int32),
+                ("clear_sphere_radius", C.c_float), ("occupied_sphere_radius", C.c_float)]
+
+    def __init__(self, **kw):
+        d = dict(full_euclidean_distance=0, max_distance_m=2.0, min_distance_m=0.2,
+                 default_distance_m=2.0, min_diff_m=0.001, min_weight=1e-6, num_buckets=20,
+                 multi_queue=0, add_occupied_crust=0, clear_sphere_radius=1.5,
+                 occupied_sphere_radius=5.0)
+        d.update(kw)
+        super().__init__(**d)
+
+
+def available(which: str) -> bool:
+    return os.path.exists(REF_SO if which == "reference" else PORT_SO)
+
+
+class OracleLib:
+    def __init__(self, which: str = "port"):
+        path = REF_SO if which == "reference" else PORT_SO
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle` (or __graft_entry__.build())")
+        self.which = which
+        lib = C.CDLL(path)
+        lib.vbo_impl_name.restype = C.c_char_p
+        lib.vbo_create.restype = C.c_void_p
+        lib.vbo_create.argtypes = [C.POINTER(TsdfConfig), C.c_float, C.c_int]
+        lib.vbo_destroy.argtypes = [C.c_void_p]
+        lib.vbo_integrate.restype = C.c_int
+        lib.vbo_integrate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        lib.vbo_last_seconds.restype = C.c_double
+        lib.vbo_last_seconds.argtypes = [C.c_void_p]
+        lib.vbo_last_counters.argtypes = [C.c_void_p, C.c_void_p]
+        lib.vbo_num_blocks.restype = C.c_uint64
+        lib.vbo_num_blocks.argtypes = [C.c_void_p, C.c_int]
+        lib.vbo_block_indices.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.vbo_get_block.restype = C.c_int
+        lib.vbo_get_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vbo_esdf_create.restype = C.c_int
+        lib.vbo_esdf_create.argtypes = [C.c_void_p, C.POINTER(EsdfConfig)]
+        lib.vbo_esdf_update.restype = C.c_int
+        lib.vbo_esdf_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.vbo_esdf_add_robot_position.restype = C.c_int
+        lib.vbo_esdf_add_robot_position.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib = lib
+        assert lib.vbo_impl_name().decode() == which
+
+
+class OracleMap:
+    """One TSDF (+ optional ESDF) layer with the three integrators attached."""
+
+    def __init__(self, lib: OracleLib, cfg: TsdfConfig, voxel_size: float, voxels_per_side: int = 16):
+        self.lib = lib.lib
+        self.vps = voxels_per_side
+        self.voxel_size = voxel_size
+        self.h = self.lib.vbo_create(C.byref(cfg), voxel_size, voxels_per_side)
+
+    def close(self):
+        if self.h:
+            self.lib.vbo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def integrate(self, kind: int, scan, freespace: bool = False, order: int = ORDER_REFERENCE):
+        pts, cols, q, t = scan
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        cols = np.ascontiguousarray(cols, dtype=np.uint8)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        assert pts.shape[0] == cols.shape[0]
+        rc = self.lib.vbo_integrate(self.h, kind, q.ctypes.data, t.ctypes.data, pts.ctypes.data,
+                                    cols.ctypes.data, pts.shape[0], int(freespace), order)
+        if rc != 0:
+            raise RuntimeError(f"vbo_integrate rc={rc}")
+
+    def last_seconds(self) -> float:
+        return float(self.lib.vbo_last_seconds(self.h))
+
+    def counters(self) -> Dict[str, int]:
+        out = np.zeros(8, dtype=np.uint64)
+        self.lib.vbo_last_counters(self.h, out.ctypes.data)
+        names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
+                 "blocks_allocated", "valid_points", "reserved"]
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def block_indices(self, layer: int = LAYER_TSDF) -> np.ndarray:
+        m = int(self.lib.vbo_num_blocks(self.h, layer))
+        out = np.zeros((m, 3), dtype=np.int32)
+        if m:
+            self.lib.vbo_block_indices(self.h, layer, out.ctypes.data)
+        return out
+
+    def block(self, idx, layer: int = LAYER_TSDF) -> Tuple[np.ndarray, int]:
+        dt = TSDF_DTYPE if layer == LAYER_TSDF else ESDF_DTYPE
+        vox = np.zeros(self.vps ** 3, dtype=dt)
+        i3 = np.ascontiguousarray(idx, dtype=np.int32)
+        upd = C.c_uint8(0)
+        rc = self.lib.vbo_get_block(self.h, layer, i3.ctypes.data, vox.ctypes.data, C.byref(upd))
+        if rc != 0:
+            raise KeyError(tuple(int(v) for v in idx))
+        return vox, int(upd.value)
+
+    def blocks(self, layer: int = LAYER_TSDF) -> Dict[Tuple[int, int, int], np.ndarray]:
+        return {tuple(int(v) for v in i): self.block(i, layer)[0] for i in self.block_indices(layer)}
+
+    def esdf_create(self, cfg: EsdfConfig):
+        rc = self.lib.vbo_esdf_create(self.h, C.byref(cfg))
+        if rc != 0:
+            raise RuntimeError(f"vbo_esdf_create rc={rc}")
+
+    def esdf_update(self, batch: bool = False, clear_updated_flag: bool = True):
+        rc = self.lib.vbo_esdf_update(self.h, int(batch), int(clear_updated_flag))
+        if rc != 0:
+            raise RuntimeError(f"vbo_esdf_update rc={rc}")
+
+    def esdf_add_robot_position(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float32)
+        rc = self.lib.vbo_esdf_add_robot_position(self.h, p.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"vbo_esdf_add_robot_position rc={rc}")

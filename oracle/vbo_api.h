@@ -1,0 +1,107 @@
+/* TEST INFRASTRUCTURE ONLY -- the C interface shared by the two CPU checkers:
+ *   oracle/_ref/libvbx_ref.so   the reference's own hot-path translation units
+ *                               (compiled verbatim from /root/reference against
+ *                               oracle/shim/), wrapped by oracle/ref_harness.cc
+ *   oracle/libvbx_oracle.so     the from-scratch restatement, oracle/vbx_oracle.cc
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load either library.  The product (voxblox_b200/) never does.
+ */
+#ifndef VBO_API_H_
+#define VBO_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* POD mirror of TsdfIntegratorBase::Config
+ * (voxblox/include/voxblox/integrator/tsdf_integrator.h:56-89). */
+typedef struct vbo_tsdf_config {
+  float default_truncation_distance;
+  float max_weight;
+  int32_t voxel_carving_enabled;
+  float min_ray_length_m;
+  float max_ray_length_m;
+  int32_t use_const_weight;
+  int32_t allow_clear;
+  int32_t use_weight_dropoff;
+  int32_t use_sparsity_compensation_factor;
+  float sparsity_compensation_factor;
+  int32_t integrator_threads;
+  int32_t integration_order_mode; /* 0 "mixed", 1 "sorted" */
+  int32_t enable_anti_grazing;
+  float start_voxel_subsampling_factor;
+  int32_t max_consecutive_ray_collisions;
+  int32_t clear_checks_every_n_frames;
+  float max_integration_time_s;
+} vbo_tsdf_config;
+
+/* POD mirror of EsdfIntegrator::Config
+ * (voxblox/include/voxblox/integrator/esdf_integrator.h:29-78). */
+typedef struct vbo_esdf_config {
+  int32_t full_euclidean_distance;
+  float max_distance_m;
+  float min_distance_m;
+  float default_distance_m;
+  float min_diff_m;
+  float min_weight;
+  int32_t num_buckets;
+  int32_t multi_queue;
+  int32_t add_occupied_crust;
+  float clear_sphere_radius;
+  float occupied_sphere_radius;
+} vbo_esdf_config;
+
+/* bundle_order for the Merged integrator:
+ *   0  reference order: libstdc++ unordered_map iteration order, as
+ *      integrateVoxels walks it (tsdf_integrator.cc:434-457)
+ *   1  canonical order: bundles ascending by (z, y, x) of their voxel index,
+ *      normal bundles before clearing bundles.  Only the restatement offers it
+ *      (the reference leaves the cross-ray update order to its thread schedule).
+ */
+enum { VBO_ORDER_REFERENCE = 0, VBO_ORDER_CANONICAL = 1 };
+enum { VBO_SIMPLE = 1, VBO_MERGED = 2, VBO_FAST = 3 }; /* TsdfIntegratorType */
+enum { VBO_LAYER_TSDF = 0, VBO_LAYER_ESDF = 1 };
+
+const char* vbo_impl_name(void); /* "reference" or "port" */
+
+void* vbo_create(const vbo_tsdf_config* cfg, float voxel_size, int voxels_per_side);
+void vbo_destroy(void* h);
+
+/* TsdfIntegratorBase::integratePointCloud (tsdf_integrator.h:100-103).
+ * q_wxyz + t = T_G_C; xyz = 3n floats (points_C); rgba = 4n bytes. */
+int vbo_integrate(void* h, int kind, const float q_wxyz[4], const float t[3],
+                  const float* xyz, const uint8_t* rgba, uint64_t n, int freespace,
+                  int bundle_order);
+/* seconds spent inside the last integratePointCloud / ESDF update call */
+double vbo_last_seconds(void* h);
+/* counters of the last integrate call (restatement only; zeros from _ref):
+ * [0] normal rays/bundles cast, [1] clearing rays/bundles cast, [2] K voxel
+ * updates attempted, [3] U distinct voxels touched, [4] B distinct blocks touched,
+ * [5] blocks newly allocated, [6] valid points, [7] reserved */
+void vbo_last_counters(void* h, uint64_t out[8]);
+
+uint64_t vbo_num_blocks(void* h, int layer);
+/* 3*M int32, sorted ascending by (x, y, z) */
+void vbo_block_indices(void* h, int layer, int32_t* out);
+/* voxels: vps^3 * 12 B (TsdfVoxel: f32 distance, f32 weight, u8 rgba;
+ * core/voxel.h:12-16) or * 20 B (EsdfVoxel: f32 distance, u8 observed,
+ * hallucinated, in_queue, fixed, i32 parent[3]; core/voxel.h:18-37), linear index
+ * x + vps*(y + vps*z).  updated_bits: bit0 kMap, bit1 kMesh, bit2 kEsdf
+ * (core/block.h:15-18).  Returns 0, or 1 if the block does not exist. */
+int vbo_get_block(void* h, int layer, const int32_t idx[3], void* voxels,
+                  uint8_t* updated_bits);
+
+int vbo_esdf_create(void* h, const vbo_esdf_config* cfg);
+/* batch=0: updateFromTsdfLayer(clear_updated_flag) (esdf_integrator.cc:104-122)
+ * batch=1: updateFromTsdfLayerBatch()              (esdf_integrator.cc:94-102) */
+int vbo_esdf_update(void* h, int batch, int clear_updated_flag);
+/* EsdfIntegrator::addNewRobotPosition (esdf_integrator.cc:25-92) */
+int vbo_esdf_add_robot_position(void* h, const float p[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBO_API_H_ */

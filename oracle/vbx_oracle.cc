@@ -1,0 +1,977 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): a single-threaded CPU restatement of the
+// voxblox TSDF / ESDF integration hot path, written from the reference's
+// behaviour (every function cites the reference file:line it follows; all paths
+// are under /root/reference/voxblox).  It exists to CHECK the CUDA engine; it is
+// never linked into, imported by or executed from the product (voxblox_b200/).
+//
+// Pinning: tests/test_oracle_pin.py runs this restatement and the reference's own
+// sources (oracle/_ref/libvbx_ref.so = the verbatim .cc files compiled against
+// oracle/shim/) on the same seeded scans and requires bit-identical layers, and
+// replays the known-answer indexing vectors of test/test_tsdf_map.cc.  Committed
+// digests under tests/golden/ pin it where /root/reference is absent.
+//
+// Arithmetic conventions restated from the reference's third-party deps (Eigen 3.3
+// and ethz-asl/minkindr, both unpinned in voxblox_https.rosinstall:5-22):
+//   sum of 3 coefficients  = c0 + (c1 + c2)            (Eigen Redux.h unroller)
+//   normalized(v)          = v / sqrt(|v|^2), v if |v|^2 == 0   (Eigen Dot.h, 3.3)
+//   q * v                  = v + w*(2 q.vec x v) + q.vec x (2 q.vec x v)
+//   T * p                  = q * p + t                 (minkindr transform())
+// Build: g++ -O2 -ffp-contract=off, no -march=native => one IEEE rounding per op.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <queue>
+#include <unordered_map>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+#include "vbo_api.h"
+
+namespace {
+
+// ----------------------------------------------------------------------- 3-vectors
+struct V3 {
+  float x, y, z;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline float dot3(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+inline float sqnorm3(V3 a) { return dot3(a, a); }
+inline float norm3(V3 a) { return std::sqrt(sqnorm3(a)); }
+inline V3 unit3(V3 a) {
+  const float z = sqnorm3(a);
+  return z > 0.0f ? a / std::sqrt(z) : a;
+}
+inline V3 cross3(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+struct Pose {  // T_G_C
+  float w, x, y, z;
+  V3 t;
+  V3 apply(V3 p) const {
+    const V3 qv{x, y, z};
+    V3 uv = cross3(qv, p);
+    uv = uv + uv;
+    return ((p + uv * w) + cross3(qv, uv)) + t;
+  }
+};
+
+// --------------------------------------------------------------------- index types
+struct I3 {  // AnyIndex / BlockIndex / VoxelIndex (core/common.h:48-51)
+  int x, y, z;
+  bool operator==(const I3& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct L3 {  // LongIndex / GlobalIndex (core/common.h:53-54)
+  int64_t x, y, z;
+  bool operator==(const L3& o) const { return x == o.x && y == o.y && z == o.z; }
+  bool operator!=(const L3& o) const { return !(*this == o); }
+};
+// core/block_hash.h:20-33 and :52-64: x + 17191 y + 17191^2 z, truncated to 32 bits.
+struct HashI3 {
+  size_t operator()(const I3& i) const {
+    return static_cast<unsigned int>(static_cast<size_t>(i.x) + static_cast<size_t>(i.y) * 17191u +
+                                     static_cast<size_t>(i.z) * (17191ull * 17191ull));
+  }
+};
+struct HashL3 {
+  size_t operator()(const L3& i) const {
+    return static_cast<unsigned int>(static_cast<size_t>(i.x) + static_cast<size_t>(i.y) * 17191u +
+                                     static_cast<size_t>(i.z) * (17191ull * 17191ull));
+  }
+};
+
+constexpr float kEps = 1e-6f;  // kEpsilon / kFloatEpsilon, core/common.h:139-140
+
+// core/common.h:153-159 (with a grid_size_inv) and :166-171 (pre-scaled point)
+inline L3 gridIndex(V3 p, float inv) {
+  return {static_cast<int64_t>(std::floor(p.x * inv + kEps)),
+          static_cast<int64_t>(std::floor(p.y * inv + kEps)),
+          static_cast<int64_t>(std::floor(p.z * inv + kEps))};
+}
+inline L3 gridIndexScaled(V3 p) {
+  return {static_cast<int64_t>(std::floor(p.x + kEps)), static_cast<int64_t>(std::floor(p.y + kEps)),
+          static_cast<int64_t>(std::floor(p.z + kEps))};
+}
+// core/common.h:186-193: (float(idx) + 0.5 [double]) * grid_size, rounded to float
+inline V3 centerPoint(const L3& i, float grid) {
+  return {static_cast<float>((static_cast<float>(i.x) + 0.5) * grid),
+          static_cast<float>((static_cast<float>(i.y) + 0.5) * grid),
+          static_cast<float>((static_cast<float>(i.z) + 0.5) * grid)};
+}
+// core/common.h:215-224
+inline I3 blockOf(const L3& g, float vps_inv) {
+  return {static_cast<int>(std::floor(static_cast<float>(g.x) * vps_inv)),
+          static_cast<int>(std::floor(static_cast<float>(g.y) * vps_inv)),
+          static_cast<int>(std::floor(static_cast<float>(g.z) * vps_inv))};
+}
+// core/common.h:233-243 and core/block_inl.h:12-27
+inline size_t localLinear(const L3& g, int vps) {
+  constexpr int64_t off = int64_t(1) << 31;  // "1 << (8*sizeof(int) - 1)" wraps to INT_MIN; & mask is the same
+  const int lx = static_cast<int>((g.x + off) & (vps - 1));
+  const int ly = static_cast<int>((g.y + off) & (vps - 1));
+  const int lz = static_cast<int>((g.z + off) & (vps - 1));
+  return static_cast<size_t>(lx + vps * (ly + lz * vps));
+}
+inline int signumf(float v) { return (v == 0) ? 0 : (v < 0 ? -1 : 1); }  // core/common.h:258
+
+// -------------------------------------------------------------------------- voxels
+struct Rgba {
+  uint8_t r, g, b, a;
+};
+struct TsdfVox {  // core/voxel.h:12-16
+  float distance = 0.0f;
+  float weight = 0.0f;
+  Rgba color{0, 0, 0, 0};
+};
+struct EsdfVox {  // core/voxel.h:18-37
+  float distance = 0.0f;
+  uint8_t observed = 0, hallucinated = 0, in_queue = 0, fixed = 0;
+  int32_t parent[3] = {0, 0, 0};
+};
+static_assert(sizeof(TsdfVox) == 12 && sizeof(EsdfVox) == 20, "voxel layouts");
+
+// core/common.h:105-125
+inline Rgba blend(Rgba c1, float w1, Rgba c2, float w2) {
+  const float total = w1 + w2;
+  w1 /= total;
+  w2 /= total;
+  Rgba o;
+  o.r = static_cast<uint8_t>(std::round(c1.r * w1 + c2.r * w2));
+  o.g = static_cast<uint8_t>(std::round(c1.g * w1 + c2.g * w2));
+  o.b = static_cast<uint8_t>(std::round(c1.b * w1 + c2.b * w2));
+  o.a = static_cast<uint8_t>(std::round(c1.a * w1 + c2.a * w2));
+  return o;
+}
+
+template <typename V>
+struct Blk {
+  std::vector<V> vox;
+  uint8_t updated = 0;  // bit0 kMap, bit1 kMesh, bit2 kEsdf (core/block.h:15-18)
+  explicit Blk(int vps) : vox(static_cast<size_t>(vps) * vps * vps) {}
+};
+template <typename V>
+using BlockMap = std::unordered_map<I3, std::shared_ptr<Blk<V>>, HashI3>;
+
+// ----------------------------------------------------------------------- ray caster
+// integrator/integrator_utils.cc:72-179 (Amanatides-Woo in voxel units)
+struct Dda {
+  L3 cur{0, 0, 0};
+  int sgn[3] = {0, 0, 0};
+  float tnext[3] = {0, 0, 0}, tstep[3] = {0, 0, 0};
+  unsigned int len = 0, step = 0;
+  bool dead = false;
+
+  Dda(V3 origin, V3 point_G, bool clearing, bool carving, float max_ray, float inv, float trunc,
+      bool from_origin) {
+    const V3 u = unit3(point_G - origin);
+    V3 a, b;
+    if (clearing) {
+      float l = norm3(point_G - origin);
+      l = std::min(std::max(l - trunc, 0.0f), max_ray);
+      b = origin + u * l;
+      a = carving ? origin : b;
+    } else {
+      b = point_G + u * trunc;
+      a = carving ? origin : (point_G - u * trunc);
+    }
+    const V3 as = a * inv, bs = b * inv;
+    if (from_origin) {
+      setup(as, bs);
+    } else {
+      setup(bs, as);
+    }
+  }
+
+  void setup(V3 s, V3 e) {
+    if (std::isnan(s.x) || std::isnan(s.y) || std::isnan(s.z) || std::isnan(e.x) || std::isnan(e.y) ||
+        std::isnan(e.z)) {
+      // the reference leaves current_step_ uninitialised here (integrator_utils.cc:129-134);
+      // the restatement defines the ray as empty.
+      dead = true;
+      return;
+    }
+    cur = gridIndexScaled(s);
+    const L3 end = gridIndexScaled(e);
+    len = static_cast<unsigned int>(std::abs(end.x - cur.x) + std::abs(end.y - cur.y) +
+                                    std::abs(end.z - cur.z));
+    const float r[3] = {e.x - s.x, e.y - s.y, e.z - s.z};
+    const float sh[3] = {s.x - static_cast<float>(cur.x), s.y - static_cast<float>(cur.y),
+                         s.z - static_cast<float>(cur.z)};
+    for (int k = 0; k < 3; ++k) {
+      sgn[k] = signumf(r[k]);
+      const int corrected = std::max(0, sgn[k]);
+      const float to_boundary = static_cast<float>(corrected) - sh[k];
+      // the "std::abs(r) < 0.0 ? 2.0 :" guards in the reference are dead code
+      tnext[k] = to_boundary / r[k];
+      tstep[k] = static_cast<float>(sgn[k]) / r[k];
+    }
+  }
+
+  bool next(L3* out) {
+    if (dead) return false;
+    if (step++ > len) return false;
+    *out = cur;
+    int k = 0;  // first minimum, strict < (Eigen minCoeff visitor)
+    float m = tnext[0];
+    if (tnext[1] < m) {
+      m = tnext[1];
+      k = 1;
+    }
+    if (tnext[2] < m) {
+      k = 2;
+    }
+    (k == 0 ? cur.x : (k == 1 ? cur.y : cur.z)) += sgn[k];
+    tnext[k] += tstep[k];
+    return true;
+  }
+};
+
+// ApproxHashSet<20, 10000, GlobalIndex, LongIndexHash> (utils/approx_hash_array.h:75-179)
+struct ApproxSet {
+  static constexpr size_t kBits = 20, kResetThreshold = 10000;
+  size_t offset = 0;
+  std::vector<size_t> slots;
+  ApproxSet() : slots((size_t(1) << kBits) + kResetThreshold, 0) { slots[0] = std::numeric_limits<size_t>::max(); }
+  bool replaceHash(const L3& idx) {
+    const size_t h = HashL3()(idx);
+    size_t& s = slots[(h & ((size_t(1) << kBits) - 1)) + offset];
+    if (s == h) return false;
+    s = h;
+    return true;
+  }
+  void reset() {
+    if (++offset >= kResetThreshold) {
+      std::fill(slots.begin(), slots.end(), 0);
+      offset = 0;
+      slots[0] = std::numeric_limits<size_t>::max();
+    }
+  }
+};
+
+// utils/bucket_queue.h:18-100
+struct BucketQ {
+  int nb = 0;
+  double maxv = 0;
+  std::vector<std::queue<L3>> b;
+  int last = 0;
+  size_t count = 0;
+  void configure(int n, double m) {
+    maxv = m;
+    nb = n;
+    b.clear();
+    b.resize(n);
+    count = 0;
+  }
+  void push(const L3& k, double v) {
+    if (v > maxv) v = maxv;
+    int bi = static_cast<int>(std::floor(std::abs(v) / maxv * (nb - 1)));
+    if (bi >= nb) bi = nb - 1;
+    if (bi < last) last = bi;
+    b[bi].push(k);
+    ++count;
+  }
+  bool empty() const { return count == 0; }
+  L3 front() {
+    while (b[last].empty() && last < nb) ++last;
+    return b[last].front();
+  }
+  void pop() {
+    if (empty()) return;
+    while (b[last].empty() && last < nb) ++last;
+    if (last < nb) {
+      b[last].pop();
+      --count;
+    }
+  }
+  void clear() {
+    b.clear();
+    b.resize(nb);
+    last = 0;
+    count = 0;
+  }
+};
+
+// src/utils/neighbor_tools.cc:8-30: 6 faces, 12 edges, 8 corners, in this order
+const int kOff[26][3] = {{-1, 0, 0},  {1, 0, 0},   {0, -1, 0},  {0, 1, 0},  {0, 0, -1},  {0, 0, 1},
+                         {-1, -1, 0}, {-1, 1, 0},  {1, -1, 0},  {1, 1, 0},  {0, -1, -1}, {0, -1, 1},
+                         {0, 1, -1},  {0, 1, 1},   {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1},  {1, 0, 1},
+                         {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1},
+                         {1, 1, -1},  {1, 1, 1}};
+inline float nbrDist(int i) {
+  static const float s2 = std::sqrt(2), s3 = std::sqrt(3);  // float(sqrt(double))
+  return i < 6 ? 1.0f : (i < 18 ? s2 : s3);
+}
+
+int64_t g_fast_reset_counter = 0;  // the reference's function-static (tsdf_integrator.cc:564)
+
+// ------------------------------------------------------------------------- the map
+struct Map {
+  vbo_tsdf_config cfg;
+  float voxel_size, voxel_size_inv, block_size, vps_inv;
+  int vps;
+  BlockMap<TsdfVox> tsdf, temp;
+  BlockMap<EsdfVox> esdf;
+  ApproxSet start_set, observed_set;
+  // esdf state (integrator/esdf_integrator.h:156-178)
+  bool has_esdf = false;
+  vbo_esdf_config ecfg;
+  BucketQ open;
+  std::queue<L3> raise;
+  std::unordered_set<I3, HashI3> updated_blocks;
+  // bookkeeping
+  double last_seconds = 0;
+  uint64_t counters[8] = {0};
+  std::unordered_map<I3, std::vector<uint64_t>, HashI3> touched;  // per-scan bitmaps
+
+  Map(const vbo_tsdf_config& c, float vs, int n) : cfg(c), voxel_size(vs), vps(n) {
+    // Layer ctor (core/layer.h:36-47) and TsdfIntegratorBase::setLayer (tsdf_integrator.cc:68-80)
+    voxel_size_inv = static_cast<float>(1.0 / voxel_size);
+    block_size = voxel_size * vps;
+    vps_inv = static_cast<float>(1.0 / static_cast<size_t>(vps));
+    if (cfg.integrator_threads == 0) cfg.integrator_threads = 1;
+    if (cfg.allow_clear && !cfg.voxel_carving_enabled) cfg.allow_clear = 0;  // cc:61-64
+  }
+
+  // tsdf_integrator.h:112-129
+  bool pointValid(V3 p, bool freespace, bool* clearing) const {
+    const float r = norm3(p);
+    if (r < cfg.min_ray_length_m) return false;
+    if (r > cfg.max_ray_length_m) {
+      if (cfg.allow_clear || freespace) {
+        *clearing = true;
+        return true;
+      }
+      return false;
+    }
+    *clearing = freespace;
+    return true;
+  }
+  // tsdf_integrator.cc:231-240
+  float pointWeight(V3 p) const {
+    if (cfg.use_const_weight) return 1.0f;
+    const float z = std::abs(p.z);
+    return z > kEps ? 1.0f / (z * z) : 0.0f;
+  }
+
+  // tsdf_integrator.cc:91-134: layer lookup, else the temporary block map; sets all updated bits
+  TsdfVox* voxelFor(const L3& g) {
+    const I3 bi = blockOf(g, vps_inv);
+    std::shared_ptr<Blk<TsdfVox>> blk;
+    auto it = tsdf.find(bi);
+    if (it != tsdf.end()) {
+      blk = it->second;
+    } else {
+      auto jt = temp.find(bi);
+      if (jt != temp.end()) {
+        blk = jt->second;
+      } else {
+        blk = temp.emplace(bi, std::make_shared<Blk<TsdfVox>>(vps)).first->second;
+        ++counters[5];
+      }
+    }
+    blk->updated = 7;
+    const size_t lin = localLinear(g, vps);
+    std::vector<uint64_t>& bits = touched[bi];
+    if (bits.empty()) bits.assign((static_cast<size_t>(vps) * vps * vps + 63) / 64, 0);
+    bits[lin >> 6] |= uint64_t(1) << (lin & 63);
+    return &blk->vox[lin];
+  }
+  // tsdf_integrator.cc:137-147
+  void commitTemp() {
+    for (const auto& kv : temp) tsdf.insert(kv);
+    temp.clear();
+  }
+
+  // tsdf_integrator.cc:150-209 (+ computeDistance :216-228)
+  void updateVoxel(V3 origin, V3 point_G, const L3& g, Rgba color, float weight, TsdfVox* v) {
+    ++counters[2];
+    const V3 c = centerPoint(g, voxel_size);
+    const V3 vo = c - origin, po = point_G - origin;
+    const float dist_G = norm3(po);
+    const float dist_G_V = dot3(vo, po) / dist_G;
+    const float sdf = dist_G - dist_G_V;
+    const float T = cfg.default_truncation_distance;
+    float w = weight;
+    const float eps = voxel_size;
+    if (cfg.use_weight_dropoff && sdf < -eps) {
+      w = weight * (T + sdf) / (T - eps);
+      w = std::max(w, 0.0f);
+    }
+    if (cfg.use_sparsity_compensation_factor) {
+      if (std::abs(sdf) < T) w *= cfg.sparsity_compensation_factor;
+    }
+    const float new_w = v->weight + w;
+    if (new_w < kEps) return;
+    const float new_sdf = (sdf * w + v->distance * v->weight) / new_w;
+    if (std::abs(sdf) < T) v->color = blend(v->color, v->weight, color, w);
+    v->distance = (new_sdf > 0.0) ? std::min(T, new_sdf) : std::max(-T, new_sdf);
+    v->weight = std::min(cfg.max_weight, new_w);
+  }
+
+  // integrator_utils.cc:17-67: the order in which one thread hands out point indices
+  std::vector<size_t> pointOrder(const float* xyz, size_t n) const {
+    std::vector<size_t> order(n);
+    if (cfg.integration_order_mode == 1) {
+      std::vector<std::pair<size_t, double>> v;
+      v.reserve(n);
+      for (size_t i = 0; i < n; ++i) {
+        v.emplace_back(i, sqnorm3(V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}));
+      }
+      std::sort(v.begin(), v.end(),
+                [](const std::pair<size_t, double>& a, const std::pair<size_t, double>& b) {
+                  return a.second < b.second;
+                });
+      for (size_t i = 0; i < n; ++i) order[i] = v[i].first;
+    } else {
+      const size_t groups = n / 1024;
+      for (size_t s = 0; s < n; ++s) {
+        order[s] = (groups * 1024 <= s) ? s : (s % groups) * 1024 + s / groups;
+      }
+    }
+    return order;
+  }
+
+  // SimpleTsdfIntegrator::integrateFunction, tsdf_integrator.cc:269-305
+  void integrateSimple(const Pose& T, const float* xyz, const uint8_t* rgba, size_t n, bool freespace) {
+    const V3 origin = T.t;
+    for (size_t idx : pointOrder(xyz, n)) {
+      const V3 p{xyz[3 * idx], xyz[3 * idx + 1], xyz[3 * idx + 2]};
+      bool clearing;
+      if (!pointValid(p, freespace, &clearing)) continue;
+      ++counters[6];
+      ++counters[clearing ? 1 : 0];
+      const V3 pg = T.apply(p);
+      const Rgba col{rgba[4 * idx], rgba[4 * idx + 1], rgba[4 * idx + 2], rgba[4 * idx + 3]};
+      Dda dda(origin, pg, clearing, cfg.voxel_carving_enabled, cfg.max_ray_length_m, voxel_size_inv,
+              cfg.default_truncation_distance, true);
+      L3 g;
+      while (dda.next(&g)) {
+        TsdfVox* v = voxelFor(g);
+        updateVoxel(origin, pg, g, col, pointWeight(p), v);
+      }
+    }
+    commitTemp();
+  }
+
+  // MergedTsdfIntegrator, tsdf_integrator.cc:307-486
+  typedef std::unordered_map<L3, std::vector<size_t>, HashL3> BundleMap;
+
+  void castBundle(const Pose& T, const float* xyz, const uint8_t* rgba, bool clearing, const L3& key,
+                  const std::vector<size_t>& members, const BundleMap& voxel_map) {
+    if (members.empty()) return;
+    const V3 origin = T.t;
+    Rgba mcol{0, 0, 0, 0};
+    V3 mp{0, 0, 0};
+    float mw = 0.0f;
+    for (size_t idx : members) {  // cc:387-405: running weighted mean in the camera frame
+      const V3 p{xyz[3 * idx], xyz[3 * idx + 1], xyz[3 * idx + 2]};
+      const float w = pointWeight(p);
+      if (w < kEps) continue;
+      mp = (mp * mw + p * w) / (mw + w);
+      mcol = blend(mcol, mw, Rgba{rgba[4 * idx], rgba[4 * idx + 1], rgba[4 * idx + 2], rgba[4 * idx + 3]}, w);
+      mw += w;
+      if (clearing) break;
+    }
+    const V3 pg = T.apply(mp);
+    ++counters[clearing ? 1 : 0];
+    Dda dda(origin, pg, clearing, cfg.voxel_carving_enabled, cfg.max_ray_length_m, voxel_size_inv,
+            cfg.default_truncation_distance, true);
+    L3 g;
+    while (dda.next(&g)) {
+      if (cfg.enable_anti_grazing) {  // cc:415-422
+        if ((clearing || g != key) && voxel_map.find(g) != voxel_map.end()) continue;
+      }
+      TsdfVox* v = voxelFor(g);
+      updateVoxel(origin, pg, g, mcol, mw, v);
+    }
+  }
+
+  void integrateMerged(const Pose& T, const float* xyz, const uint8_t* rgba, size_t n, bool freespace,
+                       int bundle_order) {
+    BundleMap voxel_map, clear_map;
+    for (size_t idx : pointOrder(xyz, n)) {  // bundleRays, cc:340-371
+      const V3 p{xyz[3 * idx], xyz[3 * idx + 1], xyz[3 * idx + 2]};
+      bool clearing;
+      if (!pointValid(p, freespace, &clearing)) continue;
+      ++counters[6];
+      const L3 key = gridIndex(T.apply(p), voxel_size_inv);
+      (clearing ? clear_map : voxel_map)[key].push_back(idx);
+    }
+    for (int pass = 0; pass < 2; ++pass) {  // integrateRays(false) then (true), cc:323-335
+      const BundleMap& m = pass ? clear_map : voxel_map;
+      if (bundle_order == VBO_ORDER_CANONICAL) {
+        std::vector<const BundleMap::value_type*> v;
+        v.reserve(m.size());
+        for (const auto& kv : m) v.push_back(&kv);
+        std::sort(v.begin(), v.end(), [](const BundleMap::value_type* a, const BundleMap::value_type* b) {
+          if (a->first.z != b->first.z) return a->first.z < b->first.z;
+          if (a->first.y != b->first.y) return a->first.y < b->first.y;
+          return a->first.x < b->first.x;
+        });
+        for (const auto* kv : v) castBundle(T, xyz, rgba, pass == 1, kv->first, kv->second, voxel_map);
+      } else {
+        // one thread visits every map entry in iteration order (cc:434-457 with threads == 1)
+        for (const auto& kv : m) castBundle(T, xyz, rgba, pass == 1, kv.first, kv.second, voxel_map);
+      }
+      commitTemp();  // cc:482-485
+    }
+  }
+
+  // FastTsdfIntegrator, tsdf_integrator.cc:488-590
+  void integrateFast(const Pose& T, const float* xyz, const uint8_t* rgba, size_t n, bool freespace) {
+    const auto start = std::chrono::steady_clock::now();
+    if ((++g_fast_reset_counter) >= cfg.clear_checks_every_n_frames) {
+      g_fast_reset_counter = 0;
+      start_set.reset();
+      observed_set.reset();
+    }
+    const V3 origin = T.t;
+    for (size_t idx : pointOrder(xyz, n)) {
+      if (!(std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - start)
+                .count() < cfg.max_integration_time_s * 1000000)) {
+        break;
+      }
+      const V3 p{xyz[3 * idx], xyz[3 * idx + 1], xyz[3 * idx + 2]};
+      bool clearing;
+      if (!pointValid(p, freespace, &clearing)) continue;
+      ++counters[6];
+      const V3 pg = T.apply(p);
+      L3 g = gridIndex(pg, cfg.start_voxel_subsampling_factor * voxel_size_inv);
+      if (!start_set.replaceHash(g)) continue;
+      ++counters[clearing ? 1 : 0];
+      const Rgba col{rgba[4 * idx], rgba[4 * idx + 1], rgba[4 * idx + 2], rgba[4 * idx + 3]};
+      Dda dda(origin, pg, clearing, cfg.voxel_carving_enabled, cfg.max_ray_length_m, voxel_size_inv,
+              cfg.default_truncation_distance, false);
+      int64_t collisions = 0;
+      while (dda.next(&g)) {
+        if (!observed_set.replaceHash(g)) {
+          ++collisions;
+        } else {
+          collisions = 0;
+        }
+        if (collisions > cfg.max_consecutive_ray_collisions) break;
+        TsdfVox* v = voxelFor(g);
+        updateVoxel(origin, pg, g, col, pointWeight(p), v);
+      }
+    }
+    commitTemp();
+  }
+
+  // --------------------------------------------------------------------------- ESDF
+  EsdfVox* esdfVoxel(const L3& g) {  // Layer::getVoxelPtrByGlobalIndex, core/layer.h:228-239
+    auto it = esdf.find(blockOf(g, vps_inv));
+    if (it == esdf.end()) return nullptr;
+    return &it->second->vox[localLinear(g, vps)];
+  }
+  std::shared_ptr<Blk<EsdfVox>> esdfAllocate(const I3& bi) {  // core/layer.h:103-111
+    auto it = esdf.find(bi);
+    if (it != esdf.end()) return it->second;
+    return esdf.emplace(bi, std::make_shared<Blk<EsdfVox>>(vps)).first->second;
+  }
+  bool isFixed(float d) const { return std::abs(d) < ecfg.min_distance_m; }  // esdf_integrator.h:131-133
+
+  // esdf_integrator.cc:498-530 (note: neighbour distance in VOXELS, cc:508)
+  bool updateFromNeighbors(const L3& g) {
+    EsdfVox* v = esdfVoxel(g);
+    for (int i = 0; i < 26; ++i) {
+      const L3 ng{g.x + kOff[i][0], g.y + kOff[i][1], g.z + kOff[i][2]};
+      EsdfVox* nv = esdfVoxel(ng);
+      if (nv == nullptr) continue;
+      if (!nv->observed || nv->distance >= ecfg.max_distance_m || nv->distance <= -ecfg.max_distance_m) continue;
+      if (signumf(nv->distance) == signumf(v->distance)) {
+        if (std::abs(nv->distance) < std::abs(v->distance)) {
+          v->distance = nv->distance + signumf(v->distance) * nbrDist(i);
+          v->parent[0] = -kOff[i][0];
+          v->parent[1] = -kOff[i][1];
+          v->parent[2] = -kOff[i][2];
+          return true;
+        }
+      }
+    }
+    return false;
+  }
+
+  // esdf_integrator.cc:124-302
+  void esdfFromBlocks(const std::vector<I3>& blocks, bool incremental) {
+    const float dflt = ecfg.default_distance_m, md = ecfg.min_diff_m;
+    for (const I3& bi : blocks) {
+      auto tb = tsdf.find(bi);
+      if (tb == tsdf.end()) continue;
+      std::shared_ptr<Blk<EsdfVox>> eb = esdfAllocate(bi);
+      eb->updated = 1;  // set_updated(true): bitset(1ull) => only kMap (cc:147)
+      const size_t nv = tb->second->vox.size();
+      for (size_t lin = 0; lin < nv; ++lin) {
+        const TsdfVox& tv = tb->second->vox[lin];
+        if (tv.weight < ecfg.min_weight) {
+          if (!incremental && ecfg.add_occupied_crust) {
+            EsdfVox& ev = eb->vox[lin];
+            ev.distance = -dflt;
+            ev.observed = 1;
+            ev.hallucinated = 1;
+            ev.fixed = 0;
+          }
+          continue;
+        }
+        EsdfVox& ev = eb->vox[lin];
+        const int z = static_cast<int>(lin) / (vps * vps), rem = static_cast<int>(lin) % (vps * vps);
+        const L3 g{int64_t(bi.x) * vps + rem % vps, int64_t(bi.y) * vps + rem / vps, int64_t(bi.z) * vps + z};
+        const bool tfixed = isFixed(tv.distance);
+        if (!ev.observed || ev.hallucinated) {
+          if (ev.hallucinated) raise.push(g);
+          if (tfixed) {
+            ev.distance = tv.distance;
+            ev.fixed = 1;
+            ev.in_queue = 1;
+            open.push(g, ev.distance);
+          } else {
+            ev.distance = signumf(tv.distance) * dflt;
+            ev.fixed = 0;
+            if (incremental) {
+              if (updateFromNeighbors(g)) {
+                ev.in_queue = 1;
+                open.push(g, ev.distance);
+              }
+            }
+          }
+          ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+        } else {
+          if (tfixed || ev.fixed) {
+            if (!tfixed) {
+              ev.distance = signumf(tv.distance) * dflt;
+              ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+              ev.fixed = 0;
+              raise.push(g);
+              ev.in_queue = 1;
+              open.push(g, ev.distance);
+            } else if ((ev.distance > 0.0f && tv.distance + md < ev.distance) ||
+                       (ev.distance <= 0.0f && tv.distance - md > ev.distance)) {
+              ev.fixed = tfixed;
+              ev.distance = ev.fixed ? tv.distance : signumf(tv.distance) * dflt;
+              ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+              ev.in_queue = 1;
+              open.push(g, ev.distance);
+            } else if ((ev.distance > 0.0f && tv.distance - md > ev.distance) ||
+                       (ev.distance <= 0.0f && tv.distance + md < ev.distance)) {
+              ev.fixed = tfixed;
+              ev.distance = ev.fixed ? tv.distance : signumf(tv.distance) * dflt;
+              ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+              raise.push(g);
+              ev.in_queue = 1;
+              open.push(g, ev.distance);
+            }
+          } else if (signumf(tv.distance) != signumf(ev.distance)) {
+            if (tv.distance < ev.distance) {
+              ev.distance = signumf(tv.distance) * dflt;
+              ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+              ev.in_queue = 1;
+              open.push(g, ev.distance);
+            } else {
+              ev.distance = signumf(tv.distance) * dflt;
+              ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+              raise.push(g);
+            }
+          }
+        }
+        ev.observed = 1;
+        ev.hallucinated = 0;
+      }
+    }
+    processRaise();
+    processOpen();
+  }
+
+  // esdf_integrator.cc:305-369
+  void processRaise() {
+    while (!raise.empty()) {
+      const L3 g = raise.front();
+      raise.pop();
+      for (int i = 0; i < 26; ++i) {
+        const L3 ng{g.x + kOff[i][0], g.y + kOff[i][1], g.z + kOff[i][2]};
+        EsdfVox* nv = esdfVoxel(ng);
+        if (nv == nullptr) continue;
+        if (!nv->observed || nv->fixed) continue;
+        bool is_parent = nv->parent[0] == -kOff[i][0] && nv->parent[1] == -kOff[i][1] &&
+                         nv->parent[2] == -kOff[i][2];
+        if (ecfg.full_euclidean_distance) {
+          V3 pd = unit3(V3{float(nv->parent[0]), float(nv->parent[1]), float(nv->parent[2])});
+          is_parent = static_cast<int>(std::round(pd.x)) == -kOff[i][0] &&
+                      static_cast<int>(std::round(pd.y)) == -kOff[i][1] &&
+                      static_cast<int>(std::round(pd.z)) == -kOff[i][2];
+        }
+        if (is_parent) {
+          nv->distance = signumf(nv->distance) * ecfg.default_distance_m;
+          nv->parent[0] = nv->parent[1] = nv->parent[2] = 0;
+          raise.push(ng);
+        } else if (!nv->in_queue) {
+          open.push(ng, nv->distance);
+          nv->in_queue = 1;
+        }
+      }
+    }
+  }
+
+  // esdf_integrator.cc:371-496
+  void processOpen() {
+    const float md = ecfg.min_diff_m;
+    while (!open.empty()) {
+      const L3 g = open.front();
+      open.pop();
+      EsdfVox* v = esdfVoxel(g);
+      v->in_queue = 0;
+      if (!v->observed || v->distance >= ecfg.max_distance_m || v->distance <= -ecfg.max_distance_m) continue;
+      for (int i = 0; i < 26; ++i) {
+        const L3 ng{g.x + kOff[i][0], g.y + kOff[i][1], g.z + kOff[i][2]};
+        float dist = nbrDist(i) * voxel_size;
+        EsdfVox* nv = esdfVoxel(ng);
+        if (nv == nullptr) continue;
+        if (!nv->observed || nv->fixed) continue;
+        int np[3] = {-kOff[i][0], -kOff[i][1], -kOff[i][2]};
+        if (ecfg.full_euclidean_distance) {
+          np[0] = v->parent[0] - kOff[i][0];
+          np[1] = v->parent[1] - kOff[i][1];
+          np[2] = v->parent[2] - kOff[i][2];
+          dist = voxel_size * (norm3(V3{float(np[0]), float(np[1]), float(np[2])}) -
+                               norm3(V3{float(v->parent[0]), float(v->parent[1]), float(v->parent[2])}));
+          if (dist < 0.0) continue;
+        }
+        bool changed = false;
+        if (v->distance > 0 && nv->distance > 0) {
+          if (v->distance + dist + md < nv->distance) {
+            nv->distance = v->distance + dist;
+            changed = true;
+          }
+        } else if (v->distance <= 0 && nv->distance <= 0) {
+          if (v->distance - dist - md > nv->distance) {
+            nv->distance = v->distance - dist;
+            changed = true;
+          }
+        } else {
+          const float pot = v->distance - signumf(v->distance) * dist;
+          if (std::abs(pot - nv->distance) > dist) {
+            if (signumf(pot) == nv->distance) {  // sic (cc:464): a sign compared with a distance
+              nv->distance = pot;
+            } else {
+              nv->distance = signumf(nv->distance) * dist;
+            }
+            changed = true;
+          }
+        }
+        if (changed) {
+          nv->parent[0] = np[0];
+          nv->parent[1] = np[1];
+          nv->parent[2] = np[2];
+          if (ecfg.multi_queue || !nv->in_queue) {
+            open.push(ng, nv->distance);
+            nv->in_queue = 1;
+          }
+        }
+      }
+    }
+  }
+
+  // esdf_integrator.cc:94-122
+  void esdfUpdate(bool batch, bool clear_flag) {
+    std::vector<I3> blocks;
+    if (batch) {
+      esdf.clear();
+      for (const auto& kv : tsdf) blocks.push_back(kv.first);
+    } else {
+      for (const auto& kv : tsdf) {
+        if (kv.second->updated & 4) blocks.push_back(kv.first);
+      }
+    }
+    blocks.insert(blocks.end(), updated_blocks.begin(), updated_blocks.end());
+    updated_blocks.clear();
+    esdfFromBlocks(blocks, !batch);
+    if (!batch && clear_flag) {
+      for (const I3& bi : blocks) {
+        auto it = tsdf.find(bi);
+        if (it != tsdf.end()) it->second->updated &= static_cast<uint8_t>(~4);
+      }
+    }
+  }
+
+  // utils/planning_utils_inl.h:15-62 + esdf_integrator.cc:25-92
+  typedef std::unordered_map<I3, std::vector<I3>, HashI3> HierMap;
+  void sphereAround(V3 center, float radius, HierMap* out) {
+    const float inv = static_cast<float>(1.0 / voxel_size);
+    const L3 c = gridIndex(center, inv);
+    const float rv = radius / voxel_size;
+    for (float x = -rv; x <= rv; x++) {
+      for (float y = -rv; y <= rv; y++) {
+        for (float z = -rv; z <= rv; z++) {
+          if (norm3(V3{x, y, z}) <= rv) {
+            const L3 g{static_cast<int64_t>(std::floor(x)) + c.x, static_cast<int64_t>(std::floor(y)) + c.y,
+                       static_cast<int64_t>(std::floor(z)) + c.z};
+            const I3 bi = blockOf(g, static_cast<float>(1.0 / vps));
+            constexpr int64_t off = int64_t(1) << 31;
+            (*out)[bi].push_back(I3{static_cast<int>((g.x + off) & (vps - 1)), static_cast<int>((g.y + off) & (vps - 1)),
+                                    static_cast<int>((g.z + off) & (vps - 1))});
+          }
+        }
+      }
+    }
+    for (auto& kv : *out) esdfAllocate(kv.first);
+  }
+  void addRobotPosition(V3 p) {
+    HierMap inner;
+    sphereAround(p, ecfg.clear_sphere_radius, &inner);
+    for (auto& kv : inner) {
+      std::shared_ptr<Blk<EsdfVox>> b = esdf.find(kv.first)->second;
+      for (const I3& vi : kv.second) {
+        EsdfVox& ev = b->vox[vi.x + vps * (vi.y + vi.z * vps)];
+        if (!ev.observed || ev.hallucinated) {
+          if (ev.hallucinated) {
+            raise.push(L3{int64_t(kv.first.x) * vps + vi.x, int64_t(kv.first.y) * vps + vi.y,
+                          int64_t(kv.first.z) * vps + vi.z});
+          }
+          ev.distance = ecfg.default_distance_m;
+          ev.observed = 1;
+          ev.hallucinated = 1;
+          ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+          updated_blocks.insert(kv.first);
+        }
+      }
+    }
+    HierMap outer;
+    sphereAround(p, ecfg.occupied_sphere_radius, &outer);
+    for (auto& kv : outer) {
+      std::shared_ptr<Blk<EsdfVox>> b = esdf.find(kv.first)->second;
+      for (const I3& vi : kv.second) {
+        EsdfVox& ev = b->vox[vi.x + vps * (vi.y + vi.z * vps)];
+        if (!ev.observed) {
+          ev.distance = -ecfg.default_distance_m;
+          ev.observed = 1;
+          ev.hallucinated = 1;
+          ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+          updated_blocks.insert(kv.first);
+        } else if (!ev.in_queue) {
+          open.push(L3{int64_t(kv.first.x) * vps + vi.x, int64_t(kv.first.y) * vps + vi.y,
+                       int64_t(kv.first.z) * vps + vi.z},
+                    ev.distance);
+        }
+      }
+    }
+  }
+};
+
+template <typename V>
+void sortedKeys(const BlockMap<V>& m, int32_t* out) {
+  std::vector<I3> k;
+  k.reserve(m.size());
+  for (const auto& kv : m) k.push_back(kv.first);
+  std::sort(k.begin(), k.end(), [](const I3& a, const I3& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  });
+  for (size_t i = 0; i < k.size(); ++i) {
+    out[3 * i] = k[i].x;
+    out[3 * i + 1] = k[i].y;
+    out[3 * i + 2] = k[i].z;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vbo_impl_name(void) { return "port"; }
+
+void* vbo_create(const vbo_tsdf_config* c, float voxel_size, int voxels_per_side) {
+  return new Map(*c, voxel_size, voxels_per_side);
+}
+void vbo_destroy(void* h) { delete static_cast<Map*>(h); }
+
+int vbo_integrate(void* hv, int kind, const float q[4], const float t[3], const float* xyz,
+                  const uint8_t* rgba, uint64_t n, int freespace, int bundle_order) {
+  Map* m = static_cast<Map*>(hv);
+  if (kind < 1 || kind > 3) return 2;
+  const Pose T{q[0], q[1], q[2], q[3], V3{t[0], t[1], t[2]}};
+  std::memset(m->counters, 0, sizeof(m->counters));
+  m->touched.clear();
+  const auto t0 = std::chrono::steady_clock::now();
+  if (kind == VBO_SIMPLE) {
+    m->integrateSimple(T, xyz, rgba, n, freespace != 0);
+  } else if (kind == VBO_MERGED) {
+    m->integrateMerged(T, xyz, rgba, n, freespace != 0, bundle_order);
+  } else {
+    m->integrateFast(T, xyz, rgba, n, freespace != 0);
+  }
+  m->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  uint64_t u = 0;
+  for (const auto& kv : m->touched) {
+    for (uint64_t w : kv.second) u += static_cast<uint64_t>(__builtin_popcountll(w));
+  }
+  m->counters[3] = u;
+  m->counters[4] = m->touched.size();
+  return 0;
+}
+
+double vbo_last_seconds(void* h) { return static_cast<Map*>(h)->last_seconds; }
+void vbo_last_counters(void* h, uint64_t out[8]) {
+  std::memcpy(out, static_cast<Map*>(h)->counters, 8 * sizeof(uint64_t));
+}
+
+uint64_t vbo_num_blocks(void* hv, int layer) {
+  Map* m = static_cast<Map*>(hv);
+  return layer == VBO_LAYER_TSDF ? m->tsdf.size() : m->esdf.size();
+}
+void vbo_block_indices(void* hv, int layer, int32_t* out) {
+  Map* m = static_cast<Map*>(hv);
+  if (layer == VBO_LAYER_TSDF) {
+    sortedKeys(m->tsdf, out);
+  } else {
+    sortedKeys(m->esdf, out);
+  }
+}
+int vbo_get_block(void* hv, int layer, const int32_t idx[3], void* voxels, uint8_t* updated_bits) {
+  Map* m = static_cast<Map*>(hv);
+  const I3 bi{idx[0], idx[1], idx[2]};
+  if (layer == VBO_LAYER_TSDF) {
+    auto it = m->tsdf.find(bi);
+    if (it == m->tsdf.end()) return 1;
+    std::memcpy(voxels, it->second->vox.data(), it->second->vox.size() * sizeof(TsdfVox));
+    if (updated_bits) *updated_bits = it->second->updated;
+  } else {
+    auto it = m->esdf.find(bi);
+    if (it == m->esdf.end()) return 1;
+    std::memcpy(voxels, it->second->vox.data(), it->second->vox.size() * sizeof(EsdfVox));
+    if (updated_bits) *updated_bits = it->second->updated;
+  }
+  return 0;
+}
+
+int vbo_esdf_create(void* hv, const vbo_esdf_config* c) {
+  Map* m = static_cast<Map*>(hv);
+  m->ecfg = *c;
+  m->has_esdf = true;
+  m->open.configure(c->num_buckets, c->max_distance_m);  // esdf_integrator.cc:21
+  m->raise = std::queue<L3>();
+  m->updated_blocks.clear();
+  return 0;
+}
+int vbo_esdf_update(void* hv, int batch, int clear_updated_flag) {
+  Map* m = static_cast<Map*>(hv);
+  if (!m->has_esdf) return 2;
+  const auto t0 = std::chrono::steady_clock::now();
+  m->esdfUpdate(batch != 0, clear_updated_flag != 0);
+  m->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+int vbo_esdf_add_robot_position(void* hv, const float p[3]) {
+  Map* m = static_cast<Map*>(hv);
+  if (!m->has_esdf) return 2;
+  m->addRobotPosition(V3{p[0], p[1], p[2]});
+  return 0;
+}
+
+}  // extern "C"
