@@ -1,0 +1,185 @@
+/* voxblox_b200 -- C-ABI of the B200-native TSDF / ESDF integration engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of ethz-asl/voxblox that this
+ * repository accelerates.  The reference has no FFI today;
+ * its "operator API" is the C++ virtual
+ *     TsdfIntegratorBase::integratePointCloud(T_G_C, points_C, colors, freespace)
+ *         voxblox/include/voxblox/integrator/tsdf_integrator.h:100-103
+ * and
+ *     EsdfIntegrator::updateFromTsdfLayer(clear_updated_flag) / ...Batch()
+ *         voxblox/include/voxblox/integrator/esdf_integrator.h:101-106
+ * operating on Layer<TsdfVoxel> / Layer<EsdfVoxel> (core/layer.h:24-296).
+ * Each entry point below names the reference interface it replaces; the voxblox-
+ * side adapter that binds them (a TsdfIntegratorBase subclass registered in
+ * TsdfIntegratorFactory::create) is include/voxblox_b200/gpu_integrators.h and is
+ * described in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success
+ * or a VBX_E_* code, with a message retrievable through vbx_last_error() (the
+ * reference aborts through glog CHECK/LOG(FATAL); the adapter maps non-zero to
+ * LOG(FATAL) to keep that behaviour).  A context is NOT thread safe, exactly like
+ * integratePointCloud (tsdf_integrator.h:95); calls are synchronous at return
+ * unless stated otherwise.  Voxel payloads use the reference's in-memory structs:
+ *   TsdfVoxel 12 B = f32 distance, f32 weight, u8 r,g,b,a        (core/voxel.h:12-16)
+ *   EsdfVoxel 20 B = f32 distance, u8 observed, hallucinated,
+ *                    in_queue, fixed, i32 parent[3]               (core/voxel.h:18-37)
+ * in linear order x + vps*(y + vps*z) (core/block_inl.h:12-27).
+ */
+#ifndef VOXBLOX_B200_H_
+#define VOXBLOX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VBX_API __attribute__((visibility("default")))
+#else
+#define VBX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBX_OK 0
+#define VBX_E_INVALID 1      /* bad argument / unknown integrator type (cc:11,22,41) */
+#define VBX_E_CUDA 2         /* CUDA runtime error                                    */
+#define VBX_E_CAPACITY 3     /* block pool / scratch capacity exceeded                */
+#define VBX_E_NOT_FOUND 4    /* block does not exist                                  */
+#define VBX_E_STATE 5        /* call order (e.g. ESDF update before vbx_esdf_create)  */
+
+/* TsdfIntegratorType, tsdf_integrator.h:30-41 */
+#define VBX_SIMPLE 1
+#define VBX_MERGED 2
+#define VBX_FAST 3
+
+#define VBX_LAYER_TSDF 0
+#define VBX_LAYER_ESDF 1
+
+/* Update::Status bits of Block::updated(), core/block.h:15-18 */
+#define VBX_UPDATED_MAP 1
+#define VBX_UPDATED_MESH 2
+#define VBX_UPDATED_ESDF 4
+
+typedef struct vbx_ctx vbx_ctx;
+
+/* POD mirror of TsdfIntegratorBase::Config, tsdf_integrator.h:56-89 (defaults there).
+ * integration_order_mode: 0 = "mixed", 1 = "sorted" (integrator_utils.cc:5-15).
+ * integrator_threads is accepted for API parity and ignored: the device applies
+ * every voxel's updates in one fixed order ("update order"). */
+typedef struct vbx_tsdf_config {
+  float default_truncation_distance;
+  float max_weight;
+  int32_t voxel_carving_enabled;
+  float min_ray_length_m;
+  float max_ray_length_m;
+  int32_t use_const_weight;
+  int32_t allow_clear;
+  int32_t use_weight_dropoff;
+  int32_t use_sparsity_compensation_factor;
+  float sparsity_compensation_factor;
+  int32_t integrator_threads;
+  int32_t integration_order_mode;
+  int32_t enable_anti_grazing;
+  float start_voxel_subsampling_factor;
+  int32_t max_consecutive_ray_collisions;
+  int32_t clear_checks_every_n_frames;
+  float max_integration_time_s;
+} vbx_tsdf_config;
+
+/* POD mirror of EsdfIntegrator::Config, esdf_integrator.h:29-78. */
+typedef struct vbx_esdf_config {
+  int32_t full_euclidean_distance;
+  float max_distance_m;
+  float min_distance_m;
+  float default_distance_m;
+  float min_diff_m;
+  float min_weight;
+  int32_t num_buckets;
+  int32_t multi_queue;
+  int32_t add_occupied_crust;
+  float clear_sphere_radius;
+  float occupied_sphere_radius;
+} vbx_esdf_config;
+
+/* Engine sizing (no reference counterpart: the CPU map grows with make_shared).
+ * Zero in any field selects the default in brackets. */
+typedef struct vbx_engine_options {
+  int32_t device;                 /* CUDA device ordinal [current]                    */
+  uint32_t max_blocks;            /* voxel-block pool capacity [32768 = 1.5 GiB TSDF] */
+  uint32_t max_points_per_scan;   /* [1 << 20]                                        */
+  uint64_t max_updates_per_pass;  /* ray-voxel update records per pass [1 << 26]      */
+  int32_t rank;                   /* this process' rank in the group [0]              */
+  int32_t world_size;             /* number of ray-range shards [1]                   */
+} vbx_engine_options;
+
+/* Layer<TsdfVoxel>(voxel_size, voxels_per_side) + TsdfIntegratorBase(config, layer)
+ * (core/layer.h:36-47, tsdf_integrator.cc:53-80). voxels_per_side must be a power
+ * of two <= 16 (the reference CHECKs the power of two, core/common.h:239). */
+VBX_API int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side,
+               const vbx_engine_options* opt, vbx_ctx** out);
+VBX_API void vbx_destroy(vbx_ctx* ctx);
+VBX_API const char* vbx_last_error(const vbx_ctx* ctx);
+VBX_API const char* vbx_version(void);
+
+/* TsdfIntegratorBase::getConfig (tsdf_integrator.h:106) */
+VBX_API int vbx_get_tsdf_config(const vbx_ctx* ctx, vbx_tsdf_config* out);
+
+/* {Simple,Merged,Fast}TsdfIntegrator::integratePointCloud
+ * (tsdf_integrator.cc:242-267, 307-338, 555-590).  kind = VBX_SIMPLE|MERGED|FAST,
+ * T_G_C = (q_wxyz, t), xyz = 3n floats points_C, rgba = 4n bytes, HOST memory.
+ * Copies the cloud to the device, integrates, and returns after the stream has
+ * drained (the reference's call is synchronous too). */
+VBX_API int vbx_tsdf_integrate(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
+                       const float* xyz, const uint8_t* rgba, uint64_t n, int freespace);
+/* Same, with xyz / rgba already resident in DEVICE memory (no copies). */
+VBX_API int vbx_tsdf_integrate_device(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
+                              const float* d_xyz, const uint8_t* d_rgba, uint64_t n,
+                              int freespace);
+
+/* Counters of the last integrate call (the reference logs some of them through
+ * VLOG(3), tsdf_integrator.cc:368-370):
+ * [0] normal rays/bundles cast  [1] clearing rays/bundles cast  [2] ray-voxel updates
+ * [3] distinct voxels touched   [4] distinct blocks touched     [5] blocks allocated
+ * [6] valid points              [7] kernels launched            [8..15] reserved */
+VBX_API int vbx_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
+/* Device time (ms, CUDA events on the context's stream) of the last integrate /
+ * ESDF update call, excluding host<->device copies of the cloud. */
+VBX_API int vbx_last_device_ms(const vbx_ctx* ctx, float* ms);
+
+/* Layer::getNumberOfAllocatedBlocks (core/layer.h:205) */
+VBX_API int vbx_num_blocks(vbx_ctx* ctx, int layer, uint64_t* n);
+/* Layer::getAllAllocatedBlocks / getAllUpdatedBlocks(bit) (core/layer.h:184-203).
+ * updated_mask = 0 lists every block, else only blocks with (updated & mask) != 0.
+ * idx3 receives up to cap (x,y,z) triples sorted ascending by (x,y,z); *n = count. */
+VBX_API int vbx_list_blocks(vbx_ctx* ctx, int layer, int updated_mask, int32_t* idx3, uint64_t cap,
+                    uint64_t* n);
+/* Block voxel payloads, device -> host (the lazy host mirror of SURVEY.md N1).
+ * voxels: m * vps^3 * sizeof(voxel) bytes; updated_bits: m bytes (may be NULL). */
+VBX_API int vbx_download_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m, void* voxels,
+                        uint8_t* updated_bits);
+/* Host -> device: Layer::insertBlock / allocateBlockPtrByIndex + voxel copy
+ * (core/layer.h:103-111,152-161); creates the block if needed. */
+VBX_API int vbx_upload_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m,
+                      const void* voxels, const uint8_t* updated_bits);
+/* Layer::removeBlock / removeAllBlocks (core/layer.h:163-164) */
+VBX_API int vbx_remove_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m);
+VBX_API int vbx_clear(vbx_ctx* ctx, int layer);
+/* block.updated().reset(bit) over a layer (esdf_integrator.cc:113-121) */
+VBX_API int vbx_clear_updated(vbx_ctx* ctx, int layer, int updated_mask);
+
+/* EsdfIntegrator(config, tsdf_layer, esdf_layer) (esdf_integrator.cc:7-22) */
+VBX_API int vbx_esdf_create(vbx_ctx* ctx, const vbx_esdf_config* cfg);
+/* batch = 0: updateFromTsdfLayer(clear_updated_flag)   (esdf_integrator.cc:104-122)
+ * batch = 1: updateFromTsdfLayerBatch()                (esdf_integrator.cc:94-102) */
+VBX_API int vbx_esdf_update(vbx_ctx* ctx, int batch, int clear_updated_flag);
+/* Counters of the last ESDF update: [0] blocks propagated [1] lower [2] raise [3] new
+ * [4] voxels raised [5] wavefront relaxations R [6] wavefront sweeps [7] kernels */
+VBX_API int vbx_esdf_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
+
+VBX_API int vbx_sync(vbx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXBLOX_B200_H_ */

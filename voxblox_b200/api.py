@@ -1,0 +1,443 @@
+"""Host-side mirror of the reference's operator interface for the TSDF / ESDF hot path.
+
+Same names, argument meaning and error behaviour as the reference's C++ API
+(voxblox/include/voxblox/integrator/tsdf_integrator.h:51-209,
+ voxblox/include/voxblox/integrator/esdf_integrator.h:25-178,
+ voxblox/include/voxblox/core/layer.h:24-296), bound to the C-ABI of
+include/voxblox_b200.h through ctypes.  There is NO CPU fallback: if
+libvoxblox_b200.so is missing or no CUDA device is present, constructing an
+integrator raises.  (The reference aborts through glog CHECK / LOG(FATAL); here the
+same conditions raise VoxbloxError with the C-ABI's message.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvoxblox_b200.so")
+
+# TsdfVoxel / EsdfVoxel exactly as the reference lays them out (core/voxel.h:12-37)
+TSDF_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4"), ("color", "u1", (4,))])
+ESDF_DTYPE = np.dtype([("distance", "<f4"), ("observed", "u1"), ("hallucinated", "u1"),
+                       ("in_queue", "u1"), ("fixed", "u1"), ("parent", "<i4", (3,))])
+assert TSDF_DTYPE.itemsize == 12 and ESDF_DTYPE.itemsize == 20
+
+LAYER_TSDF, LAYER_ESDF = 0, 1
+UPDATED_MAP, UPDATED_MESH, UPDATED_ESDF = 1, 2, 4  # Update::Status, core/block.h:15-18
+
+
+class TsdfIntegratorType:  # tsdf_integrator.h:30-41
+    kSimple, kMerged, kFast = 1, 2, 3
+
+
+kTsdfIntegratorTypeNames = ("simple", "merged", "fast")
+
+
+class VoxbloxError(RuntimeError):
+    pass
+
+
+class TsdfIntegratorConfig(C.Structure):
+    """TsdfIntegratorBase::Config (tsdf_integrator.h:56-89), same field names and defaults.
+
+    integration_order_mode accepts "mixed"/"sorted" or 0/1."""
+    _fields_ = [("default_truncation_distance", C.c_float), ("max_weight", C.c_float),
+                ("voxel_carving_enabled", C.c_int32), ("min_ray_length_m", C.c_float),
+                ("max_ray_length_m", C.c_float), ("use_const_weight", C.c_int32),
+                ("allow_clear", C.c_int32), ("use_weight_dropoff", C.c_int32),
+                ("use_sparsity_compensation_factor", C.c_int32),
+                ("sparsity_compensation_factor", C.c_float), ("integrator_threads", C.c_int32),
+                ("integration_order_mode", C.c_int32), ("enable_anti_grazing", C.c_int32),
+                ("start_voxel_subsampling_factor", C.c_float),
+                ("max_consecutive_ray_collisions", C.c_int32),
+                ("clear_checks_every_n_frames", C.c_int32), ("max_integration_time_s", C.c_float)]
+
+    def __init__(self, **kw):
+        d = dict(default_truncation_distance=0.1, max_weight=10000.0, voxel_carving_enabled=1,
+                 min_ray_length_m=0.1, max_ray_length_m=5.0, use_const_weight=0, allow_clear=1,
+                 use_weight_dropoff=1, use_sparsity_compensation_factor=0,
+                 sparsity_compensation_factor=1.0, integrator_threads=os.cpu_count() or 1,
+                 integration_order_mode=0, enable_anti_grazing=0,
+                 start_voxel_subsampling_factor=2.0, max_consecutive_ray_collisions=2,
+                 clear_checks_every_n_frames=1, max_integration_time_s=3.4028234663852886e38)
+        d.update(kw)
+        mode = d["integration_order_mode"]
+        if isinstance(mode, str):
+            if mode not in ("mixed", "sorted"):  # LOG(FATAL), integrator_utils.cc:12
+                raise VoxbloxError(f"Unknown integration order mode: '{mode}'!")
+            d["integration_order_mode"] = 0 if mode == "mixed" else 1
+        super().__init__(**d)
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class EsdfIntegratorConfig(C.Structure):
+    """EsdfIntegrator::Config (esdf_integrator.h:29-78)."""
+    _fields_ = [("full_euclidean_distance", C.c_int32), ("max_distance_m", C.c_float),
+                ("min_distance_m", C.c_float), ("default_distance_m", C.c_float),
+                ("min_diff_m", C.c_float), ("min_weight", C.c_float), ("num_buckets", C.c_int32),
+                ("multi_queue", C.c_int32), ("add_occupied_crust", C.c_int32),
+                ("clear_sphere_radius", C.c_float), ("occupied_sphere_radius", C.c_float)]
+
+    def __init__(self, **kw):
+        d = dict(full_euclidean_distance=0, max_distance_m=2.0, min_distance_m=0.2,
+                 default_distance_m=2.0, min_diff_m=0.001, min_weight=1e-6, num_buckets=20,
+                 multi_queue=0, add_occupied_crust=0, clear_sphere_radius=1.5,
+                 occupied_sphere_radius=5.0)
+        d.update(kw)
+        super().__init__(**d)
+
+
+class EngineOptions(C.Structure):
+    """vbx_engine_options: device-side sizing (no reference counterpart)."""
+    _fields_ = [("device", C.c_int32), ("max_blocks", C.c_uint32),
+                ("max_points_per_scan", C.c_uint32), ("max_updates_per_pass", C.c_uint64),
+                ("rank", C.c_int32), ("world_size", C.c_int32)]
+
+    def __init__(self, **kw):
+        d = dict(device=-1, max_blocks=0, max_points_per_scan=0, max_updates_per_pass=0, rank=0,
+                 world_size=1)
+        d.update(kw)
+        super().__init__(**d)
+
+
+EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_get_tsdf_config",
+           "vbx_tsdf_integrate", "vbx_tsdf_integrate_device", "vbx_get_counters",
+           "vbx_last_device_ms", "vbx_num_blocks", "vbx_list_blocks", "vbx_download_blocks",
+           "vbx_upload_blocks", "vbx_remove_blocks", "vbx_clear", "vbx_clear_updated",
+           "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the engine; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VoxbloxError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ "
+                           "as g; g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    lib.vbx_create.restype = i32
+    lib.vbx_create.argtypes = [C.POINTER(TsdfIntegratorConfig), C.c_float, i32,
+                               C.POINTER(EngineOptions), C.POINTER(vp)]
+    lib.vbx_destroy.restype = None
+    lib.vbx_destroy.argtypes = [vp]
+    lib.vbx_last_error.restype = C.c_char_p
+    lib.vbx_last_error.argtypes = [vp]
+    lib.vbx_version.restype = C.c_char_p
+    lib.vbx_get_tsdf_config.restype = i32
+    lib.vbx_get_tsdf_config.argtypes = [vp, C.POINTER(TsdfIntegratorConfig)]
+    for name in ("vbx_tsdf_integrate", "vbx_tsdf_integrate_device"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [vp, i32, vp, vp, vp, vp, u64, i32]
+    lib.vbx_get_counters.restype = i32
+    lib.vbx_get_counters.argtypes = [vp, vp]
+    lib.vbx_esdf_get_counters.restype = i32
+    lib.vbx_esdf_get_counters.argtypes = [vp, vp]
+    lib.vbx_last_device_ms.restype = i32
+    lib.vbx_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.vbx_num_blocks.restype = i32
+    lib.vbx_num_blocks.argtypes = [vp, i32, C.POINTER(u64)]
+    lib.vbx_list_blocks.restype = i32
+    lib.vbx_list_blocks.argtypes = [vp, i32, i32, vp, u64, C.POINTER(u64)]
+    lib.vbx_download_blocks.restype = i32
+    lib.vbx_download_blocks.argtypes = [vp, i32, vp, u64, vp, vp]
+    lib.vbx_upload_blocks.restype = i32
+    lib.vbx_upload_blocks.argtypes = [vp, i32, vp, u64, vp, vp]
+    lib.vbx_remove_blocks.restype = i32
+    lib.vbx_remove_blocks.argtypes = [vp, i32, vp, u64]
+    lib.vbx_clear.restype = i32
+    lib.vbx_clear.argtypes = [vp, i32]
+    lib.vbx_clear_updated.restype = i32
+    lib.vbx_clear_updated.argtypes = [vp, i32, i32]
+    lib.vbx_esdf_create.restype = i32
+    lib.vbx_esdf_create.argtypes = [vp, C.POINTER(EsdfIntegratorConfig)]
+    lib.vbx_esdf_update.restype = i32
+    lib.vbx_esdf_update.argtypes = [vp, i32, i32]
+    lib.vbx_sync.restype = i32
+    lib.vbx_sync.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+class _Context:
+    """One vbx_ctx: the device-resident map shared by a TSDF layer, its ESDF layer and
+    the integrators attached to them."""
+
+    def __init__(self, config: TsdfIntegratorConfig, voxel_size: float, voxels_per_side: int,
+                 options: Optional[EngineOptions]):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        self.config = config
+        self.vps = voxels_per_side
+        opt = options if options is not None else EngineOptions()
+        rc = self.lib.vbx_create(C.byref(config), voxel_size, voxels_per_side, C.byref(opt),
+                                 C.byref(self.handle))
+        if rc != 0:
+            msg = self.lib.vbx_last_error(self.handle).decode() if self.handle else "invalid arguments"
+            if self.handle:
+                self.lib.vbx_destroy(self.handle)
+                self.handle = C.c_void_p()
+            raise VoxbloxError(f"vbx_create failed ({rc}): {msg}")
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise VoxbloxError(f"{what} failed ({rc}): {self.lib.vbx_last_error(self.handle).decode()}")
+
+    def close(self):
+        if self.handle:
+            self.lib.vbx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Layer:
+    """Layer<VoxelType> (core/layer.h:24-296) whose blocks live in HBM.
+
+    Construct it like the reference's (voxel_size, voxels_per_side); it binds to the
+    device map when the first integrator is created on it.  Read access downloads
+    blocks on demand (the lazy host mirror)."""
+
+    def __init__(self, voxel_size: float, voxels_per_side: int = 16, voxel_type: str = "tsdf",
+                 engine_options: Optional[EngineOptions] = None):
+        if not voxel_size > 0.0:  # CHECK_GT(voxel_size_, 0.0f), core/layer.h:38
+            raise VoxbloxError("Check failed: voxel_size_ > 0.0f")
+        if voxels_per_side <= 0:
+            raise VoxbloxError("Check failed: voxels_per_side_ > 0u")
+        self._voxel_size = float(np.float32(voxel_size))
+        self._vps = int(voxels_per_side)
+        self.voxel_type = voxel_type
+        self.engine_options = engine_options
+        self._ctx: Optional[_Context] = None
+        self._layer_id = LAYER_TSDF if voxel_type == "tsdf" else LAYER_ESDF
+
+    # -- reference accessors (core/layer.h:241-246)
+    def voxel_size(self) -> float:
+        return self._voxel_size
+
+    def voxels_per_side(self) -> int:
+        return self._vps
+
+    def block_size(self) -> float:
+        return float(np.float32(self._voxel_size) * np.float32(self._vps))
+
+    def _bound(self) -> _Context:
+        if self._ctx is None:
+            raise VoxbloxError("layer is not attached to an integrator yet")
+        return self._ctx
+
+    def getNumberOfAllocatedBlocks(self) -> int:  # core/layer.h:205
+        if self._ctx is None:
+            return 0
+        n = C.c_uint64(0)
+        self._ctx.check(self._ctx.lib.vbx_num_blocks(self._ctx.handle, self._layer_id, C.byref(n)),
+                        "vbx_num_blocks")
+        return int(n.value)
+
+    def _list(self, mask: int) -> np.ndarray:
+        if self._ctx is None:
+            return np.zeros((0, 3), dtype=np.int32)
+        ctx = self._ctx
+        n = C.c_uint64(0)
+        ctx.check(ctx.lib.vbx_list_blocks(ctx.handle, self._layer_id, mask, None, 0, C.byref(n)),
+                  "vbx_list_blocks")
+        out = np.zeros((int(n.value), 3), dtype=np.int32)
+        if n.value:
+            ctx.check(ctx.lib.vbx_list_blocks(ctx.handle, self._layer_id, mask, out.ctypes.data,
+                                              n.value, C.byref(n)), "vbx_list_blocks")
+        return out
+
+    def getAllAllocatedBlocks(self) -> np.ndarray:  # core/layer.h:184-192 (sorted here)
+        return self._list(0)
+
+    def getAllUpdatedBlocks(self, bit: int) -> np.ndarray:  # core/layer.h:194-203
+        return self._list(1 << bit if bit < 3 else bit)
+
+    def hasBlock(self, index: Sequence[int]) -> bool:  # core/layer.h:207-209
+        idx = self.getAllAllocatedBlocks()
+        return bool(len(idx)) and bool((idx == np.asarray(index, dtype=np.int32)).all(axis=1).any())
+
+    def getBlocks(self, indices: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Download blocks: (voxels [m, vps^3] structured, updated bits [m] u8)."""
+        ctx = self._bound()
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        dt = TSDF_DTYPE if self._layer_id == LAYER_TSDF else ESDF_DTYPE
+        vox = np.zeros((idx.shape[0], self._vps ** 3), dtype=dt)
+        upd = np.zeros(idx.shape[0], dtype=np.uint8)
+        if idx.shape[0]:
+            ctx.check(ctx.lib.vbx_download_blocks(ctx.handle, self._layer_id, idx.ctypes.data,
+                                                  idx.shape[0], vox.ctypes.data, upd.ctypes.data),
+                      "vbx_download_blocks")
+        return vox, upd
+
+    def getBlockByIndex(self, index: Sequence[int]) -> np.ndarray:
+        """core/layer.h:55-62: LOG(FATAL) "Accessed unallocated block" -> VoxbloxError."""
+        vox, _ = self.getBlocks(np.asarray([index], dtype=np.int32))
+        return vox[0]
+
+    def blocks(self) -> Dict[Tuple[int, int, int], np.ndarray]:
+        idx = self.getAllAllocatedBlocks()
+        vox, _ = self.getBlocks(idx)
+        return {tuple(int(v) for v in i): vox[k] for k, i in enumerate(idx)}
+
+    def clearUpdated(self, bit: int):
+        """block.updated().reset(bit) on every block (esdf_integrator.cc:113-121)."""
+        ctx = self._bound()
+        ctx.check(ctx.lib.vbx_clear_updated(ctx.handle, self._layer_id, 1 << bit), "vbx_clear_updated")
+
+
+def _as_pose(T_G_C) -> Tuple[np.ndarray, np.ndarray]:
+    q, t = T_G_C
+    q = np.ascontiguousarray(q, dtype=np.float32).reshape(4)
+    t = np.ascontiguousarray(t, dtype=np.float32).reshape(3)
+    return q, t
+
+
+class TsdfIntegratorBase:
+    """TsdfIntegratorBase (tsdf_integrator.h:51-198) dispatching to the device."""
+
+    kind = 0
+
+    def __init__(self, config: TsdfIntegratorConfig, layer: Layer):
+        if layer is None:  # CHECK_NOTNULL(layer), tsdf_integrator.cc:69
+            raise VoxbloxError("Check failed: 'layer' Must be non NULL")
+        if layer.voxel_type != "tsdf":
+            raise VoxbloxError("TSDF integrators need a Layer<TsdfVoxel>")
+        if layer._ctx is None:
+            layer._ctx = _Context(config, layer.voxel_size(), layer.voxels_per_side(),
+                                  layer.engine_options)
+        elif bytes(layer._ctx.config) != bytes(config):
+            raise VoxbloxError("integrators sharing one device layer must share one Config")
+        self.layer_ = layer
+        self._ctx = layer._ctx
+        cfg = TsdfIntegratorConfig()
+        self._ctx.check(self._ctx.lib.vbx_get_tsdf_config(self._ctx.handle, C.byref(cfg)),
+                        "vbx_get_tsdf_config")
+        self.config_ = cfg
+
+    def getConfig(self) -> TsdfIntegratorConfig:  # tsdf_integrator.h:106
+        return self.config_
+
+    def integratePointCloud(self, T_G_C, points_C: np.ndarray, colors: np.ndarray,
+                            freespace_points: bool = False) -> None:
+        """tsdf_integrator.h:100-103.  points_C [N,3] f32 (Pointcloud), colors [N,4] u8
+        (Colors) in HOST memory; CHECK_EQ(points_C.size(), colors.size()) (cc:247)."""
+        q, t = _as_pose(T_G_C)
+        pts = np.ascontiguousarray(points_C, dtype=np.float32).reshape(-1, 3)
+        cols = np.ascontiguousarray(colors, dtype=np.uint8).reshape(-1, 4)
+        if pts.shape[0] != cols.shape[0]:
+            raise VoxbloxError("Check failed: points_C.size() == colors.size()")
+        ctx = self._ctx
+        ctx.check(ctx.lib.vbx_tsdf_integrate(ctx.handle, self.kind, q.ctypes.data, t.ctypes.data,
+                                             pts.ctypes.data, cols.ctypes.data, pts.shape[0],
+                                             int(bool(freespace_points))), "integratePointCloud")
+
+    def integratePointCloudDevice(self, T_G_C, d_xyz: int, d_rgba: int, n: int,
+                                  freespace_points: bool = False) -> None:
+        """Same call with the cloud already resident in HBM (raw device pointers)."""
+        q, t = _as_pose(T_G_C)
+        ctx = self._ctx
+        ctx.check(ctx.lib.vbx_tsdf_integrate_device(ctx.handle, self.kind, q.ctypes.data,
+                                                    t.ctypes.data, d_xyz, d_rgba, n,
+                                                    int(bool(freespace_points))),
+                  "integratePointCloudDevice")
+
+    def counters(self) -> Dict[str, int]:
+        out = np.zeros(16, dtype=np.uint64)
+        self._ctx.check(self._ctx.lib.vbx_get_counters(self._ctx.handle, out.ctypes.data),
+                        "vbx_get_counters")
+        names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
+                 "blocks_allocated", "valid_points", "kernel_launches"]
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def lastDeviceMs(self) -> float:
+        ms = C.c_float(0)
+        self._ctx.check(self._ctx.lib.vbx_last_device_ms(self._ctx.handle, C.byref(ms)),
+                        "vbx_last_device_ms")
+        return float(ms.value)
+
+
+class SimpleTsdfIntegrator(TsdfIntegratorBase):  # tsdf_integrator.h:211-230
+    kind = TsdfIntegratorType.kSimple
+
+
+class MergedTsdfIntegrator(TsdfIntegratorBase):  # tsdf_integrator.h:232-271
+    kind = TsdfIntegratorType.kMerged
+
+
+class FastTsdfIntegrator(TsdfIntegratorBase):  # tsdf_integrator.h:273-341
+    kind = TsdfIntegratorType.kFast
+
+
+class TsdfIntegratorFactory:
+    """TsdfIntegratorFactory::create (tsdf_integrator.cc:8-46)."""
+
+    @staticmethod
+    def create(integrator_type, config: TsdfIntegratorConfig, layer: Layer) -> TsdfIntegratorBase:
+        if isinstance(integrator_type, str):
+            if not integrator_type:
+                raise VoxbloxError("Check failed: !integrator_type_name.empty()")
+            if integrator_type not in kTsdfIntegratorTypeNames:
+                raise VoxbloxError(f"Unknown TSDF integrator type: {integrator_type}")
+            integrator_type = kTsdfIntegratorTypeNames.index(integrator_type) + 1
+        if layer is None:
+            raise VoxbloxError("Check failed: 'layer' Must be non NULL")
+        cls = {1: SimpleTsdfIntegrator, 2: MergedTsdfIntegrator, 3: FastTsdfIntegrator}.get(
+            int(integrator_type))
+        if cls is None:
+            raise VoxbloxError(f"Unknown TSDF integrator type: {int(integrator_type)}")
+        return cls(config, layer)
+
+
+class EsdfIntegrator:
+    """EsdfIntegrator (esdf_integrator.h:25-178) over the device map."""
+
+    def __init__(self, config: EsdfIntegratorConfig, tsdf_layer: Layer, esdf_layer: Layer):
+        if tsdf_layer is None or esdf_layer is None:  # CHECK(tsdf_layer_), esdf_integrator.cc:11-12
+            raise VoxbloxError("Check failed: tsdf_layer_ / esdf_layer_")
+        if esdf_layer.voxels_per_side() != tsdf_layer.voxels_per_side():  # cc:17
+            raise VoxbloxError("Check failed: esdf_layer_->voxels_per_side() == tsdf_layer_->voxels_per_side()")
+        if abs(esdf_layer.voxel_size() - tsdf_layer.voxel_size()) > 1e-6:  # cc:18
+            raise VoxbloxError("Check failed: voxel sizes differ")
+        ctx = tsdf_layer._bound()
+        self._ctx = ctx
+        self.config_ = config
+        esdf_layer._ctx = ctx
+        esdf_layer._layer_id = LAYER_ESDF
+        self.tsdf_layer_, self.esdf_layer_ = tsdf_layer, esdf_layer
+        ctx.check(ctx.lib.vbx_esdf_create(ctx.handle, C.byref(config)), "vbx_esdf_create")
+
+    def updateFromTsdfLayer(self, clear_updated_flag: bool) -> None:  # esdf_integrator.cc:104-122
+        self._ctx.check(self._ctx.lib.vbx_esdf_update(self._ctx.handle, 0, int(bool(clear_updated_flag))),
+                        "updateFromTsdfLayer")
+
+    def updateFromTsdfLayerBatch(self) -> None:  # esdf_integrator.cc:94-102
+        self._ctx.check(self._ctx.lib.vbx_esdf_update(self._ctx.handle, 1, 0), "updateFromTsdfLayerBatch")
+
+    def counters(self) -> Dict[str, int]:
+        out = np.zeros(16, dtype=np.uint64)
+        self._ctx.check(self._ctx.lib.vbx_esdf_get_counters(self._ctx.handle, out.ctypes.data),
+                        "vbx_esdf_get_counters")
+        names = ["blocks", "lower", "raise", "new", "raised_voxels", "relaxations", "sweeps",
+                 "kernel_launches"]
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def lastDeviceMs(self) -> float:
+        ms = C.c_float(0)
+        self._ctx.check(self._ctx.lib.vbx_last_device_ms(self._ctx.handle, C.byref(ms)),
+                        "vbx_last_device_ms")
+        return float(ms.value)

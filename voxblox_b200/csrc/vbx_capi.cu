@@ -1,0 +1,362 @@
+// The C-ABI of include/voxblox_b200.h: context life cycle, the host<->device block
+// mirror (Layer<T> on the host side stays the reference's own container; see
+// INTEGRATION.md) and the entry points that dispatch into the device pipelines.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "vbx_engine.h"
+
+namespace vbx {
+
+int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
+                     const uint8_t* d_rgba, uint64_t n, int freespace);
+size_t cub_temp_bytes(uint32_t max_points, uint64_t max_updates);
+int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
+int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
+
+int fail(vbx_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(vbx_ctx* c, cudaError_t e, const char* what) {
+  if (c) c->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return VBX_E_CUDA;
+}
+
+// Bring the host copy of slot -> block index up to date (new blocks are appended to
+// slot_key by k_assign; removal rebuilds it).
+int refresh_host_mirror(vbx_ctx* c) {
+  const size_t have = c->host_slot_key.size();
+  if (have < c->n_blocks) {
+    c->host_slot_key.resize(c->n_blocks);
+    VBX_CUDA(c, cudaMemcpyAsync(c->host_slot_key.data() + have, c->tab.slot_key + have,
+                                (c->n_blocks - have) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t s = have; s < c->n_blocks; ++s) c->host_key2slot[c->host_slot_key[s]] = (int32_t)s;
+  }
+  return VBX_OK;
+}
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+}  // namespace vbx
+
+using namespace vbx;
+
+extern "C" {
+
+const char* vbx_version(void) { return "voxblox_b200 0.1 (sm_100a)"; }
+
+const char* vbx_last_error(const vbx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side,
+               const vbx_engine_options* opt_in, vbx_ctx** out) {
+  if (!cfg || !out) return VBX_E_INVALID;
+  *out = nullptr;
+  if (!(voxel_size > 0.0f)) return VBX_E_INVALID;  // CHECK_GT(voxel_size_, 0.0f), core/layer.h:38
+  if (voxels_per_side <= 0 || voxels_per_side > 16 || (voxels_per_side & (voxels_per_side - 1))) {
+    return VBX_E_INVALID;  // CHECK(isPowerOfTwo(voxels_per_side)), core/common.h:239
+  }
+  vbx_ctx* c = new vbx_ctx;
+  c->cfg = *cfg;
+  // TsdfIntegratorBase ctor, tsdf_integrator.cc:57-64
+  if (c->cfg.integrator_threads == 0) c->cfg.integrator_threads = 1;
+  if (c->cfg.allow_clear && !c->cfg.voxel_carving_enabled) c->cfg.allow_clear = 0;
+  vbx_engine_options o;
+  std::memset(&o, 0, sizeof(o));
+  if (opt_in) o = *opt_in;
+  int cur = 0;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) {
+    delete c;
+    return VBX_E_CUDA;
+  }
+  if (!opt_in || opt_in->device < 0) o.device = cur;
+  if (o.max_blocks == 0) o.max_blocks = 32768;
+  if (o.max_points_per_scan == 0) o.max_points_per_scan = 1u << 20;
+  if (o.max_updates_per_pass == 0) o.max_updates_per_pass = 1ull << 26;
+  if (o.world_size <= 0) o.world_size = 1;
+  c->opt = o;
+  c->device = o.device;
+  c->voxel_size = voxel_size;
+  c->voxel_size_inv = (float)(1.0 / voxel_size);  // setLayer, tsdf_integrator.cc:77
+  c->vps = voxels_per_side;
+  c->L = 0;
+  while ((1 << c->L) < voxels_per_side) ++c->L;
+  c->vox_per_block = 1u << (3 * c->L);
+  c->max_points = o.max_points_per_scan;
+  c->max_updates = std::min<uint64_t>(o.max_updates_per_pass, 0x7fffffffull);
+  int rb = 0;
+  for (uint32_t v = o.max_blocks; v; v >>= 1) ++rb;
+  if (rb + 3 * c->L > 32) {
+    delete c;
+    return VBX_E_INVALID;
+  }
+  *out = c;  // from here on the caller can read vbx_last_error and must vbx_destroy
+#define CK(expr)                                   \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
+  } while (0)
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  uint32_t hcap = 1;
+  while (hcap < 2 * o.max_blocks) hcap <<= 1;
+  c->hcap = hcap;
+  Tables& t = c->tab;
+  std::memset(&t, 0, sizeof(t));
+  t.hmask = hcap - 1;
+  t.max_blocks = o.max_blocks;
+  CK(dmalloc(&t.hkeys, hcap));
+  CK(dmalloc(&t.hslot, hcap));
+  CK(dmalloc(&t.htouch_epoch, hcap));
+  CK(dmalloc(&t.htouch_rank, hcap));
+  CK(dmalloc(&t.new_list, o.max_blocks));
+  CK(dmalloc(&t.touched_list, o.max_blocks));
+  CK(dmalloc(&t.slot_key, o.max_blocks));
+  CK(dmalloc(&t.slot_updated, o.max_blocks));
+  CK(dmalloc(&t.slot_esdf_updated, o.max_blocks));
+  CK(dmalloc(&t.slot_has_esdf, o.max_blocks));
+  CK(dmalloc(&t.tsdf, (size_t)o.max_blocks * c->vox_per_block));
+  CK(cudaMemsetAsync(t.hkeys, 0xff, (size_t)hcap * sizeof(uint64_t), c->stream));
+  CK(cudaMemsetAsync(t.hslot, 0xff, (size_t)hcap * sizeof(int32_t), c->stream));
+  CK(cudaMemsetAsync(t.htouch_epoch, 0, (size_t)hcap * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(t.htouch_rank, 0, (size_t)hcap * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(t.slot_updated, 0, o.max_blocks, c->stream));
+  CK(cudaMemsetAsync(t.slot_esdf_updated, 0, o.max_blocks, c->stream));
+  CK(cudaMemsetAsync(t.slot_has_esdf, 0, o.max_blocks, c->stream));
+  // new Block: voxels default-constructed = all zero bytes (core/voxel.h:12-16)
+  CK(cudaMemsetAsync(t.tsdf, 0, (size_t)o.max_blocks * c->vox_per_block * sizeof(TsdfVoxel), c->stream));
+  const size_t np = c->max_points;
+  CK(dmalloc(&c->d_xyz, 3 * np));
+  CK(dmalloc(&c->d_rgba, 4 * np));
+  for (int i = 0; i < 2; ++i) {
+    CK(dmalloc(&c->pkeys[i], np));
+    CK(dmalloc(&c->pvals[i], np));
+    CK(dmalloc(&c->ckeys[i], (size_t)c->max_updates));
+    CK(dmalloc(&c->cvals[i], (size_t)c->max_updates));
+  }
+  CK(dmalloc(&c->order, np));
+  CK(dmalloc(&c->ray_p, np));
+  CK(dmalloc(&c->ray_c, np));
+  CK(dmalloc(&c->cnt, np + 1));
+  CK(dmalloc(&c->off, np + 1));
+  c->cub_tmp_bytes = cub_temp_bytes(c->max_points, c->max_updates);
+  CK(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
+  CK(dmalloc(&c->set_start, 1u << 20));
+  CK(dmalloc(&c->set_observed, 1u << 20));
+  CK(cudaMemsetAsync(c->set_start, 0, sizeof(unsigned long long) << 20, c->stream));
+  CK(cudaMemsetAsync(c->set_observed, 0, sizeof(unsigned long long) << 20, c->stream));
+  CK(dmalloc(&c->d_state, 1));
+  CK(cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), c->stream));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_state), sizeof(ScanState)));
+  CK(cudaStreamSynchronize(c->stream));
+#undef CK
+  return VBX_OK;
+}
+
+void vbx_destroy(vbx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  esdf_destroy(c);
+  Tables& t = c->tab;
+  void* ptrs[] = {t.hkeys,        t.hslot,       t.htouch_epoch, t.htouch_rank, t.new_list, t.touched_list,
+                  t.slot_key,     t.slot_updated, t.slot_esdf_updated, t.slot_has_esdf, t.tsdf, c->d_xyz,
+                  c->d_rgba,      c->pkeys[0],   c->pkeys[1],    c->pvals[0],   c->pvals[1], c->ckeys[0],
+                  c->ckeys[1],    c->cvals[0],   c->cvals[1],    c->order,      c->ray_p,    c->ray_c,
+                  c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state};
+  for (void* p : ptrs) {
+    if (p) cudaFree(p);
+  }
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int vbx_get_tsdf_config(const vbx_ctx* c, vbx_tsdf_config* out) {
+  if (!c || !out) return VBX_E_INVALID;
+  *out = c->cfg;
+  return VBX_OK;
+}
+
+int vbx_tsdf_integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
+                              const uint8_t* d_rgba, uint64_t n, int freespace) {
+  if (!c || !q || !t || (n && (!d_xyz || !d_rgba))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return integrate_device(c, kind, q, t, d_xyz, d_rgba, n, freespace);
+}
+
+int vbx_tsdf_integrate(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* xyz,
+                       const uint8_t* rgba, uint64_t n, int freespace) {
+  if (!c || !q || !t || (n && (!xyz || !rgba))) return fail(c, VBX_E_INVALID, "null argument");
+  if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  if (n) {
+    VBX_CUDA(c, cudaMemcpyAsync(c->d_xyz, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VBX_CUDA(c, cudaMemcpyAsync(c->d_rgba, rgba, n * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  return integrate_device(c, kind, q, t, c->d_xyz, c->d_rgba, n, freespace);
+}
+
+int vbx_get_counters(const vbx_ctx* c, uint64_t out[16]) {
+  if (!c || !out) return VBX_E_INVALID;
+  std::memcpy(out, c->counters, sizeof(c->counters));
+  return VBX_OK;
+}
+
+int vbx_esdf_get_counters(const vbx_ctx* c, uint64_t out[16]) {
+  if (!c || !out) return VBX_E_INVALID;
+  std::memcpy(out, c->esdf_counters, sizeof(c->esdf_counters));
+  return VBX_OK;
+}
+
+int vbx_last_device_ms(const vbx_ctx* c, float* ms) {
+  if (!c || !ms) return VBX_E_INVALID;
+  *ms = c->last_ms;
+  return VBX_OK;
+}
+
+int vbx_sync(vbx_ctx* c) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VBX_OK;
+}
+
+static int fetch_flags(vbx_ctx* c, int layer, std::vector<uint8_t>* upd, std::vector<uint8_t>* has) {
+  upd->resize(c->n_blocks);
+  has->assign(c->n_blocks, 1);
+  if (c->n_blocks == 0) return VBX_OK;
+  const uint8_t* src = (layer == VBX_LAYER_TSDF) ? c->tab.slot_updated : c->tab.slot_esdf_updated;
+  VBX_CUDA(c, cudaMemcpyAsync(upd->data(), src, c->n_blocks, cudaMemcpyDeviceToHost, c->stream));
+  if (layer == VBX_LAYER_ESDF) {
+    VBX_CUDA(c, cudaMemcpyAsync(has->data(), c->tab.slot_has_esdf, c->n_blocks, cudaMemcpyDeviceToHost,
+                                c->stream));
+  }
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VBX_OK;
+}
+
+int vbx_num_blocks(vbx_ctx* c, int layer, uint64_t* n) {
+  if (!c || !n) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  if (layer == VBX_LAYER_TSDF) {
+    *n = c->n_blocks;
+    return VBX_OK;
+  }
+  if (!c->has_esdf) {
+    *n = 0;
+    return VBX_OK;
+  }
+  std::vector<uint8_t> upd, has;
+  if (int rc = fetch_flags(c, layer, &upd, &has)) return rc;
+  uint64_t k = 0;
+  for (uint8_t h : has) k += h ? 1 : 0;
+  *n = k;
+  return VBX_OK;
+}
+
+int vbx_list_blocks(vbx_ctx* c, int layer, int updated_mask, int32_t* idx3, uint64_t cap, uint64_t* n) {
+  if (!c || !n) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  *n = 0;
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
+  if (int rc = refresh_host_mirror(c)) return rc;
+  std::vector<uint8_t> upd, has;
+  if (int rc = fetch_flags(c, layer, &upd, &has)) return rc;
+  struct K3 {
+    int x, y, z;
+  };
+  std::vector<K3> keys;
+  keys.reserve(c->n_blocks);
+  for (uint32_t s = 0; s < c->n_blocks; ++s) {
+    if (!has[s]) continue;
+    if (updated_mask && !(upd[s] & updated_mask)) continue;
+    K3 k;
+    unpack3(c->host_slot_key[s], &k.x, &k.y, &k.z);
+    keys.push_back(k);
+  }
+  std::sort(keys.begin(), keys.end(), [](const K3& a, const K3& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  });
+  *n = keys.size();
+  if (idx3) {
+    const uint64_t m = std::min<uint64_t>(cap, keys.size());
+    for (uint64_t i = 0; i < m; ++i) {
+      idx3[3 * i] = keys[i].x;
+      idx3[3 * i + 1] = keys[i].y;
+      idx3[3 * i + 2] = keys[i].z;
+    }
+  }
+  return VBX_OK;
+}
+
+int vbx_download_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, void* voxels,
+                        uint8_t* updated_bits) {
+  if (!c || (m && (!idx3 || !voxels))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF layer");
+  if (int rc = refresh_host_mirror(c)) return rc;
+  std::vector<uint8_t> upd, has;
+  if (int rc = fetch_flags(c, layer, &upd, &has)) return rc;
+  const size_t vbytes = (layer == VBX_LAYER_TSDF) ? sizeof(TsdfVoxel) : sizeof(EsdfVoxel);
+  const size_t bbytes = vbytes * c->vox_per_block;
+  const char* pool = (layer == VBX_LAYER_TSDF) ? reinterpret_cast<const char*>(c->tab.tsdf)
+                                               : reinterpret_cast<const char*>(c->tab.esdf);
+  for (uint64_t i = 0; i < m; ++i) {
+    auto it = c->host_key2slot.find(pack3(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
+    if (it == c->host_key2slot.end() || !has[it->second]) return fail(c, VBX_E_NOT_FOUND, "block not allocated");
+    VBX_CUDA(c, cudaMemcpyAsync(static_cast<char*>(voxels) + i * bbytes, pool + (size_t)it->second * bbytes,
+                                bbytes, cudaMemcpyDeviceToHost, c->stream));
+    if (updated_bits) updated_bits[i] = upd[it->second];
+  }
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VBX_OK;
+}
+
+int vbx_clear_updated(vbx_ctx* c, int layer, int updated_mask) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  if (c->n_blocks == 0) return VBX_OK;
+  std::vector<uint8_t> upd, has;
+  if (int rc = fetch_flags(c, layer, &upd, &has)) return rc;
+  for (uint8_t& u : upd) u &= (uint8_t)~updated_mask;
+  uint8_t* dst = (layer == VBX_LAYER_TSDF) ? c->tab.slot_updated : c->tab.slot_esdf_updated;
+  VBX_CUDA(c, cudaMemcpyAsync(dst, upd.data(), c->n_blocks, cudaMemcpyHostToDevice, c->stream));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VBX_OK;
+}
+
+int vbx_upload_blocks(vbx_ctx* c, int, const int32_t*, uint64_t, const void*, const uint8_t*) {
+  return fail(c, VBX_E_STATE, "vbx_upload_blocks: not implemented yet");
+}
+int vbx_remove_blocks(vbx_ctx* c, int, const int32_t*, uint64_t) {
+  return fail(c, VBX_E_STATE, "vbx_remove_blocks: not implemented yet");
+}
+int vbx_clear(vbx_ctx* c, int) { return fail(c, VBX_E_STATE, "vbx_clear: not implemented yet"); }
+
+int vbx_esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
+  if (!c || !cfg) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return esdf_create(c, cfg);
+}
+
+int vbx_esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_update before vbx_esdf_create");
+  return esdf_update(c, batch, clear_updated_flag);
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Internal declarations shared by the engine's translation units (not installed;
+// the public boundary is include/voxblox_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/voxblox_b200.h"
+#include "vbx_math.cuh"
+
+namespace vbx {
+
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint64_t kInvalidPointKey = ~0ull;
+constexpr int kCoordBias = 1 << 20;  // block / voxel coordinates are packed 21 bits per axis
+
+struct EsdfVoxel {  // core/voxel.h:18-37
+  float distance;
+  uint8_t observed, hallucinated, in_queue, fixed;
+  int32_t parent[3];
+};
+static_assert(sizeof(TsdfVoxel) == 12 && sizeof(EsdfVoxel) == 20, "voxel layouts");
+
+// Error bits raised on the device (ScanState::error)
+enum : uint32_t {
+  kErrPoolFull = 1u,        // more blocks than max_blocks
+  kErrHashFull = 2u,        // block hash probe wrapped around
+  kErrCoordRange = 4u,      // |voxel coordinate| >= 2^20 * vps
+  kErrUpdatesFull = 8u,     // ray-voxel updates exceed max_updates_per_pass
+};
+
+// Device-resident per-call state; the host reads it back through pinned memory.
+struct ScanState {
+  uint32_t n_new;            // hash entries created by this call
+  uint32_t n_touched;        // distinct blocks touched by this call
+  uint32_t error;
+  uint32_t n_rays;           // normal rays / bundles cast
+  uint32_t n_clear_rays;     // clearing rays / bundles cast
+  uint32_t n_valid_points;
+  uint32_t n_voxels;         // distinct voxels updated (U)
+  uint32_t n_blocks;         // pool slots in use after the call
+  unsigned long long total_updates;  // K
+  // ESDF
+  uint32_t esdf_counts[8];
+  uint32_t frontier_n[2];
+  uint32_t raise_n[2];
+  uint32_t pad[2];
+};
+
+// The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
+// core/layer.h:30-32,292).
+struct Tables {
+  uint64_t* hkeys;        // [hcap] packed block index, kEmptyKey when free
+  int32_t* hslot;         // [hcap] pool slot
+  uint32_t* htouch_epoch; // [hcap] call id of the last call that touched the block
+  uint32_t* htouch_rank;  // [hcap] dense id among the blocks touched by that call
+  uint32_t hmask;         // hcap - 1
+  uint32_t max_blocks;
+  uint32_t* new_list;     // [max_blocks] hash positions created by this call
+  uint32_t* touched_list; // [max_blocks] hash positions touched by this call
+  uint64_t* slot_key;     // [max_blocks] packed block index per pool slot
+  uint8_t* slot_updated;  // [max_blocks] TSDF Block::updated() bits
+  uint8_t* slot_esdf_updated;  // [max_blocks] ESDF Block::updated() bits
+  uint8_t* slot_has_esdf;      // [max_blocks] 1 once the ESDF layer holds this block
+  TsdfVoxel* tsdf;        // [max_blocks << 3L]
+  EsdfVoxel* esdf;        // [max_blocks << 3L] (allocated by vbx_esdf_create)
+};
+
+__host__ __device__ inline uint64_t pack3(int x, int y, int z) {
+  return ((uint64_t)(uint32_t)(z + kCoordBias) << 42) | ((uint64_t)(uint32_t)(y + kCoordBias) << 21) |
+         (uint64_t)(uint32_t)(x + kCoordBias);
+}
+__host__ __device__ inline void unpack3(uint64_t k, int* x, int* y, int* z) {
+  *x = (int)(k & 0x1fffffu) - kCoordBias;
+  *y = (int)((k >> 21) & 0x1fffffu) - kCoordBias;
+  *z = (int)((k >> 42) & 0x1fffffu) - kCoordBias;
+}
+__host__ __device__ inline uint32_t hash64(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+}  // namespace vbx
+
+struct vbx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  vbx_tsdf_config cfg;
+  vbx_engine_options opt;
+  float voxel_size = 0, voxel_size_inv = 0;
+  int vps = 16, L = 4;         // voxels per side and log2
+  uint32_t vox_per_block = 4096;
+  uint32_t hcap = 0;
+  vbx::Tables tab;
+  // scratch
+  uint32_t max_points = 0;
+  uint64_t max_updates = 0;
+  float* d_xyz = nullptr;
+  uint8_t* d_rgba = nullptr;
+  uint64_t* pkeys[2] = {nullptr, nullptr};
+  uint32_t* pvals[2] = {nullptr, nullptr};
+  uint32_t* order = nullptr;
+  float4* ray_p = nullptr;    // point_G.xyz, weight
+  uint2* ray_c = nullptr;     // colour, flags
+  uint32_t* cnt = nullptr;    // [max_points + 1]
+  uint32_t* off = nullptr;    // [max_points + 1]
+  uint32_t* ckeys[2] = {nullptr, nullptr};
+  uint32_t* cvals[2] = {nullptr, nullptr};
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  unsigned long long* set_start = nullptr;  // Fast integrator approximate sets
+  unsigned long long* set_observed = nullptr;
+  uint32_t set_epoch = 1;
+  int64_t fast_reset_counter = 0;
+  vbx::ScanState* d_state = nullptr;
+  vbx::ScanState* h_state = nullptr;  // pinned
+  uint32_t epoch = 0;                 // call id for touch marks
+  uint32_t n_blocks = 0;              // pool slots in use
+  // host mirror of slot_key (refreshed lazily)
+  std::vector<uint64_t> host_slot_key;
+  std::unordered_map<uint64_t, int32_t> host_key2slot;
+  // ESDF
+  bool has_esdf = false;
+  vbx_esdf_config ecfg;
+  uint32_t* frontier[2] = {nullptr, nullptr};
+  uint32_t* raise_q[2] = {nullptr, nullptr};
+  uint64_t frontier_cap = 0;
+  uint32_t* esdf_block_list = nullptr;
+  // reporting
+  uint64_t counters[16] = {0};
+  uint64_t esdf_counters[16] = {0};
+  float last_ms = 0.f;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace vbx {
+int fail(vbx_ctx* c, int code, const std::string& msg);
+int cuda_fail(vbx_ctx* c, cudaError_t e, const char* what);
+int refresh_host_mirror(vbx_ctx* c);
+int esdf_destroy(vbx_ctx* c);
+}  // namespace vbx
+
+#define VBX_CUDA(c, expr)                                          \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return vbx::cuda_fail((c), _e, #expr);  \
+  } while (0)
