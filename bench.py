@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: integrated points/s of MergedTsdfIntegrator on 640x480
+scans at 0.05 m voxels (BASELINE.json's metric), one scan per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our engine (one JSON line)
+  python bench.py --impl reference ...                         the reference's own CPU
+                                                               MergedTsdfIntegrator (oracle/_ref)
+Multi-GPU runs are launched by torchrun, one rank per GPU (DESIGN.md "multi-GPU").
+
+JSON keys follow the driver's contract; see DESIGN.md "measurement" for how value, e2e,
+roofline and cpu_baseline are produced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "integrated points/sec (640x480 scan, 0.05 m voxel)"
+VOXEL_SIZE = 0.05
+TRUNC = 0.2  # 4 voxels (voxblox_ros ros_params.h:66-67, cow_and_lady_dataset.launch)
+WORKLOAD = "merged_640x480_room_sequence_0.05m"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_scans(n, start=0):
+    from voxblox_b200 import scenes
+
+    return scenes.generate_parallel(scenes.c3_room_scan, range(start, start + n))
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------- CPU baseline
+def time_reference(scans, threads, kind=2, which=None):
+    """Seconds inside integratePointCloud per scan (stopwatch placed like
+    voxblox_ros/src/tsdf_server.cc:305-307) for the CPU implementation."""
+    from oracle import pyoracle as po
+
+    which = which or ("reference" if po.available("reference") else "port")
+    lib = po.OracleLib(which)
+    cfg = po.TsdfConfig(default_truncation_distance=TRUNC, integrator_threads=threads)
+    m = po.OracleMap(lib, cfg, VOXEL_SIZE, 16)
+    secs = []
+    for s in scans:
+        m.integrate(kind, s)
+        secs.append(m.last_seconds())
+    m.close()
+    return which, secs
+
+
+def calibrate_threads(scans):
+    """The reference defaults to hardware_concurrency threads (tsdf_integrator.h:70) but
+    its per-call std::thread fan-out often loses to fewer threads; give it the best."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({1, 4, 8, 16, min(32, ncpu), ncpu})
+    best = None
+    detail = {}
+    for t in cands:
+        if t > ncpu:
+            continue
+        _, secs = time_reference(scans, t)
+        v = float(np.mean(secs[1:])) if len(secs) > 1 else secs[0]
+        detail[str(t)] = round(v * 1e3, 3)
+        if best is None or v < best[1]:
+            best = (t, v)
+    return best[0], detail
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+
+    scans = make_scans(args.warmup + args.steps)
+    threads, detail = calibrate_threads(scans[:3])
+    which, secs = time_reference(scans, threads)
+    timed = secs[args.warmup:]
+    pts = sum(int(s[0].shape[0]) for s in scans[args.warmup:])
+    total = float(sum(timed))
+    value = pts / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(timed)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "integrator": "merged", "voxel_size_m": VOXEL_SIZE,
+                   "truncation_m": TRUNC, "scan": "640x480 pinhole, box room + 4 objects, 15% dropouts",
+                   "points_per_scan_mean": pts / max(1, len(timed))},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": which,
+                         "sample": f"{len(timed)} scans of the workload; MergedTsdfIntegrator, integrator_threads={threads} "
+                                   f"(fastest of {detail} ms/scan; host has {os.cpu_count()} logical cores)"},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- ours
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import voxblox_b200 as vb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_total = args.warmup + args.steps
+    # weak scaling: every rank integrates its own stream of scans (a different stretch of
+    # the trajectory) into its own map -- see DESIGN.md "multi-GPU" for the sharded mode.
+    scans = make_scans(n_total, start=rank * n_total)
+    npts = [int(s[0].shape[0]) for s in scans]
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=TRUNC)
+    opts = vb.EngineOptions(device=local, max_blocks=16384, max_points_per_scan=1 << 19,
+                            max_updates_per_pass=1 << 24)
+
+    def fresh():
+        layer = vb.Layer(VOXEL_SIZE, 16, engine_options=opts)
+        return layer, vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (1) value: inputs resident in HBM, device-timed over the K steps -----------------
+    d_xyz = [torch.from_numpy(s[0]).to(dev) for s in scans]
+    d_rgba = [torch.from_numpy(s[1]).to(dev) for s in scans]
+    layer, integ = fresh()
+    launches = 0
+    for i in range(args.warmup):
+        integ.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    layer.timerStart()
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_total):
+        integ.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+        launches += integ.counters()["kernel_launches"]
+    dev_ms = layer.timerStopMs()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    last_counters = integ.counters()
+    n_blocks = layer.getNumberOfAllocatedBlocks()
+    pts_timed = sum(npts[args.warmup:])
+    t_ms = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    tot_pts = torch.tensor([float(pts_timed)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_pts, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms = float(t_ms[0]), float(t_ms[1])
+    all_pts = float(tot_pts[0])
+    value = all_pts / (dev_ms * 1e-3)
+
+    # ---- (2) e2e: the reference-facing call with HOST buffers (pinned), H2D inside -------
+    h_xyz = [torch.from_numpy(s[0]).pin_memory() for s in scans]
+    h_rgba = [torch.from_numpy(s[1]).pin_memory() for s in scans]
+    layer2, integ2 = fresh()
+    for i in range(args.warmup):
+        integ2.integratePointCloud((scans[i][2], scans[i][3]), h_xyz[i].numpy(), h_rgba[i].numpy())
+    barrier()
+    layer2.timerStart()
+    for i in range(args.warmup, n_total):
+        integ2.integratePointCloud((scans[i][2], scans[i][3]), h_xyz[i].numpy(), h_rgba[i].numpy())
+        _ = integ2.counters()  # the step's result block (counters) read back on the host
+    e2e_ms = layer2.timerStopMs()
+    barrier()
+    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = all_pts / (float(t_e[0]) * 1e-3)
+    h2d = int(np.mean([16 * n for n in npts[args.warmup:]]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- (3) per-stage device time (profiling pass) and the roofline of the top kernel ---
+    layer3, integ3 = fresh()
+    U = B = K = 0
+    for i in range(n_total):
+        if i == args.warmup:
+            layer3.setStageProfiling(True)
+        integ3.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+        if i >= args.warmup:
+            c = integ3.counters()
+            U += c["voxels_touched"]
+            B += c["blocks_touched"]
+            K += c["updates"]
+    stages = {k: v for k, v in layer3.stageMs().items() if v[1] > 0}
+    top = max(stages, key=lambda k: stages[k][0])
+    steps = max(1, args.steps)
+    n_mean, u_mean, b_mean, k_mean = pts_timed / steps, U / steps, B / steps, K / steps
+    # algorithmic bytes per launch of each stage (DESIGN.md "kernels"): SURVEY.md 8(d)'s
+    # per-scan figure 16 N + 24 U + 20 B split over the stages that must move it.
+    alg = {"point_keys": 12 * n_mean + 12 * n_mean, "point_sort": 2 * 12 * n_mean,
+           "ray_count": 16 * n_mean + 20 * b_mean, "scan": 8 * n_mean, "assign": 20 * b_mean,
+           "ray_emit": 8 * k_mean, "update_sort": 2 * 8 * k_mean, "apply": 24 * u_mean + 8 * k_mean}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    top_ms = stages[top][0] / stages[top][1]
+    achieved = alg[top] / (top_ms * 1e-3) / 1e9
+    scan_alg = 16 * n_mean + 24 * u_mean + 20 * b_mean
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "alg_bytes_per_launch": alg[top], "avg_launch_ms": top_ms,
+                "whole_scan": {"alg_bytes": scan_alg, "ms": dev_ms / steps,
+                               "achieved": scan_alg / (dev_ms / steps * 1e-3) / 1e9,
+                               "frac": scan_alg / (dev_ms / steps * 1e-3) / 1e9 / peak},
+                "stage_ms_per_scan": {k: round(v[0] / steps, 5) for k, v in stages.items()}}
+
+    # ---- (4) CPU baseline on this box's host cores, bounded sample ------------------------
+    from oracle import pyoracle as po
+
+    sample = scans[:min(len(scans), 12)]
+    threads, detail = calibrate_threads(sample[:3])
+    which, secs = time_reference(sample, threads)
+    cpu_pts = sum(int(s[0].shape[0]) for s in sample[2:])
+    cpu_value = cpu_pts / float(sum(secs[2:]))
+    cpu = {"value": cpu_value, "unit": "points/s", "cores": threads, "kind": which,
+           "sample": f"{len(sample) - 2} scans of the workload after 2 warm-up scans; MergedTsdfIntegrator "
+                     f"with integrator_threads={threads} (fastest of {detail} ms/scan; {os.cpu_count()} logical cores)"}
+
+    # ---- (5) parity spot check against the oracle on the same scans -----------------------
+    from tests.parity import compare_tsdf
+
+    layer4, integ4 = fresh()
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=TRUNC), VOXEL_SIZE, 16)
+    for s in scans[:3]:
+        integ4.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    rep = compare_tsdf(layer4, omap)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "integrator": "merged", "voxel_size_m": VOXEL_SIZE,
+                   "truncation_m": TRUNC, "voxels_per_side": 16,
+                   "scan": "640x480 pinhole, box room + 4 objects, 15% dropouts, 30 Hz handheld trajectory",
+                   "points_per_scan_mean": n_mean, "updates_per_scan_mean": k_mean,
+                   "voxels_touched_per_scan_mean": u_mean, "blocks_touched_per_scan_mean": b_mean,
+                   "map_blocks_after_run": n_blocks,
+                   "l2": "every step integrates a different scan (cloud set > L2); the map's voxel blocks stay "
+                         "hot across steps as they do in a mapping session",
+                   "parallelism": "one map per GPU" if world > 1 else "single GPU"},
+        "clocks": clocks, "wall_ms_per_step": wall_ms / steps,
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 128,
+                "ms_per_step": float(t_e[0]) / steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "parity": {"scans": 3, "blocks_equal": rep["blocks_equal"], "max_rel_err": rep.get("max_rel_err"),
+                   "bit_exact_voxels": rep.get("n_bit_exact"), "voxels": rep.get("n_voxels"),
+                   "color_mismatch": rep.get("color_mismatch")},
+        "last_counters": last_counters,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import __graft_entry__ as g
+
+    if rank == 0:
+        with open(os.devnull, "w") as devnull:
+            old = sys.stdout
+            sys.stdout = sys.stderr
+            try:
+                g.build()
+            finally:
+                sys.stdout = old
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

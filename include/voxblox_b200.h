@@ -179,6 +179,20 @@ VBX_API int vbx_esdf_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
 
 VBX_API int vbx_sync(vbx_ctx* ctx);
 
+/* Measurement aids (the reference's counterpart is timing::Timer, utils/timing.h:132-199).
+ * vbx_timer_start / vbx_timer_stop_ms bracket any number of calls with two CUDA events
+ * recorded on the context's stream (device timeline, host gaps included).
+ * With stage profiling on, every integrate / ESDF call also records events at its
+ * stage boundaries and accumulates per-stage device time:
+ *   TSDF  [0] point keys  [1] point sort  [2] ray count + block allocation  [3] scan
+ *         [4] slot assign [5] ray emit    [6] update sort                   [7] apply
+ *   ESDF  [8] propagate   [9] raise       [10] lower wavefront              [11..15] reserved
+ * calls[i] counts how many times stage i ran. */
+VBX_API int vbx_timer_start(vbx_ctx* ctx);
+VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms);
+VBX_API int vbx_set_stage_profiling(vbx_ctx* ctx, int enabled);
+VBX_API int vbx_get_stage_ms(const vbx_ctx* ctx, double ms[16], uint64_t calls[16]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,7 +110,8 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_tsdf_integrate", "vbx_tsdf_integrate_device", "vbx_get_counters",
            "vbx_last_device_ms", "vbx_num_blocks", "vbx_list_blocks", "vbx_download_blocks",
            "vbx_upload_blocks", "vbx_remove_blocks", "vbx_clear", "vbx_clear_updated",
-           "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync"]
+           "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync",
+           "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms"]
 
 _lib = None
 
@@ -165,6 +166,14 @@ def load_library():
     lib.vbx_esdf_update.argtypes = [vp, i32, i32]
     lib.vbx_sync.restype = i32
     lib.vbx_sync.argtypes = [vp]
+    lib.vbx_timer_start.restype = i32
+    lib.vbx_timer_start.argtypes = [vp]
+    lib.vbx_timer_stop_ms.restype = i32
+    lib.vbx_timer_stop_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.vbx_set_stage_profiling.restype = i32
+    lib.vbx_set_stage_profiling.argtypes = [vp, i32]
+    lib.vbx_get_stage_ms.restype = i32
+    lib.vbx_get_stage_ms.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 
@@ -293,6 +302,35 @@ class Layer:
         idx = self.getAllAllocatedBlocks()
         vox, _ = self.getBlocks(idx)
         return {tuple(int(v) for v in i): vox[k] for k, i in enumerate(idx)}
+
+    # -- measurement aids (reference: timing::Timer, utils/timing.h:132-199)
+    def timerStart(self):
+        ctx = self._bound()
+        ctx.check(ctx.lib.vbx_timer_start(ctx.handle), "vbx_timer_start")
+
+    def timerStopMs(self) -> float:
+        ctx = self._bound()
+        ms = C.c_float(0)
+        ctx.check(ctx.lib.vbx_timer_stop_ms(ctx.handle, C.byref(ms)), "vbx_timer_stop_ms")
+        return float(ms.value)
+
+    def setStageProfiling(self, enabled: bool):
+        ctx = self._bound()
+        ctx.check(ctx.lib.vbx_set_stage_profiling(ctx.handle, int(enabled)), "vbx_set_stage_profiling")
+
+    STAGE_NAMES = ("point_keys", "point_sort", "ray_count", "scan", "assign", "ray_emit",
+                   "update_sort", "apply", "esdf_propagate", "esdf_raise", "esdf_lower")
+
+    def stageMs(self):
+        ctx = self._bound()
+        ms = np.zeros(16, dtype=np.float64)
+        calls = np.zeros(16, dtype=np.uint64)
+        ctx.check(ctx.lib.vbx_get_stage_ms(ctx.handle, ms.ctypes.data, calls.ctypes.data), "vbx_get_stage_ms")
+        return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(self.STAGE_NAMES)}
+
+    def sync(self):
+        ctx = self._bound()
+        ctx.check(ctx.lib.vbx_sync(ctx.handle), "vbx_sync")
 
     def clearUpdated(self, bit: int):
         """block.updated().reset(bit) on every block (esdf_integrator.cc:113-121)."""

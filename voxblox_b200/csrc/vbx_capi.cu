@@ -106,6 +106,9 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreate(&c->tev0));
+  CK(cudaEventCreate(&c->tev1));
+  for (int i = 0; i < 20; ++i) CK(cudaEventCreate(&c->sev[i]));
   uint32_t hcap = 1;
   while (hcap < 2 * o.max_blocks) hcap <<= 1;
   c->hcap = hcap;
@@ -178,6 +181,11 @@ void vbx_destroy(vbx_ctx* c) {
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->tev0) cudaEventDestroy(c->tev0);
+  if (c->tev1) cudaEventDestroy(c->tev1);
+  for (int i = 0; i < 20; ++i) {
+    if (c->sev[i]) cudaEventDestroy(c->sev[i]);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -222,6 +230,37 @@ int vbx_esdf_get_counters(const vbx_ctx* c, uint64_t out[16]) {
 int vbx_last_device_ms(const vbx_ctx* c, float* ms) {
   if (!c || !ms) return VBX_E_INVALID;
   *ms = c->last_ms;
+  return VBX_OK;
+}
+
+int vbx_timer_start(vbx_ctx* c) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_CUDA(c, cudaEventRecord(c->tev0, c->stream));
+  return VBX_OK;
+}
+
+int vbx_timer_stop_ms(vbx_ctx* c, float* ms) {
+  if (!c || !ms) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_CUDA(c, cudaEventRecord(c->tev1, c->stream));
+  VBX_CUDA(c, cudaEventSynchronize(c->tev1));
+  VBX_CUDA(c, cudaEventElapsedTime(ms, c->tev0, c->tev1));
+  return VBX_OK;
+}
+
+int vbx_set_stage_profiling(vbx_ctx* c, int enabled) {
+  if (!c) return VBX_E_INVALID;
+  c->profiling = enabled != 0;
+  std::memset(c->stage_ms, 0, sizeof(c->stage_ms));
+  std::memset(c->stage_calls, 0, sizeof(c->stage_calls));
+  return VBX_OK;
+}
+
+int vbx_get_stage_ms(const vbx_ctx* c, double ms[16], uint64_t calls[16]) {
+  if (!c || !ms || !calls) return VBX_E_INVALID;
+  std::memcpy(ms, c->stage_ms, sizeof(c->stage_ms));
+  std::memcpy(calls, c->stage_calls, sizeof(c->stage_calls));
   return VBX_OK;
 }
 

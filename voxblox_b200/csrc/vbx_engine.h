@@ -140,6 +140,11 @@ struct vbx_ctx {
   uint64_t esdf_counters[16] = {0};
   float last_ms = 0.f;
   uint64_t launches = 0;
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // vbx_timer_*
+  bool profiling = false;
+  cudaEvent_t sev[20] = {nullptr};             // stage boundaries
+  double stage_ms[16] = {0};
+  uint64_t stage_calls[16] = {0};
   std::string err;
 };
 

@@ -486,6 +486,15 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     return VBX_OK;
   }
   const int TB = 256;
+  int n_marks = 0;
+  int mark_stage[20];
+  auto mark = [&](int stage_just_finished) {
+    if (c->profiling && n_marks < 19) {
+      cudaEventRecord(c->sev[n_marks + 1], s);
+      mark_stage[n_marks++] = stage_just_finished;
+    }
+  };
+  if (c->profiling) cudaEventRecord(c->sev[0], s);
 
   const uint32_t* order = nullptr;
   if (cfg.integration_order_mode == 1) {
@@ -504,6 +513,7 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   const uint32_t* vals = nullptr;
   if (kind == VBX_MERGED) {
     k_point_keys<<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, c->pkeys[0], c->pvals[0], c->d_state);
+    mark(0);
     cub::DoubleBuffer<uint64_t> kb(c->pkeys[0], c->pkeys[1]);
     cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
     size_t tmp = c->cub_tmp_bytes;
@@ -511,17 +521,21 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     keys = kb.Current();
     vals = vb.Current();
     launches += 10;
+    mark(1);
   }
 
   k_rays_count<<<grid_for((uint64_t)n + 1, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, vals,
                                                                 c->ray_p, c->ray_c, c->cnt, c->set_start,
                                                                 c->set_observed, c->d_state);
+  mark(2);
   {
     size_t tmp = c->cub_tmp_bytes;
     VBX_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp, tmp, c->cnt, c->off, (int)(n + 1), s));
   }
+  mark(3);
   k_assign<<<grid_for(c->tab.max_blocks, TB), TB, 0, s>>>(c->tab, c->off, n, c->n_blocks, c->max_updates,
                                                           c->d_state);
+  mark(4);
   launches += 4;
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
@@ -533,13 +547,16 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   if (K > 0) {
     k_rays_emit<<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_p, c->ray_c, c->cnt, c->off,
                                                   c->ckeys[0], c->cvals[0]);
+    mark(5);
     cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
     cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
     size_t tmp = c->cub_tmp_bytes;
     const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
     VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
+    mark(6);
     k_apply<<<grid_for(K, TB), TB, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_p, c->ray_c,
                                            c->d_state);
+    mark(7);
     launches += 3 + (key_bits + 7) / 8;
   }
   VBX_CUDA(c, cudaEventRecord(c->ev1, s));
@@ -547,6 +564,13 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   VBX_CUDA(c, cudaStreamSynchronize(s));
   VBX_CUDA(c, cudaGetLastError());
   VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  for (int m = 0; m < n_marks; ++m) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->sev[m], c->sev[m + 1]) == cudaSuccess) {
+      c->stage_ms[mark_stage[m]] += ms;
+      c->stage_calls[mark_stage[m]] += 1;
+    }
+  }
   c->launches += launches;
   c->counters[0] = c->h_state->n_rays;
   c->counters[1] = c->h_state->n_clear_rays;

@@ -260,20 +260,22 @@ def _orbit_pose(i: int, n: int, radius: float, height: float, target, rng, jitte
     return look_at(pos, tgt), pos
 
 
-def c2_sphere_room(n_scans: int = 300, width: int = 640, height: int = 480,
-                   seed: int = 0) -> List[Scan]:
-    """C2: camera orbiting inside a sphere of radius 3 m (far-root hits), depth + colour."""
-    rng = np.random.default_rng(seed)
+def c2_sphere_scan(i: int, n_scans: int = 300, width: int = 640, height: int = 480,
+                   seed: int = 0) -> Scan:
+    """C2, scan i: camera orbiting inside a sphere of radius 3 m (far-root hits)."""
+    rng = np.random.default_rng([seed, 2, i])
     f = 525.0 * width / 640.0
     dirs = pinhole_dirs(width, height, f, f, width / 2.0, height / 2.0)
     prims = [Sphere((0.0, 0.0, 0.0), 3.0, (180, 160, 140))]
-    scans = []
-    for i in range(n_scans):
-        q, pos = _orbit_pose(i, n_scans, 0.9, 0.1, (2.5 * math.cos(2 * math.pi * i / n_scans + 0.6),
-                                                   2.5 * math.sin(2 * math.pi * i / n_scans + 0.6),
-                                                   0.2), rng, 0.01)
-        scans.append(render(prims, dirs, q, pos))
-    return scans
+    ang = 2 * math.pi * i / n_scans
+    q, pos = _orbit_pose(i, n_scans, 0.9, 0.1,
+                         (2.5 * math.cos(ang + 0.6), 2.5 * math.sin(ang + 0.6), 0.2), rng, 0.01)
+    return render(prims, dirs, q, pos)
+
+
+def c2_sphere_room(n_scans: int = 300, width: int = 640, height: int = 480, seed: int = 0,
+                   total: int = 300) -> List[Scan]:
+    return [c2_sphere_scan(i, total, width, height, seed) for i in range(n_scans)]
 
 
 def room_prims() -> list:
@@ -285,26 +287,29 @@ def room_prims() -> list:
             Sphere((-0.9, -0.9, 1.6), 0.35, (220, 200, 60))]
 
 
-def c3_room_sequence(n_scans: int = 1000, width: int = 640, height: int = 480, seed: int = 0,
-                     drop_fraction: float = 0.15, depth_noise_sigma: float = 0.0) -> List[Scan]:
-    """C3/C4: handheld-style trajectory through the room, depth 0.5-4.5 m, 15 % dropouts."""
-    rng = np.random.default_rng(seed)
+def c3_room_scan(i: int, width: int = 640, height: int = 480, seed: int = 0,
+                 drop_fraction: float = 0.15, depth_noise_sigma: float = 0.0) -> Scan:
+    """C3/C4, scan i of a handheld-style trajectory (30 Hz) through the room: depth
+    0.5-4.5 m, a seeded fraction of pixels dropped.  Scans are independent of each other
+    (per-scan RNG stream), so a sequence can be generated in parallel."""
+    rng = np.random.default_rng([seed, 3, i])
     f = 525.0 * width / 640.0
     dirs = pinhole_dirs(width, height, f, f, width / 2.0 - 0.5, height / 2.0 - 0.5)
-    prims = room_prims()
-    scans = []
-    for i in range(n_scans):
-        s = i / 30.0  # seconds at 30 Hz
-        pos = np.array([1.25 * math.cos(0.35 * s) + 0.1 * math.sin(1.3 * s),
-                        1.25 * math.sin(0.35 * s) + 0.1 * math.cos(1.1 * s),
-                        1.35 + 0.2 * math.sin(0.7 * s)]) + rng.normal(0.0, 0.004, size=3)
-        tgt = np.array([0.25 * math.sin(0.21 * s), 0.25 * math.cos(0.17 * s),
-                        0.7 + 0.25 * math.sin(0.5 * s)])
-        q = look_at(pos, tgt)
-        scans.append(render(prims, dirs, q, pos, min_range=0.5, max_range=4.5,
-                            drop_fraction=drop_fraction, rng=rng,
-                            depth_noise_sigma=depth_noise_sigma))
-    return scans
+    s = i / 30.0
+    pos = np.array([1.25 * math.cos(0.35 * s) + 0.1 * math.sin(1.3 * s),
+                    1.25 * math.sin(0.35 * s) + 0.1 * math.cos(1.1 * s),
+                    1.35 + 0.2 * math.sin(0.7 * s)]) + rng.normal(0.0, 0.004, size=3)
+    tgt = np.array([0.25 * math.sin(0.21 * s), 0.25 * math.cos(0.17 * s),
+                    0.7 + 0.25 * math.sin(0.5 * s)])
+    return render(room_prims(), dirs, look_at(pos, tgt), pos, min_range=0.5, max_range=4.5,
+                  drop_fraction=drop_fraction, rng=rng, depth_noise_sigma=depth_noise_sigma)
+
+
+def c3_room_sequence(n_scans: int = 1000, width: int = 640, height: int = 480, seed: int = 0,
+                     drop_fraction: float = 0.15, depth_noise_sigma: float = 0.0,
+                     start: int = 0) -> List[Scan]:
+    return [c3_room_scan(start + i, width, height, seed, drop_fraction, depth_noise_sigma)
+            for i in range(n_scans)]
 
 
 def lidar_prims() -> list:
@@ -315,16 +320,35 @@ def lidar_prims() -> list:
             CylinderZ((2.6, -1.9), 0.35, 0.0, 4.0, (200, 200, 60))]
 
 
+def c5_lidar_scan(i: int, n_azimuth: int = 2048, n_rings: int = 128, seed: int = 0) -> Scan:
+    """C5, scan i: spinning LiDAR (360 x +-22.5 deg) inside a 9 x 9 x 4 m hall with pillars."""
+    rng = np.random.default_rng([seed, 5, i])
+    dirs = lidar_dirs(n_azimuth, n_rings, 22.5)
+    pos = np.array([0.4 * math.cos(0.4 * i) + 0.05, 0.4 * math.sin(0.4 * i) - 0.03,
+                    1.8 + 0.02 * math.sin(i)]) + rng.normal(0.0, 0.003, size=3)
+    q = quat_from_rpy(0.011 + 0.002 * i, -0.007, 0.13 * i + 0.017)
+    return render(lidar_prims(), dirs, q, pos, min_range=0.3, max_range=9.5)
+
+
 def c5_lidar_sequence(n_scans: int = 16, n_azimuth: int = 2048, n_rings: int = 128,
                       seed: int = 0) -> List[Scan]:
-    """C5: spinning LiDAR (360 x +-22.5 deg) inside a 9 x 9 x 4 m hall with pillars."""
-    rng = np.random.default_rng(seed)
-    dirs = lidar_dirs(n_azimuth, n_rings, 22.5)
-    prims = lidar_prims()
-    scans = []
-    for i in range(n_scans):
-        pos = np.array([0.4 * math.cos(0.4 * i) + 0.05, 0.4 * math.sin(0.4 * i) - 0.03,
-                        1.8 + 0.02 * math.sin(i)]) + rng.normal(0.0, 0.003, size=3)
-        q = quat_from_rpy(0.011 + 0.002 * i, -0.007, 0.13 * i + 0.017)
-        scans.append(render(prims, dirs, q, pos, min_range=0.3, max_range=9.5))
-    return scans
+    return [c5_lidar_scan(i, n_azimuth, n_rings, seed) for i in range(n_scans)]
+
+
+def _call(args):
+    fn, a, kw = args
+    return fn(*a, **kw)
+
+
+def generate_parallel(fn, indices: Sequence[int], workers: Optional[int] = None, **kw) -> List[Scan]:
+    """[fn(i, **kw) for i in indices] on a process pool (scan generation is host-side
+    numpy and embarrassingly parallel; it is never inside a timed region)."""
+    import multiprocessing as mp
+    import os
+
+    indices = list(indices)
+    workers = max(1, min(workers or (os.cpu_count() or 1), len(indices), 32))
+    if workers == 1:
+        return [fn(i, **kw) for i in indices]
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_call, [(fn, (i,), kw) for i in indices], chunksize=1)
