@@ -267,7 +267,8 @@ def run_ours(args, rank, world):
     # per-scan figure 16 N + 24 U + 20 B split over the stages that must move it.
     alg = {"point_keys": 12 * n_mean + 12 * n_mean, "point_sort": 2 * 12 * n_mean,
            "ray_count": 16 * n_mean + 20 * b_mean, "scan": 8 * n_mean, "assign": 20 * b_mean,
-           "ray_emit": 8 * k_mean, "update_sort": 2 * 8 * k_mean, "apply": 24 * u_mean + 8 * k_mean}
+           "ray_emit": 8 * k_mean, "update_sort": 2 * 8 * k_mean, "apply": 24 * u_mean + 8 * k_mean,
+           "bundle_merge": 16 * n_mean + 8 * n_mean}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -186,7 +186,8 @@ VBX_API int vbx_sync(vbx_ctx* ctx);
  * stage boundaries and accumulates per-stage device time:
  *   TSDF  [0] point keys  [1] point sort  [2] ray count + block allocation  [3] scan
  *         [4] slot assign [5] ray emit    [6] update sort                   [7] apply
- *   ESDF  [8] propagate   [9] raise       [10] lower wavefront              [11..15] reserved
+ *         [8] bundle heads + merge
+ *   ESDF  [9] propagate   [10] raise      [11] lower wavefront              [12..15] reserved
  * calls[i] counts how many times stage i ran. */
 VBX_API int vbx_timer_start(vbx_ctx* ctx);
 VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms);

@@ -319,7 +319,7 @@ class Layer:
         ctx.check(ctx.lib.vbx_set_stage_profiling(ctx.handle, int(enabled)), "vbx_set_stage_profiling")
 
     STAGE_NAMES = ("point_keys", "point_sort", "ray_count", "scan", "assign", "ray_emit",
-                   "update_sort", "apply", "esdf_propagate", "esdf_raise", "esdf_lower")
+                   "update_sort", "apply", "bundle_merge", "esdf_propagate", "esdf_raise", "esdf_lower")
 
     def stageMs(self):
         ctx = self._bound()

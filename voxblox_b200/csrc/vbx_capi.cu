@@ -146,6 +146,8 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     CK(dmalloc(&c->cvals[i], (size_t)c->max_updates));
   }
   CK(dmalloc(&c->order, np));
+  CK(dmalloc(&c->ray_list, np));
+  CK(dmalloc(&c->long_list, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->ray_p, np));
   CK(dmalloc(&c->ray_c, np));
   CK(dmalloc(&c->cnt, np + 1));
@@ -174,7 +176,8 @@ void vbx_destroy(vbx_ctx* c) {
                   t.slot_key,     t.slot_updated, t.slot_esdf_updated, t.slot_has_esdf, t.tsdf, c->d_xyz,
                   c->d_rgba,      c->pkeys[0],   c->pkeys[1],    c->pvals[0],   c->pvals[1], c->ckeys[0],
                   c->ckeys[1],    c->cvals[0],   c->cvals[1],    c->order,      c->ray_p,    c->ray_c,
-                  c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state};
+                  c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
+                  c->ray_list,    c->long_list};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }

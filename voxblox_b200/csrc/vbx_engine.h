@@ -31,6 +31,7 @@ enum : uint32_t {
   kErrHashFull = 2u,        // block hash probe wrapped around
   kErrCoordRange = 4u,      // |voxel coordinate| >= 2^20 * vps
   kErrUpdatesFull = 8u,     // ray-voxel updates exceed max_updates_per_pass
+  kNeedWideKeys = 16u,      // not an error: a clearing point fell outside the compact bundle-key range
 };
 
 // Device-resident per-call state; the host reads it back through pinned memory.
@@ -48,7 +49,8 @@ struct ScanState {
   uint32_t esdf_counts[8];
   uint32_t frontier_n[2];
   uint32_t raise_n[2];
-  uint32_t pad[2];
+  uint32_t n_ray_list;       // bundle heads (Merged)
+  uint32_t n_long;           // voxel runs handed to k_apply_long
 };
 
 // The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
@@ -109,6 +111,8 @@ struct vbx_ctx {
   uint64_t* pkeys[2] = {nullptr, nullptr};
   uint32_t* pvals[2] = {nullptr, nullptr};
   uint32_t* order = nullptr;
+  uint32_t* ray_list = nullptr;            // [max_points] dense list of bundle heads
+  unsigned long long* long_list = nullptr; // [max_updates / 32 + 1] starts of long voxel runs
   float4* ray_p = nullptr;    // point_G.xyz, weight
   uint2* ray_c = nullptr;     // colour, flags
   uint32_t* cnt = nullptr;    // [max_points + 1]

@@ -5,17 +5,21 @@
 //                    (bundleRays, cc:340-371)
 //   sort             stable radix sort of the point keys: bundles become runs, in the
 //                    reference's point order inside a run
-//   k_rays_count     one thread per ray / bundle: sequential weighted merge of the
-//                    bundle (integrateVoxel cc:387-405), DDA walk (RayCaster) that
-//                    creates missing blocks in the device hash and counts the voxels
-//                    it will update (allocateStorageAndGetVoxelPtr cc:91-134)
+//   k_heads          dense list of bundle heads
+//   k_merge          one WARP per bundle: 32 members prefetched per step, the
+//                    reference's sequential weighted mean (integrateVoxel cc:387-405)
+//                    evaluated in order on the prefetched registers
+//   k_rays_count     one thread per ray: DDA walk (RayCaster) that creates missing
+//                    blocks in the device hash and counts the voxels it will update
+//                    (allocateStorageAndGetVoxelPtr cc:91-134)
 //   scan + k_assign  offsets of every ray's update records; pool slots for new blocks
 //   k_rays_emit      second DDA walk writing (voxel id, ray id) records
 //   sort             stable radix sort by voxel id: every voxel's updates become one
 //                    run, ordered by ray rank
-//   k_apply          one pass over the runs applying updateTsdfVoxel (cc:150-209)
-//                    sequentially per voxel -- clamp-after-every-update semantics
-//                    preserved exactly, with no locks and no atomics on voxels
+//   k_apply_short /  updateTsdfVoxel (cc:150-209) applied sequentially per voxel --
+//   k_apply_long     clamp-after-every-update semantics preserved exactly, with no
+//                    locks and no atomics on voxels.  Runs longer than 32 updates
+//                    (free space near the sensor) continue in a warp-per-run kernel.
 //
 // Update order.  The reference applies a voxel's updates in whatever order its
 // threads reach the voxel's mutex (cc:186); with one thread that is point order for
@@ -32,6 +36,8 @@
 #include "vbx_engine.h"
 
 namespace vbx {
+
+constexpr int kShortRun = 32;  // updates a single thread applies before handing the run to a warp
 
 struct ScanParams {
   Pose T;
@@ -50,6 +56,12 @@ struct ScanParams {
   uint32_t set_epoch;  // generation tag of the Fast integrator's approximate sets
   uint32_t epoch;      // call id
   uint64_t max_updates;
+  // bundle keys: voxel coordinates relative to (origin voxel - key_radius), key_bits per
+  // axis; wide = full 21-bit absolute coordinates (fallback for far clearing points)
+  int ovx, ovy, ovz;
+  int key_radius;
+  int key_bits;
+  int wide_keys;
 };
 
 // MixedThreadSafeIndex::getNextIndexImpl, integrator_utils.cc:54-63
@@ -64,6 +76,28 @@ __device__ __forceinline__ F3 load_point(const float* xyz, uint32_t idx) {
 }
 __device__ __forceinline__ uint32_t load_color(const uint8_t* rgba, uint32_t idx) {
   return __ldg(reinterpret_cast<const uint32_t*>(rgba) + idx);
+}
+
+// ------------------------------------------------------------------ bundle keys
+// key = [clearing | z | y | x]; ascending key order = (clearing, z, y, x).
+__device__ __forceinline__ uint64_t make_point_key(const ScanParams& P, I3 v, bool clearing, bool* in_range) {
+  if (P.wide_keys) {
+    const int lim = kCoordBias - 1;
+    *in_range = !(v.x < -lim || v.x > lim || v.y < -lim || v.y > lim || v.z < -lim || v.z > lim);
+    return pack3(v.x, v.y, v.z) | ((uint64_t)clearing << 63);
+  }
+  const int rx = v.x - P.ovx + P.key_radius, ry = v.y - P.ovy + P.key_radius, rz = v.z - P.ovz + P.key_radius;
+  const int span = 2 * P.key_radius;
+  *in_range = !(rx < 0 || rx > span || ry < 0 || ry > span || rz < 0 || rz > span);
+  return (uint64_t)rx | ((uint64_t)ry << P.key_bits) | ((uint64_t)rz << (2 * P.key_bits)) |
+         ((uint64_t)clearing << (3 * P.key_bits));
+}
+// the key a NORMAL bundle ending in voxel v would have (anti-grazing lookup)
+__device__ __forceinline__ uint64_t normal_key_of(const ScanParams& P, int x, int y, int z, bool* in_range) {
+  return make_point_key(P, i3(x, y, z), false, in_range);
+}
+__device__ __forceinline__ bool key_is_clearing(const ScanParams& P, uint64_t key) {
+  return ((key >> (P.wide_keys ? 63 : 3 * P.key_bits)) & 1ull) != 0;
 }
 
 // ------------------------------------------------------------------ block hash
@@ -118,23 +152,25 @@ __device__ __forceinline__ void mark_touched(const Tables& t, uint32_t hp, uint3
 
 // ------------------------------------------------------------------- kernels
 // Merged: key every point by its end voxel (bundleRays, cc:340-371).
+template <typename KeyT>
 __global__ void k_point_keys(ScanParams P, const float* __restrict__ xyz, const uint32_t* __restrict__ order,
-                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, ScanState* st) {
+                             KeyT* __restrict__ keys, uint32_t* __restrict__ vals, ScanState* st) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = false;
   if (s < P.n) {
     const uint32_t idx = point_order(P, order, s);
     const F3 p = load_point(xyz, idx);
     const int cls = classify_point(p, P.min_ray, P.max_ray, P.allow_clear != 0, P.freespace != 0);
-    uint64_t key = kInvalidPointKey;
+    KeyT key = (KeyT)~(KeyT)0;
     if (cls != 0) {
       const I3 v = grid_index(transform(P.T, p), P.voxel_size_inv);
-      const int lim = kCoordBias - 1;
-      if (v.x < -lim || v.x > lim || v.y < -lim || v.y > lim || v.z < -lim || v.z > lim) {
-        atomicOr(&st->error, kErrCoordRange);
-      } else {
-        key = pack3(v.x, v.y, v.z) | ((uint64_t)(cls == 2) << 63);
+      bool in_range;
+      const uint64_t k = make_point_key(P, v, cls == 2, &in_range);
+      if (in_range) {
+        key = (KeyT)k;
         valid = true;
+      } else {
+        atomicOr(&st->error, P.wide_keys ? kErrCoordRange : kNeedWideKeys);
       }
     }
     keys[s] = key;
@@ -156,9 +192,221 @@ __global__ void k_sqnorm_keys(uint32_t n, const float* __restrict__ xyz, uint64_
   vals[i] = i;
 }
 
+// Dense (unordered) list of bundle heads; a ray's rank stays its sorted position.
+template <typename KeyT>
+__global__ void k_heads(uint32_t n, const KeyT* __restrict__ keys, uint32_t* __restrict__ ray_list,
+                        uint32_t* __restrict__ cnt, ScanState* st) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool head = false;
+  if (i <= n) cnt[i] = 0;
+  if (i < n) {
+    const KeyT key = keys[i];
+    head = key != (KeyT)~(KeyT)0 && (i == 0 || keys[i - 1] != key);
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, head);
+  if (b) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&st->n_ray_list, (uint32_t)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (head) ray_list[base + __popc(b & ((1u << lane) - 1u))] = i;
+  }
+}
+
+// Correctly rounded a / b in three dependent operations, given y = RN(1 / b):
+//   q = RN(a y);  r = a - q b (exact, one FMA);  a / b = RN(q + r y)
+// (Markstein's division step; checked against IEEE division on 8e8 random and adversarial
+// operand pairs by tests/exact_div_check.c).  It is only trusted for operands in a
+// comfortable exponent band with a non-zero dividend (sign of zero) and a divisor whose
+// mantissa is not all ones; anything else is flagged and the bundle is folded again with the
+// IEEE division instruction.
+__device__ __forceinline__ bool exact_div_operand_ok(float v) {
+  const float a = fabsf(v);
+  return a > 1e-18f && a < 1e18f;
+}
+__device__ __forceinline__ float recip_for_exact_div(float b, bool* ok) {
+  *ok = exact_div_operand_ok(b) && (__float_as_uint(b) & 0x7fffffu) != 0x7fffffu;
+  return __frcp_rn(b);
+}
+
+constexpr int kStageStride = 9;  // float4 per staged member (8 roles + 1 pad: conflict-free stores)
+
+// One member's step of the fold for this lane's role:
+//   t = state * A + B;   mean lanes: state = t / C;   colour lanes: state = round(t)
+// kIeee = false uses the three-operation division with D = RN(1/C) and records operands it does
+// not trust in *suspect; kIeee = true is the plain reference arithmetic.
+template <bool kIeee>
+__device__ __forceinline__ float fold_step(float state, float4 abcd, bool is_mean, bool* suspect) {
+  const float tt = fadd(fmul(state, abcd.x), abcd.y);
+  float quot;
+  if (kIeee) {
+    quot = is_mean ? fdiv(tt, abcd.z) : 0.f;
+  } else {
+    const float q = __fmul_rn(tt, abcd.w);
+    quot = __fmaf_rn(__fmaf_rn(-q, abcd.z, tt), abcd.w, q);
+    *suspect |= is_mean && !exact_div_operand_ok(tt);
+  }
+  // C round() (half away from zero) of t in [0, 2^22): nearest-even via the 2^23 trick, then
+  // bump exact ties that went down
+  const float m = fadd(fadd(tt, 8388608.0f), -8388608.0f);
+  const float rnd = (fsub(tt, m) == 0.5f) ? fadd(m, 1.0f) : m;
+  return is_mean ? quot : rnd;
+}
+
+// Fold one bundle (a run of equal keys starting at sorted position i) with one warp.
+// Members are loaded 32 at a time (keys coalesced, points gathered, next chunk prefetched) and
+// folded in list order with the reference's running weighted mean
+//   merged = (merged * W + p * w) / (W + w); colour blended; W += w            (cc:387-405)
+// Lanes 0-2 carry x, y, z of the mean, lanes 3-6 the colour channels (floats holding exact
+// integers 0..255).  Returns true if the fast division met an operand it does not trust.
+template <typename KeyT, bool kIeee>
+__device__ bool fold_bundle(const ScanParams& P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
+                            const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t i,
+                            float4* stage_warp, F3* out_mp, float* out_mw, uint32_t* out_col) {
+  const int lane = threadIdx.x & 31;
+  const KeyT key = keys[i];
+  const bool clearing = key_is_clearing(P, (uint64_t)key);
+  float mw = 0.0f;
+  bool done = false;
+  bool suspect = false;
+  float state = 0.f;
+  const int role = lane < 7 ? lane : 7;  // lanes 7.. mirror a benign slot
+  const bool is_mean = lane < 3;
+  uint32_t j0 = i;
+  bool in;
+  F3 p = f3(0.f, 0.f, 0.f);
+  uint32_t col = 0u;
+  {
+    // key and point-index loads are issued together; only the point gather depends on them
+    const uint32_t jj = j0 + lane;
+    const bool inb = jj < P.n;
+    const KeyT kk = inb ? keys[jj] : (KeyT)~(KeyT)0;
+    const uint32_t idx = inb ? vals[jj] : 0u;
+    in = inb && kk == key;
+    if (in) {
+      p = load_point(xyz, idx);
+      col = load_color(rgba, idx);
+    }
+  }
+  while (!done) {
+    const int cnt = __popc(__ballot_sync(0xffffffffu, in));  // members form a prefix
+    const F3 pc = p;
+    const uint32_t colc = col;
+    const bool inc = in;
+    if (cnt == 32) {  // prefetch the next chunk while this one is folded
+      j0 += 32;
+      const uint32_t jj = j0 + lane;
+      const bool inb = jj < P.n;
+      const KeyT kk = inb ? keys[jj] : (KeyT)~(KeyT)0;
+      const uint32_t idx = inb ? vals[jj] : 0u;
+      in = inb && kk == key;
+      if (in) {
+        p = load_point(xyz, idx);
+        col = load_color(rgba, idx);
+      }
+    }
+    const float w = inc ? point_weight(pc.z, P.use_const_weight != 0) : 0.f;
+    // (1) the weight chain W <- W + w is the only part every member depends on.  Lane L needs
+    //     the W its member sees = mw + w_0 + ... + w_{L-1} added in list order (members below
+    //     kEpsilon are skipped, cc:391-393: adding +0.0f is the identity).
+    const float wl = (inc && !(w < VBX_EPS)) ? w : 0.f;
+    float wb = mw;
+#pragma unroll
+    for (int k = 0; k < 31; ++k) {
+      const float wk = __shfl_sync(0xffffffffu, wl, k);
+      if (k < lane) wb = fadd(wb, wk);
+    }
+    float mw_run = __shfl_sync(0xffffffffu, fadd(wb, wl), 31);
+    // (2) everything that does not depend on the running state, in parallel per lane, staged
+    //     per role as (A, B, C, D = RN(1/C))
+    const float tot = fadd(wb, w);
+    const F3 pw = scale3(pc, w);
+    float w1 = 0.f, w2 = 0.f, rtot = 1.f;
+    if (wl != 0.f) {
+      w1 = fdiv(wb, tot);  // blendTwoColors' normalised weights, core/common.h:112-113
+      w2 = fdiv(w, tot);
+      bool ok;
+      rtot = recip_for_exact_div(tot, &ok);
+      suspect |= !ok;
+    }
+    float4* st_row = stage_warp + lane * kStageStride;
+    __syncwarp();  // the previous chunk's readers are done
+    st_row[0] = make_float4(wb, pw.x, tot, rtot);
+    st_row[1] = make_float4(wb, pw.y, tot, rtot);
+    st_row[2] = make_float4(wb, pw.z, tot, rtot);
+    st_row[3] = make_float4(w1, fmul((float)(int)(colc & 0xffu), w2), 1.f, 1.f);
+    st_row[4] = make_float4(w1, fmul((float)(int)((colc >> 8) & 0xffu), w2), 1.f, 1.f);
+    st_row[5] = make_float4(w1, fmul((float)(int)((colc >> 16) & 0xffu), w2), 1.f, 1.f);
+    st_row[6] = make_float4(w1, fmul((float)(int)(colc >> 24), w2), 1.f, 1.f);
+    st_row[7] = make_float4(0.f, 1.f, 1.f, 1.f);
+    __syncwarp();
+    // (3) the dependent chain, in list order, over the members that carry weight
+    unsigned live = __ballot_sync(0xffffffffu, wl != 0.f);
+    const float4* st_col = stage_warp + role;
+    if (clearing && live) {  // "only take first point when clearing", cc:401-404
+      const int k = __ffs(live) - 1;
+      live = 1u << k;
+      mw_run = fadd(__shfl_sync(0xffffffffu, wb, k), __shfl_sync(0xffffffffu, w, k));
+      done = true;
+    }
+    if (live == 0xffffffffu) {
+      float4 cur = st_col[0];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float4 nxt = st_col[((k + 1) & 31) * kStageStride];
+        state = fold_step<kIeee>(state, cur, is_mean, &suspect);
+        cur = nxt;
+      }
+    } else {
+      for (unsigned m = live; m; m &= m - 1) {
+        state = fold_step<kIeee>(state, st_col[(__ffs(m) - 1) * kStageStride], is_mean, &suspect);
+      }
+    }
+    mw = mw_run;
+    if (cnt < 32) done = true;
+  }
+  *out_mp = f3(__shfl_sync(0xffffffffu, state, 0), __shfl_sync(0xffffffffu, state, 1),
+               __shfl_sync(0xffffffffu, state, 2));
+  *out_col = ((uint32_t)(int)__shfl_sync(0xffffffffu, state, 3) & 0xffu) |
+             (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 4) & 0xffu) << 8) |
+             (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 5) & 0xffu) << 16) |
+             (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 6) & 0xffu) << 24);
+  *out_mw = mw;
+  return __any_sync(0xffffffffu, suspect);
+}
+
+// One warp per bundle (integrateVoxel's merge, cc:384-407).
+template <typename KeyT>
+__global__ void __launch_bounds__(128)
+k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
+        const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ray_list,
+        float4* __restrict__ ray_p, uint2* __restrict__ ray_c, const ScanState* st) {
+  __shared__ float4 stage[4 * 32 * kStageStride];  // [warp in block][member][role]
+  const int lane = threadIdx.x & 31;
+  float4* stage_warp = stage + (threadIdx.x >> 5) * (32 * kStageStride);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_bundles = st->n_ray_list;
+  for (uint32_t b = warp; b < n_bundles; b += n_warps) {
+    const uint32_t i = ray_list[b];
+    F3 mp;
+    float mw;
+    uint32_t mcol;
+    if (fold_bundle<KeyT, false>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol)) {
+      fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol);
+    }
+    if (lane == 0) {
+      const F3 pg = transform(P.T, mp);
+      ray_p[i] = make_float4(pg.x, pg.y, pg.z, mw);
+      ray_c[i] = make_uint2(mcol, key_is_clearing(P, (uint64_t)keys[i]) ? 1u : 0u);
+    }
+  }
+}
+
 // binary search over the sorted point keys: is there a NORMAL bundle ending in this voxel?
 // (the voxel_map.find() of the anti-grazing test, cc:415-422)
-__device__ bool bundle_exists(const uint64_t* keys, uint32_t n, uint64_t key) {
+template <typename KeyT>
+__device__ bool bundle_exists(const KeyT* keys, uint32_t n, KeyT key) {
   uint32_t lo = 0, hi = n;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
@@ -171,54 +419,14 @@ __device__ bool bundle_exists(const uint64_t* keys, uint32_t n, uint64_t key) {
   return lo < n && keys[lo] == key;
 }
 
-struct RayJob {
-  F3 point_G;
-  float weight;
-  uint32_t color;
-  bool clearing;
-  uint64_t bundle_key;  // Merged: key of the bundle's own voxel (anti-grazing)
-};
-
-// Build ray i of this call, or return false when slot i casts nothing.
-__device__ bool make_ray(const ScanParams& P, uint32_t i, const float* xyz, const uint8_t* rgba,
-                         const uint32_t* order, const uint64_t* keys, const uint32_t* vals, RayJob* job) {
-  if (P.kind == VBX_MERGED) {
-    const uint64_t key = keys[i];
-    if (key == kInvalidPointKey) return false;
-    if (i > 0 && keys[i - 1] == key) return false;  // not the head of its bundle
-    const bool clearing = (key >> 63) != 0;
-    // integrateVoxel, cc:384-405: running weighted mean in the CAMERA frame, in list order
-    F3 mp = f3(0.f, 0.f, 0.f);
-    float mw = 0.0f;
-    uint32_t mcol = 0u;
-    for (uint32_t j = i; j < P.n && keys[j] == key; ++j) {
-      const uint32_t idx = vals[j];
-      const F3 p = load_point(xyz, idx);
-      const float w = point_weight(p.z, P.use_const_weight != 0);
-      if (w < VBX_EPS) continue;
-      mp = div3(add3(scale3(mp, mw), scale3(p, w)), fadd(mw, w));
-      mcol = blend_rgba(mcol, mw, load_color(rgba, idx), w);
-      mw = fadd(mw, w);
-      if (clearing) break;  // "only take first point when clearing"
-    }
-    job->point_G = transform(P.T, mp);
-    job->weight = mw;
-    job->color = mcol;
-    job->clearing = clearing;
-    job->bundle_key = key;
-    return true;
-  }
-  // Simple / Fast: one ray per valid point (integrateFunction, cc:269-305 / :488-553)
-  const uint32_t idx = point_order(P, order, i);
-  const F3 p = load_point(xyz, idx);
-  const int cls = classify_point(p, P.min_ray, P.max_ray, P.allow_clear != 0, P.freespace != 0);
-  if (cls == 0) return false;
-  job->point_G = transform(P.T, p);
-  job->weight = point_weight(p.z, P.use_const_weight != 0);
-  job->color = load_color(rgba, idx);
-  job->clearing = (cls == 2);
-  job->bundle_key = 0;
-  return true;
+template <typename KeyT>
+__device__ __forceinline__ bool grazing_skip(const ScanParams& P, const KeyT* keys, KeyT own, bool clearing,
+                                             int x, int y, int z) {
+  bool in_range;
+  const KeyT vkey = (KeyT)normal_key_of(P, x, y, z, &in_range);
+  if (!in_range) return false;
+  const KeyT own_normal = clearing ? (KeyT)~(KeyT)0 : own;
+  return (clearing || vkey != own_normal) && bundle_exists<KeyT>(keys, P.n, vkey);
 }
 
 // LongIndexHash, core/block_hash.h:52-64 (32-bit wrap of x + 17191 y + 17191^2 z)
@@ -233,37 +441,58 @@ __device__ __forceinline__ bool replace_hash(unsigned long long* set, uint32_t h
   return old != tag;
 }
 
+// One thread per ray: first DDA walk.  Merged rays come from k_merge's records through the
+// dense ray list; Simple / Fast build their ray from point slot i (integrateFunction,
+// cc:269-305 / :488-553).
+template <typename KeyT>
 __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__ xyz,
                              const uint8_t* __restrict__ rgba, const uint32_t* __restrict__ order,
-                             const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                             float4* __restrict__ ray_p, uint2* __restrict__ ray_c,
-                             uint32_t* __restrict__ cnt, unsigned long long* set_start,
-                             unsigned long long* set_observed, ScanState* st) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > P.n) return;
-  if (i == P.n) {
-    cnt[i] = 0;
-    return;
-  }
-  RayJob job;
-  if (!make_ray(P, i, xyz, rgba, order, keys, vals, &job)) {
-    cnt[i] = 0;
-    return;
-  }
-  if (P.kind == VBX_FAST) {
-    // start-voxel subsampling, cc:507-519
-    const I3 g = grid_index(job.point_G, P.start_inv);
-    if (!replace_hash(set_start, long_index_hash(g.x, g.y, g.z), P.set_epoch)) {
+                             const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
+                             float4* __restrict__ ray_p, uint2* __restrict__ ray_c, uint32_t* __restrict__ cnt,
+                             unsigned long long* set_start, unsigned long long* set_observed, ScanState* st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i;
+  F3 point_G;
+  bool clearing;
+  KeyT own = 0;
+  if (P.kind == VBX_MERGED) {
+    if (t >= st->n_ray_list) return;
+    i = ray_list[t];
+    const float4 rp = ray_p[i];
+    point_G = f3(rp.x, rp.y, rp.z);
+    clearing = (ray_c[i].y & 1u) != 0;
+    own = keys[i];
+  } else {
+    i = t;
+    if (i > P.n) return;
+    if (i == P.n) {
       cnt[i] = 0;
       return;
     }
+    const uint32_t idx = point_order(P, order, i);
+    const F3 p = load_point(xyz, idx);
+    const int cls = classify_point(p, P.min_ray, P.max_ray, P.allow_clear != 0, P.freespace != 0);
+    if (cls == 0) {
+      cnt[i] = 0;
+      return;
+    }
+    point_G = transform(P.T, p);
+    clearing = (cls == 2);
+    if (P.kind == VBX_FAST) {
+      // start-voxel subsampling, cc:507-519
+      const I3 g = grid_index(point_G, P.start_inv);
+      if (!replace_hash(set_start, long_index_hash(g.x, g.y, g.z), P.set_epoch)) {
+        cnt[i] = 0;
+        return;
+      }
+    }
+    ray_p[i] = make_float4(point_G.x, point_G.y, point_G.z, point_weight(p.z, P.use_const_weight != 0));
+    ray_c[i] = make_uint2(load_color(rgba, idx), clearing ? 1u : 0u);
   }
-  ray_p[i] = make_float4(job.point_G.x, job.point_G.y, job.point_G.z, job.weight);
-  ray_c[i] = make_uint2(job.color, job.clearing ? 1u : 0u);
-  atomicAdd(job.clearing ? &st->n_clear_rays : &st->n_rays, 1u);
+  atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
 
   Dda d;
-  dda_setup(d, P.origin, job.point_G, job.clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
+  dda_setup(d, P.origin, point_G, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
             P.kind != VBX_FAST);
   uint32_t count = 0;
   int collisions = 0;
@@ -271,8 +500,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   const int lim = (kCoordBias - 1) << P.L;
   for (unsigned int s = 0; s <= d.len; ++s, dda_advance(d)) {
     if (P.kind == VBX_MERGED && P.anti_grazing) {
-      const uint64_t vkey = pack3(d.cx, d.cy, d.cz);
-      if ((job.clearing || vkey != (job.bundle_key & ~(1ull << 63))) && bundle_exists(keys, P.n, vkey)) continue;
+      if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
     }
     if (P.kind == VBX_FAST) {
       // cc:531-543: stop once the ray runs through voxels other rays already observed
@@ -325,12 +553,21 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ off, uint32_t 
   }
 }
 
-__global__ void k_rays_emit(ScanParams P, Tables tab, const uint64_t* __restrict__ keys,
-                            const float4* __restrict__ ray_p, const uint2* __restrict__ ray_c,
-                            const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
-                            uint32_t* __restrict__ ckeys, uint32_t* __restrict__ cvals) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n) return;
+template <typename KeyT>
+__global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ keys,
+                            const uint32_t* __restrict__ ray_list, const float4* __restrict__ ray_p,
+                            const uint2* __restrict__ ray_c, const uint32_t* __restrict__ cnt,
+                            const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
+                            uint32_t* __restrict__ cvals, const ScanState* st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i;
+  if (P.kind == VBX_MERGED) {
+    if (t >= st->n_ray_list) return;
+    i = ray_list[t];
+  } else {
+    i = t;
+    if (i >= P.n) return;
+  }
   const uint32_t c = cnt[i];
   if (c == 0) return;
   const float4 rp = ray_p[i];
@@ -339,7 +576,7 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const uint64_t* __restrict
   Dda d;
   dda_setup(d, P.origin, point_G, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
             P.kind != VBX_FAST);
-  const uint64_t own = (P.kind == VBX_MERGED) ? (keys[i] & ~(1ull << 63)) : 0ull;
+  const KeyT own = (P.kind == VBX_MERGED) ? keys[i] : (KeyT)0;
   uint32_t emitted = 0;
   int lbx = INT_MIN, lby = INT_MIN, lbz = INT_MIN;
   uint32_t rank = 0;
@@ -347,8 +584,7 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const uint64_t* __restrict
   const int mask = (1 << P.L) - 1;
   for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
     if (P.kind == VBX_MERGED && P.anti_grazing) {
-      const uint64_t vkey = pack3(d.cx, d.cy, d.cz);
-      if ((clearing || vkey != own) && bundle_exists(keys, P.n, vkey)) continue;
+      if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
     }
     const int bx = d.cx >> P.L, by = d.cy >> P.L, bz = d.cz >> P.L;
     if (bx != lbx || by != lby || bz != lbz) {
@@ -367,40 +603,181 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const uint64_t* __restrict
   }
 }
 
-// One thread per run of equal voxel ids: the run is that voxel's updates in ray-rank
-// order; apply them one after the other exactly like updateTsdfVoxel (cc:150-209).
-__global__ void k_apply(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
-                        const uint32_t* __restrict__ cvals, unsigned long long total,
-                        const float4* __restrict__ ray_p, const uint2* __restrict__ ray_c, ScanState* st) {
+// ----------------------------------------------------------------------- apply
+struct VoxelRef {
+  TsdfVoxel* ptr;
+  F3 vo;  // voxel centre - sensor origin
+};
+
+__device__ __forceinline__ VoxelRef locate_voxel(const ScanParams& P, const Tables& tab, uint32_t key) {
+  const uint32_t rank = key >> (3 * P.L);
+  const uint32_t lin = key & ((1u << (3 * P.L)) - 1u);
+  const uint32_t hp = tab.touched_list[rank];
+  int bx, by, bz;
+  unpack3(tab.hkeys[hp], &bx, &by, &bz);
+  const int mask = (1 << P.L) - 1;
+  const int vx = (bx << P.L) + (int)(lin & mask);
+  const int vy = (by << P.L) + (int)((lin >> P.L) & mask);
+  const int vz = (bz << P.L) + (int)(lin >> (2 * P.L));
+  VoxelRef r;
+  r.ptr = tab.tsdf + (((size_t)tab.hslot[hp]) << (3 * P.L)) + lin;
+  const F3 c = f3(center_coord(vx, P.voxel_size), center_coord(vy, P.voxel_size), center_coord(vz, P.voxel_size));
+  r.vo = sub3(c, P.origin);
+  return r;
+}
+
+// computeDistance (cc:216-228) with the voxel side hoisted: sdf = |p-o| - (c-o).(p-o)/|p-o|
+__device__ __forceinline__ float sdf_from(const ScanParams& P, F3 vo, float4 rp) {
+  const F3 po = sub3(f3(rp.x, rp.y, rp.z), P.origin);
+  const float dist_G = norm3(po);
+  return fsub(dist_G, fdiv(dot3(vo, po), dist_G));
+}
+
+// One thread per run head applies the first kShortRun updates of its voxel in order
+// (updateTsdfVoxel, cc:150-209); longer runs are queued for k_apply_long.
+__global__ void k_apply_short(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
+                              const uint32_t* __restrict__ cvals, unsigned long long total,
+                              const float4* __restrict__ ray_p, const uint2* __restrict__ ray_c,
+                              unsigned long long* __restrict__ long_list, ScanState* st) {
   const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool head = false;
   if (e < total) {
     const uint32_t key = ckeys[e];
     head = (e == 0) || (ckeys[e - 1] != key);
     if (head) {
-      const uint32_t rank = key >> (3 * P.L);
-      const uint32_t lin = key & ((1u << (3 * P.L)) - 1u);
-      const uint32_t hp = tab.touched_list[rank];
-      int bx, by, bz;
-      unpack3(tab.hkeys[hp], &bx, &by, &bz);
-      const int mask = (1 << P.L) - 1;
-      const int vx = (bx << P.L) + (int)(lin & mask);
-      const int vy = (by << P.L) + (int)((lin >> P.L) & mask);
-      const int vz = (bz << P.L) + (int)(lin >> (2 * P.L));
-      TsdfVoxel* vp = tab.tsdf + (((size_t)tab.hslot[hp]) << (3 * P.L)) + lin;
-      TsdfVoxel v = *vp;
-      for (unsigned long long j = e; j < total && ckeys[j] == key; ++j) {
+      const VoxelRef vr = locate_voxel(P, tab, key);
+      TsdfVoxel v = *vr.ptr;
+      unsigned long long j = e;
+      for (int k = 0; k < kShortRun && j < total && ckeys[j] == key; ++k, ++j) {
         const uint32_t r = cvals[j];
         const float4 rp = ray_p[r];
-        const float sdf = ray_sdf(P.origin, f3(rp.x, rp.y, rp.z), vx, vy, vz, P.voxel_size);
-        const float w = update_weight(sdf, rp.w, P.up);
-        apply_update(v, sdf, w, ray_c[r].x, P.up);
+        const float sdf = sdf_from(P, vr.vo, rp);
+        apply_update(v, sdf, update_weight(sdf, rp.w, P.up), ray_c[r].x, P.up);
       }
-      *vp = v;
+      *vr.ptr = v;
+      if (j < total && ckeys[j] == key) {
+        const uint32_t q = atomicAdd(&st->n_long, 1u);
+        long_list[q] = j;
+      }
     }
   }
   const unsigned b = __ballot_sync(0xffffffffu, head);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->n_voxels, (uint32_t)__popc(b));
+}
+
+// One warp per long run.  32 updates are prefetched per step (records coalesced, ray data
+// gathered, sdf and weight computed in parallel); the read-modify-write chain is then
+// evaluated in order.  Free space far in front of any surface is the common long run:
+// there every update has sdf >= T and the voxel already sits at +T, so after computing the
+// exact sequential weight chain each lane checks that ITS update maps +T to +T; if all do,
+// the sequential result is (+T, chained weight) without walking the distance chain.
+__global__ void k_apply_long(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
+                             const uint32_t* __restrict__ cvals, unsigned long long total,
+                             const float4* __restrict__ ray_p, const uint2* __restrict__ ray_c,
+                             const unsigned long long* __restrict__ long_list, const ScanState* st) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_long = st->n_long;
+  const float T = P.up.trunc;
+  for (uint32_t q = warp; q < n_long; q += n_warps) {
+    unsigned long long j0 = long_list[q];
+    const uint32_t key = ckeys[j0];
+    const VoxelRef vr = locate_voxel(P, tab, key);
+    TsdfVoxel v = *vr.ptr;
+    bool done = false;
+    // Three-stage software pipeline over 32-record chunks (one warp has nothing else to
+    // hide a record -> ray-data load chain behind): while chunk c is applied, the ray data
+    // of chunk c+1 and the records of chunk c+2 are in flight.
+    bool in_a, in_b;
+    uint32_t r_a = 0u;
+    float4 rp_b = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t col_b = 0u;
+    {
+      unsigned long long j = j0 + lane;
+      in_a = j < total && ckeys[j] == key;
+      r_a = j < total ? cvals[j] : 0u;
+      in_b = in_a;
+      if (in_b) {
+        rp_b = ray_p[r_a];
+        col_b = ray_c[r_a].x;
+      }
+      j += 32;
+      in_a = j < total && ckeys[j] == key;
+      r_a = j < total ? cvals[j] : 0u;
+    }
+    while (!done) {
+      const bool in = in_b;
+      const float4 rp = rp_b;
+      const uint32_t col = col_b;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+      if (cnt == 32) {
+        in_b = in_a;
+        if (in_b) {
+          rp_b = ray_p[r_a];
+          col_b = ray_c[r_a].x;
+        }
+        const unsigned long long j = j0 + 64 + lane;
+        in_a = j < total && ckeys[j] == key;
+        r_a = j < total ? cvals[j] : 0u;
+      }
+      float sdf = 0.f, w = 0.f;
+      if (in) {
+        sdf = sdf_from(P, vr.vo, rp);
+        w = update_weight(sdf, rp.w, P.up);
+      }
+      const bool far_free = !in || sdf >= T;
+      bool fast = __all_sync(0xffffffffu, far_free) && v.distance == T;
+      float w_end = v.weight;
+      if (fast) {
+        // exact sequential weight chain: W <- min(W + w, max_weight) unless W + w < 1e-6
+        float my_before = 0.f;
+        float wsum = in ? w : 0.f;  // any-order sum, used only as a bound
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        if (v.weight >= VBX_EPS && (v.weight + wsum) * 1.0001f < P.up.max_weight) {
+          // neither the 1e-6 guard nor the max_weight clamp can fire in this chunk: the
+          // chain is plain in-order addition; lane L forms its own prefix
+          const float wl = in ? w : 0.f;
+          my_before = v.weight;
+#pragma unroll
+          for (int k = 0; k < 31; ++k) {
+            const float wk = __shfl_sync(0xffffffffu, wl, k);
+            if (k < lane) my_before = fadd(my_before, wk);
+          }
+          w_end = __shfl_sync(0xffffffffu, fadd(my_before, wl), 31);
+        } else {
+          for (int k = 0; k < cnt; ++k) {
+            const float wk = __shfl_sync(0xffffffffu, w, k);
+            if (lane == k) my_before = w_end;
+            const float nw = fadd(w_end, wk);
+            w_end = (nw < VBX_EPS) ? w_end : ((nw < P.up.max_weight) ? nw : P.up.max_weight);
+          }
+        }
+        bool keeps_T = true;
+        if (in) {
+          const float nw = fadd(my_before, w);
+          if (!(nw < VBX_EPS)) {
+            const float ns = fdiv(fadd(fmul(sdf, w), fmul(T, my_before)), nw);
+            const float clamped = (ns > 0.0f) ? ((ns < T) ? ns : T) : ((-T < ns) ? ns : -T);
+            keeps_T = (clamped == T);
+          }
+        }
+        fast = __all_sync(0xffffffffu, keeps_T);
+      }
+      if (fast) {
+        v.weight = w_end;
+      } else {
+        for (int k = 0; k < cnt; ++k) {
+          apply_update(v, __shfl_sync(0xffffffffu, sdf, k), __shfl_sync(0xffffffffu, w, k),
+                       __shfl_sync(0xffffffffu, col, k), P.up);
+        }
+      }
+      j0 += 32;
+      if (cnt < 32) done = true;
+    }
+    if (lane == 0) *vr.ptr = v;
+  }
 }
 
 // --------------------------------------------------------------------- host side
@@ -416,6 +793,7 @@ static int bits_for(uint64_t v) {
 }
 
 static int check_state_errors(vbx_ctx* c, uint32_t err) {
+  err &= ~kNeedWideKeys;
   if (!err) return VBX_OK;
   std::string m = "device reported:";
   if (err & kErrPoolFull) m += " block pool full (raise vbx_engine_options.max_blocks);";
@@ -423,6 +801,107 @@ static int check_state_errors(vbx_ctx* c, uint32_t err) {
   if (err & kErrCoordRange) m += " voxel coordinate outside +-2^20 blocks;";
   if (err & kErrUpdatesFull) m += " ray-voxel updates exceed max_updates_per_pass;";
   return fail(c, VBX_E_CAPACITY, m);
+}
+
+namespace {
+struct Marks {
+  vbx_ctx* c;
+  cudaStream_t s;
+  int n = 0;
+  int stage[20];
+  void begin() {
+    if (c->profiling) cudaEventRecord(c->sev[0], s);
+  }
+  void mark(int stage_just_finished) {
+    if (c->profiling && n < 19) {
+      cudaEventRecord(c->sev[n + 1], s);
+      stage[n++] = stage_just_finished;
+    }
+  }
+  void collect() {
+    for (int m = 0; m < n; ++m) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->sev[m], c->sev[m + 1]) == cudaSuccess) {
+        c->stage_ms[stage[m]] += ms;
+        c->stage_calls[stage[m]] += 1;
+      }
+    }
+  }
+};
+}  // namespace
+
+// Stages up to and including k_assign: everything that decides WHICH voxels are updated.
+template <typename KeyT>
+static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8_t* d_rgba, const uint32_t* order,
+                      Marks& mk, uint64_t* launches, const KeyT** keys_out) {
+  cudaStream_t s = c->stream;
+  const uint32_t n = P.n;
+  const int TB = 256;
+  const KeyT* keys = nullptr;
+  const uint32_t* vals = nullptr;
+  if (P.kind == VBX_MERGED) {
+    KeyT* k0 = reinterpret_cast<KeyT*>(c->pkeys[0]);
+    KeyT* k1 = reinterpret_cast<KeyT*>(c->pkeys[1]);
+    k_point_keys<KeyT><<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, k0, c->pvals[0], c->d_state);
+    mk.mark(0);
+    cub::DoubleBuffer<KeyT> kb(k0, k1);
+    cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
+    size_t tmp = c->cub_tmp_bytes;
+    const int end_bit = P.wide_keys ? 64 : 3 * P.key_bits + 1;
+    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, end_bit, s));
+    keys = kb.Current();
+    vals = vb.Current();
+    mk.mark(1);
+    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, keys, c->ray_list, c->cnt, c->d_state);
+    k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_c,
+                                           c->d_state);
+    mk.mark(8);
+    *launches += 5 + (end_bit + 7) / 8;
+    // the bundle count is only known on the device: launch for the worst case (every
+    // point its own bundle); surplus threads exit on the first load
+    k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->ray_list,
+                                                         c->ray_p, c->ray_c, c->cnt, c->set_start,
+                                                         c->set_observed, c->d_state);
+  } else {
+    k_rays_count<KeyT><<<grid_for((uint64_t)n + 1, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys,
+                                                                       c->ray_list, c->ray_p, c->ray_c, c->cnt,
+                                                                       c->set_start, c->set_observed, c->d_state);
+  }
+  mk.mark(2);
+  {
+    size_t tmp = c->cub_tmp_bytes;
+    VBX_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp, tmp, c->cnt, c->off, (int)(n + 1), s));
+  }
+  mk.mark(3);
+  k_assign<<<grid_for(c->tab.max_blocks, TB), TB, 0, s>>>(c->tab, c->off, n, c->n_blocks, c->max_updates,
+                                                          c->d_state);
+  mk.mark(4);
+  *launches += 4;
+  *keys_out = keys;
+  return VBX_OK;
+}
+
+template <typename KeyT>
+static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned long long K, uint32_t n_touched,
+                     Marks& mk, uint64_t* launches) {
+  cudaStream_t s = c->stream;
+  const uint32_t n = P.n;
+  k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->ray_c, c->cnt,
+                                                      c->off, c->ckeys[0], c->cvals[0], c->d_state);
+  mk.mark(5);
+  cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
+  cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
+  size_t tmp = c->cub_tmp_bytes;
+  const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
+  VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
+  mk.mark(6);
+  k_apply_short<<<grid_for(K, 256), 256, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_p, c->ray_c,
+                                                  c->long_list, c->d_state);
+  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_p, c->ray_c,
+                                       c->long_list, c->d_state);
+  mk.mark(7);
+  *launches += 4 + (key_bits + 7) / 8;
+  return VBX_OK;
 }
 
 int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
@@ -436,6 +915,7 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   uint64_t launches = 0;
 
   ScanParams P;
+  std::memset(&P, 0, sizeof(P));
   P.T.w = q[0];
   P.T.x = q[1];
   P.T.y = q[2];
@@ -476,6 +956,18 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     }
   }
   P.set_epoch = c->set_epoch;
+  // compact bundle keys: every non-clearing point lies within max_ray_length of the sensor,
+  // so its voxel is within key_radius voxels of the origin's voxel on every axis
+  {
+    const I3 ov = grid_index(P.origin, P.voxel_size_inv);
+    P.ovx = ov.x;
+    P.ovy = ov.y;
+    P.ovz = ov.z;
+    const double r = (double)cfg.max_ray_length_m * (double)c->voxel_size_inv;
+    P.key_radius = (r < 2.0e5) ? (int)std::ceil(r) + 3 : (1 << 20);
+    P.key_bits = bits_for((uint64_t)(2 * (int64_t)P.key_radius));
+    P.wide_keys = (3 * P.key_bits + 1 > 32) ? 1 : 0;
+  }
 
   VBX_CUDA(c, cudaEventRecord(c->ev0, s));
   VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
@@ -486,15 +978,10 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     return VBX_OK;
   }
   const int TB = 256;
-  int n_marks = 0;
-  int mark_stage[20];
-  auto mark = [&](int stage_just_finished) {
-    if (c->profiling && n_marks < 19) {
-      cudaEventRecord(c->sev[n_marks + 1], s);
-      mark_stage[n_marks++] = stage_just_finished;
-    }
-  };
-  if (c->profiling) cudaEventRecord(c->sev[0], s);
+  Marks mk;
+  mk.c = c;
+  mk.s = s;
+  mk.begin();
 
   const uint32_t* order = nullptr;
   if (cfg.integration_order_mode == 1) {
@@ -506,78 +993,56 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, 64, s));
     VBX_CUDA(c, cudaMemcpyAsync(c->order, vb.Current(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     order = c->order;
-    launches += 10;
+    launches += 11;
   }
 
-  const uint64_t* keys = nullptr;
-  const uint32_t* vals = nullptr;
-  if (kind == VBX_MERGED) {
-    k_point_keys<<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, c->pkeys[0], c->pvals[0], c->d_state);
-    mark(0);
-    cub::DoubleBuffer<uint64_t> kb(c->pkeys[0], c->pkeys[1]);
-    cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
-    size_t tmp = c->cub_tmp_bytes;
-    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, 64, s));
-    keys = kb.Current();
-    vals = vb.Current();
-    launches += 10;
-    mark(1);
+  uint32_t new_blocks_first_attempt = 0;
+  const uint32_t* keys32 = nullptr;
+  const uint64_t* keys64 = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (P.wide_keys) {
+      if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
+    } else {
+      if (int rc = front_half<uint32_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys32)) return rc;
+    }
+    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+    c->n_blocks = c->h_state->n_blocks;
+    if (!(c->h_state->error & kNeedWideKeys)) break;
+    // A clearing point landed outside the compact key range.  The rays cast so far are
+    // a correct SUBSET of the call's rays (block allocation is monotone), so keep the
+    // blocks they created and redo the call's front half with full-width keys under
+    // a fresh call id (touch marks restart).
+    new_blocks_first_attempt = c->h_state->n_new;
+    VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+    c->epoch += 1;
+    P.epoch = c->epoch;
+    P.wide_keys = 1;
   }
-
-  k_rays_count<<<grid_for((uint64_t)n + 1, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, vals,
-                                                                c->ray_p, c->ray_c, c->cnt, c->set_start,
-                                                                c->set_observed, c->d_state);
-  mark(2);
-  {
-    size_t tmp = c->cub_tmp_bytes;
-    VBX_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp, tmp, c->cnt, c->off, (int)(n + 1), s));
-  }
-  mark(3);
-  k_assign<<<grid_for(c->tab.max_blocks, TB), TB, 0, s>>>(c->tab, c->off, n, c->n_blocks, c->max_updates,
-                                                          c->d_state);
-  mark(4);
-  launches += 4;
-  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-  VBX_CUDA(c, cudaStreamSynchronize(s));
-  if (int rc = check_state_errors(c, c->h_state->error)) return rc;
   const unsigned long long K = c->h_state->total_updates;
   const uint32_t n_touched = c->h_state->n_touched;
-  c->n_blocks = c->h_state->n_blocks;
 
   if (K > 0) {
-    k_rays_emit<<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_p, c->ray_c, c->cnt, c->off,
-                                                  c->ckeys[0], c->cvals[0]);
-    mark(5);
-    cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
-    cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
-    size_t tmp = c->cub_tmp_bytes;
-    const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
-    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
-    mark(6);
-    k_apply<<<grid_for(K, TB), TB, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_p, c->ray_c,
-                                           c->d_state);
-    mark(7);
-    launches += 3 + (key_bits + 7) / 8;
+    if (P.wide_keys) {
+      if (int rc = back_half<uint64_t>(c, P, keys64, K, n_touched, mk, &launches)) return rc;
+    } else {
+      if (int rc = back_half<uint32_t>(c, P, keys32, K, n_touched, mk, &launches)) return rc;
+    }
   }
   VBX_CUDA(c, cudaEventRecord(c->ev1, s));
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   VBX_CUDA(c, cudaGetLastError());
   VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-  for (int m = 0; m < n_marks; ++m) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->sev[m], c->sev[m + 1]) == cudaSuccess) {
-      c->stage_ms[mark_stage[m]] += ms;
-      c->stage_calls[mark_stage[m]] += 1;
-    }
-  }
+  mk.collect();
   c->launches += launches;
   c->counters[0] = c->h_state->n_rays;
   c->counters[1] = c->h_state->n_clear_rays;
   c->counters[2] = K;
   c->counters[3] = c->h_state->n_voxels;
   c->counters[4] = n_touched;
-  c->counters[5] = c->h_state->n_new;
+  c->counters[5] = (uint64_t)c->h_state->n_new + new_blocks_first_attempt;
   c->counters[6] = (kind == VBX_MERGED) ? c->h_state->n_valid_points
                                         : (uint64_t)c->h_state->n_rays + c->h_state->n_clear_rays;
   c->counters[7] = launches;
