@@ -189,6 +189,13 @@ VBX_API int vbx_sync(vbx_ctx* ctx);
  *         [8] bundle heads + merge
  *   ESDF  [9] propagate   [10] raise      [11] lower wavefront              [12..15] reserved
  * calls[i] counts how many times stage i ran. */
+/* Page-locked host buffers for point clouds: vbx_tsdf_integrate copies asynchronously (and at
+ * full PCIe rate) only from memory that is page-locked; anything else is staged by the driver.
+ * vbx_host_alloc / vbx_host_free wrap cudaHostAlloc / cudaFreeHost; vbx_host_copy_ms times one
+ * host->device copy of `bytes` from `src` into the context's staging buffer (diagnostic). */
+VBX_API int vbx_host_alloc(vbx_ctx* ctx, size_t bytes, void** out);
+VBX_API int vbx_host_free(vbx_ctx* ctx, void* p);
+VBX_API int vbx_host_copy_ms(vbx_ctx* ctx, const void* src, size_t bytes, float* ms);
 VBX_API int vbx_timer_start(vbx_ctx* ctx);
 VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms);
 VBX_API int vbx_set_stage_profiling(vbx_ctx* ctx, int enabled);

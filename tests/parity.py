@@ -42,3 +42,36 @@ def compare_tsdf(layer, omap, dist_floor: float = None) -> Dict:
     })
     rep["max_rel_err"] = max(rep["max_rel_err_distance"], rep["max_rel_err_weight"])
     return rep
+
+
+def compare_esdf(layer, omap, max_distance: float) -> Dict:
+    """GPU ESDF Layer against the oracle's ESDF layer (layer id 1)."""
+    gi = layer.getAllAllocatedBlocks()
+    oi = omap.block_indices(1)
+    rep = {"gpu_blocks": int(len(gi)), "oracle_blocks": int(len(oi)),
+           "blocks_equal": gi.shape == oi.shape and bool((gi == oi).all())}
+    if not rep["blocks_equal"]:
+        return rep
+    gv, gupd = layer.getBlocks(gi)
+    ov = np.stack([omap.block(i, 1)[0] for i in oi]) if len(oi) else gv
+    oupd = np.array([omap.block(i, 1)[1] for i in oi], dtype=np.uint8)
+    obs = ov["observed"] != 0
+    d_g, d_o = gv["distance"][obs].astype(np.float64), ov["distance"][obs].astype(np.float64)
+    err = np.abs(d_g - d_o)
+    rel = err / np.maximum(np.abs(d_o), 1e-3 * layer.voxel_size())
+    rep.update({
+        "voxels_observed": int(obs.sum()),
+        "observed_equal": bool(((gv["observed"] != 0) == obs).all()),
+        "fixed_equal": bool((gv["fixed"][obs] == ov["fixed"][obs]).all()),
+        "hallucinated_equal": bool((gv["hallucinated"] == ov["hallucinated"]).all()),
+        "in_queue_gpu": int((gv["in_queue"] != 0).sum()), "in_queue_oracle": int((ov["in_queue"] != 0).sum()),
+        "n_bit_exact": int((gv["distance"][obs] == ov["distance"][obs]).sum()),
+        "n_over_1e-4": int((rel > 1e-4).sum()),
+        "max_rel_err": float(rel.max()) if rel.size else 0.0,
+        "max_abs_err": float(err.max()) if err.size else 0.0,
+        "rmse": float(np.sqrt(np.mean(err ** 2))) if err.size else 0.0,
+        "parent_mismatch": int((gv["parent"][obs] != ov["parent"][obs]).any(axis=-1).sum()),
+        "updated_equal": bool((gupd == oupd).all()),
+        "flag_bytes_clean": bool((gv["in_queue"] <= 1).all() and (gv["observed"] <= 1).all()),
+    })
+    return rep

@@ -1,0 +1,89 @@
+"""-m gpu parity: the device ESDF wavefront against the CPU oracle."""
+import numpy as np
+import pytest
+
+import voxblox_b200 as vb
+from oracle import pyoracle as po
+from tests.parity import compare_esdf, compare_tsdf
+from voxblox_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(voxel_size, trunc, ekw):
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=trunc, integrator_threads=1)
+    tsdf = vb.Layer(voxel_size, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, tsdf)
+    esdf = vb.Layer(voxel_size, 16, voxel_type="esdf")
+    eint = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(**ekw), tsdf, esdf)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=trunc), voxel_size, 16)
+    omap.esdf_create(po.EsdfConfig(**ekw))
+    return tsdf, integ, esdf, eint, omap
+
+
+# the reference's own ESDF test configuration (test_sdf_integrators.cc:196-203)
+EKW = dict(max_distance_m=4.0, default_distance_m=4.0, min_distance_m=0.2, min_diff_m=0.0, multi_queue=1)
+
+
+def test_esdf_batch_matches_oracle():
+    scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
+    tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
+    for s in scans:
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    assert compare_tsdf(tsdf, omap)["max_rel_err"] == 0.0
+    eint.updateFromTsdfLayerBatch()
+    omap.esdf_update(batch=True)
+    rep = compare_esdf(esdf, omap, 4.0)
+    print(rep, eint.counters())
+    assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
+    assert rep["flag_bytes_clean"] and rep["in_queue_gpu"] == 0, rep
+    # Same-sign propagation converges to an order-independent fixed point (bit-exact); where a
+    # free voxel touches a voxel of the opposite sign the reference ASSIGNS sign*dist in queue
+    # order (esdf_integrator.cc:458-488) and no parallel order can reproduce it -- bound it.
+    assert rep["n_bit_exact"] >= 0.93 * rep["voxels_observed"], rep
+    assert rep["rmse"] < 0.1 * 0.1, rep
+    assert rep["max_abs_err"] <= 2 * 0.1 * 3 ** 0.5, rep
+
+
+def _wall_scans():
+    """A wall seen from three poses: no thin structures, so no opposite-sign neighbours."""
+    dirs = scenes.pinhole_dirs(160, 120, 131.25, 131.25, 80.0, 60.0)
+    prims = [scenes.Plane((0.0, 0.0, 1.0), 3.0)]
+    out = []
+    for k in range(3):
+        q = scenes.quat_from_rpy(0.013 + 0.05 * k, -0.021 - 0.04 * k, 0.017)
+        t = np.array([0.013 + 0.3 * k, 0.021 - 0.2 * k, 0.017 + 0.1 * k])
+        out.append(scenes.render(prims, dirs, q, t))
+    return out
+
+
+def test_esdf_batch_exact_without_sign_conflicts():
+    tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
+    for s in _wall_scans():
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    eint.updateFromTsdfLayerBatch()
+    omap.esdf_update(batch=True)
+    rep = compare_esdf(esdf, omap, 4.0)
+    print(rep, eint.counters())
+    assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
+    assert rep["n_over_1e-4"] <= 0.002 * rep["voxels_observed"], rep
+
+
+def test_esdf_incremental_tracks_oracle():
+    scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
+    tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
+    for s in scans:
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        eint.updateFromTsdfLayer(True)
+        omap.esdf_update(batch=False, clear_updated_flag=True)
+        rep = compare_esdf(esdf, omap, 4.0)
+        print(rep, eint.counters())
+        assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
+    assert len(tsdf.getAllUpdatedBlocks(2)) == 0  # kEsdf bits were cleared
+    frac_bad = rep["n_over_1e-4"] / max(1, rep["voxels_observed"])
+    # the reference's own incremental-vs-batch criterion is statistical (test_sdf_integrators.cc:261-270)
+    assert rep["rmse"] < 4.0 * 0.1, rep
+    assert frac_bad < 0.06, rep  # same order-dependent sign-conflict voxels as in the batch test

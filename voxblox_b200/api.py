@@ -111,7 +111,8 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_last_device_ms", "vbx_num_blocks", "vbx_list_blocks", "vbx_download_blocks",
            "vbx_upload_blocks", "vbx_remove_blocks", "vbx_clear", "vbx_clear_updated",
            "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync",
-           "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms"]
+           "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
+           "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms"]
 
 _lib = None
 
@@ -166,6 +167,12 @@ def load_library():
     lib.vbx_esdf_update.argtypes = [vp, i32, i32]
     lib.vbx_sync.restype = i32
     lib.vbx_sync.argtypes = [vp]
+    lib.vbx_host_alloc.restype = i32
+    lib.vbx_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.vbx_host_free.restype = i32
+    lib.vbx_host_free.argtypes = [vp, vp]
+    lib.vbx_host_copy_ms.restype = i32
+    lib.vbx_host_copy_ms.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_float)]
     lib.vbx_timer_start.restype = i32
     lib.vbx_timer_start.argtypes = [vp]
     lib.vbx_timer_stop_ms.restype = i32
@@ -312,6 +319,26 @@ class Layer:
         ctx = self._bound()
         ms = C.c_float(0)
         ctx.check(ctx.lib.vbx_timer_stop_ms(ctx.handle, C.byref(ms)), "vbx_timer_stop_ms")
+        return float(ms.value)
+
+    def hostBuffer(self, shape, dtype) -> np.ndarray:
+        """A page-locked numpy array (cudaHostAlloc) for clouds handed to integratePointCloud."""
+        ctx = self._bound()
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        ptr = C.c_void_p()
+        ctx.check(ctx.lib.vbx_host_alloc(ctx.handle, max(nbytes, 1), C.byref(ptr)), "vbx_host_alloc")
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        ctx._host_allocs = getattr(ctx, "_host_allocs", [])
+        ctx._host_allocs.append(ptr)
+        return arr
+
+    def hostCopyMs(self, arr: np.ndarray) -> float:
+        ctx = self._bound()
+        ms = C.c_float(0)
+        a = np.ascontiguousarray(arr)
+        ctx.check(ctx.lib.vbx_host_copy_ms(ctx.handle, a.ctypes.data, a.nbytes, C.byref(ms)), "vbx_host_copy_ms")
         return float(ms.value)
 
     def setStageProfiling(self, enabled: bool):

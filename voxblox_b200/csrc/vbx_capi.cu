@@ -150,6 +150,7 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->long_list, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->ray_p, np));
   CK(dmalloc(&c->ray_c, np));
+  CK(dmalloc(&c->ray_a, np));
   CK(dmalloc(&c->cnt, np + 1));
   CK(dmalloc(&c->off, np + 1));
   c->cub_tmp_bytes = cub_temp_bytes(c->max_points, c->max_updates);
@@ -177,7 +178,7 @@ void vbx_destroy(vbx_ctx* c) {
                   c->d_rgba,      c->pkeys[0],   c->pkeys[1],    c->pvals[0],   c->pvals[1], c->ckeys[0],
                   c->ckeys[1],    c->cvals[0],   c->cvals[1],    c->order,      c->ray_p,    c->ray_c,
                   c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
-                  c->ray_list,    c->long_list};
+                  c->ray_list,    c->long_list,  c->ray_a};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }
@@ -233,6 +234,31 @@ int vbx_esdf_get_counters(const vbx_ctx* c, uint64_t out[16]) {
 int vbx_last_device_ms(const vbx_ctx* c, float* ms) {
   if (!c || !ms) return VBX_E_INVALID;
   *ms = c->last_ms;
+  return VBX_OK;
+}
+
+int vbx_host_alloc(vbx_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_CUDA(c, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return VBX_OK;
+}
+
+int vbx_host_free(vbx_ctx* c, void* p) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaFreeHost(p));
+  return VBX_OK;
+}
+
+int vbx_host_copy_ms(vbx_ctx* c, const void* src, size_t bytes, float* ms) {
+  if (!c || !src || !ms) return VBX_E_INVALID;
+  if (bytes > (size_t)c->max_points * 12) return fail(c, VBX_E_CAPACITY, "copy larger than the staging buffer");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_CUDA(c, cudaEventRecord(c->tev0, c->stream));
+  VBX_CUDA(c, cudaMemcpyAsync(c->d_xyz, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  VBX_CUDA(c, cudaEventRecord(c->tev1, c->stream));
+  VBX_CUDA(c, cudaEventSynchronize(c->tev1));
+  VBX_CUDA(c, cudaEventElapsedTime(ms, c->tev0, c->tev1));
   return VBX_OK;
 }
 

@@ -49,6 +49,8 @@ struct ScanState {
   uint32_t esdf_counts[8];
   uint32_t frontier_n[2];
   uint32_t raise_n[2];
+  uint32_t seed_n;           // ESDF: new free voxels waiting for updateVoxelFromNeighbors
+  uint32_t lowered_n;        // ESDF: voxels lowered by the wavefront
   uint32_t n_ray_list;       // bundle heads (Merged)
   uint32_t n_long;           // voxel runs handed to k_apply_long
 };
@@ -113,8 +115,9 @@ struct vbx_ctx {
   uint32_t* order = nullptr;
   uint32_t* ray_list = nullptr;            // [max_points] dense list of bundle heads
   unsigned long long* long_list = nullptr; // [max_updates / 32 + 1] starts of long voxel runs
-  float4* ray_p = nullptr;    // point_G.xyz, weight
-  uint2* ray_c = nullptr;     // colour, flags
+  float4* ray_p = nullptr;    // point_G.xyz, flags (bit 0: clearing ray)
+  float4* ray_a = nullptr;    // point_G - origin, |point_G - origin|
+  uint2* ray_c = nullptr;     // colour, weight bits
   uint32_t* cnt = nullptr;    // [max_points + 1]
   uint32_t* off = nullptr;    // [max_points + 1]
   uint32_t* ckeys[2] = {nullptr, nullptr};
@@ -139,6 +142,10 @@ struct vbx_ctx {
   uint32_t* raise_q[2] = {nullptr, nullptr};
   uint64_t frontier_cap = 0;
   uint32_t* esdf_block_list = nullptr;
+  uint32_t* esdf_seed_list = nullptr;
+  float* esdf_seed_val = nullptr;
+  uint32_t* esdf_touched = nullptr;
+  int esdf_grid_raise = 0, esdf_grid_lower = 0;
   // reporting
   uint64_t counters[16] = {0};
   uint64_t esdf_counters[16] = {0};

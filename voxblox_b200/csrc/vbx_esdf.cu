@@ -1,13 +1,575 @@
-// ESDF wavefront on the device (EsdfIntegrator, voxblox/src/integrator/esdf_integrator.cc).
-// Placeholder until the TSDF path is parity-green on hardware.
+// ESDF update on the device: EsdfIntegrator::updateFromTsdfLayer / ...Batch
+// (voxblox/src/integrator/esdf_integrator.cc:94-530) over the same block hash and pool
+// slots as the TSDF layer.
+//
+// The reference is a single-threaded queue algorithm: (1) a streaming pass classifies every
+// voxel of every updated TSDF block against its stored ESDF voxel (new / lower / raise / sign
+// flip, cc:136-287) and fills a FIFO raise queue and a bucketed open queue, (2) the raise
+// queue invalidates the descendants of raised voxels through their parent pointers
+// (cc:305-369), (3) the open queue relaxes 26-neighbourhoods until no distance can be lowered
+// (cc:371-496).  On the device the three steps become
+//   k_esdf_propagate   one thread per voxel of every listed block (streaming, coalesced)
+//   k_esdf_seed        incremental only: updateVoxelFromNeighbors for new free voxels (cc:498-530)
+//   k_esdf_raise       persistent cooperative kernel, level-synchronous BFS over the parent tree
+//   k_esdf_lower       persistent cooperative kernel, wavefront relaxation with atomicMin on the
+//                      distance word; one warp per frontier voxel, one lane per neighbour
+//   k_esdf_parents     parent direction of every voxel the wavefront lowered, recomputed from the
+//                      converged distances
+// Distances are compared and lowered through their integer bit patterns: for two floats of the
+// same sign the one nearer zero has the smaller signed-integer pattern, so "closer to the
+// surface" is atomicMin on both sides of the surface.
+//
+// With min_diff_m = 0 (what the reference's own tests use, test_sdf_integrators.cc:200) the
+// converged distances are the unique least fixed point of the relaxation rule and do not
+// depend on visiting order; see DESIGN.md "ESDF" for what is and is not order dependent.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "vbx_engine.h"
+
+namespace cg = cooperative_groups;
 
 namespace vbx {
 
-int esdf_create(vbx_ctx* c, const vbx_esdf_config*) {
-  return fail(c, VBX_E_STATE, "ESDF device path not built yet");
+// src/utils/neighbor_tools.cc:24-30: 6 faces, 12 edges, 8 corners, in this order
+__constant__ int8_t kOff[26][3] = {
+    {-1, 0, 0},  {1, 0, 0},   {0, -1, 0},  {0, 1, 0},  {0, 0, -1},  {0, 0, 1},  {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0},
+    {1, 1, 0},   {0, -1, -1}, {0, -1, 1},  {0, 1, -1}, {0, 1, 1},   {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1},
+    {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1},  {1, 1, 1}};
+
+struct EsdfParams {
+  int L;
+  float voxel_size;
+  float max_distance, min_distance, default_distance, min_diff, min_weight;
+  int full_euclidean, multi_queue, add_occupied_crust;
+  int incremental;
+  float d1, d2, d3;  // kDistances * voxel_size (1, sqrtf(2), sqrtf(3)), neighbor_tools.cc:8-21
+  float u1, u2, u3;  // kDistances unscaled (used by updateVoxelFromNeighbors, cc:508)
+  uint32_t cap;      // frontier capacity
+};
+
+// the four bools of EsdfVoxel as bits of one word (each bool byte holds 0 or 1); kBitLowered is a
+// scratch mark that lives only inside one update call
+constexpr uint32_t kFlagObserved = 0x00000001u, kFlagHallucinated = 0x00000100u, kFlagInQueue = 0x00010000u,
+                   kFlagFixed = 0x01000000u, kBitLowered = 0x00020000u;
+constexpr uint32_t kBitObserved = kFlagObserved, kBitHallucinated = kFlagHallucinated, kBitInQueue = kFlagInQueue,
+                   kBitFixed = kFlagFixed;
+
+// EsdfVoxel viewed as five 32-bit words: distance, flags (4 bools), parent x, y, z
+struct EsdfWords {
+  float distance;
+  uint32_t flags;
+  int32_t px, py, pz;
+};
+static_assert(sizeof(EsdfWords) == sizeof(EsdfVoxel), "EsdfVoxel words");
+
+__device__ __forceinline__ int signum_d(float v) { return (v == 0.0f) ? 0 : (v < 0.0f ? -1 : 1); }
+__device__ __forceinline__ float nbr_dist(const EsdfParams& E, int i) { return i < 6 ? E.d1 : (i < 18 ? E.d2 : E.d3); }
+__device__ __forceinline__ float nbr_dist_unscaled(const EsdfParams& E, int i) {
+  return i < 6 ? E.u1 : (i < 18 ? E.u2 : E.u3);
 }
-int esdf_update(vbx_ctx* c, int, int) { return fail(c, VBX_E_STATE, "ESDF device path not built yet"); }
-int esdf_destroy(vbx_ctx*) { return VBX_OK; }
+
+// (slot, lin) of the neighbour of voxel (slot, lin) in direction i, or ~0 if its ESDF block does
+// not exist (Layer::getVoxelPtrByGlobalIndex returning nullptr, core/layer.h:228-239)
+__device__ __forceinline__ uint32_t neighbor_ref(const Tables& tab, int L, uint32_t ref, int i) {
+  const uint32_t slot = ref >> (3 * L), lin = ref & ((1u << (3 * L)) - 1u);
+  const int mask = (1 << L) - 1;
+  int x = (int)(lin & mask) + kOff[i][0];
+  int y = (int)((lin >> L) & mask) + kOff[i][1];
+  int z = (int)(lin >> (2 * L)) + kOff[i][2];
+  uint32_t nslot = slot;
+  if ((x | y | z) & ~mask) {  // leaves the block
+    int bx, by, bz;
+    unpack3(tab.slot_key[slot], &bx, &by, &bz);
+    bx += x >> L;
+    by += y >> L;
+    bz += z >> L;
+    x &= mask;
+    y &= mask;
+    z &= mask;
+    uint32_t hp = hash64(pack3(bx, by, bz)) & tab.hmask;
+    nslot = 0xffffffffu;
+    for (uint32_t probe = 0; probe <= tab.hmask; ++probe) {
+      const uint64_t k = tab.hkeys[hp];
+      if (k == pack3(bx, by, bz)) {
+        nslot = (uint32_t)tab.hslot[hp];
+        break;
+      }
+      if (k == kEmptyKey) break;
+      hp = (hp + 1) & tab.hmask;
+    }
+    if (nslot == 0xffffffffu) return 0xffffffffu;
+  }
+  if (!tab.slot_has_esdf[nslot]) return 0xffffffffu;
+  return (nslot << (3 * L)) | (uint32_t)(x | (y << L) | (z << (2 * L)));
+}
+
+__device__ __forceinline__ void push(uint32_t* list, uint32_t* count, uint32_t cap, uint32_t ref, ScanState* st) {
+  const uint32_t j = atomicAdd(count, 1u);
+  if (j < cap) {
+    list[j] = ref;
+  } else {
+    atomicOr(&st->error, kErrUpdatesFull);
+  }
+}
+
+// Step (1), esdf_integrator.cc:136-287: one thread per voxel of every listed block.
+// esdf_counts: [1] lower [2] raise [3] new
+__global__ void k_esdf_propagate(EsdfParams E, Tables tab, const uint32_t* __restrict__ block_list, uint32_t n_blocks,
+                                 uint32_t* open_list, uint32_t* raise_list, uint32_t* seed_list, ScanState* st) {
+  const uint32_t vpb = 1u << (3 * E.L);
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint64_t)n_blocks * vpb) return;
+  const uint32_t slot = block_list[gid >> (3 * E.L)];
+  const uint32_t lin = (uint32_t)(gid & (vpb - 1));
+  const uint32_t ref = (slot << (3 * E.L)) | lin;
+  const TsdfVoxel tv = tab.tsdf[(size_t)slot * vpb + lin];
+  EsdfWords* ep = reinterpret_cast<EsdfWords*>(tab.esdf) + (size_t)slot * vpb + lin;
+  if (tv.weight < E.min_weight) {  // unobserved in the TSDF, cc:153-164
+    if (!E.incremental && E.add_occupied_crust) {
+      ep->distance = -E.default_distance;
+      ep->flags = (ep->flags & ~(kFlagObserved | kFlagHallucinated | kFlagFixed)) | kBitObserved | kBitHallucinated;
+    }
+    return;
+  }
+  EsdfWords ev = *ep;
+  const bool observed = (ev.flags & kFlagObserved) != 0, halluc = (ev.flags & kFlagHallucinated) != 0;
+  bool fixed = (ev.flags & kFlagFixed) != 0, in_queue = (ev.flags & kFlagInQueue) != 0;
+  const bool tfixed = fabsf(tv.distance) < E.min_distance;  // isFixed, esdf_integrator.h:131-133
+  const float sgn_default = (float)signum_d(tv.distance) * E.default_distance;
+  const float md = E.min_diff;
+  bool to_open = false, to_raise = false, to_seed = false, reset_parent = false;
+  if (!observed || halluc) {  // nothing there before, cc:174-200
+    if (halluc) to_raise = true;
+    if (tfixed) {
+      ev.distance = tv.distance;
+      fixed = true;
+      to_open = true;
+    } else {
+      ev.distance = sgn_default;
+      fixed = false;
+      if (E.incremental) to_seed = true;
+    }
+    reset_parent = true;
+    atomicAdd(&st->esdf_counts[3], 1u);
+  } else if (tfixed || fixed) {  // cc:211-262
+    if (!tfixed) {
+      ev.distance = sgn_default;
+      reset_parent = true;
+      fixed = false;
+      to_raise = true;
+      to_open = true;
+      atomicAdd(&st->esdf_counts[2], 1u);
+    } else if ((ev.distance > 0.0f && tv.distance + md < ev.distance) ||
+               (ev.distance <= 0.0f && tv.distance - md > ev.distance)) {
+      fixed = tfixed;
+      ev.distance = fixed ? tv.distance : sgn_default;
+      reset_parent = true;
+      to_open = true;
+      atomicAdd(&st->esdf_counts[1], 1u);
+    } else if ((ev.distance > 0.0f && tv.distance - md > ev.distance) ||
+               (ev.distance <= 0.0f && tv.distance + md < ev.distance)) {
+      fixed = tfixed;
+      ev.distance = fixed ? tv.distance : sgn_default;
+      reset_parent = true;
+      to_raise = true;
+      to_open = true;
+      atomicAdd(&st->esdf_counts[2], 1u);
+    }
+  } else if (signum_d(tv.distance) != signum_d(ev.distance)) {  // cc:263-282
+    if (tv.distance < ev.distance) {
+      ev.distance = sgn_default;
+      reset_parent = true;
+      to_open = true;
+      atomicAdd(&st->esdf_counts[1], 1u);
+    } else {
+      ev.distance = sgn_default;
+      reset_parent = true;
+      to_raise = true;
+      atomicAdd(&st->esdf_counts[2], 1u);
+    }
+  }
+  if (to_open) in_queue = true;
+  if (reset_parent) ev.px = ev.py = ev.pz = 0;
+  // esdf_voxel.observed = true; hallucinated = false, cc:285-286
+  ev.flags = kBitObserved | (in_queue ? kBitInQueue : 0u) | (fixed ? kBitFixed : 0u);
+  *ep = ev;
+  if (to_open) push(open_list, &st->frontier_n[0], E.cap, ref, st);
+  if (to_raise) push(raise_list, &st->raise_n[0], E.cap, ref, st);
+  if (to_seed) push(seed_list, &st->seed_n, E.cap, ref, st);
+}
+
+// updateVoxelFromNeighbors (cc:498-530) for the new free-space voxels of an incremental update:
+// first neighbour in table order that is observed, inside +-max_distance, of the same sign and
+// closer; the distance added is the UNSCALED table entry (cc:508).  Candidates are read in
+// their post-classification state (the reference sees neighbours seeded earlier in its own
+// loop order as well).
+__global__ void k_esdf_seed(EsdfParams E, Tables tab, const uint32_t* __restrict__ seed_list, uint32_t* open_list,
+                            float* seed_val, ScanState* st) {
+  const uint32_t n = min(st->seed_n, E.cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t ref = seed_list[i];
+    EsdfWords* ep = reinterpret_cast<EsdfWords*>(tab.esdf) + ref;
+    const float d = ep->distance;
+    float out = d;
+    for (int k = 0; k < 26; ++k) {
+      const uint32_t nref = neighbor_ref(tab, E.L, ref, k);
+      if (nref == 0xffffffffu) continue;
+      const EsdfWords* np = reinterpret_cast<const EsdfWords*>(tab.esdf) + nref;
+      const uint32_t nf = np->flags;
+      const float nd = np->distance;
+      // a neighbour that is itself waiting to be seeded still holds +-default_distance
+      if (!(nf & kFlagObserved) || nd >= E.max_distance || nd <= -E.max_distance) continue;
+      if (signum_d(nd) == signum_d(d) && fabsf(nd) < fabsf(d)) {
+        out = fadd(nd, fmul((float)signum_d(d), nbr_dist_unscaled(E, k)));
+        // (the parent the reference assigns here is zeroed again right after, cc:199-200)
+        atomicOr(&ep->flags, kBitInQueue);
+        push(open_list, &st->frontier_n[0], E.cap, ref, st);
+        break;
+      }
+    }
+    // published by k_esdf_seed_commit so that no thread of this kernel reads a half-seeded neighbour
+    seed_val[i] = out;
+  }
+}
+
+__global__ void k_esdf_seed_commit(EsdfParams E, Tables tab, const uint32_t* __restrict__ seed_list,
+                                   const float* __restrict__ seed_val, const ScanState* st) {
+  const uint32_t n = min(st->seed_n, E.cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    (reinterpret_cast<EsdfWords*>(tab.esdf) + seed_list[i])->distance = seed_val[i];
+  }
+}
+
+// Step (2), processRaiseSet cc:305-369: level-synchronous BFS.  One warp per raised voxel, one
+// lane per neighbour.  A neighbour whose parent points back at the raised voxel is reset and
+// raised in turn; any other observed, non-fixed neighbour joins the open set.
+__global__ void k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32_t* raise_b, uint32_t* open_list,
+                             ScanState* st) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  int cur = 0;
+  while (true) {
+    uint32_t* in = cur ? raise_b : raise_a;
+    uint32_t* out = cur ? raise_a : raise_b;
+    const uint32_t n = min(__ldcg(&st->raise_n[cur]), E.cap);
+    if (n == 0) break;
+    for (uint32_t q = warp; q < n; q += n_warps) {
+      const uint32_t ref = __ldcg(&in[q]);
+      if (lane == 0) atomicAdd(&st->esdf_counts[4], 1u);
+      if (lane < 26) {
+        const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
+        if (nref != 0xffffffffu) {
+          EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
+          const uint32_t nf = np->flags;
+          if ((nf & kFlagObserved) && !(nf & kFlagFixed)) {
+            bool is_parent = np->px == -kOff[lane][0] && np->py == -kOff[lane][1] && np->pz == -kOff[lane][2];
+            if (E.full_euclidean) {  // cc:339-347
+              const F3 pd = unit3(f3((float)np->px, (float)np->py, (float)np->pz));
+              is_parent = (int)roundf(pd.x) == -kOff[lane][0] && (int)roundf(pd.y) == -kOff[lane][1] &&
+                          (int)roundf(pd.z) == -kOff[lane][2];
+            }
+            if (is_parent) {
+              np->distance = (float)signum_d(np->distance) * E.default_distance;
+              np->px = np->py = np->pz = 0;
+              push(out, &st->raise_n[cur ^ 1], E.cap, nref, st);
+            } else if (!(atomicOr(&np->flags, kBitInQueue) & kFlagInQueue)) {
+              push(open_list, &st->frontier_n[0], E.cap, nref, st);
+            }
+          }
+        }
+      }
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->raise_n[cur] = 0;
+    cur ^= 1;
+    grid.sync();
+  }
+}
+
+// Step (3), processOpenSet cc:371-496: wavefront relaxation.  One warp per frontier voxel, one
+// lane per neighbour; a lowered neighbour joins the next frontier (once: the in_queue flag).
+__global__ void k_esdf_lower(EsdfParams E, Tables tab, uint32_t* front_a, uint32_t* front_b, uint32_t* touched_list,
+                             ScanState* st) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  int cur = 0;
+  while (true) {
+    uint32_t* in = cur ? front_b : front_a;
+    uint32_t* out = cur ? front_a : front_b;
+    const uint32_t n = min(__ldcg(&st->frontier_n[cur]), E.cap);
+    if (n == 0) break;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->esdf_counts[6], 1u);
+    // pass A: leave the queue (voxel->in_queue = false, cc:384)
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+      atomicAnd(&(reinterpret_cast<EsdfWords*>(tab.esdf) + __ldcg(&in[i]))->flags, ~kBitInQueue);
+    }
+    grid.sync();
+    // pass B: relax the 26-neighbourhood
+    for (uint32_t q = warp; q < n; q += n_warps) {
+      const uint32_t ref = __ldcg(&in[q]);
+      const EsdfWords* vp = reinterpret_cast<const EsdfWords*>(tab.esdf) + ref;
+      const float vd = *reinterpret_cast<const volatile float*>(&vp->distance);
+      const uint32_t vf = vp->flags;
+      if (!(vf & kFlagObserved) || vd >= E.max_distance || vd <= -E.max_distance) continue;  // cc:387-390
+      if (lane >= 26) continue;
+      const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
+      if (nref == 0xffffffffu) continue;
+      EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
+      const uint32_t nf = np->flags;
+      if (!(nf & kFlagObserved) || (nf & kFlagFixed)) continue;  // cc:407-411
+      float dist = nbr_dist(E, lane);
+      if (E.full_euclidean) {  // cc:414-426
+        const F3 npar = f3((float)(vp->px - kOff[lane][0]), (float)(vp->py - kOff[lane][1]),
+                           (float)(vp->pz - kOff[lane][2]));
+        dist = fmul(E.voxel_size, fsub(norm3(npar), norm3(f3((float)vp->px, (float)vp->py, (float)vp->pz))));
+        if (dist < 0.0f) continue;
+      }
+      const float nd = *reinterpret_cast<const volatile float*>(&np->distance);
+      bool changed = false;
+      int* nbits = reinterpret_cast<int*>(&np->distance);
+      if (vd > 0.0f && nd > 0.0f) {  // both outside, cc:429-443
+        if (fadd(fadd(vd, dist), E.min_diff) < nd) {
+          const float cand = fadd(vd, dist);
+          changed = atomicMin(nbits, __float_as_int(cand)) > __float_as_int(cand);
+        }
+      } else if (vd <= 0.0f && nd <= 0.0f) {  // both inside, cc:444-457
+        if (fsub(fsub(vd, dist), E.min_diff) > nd) {
+          const float cand = fsub(vd, dist);
+          changed = atomicMin(nbits, __float_as_int(cand)) > __float_as_int(cand);
+        }
+      } else {  // signs differ, cc:458-488 (incl. the sign-vs-distance comparison of cc:464)
+        const float pot = fsub(vd, fmul((float)signum_d(vd), dist));
+        if (fabsf(fsub(pot, nd)) > dist) {
+          // The reference ASSIGNS sign(n) * dist here, so its result depends on which source it
+          // pops first.  The device keeps the candidate nearest the surface (order free): the
+          // assignment is applied only when it lowers |distance|.
+          const float nv = ((float)signum_d(pot) == nd) ? pot : fmul((float)signum_d(nd), dist);
+          if ((nv > 0.0f) == (nd > 0.0f)) {
+            changed = atomicMin(nbits, __float_as_int(nv)) > __float_as_int(nv);
+          }
+        }
+      }
+      if (changed) {
+        atomicAdd(&st->esdf_counts[5], 1u);
+        // neighbor_voxel->parent = new_parent (cc:436,450,470,481).  Written unguarded: when two
+        // sources lower the same voxel in one sweep the last writer wins; k_esdf_parents then
+        // re-derives the parent from the converged distances (quasi-Euclidean mode).
+        if (E.full_euclidean) {
+          np->px = vp->px - kOff[lane][0];
+          np->py = vp->py - kOff[lane][1];
+          np->pz = vp->pz - kOff[lane][2];
+        } else {
+          np->px = -kOff[lane][0];
+          np->py = -kOff[lane][1];
+          np->pz = -kOff[lane][2];
+        }
+        const uint32_t old = atomicOr(&np->flags, kBitInQueue | kBitLowered);
+        if (!(old & kBitLowered)) push(touched_list, &st->lowered_n, E.cap, nref, st);
+        if (E.multi_queue || !(old & kFlagInQueue)) push(out, &st->frontier_n[cur ^ 1], E.cap, nref, st);
+      }
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->frontier_n[cur] = 0;
+    cur ^= 1;
+    grid.sync();
+  }
+}
+
+// Parent direction of every voxel the wavefront lowered (quasi-Euclidean mode): the first
+// neighbour in table order whose converged distance reproduces this voxel's distance through
+// the relaxation rule.  (The reference stores the neighbour that happened to lower it last;
+// with equal candidates that is its visiting order.)
+__global__ void k_esdf_parents(EsdfParams E, Tables tab, const uint32_t* __restrict__ touched_list, ScanState* st) {
+  const uint32_t n = min(st->lowered_n, E.cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t ref = touched_list[i];
+    EsdfWords* ep = reinterpret_cast<EsdfWords*>(tab.esdf) + ref;
+    atomicAnd(&ep->flags, ~kBitLowered);
+    if (E.full_euclidean) continue;
+    const float d = ep->distance;
+    for (int k = 0; k < 26; ++k) {
+      const uint32_t nref = neighbor_ref(tab, E.L, ref, k);
+      if (nref == 0xffffffffu) continue;
+      const EsdfWords* np = reinterpret_cast<const EsdfWords*>(tab.esdf) + nref;
+      if (!(np->flags & kFlagObserved)) continue;
+      const float nd = np->distance;
+      if (nd >= E.max_distance || nd <= -E.max_distance) continue;
+      const float dist = nbr_dist(E, k);
+      const bool same = (d > 0.0f && nd > 0.0f && fadd(nd, dist) == d) || (d <= 0.0f && nd <= 0.0f && fsub(nd, dist) == d);
+      const bool mixed = ((d > 0.0f) != (nd > 0.0f)) && fmul((float)signum_d(d), dist) == d;
+      if (same || mixed) {
+        // the voxel at offset k is a source of this distance; the parent points towards it
+        ep->px = kOff[k][0];
+        ep->py = kOff[k][1];
+        ep->pz = kOff[k][2];
+        break;
+      }
+    }
+  }
+}
+
+// blocks to propagate: every slot with the kEsdf bit (incremental) or every slot (batch)
+__global__ void k_esdf_block_list(Tables tab, uint32_t n_slots, int batch, uint32_t* block_list, ScanState* st) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  if (batch || (tab.slot_updated[s] & VBX_UPDATED_ESDF)) {
+    block_list[atomicAdd(&st->esdf_counts[0], 1u)] = s;
+    tab.slot_has_esdf[s] = 1;      // allocateBlockPtrByIndex in the ESDF layer, cc:143-146
+    tab.slot_esdf_updated[s] = 1;  // esdf_block->set_updated(true): bitset(1) = kMap only, cc:147
+  }
+}
+
+__global__ void k_esdf_clear_tsdf_flag(Tables tab, const uint32_t* __restrict__ block_list, const ScanState* st) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->esdf_counts[0]) return;
+  tab.slot_updated[block_list[i]] &= (uint8_t)~VBX_UPDATED_ESDF;  // cc:113-121
+}
+
+static inline unsigned int grid_for(uint64_t n, int block) { return (unsigned int)((n + block - 1) / block); }
+
+int esdf_destroy(vbx_ctx* c) {
+  void* ptrs[] = {c->tab.esdf, c->frontier[0], c->frontier[1], c->raise_q[0], c->raise_q[1], c->esdf_block_list,
+                  c->esdf_seed_list, c->esdf_seed_val, c->esdf_touched};
+  for (void* p : ptrs) {
+    if (p) cudaFree(p);
+  }
+  c->tab.esdf = nullptr;
+  c->frontier[0] = c->frontier[1] = c->raise_q[0] = c->raise_q[1] = c->esdf_block_list = nullptr;
+  c->esdf_seed_list = c->esdf_touched = nullptr;
+  c->esdf_seed_val = nullptr;
+  c->has_esdf = false;
+  return VBX_OK;
+}
+
+int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
+  if (c->has_esdf) esdf_destroy(c);
+  c->ecfg = *cfg;
+  const size_t nvox = (size_t)c->tab.max_blocks * c->vox_per_block;
+  VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tab.esdf), nvox * sizeof(EsdfVoxel)));
+  // new Block<EsdfVoxel>: distance 0, all flags false, parent 0 (core/voxel.h:18-37)
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, nvox * sizeof(EsdfVoxel), c->stream));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->tab.max_blocks, c->stream));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->tab.max_blocks, c->stream));
+  c->frontier_cap = std::min<uint64_t>(nvox, 1ull << 25);
+  for (int i = 0; i < 2; ++i) {
+    VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->frontier[i]), c->frontier_cap * sizeof(uint32_t)));
+    VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->raise_q[i]), c->frontier_cap * sizeof(uint32_t)));
+  }
+  VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->esdf_block_list), c->tab.max_blocks * sizeof(uint32_t)));
+  VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->esdf_seed_list), c->frontier_cap * sizeof(uint32_t)));
+  VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->esdf_seed_val), c->frontier_cap * sizeof(float)));
+  VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->esdf_touched), c->frontier_cap * sizeof(uint32_t)));
+  int dev = c->device, sms = 0, per_sm_r = 0, per_sm_l = 0;
+  VBX_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  VBX_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, k_esdf_raise, 256, 0));
+  VBX_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, k_esdf_lower, 256, 0));
+  c->esdf_grid_raise = sms * std::max(1, std::min(per_sm_r, 4));
+  c->esdf_grid_lower = sms * std::max(1, std::min(per_sm_l, 4));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->has_esdf = true;
+  return VBX_OK;
+}
+
+int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
+  cudaStream_t s = c->stream;
+  std::memset(c->esdf_counters, 0, sizeof(c->esdf_counters));
+  const vbx_esdf_config& cfg = c->ecfg;
+  EsdfParams E;
+  std::memset(&E, 0, sizeof(E));
+  E.L = c->L;
+  E.voxel_size = c->voxel_size;
+  E.max_distance = cfg.max_distance_m;
+  E.min_distance = cfg.min_distance_m;
+  E.default_distance = cfg.default_distance_m;
+  E.min_diff = cfg.min_diff_m;
+  E.min_weight = cfg.min_weight;
+  E.full_euclidean = cfg.full_euclidean_distance;
+  E.multi_queue = cfg.multi_queue;
+  E.add_occupied_crust = cfg.add_occupied_crust;
+  E.incremental = batch ? 0 : 1;
+  E.u1 = 1.0f;
+  E.u2 = (float)std::sqrt(2.0);  // const float sqrt_2 = std::sqrt(2), neighbor_tools.cc:9
+  E.u3 = (float)std::sqrt(3.0);
+  E.d1 = E.u1 * c->voxel_size;
+  E.d2 = E.u2 * c->voxel_size;
+  E.d3 = E.u3 * c->voxel_size;
+  E.cap = (uint32_t)c->frontier_cap;
+  uint64_t launches = 0;
+  VBX_CUDA(c, cudaEventRecord(c->ev0, s));
+  if (c->profiling) cudaEventRecord(c->sev[0], s);
+  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+  if (c->n_blocks == 0) {
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    return VBX_OK;
+  }
+  if (batch) {
+    // esdf_layer_->removeAllBlocks() (cc:95): every ESDF block starts from scratch
+    const size_t nvox = (size_t)c->n_blocks * c->vox_per_block;
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, nvox * sizeof(EsdfVoxel), s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->n_blocks, s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->n_blocks, s));
+  }
+  k_esdf_block_list<<<grid_for(c->n_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, batch, c->esdf_block_list, c->d_state);
+  // the propagate grid covers every slot in use; threads beyond the listed blocks exit
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  const uint32_t nb = c->h_state->esdf_counts[0];
+  launches += 1;
+  if (nb > 0) {
+    k_esdf_propagate<<<grid_for((uint64_t)nb * c->vox_per_block, 256), 256, 0, s>>>(
+        E, c->tab, c->esdf_block_list, nb, c->frontier[0], c->raise_q[0], c->esdf_seed_list, c->d_state);
+    launches += 1;
+    if (!batch) {
+      const unsigned int g = 148 * 8;
+      k_esdf_seed<<<g, 256, 0, s>>>(E, c->tab, c->esdf_seed_list, c->frontier[0], c->esdf_seed_val, c->d_state);
+      k_esdf_seed_commit<<<g, 256, 0, s>>>(E, c->tab, c->esdf_seed_list, c->esdf_seed_val, c->d_state);
+      launches += 2;
+    }
+    if (c->profiling) cudaEventRecord(c->sev[1], s);
+    {
+      void* args[] = {&E, &c->tab, &c->raise_q[0], &c->raise_q[1], &c->frontier[0], &c->d_state};
+      VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_esdf_raise, dim3(c->esdf_grid_raise), dim3(256), args, 0, s));
+    }
+    if (c->profiling) cudaEventRecord(c->sev[2], s);
+    {
+      void* args[] = {&E, &c->tab, &c->frontier[0], &c->frontier[1], &c->esdf_touched, &c->d_state};
+      VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_esdf_lower, dim3(c->esdf_grid_lower), dim3(256), args, 0, s));
+    }
+    k_esdf_parents<<<148 * 8, 256, 0, s>>>(E, c->tab, c->esdf_touched, c->d_state);
+    if (c->profiling) cudaEventRecord(c->sev[3], s);
+    launches += 3;
+    if (!batch && clear_updated_flag) {
+      k_esdf_clear_tsdf_flag<<<grid_for(nb, 256), 256, 0, s>>>(c->tab, c->esdf_block_list, c->d_state);
+      launches += 1;
+    }
+  }
+  VBX_CUDA(c, cudaEventRecord(c->ev1, s));
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
+  VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (c->profiling && nb > 0) {
+    for (int m = 0; m < 3; ++m) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->sev[m], c->sev[m + 1]) == cudaSuccess) {
+        c->stage_ms[9 + m] += ms;
+        c->stage_calls[9 + m] += 1;
+      }
+    }
+  }
+  if (c->h_state->error & kErrUpdatesFull) return fail(c, VBX_E_CAPACITY, "ESDF wavefront queue capacity exceeded");
+  for (int i = 0; i < 7; ++i) c->esdf_counters[i] = c->h_state->esdf_counts[i];
+  c->esdf_counters[7] = launches;
+  c->launches += launches;
+  return VBX_OK;
+}
 
 }  // namespace vbx

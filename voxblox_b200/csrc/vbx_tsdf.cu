@@ -375,12 +375,23 @@ __device__ bool fold_bundle(const ScanParams& P, const float* __restrict__ xyz, 
   return __any_sync(0xffffffffu, suspect);
 }
 
+// Per-ray records.  ray_p (point_G, flags) feeds the two DDA walks; ray_a (point_G - origin and
+// its norm, the per-ray half of computeDistance cc:216-228) and ray_c (colour, weight) feed the
+// apply kernels, so that an update costs one division and no square root.
+__device__ __forceinline__ void store_ray(const ScanParams& P, uint32_t i, F3 point_G, float weight, uint32_t color,
+                                          bool clearing, float4* ray_p, float4* ray_a, uint2* ray_c) {
+  const F3 po = sub3(point_G, P.origin);
+  ray_p[i] = make_float4(point_G.x, point_G.y, point_G.z, __uint_as_float(clearing ? 1u : 0u));
+  ray_a[i] = make_float4(po.x, po.y, po.z, norm3(po));
+  ray_c[i] = make_uint2(color, __float_as_uint(weight));
+}
+
 // One warp per bundle (integrateVoxel's merge, cc:384-407).
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
 k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
         const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ray_list,
-        float4* __restrict__ ray_p, uint2* __restrict__ ray_c, const ScanState* st) {
+        float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c, const ScanState* st) {
   __shared__ float4 stage[4 * 32 * kStageStride];  // [warp in block][member][role]
   const int lane = threadIdx.x & 31;
   float4* stage_warp = stage + (threadIdx.x >> 5) * (32 * kStageStride);
@@ -396,9 +407,7 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
       fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol);
     }
     if (lane == 0) {
-      const F3 pg = transform(P.T, mp);
-      ray_p[i] = make_float4(pg.x, pg.y, pg.z, mw);
-      ray_c[i] = make_uint2(mcol, key_is_clearing(P, (uint64_t)keys[i]) ? 1u : 0u);
+      store_ray(P, i, transform(P.T, mp), mw, mcol, key_is_clearing(P, (uint64_t)keys[i]), ray_p, ray_a, ray_c);
     }
   }
 }
@@ -448,7 +457,8 @@ template <typename KeyT>
 __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__ xyz,
                              const uint8_t* __restrict__ rgba, const uint32_t* __restrict__ order,
                              const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
-                             float4* __restrict__ ray_p, uint2* __restrict__ ray_c, uint32_t* __restrict__ cnt,
+                             float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c,
+                             uint32_t* __restrict__ cnt,
                              unsigned long long* set_start, unsigned long long* set_observed, ScanState* st) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t i;
@@ -460,7 +470,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
     i = ray_list[t];
     const float4 rp = ray_p[i];
     point_G = f3(rp.x, rp.y, rp.z);
-    clearing = (ray_c[i].y & 1u) != 0;
+    clearing = (__float_as_uint(rp.w) & 1u) != 0;
     own = keys[i];
   } else {
     i = t;
@@ -486,8 +496,8 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
         return;
       }
     }
-    ray_p[i] = make_float4(point_G.x, point_G.y, point_G.z, point_weight(p.z, P.use_const_weight != 0));
-    ray_c[i] = make_uint2(load_color(rgba, idx), clearing ? 1u : 0u);
+    store_ray(P, i, point_G, point_weight(p.z, P.use_const_weight != 0), load_color(rgba, idx), clearing, ray_p,
+              ray_a, ray_c);
   }
   atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
 
@@ -556,7 +566,7 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ off, uint32_t 
 template <typename KeyT>
 __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ keys,
                             const uint32_t* __restrict__ ray_list, const float4* __restrict__ ray_p,
-                            const uint2* __restrict__ ray_c, const uint32_t* __restrict__ cnt,
+                            const uint32_t* __restrict__ cnt,
                             const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
                             uint32_t* __restrict__ cvals, const ScanState* st) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,7 +581,7 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
   const uint32_t c = cnt[i];
   if (c == 0) return;
   const float4 rp = ray_p[i];
-  const bool clearing = (ray_c[i].y & 1u) != 0;
+  const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
   const F3 point_G = f3(rp.x, rp.y, rp.z);
   Dda d;
   dda_setup(d, P.origin, point_G, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
@@ -626,18 +636,17 @@ __device__ __forceinline__ VoxelRef locate_voxel(const ScanParams& P, const Tabl
   return r;
 }
 
-// computeDistance (cc:216-228) with the voxel side hoisted: sdf = |p-o| - (c-o).(p-o)/|p-o|
-__device__ __forceinline__ float sdf_from(const ScanParams& P, F3 vo, float4 rp) {
-  const F3 po = sub3(f3(rp.x, rp.y, rp.z), P.origin);
-  const float dist_G = norm3(po);
-  return fsub(dist_G, fdiv(dot3(vo, po), dist_G));
+// computeDistance (cc:216-228) with both sides hoisted: vo = voxel centre - origin (per voxel),
+// ra = (point_G - origin, |point_G - origin|) (per ray):  sdf = |po| - (vo . po) / |po|
+__device__ __forceinline__ float sdf_from(F3 vo, float4 ra) {
+  return fsub(ra.w, fdiv(dot3(vo, f3(ra.x, ra.y, ra.z)), ra.w));
 }
 
 // One thread per run head applies the first kShortRun updates of its voxel in order
 // (updateTsdfVoxel, cc:150-209); longer runs are queued for k_apply_long.
 __global__ void k_apply_short(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
                               const uint32_t* __restrict__ cvals, unsigned long long total,
-                              const float4* __restrict__ ray_p, const uint2* __restrict__ ray_c,
+                              const float4* __restrict__ ray_a, const uint2* __restrict__ ray_c,
                               unsigned long long* __restrict__ long_list, ScanState* st) {
   const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool head = false;
@@ -650,9 +659,10 @@ __global__ void k_apply_short(ScanParams P, Tables tab, const uint32_t* __restri
       unsigned long long j = e;
       for (int k = 0; k < kShortRun && j < total && ckeys[j] == key; ++k, ++j) {
         const uint32_t r = cvals[j];
-        const float4 rp = ray_p[r];
-        const float sdf = sdf_from(P, vr.vo, rp);
-        apply_update(v, sdf, update_weight(sdf, rp.w, P.up), ray_c[r].x, P.up);
+        const float4 ra = ray_a[r];
+        const uint2 rc = ray_c[r];
+        const float sdf = sdf_from(vr.vo, ra);
+        apply_update(v, sdf, update_weight(sdf, __uint_as_float(rc.y), P.up), rc.x, P.up);
       }
       *vr.ptr = v;
       if (j < total && ckeys[j] == key) {
@@ -673,7 +683,7 @@ __global__ void k_apply_short(ScanParams P, Tables tab, const uint32_t* __restri
 // the sequential result is (+T, chained weight) without walking the distance chain.
 __global__ void k_apply_long(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
                              const uint32_t* __restrict__ cvals, unsigned long long total,
-                             const float4* __restrict__ ray_p, const uint2* __restrict__ ray_c,
+                             const float4* __restrict__ ray_a, const uint2* __restrict__ ray_c,
                              const unsigned long long* __restrict__ long_list, const ScanState* st) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -688,43 +698,49 @@ __global__ void k_apply_long(ScanParams P, Tables tab, const uint32_t* __restric
     bool done = false;
     // Three-stage software pipeline over 32-record chunks (one warp has nothing else to
     // hide a record -> ray-data load chain behind): while chunk c is applied, the ray data
-    // of chunk c+1 and the records of chunk c+2 are in flight.
-    bool in_a, in_b;
-    uint32_t r_a = 0u;
-    float4 rp_b = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t col_b = 0u;
+    // of chunk c+1 and the records of chunk c+2 are in flight.  Loaded values are only
+    // LOOKED AT one stage later, so no stage waits on its own loads.
+    uint32_t key_a = ~key, r_a = 0u;   // stage A: raw record words of chunk c+2
+    bool in_b;                          // stage B: membership + ray data of chunk c+1
+    float4 ra_b = make_float4(0.f, 0.f, 0.f, 1.f);
+    uint2 rc_b = make_uint2(0u, 0u);
     {
       unsigned long long j = j0 + lane;
-      in_a = j < total && ckeys[j] == key;
-      r_a = j < total ? cvals[j] : 0u;
-      in_b = in_a;
+      in_b = j < total && ckeys[j] == key;
       if (in_b) {
-        rp_b = ray_p[r_a];
-        col_b = ray_c[r_a].x;
+        const uint32_t r = cvals[j];
+        ra_b = ray_a[r];
+        rc_b = ray_c[r];
       }
       j += 32;
-      in_a = j < total && ckeys[j] == key;
-      r_a = j < total ? cvals[j] : 0u;
+      if (j < total) {
+        key_a = ckeys[j];
+        r_a = cvals[j];
+      }
     }
     while (!done) {
       const bool in = in_b;
-      const float4 rp = rp_b;
-      const uint32_t col = col_b;
+      const float4 ra = ra_b;
+      const uint2 rc = rc_b;
+      const uint32_t col = rc.x;
       const int cnt = __popc(__ballot_sync(0xffffffffu, in));
       if (cnt == 32) {
-        in_b = in_a;
+        in_b = key_a == key;
         if (in_b) {
-          rp_b = ray_p[r_a];
-          col_b = ray_c[r_a].x;
+          ra_b = ray_a[r_a];
+          rc_b = ray_c[r_a];
         }
         const unsigned long long j = j0 + 64 + lane;
-        in_a = j < total && ckeys[j] == key;
-        r_a = j < total ? cvals[j] : 0u;
+        key_a = ~key;
+        if (j < total) {
+          key_a = ckeys[j];
+          r_a = cvals[j];
+        }
       }
       float sdf = 0.f, w = 0.f;
       if (in) {
-        sdf = sdf_from(P, vr.vo, rp);
-        w = update_weight(sdf, rp.w, P.up);
+        sdf = sdf_from(vr.vo, ra);
+        w = update_weight(sdf, __uint_as_float(rc.y), P.up);
       }
       const bool far_free = !in || sdf >= T;
       bool fast = __all_sync(0xffffffffu, far_free) && v.distance == T;
@@ -735,7 +751,11 @@ __global__ void k_apply_long(ScanParams P, Tables tab, const uint32_t* __restric
         float wsum = in ? w : 0.f;  // any-order sum, used only as a bound
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-        if (v.weight >= VBX_EPS && (v.weight + wsum) * 1.0001f < P.up.max_weight) {
+        if (v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS) {
+          // the weight already sits at max_weight: W + w >= max_weight for every w >= 0, so the
+          // clamp returns max_weight at every step
+          my_before = v.weight;
+        } else if (v.weight >= VBX_EPS && (v.weight + wsum) * 1.0001f < P.up.max_weight) {
           // neither the 1e-6 guard nor the max_weight clamp can fire in this chunk: the
           // chain is plain in-order addition; lane L forms its own prefix
           const float wl = in ? w : 0.f;
@@ -853,18 +873,18 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     vals = vb.Current();
     mk.mark(1);
     k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, keys, c->ray_list, c->cnt, c->d_state);
-    k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_c,
+    k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_a, c->ray_c,
                                            c->d_state);
     mk.mark(8);
     *launches += 5 + (end_bit + 7) / 8;
     // the bundle count is only known on the device: launch for the worst case (every
     // point its own bundle); surplus threads exit on the first load
     k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->ray_list,
-                                                         c->ray_p, c->ray_c, c->cnt, c->set_start,
+                                                         c->ray_p, c->ray_a, c->ray_c, c->cnt, c->set_start,
                                                          c->set_observed, c->d_state);
   } else {
     k_rays_count<KeyT><<<grid_for((uint64_t)n + 1, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys,
-                                                                       c->ray_list, c->ray_p, c->ray_c, c->cnt,
+                                                                       c->ray_list, c->ray_p, c->ray_a, c->ray_c, c->cnt,
                                                                        c->set_start, c->set_observed, c->d_state);
   }
   mk.mark(2);
@@ -886,7 +906,7 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
                      Marks& mk, uint64_t* launches) {
   cudaStream_t s = c->stream;
   const uint32_t n = P.n;
-  k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->ray_c, c->cnt,
+  k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt,
                                                       c->off, c->ckeys[0], c->cvals[0], c->d_state);
   mk.mark(5);
   cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
@@ -895,9 +915,9 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
   VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
   mk.mark(6);
-  k_apply_short<<<grid_for(K, 256), 256, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_p, c->ray_c,
+  k_apply_short<<<grid_for(K, 256), 256, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_a, c->ray_c,
                                                   c->long_list, c->d_state);
-  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_p, c->ray_c,
+  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_a, c->ray_c,
                                        c->long_list, c->d_state);
   mk.mark(7);
   *launches += 4 + (key_bits + 7) / 8;
