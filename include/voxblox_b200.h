@@ -179,6 +179,38 @@ VBX_API int vbx_esdf_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
 
 VBX_API int vbx_sync(vbx_ctx* ctx);
 
+/* Ray-range sharding over the GPUs of one box (BASELINE.json north_star).
+ * Every rank holds a full replica of the map and receives the full cloud.  A scan is integrated
+ * in three steps per rank (vbx_engine_options.rank / world_size):
+ *   1. vbx_shard_front: transform + bundle the WHOLE cloud (cheap, identical on every rank so
+ *      that all ranks agree on the bundles), then merge and ray-cast only this rank's contiguous
+ *      range of ray slots [rank*slice, (rank+1)*slice).  Writes this rank's update records
+ *      (global voxel key, ray slot) and its slice of the per-ray tables into `d_pack` (device
+ *      memory, vbx_shard_layout.pack_bytes bytes) and returns the record count.
+ *   2. the caller all-gathers the counts and then the used prefix of every rank's pack
+ *      (NCCL, torch.distributed), rank order.
+ *   3. vbx_shard_back: every rank allocates the blocks of all gathered records on its replica
+ *      and applies them in ray order -- the same per-voxel update order as one GPU, so all
+ *      replicas (and the single-GPU result) are bit-identical.
+ * Supported for the Simple and Merged integrators. */
+typedef struct vbx_shard_layout {
+  uint64_t record_capacity; /* update records per rank the pack can hold            */
+  uint64_t slice;           /* ray slots per rank = ceil(n / world_size)             */
+  uint64_t pack_bytes;      /* size of one rank's pack                               */
+  uint64_t off_ray_a, off_ray_c, off_records; /* byte offsets inside a pack: per-ray tables
+                                               * first, then 16-byte update records, so that
+                                               * a prefix of the pack is enough to exchange   */
+} vbx_shard_layout;
+VBX_API int vbx_shard_layout_for(vbx_ctx* ctx, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out);
+VBX_API int vbx_shard_front(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3], const float* d_xyz,
+                    const uint8_t* d_rgba, uint64_t n, int freespace, const vbx_shard_layout* layout,
+                    void* d_pack, uint64_t* count_out);
+/* d_gathered holds world_size pack prefixes, pack_stride bytes apart (>= off_records + 16 * max
+ * count); counts = the world_size record counts (host memory). */
+VBX_API int vbx_shard_back(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3], uint64_t n,
+                   const vbx_shard_layout* layout, const void* d_gathered, uint64_t pack_stride,
+                   const uint64_t* counts);
+
 /* Measurement aids (the reference's counterpart is timing::Timer, utils/timing.h:132-199).
  * vbx_timer_start / vbx_timer_stop_ms bracket any number of calls with two CUDA events
  * recorded on the context's stream (device timeline, host gaps included).

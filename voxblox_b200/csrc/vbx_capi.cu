@@ -12,6 +12,11 @@ namespace vbx {
 int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
                      const uint8_t* d_rgba, uint64_t n, int freespace);
 size_t cub_temp_bytes(uint32_t max_points, uint64_t max_updates);
+int shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out);
+int shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz, const uint8_t* d_rgba,
+                uint64_t n, int freespace, const vbx_shard_layout* lay, void* d_pack, uint64_t* count_out);
+int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n, const vbx_shard_layout* lay,
+               const void* d_gathered, uint64_t pack_stride, const uint64_t* counts);
 int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
 
@@ -217,6 +222,28 @@ int vbx_tsdf_integrate(vbx_ctx* c, int kind, const float q[4], const float t[3],
     VBX_CUDA(c, cudaMemcpyAsync(c->d_rgba, rgba, n * 4, cudaMemcpyHostToDevice, c->stream));
   }
   return integrate_device(c, kind, q, t, c->d_xyz, c->d_rgba, n, freespace);
+}
+
+int vbx_shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out) {
+  if (!c || !out) return VBX_E_INVALID;
+  return shard_layout_for(c, n, record_capacity, out);
+}
+
+int vbx_shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
+                    const uint8_t* d_rgba, uint64_t n, int freespace, const vbx_shard_layout* lay, void* d_pack,
+                    uint64_t* count_out) {
+  if (!c || !q || !t || !lay || !d_pack || !count_out || (n && (!d_xyz || !d_rgba))) {
+    return fail(c, VBX_E_INVALID, "null argument");
+  }
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return shard_front(c, kind, q, t, d_xyz, d_rgba, n, freespace, lay, d_pack, count_out);
+}
+
+int vbx_shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n, const vbx_shard_layout* lay,
+                   const void* d_gathered, uint64_t pack_stride, const uint64_t* counts) {
+  if (!c || !q || !t || !lay || !d_gathered || !counts) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return shard_back(c, kind, q, t, n, lay, d_gathered, pack_stride, counts);
 }
 
 int vbx_get_counters(const vbx_ctx* c, uint64_t out[16]) {

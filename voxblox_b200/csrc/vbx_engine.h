@@ -149,6 +149,7 @@ struct vbx_ctx {
   // reporting
   uint64_t counters[16] = {0};
   uint64_t esdf_counters[16] = {0};
+  uint64_t shard_front_counters[4] = {0};
   float last_ms = 0.f;
   uint64_t launches = 0;
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // vbx_timer_*

@@ -62,6 +62,10 @@ struct ScanParams {
   int key_radius;
   int key_bits;
   int wide_keys;
+  // ray-range sharding (multi-GPU): this rank casts the rays whose slot lies in
+  // [slot_lo, slot_hi); shard != 0 defers all block-hash work to vbx_shard_back
+  uint32_t slot_lo, slot_hi;
+  int shard;
 };
 
 // MixedThreadSafeIndex::getNextIndexImpl, integrator_utils.cc:54-63
@@ -194,14 +198,14 @@ __global__ void k_sqnorm_keys(uint32_t n, const float* __restrict__ xyz, uint64_
 
 // Dense (unordered) list of bundle heads; a ray's rank stays its sorted position.
 template <typename KeyT>
-__global__ void k_heads(uint32_t n, const KeyT* __restrict__ keys, uint32_t* __restrict__ ray_list,
-                        uint32_t* __restrict__ cnt, ScanState* st) {
+__global__ void k_heads(uint32_t n, uint32_t slot_lo, uint32_t slot_hi, const KeyT* __restrict__ keys,
+                        uint32_t* __restrict__ ray_list, uint32_t* __restrict__ cnt, ScanState* st) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool head = false;
   if (i <= n) cnt[i] = 0;
   if (i < n) {
     const KeyT key = keys[i];
-    head = key != (KeyT)~(KeyT)0 && (i == 0 || keys[i - 1] != key);
+    head = key != (KeyT)~(KeyT)0 && (i == 0 || keys[i - 1] != key) && i >= slot_lo && i < slot_hi;
   }
   const unsigned b = __ballot_sync(0xffffffffu, head);
   if (b) {
@@ -475,7 +479,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   } else {
     i = t;
     if (i > P.n) return;
-    if (i == P.n) {
+    if (i == P.n || i < P.slot_lo || i >= P.slot_hi) {
       cnt[i] = 0;
       return;
     }
@@ -526,7 +530,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
       break;
     }
     const int bx = d.cx >> P.L, by = d.cy >> P.L, bz = d.cz >> P.L;
-    if (bx != lbx || by != lby || bz != lbz) {
+    if (!P.shard && (bx != lbx || by != lby || bz != lbz)) {
       const uint32_t hp = ensure_block(tab, pack3(bx, by, bz), st);
       if (hp == 0xffffffffu) break;
       mark_touched(tab, hp, P.epoch, st);
@@ -541,7 +545,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
 
 // Pool slots for the blocks created by this call, dense ranks for the touched ones.
 __global__ void k_assign(Tables tab, const uint32_t* __restrict__ off, uint32_t n, uint32_t n_blocks_before,
-                         uint64_t max_updates, ScanState* st) {
+                         uint64_t max_updates, ScanState* st, unsigned long long total_if_no_off = 0) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_new = min(st->n_new, tab.max_blocks);
   const uint32_t n_touched = min(st->n_touched, tab.max_blocks);
@@ -557,9 +561,10 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ off, uint32_t 
   }
   if (j < n_touched) tab.htouch_rank[tab.touched_list[j]] = j;
   if (j == 0) {
-    st->total_updates = off[n];
+    const unsigned long long total = off ? (unsigned long long)off[n] : total_if_no_off;
+    st->total_updates = total;
     st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
-    if ((uint64_t)off[n] > max_updates) atomicOr(&st->error, kErrUpdatesFull);
+    if (total > max_updates) atomicOr(&st->error, kErrUpdatesFull);
   }
 }
 
@@ -611,6 +616,109 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
     cvals[base + emitted] = i;
     ++emitted;
   }
+}
+
+// ------------------------------------------------------------- ray-range sharding
+// Multi-GPU: a rank's rays emit records keyed by GLOBAL voxel coordinates (17 bits per block
+// axis + 3L bits inside the block) so that every rank can apply every rank's records to its own
+// replica of the map.
+constexpr int kShardBias = 1 << 16;
+__device__ __forceinline__ bool shard_key(int bx, int by, int bz, uint32_t lin, int L, uint64_t* key) {
+  const int lim = kShardBias - 1;
+  if (bx < -lim || bx > lim || by < -lim || by > lim || bz < -lim || bz > lim) return false;
+  *key = ((((uint64_t)(uint32_t)(bz + kShardBias) << 34) | ((uint64_t)(uint32_t)(by + kShardBias) << 17) |
+           (uint64_t)(uint32_t)(bx + kShardBias))
+          << (3 * L)) |
+         lin;
+  return true;
+}
+__device__ __forceinline__ uint64_t shard_key_block(uint64_t key, int L) {
+  const uint64_t b = key >> (3 * L);
+  return pack3((int)(b & 0x1ffffu) - kShardBias, (int)((b >> 17) & 0x1ffffu) - kShardBias,
+               (int)((b >> 34) & 0x1ffffu) - kShardBias);
+}
+
+template <typename KeyT>
+__global__ void k_rays_emit_global(ScanParams P, const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
+                                   const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
+                                   const uint32_t* __restrict__ off, uint4* __restrict__ grec, uint64_t cap,
+                                   ScanState* st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i;
+  if (P.kind == VBX_MERGED) {
+    if (t >= st->n_ray_list) return;
+    i = ray_list[t];
+  } else {
+    i = t;
+    if (i >= P.n) return;
+  }
+  const uint32_t c = cnt[i];
+  if (c == 0) return;
+  const uint32_t base = off[i];
+  if ((uint64_t)base + c > cap) {
+    atomicOr(&st->error, kErrUpdatesFull);
+    return;
+  }
+  const float4 rp = ray_p[i];
+  const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
+  Dda d;
+  dda_setup(d, P.origin, f3(rp.x, rp.y, rp.z), clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
+            P.kind != VBX_FAST);
+  const KeyT own = (P.kind == VBX_MERGED) ? keys[i] : (KeyT)0;
+  uint32_t emitted = 0;
+  const int mask = (1 << P.L) - 1;
+  for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
+    if (P.kind == VBX_MERGED && P.anti_grazing) {
+      if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
+    }
+    const uint32_t lin = (uint32_t)(d.cx & mask) | ((uint32_t)(d.cy & mask) << P.L) |
+                         ((uint32_t)(d.cz & mask) << (2 * P.L));
+    uint64_t key = ~0ull;
+    if (!shard_key(d.cx >> P.L, d.cy >> P.L, d.cz >> P.L, lin, P.L, &key)) atomicOr(&st->error, kErrCoordRange);
+    grec[base + emitted] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), i, 0u);  // 16-byte record
+    ++emitted;
+  }
+}
+
+// the gathered records of all ranks, rank after rank (= ascending ray slots)
+struct ShardSegments {
+  const uint4* rec[8];  // (key lo, key hi, ray slot, pad)
+  unsigned long long start[9];  // prefix of the per-rank record counts
+  int world;
+};
+
+// find-or-create the block of every gathered record on THIS rank's replica
+__global__ void k_localize_blocks(ShardSegments seg, Tables tab, int L, uint32_t epoch, uint32_t* __restrict__ hp_of,
+                                  ScanState* st) {
+  const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= seg.start[seg.world]) return;
+  int r = 0;
+  while (p >= seg.start[r + 1]) ++r;
+  const uint4 rec = seg.rec[r][p - seg.start[r]];
+  const uint64_t key = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+  const uint32_t hp = ensure_block(tab, shard_key_block(key, L), st);
+  if (hp != 0xffffffffu) mark_touched(tab, hp, epoch, st);
+  hp_of[p] = hp;
+}
+
+__global__ void k_localize_keys(ShardSegments seg, Tables tab, int L, const uint32_t* __restrict__ hp_of,
+                                uint32_t* __restrict__ ckeys, uint32_t* __restrict__ cvals) {
+  const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= seg.start[seg.world]) return;
+  int r = 0;
+  while (p >= seg.start[r + 1]) ++r;
+  const unsigned long long j = p - seg.start[r];
+  const uint32_t hp = hp_of[p];
+  if (hp == 0xffffffffu) {
+    ckeys[p] = 0xffffffffu;
+    cvals[p] = 0;
+    return;
+  }
+  const uint4 rec = seg.rec[r][j];
+  const uint32_t lin = rec.x & ((1u << (3 * L)) - 1u);
+  ckeys[p] = (tab.htouch_rank[hp] << (3 * L)) | lin;
+  cvals[p] = rec.z;
+  tab.slot_updated[tab.hslot[hp]] = 7;  // (*last_block)->updated().set(), cc:128
 }
 
 // ----------------------------------------------------------------------- apply
@@ -872,7 +980,8 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     keys = kb.Current();
     vals = vb.Current();
     mk.mark(1);
-    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, keys, c->ray_list, c->cnt, c->d_state);
+    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, P.slot_lo, P.slot_hi, keys, c->ray_list, c->cnt,
+                                                               c->d_state);
     k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_a, c->ray_c,
                                            c->d_state);
     mk.mark(8);
@@ -901,14 +1010,10 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
   return VBX_OK;
 }
 
-template <typename KeyT>
-static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned long long K, uint32_t n_touched,
-                     Marks& mk, uint64_t* launches) {
+// update-record sort + the two apply kernels (shared by the single-GPU and the sharded path)
+static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K, uint32_t n_touched, Marks& mk,
+                          uint64_t* launches) {
   cudaStream_t s = c->stream;
-  const uint32_t n = P.n;
-  k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt,
-                                                      c->off, c->ckeys[0], c->cvals[0], c->d_state);
-  mk.mark(5);
   cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
   cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
   size_t tmp = c->cub_tmp_bytes;
@@ -920,21 +1025,25 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_a, c->ray_c,
                                        c->long_list, c->d_state);
   mk.mark(7);
-  *launches += 4 + (key_bits + 7) / 8;
+  *launches += 3 + (key_bits + 7) / 8;
   return VBX_OK;
 }
 
-int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
-                     const uint8_t* d_rgba, uint64_t n64, int freespace) {
-  if (kind < VBX_SIMPLE || kind > VBX_FAST) return fail(c, VBX_E_INVALID, "Unknown TSDF integrator type");
-  if (n64 > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
-  const uint32_t n = (uint32_t)n64;
+template <typename KeyT>
+static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned long long K, uint32_t n_touched,
+                     Marks& mk, uint64_t* launches) {
   cudaStream_t s = c->stream;
-  const vbx_tsdf_config& cfg = c->cfg;
-  std::memset(c->counters, 0, sizeof(c->counters));
-  uint64_t launches = 0;
+  const uint32_t n = P.n;
+  k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off,
+                                                      c->ckeys[0], c->cvals[0], c->d_state);
+  mk.mark(5);
+  *launches += 1;
+  return sort_and_apply(c, P, K, n_touched, mk, launches);
+}
 
-  ScanParams P;
+static void fill_params(vbx_ctx* c, int kind, const float q[4], const float t[3], uint32_t n, int freespace,
+                        ScanParams& P) {
+  const vbx_tsdf_config& cfg = c->cfg;
   std::memset(&P, 0, sizeof(P));
   P.T.w = q[0];
   P.T.x = q[1];
@@ -988,6 +1097,24 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     P.key_bits = bits_for((uint64_t)(2 * (int64_t)P.key_radius));
     P.wide_keys = (3 * P.key_bits + 1 > 32) ? 1 : 0;
   }
+
+  P.slot_lo = 0;
+  P.slot_hi = n;
+  P.shard = 0;
+}
+
+int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
+                     const uint8_t* d_rgba, uint64_t n64, int freespace) {
+  if (kind < VBX_SIMPLE || kind > VBX_FAST) return fail(c, VBX_E_INVALID, "Unknown TSDF integrator type");
+  if (n64 > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
+  const uint32_t n = (uint32_t)n64;
+  cudaStream_t s = c->stream;
+  const vbx_tsdf_config& cfg = c->cfg;
+  std::memset(c->counters, 0, sizeof(c->counters));
+  uint64_t launches = 0;
+
+  ScanParams P;
+  fill_params(c, kind, q, t, n, freespace, P);
 
   VBX_CUDA(c, cudaEventRecord(c->ev0, s));
   VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
@@ -1066,6 +1193,175 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   c->counters[6] = (kind == VBX_MERGED) ? c->h_state->n_valid_points
                                         : (uint64_t)c->h_state->n_rays + c->h_state->n_clear_rays;
   c->counters[7] = launches;
+  return VBX_OK;
+}
+
+// ------------------------------------------------------------- ray-range sharding, host side
+static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+int shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out) {
+  const uint64_t world = (uint64_t)c->opt.world_size;
+  if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
+  if (record_capacity == 0 || record_capacity * world > c->max_updates) {
+    return fail(c, VBX_E_CAPACITY, "record_capacity * world_size exceeds max_updates_per_pass");
+  }
+  out->record_capacity = record_capacity;
+  out->slice = (n + world - 1) / world;
+  out->off_ray_a = 0;
+  out->off_ray_c = out->slice * 16;
+  out->off_records = round_up(out->slice * 24, 256);
+  out->pack_bytes = out->off_records + record_capacity * 16;
+  return VBX_OK;
+}
+
+int shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz, const uint8_t* d_rgba,
+                uint64_t n64, int freespace, const vbx_shard_layout* lay, void* d_pack, uint64_t* count_out) {
+  if (kind != VBX_SIMPLE && kind != VBX_MERGED) {
+    return fail(c, VBX_E_INVALID, "ray-range sharding supports the simple and merged integrators");
+  }
+  if (n64 > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
+  const uint32_t n = (uint32_t)n64;
+  cudaStream_t s = c->stream;
+  uint64_t launches = 0;
+  ScanParams P;
+  fill_params(c, kind, q, t, n, freespace, P);
+  P.shard = 1;
+  P.slot_lo = (uint32_t)std::min<uint64_t>((uint64_t)c->opt.rank * lay->slice, n);
+  P.slot_hi = (uint32_t)std::min<uint64_t>((uint64_t)(c->opt.rank + 1) * lay->slice, n);
+  *count_out = 0;
+  VBX_CUDA(c, cudaEventRecord(c->ev0, s));
+  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+  if (n == 0) {
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    return VBX_OK;
+  }
+  Marks mk;
+  mk.c = c;
+  mk.s = s;
+  mk.begin();
+  const uint32_t* order = nullptr;
+  if (c->cfg.integration_order_mode == 1) {
+    k_sqnorm_keys<<<grid_for(n, 256), 256, 0, s>>>(n, d_xyz, c->pkeys[0], c->pvals[0]);
+    cub::DoubleBuffer<uint64_t> kb(c->pkeys[0], c->pkeys[1]);
+    cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
+    size_t tmp = c->cub_tmp_bytes;
+    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, 64, s));
+    VBX_CUDA(c, cudaMemcpyAsync(c->order, vb.Current(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    order = c->order;
+  }
+  const uint32_t* keys32 = nullptr;
+  const uint64_t* keys64 = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (P.wide_keys) {
+      if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
+    } else {
+      if (int rc = front_half<uint32_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys32)) return rc;
+    }
+    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+    if (!(c->h_state->error & kNeedWideKeys)) break;
+    VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+    P.wide_keys = 1;
+  }
+  const unsigned long long K = c->h_state->total_updates;
+  if (K > lay->record_capacity) return fail(c, VBX_E_CAPACITY, "this rank's update records exceed record_capacity");
+  char* pack = static_cast<char*>(d_pack);
+  if (K > 0) {
+    uint4* grec = reinterpret_cast<uint4*>(pack + lay->off_records);
+    if (P.wide_keys) {
+      k_rays_emit_global<uint64_t><<<grid_for(n, 128), 128, 0, s>>>(P, keys64, c->ray_list, c->ray_p, c->cnt, c->off,
+                                                                     grec, lay->record_capacity, c->d_state);
+    } else {
+      k_rays_emit_global<uint32_t><<<grid_for(n, 128), 128, 0, s>>>(P, keys32, c->ray_list, c->ray_p, c->cnt, c->off,
+                                                                     grec, lay->record_capacity, c->d_state);
+    }
+    launches += 1;
+  }
+  const uint32_t len = P.slot_hi - P.slot_lo;
+  if (len > 0) {
+    VBX_CUDA(c, cudaMemcpyAsync(pack + lay->off_ray_a, c->ray_a + P.slot_lo, (size_t)len * sizeof(float4),
+                                cudaMemcpyDeviceToDevice, s));
+    VBX_CUDA(c, cudaMemcpyAsync(pack + lay->off_ray_c, c->ray_c + P.slot_lo, (size_t)len * sizeof(uint2),
+                                cudaMemcpyDeviceToDevice, s));
+  }
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+  mk.collect();
+  c->launches += launches;
+  c->shard_front_counters[0] = c->h_state->n_rays;
+  c->shard_front_counters[1] = c->h_state->n_clear_rays;
+  c->shard_front_counters[2] = c->h_state->n_valid_points;
+  c->shard_front_counters[3] = launches;
+  *count_out = K;
+  return VBX_OK;
+}
+
+int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n64, const vbx_shard_layout* lay,
+               const void* d_gathered, uint64_t pack_stride, const uint64_t* counts) {
+  const int world = c->opt.world_size;
+  if (world > 8) return fail(c, VBX_E_INVALID, "at most 8 ranks");
+  const uint32_t n = (uint32_t)n64;
+  cudaStream_t s = c->stream;
+  uint64_t launches = 0;
+  std::memset(c->counters, 0, sizeof(c->counters));
+  ScanParams P;
+  fill_params(c, kind, q, t, n, 0, P);
+  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+  ShardSegments seg;
+  std::memset(&seg, 0, sizeof(seg));
+  seg.world = world;
+  const char* base = static_cast<const char*>(d_gathered);
+  for (int r = 0; r < world; ++r) {
+    const char* pack = base + (size_t)r * pack_stride;
+    seg.rec[r] = reinterpret_cast<const uint4*>(pack + lay->off_records);
+    if (counts[r] > lay->record_capacity || lay->off_records + counts[r] * 16 > pack_stride) {
+      return fail(c, VBX_E_INVALID, "count exceeds the gathered pack");
+    }
+    seg.start[r + 1] = seg.start[r] + counts[r];
+    const uint64_t lo = std::min<uint64_t>((uint64_t)r * lay->slice, n), hi = std::min<uint64_t>((uint64_t)(r + 1) * lay->slice, n);
+    if (hi > lo) {
+      VBX_CUDA(c, cudaMemcpyAsync(c->ray_a + lo, pack + lay->off_ray_a, (hi - lo) * sizeof(float4),
+                                  cudaMemcpyDeviceToDevice, s));
+      VBX_CUDA(c, cudaMemcpyAsync(c->ray_c + lo, pack + lay->off_ray_c, (hi - lo) * sizeof(uint2),
+                                  cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  const unsigned long long K = seg.start[world];
+  if (K > c->max_updates) return fail(c, VBX_E_CAPACITY, "gathered update records exceed max_updates_per_pass");
+  Marks mk;
+  mk.c = c;
+  mk.s = s;
+  mk.begin();
+  uint32_t n_touched = 0;
+  if (K > 0) {
+    uint32_t* hp_of = c->cvals[1];
+    k_localize_blocks<<<grid_for(K, 256), 256, 0, s>>>(seg, c->tab, c->L, P.epoch, hp_of, c->d_state);
+    k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, nullptr, 0, c->n_blocks, c->max_updates,
+                                                              c->d_state, K);
+    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+    c->n_blocks = c->h_state->n_blocks;
+    n_touched = c->h_state->n_touched;
+    k_localize_keys<<<grid_for(K, 256), 256, 0, s>>>(seg, c->tab, c->L, hp_of, c->ckeys[0], c->cvals[0]);
+    mk.mark(5);
+    launches += 3;
+    if (int rc = sort_and_apply(c, P, K, n_touched, mk, &launches)) return rc;
+  }
+  VBX_CUDA(c, cudaEventRecord(c->ev1, s));
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
+  VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  mk.collect();
+  c->launches += launches;
+  c->counters[2] = K;
+  c->counters[3] = c->h_state->n_voxels;
+  c->counters[4] = n_touched;
+  c->counters[5] = c->h_state->n_new;
+  c->counters[7] = launches + c->shard_front_counters[3];
   return VBX_OK;
 }
 
