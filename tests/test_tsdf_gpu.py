@@ -53,3 +53,125 @@ def test_room_sequence_small(kind, order):
     rep = _run(kind, scans, 0.1, 0.4, order)
     print(rep)
     _assert_parity(rep)
+
+
+# ----------------------------------------------------------------------------- edge cases
+def _small_scans(n=2, w=96, h=72):
+    return scenes.c3_room_sequence(n_scans=n, width=w, height=h)
+
+
+@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_CANONICAL)])
+@pytest.mark.parametrize("cfg_kw", [
+    dict(use_const_weight=1),
+    dict(voxel_carving_enabled=0),
+    dict(use_weight_dropoff=0),
+    dict(use_sparsity_compensation_factor=1, sparsity_compensation_factor=3.0),
+    dict(max_ray_length_m=2.0),                    # far points become clearing rays (allow_clear)
+    dict(max_ray_length_m=2.0, allow_clear=0),     # ... or are dropped
+    dict(min_ray_length_m=1.5),
+    dict(max_weight=5.0),                          # the weight clamp fires
+    dict(integration_order_mode=1),                # "sorted"
+], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_config_variants(kind, order, cfg_kw):
+    if cfg_kw.get("integration_order_mode") == 1:
+        # std::sort leaves ties unspecified; the room scans have no exact |p|^2 ties
+        pass
+    rep = _run(kind, _small_scans(), 0.1, 0.4, order, **cfg_kw)
+    print(rep)
+    _assert_parity(rep)
+
+
+def test_merged_anti_grazing():
+    rep = _run(2, _small_scans(), 0.1, 0.4, po.ORDER_CANONICAL, enable_anti_grazing=1)
+    print(rep)
+    _assert_parity(rep)
+
+
+@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_CANONICAL)])
+def test_freespace_points(kind, order):
+    """freespace_points=true: every ray is a clearing ray (tsdf_integrator.h:96-99)."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create(kind, cfg, layer)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 16)
+    for s in _small_scans():
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1], freespace_points=True)
+        omap.integrate(kind, s, freespace=True, order=order)
+    rep = compare_tsdf(layer, omap)
+    print(rep)
+    _assert_parity(rep)
+
+
+def test_far_clearing_points_use_wide_keys():
+    """Points far beyond max_ray_length fall outside the compact bundle-key range: the call is
+    redone with full-width keys and must still match."""
+    s = _small_scans(1)[0]
+    pts = s[0].copy()
+    pts[::7] *= 40.0      # ~100 m away: clearing rays whose end voxels are thousands of voxels off
+    scan = (pts, s[1], s[2], s[3])
+    rep = _run(2, [scan], 0.1, 0.4, po.ORDER_CANONICAL)
+    print(rep)
+    _assert_parity(rep)
+
+
+def test_degenerate_clouds():
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    s = _small_scans(1)[0]
+    # empty cloud
+    integ.integratePointCloud((s[2], s[3]), np.zeros((0, 3), np.float32), np.zeros((0, 4), np.uint8))
+    assert layer.getNumberOfAllocatedBlocks() == 0
+    # every point invalid (closer than min_ray_length_m) or non-finite
+    pts = np.full((100, 3), 0.01, np.float32)
+    pts[50:] = np.nan
+    pts[75:] = np.inf
+    integ.integratePointCloud((s[2], s[3]), pts, np.zeros((100, 4), np.uint8))
+    assert layer.getNumberOfAllocatedBlocks() == 0
+    assert integ.counters()["rays"] == 0
+    # mismatched sizes: CHECK_EQ(points_C.size(), colors.size()), tsdf_integrator.cc:312
+    with pytest.raises(vb.VoxbloxError):
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1][:-1])
+    # a cloud larger than the engine was sized for is refused, not truncated
+    small = vb.Layer(0.1, 16, engine_options=vb.EngineOptions(max_points_per_scan=1024))
+    integ2 = vb.TsdfIntegratorFactory.create("merged", cfg, small)
+    with pytest.raises(vb.VoxbloxError):
+        integ2.integratePointCloud((s[2], s[3]), s[0], s[1])
+
+
+def test_voxels_per_side_8():
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 8)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 8)
+    for s in _small_scans():
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    gi, oi = layer.getAllAllocatedBlocks(), omap.block_indices()
+    assert gi.shape == oi.shape and (gi == oi).all()
+    gv, _ = layer.getBlocks(gi)
+    ov = np.stack([omap.block(i)[0] for i in oi])
+    assert gv.tobytes() == ov.tobytes()
+
+
+def test_fast_integrator_statistics():
+    """The Fast integrator is approximate by design (lossy sets, racy in the reference with more
+    than one thread): block set and per-voxel values are compared statistically."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("fast", cfg, layer)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 16)
+    for s in scenes.c3_room_sequence(n_scans=4, width=160, height=120):
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(3, s)
+    gb, ob = layer.blocks(), omap.blocks()
+    common = set(gb) & set(ob)
+    assert len(common) >= 0.9 * max(len(gb), len(ob))
+    g = np.stack([gb[k] for k in sorted(common)])
+    o = np.stack([ob[k] for k in sorted(common)])
+    both = (g["weight"] > 0) & (o["weight"] > 0)
+    either = (g["weight"] > 0) | (o["weight"] > 0)
+    assert both.sum() >= 0.9 * either.sum()
+    rmse = float(np.sqrt(np.mean((g["distance"][both] - o["distance"][both]) ** 2)))
+    print("fast: blocks", len(gb), len(ob), "observed overlap", both.sum() / either.sum(), "rmse", rmse)
+    assert rmse < 0.1  # one voxel
