@@ -1,0 +1,168 @@
+// voxblox-side adapter: plugs the B200 engine in underneath voxblox's own integrator API.
+//
+// GpuTsdfIntegrator IS-A voxblox::TsdfIntegratorBase (voxblox/integrator/tsdf_integrator.h:51-198):
+// same constructor arguments, same virtual integratePointCloud(), so TsdfServer / TsdfMap /
+// user code keep working unchanged.  The voxel blocks live in HBM; the host Layer<TsdfVoxel>
+// stays the reference's own container and is refreshed on demand by syncLayer() (only blocks
+// whose updated() bits are set are downloaded -- SURVEY.md section 8f N1).
+//
+// This header is compiled against the REFERENCE's headers (it includes them); it contains no
+// reference code.  See INTEGRATION.md for the three-line change to TsdfIntegratorFactory::create.
+#ifndef VOXBLOX_B200_GPU_INTEGRATORS_H_
+#define VOXBLOX_B200_GPU_INTEGRATORS_H_
+
+#include <cstring>
+#include <vector>
+
+#include <voxblox/core/layer.h>
+#include <voxblox/core/voxel.h>
+#include <voxblox/integrator/esdf_integrator.h>
+#include <voxblox/integrator/tsdf_integrator.h>
+
+#include "../voxblox_b200.h"
+
+namespace voxblox {
+
+static_assert(sizeof(TsdfVoxel) == 12, "TsdfVoxel must be the 12-byte struct of core/voxel.h:12-16");
+static_assert(sizeof(EsdfVoxel) == 20, "EsdfVoxel must be the 20-byte struct of core/voxel.h:18-37");
+static_assert(sizeof(Point) == 12 && sizeof(Color) == 4, "Pointcloud / Colors must be packed xyz / rgba");
+
+namespace gpu_detail {
+inline vbx_tsdf_config toPod(const TsdfIntegratorBase::Config& c) {
+  vbx_tsdf_config p;
+  p.default_truncation_distance = c.default_truncation_distance;
+  p.max_weight = c.max_weight;
+  p.voxel_carving_enabled = c.voxel_carving_enabled;
+  p.min_ray_length_m = c.min_ray_length_m;
+  p.max_ray_length_m = c.max_ray_length_m;
+  p.use_const_weight = c.use_const_weight;
+  p.allow_clear = c.allow_clear;
+  p.use_weight_dropoff = c.use_weight_dropoff;
+  p.use_sparsity_compensation_factor = c.use_sparsity_compensation_factor;
+  p.sparsity_compensation_factor = c.sparsity_compensation_factor;
+  p.integrator_threads = static_cast<int32_t>(c.integrator_threads);
+  if (c.integration_order_mode == "mixed") {
+    p.integration_order_mode = 0;
+  } else if (c.integration_order_mode == "sorted") {
+    p.integration_order_mode = 1;
+  } else {  // ThreadSafeIndexFactory::get, integrator_utils.cc:12
+    LOG(FATAL) << "Unknown integration order mode: '" << c.integration_order_mode << "'!";
+    p.integration_order_mode = 0;
+  }
+  p.enable_anti_grazing = c.enable_anti_grazing;
+  p.start_voxel_subsampling_factor = c.start_voxel_subsampling_factor;
+  p.max_consecutive_ray_collisions = c.max_consecutive_ray_collisions;
+  p.clear_checks_every_n_frames = c.clear_checks_every_n_frames;
+  p.max_integration_time_s = c.max_integration_time_s;
+  return p;
+}
+inline vbx_esdf_config toPod(const EsdfIntegrator::Config& c) {
+  vbx_esdf_config p;
+  p.full_euclidean_distance = c.full_euclidean_distance;
+  p.max_distance_m = c.max_distance_m;
+  p.min_distance_m = c.min_distance_m;
+  p.default_distance_m = c.default_distance_m;
+  p.min_diff_m = c.min_diff_m;
+  p.min_weight = c.min_weight;
+  p.num_buckets = c.num_buckets;
+  p.multi_queue = c.multi_queue;
+  p.add_occupied_crust = c.add_occupied_crust;
+  p.clear_sphere_radius = c.clear_sphere_radius;
+  p.occupied_sphere_radius = c.occupied_sphere_radius;
+  return p;
+}
+// the reference aborts on errors (glog CHECK / LOG(FATAL)); keep that behaviour
+inline void check(vbx_ctx* ctx, int rc, const char* what) {
+  if (rc != VBX_OK) LOG(FATAL) << what << " failed (" << rc << "): " << vbx_last_error(ctx);
+}
+// device -> host: refresh (or create) the host blocks listed by the device
+template <typename VoxelType>
+inline size_t downloadBlocks(vbx_ctx* ctx, int layer_id, int updated_mask, Layer<VoxelType>* layer) {
+  uint64_t n = 0;
+  check(ctx, vbx_list_blocks(ctx, layer_id, updated_mask, nullptr, 0, &n), "vbx_list_blocks");
+  if (n == 0) return 0;
+  std::vector<int32_t> idx(3 * n);
+  check(ctx, vbx_list_blocks(ctx, layer_id, updated_mask, idx.data(), n, &n), "vbx_list_blocks");
+  const size_t vpb = layer->voxels_per_side() * layer->voxels_per_side() * layer->voxels_per_side();
+  std::vector<VoxelType> vox(vpb * n);
+  std::vector<uint8_t> upd(n);
+  check(ctx, vbx_download_blocks(ctx, layer_id, idx.data(), n, vox.data(), upd.data()), "vbx_download_blocks");
+  for (uint64_t b = 0; b < n; ++b) {
+    typename Block<VoxelType>::Ptr block =
+        layer->allocateBlockPtrByIndex(BlockIndex(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2]));
+    std::memcpy(&block->getVoxelByLinearIndex(0), vox.data() + b * vpb, vpb * sizeof(VoxelType));
+    for (int bit = 0; bit < static_cast<int>(Update::kCount); ++bit) {
+      if (upd[b] & (1u << bit)) block->updated().set(bit);
+    }
+  }
+  return n;
+}
+}  // namespace gpu_detail
+
+class GpuTsdfIntegrator : public TsdfIntegratorBase {
+ public:
+  EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+  GpuTsdfIntegrator(TsdfIntegratorType type, const Config& config, Layer<TsdfVoxel>* layer,
+                    const vbx_engine_options* options = nullptr)
+      : TsdfIntegratorBase(config, layer), type_(type), ctx_(nullptr) {
+    CHECK_EQ(layer->getNumberOfAllocatedBlocks(), 0u)
+        << "GpuTsdfIntegrator: start from an empty layer (existing blocks: vbx_upload_blocks)";
+    const vbx_tsdf_config pod = gpu_detail::toPod(config_);
+    const int rc = vbx_create(&pod, voxel_size_, static_cast<int>(voxels_per_side_), options, &ctx_);
+    if (rc != VBX_OK) LOG(FATAL) << "vbx_create failed (" << rc << "): " << vbx_last_error(ctx_);
+  }
+  ~GpuTsdfIntegrator() { vbx_destroy(ctx_); }
+
+  void integratePointCloud(const Transformation& T_G_C, const Pointcloud& points_C, const Colors& colors,
+                           const bool freespace_points = false) override {
+    CHECK_EQ(points_C.size(), colors.size());  // tsdf_integrator.cc:247,312,560
+    const float q[4] = {T_G_C.getRotation().w(), T_G_C.getRotation().x(), T_G_C.getRotation().y(),
+                        T_G_C.getRotation().z()};
+    const Point p = T_G_C.getPosition();
+    const float t[3] = {p.x(), p.y(), p.z()};
+    gpu_detail::check(ctx_,
+                      vbx_tsdf_integrate(ctx_, static_cast<int>(type_), q, t,
+                                         points_C.empty() ? nullptr : reinterpret_cast<const float*>(points_C.data()),
+                                         colors.empty() ? nullptr : reinterpret_cast<const uint8_t*>(colors.data()),
+                                         points_C.size(), freespace_points ? 1 : 0),
+                      "vbx_tsdf_integrate");
+  }
+
+  /// Bring the host Layer<TsdfVoxel> up to date: downloads every block whose updated() bits
+  /// match `updated_mask` (0 = all blocks).  Call it before host code reads the layer (meshing,
+  /// saving, interpolation); like the reference, clearing the bits is the consumer's job.
+  size_t syncLayer(int updated_mask = 0) { return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_TSDF, updated_mask, layer_); }
+
+  vbx_ctx* context() { return ctx_; }
+
+ private:
+  TsdfIntegratorType type_;
+  vbx_ctx* ctx_;
+};
+
+/// EsdfIntegrator's update entry points (esdf_integrator.h:101-106) on the device map owned by a
+/// GpuTsdfIntegrator.
+class GpuEsdfIntegrator {
+ public:
+  GpuEsdfIntegrator(const EsdfIntegrator::Config& config, GpuTsdfIntegrator* tsdf, Layer<EsdfVoxel>* esdf_layer)
+      : ctx_(CHECK_NOTNULL(tsdf)->context()), esdf_layer_(CHECK_NOTNULL(esdf_layer)) {
+    const vbx_esdf_config pod = gpu_detail::toPod(config);
+    gpu_detail::check(ctx_, vbx_esdf_create(ctx_, &pod), "vbx_esdf_create");
+  }
+  void updateFromTsdfLayer(bool clear_updated_flag) {
+    gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 0, clear_updated_flag ? 1 : 0), "vbx_esdf_update");
+  }
+  void updateFromTsdfLayerBatch() { gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 1, 0), "vbx_esdf_update"); }
+  size_t syncLayer(int updated_mask = 0) {
+    return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_ESDF, updated_mask, esdf_layer_);
+  }
+
+ private:
+  vbx_ctx* ctx_;
+  Layer<EsdfVoxel>* esdf_layer_;
+};
+
+}  // namespace voxblox
+
+#endif  // VOXBLOX_B200_GPU_INTEGRATORS_H_

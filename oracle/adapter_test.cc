@@ -1,0 +1,121 @@
+// TEST PROGRAM (oracle/, built only where /root/reference exists): drives the voxblox-side
+// adapter include/voxblox_b200/gpu_integrators.h through the reference's OWN headers and
+// classes, next to the reference's CPU integrators, the way test/test_sdf_integrators.cc does.
+// Simple must agree voxel for voxel (same update order); Merged is compared on the block set
+// and statistically (its CPU order is unordered_map iteration order).  Exit code 0 = pass.
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <vector>
+
+#include "voxblox_b200/gpu_integrators.h"
+
+using namespace voxblox;  // NOLINT
+
+static void makeScan(int k, Transformation* T, Pointcloud* pts, Colors* cols) {
+  // a wall at z = 3 m and a floor, seen by a 96x72 pinhole camera from slightly different poses
+  const float yaw = 0.05f * k, pitch = -0.03f * k;
+  const float cy = std::cos(yaw / 2), sy = std::sin(yaw / 2), cp = std::cos(pitch / 2), sp = std::sin(pitch / 2);
+  const Rotation rot(cy * cp, -sy * sp, cy * sp, sy * cp);  // not exactly unit: kept as is on both paths
+  *T = Transformation(rot, Point(0.013f + 0.1f * k, 0.021f, 0.017f));
+  pts->clear();
+  cols->clear();
+  for (int v = 0; v < 72; ++v) {
+    for (int u = 0; u < 96; ++u) {
+      const float dx = (u - 47.6f) / 80.0f, dy = (v - 35.7f) / 80.0f;
+      float depth = 3.0f + 0.2f * std::sin(0.3f * u) * std::cos(0.2f * v);
+      if (dy > 0.25f) depth = 1.2f / dy * 0.4f;  // "floor"
+      if (depth > 4.5f || depth < 0.5f) continue;
+      pts->push_back(Point(dx * depth, dy * depth, depth));
+      cols->push_back(Color(static_cast<uint8_t>(u * 2), static_cast<uint8_t>(v * 3), 128, 255));
+    }
+  }
+}
+
+template <typename V>
+static std::vector<BlockIndex> sortedBlocks(const Layer<V>& l) {
+  BlockIndexList b;
+  l.getAllAllocatedBlocks(&b);
+  std::vector<BlockIndex> v(b.begin(), b.end());
+  std::sort(v.begin(), v.end(), [](const BlockIndex& a, const BlockIndex& c) {
+    if (a.x() != c.x()) return a.x() < c.x();
+    if (a.y() != c.y()) return a.y() < c.y();
+    return a.z() < c.z();
+  });
+  return v;
+}
+
+int main() {
+  const float voxel_size = 0.1f;
+  TsdfIntegratorBase::Config config;
+  config.default_truncation_distance = 0.4f;
+  config.integrator_threads = 1;
+  int failures = 0;
+  for (int type = 1; type <= 2; ++type) {
+    Layer<TsdfVoxel> cpu_layer(voxel_size, 16), gpu_layer(voxel_size, 16);
+    TsdfIntegratorBase::Ptr cpu = TsdfIntegratorFactory::create(static_cast<TsdfIntegratorType>(type), config, &cpu_layer);
+    // the drop-in: same base-class pointer type, same call
+    std::shared_ptr<GpuTsdfIntegrator> gpu_impl(
+        new GpuTsdfIntegrator(static_cast<TsdfIntegratorType>(type), config, &gpu_layer));
+    TsdfIntegratorBase::Ptr gpu = gpu_impl;
+    for (int k = 0; k < 4; ++k) {
+      Transformation T;
+      Pointcloud pts;
+      Colors cols;
+      makeScan(k, &T, &pts, &cols);
+      cpu->integratePointCloud(T, pts, cols);
+      gpu->integratePointCloud(T, pts, cols);
+    }
+    gpu_impl->syncLayer(0);
+    const std::vector<BlockIndex> a = sortedBlocks(cpu_layer), b = sortedBlocks(gpu_layer);
+    bool same_blocks = a.size() == b.size();
+    for (size_t i = 0; same_blocks && i < a.size(); ++i) same_blocks = a[i] == b[i];
+    size_t n = 0, exact = 0, observed = 0;
+    double se = 0;
+    if (same_blocks) {
+      for (const BlockIndex& bi : a) {
+        const Block<TsdfVoxel>& x = cpu_layer.getBlockByIndex(bi);
+        const Block<TsdfVoxel>& y = gpu_layer.getBlockByIndex(bi);
+        for (size_t l = 0; l < x.num_voxels(); ++l) {
+          const TsdfVoxel& p = x.getVoxelByLinearIndex(l);
+          const TsdfVoxel& q = y.getVoxelByLinearIndex(l);
+          ++n;
+          if (p.distance == q.distance && p.weight == q.weight && p.color.r == q.color.r && p.color.g == q.color.g &&
+              p.color.b == q.color.b && p.color.a == q.color.a) {
+            ++exact;
+          }
+          if (p.weight > 0 || q.weight > 0) {
+            ++observed;
+            se += (p.distance - q.distance) * (p.distance - q.distance);
+          }
+        }
+      }
+    }
+    const double rmse = observed ? std::sqrt(se / observed) : 0.0;
+    std::printf("type %d (%s): blocks cpu %zu gpu %zu same %d, voxels %zu bit-exact %zu, rmse %.3g\n", type,
+                type == 1 ? "simple" : "merged", a.size(), b.size(), same_blocks ? 1 : 0, n, exact, rmse);
+    if (!same_blocks) ++failures;
+    if (type == 1 && exact != n) ++failures;                 // same update order: bit-identical
+    if (type == 2 && !(rmse < 0.25 * voxel_size)) ++failures;  // CPU order = hash-map iteration order
+  }
+  // ESDF through the adapter: incremental update after a scan, then batch
+  {
+    Layer<TsdfVoxel> tsdf(voxel_size, 16);
+    Layer<EsdfVoxel> esdf(voxel_size, 16);
+    GpuTsdfIntegrator gpu(TsdfIntegratorType::kMerged, config, &tsdf);
+    EsdfIntegrator::Config ec;
+    ec.min_distance_m = 0.2f;
+    GpuEsdfIntegrator ge(ec, &gpu, &esdf);
+    Transformation T;
+    Pointcloud pts;
+    Colors cols;
+    makeScan(0, &T, &pts, &cols);
+    gpu.integratePointCloud(T, pts, cols);
+    ge.updateFromTsdfLayer(true);
+    const size_t nb = ge.syncLayer(0);
+    std::printf("esdf blocks %zu (tsdf %zu)\n", nb, gpu.syncLayer(0));
+    if (nb == 0 || esdf.getNumberOfAllocatedBlocks() != tsdf.getNumberOfAllocatedBlocks()) ++failures;
+  }
+  std::printf(failures ? "ADAPTER TEST FAILED\n" : "ADAPTER TEST OK\n");
+  return failures ? 1 : 0;
+}
