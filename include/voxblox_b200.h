@@ -228,6 +228,11 @@ VBX_API int vbx_shard_back(vbx_ctx* ctx, int kind, const float q_wxyz[4], const 
 VBX_API int vbx_host_alloc(vbx_ctx* ctx, size_t bytes, void** out);
 VBX_API int vbx_host_free(vbx_ctx* ctx, void* p);
 VBX_API int vbx_host_copy_ms(vbx_ctx* ctx, const void* src, size_t bytes, float* ms);
+/* Test hooks for the engine's own device primitives (stable radix sort with a device-side
+ * element count, exclusive scan); host arrays in, host arrays out. */
+VBX_API int vbx_debug_sort(vbx_ctx* ctx, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
+                   uint32_t* perm_out);
+VBX_API int vbx_debug_scan(vbx_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out);
 VBX_API int vbx_timer_start(vbx_ctx* ctx);
 VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms);
 VBX_API int vbx_set_stage_profiling(vbx_ctx* ctx, int enabled);

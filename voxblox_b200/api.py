@@ -113,7 +113,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync",
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
-           "vbx_shard_back"]
+           "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan"]
 
 _lib = None
 

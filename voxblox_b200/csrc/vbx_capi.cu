@@ -3,9 +3,11 @@
 // INTEGRATION.md) and the entry points that dispatch into the device pipelines.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "vbx_engine.h"
+#include "vbx_sort.cuh"
 
 namespace vbx {
 
@@ -17,6 +19,9 @@ int shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const 
                 uint64_t n, int freespace, const vbx_shard_layout* lay, void* d_pack, uint64_t* count_out);
 int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n, const vbx_shard_layout* lay,
                const void* d_gathered, uint64_t pack_stride, const uint64_t* counts);
+int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
+               uint32_t* vals_out);
+int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out);
 int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
 
@@ -158,6 +163,19 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->ray_a, np));
   CK(dmalloc(&c->cnt, np + 1));
   CK(dmalloc(&c->off, np + 1));
+  {
+    // own sort / scan state; VBX_USE_CUB=1 selects the library sort (A/B measurements)
+    const char* env = std::getenv("VBX_USE_CUB");
+    c->use_cub = env && env[0] == '1';
+    c->sort_tiles_cap[0] = (uint32_t)((np + kSortTile - 1) / kSortTile);
+    c->sort_tiles_cap[1] = (uint32_t)((c->max_updates + kSortTile - 1) / kSortTile);
+    for (int i = 0; i < 2; ++i) {
+      CK(dmalloc(&c->sort_plan[i], 1));
+      const size_t words = (size_t)(i == 0 ? 8 : 4) * c->sort_tiles_cap[i] * kRadix;
+      CK(dmalloc(&c->sort_status[i], words));
+    }
+    CK(dmalloc(&c->scan_status, (np + 1) / kScanTile + 4));
+  }
   c->cub_tmp_bytes = cub_temp_bytes(c->max_points, c->max_updates);
   CK(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
   CK(dmalloc(&c->set_start, 1u << 20));
@@ -183,7 +201,8 @@ void vbx_destroy(vbx_ctx* c) {
                   c->d_rgba,      c->pkeys[0],   c->pkeys[1],    c->pvals[0],   c->pvals[1], c->ckeys[0],
                   c->ckeys[1],    c->cvals[0],   c->cvals[1],    c->order,      c->ray_p,    c->ray_c,
                   c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
-                  c->ray_list,    c->long_list,  c->ray_a};
+                  c->ray_list,    c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
+                  c->sort_status[0], c->sort_status[1], c->scan_status};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }
@@ -244,6 +263,19 @@ int vbx_shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uin
   if (!c || !q || !t || !lay || !d_gathered || !counts) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
   return shard_back(c, kind, q, t, n, lay, d_gathered, pack_stride, counts);
+}
+
+int vbx_debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
+                   uint32_t* vals_out) {
+  if (!c || (n && (!keys || !keys_out || !vals_out))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return debug_sort(c, keys, key_bytes, n, key_bits, keys_out, vals_out);
+}
+
+int vbx_debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {
+  if (!c || (n && (!in || !out))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return debug_scan(c, in, n, out);
 }
 
 int vbx_get_counters(const vbx_ctx* c, uint64_t out[16]) {

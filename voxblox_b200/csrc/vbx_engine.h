@@ -13,6 +13,10 @@
 #include "vbx_math.cuh"
 
 namespace vbx {
+struct SortPlan;
+}
+
+namespace vbx {
 
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint64_t kInvalidPointKey = ~0ull;
@@ -44,7 +48,8 @@ struct ScanState {
   uint32_t n_valid_points;
   uint32_t n_voxels;         // distinct voxels updated (U)
   uint32_t n_blocks;         // pool slots in use after the call
-  unsigned long long total_updates;  // K
+  unsigned long long total_updates;  // K the back half runs on (0 when the call failed / is redone)
+  unsigned long long total_found;    // K as counted
   // ESDF
   uint32_t esdf_counts[8];
   uint32_t frontier_n[2];
@@ -122,6 +127,12 @@ struct vbx_ctx {
   uint32_t* off = nullptr;    // [max_points + 1]
   uint32_t* ckeys[2] = {nullptr, nullptr};
   uint32_t* cvals[2] = {nullptr, nullptr};
+  // the engine's own radix sort / scan (vbx_sort.cuh): [0] point keys, [1] update records
+  bool use_cub = false;
+  vbx::SortPlan* sort_plan[2] = {nullptr, nullptr};
+  uint32_t* sort_status[2] = {nullptr, nullptr};
+  uint32_t sort_tiles_cap[2] = {0, 0};
+  uint32_t* scan_status = nullptr;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
   unsigned long long* set_start = nullptr;  // Fast integrator approximate sets

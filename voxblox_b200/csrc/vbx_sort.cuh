@@ -1,0 +1,274 @@
+// Hand-written device primitives for the integration pipeline: a stable LSD radix sort of
+// (key, value) pairs whose element count lives in DEVICE memory, and an exclusive prefix sum.
+//
+// Both are single-pass "chained scan" designs (one kernel per radix pass, one kernel for the
+// scan): a tile publishes its local aggregate, looks back over its predecessors' status words
+// until it meets an inclusive prefix, publishes its own inclusive prefix and scatters.  Tiles are
+// handed out through an atomic ticket, so every predecessor of a running tile is itself running
+// or finished (no deadlock regardless of block scheduling).  A status word packs a 2-bit flag and
+// a 30-bit count, so flag and value travel in one 32-bit store and no fence is needed.
+//
+// Why not a library sort: (1) the number of update records K is only known on the device; a
+// library call needs it on the host, which costs a stream synchronisation in the middle of every
+// integratePointCloud call; (2) passes whose digit is the same for every key (typical for the
+// compact bundle keys and for small maps) are detected on the device and skipped.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vbx {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                              // per thread
+constexpr int kSortTile = kSortThreads * kSortItems;        // 4096 elements
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 8;
+constexpr uint32_t kFlagAggregate = 1u << 30, kFlagPrefix = 2u << 30, kValueMask = (1u << 30) - 1u;
+
+struct SortPlan {  // device resident; zeroed by the host before every sort
+  uint32_t n;
+  uint32_t n_tiles;
+  uint32_t final_buf;                 // 0: sorted data is in buffer A (the input), 1: in buffer B
+  uint32_t done_blocks;
+  uint32_t active[kMaxPasses];
+  uint32_t src_buf[kMaxPasses];
+  uint32_t tile_counter[kMaxPasses];
+  uint32_t hist[kMaxPasses][kRadix];  // global digit histograms
+};
+
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
+// exclusive scan of one value per thread over a 256-thread block; returns the exclusive prefix
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* warp_sums /* [8] shared */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) {
+    if (w < warp) base += warp_sums[w];
+  }
+  __syncthreads();
+  return base + inc - v;
+}
+
+// Kernel 1: digit histograms of every pass in one read of the keys, status words of the used
+// tiles cleared, and (last block) the plan: which passes are needed, which buffer feeds each.
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_prepare(const KeyT* __restrict__ keys, const unsigned long long* d_n, uint32_t n_fixed, int passes,
+               SortPlan* plan, uint32_t* status, uint32_t tiles_cap) {
+  __shared__ uint32_t hist[kMaxPasses][kRadix];
+  __shared__ uint32_t is_last;
+  const uint32_t n = d_n ? (uint32_t)min(*d_n, (unsigned long long)tiles_cap * kSortTile) : n_fixed;
+  const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
+  for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
+  __syncthreads();
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int p = 0; p < passes; ++p) status[((size_t)p * tiles_cap + tile) * kRadix + threadIdx.x] = 0;
+    const uint32_t base = tile * kSortTile;
+#pragma unroll 4
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint32_t e = base + j * kSortThreads + threadIdx.x;
+      if (e < n) {
+        const KeyT k = keys[e];
+        for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(uint32_t)(k >> (8 * p)) & 0xffu], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) {
+    const uint32_t v = (&hist[0][0])[i];
+    if (v) atomicAdd(&plan->hist[0][0] + i, v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&plan->done_blocks, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // a pass whose digit is identical for all keys is the identity permutation: skip it
+  __shared__ uint32_t uniform[kMaxPasses];
+  if (threadIdx.x < kMaxPasses) uniform[threadIdx.x] = 0;
+  __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    if (ld_status(&plan->hist[p][threadIdx.x]) == n) uniform[p] = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t buf = 0;
+    for (int p = 0; p < passes; ++p) {
+      const uint32_t act = (n > 1 && !uniform[p]) ? 1u : 0u;
+      plan->active[p] = act;
+      plan->src_buf[p] = buf;
+      if (act) buf ^= 1u;
+    }
+    plan->final_buf = buf;
+    plan->n = n;
+    plan->n_tiles = n_tiles;
+  }
+}
+
+// Kernel 2: one radix pass.  Stable: tiles, warps inside a tile and items inside a warp are all
+// ranked in element order.
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_pass(int pass, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, SortPlan* plan,
+            uint32_t* status_all, uint32_t tiles_cap) {
+  if (!plan->active[pass]) return;
+  __shared__ uint32_t digit_base[kRadix];             // global exclusive prefix of the digit counts
+  __shared__ uint32_t warp_hist[kSortWarps][kRadix];  // per-warp digit counts -> exclusive warp offsets
+  __shared__ uint32_t tile_excl[kRadix];
+  __shared__ uint32_t warp_sums[kSortWarps];
+  __shared__ uint32_t cur_tile;
+  const uint32_t n = plan->n, n_tiles = plan->n_tiles;
+  const bool from_a = plan->src_buf[pass] == 0;
+  const KeyT* src_k = from_a ? keys_a : keys_b;
+  const uint32_t* src_v = from_a ? vals_a : vals_b;
+  KeyT* dst_k = from_a ? keys_b : keys_a;
+  uint32_t* dst_v = from_a ? vals_b : vals_a;
+  uint32_t* status = status_all + (size_t)pass * tiles_cap * kRadix;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  {
+    const uint32_t h = plan->hist[pass][threadIdx.x];
+    const uint32_t ex = block_exclusive_scan_256(h, warp_sums);
+    digit_base[threadIdx.x] = ex;
+  }
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) cur_tile = atomicAdd(&plan->tile_counter[pass], 1u);
+    for (int w = 0; w < kSortWarps; ++w) warp_hist[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = cur_tile;
+    if (tile >= n_tiles) break;
+    const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
+    KeyT key[kSortItems];
+    uint32_t val[kSortItems];
+    uint32_t rank[kSortItems];
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint32_t e = base + j * 32 + lane;
+      key[j] = e < n ? src_k[e] : (KeyT)0;
+      val[j] = e < n ? src_v[e] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint32_t e = base + j * 32 + lane;
+      const uint32_t d = e < n ? ((uint32_t)(key[j] >> (8 * pass)) & 0xffu) : 0xffffffffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t before = 0;
+      if (lane == leader && d != 0xffffffffu) {
+        before = warp_hist[warp][d];
+        warp_hist[warp][d] = before + (uint32_t)__popc(peers);
+      }
+      before = __shfl_sync(0xffffffffu, before, leader);
+      rank[j] = before + (uint32_t)__popc(peers & lt_mask);
+      __syncwarp();
+    }
+    __syncthreads();
+    // thread d: exclusive offsets of digit d over the warps of this tile, and the tile total
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = warp_hist[w][threadIdx.x];
+      warp_hist[w][threadIdx.x] = total;
+      total += c;
+    }
+    // chained scan over the tiles, one digit per thread
+    uint32_t* mine = status + (size_t)tile * kRadix + threadIdx.x;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_status(mine, kFlagPrefix | total);
+    } else {
+      st_status(mine, kFlagAggregate | total);
+      for (uint32_t t = tile; t-- > 0;) {
+        const uint32_t* theirs = status + (size_t)t * kRadix + threadIdx.x;
+        uint32_t v;
+        do {
+          v = ld_status(theirs);
+        } while ((v & ~kValueMask) == 0u);
+        excl += v & kValueMask;
+        if (v & kFlagPrefix) break;
+      }
+      st_status(mine, kFlagPrefix | (excl + total));
+    }
+    tile_excl[threadIdx.x] = excl;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint32_t e = base + j * 32 + lane;
+      if (e < n) {
+        const uint32_t d = (uint32_t)(key[j] >> (8 * pass)) & 0xffu;
+        const uint32_t pos = digit_base[d] + tile_excl[d] + warp_hist[warp][d] + rank[j];
+        dst_k[pos] = key[j];
+        dst_v[pos] = val[j];
+      }
+    }
+  }
+}
+
+// Exclusive prefix sum of n uint32 (n known on the host), chained scan over tiles of 2048.
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kSortThreads * kScanItems;
+static __global__ void __launch_bounds__(kSortThreads)
+k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* status,
+                 uint32_t* tile_counter) {
+  __shared__ uint32_t warp_sums[kSortWarps];
+  __shared__ uint32_t cur_tile, tile_base;
+  const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) cur_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = cur_tile;
+    if (tile >= n_tiles) break;
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      v[j] = (base + j < n) ? in[base + j] : 0u;
+      sum += v[j];
+    }
+    const uint32_t excl_in_tile = block_exclusive_scan_256(sum, warp_sums);
+    if (threadIdx.x == kSortThreads - 1) {
+      const uint32_t total = excl_in_tile + sum;
+      uint32_t excl = 0;
+      if (tile == 0) {
+        st_status(status, kFlagPrefix | total);
+      } else {
+        st_status(status + tile, kFlagAggregate | total);
+        for (uint32_t t = tile; t-- > 0;) {
+          uint32_t s;
+          do {
+            s = ld_status(status + t);
+          } while ((s & ~kValueMask) == 0u);
+          excl += s & kValueMask;
+          if (s & kFlagPrefix) break;
+        }
+        st_status(status + tile, kFlagPrefix | (excl + total));
+      }
+      tile_base = excl;
+    }
+    __syncthreads();
+    uint32_t run = tile_base + excl_in_tile;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (base + j < n) out[base + j] = run;
+      run += v[j];
+    }
+  }
+}
+
+}  // namespace vbx

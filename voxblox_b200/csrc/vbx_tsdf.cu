@@ -34,6 +34,7 @@
 #include <cstring>
 
 #include "vbx_engine.h"
+#include "vbx_sort.cuh"
 
 namespace vbx {
 
@@ -561,10 +562,13 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ off, uint32_t 
   }
   if (j < n_touched) tab.htouch_rank[tab.touched_list[j]] = j;
   if (j == 0) {
-    const unsigned long long total = off ? (unsigned long long)off[n] : total_if_no_off;
-    st->total_updates = total;
+    unsigned long long total = off ? (unsigned long long)off[n] : total_if_no_off;
     st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
     if (total > max_updates) atomicOr(&st->error, kErrUpdatesFull);
+    st->total_found = total;
+    // nothing downstream may run on a call that failed or must be redone with wide keys
+    if (st->error != 0 || total > max_updates) total = 0;
+    st->total_updates = total;
   }
 }
 
@@ -584,7 +588,7 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
     if (i >= P.n) return;
   }
   const uint32_t c = cnt[i];
-  if (c == 0) return;
+  if (c == 0 || st->total_updates == 0) return;  // (a failed / to-be-redone call emits nothing)
   const float4 rp = ray_p[i];
   const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
   const F3 point_G = f3(rp.x, rp.y, rp.z);
@@ -750,37 +754,61 @@ __device__ __forceinline__ float sdf_from(F3 vo, float4 ra) {
   return fsub(ra.w, fdiv(dot3(vo, f3(ra.x, ra.y, ra.z)), ra.w));
 }
 
+// The sorted update records as the apply kernels see them: with the library sort the host knows
+// which buffer holds the result and how many records there are; with the engine's own sort both
+// live in device memory (SortPlan::final_buf, ScanState::total_updates).
+struct RecordView {
+  const uint32_t* keys[2];
+  const uint32_t* vals[2];
+  const SortPlan* plan;                 // nullptr: buffer 0 holds the sorted records
+  const unsigned long long* d_total;    // nullptr: total_fixed
+  unsigned long long total_fixed;
+};
+__device__ __forceinline__ void open_records(const RecordView& rv, const uint32_t** ckeys, const uint32_t** cvals,
+                                             unsigned long long* total) {
+  const uint32_t sel = rv.plan ? rv.plan->final_buf : 0u;
+  *ckeys = rv.keys[sel];
+  *cvals = rv.vals[sel];
+  *total = rv.d_total ? *rv.d_total : rv.total_fixed;
+}
+
 // One thread per run head applies the first kShortRun updates of its voxel in order
 // (updateTsdfVoxel, cc:150-209); longer runs are queued for k_apply_long.
-__global__ void k_apply_short(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
-                              const uint32_t* __restrict__ cvals, unsigned long long total,
-                              const float4* __restrict__ ray_a, const uint2* __restrict__ ray_c,
-                              unsigned long long* __restrict__ long_list, ScanState* st) {
-  const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool head = false;
-  if (e < total) {
-    const uint32_t key = ckeys[e];
-    head = (e == 0) || (ckeys[e - 1] != key);
-    if (head) {
-      const VoxelRef vr = locate_voxel(P, tab, key);
-      TsdfVoxel v = *vr.ptr;
-      unsigned long long j = e;
-      for (int k = 0; k < kShortRun && j < total && ckeys[j] == key; ++k, ++j) {
-        const uint32_t r = cvals[j];
-        const float4 ra = ray_a[r];
-        const uint2 rc = ray_c[r];
-        const float sdf = sdf_from(vr.vo, ra);
-        apply_update(v, sdf, update_weight(sdf, __uint_as_float(rc.y), P.up), rc.x, P.up);
-      }
-      *vr.ptr = v;
-      if (j < total && ckeys[j] == key) {
-        const uint32_t q = atomicAdd(&st->n_long, 1u);
-        long_list[q] = j;
+__global__ void k_apply_short(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
+                              const uint2* __restrict__ ray_c, unsigned long long* __restrict__ long_list,
+                              ScanState* st) {
+  const uint32_t* ckeys;
+  const uint32_t* cvals;
+  unsigned long long total;
+  open_records(rv, &ckeys, &cvals, &total);
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long total_up = (total + 31ull) & ~31ull;  // whole warps stay in the loop
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_up; e += stride) {
+    bool head = false;
+    if (e < total) {
+      const uint32_t key = ckeys[e];
+      head = (e == 0) || (ckeys[e - 1] != key);
+      if (head) {
+        const VoxelRef vr = locate_voxel(P, tab, key);
+        TsdfVoxel v = *vr.ptr;
+        unsigned long long j = e;
+        for (int k = 0; k < kShortRun && j < total && ckeys[j] == key; ++k, ++j) {
+          const uint32_t r = cvals[j];
+          const float4 ra = ray_a[r];
+          const uint2 rc = ray_c[r];
+          const float sdf = sdf_from(vr.vo, ra);
+          apply_update(v, sdf, update_weight(sdf, __uint_as_float(rc.y), P.up), rc.x, P.up);
+        }
+        *vr.ptr = v;
+        if (j < total && ckeys[j] == key) {
+          const uint32_t q = atomicAdd(&st->n_long, 1u);
+          long_list[q] = j;
+        }
       }
     }
+    const unsigned b = __ballot_sync(0xffffffffu, head);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->n_voxels, (uint32_t)__popc(b));
   }
-  const unsigned b = __ballot_sync(0xffffffffu, head);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->n_voxels, (uint32_t)__popc(b));
 }
 
 // One warp per long run.  32 updates are prefetched per step (records coalesced, ray data
@@ -789,10 +817,13 @@ __global__ void k_apply_short(ScanParams P, Tables tab, const uint32_t* __restri
 // there every update has sdf >= T and the voxel already sits at +T, so after computing the
 // exact sequential weight chain each lane checks that ITS update maps +T to +T; if all do,
 // the sequential result is (+T, chained weight) without walking the distance chain.
-__global__ void k_apply_long(ScanParams P, Tables tab, const uint32_t* __restrict__ ckeys,
-                             const uint32_t* __restrict__ cvals, unsigned long long total,
-                             const float4* __restrict__ ray_a, const uint2* __restrict__ ray_c,
-                             const unsigned long long* __restrict__ long_list, const ScanState* st) {
+__global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
+                             const uint2* __restrict__ ray_c, const unsigned long long* __restrict__ long_list,
+                             const ScanState* st) {
+  const uint32_t* ckeys;
+  const uint32_t* cvals;
+  unsigned long long total;
+  open_records(rv, &ckeys, &cvals, &total);
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -958,6 +989,37 @@ struct Marks {
 };
 }  // namespace
 
+// The engine's own stable radix sort (vbx_sort.cuh).  n lives on the device (d_n) or is n_fixed.
+template <typename KeyT>
+static int own_sort(vbx_ctx* c, int which, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
+                    const unsigned long long* d_n, uint32_t n_fixed, int key_bits, uint64_t* launches) {
+  cudaStream_t s = c->stream;
+  const int passes = std::min(kMaxPasses, (key_bits + 7) / 8);
+  SortPlan* plan = c->sort_plan[which];
+  uint32_t* status = c->sort_status[which];
+  const uint32_t tiles_cap = c->sort_tiles_cap[which];
+  VBX_CUDA(c, cudaMemsetAsync(plan, 0, sizeof(SortPlan), s));
+  const unsigned int grid = std::min<uint32_t>(tiles_cap, 148 * 4);
+  k_sort_prepare<KeyT><<<grid, kSortThreads, 0, s>>>(keys_a, d_n, n_fixed, passes, plan, status, tiles_cap);
+  for (int p = 0; p < passes; ++p) {
+    k_sort_pass<KeyT><<<grid, kSortThreads, 0, s>>>(p, keys_a, vals_a, keys_b, vals_b, plan, status, tiles_cap);
+  }
+  *launches += 1 + passes;
+  return VBX_OK;
+}
+
+// after a sort whose consumers want the result in buffer A
+template <typename KeyT>
+__global__ void k_sort_to_a(KeyT* keys_a, uint32_t* vals_a, const KeyT* keys_b, const uint32_t* vals_b,
+                            const SortPlan* plan) {
+  if (plan->final_buf == 0) return;
+  const uint32_t n = plan->n;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    keys_a[i] = keys_b[i];
+    vals_a[i] = vals_b[i];
+  }
+}
+
 // Stages up to and including k_assign: everything that decides WHICH voxels are updated.
 template <typename KeyT>
 static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8_t* d_rgba, const uint32_t* order,
@@ -972,20 +1034,27 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     KeyT* k1 = reinterpret_cast<KeyT*>(c->pkeys[1]);
     k_point_keys<KeyT><<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, k0, c->pvals[0], c->d_state);
     mk.mark(0);
-    cub::DoubleBuffer<KeyT> kb(k0, k1);
-    cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
-    size_t tmp = c->cub_tmp_bytes;
     const int end_bit = P.wide_keys ? 64 : 3 * P.key_bits + 1;
-    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, end_bit, s));
-    keys = kb.Current();
-    vals = vb.Current();
+    if (c->use_cub) {
+      cub::DoubleBuffer<KeyT> kb(k0, k1);
+      cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
+      size_t tmp = c->cub_tmp_bytes;
+      VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, end_bit, s));
+      keys = kb.Current();
+      vals = vb.Current();
+    } else {
+      if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, end_bit, launches)) return rc;
+      k_sort_to_a<KeyT><<<148, 256, 0, s>>>(k0, c->pvals[0], k1, c->pvals[1], c->sort_plan[0]);
+      keys = k0;
+      vals = c->pvals[0];
+    }
     mk.mark(1);
     k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, P.slot_lo, P.slot_hi, keys, c->ray_list, c->cnt,
                                                                c->d_state);
     k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_a, c->ray_c,
                                            c->d_state);
     mk.mark(8);
-    *launches += 5 + (end_bit + 7) / 8;
+    *launches += c->use_cub ? 5 + (end_bit + 7) / 8 : 5;
     // the bundle count is only known on the device: launch for the worst case (every
     // point its own bundle); surplus threads exit on the first load
     k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->ray_list,
@@ -997,9 +1066,14 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
                                                                        c->set_start, c->set_observed, c->d_state);
   }
   mk.mark(2);
-  {
+  if (c->use_cub) {
     size_t tmp = c->cub_tmp_bytes;
     VBX_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp, tmp, c->cnt, c->off, (int)(n + 1), s));
+  } else {
+    const uint32_t tiles = (n + 1 + kScanTile - 1) / kScanTile;
+    VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
+    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, c->off, n + 1, c->scan_status + 1,
+                                                                               c->scan_status);
   }
   mk.mark(3);
   k_assign<<<grid_for(c->tab.max_blocks, TB), TB, 0, s>>>(c->tab, c->off, n, c->n_blocks, c->max_updates,
@@ -1014,18 +1088,41 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
 static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K, uint32_t n_touched, Marks& mk,
                           uint64_t* launches) {
   cudaStream_t s = c->stream;
-  cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
-  cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
-  size_t tmp = c->cub_tmp_bytes;
-  const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
-  VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
+  RecordView rv;
+  if (c->use_cub) {
+    cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
+    cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
+    size_t tmp = c->cub_tmp_bytes;
+    const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
+    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
+    rv.keys[0] = rv.keys[1] = kb.Current();
+    rv.vals[0] = rv.vals[1] = vb.Current();
+    rv.plan = nullptr;
+    rv.d_total = nullptr;
+    rv.total_fixed = K;
+    *launches += 1 + (key_bits + 7) / 8;
+  } else {
+    // K and the number of touched blocks are only known on the device: sort on every bit a
+    // record key can have; passes whose digit is uniform are skipped on the device
+    const int key_bits = 3 * c->L + std::max(1, bits_for(c->tab.max_blocks - 1));
+    if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
+                                     &c->d_state->total_updates, 0, key_bits, launches)) {
+      return rc;
+    }
+    rv.keys[0] = c->ckeys[0];
+    rv.keys[1] = c->ckeys[1];
+    rv.vals[0] = c->cvals[0];
+    rv.vals[1] = c->cvals[1];
+    rv.plan = c->sort_plan[1];
+    rv.d_total = &c->d_state->total_updates;
+    rv.total_fixed = 0;
+  }
   mk.mark(6);
-  k_apply_short<<<grid_for(K, 256), 256, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_a, c->ray_c,
-                                                  c->long_list, c->d_state);
-  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, kb.Current(), vb.Current(), K, c->ray_a, c->ray_c,
-                                       c->long_list, c->d_state);
+  const unsigned int g_short = c->use_cub ? grid_for(K, 256) : 148 * 8;
+  k_apply_short<<<g_short, 256, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, c->long_list, c->d_state);
+  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, c->long_list, c->d_state);
   mk.mark(7);
-  *launches += 3 + (key_bits + 7) / 8;
+  *launches += 2;
   return VBX_OK;
 }
 
@@ -1146,36 +1243,59 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   uint32_t new_blocks_first_attempt = 0;
   const uint32_t* keys32 = nullptr;
   const uint64_t* keys64 = nullptr;
+  unsigned long long K = 0;
+  uint32_t n_touched = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (P.wide_keys) {
       if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
     } else {
       if (int rc = front_half<uint32_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys32)) return rc;
     }
-    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
-    c->n_blocks = c->h_state->n_blocks;
-    if (!(c->h_state->error & kNeedWideKeys)) break;
+    if (c->use_cub) {
+      // the library sort needs K on the host: one stream synchronisation in the middle of the call
+      VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+      VBX_CUDA(c, cudaStreamSynchronize(s));
+      if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+      c->n_blocks = c->h_state->n_blocks;
+      if (!(c->h_state->error & kNeedWideKeys)) {
+        K = c->h_state->total_updates;
+        n_touched = c->h_state->n_touched;
+        if (K > 0) {
+          if (P.wide_keys) {
+            if (int rc = back_half<uint64_t>(c, P, keys64, K, n_touched, mk, &launches)) return rc;
+          } else {
+            if (int rc = back_half<uint32_t>(c, P, keys32, K, n_touched, mk, &launches)) return rc;
+          }
+        }
+        break;
+      }
+    } else {
+      // own sort: K stays on the device, the whole call is enqueued without a host round trip
+      if (P.wide_keys) {
+        if (int rc = back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches)) return rc;
+      } else {
+        if (int rc = back_half<uint32_t>(c, P, keys32, 0, 0, mk, &launches)) return rc;
+      }
+      VBX_CUDA(c, cudaEventRecord(c->ev1, s));
+      VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+      VBX_CUDA(c, cudaStreamSynchronize(s));
+      if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+      c->n_blocks = c->h_state->n_blocks;
+      if (!(c->h_state->error & kNeedWideKeys)) {
+        K = c->h_state->total_found;
+        n_touched = c->h_state->n_touched;
+        break;
+      }
+    }
     // A clearing point landed outside the compact key range.  The rays cast so far are
     // a correct SUBSET of the call's rays (block allocation is monotone), so keep the
-    // blocks they created and redo the call's front half with full-width keys under
-    // a fresh call id (touch marks restart).
+    // blocks they created and redo the call with full-width keys under a fresh call id
+    // (touch marks restart).  Nothing was applied: k_assign zeroes K for such a call.
     new_blocks_first_attempt = c->h_state->n_new;
     VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
     c->epoch += 1;
     P.epoch = c->epoch;
     P.wide_keys = 1;
-  }
-  const unsigned long long K = c->h_state->total_updates;
-  const uint32_t n_touched = c->h_state->n_touched;
-
-  if (K > 0) {
-    if (P.wide_keys) {
-      if (int rc = back_half<uint64_t>(c, P, keys64, K, n_touched, mk, &launches)) return rc;
-    } else {
-      if (int rc = back_half<uint32_t>(c, P, keys32, K, n_touched, mk, &launches)) return rc;
-    }
   }
   VBX_CUDA(c, cudaEventRecord(c->ev1, s));
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
@@ -1362,6 +1482,68 @@ int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_
   c->counters[4] = n_touched;
   c->counters[5] = c->h_state->n_new;
   c->counters[7] = launches + c->shard_front_counters[3];
+  return VBX_OK;
+}
+
+// ------------------------------------------------------------------ test hooks
+__global__ void k_iota(uint32_t* v, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+// Sorts n host keys with the engine's radix sort and returns the sorted keys and the permutation
+// (tests/test_sort_gpu.py checks it against a stable host sort).  key_bytes 4 uses the update-
+// record buffers with the count in device memory, 8 the point-key buffers with a host count.
+int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
+               uint32_t* vals_out) {
+  cudaStream_t s = c->stream;
+  uint64_t launches = 0;
+  if (key_bytes == 4) {
+    if (n > c->max_updates) return fail(c, VBX_E_CAPACITY, "debug_sort: n > max_updates_per_pass");
+    VBX_CUDA(c, cudaMemcpyAsync(c->ckeys[0], keys, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    k_iota<<<148, 256, 0, s>>>(c->cvals[0], n);
+    VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+    const unsigned long long nn = n;
+    VBX_CUDA(c, cudaMemcpyAsync(&c->d_state->total_updates, &nn, sizeof(nn), cudaMemcpyHostToDevice, s));
+    if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
+                                     &c->d_state->total_updates, 0, key_bits, &launches)) {
+      return rc;
+    }
+    k_sort_to_a<uint32_t><<<148, 256, 0, s>>>(c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1], c->sort_plan[1]);
+    VBX_CUDA(c, cudaMemcpyAsync(keys_out, c->ckeys[0], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaMemcpyAsync(vals_out, c->cvals[0], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  } else if (key_bytes == 8) {
+    if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "debug_sort: n > max_points_per_scan");
+    VBX_CUDA(c, cudaMemcpyAsync(c->pkeys[0], keys, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    k_iota<<<148, 256, 0, s>>>(c->pvals[0], n);
+    if (int rc = own_sort<uint64_t>(c, 0, c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], nullptr, n, key_bits,
+                                     &launches)) {
+      return rc;
+    }
+    k_sort_to_a<uint64_t><<<148, 256, 0, s>>>(c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], c->sort_plan[0]);
+    VBX_CUDA(c, cudaMemcpyAsync(keys_out, c->pkeys[0], (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaMemcpyAsync(vals_out, c->pvals[0], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  } else {
+    return fail(c, VBX_E_INVALID, "debug_sort: key_bytes must be 4 or 8");
+  }
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
+  return VBX_OK;
+}
+
+// exclusive prefix sum of n host uint32 through the engine's scan kernel
+int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {
+  cudaStream_t s = c->stream;
+  if (n > c->max_points + 1) return fail(c, VBX_E_CAPACITY, "debug_scan: n > max_points_per_scan + 1");
+  VBX_CUDA(c, cudaMemcpyAsync(c->cnt, in, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
+  VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
+  if (n) {
+    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, c->off, n, c->scan_status + 1,
+                                                                               c->scan_status);
+  }
+  VBX_CUDA(c, cudaMemcpyAsync(out, c->off, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
   return VBX_OK;
 }
 
