@@ -360,6 +360,29 @@ class Layer:
         ctx = self._bound()
         ctx.check(ctx.lib.vbx_sync(ctx.handle), "vbx_sync")
 
+    def insertBlocks(self, indices: np.ndarray, voxels: np.ndarray, updated_bits: Optional[np.ndarray] = None):
+        """Layer::insertBlock / allocateBlockPtrByIndex + voxel copy (core/layer.h:103-111,152-161)."""
+        ctx = self._bound()
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        dt = TSDF_DTYPE if self._layer_id == LAYER_TSDF else ESDF_DTYPE
+        vox = np.ascontiguousarray(voxels, dtype=dt).reshape(idx.shape[0], self._vps ** 3)
+        upd = None if updated_bits is None else np.ascontiguousarray(updated_bits, dtype=np.uint8)
+        ctx.check(ctx.lib.vbx_upload_blocks(ctx.handle, self._layer_id, idx.ctypes.data, idx.shape[0], vox.ctypes.data,
+                                            None if upd is None else upd.ctypes.data), "vbx_upload_blocks")
+
+    def removeBlock(self, index: Sequence[int]):  # core/layer.h:163
+        self.removeBlocks(np.asarray([index], dtype=np.int32))
+
+    def removeBlocks(self, indices: np.ndarray):
+        ctx = self._bound()
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        ctx.check(ctx.lib.vbx_remove_blocks(ctx.handle, self._layer_id, idx.ctypes.data, idx.shape[0]),
+                  "vbx_remove_blocks")
+
+    def removeAllBlocks(self):  # core/layer.h:164
+        ctx = self._bound()
+        ctx.check(ctx.lib.vbx_clear(ctx.handle, self._layer_id), "vbx_clear")
+
     def clearUpdated(self, bit: int):
         """block.updated().reset(bit) on every block (esdf_integrator.cc:113-121)."""
         ctx = self._bound()

@@ -1,0 +1,198 @@
+// Host-driven block management of the device map: the counterparts of Layer::insertBlock /
+// allocateBlockPtrByIndex (+ voxel copy), removeBlock and removeAllBlocks
+// (voxblox/include/voxblox/core/layer.h:103-111,152-164).  None of this is on the per-scan hot
+// path; it exists so that host code which edits the Layer between scans (loading a map,
+// TsdfServer's removeDistantBlocks, voxblox_ros/src/tsdf_server.cc:314-316) can keep the HBM map
+// of record in step.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "vbx_engine.h"
+#include "vbx_hash.cuh"
+
+namespace vbx {
+
+__global__ void k_ensure_keys(Tables tab, const uint64_t* __restrict__ keys, uint32_t m, uint32_t* __restrict__ hp_out,
+                              ScanState* st) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  hp_out[i] = ensure_block(tab, keys[i], st);
+}
+
+__global__ void k_assign_uploaded(Tables tab, uint32_t n_blocks_before, ScanState* st) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_new = min(st->n_new, tab.max_blocks);
+  if (j < n_new) {
+    const uint32_t slot = n_blocks_before + j;
+    if (slot < tab.max_blocks) {
+      const uint32_t hp = tab.new_list[j];
+      tab.hslot[hp] = (int32_t)slot;
+      tab.slot_key[slot] = tab.hkeys[hp];
+    } else {
+      atomicOr(&st->error, kErrPoolFull);
+    }
+  }
+  if (j == 0) st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
+}
+
+__global__ void k_slots_of(Tables tab, const uint32_t* __restrict__ hp, uint32_t m, int32_t* __restrict__ slot_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  slot_out[i] = hp[i] == 0xffffffffu ? -1 : tab.hslot[hp[i]];
+}
+
+// rebuild the hash from the per-slot keys (after blocks were removed and the pool compacted)
+__global__ void k_rebuild_hash(Tables tab, uint32_t n_blocks) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_blocks) return;
+  const uint64_t key = tab.slot_key[s];
+  uint32_t hp = hash64(key) & tab.hmask;
+  while (true) {
+    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(tab.hkeys + hp),
+                                             (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (old == kEmptyKey) {
+      tab.hslot[hp] = (int32_t)s;
+      return;
+    }
+    hp = (hp + 1) & tab.hmask;
+  }
+}
+
+static inline unsigned int grid_for(uint64_t n, int block) { return (unsigned int)((n + block - 1) / block); }
+
+static size_t voxel_bytes(int layer) { return layer == VBX_LAYER_TSDF ? sizeof(TsdfVoxel) : sizeof(EsdfVoxel); }
+
+int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const void* voxels,
+                  const uint8_t* updated_bits) {
+  if (m == 0) return VBX_OK;
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF layer");
+  if (m > c->tab.max_blocks) return fail(c, VBX_E_CAPACITY, "more blocks than the pool holds");
+  cudaStream_t s = c->stream;
+  std::vector<uint64_t> keys(m);
+  for (uint64_t i = 0; i < m; ++i) {
+    const int32_t* p = idx3 + 3 * i;
+    const int lim = kCoordBias - 1;
+    if (p[0] < -lim || p[0] > lim || p[1] < -lim || p[1] > lim || p[2] < -lim || p[2] > lim) {
+      return fail(c, VBX_E_INVALID, "block index outside +-2^20");
+    }
+    keys[i] = pack3(p[0], p[1], p[2]);
+  }
+  // scratch: the point-key buffer holds the keys, the ray list the hash positions, cnt the slots
+  if (m > c->max_points) return fail(c, VBX_E_CAPACITY, "upload more than max_points_per_scan blocks at once");
+  VBX_CUDA(c, cudaMemcpyAsync(c->pkeys[0], keys.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+  k_ensure_keys<<<grid_for(m, 256), 256, 0, s>>>(c->tab, c->pkeys[0], (uint32_t)m, c->ray_list, c->d_state);
+  k_assign_uploaded<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
+  k_slots_of<<<grid_for(m, 256), 256, 0, s>>>(c->tab, c->ray_list, (uint32_t)m, reinterpret_cast<int32_t*>(c->cnt));
+  std::vector<int32_t> slots(m);
+  VBX_CUDA(c, cudaMemcpyAsync(slots.data(), c->cnt, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  if (c->h_state->error & kFatalErrors) return fail(c, VBX_E_CAPACITY, "block pool / hash full during upload");
+  c->n_blocks = c->h_state->n_blocks;
+  const size_t bbytes = voxel_bytes(layer) * c->vox_per_block;
+  char* pool = layer == VBX_LAYER_TSDF ? reinterpret_cast<char*>(c->tab.tsdf) : reinterpret_cast<char*>(c->tab.esdf);
+  std::vector<uint8_t> ones(1, 1);
+  for (uint64_t i = 0; i < m; ++i) {
+    if (slots[i] < 0) return fail(c, VBX_E_CAPACITY, "upload: block without a slot");
+    VBX_CUDA(c, cudaMemcpyAsync(pool + (size_t)slots[i] * bbytes, static_cast<const char*>(voxels) + i * bbytes, bbytes,
+                                cudaMemcpyHostToDevice, s));
+    const uint8_t u = updated_bits ? updated_bits[i] : 0;
+    uint8_t* flags = layer == VBX_LAYER_TSDF ? c->tab.slot_updated : c->tab.slot_esdf_updated;
+    VBX_CUDA(c, cudaMemcpyAsync(flags + slots[i], &u, 1, cudaMemcpyHostToDevice, s));
+    if (layer == VBX_LAYER_ESDF) {
+      VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_has_esdf + slots[i], ones.data(), 1, cudaMemcpyHostToDevice, s));
+    }
+    VBX_CUDA(c, cudaStreamSynchronize(s));  // `u` lives on this stack frame
+  }
+  return refresh_host_mirror(c);
+}
+
+int clear_layer(vbx_ctx* c, int layer) {
+  cudaStream_t s = c->stream;
+  const size_t used = (size_t)c->n_blocks * c->vox_per_block;
+  if (layer == VBX_LAYER_ESDF) {
+    if (!c->has_esdf) return VBX_OK;
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, used * sizeof(EsdfVoxel), s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->tab.max_blocks, s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->tab.max_blocks, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    return VBX_OK;
+  }
+  // removing every TSDF block also empties the ESDF layer's storage (the two layers share slots)
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.tsdf, 0, used * sizeof(TsdfVoxel), s));
+  if (c->has_esdf) VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, used * sizeof(EsdfVoxel), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.hkeys, 0xff, (size_t)c->hcap * sizeof(uint64_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.hslot, 0xff, (size_t)c->hcap * sizeof(int32_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.htouch_epoch, 0, (size_t)c->hcap * sizeof(uint32_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_updated, 0, c->tab.max_blocks, s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->tab.max_blocks, s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->tab.max_blocks, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  c->n_blocks = 0;
+  c->host_slot_key.clear();
+  c->host_key2slot.clear();
+  return VBX_OK;
+}
+
+int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
+  if (m == 0) return VBX_OK;
+  cudaStream_t s = c->stream;
+  if (int rc = refresh_host_mirror(c)) return rc;
+  std::vector<int32_t> victims;
+  for (uint64_t i = 0; i < m; ++i) {
+    auto it = c->host_key2slot.find(pack3(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
+    if (it != c->host_key2slot.end()) victims.push_back(it->second);  // erasing a missing block is a no-op
+  }
+  std::sort(victims.begin(), victims.end());
+  victims.erase(std::unique(victims.begin(), victims.end()), victims.end());
+  if (victims.empty()) return VBX_OK;
+  const size_t tb = sizeof(TsdfVoxel) * c->vox_per_block, eb = sizeof(EsdfVoxel) * c->vox_per_block;
+  if (layer == VBX_LAYER_ESDF) {
+    if (!c->has_esdf) return VBX_OK;
+    for (int32_t v : victims) {
+      VBX_CUDA(c, cudaMemsetAsync(reinterpret_cast<char*>(c->tab.esdf) + (size_t)v * eb, 0, eb, s));
+      VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf + v, 0, 1, s));
+      VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated + v, 0, 1, s));
+    }
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    return VBX_OK;
+  }
+  // TSDF: swap-remove in the pool (highest victim first), then rebuild the hash from slot_key
+  uint32_t n = c->n_blocks;
+  for (auto it = victims.rbegin(); it != victims.rend(); ++it) {
+    const uint32_t v = (uint32_t)*it, last = n - 1;
+    if (v != last) {
+      VBX_CUDA(c, cudaMemcpyAsync(reinterpret_cast<char*>(c->tab.tsdf) + (size_t)v * tb,
+                                  reinterpret_cast<char*>(c->tab.tsdf) + (size_t)last * tb, tb, cudaMemcpyDeviceToDevice, s));
+      if (c->has_esdf) {
+        VBX_CUDA(c, cudaMemcpyAsync(reinterpret_cast<char*>(c->tab.esdf) + (size_t)v * eb,
+                                    reinterpret_cast<char*>(c->tab.esdf) + (size_t)last * eb, eb, cudaMemcpyDeviceToDevice, s));
+      }
+      VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_key + v, c->tab.slot_key + last, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+      VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_updated + v, c->tab.slot_updated + last, 1, cudaMemcpyDeviceToDevice, s));
+      VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_esdf_updated + v, c->tab.slot_esdf_updated + last, 1, cudaMemcpyDeviceToDevice, s));
+      VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_has_esdf + v, c->tab.slot_has_esdf + last, 1, cudaMemcpyDeviceToDevice, s));
+    }
+    // a freed slot must read as a freshly constructed block for its next owner
+    VBX_CUDA(c, cudaMemsetAsync(reinterpret_cast<char*>(c->tab.tsdf) + (size_t)last * tb, 0, tb, s));
+    if (c->has_esdf) VBX_CUDA(c, cudaMemsetAsync(reinterpret_cast<char*>(c->tab.esdf) + (size_t)last * eb, 0, eb, s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_updated + last, 0, 1, s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated + last, 0, 1, s));
+    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf + last, 0, 1, s));
+    --n;
+  }
+  c->n_blocks = n;
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.hkeys, 0xff, (size_t)c->hcap * sizeof(uint64_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.hslot, 0xff, (size_t)c->hcap * sizeof(int32_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.htouch_epoch, 0, (size_t)c->hcap * sizeof(uint32_t), s));
+  if (n) k_rebuild_hash<<<grid_for(n, 256), 256, 0, s>>>(c->tab, n);
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
+  c->host_slot_key.clear();
+  c->host_key2slot.clear();
+  return refresh_host_mirror(c);
+}
+
+}  // namespace vbx

@@ -22,6 +22,10 @@ int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_
 int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
                uint32_t* vals_out);
 int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out);
+int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const void* voxels,
+                  const uint8_t* updated_bits);
+int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m);
+int clear_layer(vbx_ctx* c, int layer);
 int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
 
@@ -102,7 +106,7 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   c->max_updates = std::min<uint64_t>(o.max_updates_per_pass, 0x7fffffffull);
   int rb = 0;
   for (uint32_t v = o.max_blocks; v; v >>= 1) ++rb;
-  if (rb + 3 * c->L > 32) {
+  if (rb + 1 + 3 * c->L > 32) {  // an update record's key = (hash position, voxel in block) in 32 bits
     delete c;
     return VBX_E_INVALID;
   }
@@ -465,13 +469,24 @@ int vbx_clear_updated(vbx_ctx* c, int layer, int updated_mask) {
   return VBX_OK;
 }
 
-int vbx_upload_blocks(vbx_ctx* c, int, const int32_t*, uint64_t, const void*, const uint8_t*) {
-  return fail(c, VBX_E_STATE, "vbx_upload_blocks: not implemented yet");
+int vbx_upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const void* voxels,
+                      const uint8_t* updated_bits) {
+  if (!c || (m && (!idx3 || !voxels))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return upload_blocks(c, layer, idx3, m, voxels, updated_bits);
 }
-int vbx_remove_blocks(vbx_ctx* c, int, const int32_t*, uint64_t) {
-  return fail(c, VBX_E_STATE, "vbx_remove_blocks: not implemented yet");
+
+int vbx_remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
+  if (!c || (m && !idx3)) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return remove_blocks(c, layer, idx3, m);
 }
-int vbx_clear(vbx_ctx* c, int) { return fail(c, VBX_E_STATE, "vbx_clear: not implemented yet"); }
+
+int vbx_clear(vbx_ctx* c, int layer) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return clear_layer(c, layer);
+}
 
 int vbx_esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
   if (!c || !cfg) return VBX_E_INVALID;

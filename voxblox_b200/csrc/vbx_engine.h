@@ -35,6 +35,7 @@ enum : uint32_t {
   kErrHashFull = 2u,        // block hash probe wrapped around
   kErrCoordRange = 4u,      // |voxel coordinate| >= 2^20 * vps
   kErrUpdatesFull = 8u,     // ray-voxel updates exceed max_updates_per_pass
+  kFatalErrors = 15u,       // any of the above
   kNeedWideKeys = 16u,      // not an error: a clearing point fell outside the compact bundle-key range
 };
 

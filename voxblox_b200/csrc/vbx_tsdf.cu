@@ -34,6 +34,7 @@
 #include <cstring>
 
 #include "vbx_engine.h"
+#include "vbx_hash.cuh"
 #include "vbx_sort.cuh"
 
 namespace vbx {
@@ -67,6 +68,9 @@ struct ScanParams {
   // [slot_lo, slot_hi); shard != 0 defers all block-hash work to vbx_shard_back
   uint32_t slot_lo, slot_hi;
   int shard;
+  // the number of voxels a ray updates is known from its DDA set-up alone (no anti-grazing, not the
+  // Fast integrator): one walk that creates blocks AND writes the update records
+  int single_walk;
 };
 
 // MixedThreadSafeIndex::getNextIndexImpl, integrator_utils.cc:54-63
@@ -103,56 +107,6 @@ __device__ __forceinline__ uint64_t normal_key_of(const ScanParams& P, int x, in
 }
 __device__ __forceinline__ bool key_is_clearing(const ScanParams& P, uint64_t key) {
   return ((key >> (P.wide_keys ? 63 : 3 * P.key_bits)) & 1ull) != 0;
-}
-
-// ------------------------------------------------------------------ block hash
-// Find the hash position of a block, creating the entry if it is missing
-// (allocateStorageAndGetVoxelPtr's find-or-emplace, cc:109-124, without the mutex:
-// one CAS decides the winner).  Pool slots are assigned later by k_assign.
-__device__ uint32_t ensure_block(const Tables& t, uint64_t key, ScanState* st) {
-  uint32_t hp = hash64(key) & t.hmask;
-  for (uint32_t probe = 0; probe <= t.hmask; ++probe) {
-    const uint64_t k = *reinterpret_cast<volatile uint64_t*>(t.hkeys + hp);
-    if (k == key) return hp;
-    if (k == kEmptyKey) {
-      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.hkeys + hp),
-                                               (unsigned long long)kEmptyKey, (unsigned long long)key);
-      if (old == kEmptyKey) {
-        const uint32_t j = atomicAdd(&st->n_new, 1u);
-        if (j < t.max_blocks) {
-          t.new_list[j] = hp;
-        } else {
-          atomicOr(&st->error, kErrPoolFull);
-        }
-        return hp;
-      }
-      if (old == key) return hp;
-    }
-    hp = (hp + 1) & t.hmask;
-  }
-  atomicOr(&st->error, kErrHashFull);
-  return 0xffffffffu;
-}
-
-__device__ __forceinline__ uint32_t find_block(const Tables& t, uint64_t key) {
-  uint32_t hp = hash64(key) & t.hmask;
-  for (uint32_t probe = 0; probe <= t.hmask; ++probe) {
-    const uint64_t k = t.hkeys[hp];
-    if (k == key) return hp;
-    if (k == kEmptyKey) return 0xffffffffu;
-    hp = (hp + 1) & t.hmask;
-  }
-  return 0xffffffffu;
-}
-
-__device__ __forceinline__ void mark_touched(const Tables& t, uint32_t hp, uint32_t epoch, ScanState* st) {
-  if (*reinterpret_cast<volatile uint32_t*>(t.htouch_epoch + hp) != epoch) {
-    const uint32_t old = atomicExch(t.htouch_epoch + hp, epoch);
-    if (old != epoch) {
-      const uint32_t j = atomicAdd(&st->n_touched, 1u);
-      if (j < t.max_blocks) t.touched_list[j] = hp;
-    }
-  }
 }
 
 // ------------------------------------------------------------------- kernels
@@ -396,7 +350,8 @@ template <typename KeyT>
 __global__ void __launch_bounds__(128)
 k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
         const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ray_list,
-        float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c, const ScanState* st) {
+        float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c, uint32_t* __restrict__ cnt,
+        ScanState* st) {
   __shared__ float4 stage[4 * 32 * kStageStride];  // [warp in block][member][role]
   const int lane = threadIdx.x & 31;
   float4* stage_warp = stage + (threadIdx.x >> 5) * (32 * kStageStride);
@@ -412,7 +367,15 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
       fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol);
     }
     if (lane == 0) {
-      store_ray(P, i, transform(P.T, mp), mw, mcol, key_is_clearing(P, (uint64_t)keys[i]), ray_p, ray_a, ray_c);
+      const bool clearing = key_is_clearing(P, (uint64_t)keys[i]);
+      const F3 pg = transform(P.T, mp);
+      store_ray(P, i, pg, mw, mcol, clearing, ray_p, ray_a, ray_c);
+      if (P.single_walk) {
+        Dda d;
+        dda_setup(d, P.origin, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc, true);
+        cnt[i] = d.len + 1u;  // RayCaster emits ray_length_in_steps_ + 1 voxels (integrator_utils.cc:111-125)
+        atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
+      }
     }
   }
 }
@@ -509,6 +472,10 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   Dda d;
   dda_setup(d, P.origin, point_G, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
             P.kind != VBX_FAST);
+  if (P.single_walk) {
+    cnt[i] = d.len + 1u;
+    return;
+  }
   uint32_t count = 0;
   int collisions = 0;
   int lbx = INT_MIN, lby = INT_MIN, lbz = INT_MIN;
@@ -544,32 +511,34 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   cnt[i] = count;
 }
 
-// Pool slots for the blocks created by this call, dense ranks for the touched ones.
-__global__ void k_assign(Tables tab, const uint32_t* __restrict__ off, uint32_t n, uint32_t n_blocks_before,
-                         uint64_t max_updates, ScanState* st, unsigned long long total_if_no_off = 0) {
+// After the scan: the call's update count, and whether anything downstream may run at all.
+__global__ void k_set_total(const uint32_t* __restrict__ off, uint32_t n, uint64_t max_updates, ScanState* st,
+                            unsigned long long total_if_no_off) {
+  unsigned long long total = off ? (unsigned long long)off[n] : total_if_no_off;
+  if (total > max_updates) atomicOr(&st->error, kErrUpdatesFull);
+  st->total_found = total;
+  // nothing downstream may run on a call that failed or must be redone with wide keys
+  if (st->error != 0 || total > max_updates) total = 0;
+  st->total_updates = total;
+}
+
+// After the last walk that can create blocks: pool slots for the blocks created by this call
+// (updateLayerWithStoredBlocks, cc:137-147); a new block is born with all updated bits set (cc:128).
+__global__ void k_assign(Tables tab, uint32_t n_blocks_before, ScanState* st) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_new = min(st->n_new, tab.max_blocks);
-  const uint32_t n_touched = min(st->n_touched, tab.max_blocks);
   if (j < n_new) {
     const uint32_t slot = n_blocks_before + j;
     if (slot < tab.max_blocks) {
       const uint32_t hp = tab.new_list[j];
       tab.hslot[hp] = (int32_t)slot;
       tab.slot_key[slot] = tab.hkeys[hp];
+      tab.slot_updated[slot] = 7;
     } else {
       atomicOr(&st->error, kErrPoolFull);
     }
   }
-  if (j < n_touched) tab.htouch_rank[tab.touched_list[j]] = j;
-  if (j == 0) {
-    unsigned long long total = off ? (unsigned long long)off[n] : total_if_no_off;
-    st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
-    if (total > max_updates) atomicOr(&st->error, kErrUpdatesFull);
-    st->total_found = total;
-    // nothing downstream may run on a call that failed or must be redone with wide keys
-    if (st->error != 0 || total > max_updates) total = 0;
-    st->total_updates = total;
-  }
+  if (j == 0) st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
 }
 
 template <typename KeyT>
@@ -577,7 +546,7 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
                             const uint32_t* __restrict__ ray_list, const float4* __restrict__ ray_p,
                             const uint32_t* __restrict__ cnt,
                             const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
-                            uint32_t* __restrict__ cvals, const ScanState* st) {
+                            uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t i;
   if (P.kind == VBX_MERGED) {
@@ -598,25 +567,42 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
   const KeyT own = (P.kind == VBX_MERGED) ? keys[i] : (KeyT)0;
   uint32_t emitted = 0;
   int lbx = INT_MIN, lby = INT_MIN, lbz = INT_MIN;
-  uint32_t rank = 0;
+  uint32_t hp = 0;
   const uint32_t base = off[i];
   const int mask = (1 << P.L) - 1;
+  const int lim = (kCoordBias - 1) << P.L;
   for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
     if (P.kind == VBX_MERGED && P.anti_grazing) {
       if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
     }
     const int bx = d.cx >> P.L, by = d.cy >> P.L, bz = d.cz >> P.L;
     if (bx != lbx || by != lby || bz != lbz) {
-      const uint32_t hp = find_block(tab, pack3(bx, by, bz));
-      rank = tab.htouch_rank[hp];
-      tab.slot_updated[tab.hslot[hp]] = 7;  // (*last_block)->updated().set(), cc:128
+      if (P.single_walk) {
+        // the only walk of this ray: allocateStorageAndGetVoxelPtr's find-or-create, cc:91-134
+        if (d.cx < -lim || d.cx > lim || d.cy < -lim || d.cy > lim || d.cz < -lim || d.cz > lim) {
+          atomicOr(&st->error, kErrCoordRange);
+          hp = 0xffffffffu;
+        } else {
+          hp = ensure_block(tab, pack3(bx, by, bz), st);
+          if (hp != 0xffffffffu) mark_touched(tab, hp, P.epoch, st);
+        }
+      } else {
+        hp = find_block(tab, pack3(bx, by, bz));
+      }
+      if (hp != 0xffffffffu) {
+        const int32_t slot = tab.hslot[hp];
+        if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
+      }
       lbx = bx;
       lby = by;
       lbz = bz;
     }
     const uint32_t lin = (uint32_t)(d.cx & mask) | ((uint32_t)(d.cy & mask) << P.L) |
                          ((uint32_t)(d.cz & mask) << (2 * P.L));
-    ckeys[base + emitted] = (rank << (3 * P.L)) | lin;
+    // a record = (hash position of the block, voxel inside the block) -> ray.  A ray whose block
+    // could not be created still fills its slots so that offsets stay valid; the error flag set
+    // above stops the apply kernels.
+    ckeys[base + emitted] = (hp << (3 * P.L)) | lin;
     cvals[base + emitted] = i;
     ++emitted;
   }
@@ -720,7 +706,7 @@ __global__ void k_localize_keys(ShardSegments seg, Tables tab, int L, const uint
   }
   const uint4 rec = seg.rec[r][j];
   const uint32_t lin = rec.x & ((1u << (3 * L)) - 1u);
-  ckeys[p] = (tab.htouch_rank[hp] << (3 * L)) | lin;
+  ckeys[p] = (hp << (3 * L)) | lin;
   cvals[p] = rec.z;
   tab.slot_updated[tab.hslot[hp]] = 7;  // (*last_block)->updated().set(), cc:128
 }
@@ -732,9 +718,8 @@ struct VoxelRef {
 };
 
 __device__ __forceinline__ VoxelRef locate_voxel(const ScanParams& P, const Tables& tab, uint32_t key) {
-  const uint32_t rank = key >> (3 * P.L);
+  const uint32_t hp = key >> (3 * P.L);
   const uint32_t lin = key & ((1u << (3 * P.L)) - 1u);
-  const uint32_t hp = tab.touched_list[rank];
   int bx, by, bz;
   unpack3(tab.hkeys[hp], &bx, &by, &bz);
   const int mask = (1 << P.L) - 1;
@@ -781,6 +766,7 @@ __global__ void k_apply_short(ScanParams P, Tables tab, RecordView rv, const flo
   const uint32_t* cvals;
   unsigned long long total;
   open_records(rv, &ckeys, &cvals, &total);
+  if (st->error & kFatalErrors) return;  // e.g. the pool filled up: blocks without a slot exist
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   const unsigned long long total_up = (total + 31ull) & ~31ull;  // whole warps stay in the loop
   for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_up; e += stride) {
@@ -824,6 +810,7 @@ __global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const floa
   const uint32_t* cvals;
   unsigned long long total;
   open_records(rv, &ckeys, &cvals, &total);
+  if (st->error & kFatalErrors) return;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -1052,18 +1039,22 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, P.slot_lo, P.slot_hi, keys, c->ray_list, c->cnt,
                                                                c->d_state);
     k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_a, c->ray_c,
-                                           c->d_state);
+                                           c->cnt, c->d_state);
     mk.mark(8);
-    *launches += c->use_cub ? 5 + (end_bit + 7) / 8 : 5;
-    // the bundle count is only known on the device: launch for the worst case (every
-    // point its own bundle); surplus threads exit on the first load
-    k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->ray_list,
-                                                         c->ray_p, c->ray_a, c->ray_c, c->cnt, c->set_start,
-                                                         c->set_observed, c->d_state);
+    *launches += c->use_cub ? 4 + (end_bit + 7) / 8 : 4;
+    if (!P.single_walk) {
+      // the bundle count is only known on the device: launch for the worst case (every
+      // point its own bundle); surplus threads exit on the first load
+      k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->ray_list,
+                                                           c->ray_p, c->ray_a, c->ray_c, c->cnt, c->set_start,
+                                                           c->set_observed, c->d_state);
+      *launches += 1;
+    }
   } else {
     k_rays_count<KeyT><<<grid_for((uint64_t)n + 1, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys,
                                                                        c->ray_list, c->ray_p, c->ray_a, c->ray_c, c->cnt,
                                                                        c->set_start, c->set_observed, c->d_state);
+    *launches += 1;
   }
   mk.mark(2);
   if (c->use_cub) {
@@ -1075,11 +1066,9 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, c->off, n + 1, c->scan_status + 1,
                                                                                c->scan_status);
   }
+  k_set_total<<<1, 1, 0, s>>>(c->off, n, c->max_updates, c->d_state, 0);
   mk.mark(3);
-  k_assign<<<grid_for(c->tab.max_blocks, TB), TB, 0, s>>>(c->tab, c->off, n, c->n_blocks, c->max_updates,
-                                                          c->d_state);
-  mk.mark(4);
-  *launches += 4;
+  *launches += 2;
   *keys_out = keys;
   return VBX_OK;
 }
@@ -1093,7 +1082,7 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
     cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
     cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
     size_t tmp = c->cub_tmp_bytes;
-    const int key_bits = 3 * c->L + std::max(1, bits_for(n_touched > 0 ? n_touched - 1 : 0));
+    const int key_bits = 3 * c->L + bits_for(c->hcap - 1);
     VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
     rv.keys[0] = rv.keys[1] = kb.Current();
     rv.vals[0] = rv.vals[1] = vb.Current();
@@ -1104,7 +1093,7 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
   } else {
     // K and the number of touched blocks are only known on the device: sort on every bit a
     // record key can have; passes whose digit is uniform are skipped on the device
-    const int key_bits = 3 * c->L + std::max(1, bits_for(c->tab.max_blocks - 1));
+    const int key_bits = 3 * c->L + bits_for(c->hcap - 1);
     if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
                                      &c->d_state->total_updates, 0, key_bits, launches)) {
       return rc;
@@ -1134,7 +1123,9 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off,
                                                       c->ckeys[0], c->cvals[0], c->d_state);
   mk.mark(5);
-  *launches += 1;
+  k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
+  mk.mark(4);
+  *launches += 2;
   return sort_and_apply(c, P, K, n_touched, mk, launches);
 }
 
@@ -1198,6 +1189,7 @@ static void fill_params(vbx_ctx* c, int kind, const float q[4], const float t[3]
   P.slot_lo = 0;
   P.slot_hi = n;
   P.shard = 0;
+  P.single_walk = (kind != VBX_FAST && !(kind == VBX_MERGED && cfg.enable_anti_grazing)) ? 1 : 0;
 }
 
 int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
@@ -1458,8 +1450,8 @@ int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_
   if (K > 0) {
     uint32_t* hp_of = c->cvals[1];
     k_localize_blocks<<<grid_for(K, 256), 256, 0, s>>>(seg, c->tab, c->L, P.epoch, hp_of, c->d_state);
-    k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, nullptr, 0, c->n_blocks, c->max_updates,
-                                                              c->d_state, K);
+    k_set_total<<<1, 1, 0, s>>>(nullptr, 0, c->max_updates, c->d_state, K);
+    k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
     VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
     VBX_CUDA(c, cudaStreamSynchronize(s));
     if (int rc = check_state_errors(c, c->h_state->error)) return rc;
