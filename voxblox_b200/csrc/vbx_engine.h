@@ -59,6 +59,8 @@ struct ScanState {
   uint32_t lowered_n;        // ESDF: voxels lowered by the wavefront
   uint32_t n_ray_list;       // bundle heads (Merged)
   uint32_t n_long;           // voxel runs handed to k_apply_long
+  uint32_t n_verify;         // work items of k_apply_verify
+  uint32_t pad_[3];
 };
 
 // The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
@@ -121,6 +123,10 @@ struct vbx_ctx {
   uint32_t* order = nullptr;
   uint32_t* ray_list = nullptr;            // [max_points] dense list of bundle heads
   unsigned long long* long_list = nullptr; // [max_updates / 32 + 1] starts of long voxel runs
+  unsigned long long* long_end = nullptr;
+  uint32_t* long_state = nullptr;
+  uint32_t* verify_run = nullptr;          // [max_updates / 32 + 1] work items of k_apply_verify
+  unsigned long long* verify_start = nullptr;
   float4* ray_p = nullptr;    // point_G.xyz, flags (bit 0: clearing ray)
   float4* ray_a = nullptr;    // point_G - origin, |point_G - origin|
   uint2* ray_c = nullptr;     // colour, weight bits

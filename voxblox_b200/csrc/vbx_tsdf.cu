@@ -757,11 +757,76 @@ __device__ __forceinline__ void open_records(const RecordView& rv, const uint32_
   *total = rv.d_total ? *rv.d_total : rv.total_fixed;
 }
 
+// Voxel runs longer than kShortRun updates.  state: 0 = apply sequentially (k_apply_long),
+// 1 = candidate for the parallel fixed-point check, |2 = the check failed.
+constexpr unsigned long long kVerifyItem = 256;  // 8 records per lane: short dependent chains, many items
+struct LongRuns {
+  unsigned long long* start;   // first record after the prefix the head thread applied
+  unsigned long long* end;     // one past the run's last record (state != 0)
+  uint32_t* state;
+  uint32_t* item_run;          // work items of k_apply_verify
+  unsigned long long* item_start;
+};
+
+// One warp per work item: do all updates in [start, start + kVerifyItem) of a saturated voxel's
+// run map (+T, max_weight) onto itself?  An update does when its sdf >= T (no colour blend), the
+// new distance clamps back to +T and the weight clamps back to max_weight -- evaluated with the
+// reference's own arithmetic, so "unchanged" is exact, not approximate.
+__global__ void k_apply_verify(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
+                               const uint2* __restrict__ ray_c, LongRuns lr, const ScanState* st) {
+  const uint32_t* ckeys;
+  const uint32_t* cvals;
+  unsigned long long total;
+  open_records(rv, &ckeys, &cvals, &total);
+  if (st->error & kFatalErrors) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_items = st->n_verify;
+  const float T = P.up.trunc, W = P.up.max_weight;
+  for (uint32_t it = warp; it < n_items; it += n_warps) {
+    const uint32_t q = lr.item_run[it];
+    const unsigned long long a = lr.item_start[it];
+    const unsigned long long b = min(a + kVerifyItem, lr.end[q]);
+    const VoxelRef vr = locate_voxel(P, tab, ckeys[a]);
+    bool ok = true;
+    // all record -> ray-table gathers of the item are issued before any is consumed
+    uint32_t r[kVerifyItem / 32];
+    float4 ra[kVerifyItem / 32];
+    uint32_t wbits[kVerifyItem / 32];
+#pragma unroll
+    for (int k = 0; k < (int)(kVerifyItem / 32); ++k) {
+      const unsigned long long j = a + lane + 32ull * k;
+      r[k] = j < b ? cvals[j] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < (int)(kVerifyItem / 32); ++k) {
+      if (r[k] != 0xffffffffu) {
+        ra[k] = ray_a[r[k]];
+        wbits[k] = ray_c[r[k]].y;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < (int)(kVerifyItem / 32); ++k) {
+      if (r[k] == 0xffffffffu) continue;
+      const float sdf = sdf_from(vr.vo, ra[k]);
+      const float w = update_weight(sdf, __uint_as_float(wbits[k]), P.up);
+      const float nw = fadd(W, w);
+      bool keeps = sdf >= T && !(nw < VBX_EPS) && !(nw < W);
+      if (keeps) {
+        const float ns = fdiv(fadd(fmul(sdf, w), fmul(T, W)), nw);
+        keeps = (ns > 0.0f) && !(ns < T);
+      }
+      ok = ok && keeps;
+    }
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicOr(&lr.state[q], 2u);
+  }
+}
+
 // One thread per run head applies the first kShortRun updates of its voxel in order
 // (updateTsdfVoxel, cc:150-209); longer runs are queued for k_apply_long.
 __global__ void k_apply_short(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
-                              const uint2* __restrict__ ray_c, unsigned long long* __restrict__ long_list,
-                              ScanState* st) {
+                              const uint2* __restrict__ ray_c, LongRuns lr, ScanState* st) {
   const uint32_t* ckeys;
   const uint32_t* cvals;
   unsigned long long total;
@@ -788,7 +853,32 @@ __global__ void k_apply_short(ScanParams P, Tables tab, RecordView rv, const flo
         *vr.ptr = v;
         if (j < total && ckeys[j] == key) {
           const uint32_t q = atomicAdd(&st->n_long, 1u);
-          long_list[q] = j;
+          lr.start[q] = j;
+          // A voxel resting at (+T, max_weight) -- free space seen many times -- stays there as
+          // long as every remaining update maps that state onto itself, which can be checked
+          // record by record, in parallel (k_apply_verify).  Find the end of the run (records are
+          // sorted) and cut it into work items.
+          const bool saturated = v.distance == P.up.trunc && v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS;
+          uint32_t state = 0u;
+          if (saturated) {
+            unsigned long long lo = j, hi = total;  // first record past the run
+            while (lo < hi) {
+              const unsigned long long mid = (lo + hi) >> 1;
+              if (ckeys[mid] <= key) {
+                lo = mid + 1;
+              } else {
+                hi = mid;
+              }
+            }
+            lr.end[q] = lo;
+            for (unsigned long long a = j; a < lo; a += kVerifyItem) {
+              const uint32_t it = atomicAdd(&st->n_verify, 1u);
+              lr.item_run[it] = q;
+              lr.item_start[it] = a;
+            }
+            state = 1u;
+          }
+          lr.state[q] = state;
         }
       }
     }
@@ -804,8 +894,7 @@ __global__ void k_apply_short(ScanParams P, Tables tab, RecordView rv, const flo
 // exact sequential weight chain each lane checks that ITS update maps +T to +T; if all do,
 // the sequential result is (+T, chained weight) without walking the distance chain.
 __global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
-                             const uint2* __restrict__ ray_c, const unsigned long long* __restrict__ long_list,
-                             const ScanState* st) {
+                             const uint2* __restrict__ ray_c, LongRuns lr, const ScanState* st) {
   const uint32_t* ckeys;
   const uint32_t* cvals;
   unsigned long long total;
@@ -817,7 +906,8 @@ __global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const floa
   const uint32_t n_long = st->n_long;
   const float T = P.up.trunc;
   for (uint32_t q = warp; q < n_long; q += n_warps) {
-    unsigned long long j0 = long_list[q];
+    if (lr.state[q] == 1u) continue;  // verified: every remaining update keeps (+T, max_weight)
+    unsigned long long j0 = lr.start[q];
     const uint32_t key = ckeys[j0];
     const VoxelRef vr = locate_voxel(P, tab, key);
     TsdfVoxel v = *vr.ptr;
@@ -1108,10 +1198,17 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
   }
   mk.mark(6);
   const unsigned int g_short = c->use_cub ? grid_for(K, 256) : 148 * 8;
-  k_apply_short<<<g_short, 256, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, c->long_list, c->d_state);
-  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, c->long_list, c->d_state);
+  LongRuns lr;
+  lr.start = c->long_list;
+  lr.end = c->long_end;
+  lr.state = c->long_state;
+  lr.item_run = c->verify_run;
+  lr.item_start = c->verify_start;
+  k_apply_short<<<g_short, 256, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
+  k_apply_verify<<<148 * 8, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
+  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
   mk.mark(7);
-  *launches += 2;
+  *launches += 3;
   return VBX_OK;
 }
 
