@@ -166,6 +166,8 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->long_state, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->verify_run, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->verify_start, (size_t)(c->max_updates / 32 + 1)));
+  CK(dmalloc(&c->rec_sdf, (size_t)c->max_updates));
+  CK(dmalloc(&c->rec_w, (size_t)c->max_updates));
   CK(dmalloc(&c->ray_p, np));
   CK(dmalloc(&c->ray_c, np));
   CK(dmalloc(&c->ray_a, np));
@@ -211,7 +213,7 @@ void vbx_destroy(vbx_ctx* c) {
                   c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
                   c->ray_list,    c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
                   c->sort_status[0], c->sort_status[1], c->scan_status, c->long_end, c->long_state,
-                  c->verify_run,  c->verify_start};
+                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }

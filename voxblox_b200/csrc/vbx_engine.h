@@ -127,6 +127,8 @@ struct vbx_ctx {
   uint32_t* long_state = nullptr;
   uint32_t* verify_run = nullptr;          // [max_updates / 32 + 1] work items of k_apply_verify
   unsigned long long* verify_start = nullptr;
+  float* rec_sdf = nullptr;                // [max_updates] per sorted record
+  float* rec_w = nullptr;
   float4* ray_p = nullptr;    // point_G.xyz, flags (bit 0: clearing ray)
   float4* ray_a = nullptr;    // point_G - origin, |point_G - origin|
   uint2* ray_c = nullptr;     // colour, weight bits

@@ -766,6 +766,8 @@ struct LongRuns {
   uint32_t* state;
   uint32_t* item_run;          // work items of k_apply_verify
   unsigned long long* item_start;
+  float* rec_sdf;              // per sorted record: sdf and effective weight, written by
+  float* rec_w;                // k_apply_short's parallel phase, read by the long-run kernels
 };
 
 // One warp per work item: do all updates in [start, start + kVerifyItem) of a saturated voxel's
@@ -788,29 +790,12 @@ __global__ void k_apply_verify(ScanParams P, Tables tab, RecordView rv, const fl
     const uint32_t q = lr.item_run[it];
     const unsigned long long a = lr.item_start[it];
     const unsigned long long b = min(a + kVerifyItem, lr.end[q]);
-    const VoxelRef vr = locate_voxel(P, tab, ckeys[a]);
     bool ok = true;
-    // all record -> ray-table gathers of the item are issued before any is consumed
-    uint32_t r[kVerifyItem / 32];
-    float4 ra[kVerifyItem / 32];
-    uint32_t wbits[kVerifyItem / 32];
 #pragma unroll
     for (int k = 0; k < (int)(kVerifyItem / 32); ++k) {
       const unsigned long long j = a + lane + 32ull * k;
-      r[k] = j < b ? cvals[j] : 0xffffffffu;
-    }
-#pragma unroll
-    for (int k = 0; k < (int)(kVerifyItem / 32); ++k) {
-      if (r[k] != 0xffffffffu) {
-        ra[k] = ray_a[r[k]];
-        wbits[k] = ray_c[r[k]].y;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < (int)(kVerifyItem / 32); ++k) {
-      if (r[k] == 0xffffffffu) continue;
-      const float sdf = sdf_from(vr.vo, ra[k]);
-      const float w = update_weight(sdf, __uint_as_float(wbits[k]), P.up);
+      if (j >= b) continue;
+      const float sdf = lr.rec_sdf[j], w = lr.rec_w[j];
       const float nw = fadd(W, w);
       bool keeps = sdf >= T && !(nw < VBX_EPS) && !(nw < W);
       if (keeps) {
@@ -825,65 +810,98 @@ __global__ void k_apply_verify(ScanParams P, Tables tab, RecordView rv, const fl
 
 // One thread per run head applies the first kShortRun updates of its voxel in order
 // (updateTsdfVoxel, cc:150-209); longer runs are queued for k_apply_long.
-__global__ void k_apply_short(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
-                              const uint2* __restrict__ ray_c, LongRuns lr, ScanState* st) {
+__global__ void __launch_bounds__(256)
+k_apply_short(ScanParams P, Tables tab, RecordView rv, const float4* __restrict__ ray_a,
+              const uint2* __restrict__ ray_c, LongRuns lr, ScanState* st) {
+  // Phase 1 (every thread): one record each -- gather its ray, form sdf and weight.  This is the
+  // expensive, perfectly parallel part; results are staged in shared memory.
+  // Phase 2 (run heads): the read-modify-write chain of updateTsdfVoxel over the staged values.
+  __shared__ uint32_t s_key[256];
+  __shared__ float s_sdf[256];
+  __shared__ float s_w[256];
+  __shared__ uint32_t s_col[256];
   const uint32_t* ckeys;
   const uint32_t* cvals;
   unsigned long long total;
   open_records(rv, &ckeys, &cvals, &total);
-  if (st->error & kFatalErrors) return;  // e.g. the pool filled up: blocks without a slot exist
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  const unsigned long long total_up = (total + 31ull) & ~31ull;  // whole warps stay in the loop
-  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_up; e += stride) {
+  if (st->error & kFatalErrors) return;
+  const unsigned long long n_tiles = (total + 255ull) / 256ull;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long base = tile * 256ull;
+    const unsigned long long e = base + threadIdx.x;
     bool head = false;
+    uint32_t key = 0xffffffffu;
+    VoxelRef vr;
+    vr.ptr = nullptr;
+    vr.vo = f3(0.f, 0.f, 0.f);
     if (e < total) {
-      const uint32_t key = ckeys[e];
+      key = ckeys[e];
       head = (e == 0) || (ckeys[e - 1] != key);
-      if (head) {
-        const VoxelRef vr = locate_voxel(P, tab, key);
-        TsdfVoxel v = *vr.ptr;
-        unsigned long long j = e;
-        for (int k = 0; k < kShortRun && j < total && ckeys[j] == key; ++k, ++j) {
-          const uint32_t r = cvals[j];
-          const float4 ra = ray_a[r];
+      const uint32_t r = cvals[e];
+      const float4 ra = ray_a[r];
+      const uint2 rc = ray_c[r];
+      vr = locate_voxel(P, tab, key);
+      const float sdf = sdf_from(vr.vo, ra);
+      const float w = update_weight(sdf, __uint_as_float(rc.y), P.up);
+      s_sdf[threadIdx.x] = sdf;
+      s_w[threadIdx.x] = w;
+      s_col[threadIdx.x] = rc.x;
+      lr.rec_sdf[e] = sdf;
+      lr.rec_w[e] = w;
+    }
+    s_key[threadIdx.x] = key;
+    __syncthreads();
+    if (head) {
+      TsdfVoxel v = *vr.ptr;
+      unsigned long long j = e;
+      int k = 0;
+      // inside this tile: staged values
+      for (; k < kShortRun && j < base + 256ull && s_key[j - base] == key; ++k, ++j) {
+        apply_update(v, s_sdf[j - base], s_w[j - base], s_col[j - base], P.up);
+      }
+      // a run that crosses the tile boundary continues from global memory
+      if (j == base + 256ull) {
+        for (; k < kShortRun && j < total && ckeys[j] == key; ++k, ++j) {
+          const uint32_t r = cvals[j];  // (the next tile's staged values are not visible here)
+          const float sdf = sdf_from(vr.vo, ray_a[r]);
           const uint2 rc = ray_c[r];
-          const float sdf = sdf_from(vr.vo, ra);
           apply_update(v, sdf, update_weight(sdf, __uint_as_float(rc.y), P.up), rc.x, P.up);
         }
-        *vr.ptr = v;
-        if (j < total && ckeys[j] == key) {
-          const uint32_t q = atomicAdd(&st->n_long, 1u);
-          lr.start[q] = j;
-          // A voxel resting at (+T, max_weight) -- free space seen many times -- stays there as
-          // long as every remaining update maps that state onto itself, which can be checked
-          // record by record, in parallel (k_apply_verify).  Find the end of the run (records are
-          // sorted) and cut it into work items.
-          const bool saturated = v.distance == P.up.trunc && v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS;
-          uint32_t state = 0u;
-          if (saturated) {
-            unsigned long long lo = j, hi = total;  // first record past the run
-            while (lo < hi) {
-              const unsigned long long mid = (lo + hi) >> 1;
-              if (ckeys[mid] <= key) {
-                lo = mid + 1;
-              } else {
-                hi = mid;
-              }
+      }
+      *vr.ptr = v;
+      if (j < total && ckeys[j] == key) {
+        const uint32_t q = atomicAdd(&st->n_long, 1u);
+        lr.start[q] = j;
+        // A voxel resting at (+T, max_weight) -- free space seen many times -- stays there as
+        // long as every remaining update maps that state onto itself, which can be checked
+        // record by record, in parallel (k_apply_verify).  Find the end of the run (records are
+        // sorted) and cut it into work items.
+        const bool saturated = v.distance == P.up.trunc && v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS;
+        uint32_t state = 0u;
+        if (saturated) {
+          unsigned long long lo = j, hi = total;  // first record past the run
+          while (lo < hi) {
+            const unsigned long long mid = (lo + hi) >> 1;
+            if (ckeys[mid] <= key) {
+              lo = mid + 1;
+            } else {
+              hi = mid;
             }
-            lr.end[q] = lo;
-            for (unsigned long long a = j; a < lo; a += kVerifyItem) {
-              const uint32_t it = atomicAdd(&st->n_verify, 1u);
-              lr.item_run[it] = q;
-              lr.item_start[it] = a;
-            }
-            state = 1u;
           }
-          lr.state[q] = state;
+          lr.end[q] = lo;
+          for (unsigned long long a = j; a < lo; a += kVerifyItem) {
+            const uint32_t it = atomicAdd(&st->n_verify, 1u);
+            lr.item_run[it] = q;
+            lr.item_start[it] = a;
+          }
+          state = 1u;
         }
+        lr.state[q] = state;
       }
     }
     const unsigned b = __ballot_sync(0xffffffffu, head);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->n_voxels, (uint32_t)__popc(b));
+    __syncthreads();  // the staging arrays are reused by the next tile
   }
 }
 
@@ -912,105 +930,107 @@ __global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const floa
     const VoxelRef vr = locate_voxel(P, tab, key);
     TsdfVoxel v = *vr.ptr;
     bool done = false;
-    // Three-stage software pipeline over 32-record chunks (one warp has nothing else to
-    // hide a record -> ray-data load chain behind): while chunk c is applied, the ray data
-    // of chunk c+1 and the records of chunk c+2 are in flight.  Loaded values are only
-    // LOOKED AT one stage later, so no stage waits on its own loads.
-    uint32_t key_a = ~key, r_a = 0u;   // stage A: raw record words of chunk c+2
-    bool in_b;                          // stage B: membership + ray data of chunk c+1
-    float4 ra_b = make_float4(0.f, 0.f, 0.f, 1.f);
-    uint2 rc_b = make_uint2(0u, 0u);
-    {
-      unsigned long long j = j0 + lane;
-      in_b = j < total && ckeys[j] == key;
-      if (in_b) {
-        const uint32_t r = cvals[j];
-        ra_b = ray_a[r];
-        rc_b = ray_c[r];
-      }
-      j += 32;
-      if (j < total) {
-        key_a = ckeys[j];
-        r_a = cvals[j];
-      }
+    // sdf and weight of every record were computed by k_apply_short's parallel phase; the chain
+    // only streams them.  Four 32-record chunks are loaded per step (and the next four are
+    // prefetched) so that the loads of a step are all in flight together; colours are gathered
+    // on the rare chunks that need the full update.
+    constexpr int kG = 4;
+    bool in_n[kG];
+    float sdf_n[kG], w_n[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const unsigned long long j = j0 + 32ull * g + lane;
+      in_n[g] = j < total && ckeys[j] == key;
+      sdf_n[g] = in_n[g] ? lr.rec_sdf[j] : 0.f;
+      w_n[g] = in_n[g] ? lr.rec_w[j] : 0.f;
     }
     while (!done) {
-      const bool in = in_b;
-      const float4 ra = ra_b;
-      const uint2 rc = rc_b;
-      const uint32_t col = rc.x;
-      const int cnt = __popc(__ballot_sync(0xffffffffu, in));
-      if (cnt == 32) {
-        in_b = key_a == key;
-        if (in_b) {
-          ra_b = ray_a[r_a];
-          rc_b = ray_c[r_a];
-        }
-        const unsigned long long j = j0 + 64 + lane;
-        key_a = ~key;
-        if (j < total) {
-          key_a = ckeys[j];
-          r_a = cvals[j];
+      bool in_c[kG];
+      float sdf_c[kG], w_c[kG];
+#pragma unroll
+      for (int g = 0; g < kG; ++g) {
+        in_c[g] = in_n[g];
+        sdf_c[g] = sdf_n[g];
+        w_c[g] = w_n[g];
+      }
+      const bool more = __all_sync(0xffffffffu, in_c[kG - 1]);  // the run may continue past these records
+      if (more) {
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+          const unsigned long long j = j0 + 32ull * (kG + g) + lane;
+          in_n[g] = j < total && ckeys[j] == key;
+          sdf_n[g] = in_n[g] ? lr.rec_sdf[j] : 0.f;
+          w_n[g] = in_n[g] ? lr.rec_w[j] : 0.f;
         }
       }
-      float sdf = 0.f, w = 0.f;
-      if (in) {
-        sdf = sdf_from(vr.vo, ra);
-        w = update_weight(sdf, __uint_as_float(rc.y), P.up);
-      }
-      const bool far_free = !in || sdf >= T;
-      bool fast = __all_sync(0xffffffffu, far_free) && v.distance == T;
-      float w_end = v.weight;
-      if (fast) {
-        // exact sequential weight chain: W <- min(W + w, max_weight) unless W + w < 1e-6
-        float my_before = 0.f;
-        float wsum = in ? w : 0.f;  // any-order sum, used only as a bound
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-        if (v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS) {
-          // the weight already sits at max_weight: W + w >= max_weight for every w >= 0, so the
-          // clamp returns max_weight at every step
-          my_before = v.weight;
-        } else if (v.weight >= VBX_EPS && (v.weight + wsum) * 1.0001f < P.up.max_weight) {
-          // neither the 1e-6 guard nor the max_weight clamp can fire in this chunk: the
-          // chain is plain in-order addition; lane L forms its own prefix
-          const float wl = in ? w : 0.f;
-          my_before = v.weight;
+      for (int g = 0; g < kG; ++g) {
+        const bool in = in_c[g];
+        const float sdf = sdf_c[g], w = w_c[g];
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        if (cnt == 0) break;
+        const bool far_free = !in || sdf >= T;
+        bool fast = __all_sync(0xffffffffu, far_free) && v.distance == T;
+        float w_end = v.weight;
+        if (fast) {
+          // exact sequential weight chain: W <- min(W + w, max_weight) unless W + w < 1e-6
+          float my_before = 0.f;
+          float wsum = in ? w : 0.f;  // any-order sum, used only as a bound
 #pragma unroll
-          for (int k = 0; k < 31; ++k) {
-            const float wk = __shfl_sync(0xffffffffu, wl, k);
-            if (k < lane) my_before = fadd(my_before, wk);
+          for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+          const bool no_clamp = v.weight >= VBX_EPS && (v.weight + wsum) * 1.0001f < P.up.max_weight;
+          if (v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS) {
+            // the weight already sits at max_weight: W + w >= max_weight for every w >= 0, so the
+            // clamp returns max_weight at every step
+            my_before = v.weight;
+          } else if (no_clamp && v.weight < 4194304.0f && v.weight == truncf(v.weight) &&
+                     __all_sync(0xffffffffu, !in || w == 1.0f)) {
+            // constant weights (use_const_weight) on an integer-valued W below 2^22: every partial
+            // sum is an integer that float represents exactly, so the in-order chain is W + k
+            my_before = v.weight + (float)lane;
+            w_end = v.weight + (float)cnt;
+          } else if (no_clamp) {
+            // neither the 1e-6 guard nor the max_weight clamp can fire in this chunk: the
+            // chain is plain in-order addition; lane L forms its own prefix
+            const float wl = in ? w : 0.f;
+            my_before = v.weight;
+#pragma unroll
+            for (int k = 0; k < 31; ++k) {
+              const float wk = __shfl_sync(0xffffffffu, wl, k);
+              if (k < lane) my_before = fadd(my_before, wk);
+            }
+            w_end = __shfl_sync(0xffffffffu, fadd(my_before, wl), 31);
+          } else {
+            for (int k = 0; k < cnt; ++k) {
+              const float wk = __shfl_sync(0xffffffffu, w, k);
+              if (lane == k) my_before = w_end;
+              const float nw = fadd(w_end, wk);
+              w_end = (nw < VBX_EPS) ? w_end : ((nw < P.up.max_weight) ? nw : P.up.max_weight);
+            }
           }
-          w_end = __shfl_sync(0xffffffffu, fadd(my_before, wl), 31);
+          bool keeps_T = true;
+          if (in) {
+            const float nw = fadd(my_before, w);
+            if (!(nw < VBX_EPS)) {
+              const float ns = fdiv(fadd(fmul(sdf, w), fmul(T, my_before)), nw);
+              const float clamped = (ns > 0.0f) ? ((ns < T) ? ns : T) : ((-T < ns) ? ns : -T);
+              keeps_T = (clamped == T);
+            }
+          }
+          fast = __all_sync(0xffffffffu, keeps_T);
+        }
+        if (fast) {
+          v.weight = w_end;
         } else {
+          const uint32_t col = in ? ray_c[cvals[j0 + 32ull * g + lane]].x : 0u;
           for (int k = 0; k < cnt; ++k) {
-            const float wk = __shfl_sync(0xffffffffu, w, k);
-            if (lane == k) my_before = w_end;
-            const float nw = fadd(w_end, wk);
-            w_end = (nw < VBX_EPS) ? w_end : ((nw < P.up.max_weight) ? nw : P.up.max_weight);
+            apply_update(v, __shfl_sync(0xffffffffu, sdf, k), __shfl_sync(0xffffffffu, w, k),
+                         __shfl_sync(0xffffffffu, col, k), P.up);
           }
         }
-        bool keeps_T = true;
-        if (in) {
-          const float nw = fadd(my_before, w);
-          if (!(nw < VBX_EPS)) {
-            const float ns = fdiv(fadd(fmul(sdf, w), fmul(T, my_before)), nw);
-            const float clamped = (ns > 0.0f) ? ((ns < T) ? ns : T) : ((-T < ns) ? ns : -T);
-            keeps_T = (clamped == T);
-          }
-        }
-        fast = __all_sync(0xffffffffu, keeps_T);
       }
-      if (fast) {
-        v.weight = w_end;
-      } else {
-        for (int k = 0; k < cnt; ++k) {
-          apply_update(v, __shfl_sync(0xffffffffu, sdf, k), __shfl_sync(0xffffffffu, w, k),
-                       __shfl_sync(0xffffffffu, col, k), P.up);
-        }
-      }
-      j0 += 32;
-      if (cnt < 32) done = true;
+      j0 += 32ull * kG;
+      if (!more) done = true;
     }
     if (lane == 0) *vr.ptr = v;
   }
@@ -1204,6 +1224,8 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
   lr.state = c->long_state;
   lr.item_run = c->verify_run;
   lr.item_start = c->verify_start;
+  lr.rec_sdf = c->rec_sdf;
+  lr.rec_w = c->rec_w;
   k_apply_short<<<g_short, 256, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
   k_apply_verify<<<148 * 8, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
   k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
