@@ -132,6 +132,19 @@ VBX_API int vbx_get_tsdf_config(const vbx_ctx* ctx, vbx_tsdf_config* out);
  * drained (the reference's call is synchronous too). */
 VBX_API int vbx_tsdf_integrate(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
                        const float* xyz, const uint8_t* rgba, uint64_t n, int freespace);
+/* Asynchronous submission (no reference counterpart: its call is synchronous).  Enqueues the scan
+ * and returns; up to two scans are in flight, the map-independent front half of scan i+1
+ * (transform, bundle sort, bundle fold) overlapping the map-updating back half of scan i on a
+ * second stream.  Map updates still happen strictly in submission order, so the result equals
+ * the synchronous calls'.  Host buffers (inputs_on_device = 0) must be page-locked and stay
+ * untouched until the scan completed (vbx_sync, or two submissions later).  Counters and errors
+ * of a scan surface at the next synchronous call / vbx_sync (a failed scan is reported, not
+ * retried: a clearing point beyond the compact key range -- 511 voxels -- drops that scan).
+ * Configurations whose front half touches the map (Fast, anti-grazing, "sorted" order) fall back
+ * to the synchronous path. */
+VBX_API int vbx_tsdf_integrate_async(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
+                             const float* xyz, const uint8_t* rgba, uint64_t n, int freespace,
+                             int inputs_on_device);
 /* Same, with xyz / rgba already resident in DEVICE memory (no copies). */
 VBX_API int vbx_tsdf_integrate_device(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
                               const float* d_xyz, const uint8_t* d_rgba, uint64_t n,
@@ -141,7 +154,9 @@ VBX_API int vbx_tsdf_integrate_device(vbx_ctx* ctx, int kind, const float q_wxyz
  * VLOG(3), tsdf_integrator.cc:368-370):
  * [0] normal rays/bundles cast  [1] clearing rays/bundles cast  [2] ray-voxel updates
  * [3] distinct voxels touched   [4] distinct blocks touched     [5] blocks allocated
- * [6] valid points              [7] kernels launched            [8..15] reserved */
+ * [6] valid points              [7] kernels launched            [8] kernels launched by all
+ * integrate calls since vbx_create                               [9..15] reserved
+ * After asynchronous submissions: the counters of the last scan collected (all, after vbx_sync). */
 VBX_API int vbx_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
 /* Device time (ms, CUDA events on the context's stream) of the last integrate /
  * ESDF update call, excluding host<->device copies of the cloud. */

@@ -175,3 +175,75 @@ def test_fast_integrator_statistics():
     rmse = float(np.sqrt(np.mean((g["distance"][both] - o["distance"][both]) ** 2)))
     print("fast: blocks", len(gb), len(ob), "observed overlap", both.sum() / either.sum(), "rmse", rmse)
     assert rmse < 0.1  # one voxel
+
+
+# ------------------------------------------------------------------ asynchronous submission
+def _layer_bytes(layer):
+    idx = layer.getAllAllocatedBlocks()
+    vox, upd = layer.getBlocks(idx)
+    return idx.tobytes(), vox.tobytes(), np.asarray(upd).tobytes()
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("pageable", [False, True])
+def test_async_submission_equals_synchronous(kind, pageable):
+    """vbx_tsdf_integrate_async overlaps the front half of scan i+1 with the back half of scan i;
+    the map must equal the synchronous calls' bit for bit (and so the oracle's)."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    scans = scenes.c3_room_sequence(n_scans=7, width=160, height=120)
+    la, ls = vb.Layer(0.1, 16), vb.Layer(0.1, 16)
+    ia = vb.TsdfIntegratorFactory.create(kind, cfg, la)
+    isync = vb.TsdfIntegratorFactory.create(kind, cfg, ls)
+    keep = []
+    for s in scans:
+        isync.integratePointCloud((s[2], s[3]), s[0], s[1])
+        if pageable:
+            p, c = np.ascontiguousarray(s[0]), np.ascontiguousarray(s[1])
+        else:
+            p, c = la.hostBuffer(s[0].shape, np.float32), la.hostBuffer(s[1].shape, np.uint8)
+            p[...] = s[0]
+            c[...] = s[1]
+        keep.append((p, c))
+        ia.integratePointCloudAsync((s[2], s[3]), p, c)
+    la.sync()
+    assert ia.counters()["updates"] == isync.counters()["updates"]
+    assert _layer_bytes(la) == _layer_bytes(ls)
+    # a synchronous call after asynchronous ones continues the same map
+    s = scans[0]
+    ia.integratePointCloud((s[2], s[3]), s[0], s[1])
+    isync.integratePointCloud((s[2], s[3]), s[0], s[1])
+    assert _layer_bytes(la) == _layer_bytes(ls)
+
+
+def test_async_far_points_are_reported_not_silently_dropped():
+    """A scan whose clearing points overflow the compact bundle keys cannot be redone once later
+    scans are queued behind it: the error surfaces at the next synchronising call, and later
+    submissions switch to full-width keys."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    s = _small_scans(1)[0]
+    pts = s[0].copy()
+    pts[::7] *= 40.0
+    integ.integratePointCloudAsync((s[2], s[3]), pts, s[1])
+    with pytest.raises(vb.VoxbloxError):
+        layer.sync()
+    assert layer.getNumberOfAllocatedBlocks() == 0
+    integ.integratePointCloudAsync((s[2], s[3]), pts, s[1])   # now with full-width keys
+    layer.sync()
+    ref = vb.Layer(0.1, 16)
+    r = vb.TsdfIntegratorFactory.create("merged", cfg, ref)
+    r.integratePointCloud((s[2], s[3]), pts, s[1])
+    assert _layer_bytes(layer) == _layer_bytes(ref)
+
+
+def test_async_falls_back_for_map_dependent_front_halves():
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1, enable_anti_grazing=True)
+    la, ls = vb.Layer(0.1, 16), vb.Layer(0.1, 16)
+    ia = vb.TsdfIntegratorFactory.create("merged", cfg, la)
+    isync = vb.TsdfIntegratorFactory.create("merged", cfg, ls)
+    for s in _small_scans(3):
+        ia.integratePointCloudAsync((s[2], s[3]), s[0], s[1])
+        isync.integratePointCloud((s[2], s[3]), s[0], s[1])
+    la.sync()
+    assert _layer_bytes(la) == _layer_bytes(ls)

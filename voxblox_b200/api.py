@@ -113,7 +113,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync",
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
-           "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan"]
+           "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async"]
 
 _lib = None
 
@@ -142,6 +142,8 @@ def load_library():
         f = getattr(lib, name)
         f.restype = i32
         f.argtypes = [vp, i32, vp, vp, vp, vp, u64, i32]
+    lib.vbx_tsdf_integrate_async.restype = i32
+    lib.vbx_tsdf_integrate_async.argtypes = [vp, i32, vp, vp, vp, vp, u64, i32, i32]
     lib.vbx_get_counters.restype = i32
     lib.vbx_get_counters.argtypes = [vp, vp]
     lib.vbx_esdf_get_counters.restype = i32
@@ -445,12 +447,30 @@ class TsdfIntegratorBase:
                                                     int(bool(freespace_points))),
                   "integratePointCloudDevice")
 
+    def integratePointCloudAsync(self, T_G_C, points, colors, n: Optional[int] = None,
+                                 freespace_points: bool = False) -> None:
+        """Enqueue a scan and return (vbx_tsdf_integrate_async).  points / colors are either
+        page-locked host numpy arrays (kept alive and untouched by the caller until Layer.sync())
+        or raw device pointers (ints) with n given."""
+        q, t = _as_pose(T_G_C)
+        ctx = self._ctx
+        if isinstance(points, (int, np.integer)):
+            px, pc, cnt, on_dev = int(points), int(colors), int(n), 1
+        else:
+            assert points.dtype == np.float32 and points.flags.c_contiguous
+            assert colors.dtype == np.uint8 and colors.flags.c_contiguous
+            if points.shape[0] != colors.shape[0]:
+                raise VoxbloxError("Check failed: points_C.size() == colors.size()")
+            px, pc, cnt, on_dev = points.ctypes.data, colors.ctypes.data, points.shape[0], 0
+        ctx.check(ctx.lib.vbx_tsdf_integrate_async(ctx.handle, self.kind, q.ctypes.data, t.ctypes.data, px, pc, cnt,
+                                                   int(bool(freespace_points)), on_dev), "integratePointCloudAsync")
+
     def counters(self) -> Dict[str, int]:
         out = np.zeros(16, dtype=np.uint64)
         self._ctx.check(self._ctx.lib.vbx_get_counters(self._ctx.handle, out.ctypes.data),
                         "vbx_get_counters")
         names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
-                 "blocks_allocated", "valid_points", "kernel_launches"]
+                 "blocks_allocated", "valid_points", "kernel_launches", "kernel_launches_total"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def lastDeviceMs(self) -> float:

@@ -90,7 +90,7 @@ int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const 
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   if (c->h_state->error & kFatalErrors) return fail(c, VBX_E_CAPACITY, "block pool / hash full during upload");
-  c->n_blocks = c->h_state->n_blocks;
+  if (int rc = set_n_blocks(c, c->h_state->n_blocks)) return rc;
   const size_t bbytes = voxel_bytes(layer) * c->vox_per_block;
   char* pool = layer == VBX_LAYER_TSDF ? reinterpret_cast<char*>(c->tab.tsdf) : reinterpret_cast<char*>(c->tab.esdf);
   std::vector<uint8_t> ones(1, 1);
@@ -130,7 +130,7 @@ int clear_layer(vbx_ctx* c, int layer) {
   VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->tab.max_blocks, s));
   VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->tab.max_blocks, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
-  c->n_blocks = 0;
+  if (int rc = set_n_blocks(c, 0)) return rc;
   c->host_slot_key.clear();
   c->host_key2slot.clear();
   return VBX_OK;
@@ -183,7 +183,7 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
     VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf + last, 0, 1, s));
     --n;
   }
-  c->n_blocks = n;
+  if (int rc = set_n_blocks(c, n)) return rc;
   VBX_CUDA(c, cudaMemsetAsync(c->tab.hkeys, 0xff, (size_t)c->hcap * sizeof(uint64_t), s));
   VBX_CUDA(c, cudaMemsetAsync(c->tab.hslot, 0xff, (size_t)c->hcap * sizeof(int32_t), s));
   VBX_CUDA(c, cudaMemsetAsync(c->tab.htouch_epoch, 0, (size_t)c->hcap * sizeof(uint32_t), s));

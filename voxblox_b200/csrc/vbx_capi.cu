@@ -26,6 +26,8 @@ int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const 
                   const uint8_t* updated_bits);
 int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m);
 int clear_layer(vbx_ctx* c, int layer);
+int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* xyz, const uint8_t* rgba,
+                    uint64_t n, int freespace, int on_device);
 int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
 
@@ -52,6 +54,66 @@ int refresh_host_mirror(vbx_ctx* c) {
   return VBX_OK;
 }
 
+int set_n_blocks(vbx_ctx* c, uint32_t n) {
+  c->n_blocks = n;
+  VBX_CUDA(c, cudaMemcpyAsync(c->d_nblocks + c->nb_cur, &c->n_blocks, sizeof(uint32_t), cudaMemcpyHostToDevice,
+                              c->stream_main));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream_main));
+  return VBX_OK;
+}
+
+// Collect a finished asynchronous scan: its counters, the block count, and any error it raised
+// (reported by the next call that can return one).
+void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S) {
+  S.in_flight = false;
+  const ScanState& h = *S.h_state;
+  c->n_blocks = std::max(c->n_blocks, h.n_blocks);
+  std::memset(c->counters, 0, sizeof(c->counters));
+  c->counters[0] = h.n_rays;
+  c->counters[1] = h.n_clear_rays;
+  c->counters[2] = h.total_found;
+  c->counters[3] = h.n_voxels;
+  c->counters[4] = h.n_touched;
+  c->counters[5] = h.n_new;
+  c->counters[6] = S.kind == VBX_MERGED ? h.n_valid_points : (uint64_t)h.n_rays + h.n_clear_rays;
+  c->counters[7] = S.launches;
+  if (h.error & kNeedWideKeys) c->force_wide_keys = true;  // later submissions use full-width keys
+  if (h.error && !c->deferred_rc) {
+    c->deferred_rc = VBX_E_CAPACITY;
+    c->deferred_msg = "an asynchronously submitted scan failed on the device (error bits " + std::to_string(h.error) +
+                      (h.error & kNeedWideKeys ? ": a point lies outside the compact bundle-key range; that scan was NOT integrated" : "") + ")";
+  }
+}
+
+int drain_async(vbx_ctx* c) {
+  for (int k = 0; k < 2; ++k) {
+    vbx_ctx::ScratchSet& S = c->set[(c->async_seq + k) & 1];  // older submission first
+    if (!S.in_flight) continue;
+    VBX_CUDA(c, cudaEventSynchronize(S.back_done));
+    harvest_async(c, S);
+  }
+  // synchronous calls use hand-off set 0
+  c->ray_p = c->set[0].ray_p;
+  c->ray_a = c->set[0].ray_a;
+  c->ray_c = c->set[0].ray_c;
+  c->ray_list = c->set[0].ray_list;
+  c->cnt = c->set[0].cnt;
+  c->off = c->set[0].off;
+  c->d_state = c->set[0].d_state;
+  c->h_state = c->set[0].h_state;
+  c->d_xyz = c->set[0].d_xyz;
+  c->d_rgba = c->set[0].d_rgba;
+  c->pkeys[0] = c->set[0].pkeys0;
+  c->stream = c->stream_main;
+  if (c->deferred_rc) {
+    const int rc = c->deferred_rc;
+    c->err = c->deferred_msg;
+    c->deferred_rc = 0;
+    return rc;
+  }
+  return VBX_OK;
+}
+
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
@@ -60,6 +122,13 @@ static cudaError_t dmalloc(T** p, size_t count) {
 }  // namespace vbx
 
 using namespace vbx;
+
+// every synchronous entry point first waits for asynchronously submitted scans (and reports a
+// deferred error of theirs)
+#define VBX_DRAIN(c)                          \
+  do {                                        \
+    if (int _rc = drain_async(c)) return _rc; \
+  } while (0)
 
 extern "C" {
 
@@ -117,7 +186,10 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
   } while (0)
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream_main, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream_f, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream_c, cudaStreamNonBlocking));
+  c->stream = c->stream_main;
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreate(&c->tev0));
@@ -195,6 +267,40 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->d_state, 1));
   CK(cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), c->stream));
   CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_state), sizeof(ScanState)));
+  CK(dmalloc(&c->d_nblocks, 2));
+  CK(cudaMemsetAsync(c->d_nblocks, 0, 2 * sizeof(uint32_t), c->stream));
+  {
+    // hand-off set 0 is the buffers above, set 1 a second copy (asynchronous submission)
+    vbx_ctx::ScratchSet& a = c->set[0];
+    a.ray_p = c->ray_p;
+    a.ray_a = c->ray_a;
+    a.ray_c = c->ray_c;
+    a.ray_list = c->ray_list;
+    a.cnt = c->cnt;
+    a.off = c->off;
+    a.d_state = c->d_state;
+    a.h_state = c->h_state;
+    a.d_xyz = c->d_xyz;
+    a.d_rgba = c->d_rgba;
+    a.pkeys0 = c->pkeys[0];
+    vbx_ctx::ScratchSet& b = c->set[1];
+    CK(dmalloc(&b.ray_p, np));
+    CK(dmalloc(&b.ray_a, np));
+    CK(dmalloc(&b.ray_c, np));
+    CK(dmalloc(&b.ray_list, np));
+    CK(dmalloc(&b.cnt, np + 1));
+    CK(dmalloc(&b.off, np + 1));
+    CK(dmalloc(&b.d_state, 1));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&b.h_state), sizeof(ScanState)));
+    CK(dmalloc(&b.d_xyz, 3 * np));
+    CK(dmalloc(&b.d_rgba, 4 * np));
+    CK(dmalloc(&b.pkeys0, np));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&c->set[i].copy_done, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->set[i].front_done, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->set[i].back_done, cudaEventDisableTiming));
+    }
+  }
   CK(cudaStreamSynchronize(c->stream));
 #undef CK
   return VBX_OK;
@@ -203,7 +309,22 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
 void vbx_destroy(vbx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream_main) cudaStreamSynchronize(c->stream_main);
+  if (c->stream_f) cudaStreamSynchronize(c->stream_f);
+  if (c->stream_c) cudaStreamSynchronize(c->stream_c);
+  // restore the aliases of hand-off set 0 before freeing
+  c->ray_p = c->set[0].ray_p;
+  c->ray_a = c->set[0].ray_a;
+  c->ray_c = c->set[0].ray_c;
+  c->ray_list = c->set[0].ray_list;
+  c->cnt = c->set[0].cnt;
+  c->off = c->set[0].off;
+  c->d_state = c->set[0].d_state;
+  c->h_state = c->set[0].h_state;
+  c->d_xyz = c->set[0].d_xyz;
+  c->d_rgba = c->set[0].d_rgba;
+  c->pkeys[0] = c->set[0].pkeys0;
+  c->stream = c->stream_main;
   esdf_destroy(c);
   Tables& t = c->tab;
   void* ptrs[] = {t.hkeys,        t.hslot,       t.htouch_epoch, t.htouch_rank, t.new_list, t.touched_list,
@@ -213,11 +334,19 @@ void vbx_destroy(vbx_ctx* c) {
                   c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
                   c->ray_list,    c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
                   c->sort_status[0], c->sort_status[1], c->scan_status, c->long_end, c->long_state,
-                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w};
+                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w, c->d_nblocks, c->set[1].ray_p,
+                  c->set[1].ray_a, c->set[1].ray_c, c->set[1].ray_list, c->set[1].cnt, c->set[1].off,
+                  c->set[1].d_state, c->set[1].d_xyz, c->set[1].d_rgba, c->set[1].pkeys0};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }
   if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->set[1].h_state) cudaFreeHost(c->set[1].h_state);
+  for (int i = 0; i < 2; ++i) {
+    if (c->set[i].copy_done) cudaEventDestroy(c->set[i].copy_done);
+    if (c->set[i].front_done) cudaEventDestroy(c->set[i].front_done);
+    if (c->set[i].back_done) cudaEventDestroy(c->set[i].back_done);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->tev0) cudaEventDestroy(c->tev0);
@@ -225,7 +354,9 @@ void vbx_destroy(vbx_ctx* c) {
   for (int i = 0; i < 20; ++i) {
     if (c->sev[i]) cudaEventDestroy(c->sev[i]);
   }
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream_main) cudaStreamDestroy(c->stream_main);
+  if (c->stream_f) cudaStreamDestroy(c->stream_f);
+  if (c->stream_c) cudaStreamDestroy(c->stream_c);
   delete c;
 }
 
@@ -239,6 +370,7 @@ int vbx_tsdf_integrate_device(vbx_ctx* c, int kind, const float q[4], const floa
                               const uint8_t* d_rgba, uint64_t n, int freespace) {
   if (!c || !q || !t || (n && (!d_xyz || !d_rgba))) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return integrate_device(c, kind, q, t, d_xyz, d_rgba, n, freespace);
 }
 
@@ -247,11 +379,19 @@ int vbx_tsdf_integrate(vbx_ctx* c, int kind, const float q[4], const float t[3],
   if (!c || !q || !t || (n && (!xyz || !rgba))) return fail(c, VBX_E_INVALID, "null argument");
   if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   if (n) {
     VBX_CUDA(c, cudaMemcpyAsync(c->d_xyz, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     VBX_CUDA(c, cudaMemcpyAsync(c->d_rgba, rgba, n * 4, cudaMemcpyHostToDevice, c->stream));
   }
   return integrate_device(c, kind, q, t, c->d_xyz, c->d_rgba, n, freespace);
+}
+
+int vbx_tsdf_integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* xyz,
+                             const uint8_t* rgba, uint64_t n, int freespace, int inputs_on_device) {
+  if (!c || !q || !t || (n && (!xyz || !rgba))) return fail(c, VBX_E_INVALID, "null argument");
+  if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, VBX_E_CUDA, "cudaSetDevice");
+  return integrate_async(c, kind, q, t, xyz, rgba, n, freespace, inputs_on_device);
 }
 
 int vbx_shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out) {
@@ -266,6 +406,7 @@ int vbx_shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     return fail(c, VBX_E_INVALID, "null argument");
   }
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return shard_front(c, kind, q, t, d_xyz, d_rgba, n, freespace, lay, d_pack, count_out);
 }
 
@@ -273,6 +414,7 @@ int vbx_shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uin
                    const void* d_gathered, uint64_t pack_stride, const uint64_t* counts) {
   if (!c || !q || !t || !lay || !d_gathered || !counts) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return shard_back(c, kind, q, t, n, lay, d_gathered, pack_stride, counts);
 }
 
@@ -280,18 +422,21 @@ int vbx_debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int 
                    uint32_t* vals_out) {
   if (!c || (n && (!keys || !keys_out || !vals_out))) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return debug_sort(c, keys, key_bytes, n, key_bits, keys_out, vals_out);
 }
 
 int vbx_debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {
   if (!c || (n && (!in || !out))) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return debug_scan(c, in, n, out);
 }
 
 int vbx_get_counters(const vbx_ctx* c, uint64_t out[16]) {
   if (!c || !out) return VBX_E_INVALID;
   std::memcpy(out, c->counters, sizeof(c->counters));
+  out[8] = c->launches;  // kernels launched by TSDF integration since vbx_create
   return VBX_OK;
 }
 
@@ -310,6 +455,7 @@ int vbx_last_device_ms(const vbx_ctx* c, float* ms) {
 int vbx_host_alloc(vbx_ctx* c, size_t bytes, void** out) {
   if (!c || !out) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   VBX_CUDA(c, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
   return VBX_OK;
 }
@@ -324,6 +470,7 @@ int vbx_host_copy_ms(vbx_ctx* c, const void* src, size_t bytes, float* ms) {
   if (!c || !src || !ms) return VBX_E_INVALID;
   if (bytes > (size_t)c->max_points * 12) return fail(c, VBX_E_CAPACITY, "copy larger than the staging buffer");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   VBX_CUDA(c, cudaEventRecord(c->tev0, c->stream));
   VBX_CUDA(c, cudaMemcpyAsync(c->d_xyz, src, bytes, cudaMemcpyHostToDevice, c->stream));
   VBX_CUDA(c, cudaEventRecord(c->tev1, c->stream));
@@ -335,6 +482,7 @@ int vbx_host_copy_ms(vbx_ctx* c, const void* src, size_t bytes, float* ms) {
 int vbx_timer_start(vbx_ctx* c) {
   if (!c) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   VBX_CUDA(c, cudaEventRecord(c->tev0, c->stream));
   return VBX_OK;
 }
@@ -342,6 +490,7 @@ int vbx_timer_start(vbx_ctx* c) {
 int vbx_timer_stop_ms(vbx_ctx* c, float* ms) {
   if (!c || !ms) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   VBX_CUDA(c, cudaEventRecord(c->tev1, c->stream));
   VBX_CUDA(c, cudaEventSynchronize(c->tev1));
   VBX_CUDA(c, cudaEventElapsedTime(ms, c->tev0, c->tev1));
@@ -366,7 +515,10 @@ int vbx_get_stage_ms(const vbx_ctx* c, double ms[16], uint64_t calls[16]) {
 int vbx_sync(vbx_ctx* c) {
   if (!c) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
-  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  VBX_DRAIN(c);
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream_c));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream_f));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream_main));
   return VBX_OK;
 }
 
@@ -387,6 +539,7 @@ static int fetch_flags(vbx_ctx* c, int layer, std::vector<uint8_t>* upd, std::ve
 int vbx_num_blocks(vbx_ctx* c, int layer, uint64_t* n) {
   if (!c || !n) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   if (layer == VBX_LAYER_TSDF) {
     *n = c->n_blocks;
     return VBX_OK;
@@ -406,6 +559,7 @@ int vbx_num_blocks(vbx_ctx* c, int layer, uint64_t* n) {
 int vbx_list_blocks(vbx_ctx* c, int layer, int updated_mask, int32_t* idx3, uint64_t cap, uint64_t* n) {
   if (!c || !n) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   *n = 0;
   if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
   if (int rc = refresh_host_mirror(c)) return rc;
@@ -444,6 +598,7 @@ int vbx_download_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, 
                         uint8_t* updated_bits) {
   if (!c || (m && (!idx3 || !voxels))) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   if (layer == VBX_LAYER_ESDF && !c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF layer");
   if (int rc = refresh_host_mirror(c)) return rc;
   std::vector<uint8_t> upd, has;
@@ -466,6 +621,7 @@ int vbx_download_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, 
 int vbx_clear_updated(vbx_ctx* c, int layer, int updated_mask) {
   if (!c) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   if (c->n_blocks == 0) return VBX_OK;
   std::vector<uint8_t> upd, has;
   if (int rc = fetch_flags(c, layer, &upd, &has)) return rc;
@@ -480,30 +636,35 @@ int vbx_upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, co
                       const uint8_t* updated_bits) {
   if (!c || (m && (!idx3 || !voxels))) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return upload_blocks(c, layer, idx3, m, voxels, updated_bits);
 }
 
 int vbx_remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
   if (!c || (m && !idx3)) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return remove_blocks(c, layer, idx3, m);
 }
 
 int vbx_clear(vbx_ctx* c, int layer) {
   if (!c) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return clear_layer(c, layer);
 }
 
 int vbx_esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
   if (!c || !cfg) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   return esdf_create(c, cfg);
 }
 
 int vbx_esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
   if (!c) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
   if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_update before vbx_esdf_create");
   return esdf_update(c, batch, clear_updated_flag);
 }

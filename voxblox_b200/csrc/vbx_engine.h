@@ -104,7 +104,10 @@ __host__ __device__ inline uint32_t hash64(uint64_t k) {
 
 struct vbx_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream the next launch goes to (main, or stream_f while a front half is enqueued)
+  cudaStream_t stream_main = nullptr; // back halves, ESDF, block management, synchronous calls
+  cudaStream_t stream_c = nullptr;    // host-to-device cloud copies of asynchronously submitted scans
+  cudaStream_t stream_f = nullptr;    // front halves of asynchronously submitted scans
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   vbx_tsdf_config cfg;
   vbx_engine_options opt;
@@ -151,7 +154,32 @@ struct vbx_ctx {
   vbx::ScanState* d_state = nullptr;
   vbx::ScanState* h_state = nullptr;  // pinned
   uint32_t epoch = 0;                 // call id for touch marks
-  uint32_t n_blocks = 0;              // pool slots in use
+  uint32_t n_blocks = 0;              // pool slots in use (host copy, exact after a drain)
+  uint32_t* d_nblocks = nullptr;      // [2] device copy, ping-pong: k_assign reads [nb_cur], writes [nb_cur ^ 1]
+  int nb_cur = 0;
+  // Asynchronous submission: two scans can be in flight, the front half (map independent) of
+  // scan i+1 overlapping the back half of scan i.  Each owns one set of hand-off buffers.
+  struct ScratchSet {
+    float4* ray_p = nullptr;
+    float4* ray_a = nullptr;
+    uint2* ray_c = nullptr;
+    uint32_t* ray_list = nullptr;
+    uint32_t* cnt = nullptr;
+    uint32_t* off = nullptr;
+    vbx::ScanState* d_state = nullptr;
+    vbx::ScanState* h_state = nullptr;
+    float* d_xyz = nullptr;
+    uint8_t* d_rgba = nullptr;
+    uint64_t* pkeys0 = nullptr;  // sorted bundle keys (read again by the ray walk)
+    cudaEvent_t copy_done = nullptr, front_done = nullptr, back_done = nullptr;
+    bool in_flight = false;
+    int kind = 0;
+    uint64_t launches = 0;
+  } set[2];
+  uint64_t async_seq = 0;
+  int deferred_rc = 0;
+  bool force_wide_keys = false;  // set once an asynchronous scan overflowed the compact bundle keys
+  std::string deferred_msg;
   // host mirror of slot_key (refreshed lazily)
   std::vector<uint64_t> host_slot_key;
   std::unordered_map<uint64_t, int32_t> host_key2slot;
@@ -185,6 +213,9 @@ int fail(vbx_ctx* c, int code, const std::string& msg);
 int cuda_fail(vbx_ctx* c, cudaError_t e, const char* what);
 int refresh_host_mirror(vbx_ctx* c);
 int esdf_destroy(vbx_ctx* c);
+int drain_async(vbx_ctx* c);           // wait for every asynchronously submitted scan, collect its results
+int set_n_blocks(vbx_ctx* c, uint32_t n);
+void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S);  // collect a finished asynchronous scan's results
 }  // namespace vbx
 
 #define VBX_CUDA(c, expr)                                          \

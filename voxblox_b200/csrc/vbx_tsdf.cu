@@ -524,8 +524,9 @@ __global__ void k_set_total(const uint32_t* __restrict__ off, uint32_t n, uint64
 
 // After the last walk that can create blocks: pool slots for the blocks created by this call
 // (updateLayerWithStoredBlocks, cc:137-147); a new block is born with all updated bits set (cc:128).
-__global__ void k_assign(Tables tab, uint32_t n_blocks_before, ScanState* st) {
+__global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_t* __restrict__ nb_out, ScanState* st) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_blocks_before = *nb_in;
   const uint32_t n_new = min(st->n_new, tab.max_blocks);
   if (j < n_new) {
     const uint32_t slot = n_blocks_before + j;
@@ -538,7 +539,11 @@ __global__ void k_assign(Tables tab, uint32_t n_blocks_before, ScanState* st) {
       atomicOr(&st->error, kErrPoolFull);
     }
   }
-  if (j == 0) st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
+  if (j == 0) {
+    const uint32_t after = min(n_blocks_before + st->n_new, tab.max_blocks);
+    st->n_blocks = after;
+    *nb_out = after;
+  }
 }
 
 template <typename KeyT>
@@ -1242,7 +1247,9 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off,
                                                       c->ckeys[0], c->cvals[0], c->d_state);
   mk.mark(5);
-  k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
+  k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->d_nblocks + c->nb_cur, c->d_nblocks + (c->nb_cur ^ 1),
+                                                            c->d_state);
+  c->nb_cur ^= 1;
   mk.mark(4);
   *launches += 2;
   return sort_and_apply(c, P, K, n_touched, mk, launches);
@@ -1301,8 +1308,11 @@ static void fill_params(vbx_ctx* c, int kind, const float q[4], const float t[3]
     P.ovz = ov.z;
     const double r = (double)cfg.max_ray_length_m * (double)c->voxel_size_inv;
     P.key_radius = (r < 2.0e5) ? (int)std::ceil(r) + 3 : (1 << 20);
+    // ... widened to what still fits a 31-bit key (10 bits per axis: +-511 voxels), so that
+    // clearing points up to 511 voxels away never need the full-width fallback
+    if (P.key_radius < 511) P.key_radius = 511;
     P.key_bits = bits_for((uint64_t)(2 * (int64_t)P.key_radius));
-    P.wide_keys = (3 * P.key_bits + 1 > 32) ? 1 : 0;
+    P.wide_keys = (3 * P.key_bits + 1 > 32 || c->force_wide_keys) ? 1 : 0;
   }
 
   P.slot_lo = 0;
@@ -1424,6 +1434,114 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   c->counters[6] = (kind == VBX_MERGED) ? c->h_state->n_valid_points
                                         : (uint64_t)c->h_state->n_rays + c->h_state->n_clear_rays;
   c->counters[7] = launches;
+  return VBX_OK;
+}
+
+// ------------------------------------------------------------- asynchronous submission
+// integratePointCloud without the host round trip: the call enqueues the scan and returns.  The
+// front half (keys, sort, bundle fold, record offsets: nothing that reads or writes the map) goes
+// to stream_f, the back half (ray walk, block creation, record sort, apply) to the main stream
+// behind an event.  Two hand-off sets alternate, so the front half of scan i+1 overlaps the back
+// half of scan i; map updates still happen strictly in submission order (one stream).  Results
+// (counters, errors) of scan i are collected when its hand-off set is reused (scan i+2) or at the
+// next synchronous call / vbx_sync.
+int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* xyz, const uint8_t* rgba,
+                    uint64_t n64, int freespace, int on_device) {
+  if (kind < VBX_SIMPLE || kind > VBX_FAST) return fail(c, VBX_E_INVALID, "Unknown TSDF integrator type");
+  if (n64 > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
+  const vbx_tsdf_config& cfg = c->cfg;
+  const bool overlappable = kind != VBX_FAST && !(kind == VBX_MERGED && cfg.enable_anti_grazing) && !c->use_cub &&
+                            cfg.integration_order_mode == 0 && n64 > 0;
+  if (!overlappable) {
+    // configurations whose front half touches the map or the Fast integrator's sets run in order
+    if (int rc = drain_async(c)) return rc;
+    const float* dx = xyz;
+    const uint8_t* dr = rgba;
+    if (!on_device && n64) {
+      VBX_CUDA(c, cudaMemcpyAsync(c->d_xyz, xyz, n64 * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      VBX_CUDA(c, cudaMemcpyAsync(c->d_rgba, rgba, n64 * 4, cudaMemcpyHostToDevice, c->stream));
+      dx = c->d_xyz;
+      dr = c->d_rgba;
+    }
+    return integrate_device(c, kind, q, t, dx, dr, n64, freespace);
+  }
+  const uint32_t n = (uint32_t)n64;
+  vbx_ctx::ScratchSet& S = c->set[c->async_seq & 1];
+  if (S.in_flight) {  // bounded run-ahead: at most two scans in flight
+    VBX_CUDA(c, cudaEventSynchronize(S.back_done));
+    harvest_async(c, S);
+  }
+  // this submission's hand-off buffers
+  c->ray_p = S.ray_p;
+  c->ray_a = S.ray_a;
+  c->ray_c = S.ray_c;
+  c->ray_list = S.ray_list;
+  c->cnt = S.cnt;
+  c->off = S.off;
+  c->d_state = S.d_state;
+  c->h_state = S.h_state;
+  c->pkeys[0] = S.pkeys0;
+  ScanParams P;
+  fill_params(c, kind, q, t, n, freespace, P);
+  uint64_t launches = 0;
+  Marks mk;
+  mk.c = c;
+  mk.s = c->stream_f;
+  const bool profiling = c->profiling;
+  c->profiling = false;  // stage events would serialise the two streams
+  int rc = VBX_OK;
+  // ---- front half on stream_f
+  c->stream = c->stream_f;
+  const float* dx = xyz;
+  const uint8_t* dr = rgba;
+  if (!on_device) {
+    // the copy engine works ahead of the front half on a stream of its own
+    if (cudaMemcpyAsync(S.d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream_c) != cudaSuccess ||
+        cudaMemcpyAsync(S.d_rgba, rgba, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream_c) != cudaSuccess ||
+        cudaEventRecord(S.copy_done, c->stream_c) != cudaSuccess ||
+        cudaStreamWaitEvent(c->stream_f, S.copy_done, 0) != cudaSuccess) {
+      rc = fail(c, VBX_E_CUDA, "asynchronous host-to-device copy failed");
+    }
+    dx = S.d_xyz;
+    dr = S.d_rgba;
+  }
+  const uint32_t* keys32 = nullptr;
+  const uint64_t* keys64 = nullptr;
+  if (rc == VBX_OK && cudaMemsetAsync(S.d_state, 0, sizeof(ScanState), c->stream_f) != cudaSuccess) {
+    rc = fail(c, VBX_E_CUDA, "cudaMemsetAsync");
+  }
+  if (rc == VBX_OK) {
+    rc = P.wide_keys ? front_half<uint64_t>(c, P, dx, dr, nullptr, mk, &launches, &keys64)
+                     : front_half<uint32_t>(c, P, dx, dr, nullptr, mk, &launches, &keys32);
+  }
+  if (rc == VBX_OK && cudaEventRecord(S.front_done, c->stream_f) != cudaSuccess) rc = fail(c, VBX_E_CUDA, "cudaEventRecord");
+  // ---- back half on the main stream
+  c->stream = c->stream_main;
+  mk.s = c->stream_main;
+  if (rc == VBX_OK && cudaStreamWaitEvent(c->stream_main, S.front_done, 0) != cudaSuccess) {
+    rc = fail(c, VBX_E_CUDA, "cudaStreamWaitEvent");
+  }
+  if (rc == VBX_OK) {
+    rc = P.wide_keys ? back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches)
+                     : back_half<uint32_t>(c, P, keys32, 0, 0, mk, &launches);
+  }
+  if (rc == VBX_OK && (cudaMemcpyAsync(S.h_state, S.d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->stream_main) != cudaSuccess ||
+                       cudaEventRecord(S.back_done, c->stream_main) != cudaSuccess)) {
+    rc = fail(c, VBX_E_CUDA, "enqueueing the result read-back failed");
+  }
+  c->profiling = profiling;
+  if (rc != VBX_OK) return rc;
+  S.in_flight = true;
+  S.kind = kind;
+  S.launches = launches;
+  c->launches += launches;
+  c->async_seq += 1;
+  if (c->deferred_rc) {
+    rc = c->deferred_rc;
+    c->err = c->deferred_msg;
+    c->deferred_rc = 0;
+    return rc;
+  }
   return VBX_OK;
 }
 
@@ -1570,7 +1688,9 @@ int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_
     uint32_t* hp_of = c->cvals[1];
     k_localize_blocks<<<grid_for(K, 256), 256, 0, s>>>(seg, c->tab, c->L, P.epoch, hp_of, c->d_state);
     k_set_total<<<1, 1, 0, s>>>(nullptr, 0, c->max_updates, c->d_state, K);
-    k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
+    k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->d_nblocks + c->nb_cur, c->d_nblocks + (c->nb_cur ^ 1),
+                                                            c->d_state);
+  c->nb_cur ^= 1;
     VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
     VBX_CUDA(c, cudaStreamSynchronize(s));
     if (int rc = check_state_errors(c, c->h_state->error)) return rc;
