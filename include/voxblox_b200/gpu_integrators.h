@@ -105,12 +105,11 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
 
   GpuTsdfIntegrator(TsdfIntegratorType type, const Config& config, Layer<TsdfVoxel>* layer,
                     const vbx_engine_options* options = nullptr)
-      : TsdfIntegratorBase(config, layer), type_(type), ctx_(nullptr) {
-    CHECK_EQ(layer->getNumberOfAllocatedBlocks(), 0u)
-        << "GpuTsdfIntegrator: start from an empty layer (existing blocks: vbx_upload_blocks)";
+      : TsdfIntegratorBase(config, layer), type_(type), ctx_(nullptr), pipelined_(false) {
     const vbx_tsdf_config pod = gpu_detail::toPod(config_);
     const int rc = vbx_create(&pod, voxel_size_, static_cast<int>(voxels_per_side_), options, &ctx_);
     if (rc != VBX_OK) LOG(FATAL) << "vbx_create failed (" << rc << "): " << vbx_last_error(ctx_);
+    uploadLayer();  // a layer loaded from a file / built by another integrator becomes the device map
   }
   ~GpuTsdfIntegrator() { vbx_destroy(ctx_); }
 
@@ -121,12 +120,68 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
                         T_G_C.getRotation().z()};
     const Point p = T_G_C.getPosition();
     const float t[3] = {p.x(), p.y(), p.z()};
-    gpu_detail::check(ctx_,
-                      vbx_tsdf_integrate(ctx_, static_cast<int>(type_), q, t,
-                                         points_C.empty() ? nullptr : reinterpret_cast<const float*>(points_C.data()),
-                                         colors.empty() ? nullptr : reinterpret_cast<const uint8_t*>(colors.data()),
-                                         points_C.size(), freespace_points ? 1 : 0),
-                      "vbx_tsdf_integrate");
+    const float* xyz = points_C.empty() ? nullptr : reinterpret_cast<const float*>(points_C.data());
+    const uint8_t* rgba = colors.empty() ? nullptr : reinterpret_cast<const uint8_t*>(colors.data());
+    if (pipelined_ && !points_C.empty()) {
+      // Pageable host memory: the runtime stages the copy before the call returns, so the
+      // caller may reuse points_C / colors immediately, as after the reference's call.
+      gpu_detail::check(ctx_,
+                        vbx_tsdf_integrate_async(ctx_, static_cast<int>(type_), q, t, xyz, rgba, points_C.size(),
+                                                 freespace_points ? 1 : 0, /*inputs_on_device=*/0),
+                        "vbx_tsdf_integrate_async");
+    } else {
+      gpu_detail::check(ctx_,
+                        vbx_tsdf_integrate(ctx_, static_cast<int>(type_), q, t, xyz, rgba, points_C.size(),
+                                           freespace_points ? 1 : 0),
+                        "vbx_tsdf_integrate");
+    }
+  }
+
+  /// Pipelined mode: integratePointCloud() enqueues the scan and returns; the transform / bundle
+  /// half of the next scan overlaps the ray-cast / update half of the current one on the device.
+  /// Every read of the map (syncLayer, the ESDF update, block management) waits for the queued
+  /// scans first, and the result is bit-identical to the non-pipelined calls.
+  void setPipelined(bool on) {
+    if (!on) gpu_detail::check(ctx_, vbx_sync(ctx_), "vbx_sync");
+    pipelined_ = on;
+  }
+
+  /// Host layer -> device map (Layer::insertBlock for every allocated block).
+  void uploadLayer() {
+    BlockIndexList blocks;
+    layer_->getAllAllocatedBlocks(&blocks);
+    if (blocks.empty()) return;
+    const size_t vpb = voxels_per_side_ * voxels_per_side_ * voxels_per_side_;
+    std::vector<int32_t> idx(3 * blocks.size());
+    std::vector<TsdfVoxel> vox(vpb * blocks.size());
+    std::vector<uint8_t> upd(blocks.size());
+    for (size_t b = 0; b < blocks.size(); ++b) {
+      const Block<TsdfVoxel>& block = layer_->getBlockByIndex(blocks[b]);
+      idx[3 * b] = blocks[b].x();
+      idx[3 * b + 1] = blocks[b].y();
+      idx[3 * b + 2] = blocks[b].z();
+      std::memcpy(vox.data() + b * vpb, &block.getVoxelByLinearIndex(0), vpb * sizeof(TsdfVoxel));
+      uint8_t bits = 0;
+      for (int bit = 0; bit < static_cast<int>(Update::kCount); ++bit) {
+        if (block.updated()[bit]) bits |= static_cast<uint8_t>(1u << bit);
+      }
+      upd[b] = bits;
+    }
+    gpu_detail::check(ctx_, vbx_upload_blocks(ctx_, VBX_LAYER_TSDF, idx.data(), blocks.size(), vox.data(), upd.data()),
+                      "vbx_upload_blocks");
+  }
+
+  /// removeDistantBlocks (core/layer_inl.h / tsdf_server.cc:314-316) on both copies of the map.
+  void removeBlocks(const BlockIndexList& blocks) {
+    if (blocks.empty()) return;
+    std::vector<int32_t> idx(3 * blocks.size());
+    for (size_t b = 0; b < blocks.size(); ++b) {
+      idx[3 * b] = blocks[b].x();
+      idx[3 * b + 1] = blocks[b].y();
+      idx[3 * b + 2] = blocks[b].z();
+      layer_->removeBlock(blocks[b]);
+    }
+    gpu_detail::check(ctx_, vbx_remove_blocks(ctx_, VBX_LAYER_TSDF, idx.data(), blocks.size()), "vbx_remove_blocks");
   }
 
   /// Bring the host Layer<TsdfVoxel> up to date: downloads every block whose updated() bits
@@ -139,6 +194,7 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
  private:
   TsdfIntegratorType type_;
   vbx_ctx* ctx_;
+  bool pipelined_;
 };
 
 /// EsdfIntegrator's update entry points (esdf_integrator.h:101-106) on the device map owned by a

@@ -5,6 +5,7 @@
 // and statistically (its CPU order is unordered_map iteration order).  Exit code 0 = pass.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <vector>
 
@@ -97,6 +98,54 @@ int main() {
     if (!same_blocks) ++failures;
     if (type == 1 && exact != n) ++failures;                 // same update order: bit-identical
     if (type == 2 && !(rmse < 0.25 * voxel_size)) ++failures;  // CPU order = hash-map iteration order
+  }
+  // Pipelined adapter, and an adapter started from a non-empty layer: both must reproduce the
+  // plain adapter bit for bit.
+  {
+    auto digest = [](Layer<TsdfVoxel>& layer) {
+      uint64_t h = 1469598103934665603ull;
+      for (const BlockIndex& bi : sortedBlocks(layer)) {
+        const Block<TsdfVoxel>& blk = layer.getBlockByIndex(bi);
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&blk.getVoxelByLinearIndex(0));
+        for (size_t i = 0; i < blk.num_voxels() * sizeof(TsdfVoxel); ++i) h = (h ^ p[i]) * 1099511628211ull;
+        h = (h ^ static_cast<uint64_t>(bi.x() * 73856093 ^ bi.y() * 19349669 ^ bi.z() * 83492791)) * 1099511628211ull;
+      }
+      return h;
+    };
+    Layer<TsdfVoxel> plain_layer(voxel_size, 16), piped_layer(voxel_size, 16), resumed_layer(voxel_size, 16);
+    GpuTsdfIntegrator plain(TsdfIntegratorType::kMerged, config, &plain_layer);
+    GpuTsdfIntegrator piped(TsdfIntegratorType::kMerged, config, &piped_layer);
+    piped.setPipelined(true);
+    Transformation T;
+    Pointcloud pts;
+    Colors cols;
+    for (int k = 0; k < 6; ++k) {
+      makeScan(k, &T, &pts, &cols);
+      plain.integratePointCloud(T, pts, cols);
+      piped.integratePointCloud(T, pts, cols);
+      pts.assign(pts.size(), Point(1e9f, 1e9f, 1e9f));  // the caller may reuse its buffers at once
+      if (k == 2) {
+        // hand the map over to a fresh adapter through the host layer
+        plain.syncLayer(0);
+        for (const BlockIndex& bi : sortedBlocks(plain_layer)) {
+          Block<TsdfVoxel>::Ptr dst = resumed_layer.allocateBlockPtrByIndex(bi);
+          const Block<TsdfVoxel>& src = plain_layer.getBlockByIndex(bi);
+          std::memcpy(&dst->getVoxelByLinearIndex(0), &src.getVoxelByLinearIndex(0), src.num_voxels() * sizeof(TsdfVoxel));
+        }
+      }
+    }
+    GpuTsdfIntegrator resumed(TsdfIntegratorType::kMerged, config, &resumed_layer);
+    for (int k = 3; k < 6; ++k) {
+      makeScan(k, &T, &pts, &cols);
+      resumed.integratePointCloud(T, pts, cols);
+    }
+    plain.syncLayer(0);
+    piped.syncLayer(0);
+    resumed.syncLayer(0);
+    const uint64_t d0 = digest(plain_layer), d1 = digest(piped_layer), d2 = digest(resumed_layer);
+    std::printf("pipelined adapter identical %d, resumed-from-host-layer identical %d (%zu blocks)\n", d0 == d1 ? 1 : 0,
+                d0 == d2 ? 1 : 0, plain_layer.getNumberOfAllocatedBlocks());
+    if (d0 != d1 || d0 != d2) ++failures;
   }
   // ESDF through the adapter: incremental update after a scan, then batch
   {
