@@ -188,6 +188,14 @@ VBX_API int vbx_esdf_create(vbx_ctx* ctx, const vbx_esdf_config* cfg);
 /* batch = 0: updateFromTsdfLayer(clear_updated_flag)   (esdf_integrator.cc:104-122)
  * batch = 1: updateFromTsdfLayerBatch()                (esdf_integrator.cc:94-102) */
 VBX_API int vbx_esdf_update(vbx_ctx* ctx, int batch, int clear_updated_flag);
+/* updateFromTsdfBlocks(tsdf_blocks, incremental = false) (esdf_integrator.h:111-112, cc:124-302):
+ * propagate / raise / lower for exactly the listed blocks; indices without a TSDF block are
+ * skipped (cc:139-141), an index listed twice is processed once. */
+VBX_API int vbx_esdf_update_blocks(vbx_ctx* ctx, const int32_t* idx3, uint64_t m, int incremental);
+/* setEsdfMaxDistance / setFullEuclidean / getters (esdf_integrator.h:139-149) */
+VBX_API int vbx_esdf_set_max_distance(vbx_ctx* ctx, float max_distance_m);
+VBX_API int vbx_esdf_set_full_euclidean(vbx_ctx* ctx, int full_euclidean);
+VBX_API int vbx_esdf_get_config(const vbx_ctx* ctx, vbx_esdf_config* out);
 /* Counters of the last ESDF update: [0] blocks propagated [1] lower [2] raise [3] new
  * [4] voxels raised [5] wavefront relaxations R [6] wavefront sweeps [7] kernels */
 VBX_API int vbx_esdf_get_counters(const vbx_ctx* ctx, uint64_t out[16]);

@@ -210,6 +210,34 @@ class GpuEsdfIntegrator {
     gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 0, clear_updated_flag ? 1 : 0), "vbx_esdf_update");
   }
   void updateFromTsdfLayerBatch() { gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 1, 0), "vbx_esdf_update"); }
+  void updateFromTsdfBlocks(const BlockIndexList& tsdf_blocks, bool incremental = false) {
+    std::vector<int32_t> idx(3 * tsdf_blocks.size());
+    for (size_t b = 0; b < tsdf_blocks.size(); ++b) {
+      idx[3 * b] = tsdf_blocks[b].x();
+      idx[3 * b + 1] = tsdf_blocks[b].y();
+      idx[3 * b + 2] = tsdf_blocks[b].z();
+    }
+    gpu_detail::check(ctx_, vbx_esdf_update_blocks(ctx_, idx.data(), tsdf_blocks.size(), incremental ? 1 : 0),
+                      "vbx_esdf_update_blocks");
+  }
+  /// esdf_integrator.h:131-136; the device keeps no queue between calls
+  void clear() {}
+  float getEsdfMaxDistance() const {
+    vbx_esdf_config c;
+    gpu_detail::check(ctx_, vbx_esdf_get_config(ctx_, &c), "vbx_esdf_get_config");
+    return c.max_distance_m;
+  }
+  void setEsdfMaxDistance(float max_distance) {
+    gpu_detail::check(ctx_, vbx_esdf_set_max_distance(ctx_, max_distance), "vbx_esdf_set_max_distance");
+  }
+  bool getFullEuclidean() const {
+    vbx_esdf_config c;
+    gpu_detail::check(ctx_, vbx_esdf_get_config(ctx_, &c), "vbx_esdf_get_config");
+    return c.full_euclidean_distance != 0;
+  }
+  void setFullEuclidean(bool full_euclidean) {
+    gpu_detail::check(ctx_, vbx_esdf_set_full_euclidean(ctx_, full_euclidean ? 1 : 0), "vbx_esdf_set_full_euclidean");
+  }
   size_t syncLayer(int updated_mask = 0) {
     return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_ESDF, updated_mask, esdf_layer_);
   }

@@ -101,6 +101,12 @@ class OracleLib:
         lib.vbo_esdf_create.argtypes = [C.c_void_p, C.POINTER(EsdfConfig)]
         lib.vbo_esdf_update.restype = C.c_int
         lib.vbo_esdf_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.vbo_esdf_update_blocks.restype = C.c_int
+        lib.vbo_esdf_update_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        lib.vbo_esdf_set_max_distance.restype = C.c_int
+        lib.vbo_esdf_set_max_distance.argtypes = [C.c_void_p, C.c_float]
+        lib.vbo_esdf_set_full_euclidean.restype = C.c_int
+        lib.vbo_esdf_set_full_euclidean.argtypes = [C.c_void_p, C.c_int]
         lib.vbo_esdf_add_robot_position.restype = C.c_int
         lib.vbo_esdf_add_robot_position.argtypes = [C.c_void_p, C.c_void_p]
         self.lib = lib
@@ -175,6 +181,21 @@ class OracleMap:
         rc = self.lib.vbo_esdf_update(self.h, int(batch), int(clear_updated_flag))
         if rc != 0:
             raise RuntimeError(f"vbo_esdf_update rc={rc}")
+
+    def esdf_update_blocks(self, indices, incremental: bool = False):
+        """EsdfIntegrator::updateFromTsdfBlocks (esdf_integrator.cc:124-302)"""
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        rc = self.lib.vbo_esdf_update_blocks(self.h, idx.ctypes.data, idx.shape[0], int(incremental))
+        if rc != 0:
+            raise RuntimeError(f"vbo_esdf_update_blocks rc={rc}")
+
+    def esdf_set_max_distance(self, d: float):
+        if self.lib.vbo_esdf_set_max_distance(self.h, float(d)) != 0:
+            raise RuntimeError("vbo_esdf_set_max_distance")
+
+    def esdf_set_full_euclidean(self, on: bool):
+        if self.lib.vbo_esdf_set_full_euclidean(self.h, int(on)) != 0:
+            raise RuntimeError("vbo_esdf_set_full_euclidean")
 
     def esdf_add_robot_position(self, p):
         p = np.ascontiguousarray(p, dtype=np.float32)

@@ -177,6 +177,29 @@ int vbo_esdf_update(void* hv, int batch, int clear_updated_flag) {
   return 0;
 }
 
+int vbo_esdf_update_blocks(void* hv, const int32_t* idx3, uint64_t m, int incremental) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h->esdf_integrator) return 2;
+  voxblox::BlockIndexList blocks;
+  for (uint64_t i = 0; i < m; ++i) blocks.push_back(voxblox::BlockIndex(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
+  h->esdf_integrator->updateFromTsdfBlocks(blocks, incremental != 0);
+  return 0;
+}
+
+int vbo_esdf_set_max_distance(void* hv, float max_distance) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h->esdf_integrator) return 2;
+  h->esdf_integrator->setEsdfMaxDistance(max_distance);
+  return 0;
+}
+
+int vbo_esdf_set_full_euclidean(void* hv, int full_euclidean) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h->esdf_integrator) return 2;
+  h->esdf_integrator->setFullEuclidean(full_euclidean != 0);
+  return 0;
+}
+
 int vbo_esdf_add_robot_position(void* hv, const float p[3]) {
   Handle* h = static_cast<Handle*>(hv);
   if (!h->esdf_integrator) return 2;

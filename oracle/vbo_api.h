@@ -98,6 +98,11 @@ int vbo_esdf_create(void* h, const vbo_esdf_config* cfg);
 /* batch=0: updateFromTsdfLayer(clear_updated_flag) (esdf_integrator.cc:104-122)
  * batch=1: updateFromTsdfLayerBatch()              (esdf_integrator.cc:94-102) */
 int vbo_esdf_update(void* h, int batch, int clear_updated_flag);
+/* EsdfIntegrator::updateFromTsdfBlocks(tsdf_blocks, incremental) (esdf_integrator.cc:124-302) */
+int vbo_esdf_update_blocks(void* h, const int32_t* idx3, uint64_t m, int incremental);
+/* setEsdfMaxDistance / setFullEuclidean (esdf_integrator.h:139-149) */
+int vbo_esdf_set_max_distance(void* h, float max_distance);
+int vbo_esdf_set_full_euclidean(void* h, int full_euclidean);
 /* EsdfIntegrator::addNewRobotPosition (esdf_integrator.cc:25-92) */
 int vbo_esdf_add_robot_position(void* h, const float p[3]);
 

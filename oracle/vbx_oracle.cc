@@ -967,6 +967,28 @@ int vbo_esdf_update(void* hv, int batch, int clear_updated_flag) {
   m->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return 0;
 }
+int vbo_esdf_update_blocks(void* hv, const int32_t* idx3, uint64_t n, int incremental) {
+  Map* m = static_cast<Map*>(hv);
+  if (!m->has_esdf) return 2;
+  std::vector<I3> blocks;
+  for (uint64_t i = 0; i < n; ++i) blocks.push_back(I3{idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]});
+  m->esdfFromBlocks(blocks, incremental != 0);  // esdf_integrator.cc:124-302
+  return 0;
+}
+// esdf_integrator.h:139-149
+int vbo_esdf_set_max_distance(void* hv, float max_distance) {
+  Map* m = static_cast<Map*>(hv);
+  if (!m->has_esdf) return 2;
+  m->ecfg.max_distance_m = max_distance;
+  if (m->ecfg.default_distance_m < max_distance) m->ecfg.default_distance_m = max_distance;
+  return 0;
+}
+int vbo_esdf_set_full_euclidean(void* hv, int full_euclidean) {
+  Map* m = static_cast<Map*>(hv);
+  if (!m->has_esdf) return 2;
+  m->ecfg.full_euclidean_distance = full_euclidean;
+  return 0;
+}
 int vbo_esdf_add_robot_position(void* hv, const float p[3]) {
   Map* m = static_cast<Map*>(hv);
   if (!m->has_esdf) return 2;

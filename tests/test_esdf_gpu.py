@@ -87,3 +87,38 @@ def test_esdf_incremental_tracks_oracle():
     # the reference's own incremental-vs-batch criterion is statistical (test_sdf_integrators.cc:261-270)
     assert rep["rmse"] < 4.0 * 0.1, rep
     assert frac_bad < 0.06, rep  # same order-dependent sign-conflict voxels as in the batch test
+
+
+def test_update_from_tsdf_blocks_and_setters():
+    """updateFromTsdfBlocks(list, incremental=False) on a subset of blocks (missing and repeated
+    indices included), then setEsdfMaxDistance / setFullEuclidean followed by a batch update
+    (esdf_integrator.h:111-112,139-149)."""
+    tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
+    for s in _wall_scans():
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    blocks = tsdf.getAllAllocatedBlocks()
+    subset = np.concatenate([blocks[::2], blocks[:1], np.array([[900, 900, 900]], np.int32)])
+    eint.updateFromTsdfBlocks(subset)
+    omap.esdf_update_blocks(np.concatenate([blocks[::2], np.array([[900, 900, 900]], np.int32)]))
+    rep = compare_esdf(esdf, omap, 4.0)
+    print(rep)
+    assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
+    assert rep["n_bit_exact"] >= 0.995 * rep["voxels_observed"], rep
+    # setters behave like the reference's
+    assert eint.getEsdfMaxDistance() == pytest.approx(4.0)
+    eint.setEsdfMaxDistance(5.0)
+    omap.esdf_set_max_distance(5.0)
+    assert eint.getEsdfMaxDistance() == pytest.approx(5.0)
+    assert eint._config().default_distance_m == pytest.approx(5.0)   # follows upwards, h:142-144
+    eint.setFullEuclidean(True)
+    omap.esdf_set_full_euclidean(True)
+    assert eint.getFullEuclidean() is True
+    eint.setFullEuclidean(False)
+    omap.esdf_set_full_euclidean(False)
+    eint.updateFromTsdfLayerBatch()
+    omap.esdf_update(batch=True)
+    rep = compare_esdf(esdf, omap, 5.0)
+    print(rep)
+    assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
+    assert rep["n_bit_exact"] >= 0.995 * rep["voxels_observed"], rep

@@ -65,6 +65,32 @@ def test_port_matches_reference_voxelwise_with_esdf():
                 assert va.tobytes() == vb.tobytes(), (kind, layer, tuple(i))
 
 
+@pytest.mark.skipif(not po.available("reference"), reason="oracle/_ref not built")
+def test_port_matches_reference_esdf_blocks_and_setters():
+    """updateFromTsdfBlocks on a block subset, setEsdfMaxDistance / setFullEuclidean, then batch."""
+    scans = scenes.c3_room_sequence(n_scans=3, width=96, height=72)
+    cfg = po.TsdfConfig(default_truncation_distance=0.4, integrator_threads=1)
+    ecfg = po.EsdfConfig(max_distance_m=2.0, default_distance_m=2.0, min_distance_m=0.2, min_diff_m=1e-3)
+    maps = [po.OracleMap(po.OracleLib(w), cfg, 0.1, 16) for w in ("reference", "port")]
+    for m in maps:
+        m.esdf_create(ecfg)
+        for s in scans:
+            m.integrate(2, s)
+        blocks = m.block_indices(0)
+        m.esdf_update_blocks(np.concatenate([blocks[::2], np.array([[77, 77, 77]], np.int32)]), incremental=False)
+    a, b = maps
+    ia, ib = a.block_indices(1), b.block_indices(1)
+    assert ia.shape == ib.shape and (ia == ib).all()
+    assert all(a.block(i, 1)[0].tobytes() == b.block(i, 1)[0].tobytes() for i in ia)
+    for m in maps:
+        m.esdf_set_max_distance(3.0)
+        m.esdf_set_full_euclidean(True)
+        m.esdf_update(True, True)
+    ia, ib = a.block_indices(1), b.block_indices(1)
+    assert ia.shape == ib.shape and (ia == ib).all()
+    assert all(a.block(i, 1)[0].tobytes() == b.block(i, 1)[0].tobytes() for i in ia)
+
+
 def _integrate_single_point(point, voxel_size, vps):
     """One point, no carving: the ray covers only [p - T, p + T] (integrator_utils.cc:93-98)."""
     cfg = po.TsdfConfig(default_truncation_distance=voxel_size * 0.4, voxel_carving_enabled=0,

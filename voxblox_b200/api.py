@@ -113,7 +113,8 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync",
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
-           "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async"]
+           "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config"]
 
 _lib = None
 
@@ -166,6 +167,14 @@ def load_library():
     lib.vbx_clear_updated.argtypes = [vp, i32, i32]
     lib.vbx_esdf_create.restype = i32
     lib.vbx_esdf_create.argtypes = [vp, C.POINTER(EsdfIntegratorConfig)]
+    lib.vbx_esdf_update_blocks.restype = i32
+    lib.vbx_esdf_update_blocks.argtypes = [vp, vp, u64, i32]
+    lib.vbx_esdf_set_max_distance.restype = i32
+    lib.vbx_esdf_set_max_distance.argtypes = [vp, C.c_float]
+    lib.vbx_esdf_set_full_euclidean.restype = i32
+    lib.vbx_esdf_set_full_euclidean.argtypes = [vp, i32]
+    lib.vbx_esdf_get_config.restype = i32
+    lib.vbx_esdf_get_config.argtypes = [vp, C.POINTER(EsdfIntegratorConfig)]
     lib.vbx_esdf_update.restype = i32
     lib.vbx_esdf_update.argtypes = [vp, i32, i32]
     lib.vbx_sync.restype = i32
@@ -533,6 +542,34 @@ class EsdfIntegrator:
     def updateFromTsdfLayer(self, clear_updated_flag: bool) -> None:  # esdf_integrator.cc:104-122
         self._ctx.check(self._ctx.lib.vbx_esdf_update(self._ctx.handle, 0, int(bool(clear_updated_flag))),
                         "updateFromTsdfLayer")
+
+    def updateFromTsdfBlocks(self, tsdf_blocks, incremental: bool = False) -> None:  # esdf_integrator.cc:124-302
+        idx = np.ascontiguousarray(tsdf_blocks, dtype=np.int32).reshape(-1, 3)
+        self._ctx.check(self._ctx.lib.vbx_esdf_update_blocks(self._ctx.handle, idx.ctypes.data, idx.shape[0],
+                                                             int(bool(incremental))), "updateFromTsdfBlocks")
+
+    def _config(self) -> EsdfIntegratorConfig:
+        out = EsdfIntegratorConfig()
+        self._ctx.check(self._ctx.lib.vbx_esdf_get_config(self._ctx.handle, C.byref(out)), "vbx_esdf_get_config")
+        return out
+
+    def getEsdfMaxDistance(self) -> float:  # esdf_integrator.h:139
+        return float(self._config().max_distance_m)
+
+    def setEsdfMaxDistance(self, max_distance: float) -> None:  # esdf_integrator.h:140-145
+        self._ctx.check(self._ctx.lib.vbx_esdf_set_max_distance(self._ctx.handle, float(max_distance)),
+                        "setEsdfMaxDistance")
+
+    def getFullEuclidean(self) -> bool:  # esdf_integrator.h:146
+        return bool(self._config().full_euclidean_distance)
+
+    def setFullEuclidean(self, full_euclidean: bool) -> None:  # esdf_integrator.h:147-149
+        self._ctx.check(self._ctx.lib.vbx_esdf_set_full_euclidean(self._ctx.handle, int(bool(full_euclidean))),
+                        "setFullEuclidean")
+
+    def clear(self) -> None:
+        """esdf_integrator.h:131-136: drops queued work of addNewRobotPosition; the device keeps no
+        queue between calls, so there is nothing to drop."""
 
     def updateFromTsdfLayerBatch(self) -> None:  # esdf_integrator.cc:94-102
         self._ctx.check(self._ctx.lib.vbx_esdf_update(self._ctx.handle, 1, 0), "updateFromTsdfLayerBatch")

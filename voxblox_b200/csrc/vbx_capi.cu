@@ -30,6 +30,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
                     uint64_t n, int freespace, int on_device);
 int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
+int esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incremental);
 
 int fail(vbx_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
@@ -667,6 +668,37 @@ int vbx_esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
   VBX_DRAIN(c);
   if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_update before vbx_esdf_create");
   return esdf_update(c, batch, clear_updated_flag);
+}
+
+int vbx_esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incremental) {
+  if (!c || (m && !idx3)) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_update_blocks before vbx_esdf_create");
+  return esdf_update_blocks(c, idx3, m, incremental);
+}
+
+int vbx_esdf_set_max_distance(vbx_ctx* c, float max_distance_m) {
+  if (!c) return VBX_E_INVALID;
+  if (!c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF integrator");
+  // setEsdfMaxDistance, esdf_integrator.h:140-145: the default distance follows upwards
+  c->ecfg.max_distance_m = max_distance_m;
+  if (c->ecfg.default_distance_m < max_distance_m) c->ecfg.default_distance_m = max_distance_m;
+  return VBX_OK;
+}
+
+int vbx_esdf_set_full_euclidean(vbx_ctx* c, int full_euclidean) {
+  if (!c) return VBX_E_INVALID;
+  if (!c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF integrator");
+  c->ecfg.full_euclidean_distance = full_euclidean ? 1 : 0;  // esdf_integrator.h:147-149
+  return VBX_OK;
+}
+
+int vbx_esdf_get_config(const vbx_ctx* c, vbx_esdf_config* out) {
+  if (!c || !out) return VBX_E_INVALID;
+  if (!c->has_esdf) return VBX_E_STATE;
+  *out = c->ecfg;
+  return VBX_OK;
 }
 
 }  // extern "C"

@@ -427,6 +427,15 @@ __global__ void k_esdf_block_list(Tables tab, uint32_t n_slots, int batch, uint3
   }
 }
 
+// updateFromTsdfBlocks with a caller-supplied block list: the listed slots get their ESDF block
+__global__ void k_esdf_mark_listed(Tables tab, const uint32_t* __restrict__ block_list, uint32_t nb) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint32_t s = block_list[i];
+  tab.slot_has_esdf[s] = 1;
+  tab.slot_esdf_updated[s] = 1;
+}
+
 __global__ void k_esdf_clear_tsdf_flag(Tables tab, const uint32_t* __restrict__ block_list, const ScanState* st) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st->esdf_counts[0]) return;
@@ -478,7 +487,31 @@ int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
   return VBX_OK;
 }
 
+static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_flag, const uint32_t* listed_slots,
+                    uint32_t n_listed);
+
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
+  return esdf_run(c, batch, batch ? 0 : 1, clear_updated_flag, nullptr, 0);
+}
+
+// EsdfIntegrator::updateFromTsdfBlocks(tsdf_blocks, incremental), esdf_integrator.cc:124-302: blocks
+// without a TSDF block are skipped (cc:139-141); a block listed twice is processed once.
+int esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incremental) {
+  if (int rc = refresh_host_mirror(c)) return rc;
+  std::vector<uint32_t> slots;
+  slots.reserve(m);
+  std::vector<uint8_t> seen(c->n_blocks, 0);
+  for (uint64_t i = 0; i < m; ++i) {
+    auto it = c->host_key2slot.find(pack3(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
+    if (it == c->host_key2slot.end() || seen[it->second]) continue;
+    seen[it->second] = 1;
+    slots.push_back((uint32_t)it->second);
+  }
+  return esdf_run(c, 0, incremental ? 1 : 0, 0, slots.data(), (uint32_t)slots.size());
+}
+
+static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_flag, const uint32_t* listed_slots,
+                    uint32_t n_listed) {
   cudaStream_t s = c->stream;
   std::memset(c->esdf_counters, 0, sizeof(c->esdf_counters));
   const vbx_esdf_config& cfg = c->ecfg;
@@ -494,7 +527,7 @@ int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
   E.full_euclidean = cfg.full_euclidean_distance;
   E.multi_queue = cfg.multi_queue;
   E.add_occupied_crust = cfg.add_occupied_crust;
-  E.incremental = batch ? 0 : 1;
+  E.incremental = incremental;
   E.u1 = 1.0f;
   E.u2 = (float)std::sqrt(2.0);  // const float sqrt_2 = std::sqrt(2), neighbor_tools.cc:9
   E.u3 = (float)std::sqrt(3.0);
@@ -517,17 +550,27 @@ int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
     VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->n_blocks, s));
     VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->n_blocks, s));
   }
-  k_esdf_block_list<<<grid_for(c->n_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, batch, c->esdf_block_list, c->d_state);
-  // the propagate grid covers every slot in use; threads beyond the listed blocks exit
-  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-  VBX_CUDA(c, cudaStreamSynchronize(s));
-  const uint32_t nb = c->h_state->esdf_counts[0];
+  uint32_t nb = 0;
+  if (listed_slots) {
+    nb = n_listed;
+    if (nb > 0) {
+      VBX_CUDA(c, cudaMemcpyAsync(c->esdf_block_list, listed_slots, (size_t)nb * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      VBX_CUDA(c, cudaMemcpyAsync(&c->d_state->esdf_counts[0], &nb, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      k_esdf_mark_listed<<<grid_for(nb, 256), 256, 0, s>>>(c->tab, c->esdf_block_list, nb);
+      VBX_CUDA(c, cudaStreamSynchronize(s));  // the two host sources above are stack / vector memory
+    }
+  } else {
+    k_esdf_block_list<<<grid_for(c->n_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, batch, c->esdf_block_list, c->d_state);
+    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    nb = c->h_state->esdf_counts[0];
+  }
   launches += 1;
   if (nb > 0) {
     k_esdf_propagate<<<grid_for((uint64_t)nb * c->vox_per_block, 256), 256, 0, s>>>(
         E, c->tab, c->esdf_block_list, nb, c->frontier[0], c->raise_q[0], c->esdf_seed_list, c->d_state);
     launches += 1;
-    if (!batch) {
+    if (incremental) {
       const unsigned int g = 148 * 8;
       k_esdf_seed<<<g, 256, 0, s>>>(E, c->tab, c->esdf_seed_list, c->frontier[0], c->esdf_seed_val, c->d_state);
       k_esdf_seed_commit<<<g, 256, 0, s>>>(E, c->tab, c->esdf_seed_list, c->esdf_seed_val, c->d_state);
