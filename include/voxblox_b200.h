@@ -173,6 +173,15 @@ VBX_API int vbx_list_blocks(vbx_ctx* ctx, int layer, int updated_mask, int32_t* 
  * voxels: m * vps^3 * sizeof(voxel) bytes; updated_bits: m bytes (may be NULL). */
 VBX_API int vbx_download_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m, void* voxels,
                         uint8_t* updated_bits);
+/* The incremental mirror as one call (what a host consumer does after a scan:
+ * getAllUpdatedBlocks(bit), core/layer.h:194-203 -> read the blocks -> updated().reset(bit),
+ * e.g. mesh_integrator.h:168-183): every block with (updated & updated_mask) != 0 (0 = every
+ * block), ascending (x,y,z); payloads are gathered on the device and leave it in ONE copy --
+ * directly into `voxels` when that is page-locked (vbx_host_alloc), else through a page-locked
+ * staging buffer; clear_mask bits are reset on the device afterwards.
+ * *n = number of matching blocks; if *n > cap nothing is copied or cleared (grow and retry). */
+VBX_API int vbx_mirror_updated(vbx_ctx* ctx, int layer, int updated_mask, int clear_mask, int32_t* idx3,
+                       void* voxels, uint8_t* updated_bits, uint64_t cap, uint64_t* n);
 /* Host -> device: Layer::insertBlock / allocateBlockPtrByIndex + voxel copy
  * (core/layer.h:103-111,152-161); creates the block if needed. */
 VBX_API int vbx_upload_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m,

@@ -11,6 +11,7 @@
 #ifndef VOXBLOX_B200_GPU_INTEGRATORS_H_
 #define VOXBLOX_B200_GPU_INTEGRATORS_H_
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -78,15 +79,25 @@ inline void check(vbx_ctx* ctx, int rc, const char* what) {
 // device -> host: refresh (or create) the host blocks listed by the device
 template <typename VoxelType>
 inline size_t downloadBlocks(vbx_ctx* ctx, int layer_id, int updated_mask, Layer<VoxelType>* layer) {
+  // one call: dirty-block list + payloads (gathered on the device, one copy out)
   uint64_t n = 0;
-  check(ctx, vbx_list_blocks(ctx, layer_id, updated_mask, nullptr, 0, &n), "vbx_list_blocks");
+  check(ctx, vbx_num_blocks(ctx, layer_id, &n), "vbx_num_blocks");
   if (n == 0) return 0;
-  std::vector<int32_t> idx(3 * n);
-  check(ctx, vbx_list_blocks(ctx, layer_id, updated_mask, idx.data(), n, &n), "vbx_list_blocks");
   const size_t vpb = layer->voxels_per_side() * layer->voxels_per_side() * layer->voxels_per_side();
-  std::vector<VoxelType> vox(vpb * n);
-  std::vector<uint8_t> upd(n);
-  check(ctx, vbx_download_blocks(ctx, layer_id, idx.data(), n, vox.data(), upd.data()), "vbx_download_blocks");
+  std::vector<int32_t> idx;
+  std::vector<VoxelType> vox;
+  std::vector<uint8_t> upd;
+  uint64_t cap = updated_mask ? std::min<uint64_t>(n, 64) : n;
+  while (true) {
+    idx.resize(3 * cap);
+    vox.resize(vpb * cap);
+    upd.resize(cap);
+    check(ctx, vbx_mirror_updated(ctx, layer_id, updated_mask, /*clear_mask=*/0, idx.data(), vox.data(), upd.data(), cap, &n),
+          "vbx_mirror_updated");
+    if (n <= cap) break;
+    cap = n;
+  }
+  if (n == 0) return 0;
   for (uint64_t b = 0; b < n; ++b) {
     typename Block<VoxelType>::Ptr block =
         layer->allocateBlockPtrByIndex(BlockIndex(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2]));

@@ -68,3 +68,44 @@ def test_remove_blocks_and_clear():
     ia.integratePointCloud((scans[2][2], scans[2][3]), scans[2][0], scans[2][1])
     i4, v4, _ = _snapshot(a)
     assert (i4 == fi).all() and v4.tobytes() == fv.tobytes()
+
+
+def test_mirror_updated_equals_list_plus_download():
+    """vbx_mirror_updated = getAllUpdatedBlocks(bit) + block payloads + updated().reset(bit) in one
+    call: same blocks, same bytes, same order; staging and direct
+    (page-locked) destinations; the clear mask only touches the mirrored bit."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    scans = scenes.c3_room_sequence(n_scans=3, width=96, height=72)
+    integ.integratePointCloud((scans[0][2], scans[0][3]), scans[0][0], scans[0][1])
+    MESH, ESDF = 2, 4
+    want_idx = layer.getAllUpdatedBlocks(1)          # Update::kMesh
+    want_vox, want_upd = layer.getBlocks(want_idx)
+    idx, vox, upd = layer.mirrorUpdated(MESH, MESH)
+    assert idx.tobytes() == want_idx.tobytes()
+    assert vox.tobytes() == want_vox.tobytes()
+    assert upd.tobytes() == np.asarray(want_upd).tobytes()
+    # the mesh bit is gone, the others stay
+    assert layer.getAllUpdatedBlocks(1).shape[0] == 0
+    assert layer.getAllUpdatedBlocks(2).tobytes() == want_idx.tobytes()
+    # next scan: only the blocks it touched come back, into a page-locked buffer, no staging
+    integ.integratePointCloud((scans[1][2], scans[1][3]), scans[1][0], scans[1][1])
+    want_idx = layer.getAllUpdatedBlocks(1)
+    want_vox, _ = layer.getBlocks(want_idx)
+    pinned = layer.hostBuffer((want_idx.shape[0] + 3, 4096), vb.TSDF_DTYPE)
+    idx, vox, upd = layer.mirrorUpdated(MESH, MESH, voxels_out=pinned)
+    assert idx.tobytes() == want_idx.tobytes() and vox.tobytes() == want_vox.tobytes()
+    assert np.shares_memory(vox, pinned)
+    # mask 0 = every block; nothing is cleared without a clear mask
+    idx_all, vox_all, _ = layer.mirrorUpdated(0, 0)
+    assert idx_all.tobytes() == layer.getAllAllocatedBlocks().tobytes()
+    assert vox_all.tobytes() == layer.getBlocks(idx_all)[0].tobytes()
+    assert layer.getAllUpdatedBlocks(2).shape[0] > 0
+    # ESDF layer
+    esdf = vb.Layer(0.1, 16, voxel_type="esdf")
+    e = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(min_distance_m=0.2), layer, esdf)
+    e.updateFromTsdfLayer(True)
+    eidx, evox, _ = esdf.mirrorUpdated(0, 0)
+    assert eidx.tobytes() == esdf.getAllAllocatedBlocks().tobytes()
+    assert evox.tobytes() == esdf.getBlocks(eidx)[0].tobytes()

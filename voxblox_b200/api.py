@@ -114,7 +114,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
            "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
-           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config"]
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_mirror_updated"]
 
 _lib = None
 
@@ -167,6 +167,8 @@ def load_library():
     lib.vbx_clear_updated.argtypes = [vp, i32, i32]
     lib.vbx_esdf_create.restype = i32
     lib.vbx_esdf_create.argtypes = [vp, C.POINTER(EsdfIntegratorConfig)]
+    lib.vbx_mirror_updated.restype = i32
+    lib.vbx_mirror_updated.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, C.POINTER(u64)]
     lib.vbx_esdf_update_blocks.restype = i32
     lib.vbx_esdf_update_blocks.argtypes = [vp, vp, u64, i32]
     lib.vbx_esdf_set_max_distance.restype = i32
@@ -311,6 +313,28 @@ class Layer:
                                                   idx.shape[0], vox.ctypes.data, upd.ctypes.data),
                       "vbx_download_blocks")
         return vox, upd
+
+    def mirrorUpdated(self, bit_mask: int = 0, clear_mask: int = 0, voxels_out: Optional[np.ndarray] = None):
+        """getAllUpdatedBlocks(bit) + block payloads + updated().reset(bit) in one call
+        (vbx_mirror_updated).  Returns (indices [m,3], voxels [m, vps^3], updated bits [m]);
+        voxels_out may be a page-locked buffer from hostBuffer() (filled in place, no staging)."""
+        ctx = self._bound()
+        dt = TSDF_DTYPE if self._layer_id == LAYER_TSDF else ESDF_DTYPE
+        n = C.c_uint64(0)
+        cap = 0 if voxels_out is None else int(voxels_out.shape[0])
+        while True:
+            idx = np.zeros((max(cap, 1), 3), dtype=np.int32)
+            upd = np.zeros(max(cap, 1), dtype=np.uint8)
+            vox = voxels_out if (voxels_out is not None and cap <= voxels_out.shape[0]) else \
+                np.zeros((max(cap, 1), self._vps ** 3), dtype=dt)
+            ctx.check(ctx.lib.vbx_mirror_updated(ctx.handle, self._layer_id, int(bit_mask), int(clear_mask),
+                                                 idx.ctypes.data, vox.ctypes.data, upd.ctypes.data, cap, C.byref(n)),
+                      "vbx_mirror_updated")
+            if n.value <= cap:
+                m = int(n.value)
+                return idx[:m], vox[:m], upd[:m]
+            cap = int(n.value)
+            voxels_out = None if (voxels_out is not None and cap > voxels_out.shape[0]) else voxels_out
 
     def getBlockByIndex(self, index: Sequence[int]) -> np.ndarray:
         """core/layer.h:55-62: LOG(FATAL) "Accessed unallocated block" -> VoxbloxError."""

@@ -195,4 +195,106 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
   return refresh_host_mirror(c);
 }
 
+// ------------------------------------------------------------------ incremental host mirror
+// what every host consumer of the Layer does after a scan --
+// getAllUpdatedBlocks(bit) (core/layer.h:194-203), read the blocks, updated().reset(bit)
+// (e.g. mesh_integrator.h:168-183, esdf_integrator.cc:113-121) -- as ONE call: the dirty blocks
+// are gathered into a contiguous staging buffer by a kernel, leave the device in one copy into
+// page-locked memory, and their bits are cleared on the device.
+__global__ void k_gather_blocks(const uint4* __restrict__ pool, const uint32_t* __restrict__ slots, uint32_t m,
+                                uint32_t vec_per_block, uint4* __restrict__ out, uint8_t* __restrict__ flags,
+                                uint8_t clear_mask) {
+  // one CTA per (block, 1/8 of its payload): 16-byte loads, fully coalesced both ways
+  const uint32_t b = blockIdx.x >> 3, part = blockIdx.x & 7u;
+  if (b >= m) return;
+  const uint32_t slot = slots[b];
+  const uint32_t per = (vec_per_block + 7u) / 8u;
+  const uint32_t lo = part * per, hi = min(vec_per_block, lo + per);
+  const uint4* src = pool + (size_t)slot * vec_per_block;
+  uint4* dst = out + (size_t)b * vec_per_block;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = __ldcs(src + i);
+  if (part == 0 && threadIdx.x == 0 && clear_mask) flags[slot] &= (uint8_t)~clear_mask;
+}
+
+int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
+                   uint8_t* updated_bits, uint64_t cap, uint64_t* n) {
+  cudaStream_t s = c->stream;
+  *n = 0;
+  if (c->n_blocks == 0) return VBX_OK;
+  if (int rc = refresh_host_mirror(c)) return rc;
+  // the flags are one byte per block: a single small copy decides what is dirty
+  std::vector<uint8_t> upd(c->n_blocks), has(c->n_blocks, 1);
+  uint8_t* flags = (layer == VBX_LAYER_TSDF) ? c->tab.slot_updated : c->tab.slot_esdf_updated;
+  VBX_CUDA(c, cudaMemcpyAsync(upd.data(), flags, c->n_blocks, cudaMemcpyDeviceToHost, s));
+  if (layer == VBX_LAYER_ESDF) {
+    VBX_CUDA(c, cudaMemcpyAsync(has.data(), c->tab.slot_has_esdf, c->n_blocks, cudaMemcpyDeviceToHost, s));
+  }
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  struct Item {
+    int x, y, z;
+    uint32_t slot;
+  };
+  std::vector<Item> items;
+  for (uint32_t sl = 0; sl < c->n_blocks; ++sl) {
+    if (!has[sl]) continue;
+    if (updated_mask && !(upd[sl] & updated_mask)) continue;
+    Item it;
+    unpack3(c->host_slot_key[sl], &it.x, &it.y, &it.z);
+    it.slot = sl;
+    items.push_back(it);
+  }
+  *n = items.size();
+  if (items.empty() || items.size() > cap) return VBX_OK;  // (too small a buffer: the caller grows it and retries)
+  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  });
+  const size_t m = items.size();
+  const size_t vbytes = (layer == VBX_LAYER_TSDF) ? sizeof(TsdfVoxel) : sizeof(EsdfVoxel);
+  const size_t bbytes = vbytes * c->vox_per_block;  // 16-byte multiple for every power-of-two block side >= 2
+  if (bbytes % 16 != 0) return fail(c, VBX_E_STATE, "block payload is not a multiple of 16 bytes");
+  if (m * bbytes > c->mirror_cap_bytes || m > c->mirror_cap_slots) {
+    if (c->mirror_dev) cudaFree(c->mirror_dev);
+    if (c->mirror_host) cudaFreeHost(c->mirror_host);
+    if (c->mirror_slots) cudaFree(c->mirror_slots);
+    c->mirror_dev = c->mirror_host = nullptr;
+    c->mirror_slots = nullptr;
+    c->mirror_cap_bytes = c->mirror_cap_slots = 0;
+    const size_t want = std::max<size_t>(2 * m, 256);
+    VBX_CUDA(c, cudaMalloc(&c->mirror_dev, want * bbytes));
+    VBX_CUDA(c, cudaMallocHost(&c->mirror_host, want * bbytes));
+    VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->mirror_slots), want * sizeof(uint32_t)));
+    c->mirror_cap_bytes = want * bbytes;
+    c->mirror_cap_slots = want;
+  }
+  std::vector<uint32_t> slots(m);
+  for (size_t i = 0; i < m; ++i) {
+    slots[i] = items[i].slot;
+    if (idx3) {
+      idx3[3 * i] = items[i].x;
+      idx3[3 * i + 1] = items[i].y;
+      idx3[3 * i + 2] = items[i].z;
+    }
+    if (updated_bits) updated_bits[i] = upd[items[i].slot];
+  }
+  VBX_CUDA(c, cudaMemcpyAsync(c->mirror_slots, slots.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  const char* pool = (layer == VBX_LAYER_TSDF) ? reinterpret_cast<const char*>(c->tab.tsdf)
+                                               : reinterpret_cast<const char*>(c->tab.esdf);
+  k_gather_blocks<<<(unsigned int)(m * 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(pool), c->mirror_slots, (uint32_t)m,
+                                                         (uint32_t)(bbytes / 16), reinterpret_cast<uint4*>(c->mirror_dev),
+                                                         flags, (uint8_t)clear_mask);
+  // straight into the caller's buffer when it is page-locked (vbx_host_alloc / cudaHostRegister),
+  // otherwise through the engine's page-locked staging buffer
+  cudaPointerAttributes attr;
+  const bool direct = voxels && cudaPointerGetAttributes(&attr, voxels) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // (an unregistered pointer may leave a sticky-free error code behind)
+  void* dst = direct ? voxels : c->mirror_host;
+  VBX_CUDA(c, cudaMemcpyAsync(dst, c->mirror_dev, m * bbytes, cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
+  if (!direct && voxels) std::memcpy(voxels, c->mirror_host, m * bbytes);
+  return VBX_OK;
+}
+
 }  // namespace vbx

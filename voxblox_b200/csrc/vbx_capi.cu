@@ -343,6 +343,9 @@ void vbx_destroy(vbx_ctx* c) {
   }
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->set[1].h_state) cudaFreeHost(c->set[1].h_state);
+  if (c->mirror_dev) cudaFree(c->mirror_dev);
+  if (c->mirror_host) cudaFreeHost(c->mirror_host);
+  if (c->mirror_slots) cudaFree(c->mirror_slots);
   for (int i = 0; i < 2; ++i) {
     if (c->set[i].copy_done) cudaEventDestroy(c->set[i].copy_done);
     if (c->set[i].front_done) cudaEventDestroy(c->set[i].front_done);
@@ -617,6 +620,16 @@ int vbx_download_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, 
   }
   VBX_CUDA(c, cudaStreamSynchronize(c->stream));
   return VBX_OK;
+}
+
+int vbx_mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
+                       uint8_t* updated_bits, uint64_t cap, uint64_t* n) {
+  if (!c || !n || (cap && (!idx3 || !voxels))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  *n = 0;
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
+  return mirror_updated(c, layer, updated_mask, clear_mask, idx3, voxels, updated_bits, cap, n);
 }
 
 int vbx_clear_updated(vbx_ctx* c, int layer, int updated_mask) {

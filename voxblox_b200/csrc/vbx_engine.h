@@ -180,6 +180,11 @@ struct vbx_ctx {
   int deferred_rc = 0;
   bool force_wide_keys = false;  // set once an asynchronous scan overflowed the compact bundle keys
   std::string deferred_msg;
+  // incremental device -> host mirror (vbx_mirror_updated): gather staging on both sides
+  void* mirror_dev = nullptr;
+  void* mirror_host = nullptr;  // page-locked
+  uint32_t* mirror_slots = nullptr;
+  size_t mirror_cap_bytes = 0, mirror_cap_slots = 0;
   // host mirror of slot_key (refreshed lazily)
   std::vector<uint64_t> host_slot_key;
   std::unordered_map<uint64_t, int32_t> host_key2slot;
@@ -212,6 +217,8 @@ namespace vbx {
 int fail(vbx_ctx* c, int code, const std::string& msg);
 int cuda_fail(vbx_ctx* c, cudaError_t e, const char* what);
 int refresh_host_mirror(vbx_ctx* c);
+int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
+                   uint8_t* updated_bits, uint64_t cap, uint64_t* n);
 int esdf_destroy(vbx_ctx* c);
 int drain_async(vbx_ctx* c);           // wait for every asynchronously submitted scan, collect its results
 int set_n_blocks(vbx_ctx* c, uint32_t n);
