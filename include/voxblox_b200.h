@@ -182,6 +182,16 @@ VBX_API int vbx_download_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, ui
  * *n = number of matching blocks; if *n > cap nothing is copied or cleared (grow and retry). */
 VBX_API int vbx_mirror_updated(vbx_ctx* ctx, int layer, int updated_mask, int clear_mask, int32_t* idx3,
                        void* voxels, uint8_t* updated_bits, uint64_t cap, uint64_t* n);
+/* The same with payloads in the reference's serialised form (Block::serializeToIntegers,
+ * src/core/block.cc:159-183 TSDF = 3 words per voxel, :203-234 ESDF = 2 words per voxel -- the
+ * `voxel_data` of BlockProto / voxblox_msgs::Block), packed on the device: words holds
+ * cap * vps^3 * (3 | 2) uint32. */
+VBX_API int vbx_serialize_updated(vbx_ctx* ctx, int layer, int updated_mask, int clear_mask, int32_t* idx3,
+                          uint32_t* words, uint8_t* updated_bits, uint64_t cap, uint64_t* n);
+/* ... and back: Block(BlockProto) + deserializeFromIntegers (core/block_inl.h:73-109,
+ * block.cc:65-90,110-135); creates the blocks as needed. */
+VBX_API int vbx_deserialize_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m,
+                           const uint32_t* words, const uint8_t* updated_bits);
 /* Host -> device: Layer::insertBlock / allocateBlockPtrByIndex + voxel copy
  * (core/layer.h:103-111,152-161); creates the block if needed. */
 VBX_API int vbx_upload_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m,

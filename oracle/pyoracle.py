@@ -101,6 +101,10 @@ class OracleLib:
         lib.vbo_esdf_create.argtypes = [C.c_void_p, C.POINTER(EsdfConfig)]
         lib.vbo_esdf_update.restype = C.c_int
         lib.vbo_esdf_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.vbo_serialize_block.restype = C.c_int
+        lib.vbo_serialize_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.vbo_deserialize_block.restype = C.c_int
+        lib.vbo_deserialize_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.vbo_esdf_update_blocks.restype = C.c_int
         lib.vbo_esdf_update_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
         lib.vbo_esdf_set_max_distance.restype = C.c_int
@@ -181,6 +185,23 @@ class OracleMap:
         rc = self.lib.vbo_esdf_update(self.h, int(batch), int(clear_updated_flag))
         if rc != 0:
             raise RuntimeError(f"vbo_esdf_update rc={rc}")
+
+    def serialize_block(self, index, layer: int = 0) -> np.ndarray:
+        """Block::serializeToIntegers (src/core/block.cc:159-183 / :203-234)"""
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        words = np.zeros(self.vps ** 3 * (3 if layer == 0 else 2), dtype=np.uint32)
+        rc = self.lib.vbo_serialize_block(self.h, layer, idx.ctypes.data, words.ctypes.data)
+        if rc != 0:
+            raise KeyError(tuple(int(v) for v in idx))
+        return words
+
+    def deserialize_block(self, index, words, layer: int = 0):
+        """Block::deserializeFromIntegers into a (new) block (block.cc:65-90 / :110-135)"""
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        assert w.size == self.vps ** 3 * (3 if layer == 0 else 2)
+        if self.lib.vbo_deserialize_block(self.h, layer, idx.ctypes.data, w.ctypes.data) != 0:
+            raise RuntimeError("vbo_deserialize_block")
 
     def esdf_update_blocks(self, indices, incremental: bool = False):
         """EsdfIntegrator::updateFromTsdfBlocks (esdf_integrator.cc:124-302)"""

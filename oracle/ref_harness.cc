@@ -64,6 +64,23 @@ int getBlock(const voxblox::Layer<V>& layer, const int32_t idx[3], void* voxels,
 
 }  // namespace
 
+template <typename V>
+static int serializeBlock(voxblox::Layer<V>& layer, const int32_t idx[3], uint32_t* words) {
+  typename voxblox::Block<V>::Ptr b = layer.getBlockPtrByIndex(voxblox::BlockIndex(idx[0], idx[1], idx[2]));
+  if (!b) return 1;
+  std::vector<uint32_t> data;
+  b->serializeToIntegers(&data);
+  std::memcpy(words, data.data(), data.size() * sizeof(uint32_t));
+  return 0;
+}
+template <typename V>
+static int deserializeBlock(voxblox::Layer<V>& layer, const int32_t idx[3], const uint32_t* words, size_t per_voxel) {
+  typename voxblox::Block<V>::Ptr b = layer.allocateBlockPtrByIndex(voxblox::BlockIndex(idx[0], idx[1], idx[2]));
+  std::vector<uint32_t> data(words, words + b->num_voxels() * per_voxel);
+  b->deserializeFromIntegers(data);
+  return 0;
+}
+
 extern "C" {
 
 const char* vbo_impl_name(void) { return "reference"; }
@@ -143,6 +160,15 @@ int vbo_get_block(void* hv, int layer, const int32_t idx[3], void* voxels,
   Handle* h = static_cast<Handle*>(hv);
   return layer == VBO_LAYER_TSDF ? getBlock(*h->tsdf, idx, voxels, updated_bits)
                                  : getBlock(*h->esdf, idx, voxels, updated_bits);
+}
+
+int vbo_serialize_block(void* hv, int layer, const int32_t idx[3], uint32_t* words) {
+  Handle* h = static_cast<Handle*>(hv);
+  return layer == VBO_LAYER_TSDF ? serializeBlock(*h->tsdf, idx, words) : serializeBlock(*h->esdf, idx, words);
+}
+int vbo_deserialize_block(void* hv, int layer, const int32_t idx[3], const uint32_t* words) {
+  Handle* h = static_cast<Handle*>(hv);
+  return layer == VBO_LAYER_TSDF ? deserializeBlock(*h->tsdf, idx, words, 3) : deserializeBlock(*h->esdf, idx, words, 2);
 }
 
 int vbo_esdf_create(void* hv, const vbo_esdf_config* c) {

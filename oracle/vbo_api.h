@@ -98,6 +98,11 @@ int vbo_esdf_create(void* h, const vbo_esdf_config* cfg);
 /* batch=0: updateFromTsdfLayer(clear_updated_flag) (esdf_integrator.cc:104-122)
  * batch=1: updateFromTsdfLayerBatch()              (esdf_integrator.cc:94-102) */
 int vbo_esdf_update(void* h, int batch, int clear_updated_flag);
+/* Block::serializeToIntegers / deserializeFromIntegers (src/core/block.cc:65-90,110-135,159-183,
+ * 203-234): words holds vps^3 * 3 (TSDF) or * 2 (ESDF) uint32.  The deserialising call creates
+ * the block if needed. */
+int vbo_serialize_block(void* h, int layer, const int32_t idx[3], uint32_t* words);
+int vbo_deserialize_block(void* h, int layer, const int32_t idx[3], const uint32_t* words);
 /* EsdfIntegrator::updateFromTsdfBlocks(tsdf_blocks, incremental) (esdf_integrator.cc:124-302) */
 int vbo_esdf_update_blocks(void* h, const int32_t* idx3, uint64_t m, int incremental);
 /* setEsdfMaxDistance / setFullEuclidean (esdf_integrator.h:139-149) */

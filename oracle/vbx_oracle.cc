@@ -950,6 +950,84 @@ int vbo_get_block(void* hv, int layer, const int32_t idx[3], void* voxels, uint8
   return 0;
 }
 
+// src/core/block.cc:8-41: the int8 fields are ORed in as sign-extended ints, so a negative y or z
+// also sets every byte above it
+static uint32_t serializeDirection(const int32_t parent[3]) {
+  uint32_t data = 0;
+  const int8_t px = static_cast<int8_t>(std::min(127, std::max(parent[0], -128)));
+  const int8_t py = static_cast<int8_t>(std::min(127, std::max(parent[1], -128)));
+  const int8_t pz = static_cast<int8_t>(std::min(127, std::max(parent[2], -128)));
+  data |= static_cast<uint32_t>(static_cast<int8_t>(px) << 24);
+  data |= static_cast<uint32_t>(static_cast<int8_t>(py) << 16);
+  data |= static_cast<uint32_t>(static_cast<int8_t>(pz) << 8);
+  return data;
+}
+int vbo_serialize_block(void* hv, int layer, const int32_t idx[3], uint32_t* words) {
+  Map* m = static_cast<Map*>(hv);
+  const I3 bi{idx[0], idx[1], idx[2]};
+  if (layer == VBO_LAYER_TSDF) {  // block.cc:159-183
+    auto it = m->tsdf.find(bi);
+    if (it == m->tsdf.end()) return 1;
+    for (const TsdfVox& v : it->second->vox) {
+      uint32_t w;
+      std::memcpy(&w, &v.distance, 4);
+      *words++ = w;
+      std::memcpy(&w, &v.weight, 4);
+      *words++ = w;
+      *words++ = static_cast<uint32_t>(v.color.a) | (static_cast<uint32_t>(v.color.b) << 8) |
+                 (static_cast<uint32_t>(v.color.g) << 16) | (static_cast<uint32_t>(v.color.r) << 24);
+    }
+  } else {  // block.cc:203-234
+    auto it = m->esdf.find(bi);
+    if (it == m->esdf.end()) return 1;
+    for (const EsdfVox& v : it->second->vox) {
+      uint32_t w;
+      std::memcpy(&w, &v.distance, 4);
+      *words++ = w;
+      uint32_t b2 = serializeDirection(v.parent);
+      uint8_t flag = 0;
+      flag |= v.observed ? 1 : 0;
+      flag |= v.hallucinated ? 2 : 0;
+      flag |= v.in_queue ? 4 : 0;
+      flag |= v.fixed ? 8 : 0;
+      b2 |= static_cast<uint32_t>(flag) & 0xFFu;
+      *words++ = b2;
+    }
+  }
+  return 0;
+}
+int vbo_deserialize_block(void* hv, int layer, const int32_t idx[3], const uint32_t* words) {
+  Map* m = static_cast<Map*>(hv);
+  const I3 bi{idx[0], idx[1], idx[2]};
+  if (layer == VBO_LAYER_TSDF) {  // block.cc:65-90
+    auto it = m->tsdf.find(bi);
+    if (it == m->tsdf.end()) it = m->tsdf.emplace(bi, std::make_shared<Blk<TsdfVox>>(m->vps)).first;
+    for (TsdfVox& v : it->second->vox) {
+      std::memcpy(&v.distance, words++, 4);
+      std::memcpy(&v.weight, words++, 4);
+      const uint32_t b3 = *words++;
+      v.color.r = static_cast<uint8_t>(b3 >> 24);
+      v.color.g = static_cast<uint8_t>((b3 & 0x00FF0000u) >> 16);
+      v.color.b = static_cast<uint8_t>((b3 & 0x0000FF00u) >> 8);
+      v.color.a = static_cast<uint8_t>(b3 & 0x000000FFu);
+    }
+  } else {  // block.cc:110-135, :43-63
+    std::shared_ptr<Blk<EsdfVox>> b = m->esdfAllocate(bi);
+    for (EsdfVox& v : b->vox) {
+      std::memcpy(&v.distance, words++, 4);
+      const uint32_t b2 = *words++;
+      v.observed = (b2 & 1u) ? 1 : 0;
+      v.hallucinated = (b2 & 2u) ? 1 : 0;
+      v.in_queue = (b2 & 4u) ? 1 : 0;
+      v.fixed = (b2 & 8u) ? 1 : 0;
+      v.parent[0] = static_cast<int8_t>((b2 >> 24) & 0xFFu);
+      v.parent[1] = static_cast<int8_t>((b2 >> 16) & 0xFFu);
+      v.parent[2] = static_cast<int8_t>((b2 >> 8) & 0xFFu);
+    }
+  }
+  return 0;
+}
+
 int vbo_esdf_create(void* hv, const vbo_esdf_config* c) {
   Map* m = static_cast<Map*>(hv);
   m->ecfg = *c;

@@ -109,3 +109,73 @@ def test_mirror_updated_equals_list_plus_download():
     eidx, evox, _ = esdf.mirrorUpdated(0, 0)
     assert eidx.tobytes() == esdf.getAllAllocatedBlocks().tobytes()
     assert evox.tobytes() == esdf.getBlocks(eidx)[0].tobytes()
+
+
+def test_serialized_blocks_match_reference_format():
+    """vbx_serialize_updated packs blocks on the device in Block::serializeToIntegers' layout
+    (src/core/block.cc:159-183 TSDF, :203-234 ESDF incl. the serializeDirection sign-extension
+    quirk): word for word equal to the oracle's; vbx_deserialize_blocks is its inverse
+    (block.cc:65-90,110-135) -- SURVEY.md section 8f N2."""
+    from oracle import pyoracle as po
+
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    ekw = dict(max_distance_m=2.0, default_distance_m=2.0, min_distance_m=0.2, min_diff_m=0.0)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    esdf = vb.Layer(0.1, 16, voxel_type="esdf")
+    eint = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(**ekw), layer, esdf)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 16)
+    omap.esdf_create(po.EsdfConfig(**ekw))
+    for s in scenes.c3_room_sequence(n_scans=2, width=96, height=72):
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    eint.updateFromTsdfLayer(False)
+    # TSDF: the device map is bit-identical to the oracle's, so the words must be too
+    idx, words, upd = layer.serializeUpdated(0, 0)
+    assert idx.tobytes() == omap.block_indices(0).tobytes()
+    for k, i in enumerate(idx):
+        assert words[k].tobytes() == omap.serialize_block(i, 0).tobytes(), tuple(i)
+    # ESDF: serialise the DEVICE's voxels with the oracle's packer (load them into a scratch map)
+    scratch = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 16)
+    scratch.esdf_create(po.EsdfConfig(**ekw))
+    eidx, ewords, _ = esdf.serializeUpdated(0, 0)
+    evox, _ = esdf.getBlocks(eidx)
+    assert (evox["parent"] < 0).any()
+    for k, i in enumerate(eidx):
+        # oracle round trip of the device words = what the reference would decode ...
+        scratch.deserialize_block(i, ewords[k], 1)
+        dec = scratch.block(i, 1)[0]
+        # ... and re-encoding that is a fixed point, equal to the device's words
+        assert scratch.serialize_block(i, 1).tobytes() == ewords[k].tobytes(), tuple(i)
+        assert dec["distance"].tobytes() == evox[k]["distance"].tobytes()
+        for f in ("observed", "hallucinated", "in_queue", "fixed"):
+            assert (dec[f] == evox[k][f]).all()
+        # block.cc:8-41,203-234 restated in numpy on the raw device voxels (int64 shifts sign-extend
+        # like the reference's `int8 << n`)
+        par = evox[k]["parent"].astype(np.int64).clip(-128, 127)
+        w2 = ((par[:, 0] << 24) | (par[:, 1] << 16) | (par[:, 2] << 8)) & 0xFFFFFFFF
+        w2 |= (evox[k]["observed"] != 0) * 1 | (evox[k]["hallucinated"] != 0) * 2 | (evox[k]["in_queue"] != 0) * 4 | \
+            (evox[k]["fixed"] != 0) * 8
+        want = np.stack([evox[k]["distance"].view(np.uint32), w2.astype(np.uint32)], axis=1).reshape(-1)
+        assert want.tobytes() == ewords[k].tobytes(), tuple(i)
+    # deserialise on the device: a fresh map fed the words must hold what the reference decodes
+    layer2 = vb.Layer(0.1, 16)
+    integ2 = vb.TsdfIntegratorFactory.create("merged", cfg, layer2)
+    esdf2 = vb.Layer(0.1, 16, voxel_type="esdf")
+    vb.EsdfIntegrator(vb.EsdfIntegratorConfig(**ekw), layer2, esdf2)
+    layer2.insertSerializedBlocks(idx, words, upd)
+    esdf2.insertSerializedBlocks(eidx, ewords)
+    assert layer2.getAllAllocatedBlocks().tobytes() == idx.tobytes()
+    assert layer2.getBlocks(idx)[0].tobytes() == layer.getBlocks(idx)[0].tobytes()       # TSDF is lossless
+    assert np.asarray(layer2.getBlocks(idx)[1]).tobytes() == np.asarray(upd).tobytes()
+    got, _ = esdf2.getBlocks(eidx)
+    for k, i in enumerate(eidx):
+        want = scratch.block(i, 1)[0]
+        assert got[k].tobytes() == want.tobytes(), tuple(i)
+    # continuing to integrate on the reloaded map equals continuing on the original
+    s = scenes.c3_room_sequence(n_scans=3, width=96, height=72)[2]
+    integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    integ2.integratePointCloud((s[2], s[3]), s[0], s[1])
+    a = layer.getAllAllocatedBlocks()
+    assert a.tobytes() == layer2.getAllAllocatedBlocks().tobytes()
+    assert layer.getBlocks(a)[0].tobytes() == layer2.getBlocks(a)[0].tobytes()

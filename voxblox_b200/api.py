@@ -114,7 +114,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
            "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
-           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_mirror_updated"]
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks"]
 
 _lib = None
 
@@ -169,6 +169,10 @@ def load_library():
     lib.vbx_esdf_create.argtypes = [vp, C.POINTER(EsdfIntegratorConfig)]
     lib.vbx_mirror_updated.restype = i32
     lib.vbx_mirror_updated.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, C.POINTER(u64)]
+    lib.vbx_serialize_updated.restype = i32
+    lib.vbx_serialize_updated.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, C.POINTER(u64)]
+    lib.vbx_deserialize_blocks.restype = i32
+    lib.vbx_deserialize_blocks.argtypes = [vp, i32, vp, u64, vp, vp]
     lib.vbx_esdf_update_blocks.restype = i32
     lib.vbx_esdf_update_blocks.argtypes = [vp, vp, u64, i32]
     lib.vbx_esdf_set_max_distance.restype = i32
@@ -335,6 +339,35 @@ class Layer:
                 return idx[:m], vox[:m], upd[:m]
             cap = int(n.value)
             voxels_out = None if (voxels_out is not None and cap > voxels_out.shape[0]) else voxels_out
+
+    def serializeUpdated(self, bit_mask: int = 0, clear_mask: int = 0):
+        """Block::serializeToIntegers (src/core/block.cc:159-183 / :203-234) of every block whose
+        updated bits match, packed on the device.  Returns (indices [m,3], words [m, vps^3 * (3|2)] u32,
+        updated bits [m])."""
+        ctx = self._bound()
+        wpv = 3 if self._layer_id == LAYER_TSDF else 2
+        n = C.c_uint64(0)
+        cap = 0
+        while True:
+            idx = np.zeros((max(cap, 1), 3), dtype=np.int32)
+            upd = np.zeros(max(cap, 1), dtype=np.uint8)
+            words = np.zeros((max(cap, 1), self._vps ** 3 * wpv), dtype=np.uint32)
+            ctx.check(ctx.lib.vbx_serialize_updated(ctx.handle, self._layer_id, int(bit_mask), int(clear_mask),
+                                                    idx.ctypes.data, words.ctypes.data, upd.ctypes.data, cap, C.byref(n)),
+                      "vbx_serialize_updated")
+            if n.value <= cap:
+                m = int(n.value)
+                return idx[:m], words[:m], upd[:m]
+            cap = int(n.value)
+
+    def insertSerializedBlocks(self, indices: np.ndarray, words: np.ndarray, updated_bits: Optional[np.ndarray] = None):
+        """Block(BlockProto): deserializeFromIntegers into (new) blocks (core/block_inl.h:73-109)."""
+        ctx = self._bound()
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        w = np.ascontiguousarray(words, dtype=np.uint32).reshape(idx.shape[0], -1)
+        upd = None if updated_bits is None else np.ascontiguousarray(updated_bits, dtype=np.uint8)
+        ctx.check(ctx.lib.vbx_deserialize_blocks(ctx.handle, self._layer_id, idx.ctypes.data, idx.shape[0], w.ctypes.data,
+                                                 None if upd is None else upd.ctypes.data), "vbx_deserialize_blocks")
 
     def getBlockByIndex(self, index: Sequence[int]) -> np.ndarray:
         """core/layer.h:55-62: LOG(FATAL) "Accessed unallocated block" -> VoxbloxError."""

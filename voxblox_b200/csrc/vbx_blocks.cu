@@ -61,10 +61,114 @@ __global__ void k_rebuild_hash(Tables tab, uint32_t n_blocks) {
 
 static inline unsigned int grid_for(uint64_t n, int block) { return (unsigned int)((n + block - 1) / block); }
 
-static size_t voxel_bytes(int layer) { return layer == VBX_LAYER_TSDF ? sizeof(TsdfVoxel) : sizeof(EsdfVoxel); }
+// ---- serialised block payloads, voxblox/src/core/block.cc:
+//   TsdfVoxel -> 3 words: distance bits, weight bits, a | b<<8 | g<<16 | r<<24      (cc:159-183, :65-90)
+//   EsdfVoxel -> 2 words: distance bits, parent x,y,z as int8 in bytes 3,2,1 | flag byte
+//                (observed 1, hallucinated 2, in_queue 4, fixed 8)                (cc:203-234, :110-135)
+// serializeDirection (cc:8-41) ORs `int8 << shift` as a sign-extended int, so a negative y or z
+// also sets every byte above it; reproduced bit for bit.
+__device__ __forceinline__ uint32_t tsdf_word(uint32_t w, uint32_t k) { return k == 2u ? __byte_perm(w, 0, 0x0123) : w; }
 
+__device__ __forceinline__ uint2 esdf_pack(const uint32_t* v) {
+  auto clamp8 = [](int32_t x) { return (int)max(-128, min(127, x)); };
+  uint32_t d = 0;
+  d |= (uint32_t)(clamp8((int32_t)v[2]) << 24);
+  d |= (uint32_t)(clamp8((int32_t)v[3]) << 16);
+  d |= (uint32_t)(clamp8((int32_t)v[4]) << 8);
+  const uint32_t f = v[1];  // four bool bytes: observed, hallucinated, in_queue, fixed
+  uint32_t flag = 0;
+  if (f & 0x000000ffu) flag |= 1u;
+  if (f & 0x0000ff00u) flag |= 2u;
+  if (f & 0x00ff0000u) flag |= 4u;
+  if (f & 0xff000000u) flag |= 8u;
+  return make_uint2(v[0], d | flag);
+}
+
+__device__ __forceinline__ void esdf_unpack(uint2 w, uint32_t* v) {
+  v[0] = w.x;
+  v[1] = ((w.y & 1u) ? 0x00000001u : 0u) | ((w.y & 2u) ? 0x00000100u : 0u) | ((w.y & 4u) ? 0x00010000u : 0u) |
+         ((w.y & 8u) ? 0x01000000u : 0u);
+  v[2] = (uint32_t)(int32_t)(int8_t)((w.y >> 24) & 0xffu);  // deserializeDirection, cc:43-63
+  v[3] = (uint32_t)(int32_t)(int8_t)((w.y >> 16) & 0xffu);
+  v[4] = (uint32_t)(int32_t)(int8_t)((w.y >> 8) & 0xffu);
+}
+
+// device pool -> contiguous words in block.cc's format; one thread per output word (TSDF) / voxel (ESDF)
+__global__ void k_serialize_blocks(int layer, const uint32_t* __restrict__ pool, const uint32_t* __restrict__ slots,
+                                   uint32_t m, uint32_t vox_per_block, uint32_t* __restrict__ out,
+                                   uint8_t* __restrict__ flags, uint8_t clear_mask) {
+  const uint32_t b = blockIdx.y;
+  if (b >= m) return;
+  const uint32_t slot = slots[b];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (layer == VBX_LAYER_TSDF) {
+    const uint32_t nw = 3u * vox_per_block;
+    if (i < nw) out[(size_t)b * nw + i] = tsdf_word(__ldcs(pool + (size_t)slot * nw + i), i % 3u);
+  } else if (i < vox_per_block) {
+    const uint32_t* v = pool + ((size_t)slot * vox_per_block + i) * 5u;
+    uint32_t w[5] = {v[0], v[1], v[2], v[3], v[4]};
+    reinterpret_cast<uint2*>(out)[(size_t)b * vox_per_block + i] = esdf_pack(w);
+  }
+  if (i == 0 && clear_mask) flags[slot] &= (uint8_t)~clear_mask;
+}
+
+// contiguous payloads (raw voxel structs or block.cc words) -> pool slots; also the per-slot flags
+__global__ void k_scatter_blocks(int layer, int serialized, const uint32_t* __restrict__ in,
+                                 const int32_t* __restrict__ slots, uint32_t m, uint32_t vox_per_block,
+                                 uint32_t* __restrict__ pool, const uint8_t* __restrict__ upd_in,
+                                 uint8_t* __restrict__ flags, uint8_t* __restrict__ has_esdf) {
+  const uint32_t b = blockIdx.y;
+  if (b >= m) return;
+  const int32_t slot = slots[b];
+  if (slot < 0) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t wpv = (layer == VBX_LAYER_TSDF) ? 3u : 5u;
+  if (!serialized || layer == VBX_LAYER_TSDF) {
+    const uint32_t nw = wpv * vox_per_block;
+    if (i < nw) {
+      const uint32_t w = in[(size_t)b * nw + i];
+      pool[(size_t)slot * nw + i] = (serialized ? tsdf_word(w, i % 3u) : w);  // the byte reversal is its own inverse
+    }
+  } else if (i < vox_per_block) {
+    uint32_t v[5];
+    esdf_unpack(reinterpret_cast<const uint2*>(in)[(size_t)b * vox_per_block + i], v);
+    uint32_t* dst = pool + ((size_t)slot * vox_per_block + i) * 5u;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst[k] = v[k];
+  }
+  if (i == 0) {
+    flags[slot] = upd_in ? upd_in[b] : (uint8_t)0;
+    if (has_esdf) has_esdf[slot] = 1;
+  }
+}
+
+static int ensure_staging(vbx_ctx* c, size_t bytes, size_t slots) {
+  if (bytes <= c->mirror_cap_bytes && slots <= c->mirror_cap_slots) return VBX_OK;
+  if (c->mirror_dev) cudaFree(c->mirror_dev);
+  if (c->mirror_host) cudaFreeHost(c->mirror_host);
+  if (c->mirror_slots) cudaFree(c->mirror_slots);
+  c->mirror_dev = c->mirror_host = nullptr;
+  c->mirror_slots = nullptr;
+  c->mirror_cap_bytes = c->mirror_cap_slots = 0;
+  const size_t want_b = std::max<size_t>(2 * bytes, 16u << 20), want_s = std::max<size_t>(2 * slots, 1024);
+  VBX_CUDA(c, cudaMalloc(&c->mirror_dev, want_b));
+  VBX_CUDA(c, cudaMallocHost(&c->mirror_host, want_b));
+  VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->mirror_slots), want_s * sizeof(uint32_t)));
+  c->mirror_cap_bytes = want_b;
+  c->mirror_cap_slots = want_s;
+  return VBX_OK;
+}
+
+static size_t payload_bytes(const vbx_ctx* c, int layer, int serialized) {
+  if (layer == VBX_LAYER_TSDF) return sizeof(TsdfVoxel) * c->vox_per_block;  // 3 words either way
+  return (serialized ? 8u : sizeof(EsdfVoxel)) * c->vox_per_block;
+}
+
+// Layer::insertBlock / allocateBlockPtrByIndex + voxel copy, or Block(BlockProto) + deserializeFromIntegers
+// (core/block_inl.h:73-109) when `serialized`: find-or-create the blocks, then ONE staged copy per
+// chunk and a scatter kernel.
 int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const void* voxels,
-                  const uint8_t* updated_bits) {
+                  const uint8_t* updated_bits, int serialized) {
   if (m == 0) return VBX_OK;
   if (layer == VBX_LAYER_ESDF && !c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF layer");
   if (m > c->tab.max_blocks) return fail(c, VBX_E_CAPACITY, "more blocks than the pool holds");
@@ -85,27 +189,30 @@ int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const 
   k_ensure_keys<<<grid_for(m, 256), 256, 0, s>>>(c->tab, c->pkeys[0], (uint32_t)m, c->ray_list, c->d_state);
   k_assign_uploaded<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
   k_slots_of<<<grid_for(m, 256), 256, 0, s>>>(c->tab, c->ray_list, (uint32_t)m, reinterpret_cast<int32_t*>(c->cnt));
-  std::vector<int32_t> slots(m);
-  VBX_CUDA(c, cudaMemcpyAsync(slots.data(), c->cnt, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   if (c->h_state->error & kFatalErrors) return fail(c, VBX_E_CAPACITY, "block pool / hash full during upload");
   if (int rc = set_n_blocks(c, c->h_state->n_blocks)) return rc;
-  const size_t bbytes = voxel_bytes(layer) * c->vox_per_block;
-  char* pool = layer == VBX_LAYER_TSDF ? reinterpret_cast<char*>(c->tab.tsdf) : reinterpret_cast<char*>(c->tab.esdf);
-  std::vector<uint8_t> ones(1, 1);
-  for (uint64_t i = 0; i < m; ++i) {
-    if (slots[i] < 0) return fail(c, VBX_E_CAPACITY, "upload: block without a slot");
-    VBX_CUDA(c, cudaMemcpyAsync(pool + (size_t)slots[i] * bbytes, static_cast<const char*>(voxels) + i * bbytes, bbytes,
+  const size_t bbytes = payload_bytes(c, layer, serialized);
+  const uint32_t wpv = (layer == VBX_LAYER_TSDF) ? 3u : (serialized ? 1u : 5u);  // threads per voxel along x
+  uint32_t* pool = layer == VBX_LAYER_TSDF ? reinterpret_cast<uint32_t*>(c->tab.tsdf) : reinterpret_cast<uint32_t*>(c->tab.esdf);
+  uint8_t* flags = layer == VBX_LAYER_TSDF ? c->tab.slot_updated : c->tab.slot_esdf_updated;
+  const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(m, (256ull << 20) / bbytes));
+  if (int rc = ensure_staging(c, chunk * bbytes + chunk, chunk)) return rc;
+  uint8_t* d_upd = static_cast<uint8_t*>(c->mirror_dev) + chunk * bbytes;
+  for (uint64_t at = 0; at < m; at += chunk) {
+    const uint64_t k = std::min<uint64_t>(chunk, m - at);
+    VBX_CUDA(c, cudaMemcpyAsync(c->mirror_dev, static_cast<const char*>(voxels) + at * bbytes, k * bbytes,
                                 cudaMemcpyHostToDevice, s));
-    const uint8_t u = updated_bits ? updated_bits[i] : 0;
-    uint8_t* flags = layer == VBX_LAYER_TSDF ? c->tab.slot_updated : c->tab.slot_esdf_updated;
-    VBX_CUDA(c, cudaMemcpyAsync(flags + slots[i], &u, 1, cudaMemcpyHostToDevice, s));
-    if (layer == VBX_LAYER_ESDF) {
-      VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_has_esdf + slots[i], ones.data(), 1, cudaMemcpyHostToDevice, s));
-    }
-    VBX_CUDA(c, cudaStreamSynchronize(s));  // `u` lives on this stack frame
+    if (updated_bits) VBX_CUDA(c, cudaMemcpyAsync(d_upd, updated_bits + at, k, cudaMemcpyHostToDevice, s));
+    const dim3 grid(grid_for((uint64_t)wpv * c->vox_per_block, 256), (unsigned int)k);
+    k_scatter_blocks<<<grid, 256, 0, s>>>(layer, serialized, static_cast<const uint32_t*>(c->mirror_dev),
+                                          reinterpret_cast<const int32_t*>(c->cnt) + at, (uint32_t)k,
+                                          (uint32_t)c->vox_per_block, pool, updated_bits ? d_upd : nullptr, flags,
+                                          layer == VBX_LAYER_ESDF ? c->tab.slot_has_esdf : nullptr);
+    VBX_CUDA(c, cudaStreamSynchronize(s));  // the staging buffer is reused by the next chunk
   }
+  VBX_CUDA(c, cudaGetLastError());
   return refresh_host_mirror(c);
 }
 
@@ -217,7 +324,7 @@ __global__ void k_gather_blocks(const uint4* __restrict__ pool, const uint32_t* 
 }
 
 int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
-                   uint8_t* updated_bits, uint64_t cap, uint64_t* n) {
+                   uint8_t* updated_bits, uint64_t cap, uint64_t* n, int serialized) {
   cudaStream_t s = c->stream;
   *n = 0;
   if (c->n_blocks == 0) return VBX_OK;
@@ -251,23 +358,10 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
     return a.z < b.z;
   });
   const size_t m = items.size();
-  const size_t vbytes = (layer == VBX_LAYER_TSDF) ? sizeof(TsdfVoxel) : sizeof(EsdfVoxel);
-  const size_t bbytes = vbytes * c->vox_per_block;  // 16-byte multiple for every power-of-two block side >= 2
-  if (bbytes % 16 != 0) return fail(c, VBX_E_STATE, "block payload is not a multiple of 16 bytes");
-  if (m * bbytes > c->mirror_cap_bytes || m > c->mirror_cap_slots) {
-    if (c->mirror_dev) cudaFree(c->mirror_dev);
-    if (c->mirror_host) cudaFreeHost(c->mirror_host);
-    if (c->mirror_slots) cudaFree(c->mirror_slots);
-    c->mirror_dev = c->mirror_host = nullptr;
-    c->mirror_slots = nullptr;
-    c->mirror_cap_bytes = c->mirror_cap_slots = 0;
-    const size_t want = std::max<size_t>(2 * m, 256);
-    VBX_CUDA(c, cudaMalloc(&c->mirror_dev, want * bbytes));
-    VBX_CUDA(c, cudaMallocHost(&c->mirror_host, want * bbytes));
-    VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->mirror_slots), want * sizeof(uint32_t)));
-    c->mirror_cap_bytes = want * bbytes;
-    c->mirror_cap_slots = want;
-  }
+  const size_t raw_bytes = ((layer == VBX_LAYER_TSDF) ? sizeof(TsdfVoxel) : sizeof(EsdfVoxel)) * c->vox_per_block;
+  const size_t bbytes = payload_bytes(c, layer, serialized);
+  if (raw_bytes % 16 != 0) return fail(c, VBX_E_STATE, "block payload is not a multiple of 16 bytes");
+  if (int rc = ensure_staging(c, m * bbytes, m)) return rc;
   std::vector<uint32_t> slots(m);
   for (size_t i = 0; i < m; ++i) {
     slots[i] = items[i].slot;
@@ -281,9 +375,18 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
   VBX_CUDA(c, cudaMemcpyAsync(c->mirror_slots, slots.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   const char* pool = (layer == VBX_LAYER_TSDF) ? reinterpret_cast<const char*>(c->tab.tsdf)
                                                : reinterpret_cast<const char*>(c->tab.esdf);
-  k_gather_blocks<<<(unsigned int)(m * 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(pool), c->mirror_slots, (uint32_t)m,
-                                                         (uint32_t)(bbytes / 16), reinterpret_cast<uint4*>(c->mirror_dev),
-                                                         flags, (uint8_t)clear_mask);
+  if (serialized) {
+    const uint32_t tpv = (layer == VBX_LAYER_TSDF) ? 3u : 1u;
+    const dim3 grid(grid_for((uint64_t)tpv * c->vox_per_block, 256), (unsigned int)m);
+    k_serialize_blocks<<<grid, 256, 0, s>>>(layer, reinterpret_cast<const uint32_t*>(pool), c->mirror_slots, (uint32_t)m,
+                                            (uint32_t)c->vox_per_block, static_cast<uint32_t*>(c->mirror_dev), flags,
+                                            (uint8_t)clear_mask);
+  } else {
+    k_gather_blocks<<<(unsigned int)(m * 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(pool), c->mirror_slots,
+                                                           (uint32_t)m, (uint32_t)(raw_bytes / 16),
+                                                           reinterpret_cast<uint4*>(c->mirror_dev), flags,
+                                                           (uint8_t)clear_mask);
+  }
   // straight into the caller's buffer when it is page-locked (vbx_host_alloc / cudaHostRegister),
   // otherwise through the engine's page-locked staging buffer
   cudaPointerAttributes attr;

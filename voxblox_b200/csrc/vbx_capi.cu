@@ -23,7 +23,7 @@ int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_
                uint32_t* vals_out);
 int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out);
 int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const void* voxels,
-                  const uint8_t* updated_bits);
+                  const uint8_t* updated_bits, int serialized);
 int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m);
 int clear_layer(vbx_ctx* c, int layer);
 int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* xyz, const uint8_t* rgba,
@@ -629,7 +629,25 @@ int vbx_mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, 
   VBX_DRAIN(c);
   *n = 0;
   if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
-  return mirror_updated(c, layer, updated_mask, clear_mask, idx3, voxels, updated_bits, cap, n);
+  return mirror_updated(c, layer, updated_mask, clear_mask, idx3, voxels, updated_bits, cap, n, 0);
+}
+
+int vbx_serialize_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, uint32_t* words,
+                          uint8_t* updated_bits, uint64_t cap, uint64_t* n) {
+  if (!c || !n || (cap && (!idx3 || !words))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  *n = 0;
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
+  return mirror_updated(c, layer, updated_mask, clear_mask, idx3, words, updated_bits, cap, n, 1);
+}
+
+int vbx_deserialize_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const uint32_t* words,
+                           const uint8_t* updated_bits) {
+  if (!c || (m && (!idx3 || !words))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  return upload_blocks(c, layer, idx3, m, words, updated_bits, 1);
 }
 
 int vbx_clear_updated(vbx_ctx* c, int layer, int updated_mask) {
@@ -651,7 +669,7 @@ int vbx_upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, co
   if (!c || (m && (!idx3 || !voxels))) return fail(c, VBX_E_INVALID, "null argument");
   VBX_CUDA(c, cudaSetDevice(c->device));
   VBX_DRAIN(c);
-  return upload_blocks(c, layer, idx3, m, voxels, updated_bits);
+  return upload_blocks(c, layer, idx3, m, voxels, updated_bits, 0);
 }
 
 int vbx_remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {

@@ -218,7 +218,7 @@ int fail(vbx_ctx* c, int code, const std::string& msg);
 int cuda_fail(vbx_ctx* c, cudaError_t e, const char* what);
 int refresh_host_mirror(vbx_ctx* c);
 int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
-                   uint8_t* updated_bits, uint64_t cap, uint64_t* n);
+                   uint8_t* updated_bits, uint64_t cap, uint64_t* n, int serialized);
 int esdf_destroy(vbx_ctx* c);
 int drain_async(vbx_ctx* c);           // wait for every asynchronously submitted scan, collect its results
 int set_n_blocks(vbx_ctx* c, uint32_t n);
