@@ -192,6 +192,24 @@ VBX_API int vbx_serialize_updated(vbx_ctx* ctx, int layer, int updated_mask, int
  * block.cc:65-90,110-135); creates the blocks as needed. */
 VBX_API int vbx_deserialize_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m,
                            const uint32_t* words, const uint8_t* updated_bits);
+/* Layer files (.vxblx), written from / read into the device map:
+ * Layer::saveToFile(file_path, clear_file) (core/layer_inl.h:81-157) and
+ * io::LoadBlocksFromFile(file_path, kReplace, multiple_layer_support = true, layer)
+ * (io/layer_io_inl.h:13-90): varint message count, LayerProto header, one BlockProto per block
+ * (proto/voxblox/*.proto); loaded blocks get every updated bit (layer_inl.h:227).  A file may
+ * hold several layers (clear_file = 0 appends); the first compatible one is loaded. */
+VBX_API int vbx_save_layer(vbx_ctx* ctx, int layer, const char* path, int clear_file);
+VBX_API int vbx_load_layer(vbx_ctx* ctx, int layer, const char* path, uint64_t* n_blocks_loaded);
+/* Host-only: the protobuf wire bytes of Layer::getProto / Block::getProto (core/layer_inl.h:41-51,
+ * core/block_inl.h:73-109), and the BlockProto parser.  *n = bytes (words) needed; nothing is
+ * written if the buffer is too small. */
+VBX_API int vbx_proto_encode_layer(double voxel_size, uint32_t voxels_per_side, const char* type, uint8_t* out,
+                           uint64_t cap, uint64_t* n);
+VBX_API int vbx_proto_encode_block(int32_t voxels_per_side, double voxel_size, const double origin[3], int has_data,
+                           const uint32_t* words, uint64_t n_words, uint8_t* out, uint64_t cap, uint64_t* n);
+VBX_API int vbx_proto_decode_block(const uint8_t* msg, uint64_t len, int32_t* voxels_per_side, double* voxel_size,
+                           double origin[3], int* has_data, uint32_t* words, uint64_t cap_words,
+                           uint64_t* n_words);
 /* Host -> device: Layer::insertBlock / allocateBlockPtrByIndex + voxel copy
  * (core/layer.h:103-111,152-161); creates the block if needed. */
 VBX_API int vbx_upload_blocks(vbx_ctx* ctx, int layer, const int32_t* idx3, uint64_t m,

@@ -179,3 +179,72 @@ def test_serialized_blocks_match_reference_format():
     a = layer.getAllAllocatedBlocks()
     assert a.tobytes() == layer2.getAllAllocatedBlocks().tobytes()
     assert layer.getBlocks(a)[0].tobytes() == layer2.getBlocks(a)[0].tobytes()
+
+
+def test_save_and_load_layer_file(tmp_path):
+    """Layer::saveToFile / io::LoadBlocksFromFile through the device map: TSDF and ESDF layers in one
+    .vxblx file (clear_file = false appends, core/layer_inl.h:96-103), reloaded into fresh layers;
+    the file is also walked with a real protobuf parser."""
+    from tests.test_proto_io import _messages
+
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    esdf = vb.Layer(0.1, 16, voxel_type="esdf")
+    eint = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(min_distance_m=0.2), layer, esdf)
+    for s in scenes.c3_room_sequence(n_scans=2, width=96, height=72):
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    eint.updateFromTsdfLayer(True)
+    path = str(tmp_path / "map.vxblx")
+    assert layer.saveToFile(path, True)
+    assert esdf.saveToFile(path, False)
+    # walk the file with python protobuf
+    BlockProto, LayerProto = _messages()
+    data = open(path, "rb").read()
+
+    def varint(pos):
+        v, shift = 0, 0
+        while True:
+            b = data[pos]
+            pos += 1
+            v |= (b & 0x7F) << shift
+            shift += 7
+            if not b & 0x80:
+                return v, pos
+    pos = 0
+    idx, words, _ = layer.serializeUpdated(0, 0)
+    eidx, ewords, _ = esdf.serializeUpdated(0, 0)
+    for typ, want_idx, want_words in (("tsdf", idx, words), ("esdf", eidx, ewords)):
+        count, pos = varint(pos)
+        assert count == 1 + want_idx.shape[0]
+        size, pos = varint(pos)
+        lm = LayerProto()
+        lm.ParseFromString(data[pos:pos + size])
+        pos += size
+        assert lm.type == typ and lm.voxels_per_side == 16 and lm.voxel_size == float(np.float32(0.1))
+        for k in range(want_idx.shape[0]):
+            size, pos = varint(pos)
+            bm = BlockProto()
+            bm.ParseFromString(data[pos:pos + size])
+            pos += size
+            bs = np.float32(0.1) * np.float32(16)
+            assert (bm.origin_x, bm.origin_y, bm.origin_z) == tuple(float(np.float32(v) * bs) for v in want_idx[k])
+            assert bm.voxels_per_side == 16 and not bm.has_data
+            assert np.asarray(bm.voxel_data, dtype=np.uint32).tobytes() == want_words[k].tobytes()
+    assert pos == len(data)
+    # reload
+    layer2 = vb.Layer(0.1, 16)
+    vb.TsdfIntegratorFactory.create("merged", cfg, layer2)
+    esdf2 = vb.Layer(0.1, 16, voxel_type="esdf")
+    vb.EsdfIntegrator(vb.EsdfIntegratorConfig(min_distance_m=0.2), layer2, esdf2)
+    assert layer2.loadBlocksFromFile(path) == idx.shape[0]
+    assert esdf2.loadBlocksFromFile(path) == eidx.shape[0]     # second layer of the file
+    assert layer2.getAllAllocatedBlocks().tobytes() == idx.tobytes()
+    assert layer2.getBlocks(idx)[0].tobytes() == layer.getBlocks(idx)[0].tobytes()
+    assert (np.asarray(layer2.getBlocks(idx)[1]) == 7).all()   # updated().set(), layer_inl.h:227
+    assert esdf2.serializeUpdated(0, 0)[1].tobytes() == ewords.tobytes()
+    # an incompatible layer is refused (isCompatible, layer_inl.h:237-260)
+    other = vb.Layer(0.2, 16)
+    vb.TsdfIntegratorFactory.create("merged", cfg, other)
+    with pytest.raises(vb.VoxbloxError):
+        other.loadBlocksFromFile(path)

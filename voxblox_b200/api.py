@@ -114,7 +114,8 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
            "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
-           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks"]
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
+           "vbx_proto_encode_layer", "vbx_proto_encode_block", "vbx_proto_decode_block"]
 
 _lib = None
 
@@ -173,6 +174,16 @@ def load_library():
     lib.vbx_serialize_updated.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, C.POINTER(u64)]
     lib.vbx_deserialize_blocks.restype = i32
     lib.vbx_deserialize_blocks.argtypes = [vp, i32, vp, u64, vp, vp]
+    lib.vbx_save_layer.restype = i32
+    lib.vbx_save_layer.argtypes = [vp, i32, C.c_char_p, i32]
+    lib.vbx_load_layer.restype = i32
+    lib.vbx_load_layer.argtypes = [vp, i32, C.c_char_p, C.POINTER(u64)]
+    lib.vbx_proto_encode_layer.restype = i32
+    lib.vbx_proto_encode_layer.argtypes = [C.c_double, C.c_uint32, C.c_char_p, vp, u64, C.POINTER(u64)]
+    lib.vbx_proto_encode_block.restype = i32
+    lib.vbx_proto_encode_block.argtypes = [i32, C.c_double, vp, i32, vp, u64, vp, u64, C.POINTER(u64)]
+    lib.vbx_proto_decode_block.restype = i32
+    lib.vbx_proto_decode_block.argtypes = [vp, u64, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
     lib.vbx_esdf_update_blocks.restype = i32
     lib.vbx_esdf_update_blocks.argtypes = [vp, vp, u64, i32]
     lib.vbx_esdf_set_max_distance.restype = i32
@@ -368,6 +379,21 @@ class Layer:
         upd = None if updated_bits is None else np.ascontiguousarray(updated_bits, dtype=np.uint8)
         ctx.check(ctx.lib.vbx_deserialize_blocks(ctx.handle, self._layer_id, idx.ctypes.data, idx.shape[0], w.ctypes.data,
                                                  None if upd is None else upd.ctypes.data), "vbx_deserialize_blocks")
+
+    def saveToFile(self, file_path: str, clear_file: bool = True) -> bool:  # core/layer_inl.h:81-86
+        ctx = self._bound()
+        ctx.check(ctx.lib.vbx_save_layer(ctx.handle, self._layer_id, str(file_path).encode(), int(bool(clear_file))),
+                  "saveToFile")
+        return True
+
+    def loadBlocksFromFile(self, file_path: str) -> int:
+        """io::LoadBlocksFromFile(file_path, kReplace, multiple_layer_support=true, this)
+        (io/layer_io_inl.h:13-90); returns the number of blocks loaded."""
+        ctx = self._bound()
+        n = C.c_uint64(0)
+        ctx.check(ctx.lib.vbx_load_layer(ctx.handle, self._layer_id, str(file_path).encode(), C.byref(n)),
+                  "LoadBlocksFromFile")
+        return int(n.value)
 
     def getBlockByIndex(self, index: Sequence[int]) -> np.ndarray:
         """core/layer.h:55-62: LOG(FATAL) "Accessed unallocated block" -> VoxbloxError."""
