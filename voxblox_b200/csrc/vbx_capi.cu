@@ -86,26 +86,49 @@ void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S) {
   }
 }
 
+void select_set(vbx_ctx* c, int k) {
+  const vbx_ctx::ScratchSet& S = c->set[k];
+  c->ray_p = S.ray_p;
+  c->ray_a = S.ray_a;
+  c->ray_c = S.ray_c;
+  c->ray_list = S.ray_list;
+  c->cnt = S.cnt;
+  c->off = S.off;
+  c->d_state = S.d_state;
+  c->h_state = S.h_state;
+  c->d_xyz = S.d_xyz;
+  c->d_rgba = S.d_rgba;
+  c->pkeys[0] = S.pkeys0;
+  for (int i = 0; i < 2; ++i) {
+    c->ckeys[i] = S.ckeys[i];
+    c->cvals[i] = S.cvals[i];
+  }
+  c->sort_plan[1] = S.sort_plan1;
+  c->sort_status[1] = S.sort_status1;
+}
+
+void select_lane(vbx_ctx* c, int l) {
+  const vbx_ctx::FrontLane& F = c->lane[l];
+  c->pkeys[1] = F.pkeys1;
+  c->pvals[0] = F.pvals[0];
+  c->pvals[1] = F.pvals[1];
+  c->sort_plan[0] = F.sort_plan0;
+  c->sort_status[0] = F.sort_status0;
+  c->scan_status = F.scan_status;
+}
+
 int drain_async(vbx_ctx* c) {
-  for (int k = 0; k < 2; ++k) {
-    vbx_ctx::ScratchSet& S = c->set[(c->async_seq + k) & 1];  // older submission first
+  for (int k = 0; k < vbx_ctx::kSets; ++k) {
+    vbx_ctx::ScratchSet& S = c->set[(c->async_seq + k) % vbx_ctx::kSets];  // oldest submission first
     if (!S.in_flight) continue;
     VBX_CUDA(c, cudaEventSynchronize(S.back_done));
     harvest_async(c, S);
   }
-  // synchronous calls use hand-off set 0
-  c->ray_p = c->set[0].ray_p;
-  c->ray_a = c->set[0].ray_a;
-  c->ray_c = c->set[0].ray_c;
-  c->ray_list = c->set[0].ray_list;
-  c->cnt = c->set[0].cnt;
-  c->off = c->set[0].off;
-  c->d_state = c->set[0].d_state;
-  c->h_state = c->set[0].h_state;
-  c->d_xyz = c->set[0].d_xyz;
-  c->d_rgba = c->set[0].d_rgba;
-  c->pkeys[0] = c->set[0].pkeys0;
+  // synchronous calls use hand-off set 0 and front lane 0 on the main stream
+  select_set(c, 0);
+  select_lane(c, 0);
   c->stream = c->stream_main;
+  c->apply_stream = nullptr;
   if (c->deferred_rc) {
     const int rc = c->deferred_rc;
     c->err = c->deferred_msg;
@@ -188,7 +211,6 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   } while (0)
   CK(cudaSetDevice(c->device));
   CK(cudaStreamCreateWithFlags(&c->stream_main, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->stream_f, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->stream_c, cudaStreamNonBlocking));
   c->stream = c->stream_main;
   CK(cudaEventCreate(&c->ev0));
@@ -271,7 +293,7 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->d_nblocks, 2));
   CK(cudaMemsetAsync(c->d_nblocks, 0, 2 * sizeof(uint32_t), c->stream));
   {
-    // hand-off set 0 is the buffers above, set 1 a second copy (asynchronous submission)
+    // hand-off set 0 / front lane 0 are the buffers above; the others are allocated by ensure_async
     vbx_ctx::ScratchSet& a = c->set[0];
     a.ray_p = c->ray_p;
     a.ray_a = c->ray_a;
@@ -284,47 +306,94 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     a.d_xyz = c->d_xyz;
     a.d_rgba = c->d_rgba;
     a.pkeys0 = c->pkeys[0];
-    vbx_ctx::ScratchSet& b = c->set[1];
-    CK(dmalloc(&b.ray_p, np));
-    CK(dmalloc(&b.ray_a, np));
-    CK(dmalloc(&b.ray_c, np));
-    CK(dmalloc(&b.ray_list, np));
-    CK(dmalloc(&b.cnt, np + 1));
-    CK(dmalloc(&b.off, np + 1));
-    CK(dmalloc(&b.d_state, 1));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&b.h_state), sizeof(ScanState)));
-    CK(dmalloc(&b.d_xyz, 3 * np));
-    CK(dmalloc(&b.d_rgba, 4 * np));
-    CK(dmalloc(&b.pkeys0, np));
     for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&c->set[i].copy_done, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&c->set[i].front_done, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&c->set[i].back_done, cudaEventDisableTiming));
+      a.ckeys[i] = c->ckeys[i];
+      a.cvals[i] = c->cvals[i];
     }
+    a.sort_plan1 = c->sort_plan[1];
+    a.sort_status1 = c->sort_status[1];
+    vbx_ctx::FrontLane& f = c->lane[0];
+    f.pkeys1 = c->pkeys[1];
+    f.pvals[0] = c->pvals[0];
+    f.pvals[1] = c->pvals[1];
+    f.sort_plan0 = c->sort_plan[0];
+    f.sort_status0 = c->sort_status[0];
+    f.scan_status = c->scan_status;
   }
   CK(cudaStreamSynchronize(c->stream));
 #undef CK
   return VBX_OK;
 }
 
+}  // extern "C" (reopened below)
+
+namespace vbx {
+// First asynchronous submission: the remaining hand-off sets, the second front lane, streams, events.
+int ensure_async(vbx_ctx* c) {
+  if (c->async_ready) return VBX_OK;
+#define CK(expr)                                           \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
+  } while (0)
+  const size_t np = c->max_points;
+  CK(cudaStreamCreateWithFlags(&c->stream_e, cudaStreamNonBlocking));
+  for (int l = 0; l < vbx_ctx::kLanes; ++l) {
+    vbx_ctx::FrontLane& F = c->lane[l];
+    CK(cudaStreamCreateWithFlags(&F.stream, cudaStreamNonBlocking));
+    if (l == 0) continue;
+    CK(dmalloc(&F.pkeys1, np));
+    CK(dmalloc(&F.pvals[0], np));
+    CK(dmalloc(&F.pvals[1], np));
+    CK(dmalloc(&F.sort_plan0, 1));
+    CK(dmalloc(&F.sort_status0, (size_t)8 * c->sort_tiles_cap[0] * kRadix));
+    CK(dmalloc(&F.scan_status, (np + 1) / kScanTile + 4));
+  }
+  for (int k = 0; k < vbx_ctx::kSets; ++k) {
+    vbx_ctx::ScratchSet& S = c->set[k];
+    CK(cudaEventCreateWithFlags(&S.copy_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.front_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.sorted, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.back_done, cudaEventDisableTiming));
+    if (k == 0) continue;
+    CK(dmalloc(&S.ray_p, np));
+    CK(dmalloc(&S.ray_a, np));
+    CK(dmalloc(&S.ray_c, np));
+    CK(dmalloc(&S.ray_list, np));
+    CK(dmalloc(&S.cnt, np + 1));
+    CK(dmalloc(&S.off, np + 1));
+    CK(dmalloc(&S.d_state, 1));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&S.h_state), sizeof(ScanState)));
+    CK(dmalloc(&S.d_xyz, 3 * np));
+    CK(dmalloc(&S.d_rgba, 4 * np));
+    CK(dmalloc(&S.pkeys0, np));
+    for (int i = 0; i < 2; ++i) {
+      CK(dmalloc(&S.ckeys[i], (size_t)c->max_updates));
+      CK(dmalloc(&S.cvals[i], (size_t)c->max_updates));
+    }
+    CK(dmalloc(&S.sort_plan1, 1));
+    CK(dmalloc(&S.sort_status1, (size_t)4 * c->sort_tiles_cap[1] * kRadix));
+  }
+#undef CK
+  c->async_ready = true;
+  return VBX_OK;
+}
+}  // namespace vbx
+
+extern "C" {
+
 void vbx_destroy(vbx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream_main) cudaStreamSynchronize(c->stream_main);
-  if (c->stream_f) cudaStreamSynchronize(c->stream_f);
   if (c->stream_c) cudaStreamSynchronize(c->stream_c);
-  // restore the aliases of hand-off set 0 before freeing
-  c->ray_p = c->set[0].ray_p;
-  c->ray_a = c->set[0].ray_a;
-  c->ray_c = c->set[0].ray_c;
-  c->ray_list = c->set[0].ray_list;
-  c->cnt = c->set[0].cnt;
-  c->off = c->set[0].off;
-  c->d_state = c->set[0].d_state;
-  c->h_state = c->set[0].h_state;
-  c->d_xyz = c->set[0].d_xyz;
-  c->d_rgba = c->set[0].d_rgba;
-  c->pkeys[0] = c->set[0].pkeys0;
+  if (c->stream_e) cudaStreamSynchronize(c->stream_e);
+  for (int l = 0; l < vbx_ctx::kLanes; ++l) {
+    if (c->lane[l].stream) cudaStreamSynchronize(c->lane[l].stream);
+  }
+  // restore the aliases of hand-off set 0 / lane 0 before freeing
+  select_set(c, 0);
+  select_lane(c, 0);
   c->stream = c->stream_main;
   esdf_destroy(c);
   Tables& t = c->tab;
@@ -335,21 +404,38 @@ void vbx_destroy(vbx_ctx* c) {
                   c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
                   c->ray_list,    c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
                   c->sort_status[0], c->sort_status[1], c->scan_status, c->long_end, c->long_state,
-                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w, c->d_nblocks, c->set[1].ray_p,
-                  c->set[1].ray_a, c->set[1].ray_c, c->set[1].ray_list, c->set[1].cnt, c->set[1].off,
-                  c->set[1].d_state, c->set[1].d_xyz, c->set[1].d_rgba, c->set[1].pkeys0};
+                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w, c->d_nblocks};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }
   if (c->h_state) cudaFreeHost(c->h_state);
-  if (c->set[1].h_state) cudaFreeHost(c->set[1].h_state);
   if (c->mirror_dev) cudaFree(c->mirror_dev);
   if (c->mirror_host) cudaFreeHost(c->mirror_host);
   if (c->mirror_slots) cudaFree(c->mirror_slots);
-  for (int i = 0; i < 2; ++i) {
-    if (c->set[i].copy_done) cudaEventDestroy(c->set[i].copy_done);
-    if (c->set[i].front_done) cudaEventDestroy(c->set[i].front_done);
-    if (c->set[i].back_done) cudaEventDestroy(c->set[i].back_done);
+  for (int k = 0; k < vbx_ctx::kSets; ++k) {
+    vbx_ctx::ScratchSet& S = c->set[k];
+    if (k > 0) {
+      void* sp[] = {S.ray_p, S.ray_a, S.ray_c, S.ray_list, S.cnt, S.off, S.d_state, S.d_xyz, S.d_rgba, S.pkeys0,
+                    S.ckeys[0], S.ckeys[1], S.cvals[0], S.cvals[1], S.sort_plan1, S.sort_status1};
+      for (void* p : sp) {
+        if (p) cudaFree(p);
+      }
+      if (S.h_state) cudaFreeHost(S.h_state);
+    }
+    if (S.copy_done) cudaEventDestroy(S.copy_done);
+    if (S.front_done) cudaEventDestroy(S.front_done);
+    if (S.sorted) cudaEventDestroy(S.sorted);
+    if (S.back_done) cudaEventDestroy(S.back_done);
+  }
+  for (int l = 0; l < vbx_ctx::kLanes; ++l) {
+    vbx_ctx::FrontLane& F = c->lane[l];
+    if (l > 0) {
+      void* fp[] = {F.pkeys1, F.pvals[0], F.pvals[1], F.sort_plan0, F.sort_status0, F.scan_status};
+      for (void* p : fp) {
+        if (p) cudaFree(p);
+      }
+    }
+    if (F.stream) cudaStreamDestroy(F.stream);
   }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -359,7 +445,7 @@ void vbx_destroy(vbx_ctx* c) {
     if (c->sev[i]) cudaEventDestroy(c->sev[i]);
   }
   if (c->stream_main) cudaStreamDestroy(c->stream_main);
-  if (c->stream_f) cudaStreamDestroy(c->stream_f);
+  if (c->stream_e) cudaStreamDestroy(c->stream_e);
   if (c->stream_c) cudaStreamDestroy(c->stream_c);
   delete c;
 }
@@ -520,9 +606,7 @@ int vbx_sync(vbx_ctx* c) {
   if (!c) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
   VBX_DRAIN(c);
-  VBX_CUDA(c, cudaStreamSynchronize(c->stream_c));
-  VBX_CUDA(c, cudaStreamSynchronize(c->stream_f));
-  VBX_CUDA(c, cudaStreamSynchronize(c->stream_main));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream_main));  // (the drain above already waited for every queued scan)
   return VBX_OK;
 }
 

@@ -104,10 +104,9 @@ __host__ __device__ inline uint32_t hash64(uint64_t k) {
 
 struct vbx_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;      // the stream the next launch goes to (main, or stream_f while a front half is enqueued)
+  cudaStream_t stream = nullptr;      // the stream the next launch goes to (main, or a pipeline stage's stream while one is enqueued)
   cudaStream_t stream_main = nullptr; // back halves, ESDF, block management, synchronous calls
   cudaStream_t stream_c = nullptr;    // host-to-device cloud copies of asynchronously submitted scans
-  cudaStream_t stream_f = nullptr;    // front halves of asynchronously submitted scans
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   vbx_tsdf_config cfg;
   vbx_engine_options opt;
@@ -157,8 +156,13 @@ struct vbx_ctx {
   uint32_t n_blocks = 0;              // pool slots in use (host copy, exact after a drain)
   uint32_t* d_nblocks = nullptr;      // [2] device copy, ping-pong: k_assign reads [nb_cur], writes [nb_cur ^ 1]
   int nb_cur = 0;
-  // Asynchronous submission: two scans can be in flight, the front half (map independent) of
-  // scan i+1 overlapping the back half of scan i.  Each owns one set of hand-off buffers.
+  // Asynchronous submission (vbx_tsdf_integrate_async): a scan passes through three stages on
+  // separate streams -- front half (keys, bundle sort, bundle fold, offsets; does not touch the map)
+  // on one of kLanes front streams, ray walk + block creation + record sort on stream_e, apply on
+  // the main stream -- so up to kSets scans are in flight, each owning one set of hand-off
+  // buffers.  Map-touching stages run in submission order.  Set 0 / lane 0 are the buffers the
+  // synchronous calls use; the others are allocated on the first asynchronous submission.
+  static constexpr int kSets = 4, kLanes = 2;
   struct ScratchSet {
     float4* ray_p = nullptr;
     float4* ray_a = nullptr;
@@ -171,11 +175,27 @@ struct vbx_ctx {
     float* d_xyz = nullptr;
     uint8_t* d_rgba = nullptr;
     uint64_t* pkeys0 = nullptr;  // sorted bundle keys (read again by the ray walk)
-    cudaEvent_t copy_done = nullptr, front_done = nullptr, back_done = nullptr;
+    uint32_t* ckeys[2] = {nullptr, nullptr};  // update records (written by the walk, read by apply)
+    uint32_t* cvals[2] = {nullptr, nullptr};
+    vbx::SortPlan* sort_plan1 = nullptr;
+    uint32_t* sort_status1 = nullptr;
+    cudaEvent_t copy_done = nullptr, front_done = nullptr, sorted = nullptr, back_done = nullptr;
     bool in_flight = false;
     int kind = 0;
     uint64_t launches = 0;
-  } set[2];
+  } set[kSets];
+  struct FrontLane {  // scratch private to one front-half stream
+    cudaStream_t stream = nullptr;
+    uint64_t* pkeys1 = nullptr;
+    uint32_t* pvals[2] = {nullptr, nullptr};
+    vbx::SortPlan* sort_plan0 = nullptr;
+    uint32_t* sort_status0 = nullptr;
+    uint32_t* scan_status = nullptr;
+  } lane[kLanes];
+  bool async_ready = false;
+  cudaStream_t stream_e = nullptr;      // ray walk + block creation + record sort of asynchronously submitted scans
+  cudaStream_t apply_stream = nullptr;  // non-null while an asynchronous back half is enqueued: apply goes here
+  cudaEvent_t sorted_event = nullptr;   // ... after this event
   uint64_t async_seq = 0;
   int deferred_rc = 0;
   bool force_wide_keys = false;  // set once an asynchronous scan overflowed the compact bundle keys
@@ -220,6 +240,9 @@ int refresh_host_mirror(vbx_ctx* c);
 int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
                    uint8_t* updated_bits, uint64_t cap, uint64_t* n, int serialized);
 int esdf_destroy(vbx_ctx* c);
+int ensure_async(vbx_ctx* c);          // allocate the extra hand-off sets / front lanes
+void select_set(vbx_ctx* c, int k);     // point the context's scratch fields at hand-off set k / front lane l
+void select_lane(vbx_ctx* c, int l);
 int drain_async(vbx_ctx* c);           // wait for every asynchronously submitted scan, collect its results
 int set_n_blocks(vbx_ctx* c, uint32_t n);
 void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S);  // collect a finished asynchronous scan's results

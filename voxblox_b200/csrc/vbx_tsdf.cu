@@ -1222,6 +1222,13 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
     rv.total_fixed = 0;
   }
   mk.mark(6);
+  if (c->apply_stream) {
+    // pipelined submission: the apply kernels run on their own stream behind the sort, so the
+    // next scan's ray walk can start while this scan's voxels are still being written
+    VBX_CUDA(c, cudaEventRecord(c->sorted_event, s));
+    VBX_CUDA(c, cudaStreamWaitEvent(c->apply_stream, c->sorted_event, 0));
+    s = c->apply_stream;
+  }
   const unsigned int g_short = c->use_cub ? grid_for(K, 256) : 148 * 8;
   LongRuns lr;
   lr.start = c->long_list;
@@ -1438,13 +1445,16 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
 }
 
 // ------------------------------------------------------------- asynchronous submission
-// integratePointCloud without the host round trip: the call enqueues the scan and returns.  The
-// front half (keys, sort, bundle fold, record offsets: nothing that reads or writes the map) goes
-// to stream_f, the back half (ray walk, block creation, record sort, apply) to the main stream
-// behind an event.  Two hand-off sets alternate, so the front half of scan i+1 overlaps the back
-// half of scan i; map updates still happen strictly in submission order (one stream).  Results
-// (counters, errors) of scan i are collected when its hand-off set is reused (scan i+2) or at the
-// next synchronous call / vbx_sync.
+// integratePointCloud without the host round trip: the call enqueues the scan and returns.  A scan
+// passes through three stages on separate streams:
+//   front   keys, bundle sort, bundle fold, record offsets -- touches nothing of the map; two front
+//           lanes alternate, so two front halves can run side by side
+//   walk    ray walk with block creation, slot assignment, record sort (stream_e)
+//   apply   the per-voxel updates (main stream)
+// Stages that touch the map run in submission order (one stream each; the walk of scan i+1 only
+// inserts new hash entries and never moves existing ones, so it can overlap the apply of scan i).
+// Up to kSets scans are in flight, each with its own hand-off buffers; results (counters, errors)
+// of a scan are collected when its set is reused or at the next synchronous call / vbx_sync.
 int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* xyz, const uint8_t* rgba,
                     uint64_t n64, int freespace, int on_device) {
   if (kind < VBX_SIMPLE || kind > VBX_FAST) return fail(c, VBX_E_INVALID, "Unknown TSDF integrator type");
@@ -1465,33 +1475,29 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     }
     return integrate_device(c, kind, q, t, dx, dr, n64, freespace);
   }
+  if (int rc = ensure_async(c)) return rc;
   const uint32_t n = (uint32_t)n64;
-  vbx_ctx::ScratchSet& S = c->set[c->async_seq & 1];
-  if (S.in_flight) {  // bounded run-ahead: at most two scans in flight
+  const int k = (int)(c->async_seq % vbx_ctx::kSets);
+  vbx_ctx::ScratchSet& S = c->set[k];
+  vbx_ctx::FrontLane& F = c->lane[c->async_seq % vbx_ctx::kLanes];
+  if (S.in_flight) {  // bounded run-ahead: wait for the scan that used this hand-off set
     VBX_CUDA(c, cudaEventSynchronize(S.back_done));
     harvest_async(c, S);
   }
-  // this submission's hand-off buffers
-  c->ray_p = S.ray_p;
-  c->ray_a = S.ray_a;
-  c->ray_c = S.ray_c;
-  c->ray_list = S.ray_list;
-  c->cnt = S.cnt;
-  c->off = S.off;
-  c->d_state = S.d_state;
-  c->h_state = S.h_state;
-  c->pkeys[0] = S.pkeys0;
+  select_set(c, k);
+  select_lane(c, (int)(c->async_seq % vbx_ctx::kLanes));
   ScanParams P;
   fill_params(c, kind, q, t, n, freespace, P);
   uint64_t launches = 0;
   Marks mk;
   mk.c = c;
-  mk.s = c->stream_f;
+  mk.s = F.stream;
   const bool profiling = c->profiling;
-  c->profiling = false;  // stage events would serialise the two streams
+  c->profiling = false;  // stage events would serialise the streams
   int rc = VBX_OK;
-  // ---- front half on stream_f
-  c->stream = c->stream_f;
+  // ---- front half on this scan's front lane
+  c->stream = F.stream;
+  c->apply_stream = nullptr;
   const float* dx = xyz;
   const uint8_t* dr = rgba;
   if (!on_device) {
@@ -1499,7 +1505,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     if (cudaMemcpyAsync(S.d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream_c) != cudaSuccess ||
         cudaMemcpyAsync(S.d_rgba, rgba, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream_c) != cudaSuccess ||
         cudaEventRecord(S.copy_done, c->stream_c) != cudaSuccess ||
-        cudaStreamWaitEvent(c->stream_f, S.copy_done, 0) != cudaSuccess) {
+        cudaStreamWaitEvent(F.stream, S.copy_done, 0) != cudaSuccess) {
       rc = fail(c, VBX_E_CUDA, "asynchronous host-to-device copy failed");
     }
     dx = S.d_xyz;
@@ -1507,18 +1513,20 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   }
   const uint32_t* keys32 = nullptr;
   const uint64_t* keys64 = nullptr;
-  if (rc == VBX_OK && cudaMemsetAsync(S.d_state, 0, sizeof(ScanState), c->stream_f) != cudaSuccess) {
+  if (rc == VBX_OK && cudaMemsetAsync(S.d_state, 0, sizeof(ScanState), F.stream) != cudaSuccess) {
     rc = fail(c, VBX_E_CUDA, "cudaMemsetAsync");
   }
   if (rc == VBX_OK) {
     rc = P.wide_keys ? front_half<uint64_t>(c, P, dx, dr, nullptr, mk, &launches, &keys64)
                      : front_half<uint32_t>(c, P, dx, dr, nullptr, mk, &launches, &keys32);
   }
-  if (rc == VBX_OK && cudaEventRecord(S.front_done, c->stream_f) != cudaSuccess) rc = fail(c, VBX_E_CUDA, "cudaEventRecord");
-  // ---- back half on the main stream
-  c->stream = c->stream_main;
-  mk.s = c->stream_main;
-  if (rc == VBX_OK && cudaStreamWaitEvent(c->stream_main, S.front_done, 0) != cudaSuccess) {
+  if (rc == VBX_OK && cudaEventRecord(S.front_done, F.stream) != cudaSuccess) rc = fail(c, VBX_E_CUDA, "cudaEventRecord");
+  // ---- walk + record sort on stream_e, apply on the main stream
+  c->stream = c->stream_e;
+  c->apply_stream = c->stream_main;
+  c->sorted_event = S.sorted;
+  mk.s = c->stream_e;
+  if (rc == VBX_OK && cudaStreamWaitEvent(c->stream_e, S.front_done, 0) != cudaSuccess) {
     rc = fail(c, VBX_E_CUDA, "cudaStreamWaitEvent");
   }
   if (rc == VBX_OK) {
@@ -1530,6 +1538,8 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     rc = fail(c, VBX_E_CUDA, "enqueueing the result read-back failed");
   }
   c->profiling = profiling;
+  c->stream = c->stream_main;
+  c->apply_stream = nullptr;
   if (rc != VBX_OK) return rc;
   S.in_flight = true;
   S.kind = kind;
