@@ -129,6 +129,7 @@ int drain_async(vbx_ctx* c) {
   select_lane(c, 0);
   c->stream = c->stream_main;
   c->apply_stream = nullptr;
+  c->sort_stream = nullptr;
   if (c->deferred_rc) {
     const int rc = c->deferred_rc;
     c->err = c->deferred_msg;
@@ -338,6 +339,7 @@ int ensure_async(vbx_ctx* c) {
   } while (0)
   const size_t np = c->max_points;
   CK(cudaStreamCreateWithFlags(&c->stream_e, cudaStreamNonBlocking));
+  for (int i = 0; i < vbx_ctx::kSortStreams; ++i) CK(cudaStreamCreateWithFlags(&c->stream_s[i], cudaStreamNonBlocking));
   for (int l = 0; l < vbx_ctx::kLanes; ++l) {
     vbx_ctx::FrontLane& F = c->lane[l];
     CK(cudaStreamCreateWithFlags(&F.stream, cudaStreamNonBlocking));
@@ -353,6 +355,7 @@ int ensure_async(vbx_ctx* c) {
     vbx_ctx::ScratchSet& S = c->set[k];
     CK(cudaEventCreateWithFlags(&S.copy_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&S.front_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.walked, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&S.sorted, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&S.back_done, cudaEventDisableTiming));
     if (k == 0) continue;
@@ -388,6 +391,9 @@ void vbx_destroy(vbx_ctx* c) {
   if (c->stream_main) cudaStreamSynchronize(c->stream_main);
   if (c->stream_c) cudaStreamSynchronize(c->stream_c);
   if (c->stream_e) cudaStreamSynchronize(c->stream_e);
+  for (int i = 0; i < vbx_ctx::kSortStreams; ++i) {
+    if (c->stream_s[i]) cudaStreamSynchronize(c->stream_s[i]);
+  }
   for (int l = 0; l < vbx_ctx::kLanes; ++l) {
     if (c->lane[l].stream) cudaStreamSynchronize(c->lane[l].stream);
   }
@@ -424,6 +430,7 @@ void vbx_destroy(vbx_ctx* c) {
     }
     if (S.copy_done) cudaEventDestroy(S.copy_done);
     if (S.front_done) cudaEventDestroy(S.front_done);
+    if (S.walked) cudaEventDestroy(S.walked);
     if (S.sorted) cudaEventDestroy(S.sorted);
     if (S.back_done) cudaEventDestroy(S.back_done);
   }
@@ -446,6 +453,9 @@ void vbx_destroy(vbx_ctx* c) {
   }
   if (c->stream_main) cudaStreamDestroy(c->stream_main);
   if (c->stream_e) cudaStreamDestroy(c->stream_e);
+  for (int i = 0; i < vbx_ctx::kSortStreams; ++i) {
+    if (c->stream_s[i]) cudaStreamDestroy(c->stream_s[i]);
+  }
   if (c->stream_c) cudaStreamDestroy(c->stream_c);
   delete c;
 }

@@ -162,7 +162,7 @@ struct vbx_ctx {
   // the main stream -- so up to kSets scans are in flight, each owning one set of hand-off
   // buffers.  Map-touching stages run in submission order.  Set 0 / lane 0 are the buffers the
   // synchronous calls use; the others are allocated on the first asynchronous submission.
-  static constexpr int kSets = 4, kLanes = 2;
+  static constexpr int kSets = 6, kLanes = 3, kSortStreams = 2;
   struct ScratchSet {
     float4* ray_p = nullptr;
     float4* ray_a = nullptr;
@@ -179,7 +179,7 @@ struct vbx_ctx {
     uint32_t* cvals[2] = {nullptr, nullptr};
     vbx::SortPlan* sort_plan1 = nullptr;
     uint32_t* sort_status1 = nullptr;
-    cudaEvent_t copy_done = nullptr, front_done = nullptr, sorted = nullptr, back_done = nullptr;
+    cudaEvent_t copy_done = nullptr, front_done = nullptr, walked = nullptr, sorted = nullptr, back_done = nullptr;
     bool in_flight = false;
     int kind = 0;
     uint64_t launches = 0;
@@ -194,7 +194,10 @@ struct vbx_ctx {
   } lane[kLanes];
   bool async_ready = false;
   cudaStream_t stream_e = nullptr;      // ray walk + block creation + record sort of asynchronously submitted scans
-  cudaStream_t apply_stream = nullptr;  // non-null while an asynchronous back half is enqueued: apply goes here
+  cudaStream_t stream_s[kSortStreams] = {nullptr, nullptr};  // record sorts (set-private buffers: independent across scans)
+  cudaStream_t sort_stream = nullptr;   // non-null while an asynchronous back half is enqueued: the record sort goes here
+  cudaEvent_t walked_event = nullptr;   // ... after this event
+  cudaStream_t apply_stream = nullptr;  // ... and the apply kernels here
   cudaEvent_t sorted_event = nullptr;   // ... after this event
   uint64_t async_seq = 0;
   int deferred_rc = 0;

@@ -1209,6 +1209,14 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
     // K and the number of touched blocks are only known on the device: sort on every bit a
     // record key can have; passes whose digit is uniform are skipped on the device
     const int key_bits = 3 * c->L + bits_for(c->hcap - 1);
+    if (c->sort_stream) {
+      // pipelined submission: the record sort works on buffers private to this scan, so it leaves
+      // the walk stream (which the next scan's ray walk is waiting for)
+      VBX_CUDA(c, cudaEventRecord(c->walked_event, s));
+      VBX_CUDA(c, cudaStreamWaitEvent(c->sort_stream, c->walked_event, 0));
+      s = c->sort_stream;
+      c->stream = s;
+    }
     if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
                                      &c->d_state->total_updates, 0, key_bits, launches)) {
       return rc;
@@ -1449,7 +1457,8 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
 // passes through three stages on separate streams:
 //   front   keys, bundle sort, bundle fold, record offsets -- touches nothing of the map; two front
 //           lanes alternate, so two front halves can run side by side
-//   walk    ray walk with block creation, slot assignment, record sort (stream_e)
+//   walk    ray walk with block creation, slot assignment (stream_e)
+//   sort    record sort on scan-private buffers (two sort streams alternate)
 //   apply   the per-voxel updates (main stream)
 // Stages that touch the map run in submission order (one stream each; the walk of scan i+1 only
 // inserts new hash entries and never moves existing ones, so it can overlap the apply of scan i).
@@ -1498,6 +1507,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   // ---- front half on this scan's front lane
   c->stream = F.stream;
   c->apply_stream = nullptr;
+  c->sort_stream = nullptr;
   const float* dx = xyz;
   const uint8_t* dr = rgba;
   if (!on_device) {
@@ -1523,6 +1533,8 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   if (rc == VBX_OK && cudaEventRecord(S.front_done, F.stream) != cudaSuccess) rc = fail(c, VBX_E_CUDA, "cudaEventRecord");
   // ---- walk + record sort on stream_e, apply on the main stream
   c->stream = c->stream_e;
+  c->sort_stream = c->stream_s[c->async_seq % vbx_ctx::kSortStreams];
+  c->walked_event = S.walked;
   c->apply_stream = c->stream_main;
   c->sorted_event = S.sorted;
   mk.s = c->stream_e;
@@ -1540,6 +1552,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   c->profiling = profiling;
   c->stream = c->stream_main;
   c->apply_stream = nullptr;
+  c->sort_stream = nullptr;
   if (rc != VBX_OK) return rc;
   S.in_flight = true;
   S.kind = kind;
