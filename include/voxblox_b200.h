@@ -133,15 +133,17 @@ VBX_API int vbx_get_tsdf_config(const vbx_ctx* ctx, vbx_tsdf_config* out);
 VBX_API int vbx_tsdf_integrate(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
                        const float* xyz, const uint8_t* rgba, uint64_t n, int freespace);
 /* Asynchronous submission (no reference counterpart: its call is synchronous).  Enqueues the scan
- * and returns; up to two scans are in flight, the map-independent front half of scan i+1
- * (transform, bundle sort, bundle fold) overlapping the map-updating back half of scan i on a
- * second stream.  Map updates still happen strictly in submission order, so the result equals
- * the synchronous calls'.  Host buffers (inputs_on_device = 0) must be page-locked and stay
- * untouched until the scan completed (vbx_sync, or two submissions later).  Counters and errors
- * of a scan surface at the next synchronous call / vbx_sync (a failed scan is reported, not
- * retried: a clearing point beyond the compact key range -- 511 voxels -- drops that scan).
+ * and returns.  A scan passes through four stages on separate streams (front: transform, bundle
+ * sort, bundle fold -- walk: ray walk with block creation -- sort: update-record sort -- apply),
+ * so the stages of up to six consecutive scans overlap; stages that touch the map run strictly in
+ * submission order, and the result equals the synchronous calls' bit for bit.  Host buffers
+ * (inputs_on_device = 0) should be page-locked and must then stay untouched until the scan
+ * completed (vbx_sync, or six submissions later); pageable buffers are staged before the call
+ * returns and may be reused at once.  Counters and errors of a scan surface at the next
+ * synchronous call / vbx_sync (a failed scan is reported, not retried: a clearing point beyond
+ * the compact key range -- 511 voxels -- drops that scan and switches later ones to wide keys).
  * Configurations whose front half touches the map (Fast, anti-grazing, "sorted" order) fall back
- * to the synchronous path. */
+ * to the synchronous path.  The extra buffers are allocated on the first call. */
 VBX_API int vbx_tsdf_integrate_async(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3],
                              const float* xyz, const uint8_t* rgba, uint64_t n, int freespace,
                              int inputs_on_device);
