@@ -562,7 +562,8 @@ class TsdfIntegratorBase:
         self._ctx.check(self._ctx.lib.vbx_get_counters(self._ctx.handle, out.ctypes.data),
                         "vbx_get_counters")
         names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
-                 "blocks_allocated", "valid_points", "kernel_launches", "kernel_launches_total"]
+                 "blocks_allocated", "valid_points", "kernel_launches", "kernel_launches_total", "refolded_bundles",
+                 "refolded_points"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def lastDeviceMs(self) -> float:

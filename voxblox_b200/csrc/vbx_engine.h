@@ -60,7 +60,9 @@ struct ScanState {
   uint32_t n_ray_list;       // bundle heads (Merged)
   uint32_t n_long;           // voxel runs handed to k_apply_long
   uint32_t n_verify;         // work items of k_apply_verify
-  uint32_t pad_[3];
+  uint32_t n_refold;         // bundles folded a second time with IEEE division (diagnostic)
+  uint32_t refold_members;   // ... and the points they hold
+  uint32_t pad_[1];
 };
 
 // The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
@@ -221,7 +223,7 @@ struct vbx_ctx {
   uint32_t* esdf_seed_list = nullptr;
   float* esdf_seed_val = nullptr;
   uint32_t* esdf_touched = nullptr;
-  int esdf_grid_raise = 0, esdf_grid_lower = 0;
+  int esdf_grid_raise = 0, esdf_grid_lower = 0, esdf_sms = 0, esdf_ctas_wide = 1;
   // reporting
   uint64_t counters[16] = {0};
   uint64_t esdf_counters[16] = {0};

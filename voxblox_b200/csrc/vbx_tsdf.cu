@@ -235,12 +235,22 @@ __device__ bool fold_bundle(const ScanParams& P, const float* __restrict__ xyz, 
   bool in;
   F3 p = f3(0.f, 0.f, 0.f);
   uint32_t col = 0u;
+  // Three-deep load pipeline: while chunk c is folded, the points of chunk c+1 are gathered (their
+  // keys / point indices arrived one iteration ago) and the keys / indices of chunk c+2 are
+  // requested -- no load is waited for right after it was issued.
+  KeyT k_next;
+  uint32_t idx_next;
+  bool inb_next;
   {
-    // key and point-index loads are issued together; only the point gather depends on them
     const uint32_t jj = j0 + lane;
     const bool inb = jj < P.n;
     const KeyT kk = inb ? keys[jj] : (KeyT)~(KeyT)0;
     const uint32_t idx = inb ? vals[jj] : 0u;
+    j0 += 32;
+    const uint32_t jn = j0 + lane;
+    inb_next = jn < P.n;
+    k_next = inb_next ? keys[jn] : (KeyT)~(KeyT)0;
+    idx_next = inb_next ? vals[jn] : 0u;
     in = inb && kk == key;
     if (in) {
       p = load_point(xyz, idx);
@@ -252,17 +262,17 @@ __device__ bool fold_bundle(const ScanParams& P, const float* __restrict__ xyz, 
     const F3 pc = p;
     const uint32_t colc = col;
     const bool inc = in;
-    if (cnt == 32) {  // prefetch the next chunk while this one is folded
-      j0 += 32;
-      const uint32_t jj = j0 + lane;
-      const bool inb = jj < P.n;
-      const KeyT kk = inb ? keys[jj] : (KeyT)~(KeyT)0;
-      const uint32_t idx = inb ? vals[jj] : 0u;
-      in = inb && kk == key;
+    if (cnt == 32) {
+      in = inb_next && k_next == key;
       if (in) {
-        p = load_point(xyz, idx);
-        col = load_color(rgba, idx);
+        p = load_point(xyz, idx_next);
+        col = load_color(rgba, idx_next);
       }
+      j0 += 32;
+      const uint32_t jn = j0 + lane;
+      inb_next = jn < P.n;
+      k_next = inb_next ? keys[jn] : (KeyT)~(KeyT)0;
+      idx_next = inb_next ? vals[jn] : 0u;
     }
     const float w = inc ? point_weight(pc.z, P.use_const_weight != 0) : 0.f;
     // (1) the weight chain W <- W + w is the only part every member depends on.  Lane L needs
@@ -365,6 +375,16 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
     uint32_t mcol;
     if (fold_bundle<KeyT, false>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol)) {
       fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol);
+      if (lane == 0) {
+        atomicAdd(&st->n_refold, 1u);
+        uint32_t lo = i, hi = P.n;  // first sorted position with a larger key
+        const KeyT k = keys[i];
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (keys[mid] <= k) lo = mid + 1; else hi = mid;
+        }
+        atomicAdd(&st->refold_members, lo - i);
+      }
     }
     if (lane == 0) {
       const bool clearing = key_is_clearing(P, (uint64_t)keys[i]);
@@ -1446,6 +1466,8 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   c->counters[3] = c->h_state->n_voxels;
   c->counters[4] = n_touched;
   c->counters[5] = (uint64_t)c->h_state->n_new + new_blocks_first_attempt;
+  c->counters[9] = c->h_state->n_refold;
+  c->counters[10] = c->h_state->refold_members;
   c->counters[6] = (kind == VBX_MERGED) ? c->h_state->n_valid_points
                                         : (uint64_t)c->h_state->n_rays + c->h_state->n_clear_rays;
   c->counters[7] = launches;
