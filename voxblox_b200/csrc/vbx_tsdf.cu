@@ -355,46 +355,239 @@ __device__ __forceinline__ void store_ray(const ScanParams& P, uint32_t i, F3 po
   ray_c[i] = make_uint2(color, __float_as_uint(weight));
 }
 
-// One warp per bundle (integrateVoxel's merge, cc:384-407).
+// One chunk (up to 32 consecutive members of one bundle) handed from the producer warp to the
+// consumer warp of a pair through shared memory.
+struct ChunkDesc {
+  uint32_t live;   // members that carry weight, in list order
+  uint32_t head;   // sorted position of the bundle's first member
+  uint32_t flags;
+  float mw;        // merged weight after this chunk (final on the bundle's last chunk)
+};
+constexpr uint32_t kChunkFirst = 1u, kChunkLast = 2u, kChunkSuspect = 4u, kChunkEnd = 8u;
+
+// named barrier of one warp pair (ids 1 and 2; 0 is __syncthreads'); literal ids so that ptxas
+// reserves three barriers, not all sixteen
+__device__ __forceinline__ void pair_barrier(int pair_in_block) {
+  if (pair_in_block == 0) {
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+  } else {
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+  }
+}
+
+// The merge of integrateVoxel (cc:384-407): every bundle's points folded in list order.  The fold
+// is one dependent chain per bundle, so the kernel's duration is the largest bundle's chain (up to
+// ~3000 points on this workload).  Warps work in PAIRS on a stream of 32-member chunks:
+//   producer  loads the members (three-deep load pipeline), walks the weight chain W <- W + w
+//             (the only thing a chunk needs from its predecessor besides the running state),
+//             computes everything else that does not depend on the running mean -- p*w, W+w,
+//             RN(1/(W+w)), blendTwoColors' normalised weights -- and stages it per role
+//   consumer  runs the dependent chain state = (state*A + B) / C  over the staged operands
+// so the preparation of chunk c+1 overlaps the chain of chunk c (two shared-memory slots, one
+// named barrier per chunk), also across bundle boundaries.
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
 k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
         const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ray_list,
         float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c, uint32_t* __restrict__ cnt,
         ScanState* st) {
-  __shared__ float4 stage[4 * 32 * kStageStride];  // [warp in block][member][role]
+  __shared__ float4 stage[2][2][32 * kStageStride];  // [pair in block][slot][member][role]
+  __shared__ ChunkDesc desc[2][2];
   const int lane = threadIdx.x & 31;
-  float4* stage_warp = stage + (threadIdx.x >> 5) * (32 * kStageStride);
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int pair_in_block = warp_in_block >> 1;
+  const bool producer = (warp_in_block & 1) == 0;
+  const int bar_id = pair_in_block;
+  const uint32_t pair = blockIdx.x * 2u + (uint32_t)pair_in_block;
+  const uint32_t n_pairs = gridDim.x * 2u;
   const uint32_t n_bundles = st->n_ray_list;
-  for (uint32_t b = warp; b < n_bundles; b += n_warps) {
-    const uint32_t i = ray_list[b];
-    F3 mp;
-    float mw;
-    uint32_t mcol;
-    if (fold_bundle<KeyT, false>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol)) {
-      fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage_warp, &mp, &mw, &mcol);
-      if (lane == 0) {
-        atomicAdd(&st->n_refold, 1u);
-        uint32_t lo = i, hi = P.n;  // first sorted position with a larger key
-        const KeyT k = keys[i];
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (keys[mid] <= k) lo = mid + 1; else hi = mid;
+  uint32_t seq = 0;
+  if (producer) {
+    for (uint32_t b = pair; b < n_bundles; b += n_pairs) {
+      const uint32_t i = ray_list[b];
+      const KeyT key = keys[i];
+      const bool clearing = key_is_clearing(P, (uint64_t)key);
+      float mw = 0.0f;
+      bool done = false, first = true;
+      uint32_t j0 = i;
+      bool in;
+      F3 p = f3(0.f, 0.f, 0.f);
+      uint32_t col = 0u;
+      // three-deep load pipeline: while chunk c is prepared, the points of chunk c+1 are gathered
+      // (their keys / point indices arrived one iteration ago) and the keys of chunk c+2 requested
+      KeyT k_next;
+      uint32_t idx_next;
+      bool inb_next;
+      {
+        const uint32_t jj = j0 + lane;
+        const bool inb = jj < P.n;
+        const KeyT kk = inb ? keys[jj] : (KeyT)~(KeyT)0;
+        const uint32_t idx = inb ? vals[jj] : 0u;
+        j0 += 32;
+        const uint32_t jn = j0 + lane;
+        inb_next = jn < P.n;
+        k_next = inb_next ? keys[jn] : (KeyT)~(KeyT)0;
+        idx_next = inb_next ? vals[jn] : 0u;
+        in = inb && kk == key;
+        if (in) {
+          p = load_point(xyz, idx);
+          col = load_color(rgba, idx);
         }
-        atomicAdd(&st->refold_members, lo - i);
+      }
+      while (!done) {
+        const int n_in = __popc(__ballot_sync(0xffffffffu, in));  // members form a prefix
+        const F3 pc = p;
+        const uint32_t colc = col;
+        const bool inc = in;
+        if (n_in == 32) {
+          in = inb_next && k_next == key;
+          if (in) {
+            p = load_point(xyz, idx_next);
+            col = load_color(rgba, idx_next);
+          }
+          j0 += 32;
+          const uint32_t jn = j0 + lane;
+          inb_next = jn < P.n;
+          k_next = inb_next ? keys[jn] : (KeyT)~(KeyT)0;
+          idx_next = inb_next ? vals[jn] : 0u;
+        }
+        const float w = inc ? point_weight(pc.z, P.use_const_weight != 0) : 0.f;
+        // the weight chain: lane L needs the W its member sees = mw + w_0 + ... + w_{L-1} added in
+        // list order (members below kEpsilon are skipped, cc:391-393: adding +0.0f is the identity)
+        const float wl = (inc && !(w < VBX_EPS)) ? w : 0.f;
+        float wb = mw;
+#pragma unroll
+        for (int k = 0; k < 31; ++k) {
+          const float wk = __shfl_sync(0xffffffffu, wl, k);
+          if (k < lane) wb = fadd(wb, wk);
+        }
+        float mw_run = __shfl_sync(0xffffffffu, fadd(wb, wl), 31);
+        const float tot = fadd(wb, w);
+        const F3 pw = scale3(pc, w);
+        float w1 = 0.f, w2 = 0.f, rtot = 1.f;
+        bool bad = false;
+        if (wl != 0.f) {
+          w1 = fdiv(wb, tot);  // blendTwoColors' normalised weights, core/common.h:112-113
+          w2 = fdiv(w, tot);
+          bool ok;
+          rtot = recip_for_exact_div(tot, &ok);
+          bad = !ok;
+        }
+        unsigned live = __ballot_sync(0xffffffffu, wl != 0.f);
+        if (clearing && live) {  // "only take first point when clearing", cc:401-404
+          const int k = __ffs(live) - 1;
+          live = 1u << k;
+          mw_run = fadd(__shfl_sync(0xffffffffu, wb, k), __shfl_sync(0xffffffffu, w, k));
+          done = true;
+        }
+        if (n_in < 32) done = true;
+        const bool any_bad = __any_sync(0xffffffffu, bad);
+        // (the slot was released by the consumer two barriers ago)
+        const int slot = (int)(seq & 1u);
+        float4* st_row = stage[pair_in_block][slot] + lane * kStageStride;
+        st_row[0] = make_float4(wb, pw.x, tot, rtot);
+        st_row[1] = make_float4(wb, pw.y, tot, rtot);
+        st_row[2] = make_float4(wb, pw.z, tot, rtot);
+        st_row[3] = make_float4(w1, fmul((float)(int)(colc & 0xffu), w2), 1.f, 1.f);
+        st_row[4] = make_float4(w1, fmul((float)(int)((colc >> 8) & 0xffu), w2), 1.f, 1.f);
+        st_row[5] = make_float4(w1, fmul((float)(int)((colc >> 16) & 0xffu), w2), 1.f, 1.f);
+        st_row[6] = make_float4(w1, fmul((float)(int)(colc >> 24), w2), 1.f, 1.f);
+        st_row[7] = make_float4(0.f, 1.f, 1.f, 1.f);
+        if (lane == 0) {
+          ChunkDesc d;
+          d.live = live;
+          d.head = i;
+          d.flags = (first ? kChunkFirst : 0u) | (done ? kChunkLast : 0u) | (any_bad ? kChunkSuspect : 0u);
+          d.mw = mw_run;
+          desc[pair_in_block][slot] = d;
+        }
+        pair_barrier(bar_id);
+        ++seq;
+        first = false;
+        mw = mw_run;
       }
     }
     if (lane == 0) {
-      const bool clearing = key_is_clearing(P, (uint64_t)keys[i]);
-      const F3 pg = transform(P.T, mp);
-      store_ray(P, i, pg, mw, mcol, clearing, ray_p, ray_a, ray_c);
-      if (P.single_walk) {
-        Dda d;
-        dda_setup(d, P.origin, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc, true);
-        cnt[i] = d.len + 1u;  // RayCaster emits ray_length_in_steps_ + 1 voxels (integrator_utils.cc:111-125)
-        atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
+      ChunkDesc d;
+      d.live = 0u;
+      d.head = 0u;
+      d.flags = kChunkEnd;
+      d.mw = 0.f;
+      desc[pair_in_block][seq & 1u] = d;
+    }
+    pair_barrier(bar_id);
+  } else {
+    const int role = lane < 7 ? lane : 7;  // lanes 7.. mirror a benign slot
+    const bool is_mean = lane < 3;
+    float state = 0.f;
+    bool suspect = false;
+    for (;; ++seq) {
+      pair_barrier(bar_id);
+      const int slot = (int)(seq & 1u);
+      const ChunkDesc d = desc[pair_in_block][slot];
+      if (d.flags & kChunkEnd) break;
+      if (d.flags & kChunkFirst) {
+        state = 0.f;
+        suspect = false;
+      }
+      suspect |= (d.flags & kChunkSuspect) != 0u;
+      const float4* st_col = stage[pair_in_block][slot] + role;
+      if (d.live == 0xffffffffu) {
+        float4 cur = st_col[0];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float4 nxt = st_col[((k + 1) & 31) * kStageStride];
+          state = fold_step<false>(state, cur, is_mean, &suspect);
+          cur = nxt;
+        }
+      } else if (d.live) {
+        unsigned m = d.live;
+        float4 cur = st_col[(__ffs(m) - 1) * kStageStride];
+        while (m) {
+          m &= m - 1;
+          const float4 nxt = st_col[(m ? __ffs(m) - 1 : 0) * kStageStride];  // the next operand's load overlaps the step
+          state = fold_step<false>(state, cur, is_mean, &suspect);
+          cur = nxt;
+        }
+      }
+      if (d.flags & kChunkLast) {
+        const uint32_t i = d.head;
+        F3 mp;
+        float mw = d.mw;
+        uint32_t mcol;
+        if (__any_sync(0xffffffffu, suspect)) {
+          // the fast division met an operand it does not trust: fold this bundle again with the
+          // IEEE division (one warp, the slot just consumed as its staging area)
+          fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage[pair_in_block][slot], &mp, &mw, &mcol);
+          if (lane == 0) {
+            atomicAdd(&st->n_refold, 1u);
+            uint32_t lo = i, hi = P.n;  // first sorted position with a larger key
+            const KeyT k = keys[i];
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (keys[mid] <= k) lo = mid + 1; else hi = mid;
+            }
+            atomicAdd(&st->refold_members, lo - i);
+          }
+        } else {
+          mp = f3(__shfl_sync(0xffffffffu, state, 0), __shfl_sync(0xffffffffu, state, 1),
+                  __shfl_sync(0xffffffffu, state, 2));
+          mcol = ((uint32_t)(int)__shfl_sync(0xffffffffu, state, 3) & 0xffu) |
+                 (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 4) & 0xffu) << 8) |
+                 (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 5) & 0xffu) << 16) |
+                 (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 6) & 0xffu) << 24);
+        }
+        if (lane == 0) {
+          const bool clearing = key_is_clearing(P, (uint64_t)keys[i]);
+          const F3 pg = transform(P.T, mp);
+          store_ray(P, i, pg, mw, mcol, clearing, ray_p, ray_a, ray_c);
+          if (P.single_walk) {
+            Dda dd;
+            dda_setup(dd, P.origin, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc, true);
+            cnt[i] = dd.len + 1u;  // RayCaster emits ray_length_in_steps_ + 1 voxels (integrator_utils.cc:111-125)
+            atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
+          }
+        }
       }
     }
   }
