@@ -69,3 +69,22 @@ def test_three_operation_division_is_correctly_rounded():
                            "-o", exe, "-lm"])
     out = subprocess.check_output([exe], text=True)
     assert "bad=0" in out, out
+
+
+def test_merge_form_of_the_ray_walk_equals_the_sequential_walk(tmp_path):
+    """k_rays_emit_warp casts a ray as the stable three-way merge of its per-axis crossing chains
+    (vbx_math.cuh: dda_rank).  tests/dda_merge_check.cc runs that formulation on the host against
+    dda_advance (= RayCaster::nextRayIndex, integrator_utils.cc:106-125) over random, tie-heavy,
+    nearly / exactly axis-parallel, clearing and far-from-origin rays: no voxel may differ, and the
+    realistic regimes must not need the sequential fallback."""
+    exe = str(tmp_path / "dda_merge_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", os.path.join(HERE, "dda_merge_check.cc"),
+                           "-o", exe])
+    out = subprocess.run([exe, "800000"], capture_output=True, text=True)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout
+    first = out.stdout.splitlines()[0].split()
+    stats = dict(zip(first[0::2], (int(v) for v in first[1::2])))
+    assert stats["mismatches"] == 0 and stats["regular"] > 0.7 * stats["rays"]
+    per_regime = [int(v) for v in out.stdout.splitlines()[1].split(":")[1].split()]
+    assert per_regime[0] == 0 and per_regime[1] == 0 and per_regime[6] == 0   # camera-like and clearing rays

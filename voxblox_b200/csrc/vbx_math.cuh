@@ -176,6 +176,7 @@ struct Dda {
   float tx, ty, tz;   // t to next boundary
   float dx, dy, dz;   // t step
   unsigned int len;   // emits len + 1 voxels
+  unsigned int nx, ny, nz;  // |end voxel - start voxel| per axis (len = nx + ny + nz)
 };
 
 VBX_HD int signum_f(float v) { return (v == 0.0f) ? 0 : (v < 0.0f ? -1 : 1); }
@@ -196,7 +197,10 @@ VBX_HD void dda_setup_scaled(Dda& d, F3 s, F3 e) {
   d.cy = grid_coord_scaled(s.y);
   d.cz = grid_coord_scaled(s.z);
   const int ex = grid_coord_scaled(e.x), ey = grid_coord_scaled(e.y), ez = grid_coord_scaled(e.z);
-  d.len = (unsigned int)(abs(ex - d.cx) + abs(ey - d.cy) + abs(ez - d.cz));
+  d.nx = (unsigned int)abs(ex - d.cx);
+  d.ny = (unsigned int)abs(ey - d.cy);
+  d.nz = (unsigned int)abs(ez - d.cz);
+  d.len = d.nx + d.ny + d.nz;
   dda_axis(s.x, e.x, d.cx, &d.sx, &d.tx, &d.dx);
   dda_axis(s.y, e.y, d.cy, &d.sy, &d.ty, &d.dy);
   dda_axis(s.z, e.z, d.cz, &d.sz, &d.tz, &d.dz);
@@ -246,6 +250,66 @@ VBX_HD void dda_advance(Dda& d) {
     d.cz += d.sz;
     d.tz = fadd(d.tz, d.dz);
   }
+}
+
+// ---- the same walk as a three-way merge (what lets a warp cast one ray cooperatively) ----------
+// nextRayIndex picks, len times, the axis whose t_to_next_boundary is smallest (first minimum on
+// ties) and adds that axis' t_step to it.  Per axis the visited values form the chain
+//   T_a(0) = t_a,  T_a(k+1) = RN(T_a(k) + dt_a)
+// which is non-decreasing when dt_a > 0, so the sequence of picks is the stable merge of the
+// three chains ordered by (value, axis): element (a, k) is the step with
+//   rank = k + #{(b, j): T_b(j) < T_a(k), or T_b(j) == T_a(k) and b < a}
+// and after it the walk stands at start + sign_a (k + 1) e_a + sum_b sign_b count_b e_b.  Elements
+// can therefore be ranked independently (two binary searches each); only the chains themselves
+// are sequential.  Rays with an axis-parallel component (sign 0: the reference's t is -inf / NaN
+// there) or non-finite increments are "irregular" and keep the sequential walk.
+VBX_HD bool dda_finite_f(float v) { return fabsf(v) <= 3.0e38f; }  // false for inf and NaN
+VBX_HD bool dda_is_regular(const Dda& d) {
+  return d.sx != 0 && d.sy != 0 && d.sz != 0 && dda_finite_f(d.tx) && dda_finite_f(d.ty) && dda_finite_f(d.tz) &&
+         dda_finite_f(d.dx) && dda_finite_f(d.dy) && dda_finite_f(d.dz) && d.dx > 0.0f && d.dy > 0.0f && d.dz > 0.0f;
+}
+// how many chain elements of an axis are computed: normally the axis takes exactly n steps, so
+// elements 0..n-1 are picked and element n is the first one that is not; one more for slack.
+// (If that turns out too few, dda_rank reports it and the ray falls back to the sequential walk.)
+VBX_HD unsigned int dda_chain_len(unsigned int n_axis, unsigned int len) {
+  const unsigned int k = n_axis + 2u;
+  return k < len ? k : len;
+}
+// number of elements of the sorted chain T[0..K) that come before value v; `inclusive`: equal
+// values count as before (the other chain belongs to an axis of higher priority)
+VBX_HD int dda_count_before(const float* T, int K, float v, bool inclusive) {
+  int lo = 0, hi = K;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const bool before = inclusive ? (T[mid] <= v) : (T[mid] < v);
+    if (before) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+// Rank of element (a, k).  counts[b] = steps taken on axis b once this step is done.  Returns
+// false if the rank cannot be trusted: some other chain was computed only partially (K_b < len) and
+// all of its computed elements precede this one.
+VBX_HD bool dda_rank(const float* const T[3], const int K[3], unsigned int len, int a, int k, unsigned int* rank,
+                     int counts[3]) {
+  const float v = T[a][k];
+  bool trusted = true;
+  unsigned int r = (unsigned int)k;
+  for (int b = 0; b < 3; ++b) {
+    if (b == a) {
+      counts[b] = k + 1;
+      continue;
+    }
+    const int cb = dda_count_before(T[b], K[b], v, b < a);
+    counts[b] = cb;
+    r += (unsigned int)cb;
+    if (cb == K[b] && (unsigned int)K[b] < len) trusted = false;
+  }
+  *rank = r;
+  return trusted;
 }
 
 // ---------------------------------------------------------------------- voxel update

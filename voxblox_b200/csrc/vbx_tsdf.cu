@@ -759,21 +759,13 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_
   }
 }
 
+// One ray, walked sequentially by the calling thread: RayCaster's loop (integrator_utils.cc:106-125)
+// with allocateStorageAndGetVoxelPtr's find-or-create per block change (cc:91-134).
 template <typename KeyT>
-__global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ keys,
-                            const uint32_t* __restrict__ ray_list, const float4* __restrict__ ray_p,
-                            const uint32_t* __restrict__ cnt,
-                            const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
-                            uint32_t* __restrict__ cvals, ScanState* st) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t i;
-  if (P.kind == VBX_MERGED) {
-    if (t >= st->n_ray_list) return;
-    i = ray_list[t];
-  } else {
-    i = t;
-    if (i >= P.n) return;
-  }
+__device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, const KeyT* __restrict__ keys, uint32_t i,
+                                    const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
+                                    const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
+                                    uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t c = cnt[i];
   if (c == 0 || st->total_updates == 0) return;  // (a failed / to-be-redone call emits nothing)
   const float4 rp = ray_p[i];
@@ -823,6 +815,166 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
     ckeys[base + emitted] = (hp << (3 * P.L)) | lin;
     cvals[base + emitted] = i;
     ++emitted;
+  }
+}
+
+template <typename KeyT>
+__global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ keys,
+                            const uint32_t* __restrict__ ray_list, const float4* __restrict__ ray_p,
+                            const uint32_t* __restrict__ cnt,
+                            const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
+                            uint32_t* __restrict__ cvals, ScanState* st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i;
+  if (P.kind == VBX_MERGED) {
+    if (t >= st->n_ray_list) return;
+    i = ray_list[t];
+  } else {
+    i = t;
+    if (i >= P.n) return;
+  }
+  emit_ray_sequential<KeyT>(P, tab, keys, i, ray_p, cnt, off, ckeys, cvals, st);
+}
+
+// The same walk cast by a WARP per ray (single-walk modes of the Merged integrator: a few thousand
+// rays of 100-300 steps each, far too few threads for a thread-per-ray walk).  The walk is the
+// stable three-way merge of the per-axis boundary-crossing chains (vbx_math.cuh, dda_rank):
+//   1. lanes 0-2 build the chains T_a(k+1) = RN(T_a(k) + dt_a) in shared memory -- the only
+//      sequential part, and plain additions;
+//   2. all lanes rank the chain elements (two binary searches each) and scatter the voxel each
+//      step reaches into a shared walk list;
+//   3. the walk list is turned into records 32 at a time: block changes are found by comparing
+//      neighbouring lanes, only the first lane of each block run does the hash find-or-create,
+//      and the records leave the warp coalesced.
+// Bit-identical to the sequential walk (tests/dda_merge_check.cc proves the merge against
+// dda_advance on the host); rays the merge form does not cover (axis-parallel components,
+// non-finite increments, more than kChainCap crossings on an axis) are walked by lane 0.
+constexpr int kChainCap = 256;
+constexpr int kWalkCap = 3 * kChainCap;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(128)
+k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
+                 const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
+                 uint32_t* __restrict__ ckeys, uint32_t* __restrict__ cvals, ScanState* st) {
+  __shared__ float chain_s[4][3][kChainCap];
+  __shared__ uint32_t walk_s[4][kWalkCap];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_rays = st->n_ray_list;
+  if (st->total_updates == 0) return;  // (a failed / to-be-redone call emits nothing)
+  const int mask = (1 << P.L) - 1;
+  const int lim = (kCoordBias - 1) << P.L;
+  for (uint32_t b = warp; b < n_rays; b += n_warps) {
+    const uint32_t i = ray_list[b];
+    const uint32_t c = cnt[i];
+    if (c == 0) continue;
+    const float4 rp = ray_p[i];
+    const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
+    Dda d;
+    dda_setup(d, P.origin, f3(rp.x, rp.y, rp.z), clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc, true);
+    const unsigned int len = d.len;
+    int K[3];
+    K[0] = (int)dda_chain_len(d.nx, len);
+    K[1] = (int)dda_chain_len(d.ny, len);
+    K[2] = (int)dda_chain_len(d.nz, len);
+    bool merge_ok = dda_is_regular(d) && K[0] <= kChainCap && K[1] <= kChainCap && K[2] <= kChainCap &&
+                    len + 1u <= (unsigned int)kWalkCap && c == len + 1u;
+    if (merge_ok) {
+      // 1. the chains
+      if (lane < 3) {
+        float t = lane == 0 ? d.tx : (lane == 1 ? d.ty : d.tz);
+        const float dt = lane == 0 ? d.dx : (lane == 1 ? d.dy : d.dz);
+        const int kk = K[lane];
+        float* dst = chain_s[w][lane];
+        for (int k = 0; k < kk; ++k) {
+          dst[k] = t;
+          t = fadd(t, dt);
+        }
+      }
+      if (lane == 0) walk_s[w][0] = 0u;
+      __syncwarp();
+      // 2. rank every chain element, scatter the voxel it leads to
+      const float* const T[3] = {chain_s[w][0], chain_s[w][1], chain_s[w][2]};
+      const int total = K[0] + K[1] + K[2];
+      unsigned int emitted = 0;
+      bool trusted_all = true;
+      for (int e = lane; e < total; e += 32) {
+        const int a = e < K[0] ? 0 : (e < K[0] + K[1] ? 1 : 2);
+        const int k = e - (a == 0 ? 0 : (a == 1 ? K[0] : K[0] + K[1]));
+        unsigned int rank;
+        int c3[3];
+        const bool trusted = dda_rank(T, K, len, a, k, &rank, c3);
+        if (rank < len) {
+          trusted_all &= trusted;
+          walk_s[w][rank + 1u] = (uint32_t)c3[0] | ((uint32_t)c3[1] << 10) | ((uint32_t)c3[2] << 20);
+          ++emitted;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
+      merge_ok = __all_sync(0xffffffffu, trusted_all) && emitted == len;
+      __syncwarp();
+    }
+    if (!merge_ok) {
+      if (lane == 0) emit_ray_sequential<KeyT>(P, tab, keys, i, ray_p, cnt, off, ckeys, cvals, st);
+      __syncwarp();
+      continue;
+    }
+    // 3. records, 32 steps at a time
+    const uint32_t base = off[i];
+    int cbx = INT_MIN, cby = INT_MIN, cbz = INT_MIN;  // block of the previous chunk's last step
+    uint32_t chp = 0u;
+    for (unsigned int r0 = 0; r0 <= len; r0 += 32u) {
+      const unsigned int r = r0 + (unsigned int)lane;
+      const bool valid = r <= len;
+      const uint32_t pk = valid ? walk_s[w][r] : 0u;
+      const int vx = d.cx + d.sx * (int)(pk & 1023u);
+      const int vy = d.cy + d.sy * (int)((pk >> 10) & 1023u);
+      const int vz = d.cz + d.sz * (int)(pk >> 20);
+      const int bx = vx >> P.L, by = vy >> P.L, bz = vz >> P.L;
+      int pbx = __shfl_up_sync(0xffffffffu, bx, 1), pby = __shfl_up_sync(0xffffffffu, by, 1),
+          pbz = __shfl_up_sync(0xffffffffu, bz, 1);
+      if (lane == 0) {
+        pbx = cbx;
+        pby = cby;
+        pbz = cbz;
+      }
+      const bool head = valid && (bx != pbx || by != pby || bz != pbz);
+      uint32_t hp = 0u;
+      if (head) {
+        // the first step inside a block: allocateStorageAndGetVoxelPtr's find-or-create, cc:91-134
+        if (vx < -lim || vx > lim || vy < -lim || vy > lim || vz < -lim || vz > lim) {
+          atomicOr(&st->error, kErrCoordRange);
+          hp = 0xffffffffu;
+        } else {
+          hp = ensure_block(tab, pack3(bx, by, bz), st);
+          if (hp != 0xffffffffu) mark_touched(tab, hp, P.epoch, st);
+        }
+        if (hp != 0xffffffffu) {
+          const int32_t slot = tab.hslot[hp];
+          if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
+        }
+      }
+      const unsigned int heads = __ballot_sync(0xffffffffu, head);
+      const unsigned int below = heads & (0xffffffffu >> (31 - lane));  // heads at or below this lane
+      const int src = below ? 31 - __clz(below) : 0;
+      const uint32_t hp_run = __shfl_sync(0xffffffffu, hp, src);
+      const uint32_t hp_l = below ? hp_run : chp;
+      if (valid) {
+        const uint32_t lin = (uint32_t)(vx & mask) | ((uint32_t)(vy & mask) << P.L) | ((uint32_t)(vz & mask) << (2 * P.L));
+        ckeys[base + r] = (hp_l << (3 * P.L)) | lin;
+        cvals[base + r] = i;
+      }
+      // carry the last step's block into the next chunk (a full chunk whenever there is a next one)
+      cbx = __shfl_sync(0xffffffffu, bx, 31);
+      cby = __shfl_sync(0xffffffffu, by, 31);
+      cbz = __shfl_sync(0xffffffffu, bz, 31);
+      chp = __shfl_sync(0xffffffffu, hp_l, 31);
+    }
+    __syncwarp();  // the walk list is reused by this warp's next ray
   }
 }
 
@@ -1472,8 +1624,14 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
                      Marks& mk, uint64_t* launches) {
   cudaStream_t s = c->stream;
   const uint32_t n = P.n;
-  k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off,
-                                                      c->ckeys[0], c->cvals[0], c->d_state);
+  if (P.kind == VBX_MERGED && P.single_walk) {
+    // a few thousand bundles of 100-300 steps: one warp per ray
+    k_rays_emit_warp<KeyT><<<148 * 8, 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off, c->ckeys[0],
+                                                   c->cvals[0], c->d_state);
+  } else {
+    k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off,
+                                                        c->ckeys[0], c->cvals[0], c->d_state);
+  }
   mk.mark(5);
   k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->d_nblocks + c->nb_cur, c->d_nblocks + (c->nb_cur ^ 1),
                                                             c->d_state);
