@@ -386,7 +386,7 @@ def run_ours(args, rank, world):
            "ray_emit": 8 * k_mean + 20 * b_mean, "assign": 20 * b_mean, "update_sort": 2 * 8 * k_mean,
            "apply": 24 * u_mean + 16 * k_mean}
     # DRAM traffic of the dominant kernels from `ncu --set full` captures (profiles/), per launch
-    traffic = {"bundle_merge": 6.34e6}
+    traffic = {"bundle_merge": 6.35e6, "apply": 4.66e6 + 1.32e6, "ray_emit": 1.18e6}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

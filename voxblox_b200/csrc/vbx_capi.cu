@@ -211,7 +211,13 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
   } while (0)
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamCreateWithFlags(&c->stream_main, cudaStreamNonBlocking));
+  // stream priorities for the pipelined path: the stages that run in submission order (apply, then
+  // the ray walk) are the pipeline's bottleneck, so their thread blocks go first
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
+  c->prio_lo = prio_lo;
+  c->prio_hi = prio_hi;
+  CK(cudaStreamCreateWithPriority(&c->stream_main, cudaStreamNonBlocking, prio_hi));
   CK(cudaStreamCreateWithFlags(&c->stream_c, cudaStreamNonBlocking));
   c->stream = c->stream_main;
   CK(cudaEventCreate(&c->ev0));
@@ -338,11 +344,13 @@ int ensure_async(vbx_ctx* c) {
     if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
   } while (0)
   const size_t np = c->max_points;
-  CK(cudaStreamCreateWithFlags(&c->stream_e, cudaStreamNonBlocking));
-  for (int i = 0; i < vbx_ctx::kSortStreams; ++i) CK(cudaStreamCreateWithFlags(&c->stream_s[i], cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithPriority(&c->stream_e, cudaStreamNonBlocking, std::min(c->prio_lo, c->prio_hi + 1)));
+  for (int i = 0; i < vbx_ctx::kSortStreams; ++i) {
+    CK(cudaStreamCreateWithPriority(&c->stream_s[i], cudaStreamNonBlocking, std::min(c->prio_lo, c->prio_hi + 2)));
+  }
   for (int l = 0; l < vbx_ctx::kLanes; ++l) {
     vbx_ctx::FrontLane& F = c->lane[l];
-    CK(cudaStreamCreateWithFlags(&F.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&F.stream, cudaStreamNonBlocking, c->prio_lo));
     if (l == 0) continue;
     CK(dmalloc(&F.pkeys1, np));
     CK(dmalloc(&F.pvals[0], np));

@@ -195,6 +195,7 @@ struct vbx_ctx {
     uint32_t* scan_status = nullptr;
   } lane[kLanes];
   bool async_ready = false;
+  int prio_lo = 0, prio_hi = 0;  // stream priority range of the device
   cudaStream_t stream_e = nullptr;      // ray walk + block creation + record sort of asynchronously submitted scans
   cudaStream_t stream_s[kSortStreams] = {nullptr, nullptr};  // record sorts (set-private buffers: independent across scans)
   cudaStream_t sort_stream = nullptr;   // non-null while an asynchronous back half is enqueued: the record sort goes here
