@@ -231,6 +231,17 @@ VBX_API int vbx_esdf_update(vbx_ctx* ctx, int batch, int clear_updated_flag);
  * propagate / raise / lower for exactly the listed blocks; indices without a TSDF block are
  * skipped (cc:139-141), an index listed twice is processed once. */
 VBX_API int vbx_esdf_update_blocks(vbx_ctx* ctx, const int32_t* idx3, uint64_t m, int incremental);
+/* addNewRobotPosition(position) (esdf_integrator.cc:25-92; utils/planning_utils_inl.h:13-62):
+ * every unobserved or hallucinated ESDF voxel within clear_sphere_radius of `position` becomes
+ * free (+default_distance_m, observed, hallucinated), every still unobserved voxel within
+ * occupied_sphere_radius becomes occupied (-default_distance_m); ESDF blocks the spheres reach
+ * are allocated (also where the TSDF layer holds no block).  The raise / open queue entries and the
+ * updated_blocks_ set this produces are consumed by the next vbx_esdf_update(_blocks), as in
+ * the reference.  Counters afterwards: [0] ESDF blocks created [1] voxels set free
+ * [2] voxels set occupied [4] raise entries queued [5] open entries queued [7] kernels. */
+VBX_API int vbx_esdf_add_robot_position(vbx_ctx* ctx, const float position[3]);
+/* EsdfIntegrator::clear() (esdf_integrator.h:135-140): drop what addNewRobotPosition queued */
+VBX_API int vbx_esdf_clear(vbx_ctx* ctx);
 /* setEsdfMaxDistance / setFullEuclidean / getters (esdf_integrator.h:139-149) */
 VBX_API int vbx_esdf_set_max_distance(vbx_ctx* ctx, float max_distance_m);
 VBX_API int vbx_esdf_set_full_euclidean(vbx_ctx* ctx, int full_euclidean);

@@ -231,8 +231,13 @@ class GpuEsdfIntegrator {
     gpu_detail::check(ctx_, vbx_esdf_update_blocks(ctx_, idx.data(), tsdf_blocks.size(), incremental ? 1 : 0),
                       "vbx_esdf_update_blocks");
   }
-  /// esdf_integrator.h:131-136; the device keeps no queue between calls
-  void clear() {}
+  /// esdf_integrator.cc:25-92: free sphere / occupied shell around the robot, queued for the next update
+  void addNewRobotPosition(const Point& position) {
+    const float p[3] = {position.x(), position.y(), position.z()};
+    gpu_detail::check(ctx_, vbx_esdf_add_robot_position(ctx_, p), "vbx_esdf_add_robot_position");
+  }
+  /// esdf_integrator.h:135-140
+  void clear() { gpu_detail::check(ctx_, vbx_esdf_clear(ctx_), "vbx_esdf_clear"); }
   float getEsdfMaxDistance() const {
     vbx_esdf_config c;
     gpu_detail::check(ctx_, vbx_esdf_get_config(ctx_, &c), "vbx_esdf_get_config");

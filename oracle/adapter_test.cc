@@ -165,6 +165,46 @@ int main() {
     std::printf("esdf blocks %zu (tsdf %zu)\n", nb, gpu.syncLayer(0));
     if (nb == 0 || esdf.getNumberOfAllocatedBlocks() != tsdf.getNumberOfAllocatedBlocks()) ++failures;
   }
+  // addNewRobotPosition through the adapter against the reference's own EsdfIntegrator on an empty
+  // map (test_clear_spheres.cc:135-136): the hallucinated free sphere / occupied shell is deterministic,
+  // so both ESDF layers must agree voxel for voxel.
+  {
+    Layer<TsdfVoxel> tsdf_c(voxel_size, 16), tsdf_g(voxel_size, 16);
+    Layer<EsdfVoxel> esdf_c(voxel_size, 16), esdf_g(voxel_size, 16);
+    EsdfIntegrator::Config ec;
+    ec.min_distance_m = 0.2f;
+    ec.clear_sphere_radius = 1.0f;
+    ec.occupied_sphere_radius = 2.5f;
+    EsdfIntegrator ce(ec, &tsdf_c, &esdf_c);
+    GpuTsdfIntegrator gpu(TsdfIntegratorType::kMerged, config, &tsdf_g);
+    GpuEsdfIntegrator ge(ec, &gpu, &esdf_g);
+    const Point pos(0.13f, -0.21f, 0.57f);
+    ce.addNewRobotPosition(pos);
+    ge.addNewRobotPosition(pos);
+    ge.syncLayer(0);
+    const std::vector<BlockIndex> a = sortedBlocks(esdf_c), b = sortedBlocks(esdf_g);
+    bool same = a.size() == b.size();
+    for (size_t i = 0; same && i < a.size(); ++i) same = a[i] == b[i];
+    size_t diff = 0, free_v = 0, occ_v = 0;
+    if (same) {
+      for (const BlockIndex& bi : a) {
+        const Block<EsdfVoxel>& x = esdf_c.getBlockByIndex(bi);
+        const Block<EsdfVoxel>& y = esdf_g.getBlockByIndex(bi);
+        for (size_t l = 0; l < x.num_voxels(); ++l) {
+          const EsdfVoxel& p = x.getVoxelByLinearIndex(l);
+          const EsdfVoxel& q = y.getVoxelByLinearIndex(l);
+          if (p.distance != q.distance || p.observed != q.observed || p.hallucinated != q.hallucinated ||
+              p.in_queue != q.in_queue || p.fixed != q.fixed || !(p.parent == q.parent)) {
+            ++diff;
+          }
+          if (q.hallucinated) (q.distance > 0 ? free_v : occ_v) += 1;
+        }
+      }
+    }
+    std::printf("addNewRobotPosition: esdf blocks cpu %zu gpu %zu same %d, differing voxels %zu, free %zu occupied %zu, tsdf blocks %zu\n",
+                a.size(), b.size(), same ? 1 : 0, diff, free_v, occ_v, gpu.syncLayer(0));
+    if (!same || diff != 0 || free_v == 0 || occ_v == 0 || tsdf_g.getNumberOfAllocatedBlocks() != 0) ++failures;
+  }
   std::printf(failures ? "ADAPTER TEST FAILED\n" : "ADAPTER TEST OK\n");
   return failures ? 1 : 0;
 }

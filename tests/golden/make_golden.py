@@ -34,6 +34,11 @@ CASES = {
                                             None, False),
     "room_simple_nocarving_shortrange": (1, "room", 0.1, 0.4, dict(voxel_carving_enabled=0, max_ray_length_m=2.0),
                                          None, False),
+    # test_clear_spheres.cc:107-165: addNewRobotPosition before every scan, incremental updates
+    "room_merged_esdf_clear_spheres": (2, "room", 0.1, 0.4, {},
+                                       dict(max_distance_m=2.0, default_distance_m=2.0, min_distance_m=0.2,
+                                            min_diff_m=0.0, clear_sphere_radius=1.0, occupied_sphere_radius=2.5),
+                                       False, "robot"),
 }
 
 
@@ -55,11 +60,14 @@ def layer_digest(omap, layer):
 
 
 def run_case(lib, name):
-    kind, scan_name, vs, trunc, tkw, ekw, batch = CASES[name]
+    kind, scan_name, vs, trunc, tkw, ekw, batch = CASES[name][:7]
+    robot = len(CASES[name]) > 7
     omap = po.OracleMap(lib, po.TsdfConfig(default_truncation_distance=trunc, integrator_threads=1, **tkw), vs, 16)
     if ekw is not None:
         omap.esdf_create(po.EsdfConfig(**ekw))
     for s in case_scans(scan_name):
+        if robot:
+            omap.esdf_add_robot_position(s[3])
         omap.integrate(kind, s)
         if ekw is not None and not batch:
             omap.esdf_update(batch=False, clear_updated_flag=True)

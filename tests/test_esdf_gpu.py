@@ -122,3 +122,73 @@ def test_update_from_tsdf_blocks_and_setters():
     print(rep)
     assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
     assert rep["n_bit_exact"] >= 0.995 * rep["voxels_observed"], rep
+
+
+# test_clear_spheres.cc:118-129 at a smaller occupied radius
+EKW_SPHERES = dict(max_distance_m=2.0, default_distance_m=2.0, min_distance_m=0.2, min_diff_m=0.0,
+                   clear_sphere_radius=1.0, occupied_sphere_radius=2.5)
+
+
+def _esdf_bytes_equal(esdf, omap):
+    gi, oi = esdf.getAllAllocatedBlocks(), omap.block_indices(1)
+    if gi.shape != oi.shape or not (gi == oi).all():
+        return False
+    gv, _ = esdf.getBlocks(gi)
+    return all(gv[k].tobytes() == omap.block(i, 1)[0].tobytes() for k, i in enumerate(oi))
+
+
+def test_add_new_robot_position_matches_oracle():
+    """EsdfIntegrator::addNewRobotPosition (esdf_integrator.cc:25-92) on the device, driven like the
+    reference's test_clear_spheres.cc:107-165: sphere, scan, incremental update, twice."""
+    scans = scenes.c3_room_sequence(n_scans=2, width=160, height=120)
+    tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW_SPHERES)
+    # 1. the spheres alone, on an empty map: deterministic -> every voxel bit-identical, and the
+    #    TSDF layer still holds no block (the sphere allocates ESDF blocks only)
+    eint.addNewRobotPosition(scans[0][3])
+    omap.esdf_add_robot_position(scans[0][3])
+    c = eint.counters()
+    print("sphere counters", c)
+    assert _esdf_bytes_equal(esdf, omap)
+    assert len(tsdf.getAllAllocatedBlocks()) == 0 and tsdf.getNumberOfAllocatedBlocks() == 0
+    assert len(esdf.getAllAllocatedBlocks()) == c["blocks"] > 0
+    for k, s in enumerate(scans):
+        if k > 0:
+            eint.addNewRobotPosition(s[3])
+            omap.esdf_add_robot_position(s[3])
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        assert compare_tsdf(tsdf, omap)["max_rel_err"] == 0.0
+        eint.updateFromTsdfLayer(True)
+        omap.esdf_update(batch=False, clear_updated_flag=True)
+        rep = compare_esdf(esdf, omap, 2.0)
+        print(k, rep, eint.counters())
+        assert rep["blocks_equal"] and rep["observed_equal"] and rep["fixed_equal"], rep
+        assert rep["hallucinated_equal"] and rep["flag_bytes_clean"] and rep["in_queue_gpu"] == 0, rep
+        assert rep["rmse"] < 0.1, rep
+        assert rep["n_over_1e-4"] < 0.08 * rep["voxels_observed"], rep
+    # the reference test's own criteria (test_clear_spheres.cc:171-203) on the device layers
+    ti = tsdf.getAllAllocatedBlocks()
+    tv, _ = tsdf.getBlocks(ti)
+    ev, _ = esdf.getBlocks(ti)          # ASSERT_TRUE(esdf_layer.hasBlock(block_index))
+    unobs = tv["weight"] < 1e-6
+    assert (ev["hallucinated"][unobs & (ev["observed"] != 0)] != 0).all()
+    band = (tv["weight"] > 1e-6) & (np.abs(tv["distance"]) <= 0.2)
+    assert (ev["observed"][band] != 0).all() and (ev["hallucinated"][band] == 0).all()
+    assert (np.sign(tv["distance"][band]) == np.sign(ev["distance"][band])).all()
+    assert np.abs(tv["distance"][band] - ev["distance"][band]).max() <= 1e-3
+
+
+def test_esdf_clear_drops_robot_position_queue():
+    """EsdfIntegrator::clear() (esdf_integrator.h:135-140): nothing queued by addNewRobotPosition
+    reaches the next update."""
+    scans = scenes.c3_room_sequence(n_scans=1, width=160, height=120)
+    tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW_SPHERES)
+    s = scans[0]
+    integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    eint.updateFromTsdfLayer(True)
+    eint.addNewRobotPosition(s[3])
+    assert eint.counters()["relaxations"] > 0      # slot [5] after the sphere call: open_ entries queued
+    eint.clear()
+    eint.updateFromTsdfLayer(True)
+    c = eint.counters()
+    assert c["blocks"] == 0 and c["relaxations"] == 0 and c["raised_voxels"] == 0, c

@@ -114,7 +114,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
            "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
-           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_esdf_add_robot_position", "vbx_esdf_clear", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
            "vbx_proto_encode_layer", "vbx_proto_encode_block", "vbx_proto_decode_block"]
 
 _lib = None
@@ -194,6 +194,10 @@ def load_library():
     lib.vbx_esdf_get_config.argtypes = [vp, C.POINTER(EsdfIntegratorConfig)]
     lib.vbx_esdf_update.restype = i32
     lib.vbx_esdf_update.argtypes = [vp, i32, i32]
+    lib.vbx_esdf_add_robot_position.restype = i32
+    lib.vbx_esdf_add_robot_position.argtypes = [vp, vp]
+    lib.vbx_esdf_clear.restype = i32
+    lib.vbx_esdf_clear.argtypes = [vp]
     lib.vbx_sync.restype = i32
     lib.vbx_sync.argtypes = [vp]
     lib.vbx_host_alloc.restype = i32
@@ -651,9 +655,13 @@ class EsdfIntegrator:
         self._ctx.check(self._ctx.lib.vbx_esdf_set_full_euclidean(self._ctx.handle, int(bool(full_euclidean))),
                         "setFullEuclidean")
 
-    def clear(self) -> None:
-        """esdf_integrator.h:131-136: drops queued work of addNewRobotPosition; the device keeps no
-        queue between calls, so there is nothing to drop."""
+    def addNewRobotPosition(self, position) -> None:  # esdf_integrator.cc:25-92
+        p = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
+        self._ctx.check(self._ctx.lib.vbx_esdf_add_robot_position(self._ctx.handle, p.ctypes.data),
+                        "addNewRobotPosition")
+
+    def clear(self) -> None:  # esdf_integrator.h:135-140
+        self._ctx.check(self._ctx.lib.vbx_esdf_clear(self._ctx.handle), "EsdfIntegrator::clear")
 
     def updateFromTsdfLayerBatch(self) -> None:  # esdf_integrator.cc:94-102
         self._ctx.check(self._ctx.lib.vbx_esdf_update(self._ctx.handle, 1, 0), "updateFromTsdfLayerBatch")

@@ -20,7 +20,7 @@ __global__ void k_ensure_keys(Tables tab, const uint64_t* __restrict__ keys, uin
   hp_out[i] = ensure_block(tab, keys[i], st);
 }
 
-__global__ void k_assign_uploaded(Tables tab, uint32_t n_blocks_before, ScanState* st) {
+__global__ void k_assign_uploaded(Tables tab, uint32_t n_blocks_before, uint8_t new_slot_flags, ScanState* st) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_new = min(st->n_new, tab.max_blocks);
   if (j < n_new) {
@@ -29,6 +29,7 @@ __global__ void k_assign_uploaded(Tables tab, uint32_t n_blocks_before, ScanStat
       const uint32_t hp = tab.new_list[j];
       tab.hslot[hp] = (int32_t)slot;
       tab.slot_key[slot] = tab.hkeys[hp];
+      tab.slot_updated[slot] = new_slot_flags;
     } else {
       atomicOr(&st->error, kErrPoolFull);
     }
@@ -137,7 +138,7 @@ __global__ void k_scatter_blocks(int layer, int serialized, const uint32_t* __re
     for (int k = 0; k < 5; ++k) dst[k] = v[k];
   }
   if (i == 0) {
-    flags[slot] = upd_in ? upd_in[b] : (uint8_t)0;
+    flags[slot] = upd_in ? (uint8_t)(upd_in[b] & 0x7f) : (uint8_t)0;  // (bit 7 is the engine's own; a TSDF upload clears kSlotNoTsdf)
     if (has_esdf) has_esdf[slot] = 1;
   }
 }
@@ -187,11 +188,14 @@ int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const 
   VBX_CUDA(c, cudaMemcpyAsync(c->pkeys[0], keys.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
   k_ensure_keys<<<grid_for(m, 256), 256, 0, s>>>(c->tab, c->pkeys[0], (uint32_t)m, c->ray_list, c->d_state);
-  k_assign_uploaded<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
+  // a block inserted into the ESDF layer at an index the TSDF layer does not hold occupies a slot of its own
+  k_assign_uploaded<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(
+      c->tab, c->n_blocks, layer == VBX_LAYER_ESDF ? kSlotNoTsdf : (uint8_t)0, c->d_state);
   k_slots_of<<<grid_for(m, 256), 256, 0, s>>>(c->tab, c->ray_list, (uint32_t)m, reinterpret_cast<int32_t*>(c->cnt));
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   if (c->h_state->error & kFatalErrors) return fail(c, VBX_E_CAPACITY, "block pool / hash full during upload");
+  if (layer == VBX_LAYER_ESDF && c->h_state->n_new) c->maybe_esdf_only = true;
   if (int rc = set_n_blocks(c, c->h_state->n_blocks)) return rc;
   const size_t bbytes = payload_bytes(c, layer, serialized);
   const uint32_t wpv = (layer == VBX_LAYER_TSDF) ? 3u : (serialized ? 1u : 5u);  // threads per voxel along x
@@ -221,12 +225,15 @@ int clear_layer(vbx_ctx* c, int layer) {
   const size_t used = (size_t)c->n_blocks * c->vox_per_block;
   if (layer == VBX_LAYER_ESDF) {
     if (!c->has_esdf) return VBX_OK;
+    c->esdf_pending_raise = c->esdf_pending_open = 0;
     VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, used * sizeof(EsdfVoxel), s));
     VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->tab.max_blocks, s));
     VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->tab.max_blocks, s));
     VBX_CUDA(c, cudaStreamSynchronize(s));
     return VBX_OK;
   }
+  c->esdf_pending_raise = c->esdf_pending_open = 0;
+  c->maybe_esdf_only = false;
   // removing every TSDF block also empties the ESDF layer's storage (the two layers share slots)
   VBX_CUDA(c, cudaMemsetAsync(c->tab.tsdf, 0, used * sizeof(TsdfVoxel), s));
   if (c->has_esdf) VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, used * sizeof(EsdfVoxel), s));
@@ -258,6 +265,7 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
   const size_t tb = sizeof(TsdfVoxel) * c->vox_per_block, eb = sizeof(EsdfVoxel) * c->vox_per_block;
   if (layer == VBX_LAYER_ESDF) {
     if (!c->has_esdf) return VBX_OK;
+    c->esdf_pending_raise = c->esdf_pending_open = 0;
     for (int32_t v : victims) {
       VBX_CUDA(c, cudaMemsetAsync(reinterpret_cast<char*>(c->tab.esdf) + (size_t)v * eb, 0, eb, s));
       VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf + v, 0, 1, s));
@@ -266,7 +274,9 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
     VBX_CUDA(c, cudaStreamSynchronize(s));
     return VBX_OK;
   }
-  // TSDF: swap-remove in the pool (highest victim first), then rebuild the hash from slot_key
+  // TSDF: swap-remove in the pool (highest victim first), then rebuild the hash from slot_key.
+  // Queue entries of addNewRobotPosition address voxels by slot: they are dropped.
+  c->esdf_pending_raise = c->esdf_pending_open = 0;
   uint32_t n = c->n_blocks;
   for (auto it = victims.rbegin(); it != victims.rend(); ++it) {
     const uint32_t v = (uint32_t)*it, last = n - 1;
@@ -337,6 +347,10 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
     VBX_CUDA(c, cudaMemcpyAsync(has.data(), c->tab.slot_has_esdf, c->n_blocks, cudaMemcpyDeviceToHost, s));
   }
   VBX_CUDA(c, cudaStreamSynchronize(s));
+  for (uint32_t sl = 0; sl < c->n_blocks; ++sl) {
+    if (layer == VBX_LAYER_TSDF && (upd[sl] & kSlotNoTsdf)) has[sl] = 0;  // an ESDF-only slot
+    upd[sl] &= 0x7f;
+  }
   struct Item {
     int x, y, z;
     uint32_t slot;
@@ -380,12 +394,12 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
     const dim3 grid(grid_for((uint64_t)tpv * c->vox_per_block, 256), (unsigned int)m);
     k_serialize_blocks<<<grid, 256, 0, s>>>(layer, reinterpret_cast<const uint32_t*>(pool), c->mirror_slots, (uint32_t)m,
                                             (uint32_t)c->vox_per_block, static_cast<uint32_t*>(c->mirror_dev), flags,
-                                            (uint8_t)clear_mask);
+                                            (uint8_t)(clear_mask & 0x7f));
   } else {
     k_gather_blocks<<<(unsigned int)(m * 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(pool), c->mirror_slots,
                                                            (uint32_t)m, (uint32_t)(raw_bytes / 16),
                                                            reinterpret_cast<uint4*>(c->mirror_dev), flags,
-                                                           (uint8_t)clear_mask);
+                                                           (uint8_t)(clear_mask & 0x7f));
   }
   // straight into the caller's buffer when it is page-locked (vbx_host_alloc / cudaHostRegister),
   // otherwise through the engine's page-locked staging buffer

@@ -31,6 +31,8 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
 int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg);
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag);
 int esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incremental);
+int esdf_add_robot_position(vbx_ctx* c, const float p[3]);
+int esdf_clear_state(vbx_ctx* c);
 
 int fail(vbx_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
@@ -628,6 +630,8 @@ int vbx_sync(vbx_ctx* c) {
   return VBX_OK;
 }
 
+// Per-slot flag bytes of a layer with the engine's internal bits resolved: `has` = the layer holds a
+// block in this slot, `upd` = Block::updated() bits only.
 static int fetch_flags(vbx_ctx* c, int layer, std::vector<uint8_t>* upd, std::vector<uint8_t>* has) {
   upd->resize(c->n_blocks);
   has->assign(c->n_blocks, 1);
@@ -639,6 +643,10 @@ static int fetch_flags(vbx_ctx* c, int layer, std::vector<uint8_t>* upd, std::ve
                                 c->stream));
   }
   VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t s = 0; s < c->n_blocks; ++s) {
+    if (layer == VBX_LAYER_TSDF && ((*upd)[s] & kSlotNoTsdf)) (*has)[s] = 0;
+    (*upd)[s] &= 0x7f;  // kSlotNoTsdf / kEsdfPending are internal
+  }
   return VBX_OK;
 }
 
@@ -646,11 +654,11 @@ int vbx_num_blocks(vbx_ctx* c, int layer, uint64_t* n) {
   if (!c || !n) return VBX_E_INVALID;
   VBX_CUDA(c, cudaSetDevice(c->device));
   VBX_DRAIN(c);
-  if (layer == VBX_LAYER_TSDF) {
+  if (layer == VBX_LAYER_TSDF && !c->maybe_esdf_only) {
     *n = c->n_blocks;
     return VBX_OK;
   }
-  if (!c->has_esdf) {
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) {
     *n = 0;
     return VBX_OK;
   }
@@ -757,10 +765,11 @@ int vbx_clear_updated(vbx_ctx* c, int layer, int updated_mask) {
   VBX_CUDA(c, cudaSetDevice(c->device));
   VBX_DRAIN(c);
   if (c->n_blocks == 0) return VBX_OK;
-  std::vector<uint8_t> upd, has;
-  if (int rc = fetch_flags(c, layer, &upd, &has)) return rc;
-  for (uint8_t& u : upd) u &= (uint8_t)~updated_mask;
+  std::vector<uint8_t> upd(c->n_blocks);
   uint8_t* dst = (layer == VBX_LAYER_TSDF) ? c->tab.slot_updated : c->tab.slot_esdf_updated;
+  VBX_CUDA(c, cudaMemcpyAsync(upd.data(), dst, c->n_blocks, cudaMemcpyDeviceToHost, c->stream));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint8_t& u : upd) u &= (uint8_t)(~updated_mask | 0x80);  // bit 7 is the engine's own (kSlotNoTsdf / kEsdfPending)
   VBX_CUDA(c, cudaMemcpyAsync(dst, upd.data(), c->n_blocks, cudaMemcpyHostToDevice, c->stream));
   VBX_CUDA(c, cudaStreamSynchronize(c->stream));
   return VBX_OK;
@@ -809,6 +818,22 @@ int vbx_esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incr
   VBX_DRAIN(c);
   if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_update_blocks before vbx_esdf_create");
   return esdf_update_blocks(c, idx3, m, incremental);
+}
+
+int vbx_esdf_add_robot_position(vbx_ctx* c, const float position[3]) {
+  if (!c || !position) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_add_robot_position before vbx_esdf_create");
+  return esdf_add_robot_position(c, position);
+}
+
+int vbx_esdf_clear(vbx_ctx* c) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  if (!c->has_esdf) return fail(c, VBX_E_STATE, "no ESDF integrator");
+  return esdf_clear_state(c);
 }
 
 int vbx_esdf_set_max_distance(vbx_ctx* c, float max_distance_m) {

@@ -21,6 +21,13 @@ namespace vbx {
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint64_t kInvalidPointKey = ~0ull;
 constexpr int kCoordBias = 1 << 20;  // block / voxel coordinates are packed 21 bits per axis
+// Internal bits of the per-slot flag bytes (never reported through the C-ABI):
+//   slot_updated bit 7: the slot holds an ESDF block only -- the TSDF layer has no block at this
+//     index (blocks allocated by EsdfIntegrator::addNewRobotPosition or uploaded into the ESDF layer).
+//     Any TSDF touch writes the byte to 7 (Block::updated().set()), which turns the slot into a TSDF block
+//     that starts from zeroed voxels, exactly like a freshly allocated one.
+//   slot_esdf_updated bit 7: member of EsdfIntegrator::updated_blocks_ (esdf_integrator.h:172-175).
+constexpr uint8_t kSlotNoTsdf = 0x80, kEsdfPending = 0x80;
 
 struct EsdfVoxel {  // core/voxel.h:18-37
   float distance;
@@ -225,6 +232,8 @@ struct vbx_ctx {
   float* esdf_seed_val = nullptr;
   uint32_t* esdf_touched = nullptr;
   int esdf_grid_raise = 0, esdf_grid_lower = 0, esdf_sms = 0, esdf_ctas_wide = 1;
+  uint32_t esdf_pending_raise = 0, esdf_pending_open = 0;  // raise_ / open_ entries queued by addNewRobotPosition
+  bool maybe_esdf_only = false;                            // some slot may carry kSlotNoTsdf
   // reporting
   uint64_t counters[16] = {0};
   uint64_t esdf_counters[16] = {0};
@@ -246,6 +255,8 @@ int refresh_host_mirror(vbx_ctx* c);
 int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
                    uint8_t* updated_bits, uint64_t cap, uint64_t* n, int serialized);
 int esdf_destroy(vbx_ctx* c);
+int esdf_add_robot_position(vbx_ctx* c, const float p[3]);
+int esdf_clear_state(vbx_ctx* c);
 int ensure_async(vbx_ctx* c);          // allocate the extra hand-off sets / front lanes
 void select_set(vbx_ctx* c, int k);     // point the context's scratch fields at hand-off set k / front lane l
 void select_lane(vbx_ctx* c, int l);

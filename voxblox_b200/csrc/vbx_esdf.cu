@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "vbx_engine.h"
+#include "vbx_hash.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -417,14 +418,21 @@ __global__ void k_esdf_parents(EsdfParams E, Tables tab, const uint32_t* __restr
   }
 }
 
-// blocks to propagate: every slot with the kEsdf bit (incremental) or every slot (batch)
+// blocks to propagate: every TSDF block with the kEsdf bit or queued by addNewRobotPosition
+// (updated_blocks_, cc:104-110) -- incremental -- or every TSDF block (batch).  Slots that hold an
+// ESDF block only (kSlotNoTsdf) are skipped like the reference skips indices without a TSDF
+// block (cc:137-141).
 __global__ void k_esdf_block_list(Tables tab, uint32_t n_slots, int batch, uint32_t* block_list, ScanState* st) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
-  if (batch || (tab.slot_updated[s] & VBX_UPDATED_ESDF)) {
+  const uint8_t u = tab.slot_updated[s];
+  const uint8_t eu = tab.slot_esdf_updated[s];
+  if (eu & kEsdfPending) tab.slot_esdf_updated[s] = eu & (uint8_t)~kEsdfPending;  // updated_blocks_.clear(), cc:99,109
+  if (u & kSlotNoTsdf) return;
+  if (batch || (u & VBX_UPDATED_ESDF) || (eu & kEsdfPending)) {
     block_list[atomicAdd(&st->esdf_counts[0], 1u)] = s;
-    tab.slot_has_esdf[s] = 1;      // allocateBlockPtrByIndex in the ESDF layer, cc:143-146
-    tab.slot_esdf_updated[s] = 1;  // esdf_block->set_updated(true): bitset(1) = kMap only, cc:147
+    tab.slot_has_esdf[s] = 1;  // allocateBlockPtrByIndex in the ESDF layer, cc:143-146
+    tab.slot_esdf_updated[s] = (tab.slot_esdf_updated[s] & kEsdfPending) | 1;  // esdf_block->set_updated(true): bitset(1) = kMap only, cc:147
   }
 }
 
@@ -434,7 +442,109 @@ __global__ void k_esdf_mark_listed(Tables tab, const uint32_t* __restrict__ bloc
   if (i >= nb) return;
   const uint32_t s = block_list[i];
   tab.slot_has_esdf[s] = 1;
-  tab.slot_esdf_updated[s] = 1;
+  tab.slot_esdf_updated[s] = (tab.slot_esdf_updated[s] & kEsdfPending) | 1;
+}
+
+// ------------------------------------------------------------------ addNewRobotPosition
+// EsdfIntegrator::addNewRobotPosition (cc:25-92) with utils::getAndAllocateSphereAroundPoint
+// (utils/planning_utils_inl.h:13-62).  The reference walks `for (float x = -r; x <= r; x++)` on all
+// three axes and keeps the offsets whose norm is <= r; the per-axis value list (with the
+// reference's accumulated float additions) comes from the host, one thread tests one (x, y, z)
+// triple.  floor() of distinct list entries is distinct, so a pass visits every voxel at most
+// once and needs no atomics on voxels.
+struct SphereParams {
+  int n;             // entries of the per-axis list
+  int cx, cy, cz;    // getGridIndexFromPoint(center), planning_utils_inl.h:22-23
+  float rv;          // radius / voxel_size
+  float default_distance;
+  int L;
+  int outer;         // 0: clear sphere (cc:28-58), 1: occupied sphere (cc:60-86)
+  uint32_t cap;
+};
+
+__device__ __forceinline__ bool sphere_voxel(const SphereParams& S, const float* __restrict__ xs, uint64_t gid, int* gx,
+                                             int* gy, int* gz) {
+  const uint64_t n = (uint64_t)S.n;
+  if (gid >= n * n * n) return false;
+  const float x = xs[gid / (n * n)], y = xs[(gid / n) % n], z = xs[gid % n];
+  if (!(norm3(f3(x, y, z)) <= S.rv)) return false;
+  *gx = (int)floorf(x) + S.cx;
+  *gy = (int)floorf(y) + S.cy;
+  *gz = (int)floorf(z) + S.cz;
+  return true;
+}
+
+// layer->allocateBlockPtrByIndex for every block the sphere reaches (planning_utils_inl.h:57-61)
+__global__ void k_esdf_sphere_blocks(SphereParams S, Tables tab, const float* __restrict__ xs, ScanState* st) {
+  int gx, gy, gz;
+  if (!sphere_voxel(S, xs, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, &gx, &gy, &gz)) return;
+  const int bx = gx >> S.L, by = gy >> S.L, bz = gz >> S.L;
+  const int lim = kCoordBias - 1;
+  if (bx < -lim || bx > lim || by < -lim || by > lim || bz < -lim || bz > lim) {
+    atomicOr(&st->error, kErrCoordRange);
+    return;
+  }
+  ensure_block(tab, pack3(bx, by, bz), st);
+}
+
+// pool slots for the blocks the sphere created: they exist in the ESDF layer only
+__global__ void k_esdf_sphere_assign(Tables tab, uint32_t n_blocks_before, ScanState* st) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_new = min(st->n_new, tab.max_blocks);
+  if (j < n_new) {
+    const uint32_t slot = n_blocks_before + j;
+    if (slot < tab.max_blocks) {
+      const uint32_t hp = tab.new_list[j];
+      tab.hslot[hp] = (int32_t)slot;
+      tab.slot_key[slot] = tab.hkeys[hp];
+      tab.slot_updated[slot] = kSlotNoTsdf;
+    } else {
+      atomicOr(&st->error, kErrPoolFull);
+    }
+  }
+  if (j == 0) st->n_blocks = min(n_blocks_before + st->n_new, tab.max_blocks);
+}
+
+__global__ void k_esdf_sphere_apply(SphereParams S, Tables tab, const float* __restrict__ xs, uint32_t* raise_list,
+                                    uint32_t* open_list, ScanState* st) {
+  int gx, gy, gz;
+  if (!sphere_voxel(S, xs, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, &gx, &gy, &gz)) return;
+  const uint32_t hp = find_block(tab, pack3(gx >> S.L, gy >> S.L, gz >> S.L));
+  if (hp == 0xffffffffu) return;  // (coordinate range error raised by the allocation pass)
+  const int32_t slot = tab.hslot[hp];
+  if (slot < 0) return;           // (pool full, error raised by the assignment)
+  const int mask = (1 << S.L) - 1;
+  const uint32_t lin = (uint32_t)((gx & mask) | ((gy & mask) << S.L) | ((gz & mask) << (2 * S.L)));
+  const uint32_t ref = ((uint32_t)slot << (3 * S.L)) | lin;
+  if (!tab.slot_has_esdf[slot]) tab.slot_has_esdf[slot] = 1;
+  EsdfWords* ep = reinterpret_cast<EsdfWords*>(tab.esdf) + ref;
+  const uint32_t f = ep->flags;
+  bool changed = false;
+  if (!S.outer) {
+    if (!(f & kFlagObserved) || (f & kFlagHallucinated)) {  // cc:44-56
+      if (f & kFlagHallucinated) push(raise_list, &st->raise_n[0], S.cap, ref, st);
+      ep->distance = S.default_distance;
+      changed = true;
+    }
+  } else {
+    if (!(f & kFlagObserved)) {  // cc:74-81
+      ep->distance = -S.default_distance;
+      changed = true;
+    } else if (!(f & kFlagInQueue)) {  // cc:81-85 (in_queue stays false, as in the reference)
+      push(open_list, &st->frontier_n[0], S.cap, ref, st);
+    }
+  }
+  if (changed) {
+    ep->flags = f | kBitObserved | kBitHallucinated;
+    ep->px = ep->py = ep->pz = 0;
+    if (!(tab.slot_esdf_updated[slot] & kEsdfPending)) tab.slot_esdf_updated[slot] |= kEsdfPending;  // updated_blocks_.insert
+    atomicAdd(&st->esdf_counts[S.outer ? 2 : 1], 1u);
+  }
+}
+
+__global__ void k_esdf_set_pending(ScanState* st, uint32_t n_raise, uint32_t n_open) {
+  st->raise_n[0] = n_raise;
+  st->frontier_n[0] = n_open;
 }
 
 __global__ void k_esdf_clear_tsdf_flag(Tables tab, const uint32_t* __restrict__ block_list, const ScanState* st) {
@@ -497,6 +607,87 @@ int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
 static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_flag, const uint32_t* listed_slots,
                     uint32_t n_listed);
 
+// EsdfIntegrator::clear(), esdf_integrator.h:135-140: forget the work addNewRobotPosition queued
+int esdf_clear_state(vbx_ctx* c) {
+  c->esdf_pending_raise = c->esdf_pending_open = 0;
+  if (c->n_blocks == 0) return VBX_OK;
+  std::vector<uint8_t> eu(c->n_blocks);
+  VBX_CUDA(c, cudaMemcpyAsync(eu.data(), c->tab.slot_esdf_updated, c->n_blocks, cudaMemcpyDeviceToHost, c->stream));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint8_t& u : eu) u &= (uint8_t)~kEsdfPending;
+  VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_esdf_updated, eu.data(), c->n_blocks, cudaMemcpyHostToDevice, c->stream));
+  VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VBX_OK;
+}
+
+// EsdfIntegrator::addNewRobotPosition(position), esdf_integrator.cc:25-92
+int esdf_add_robot_position(vbx_ctx* c, const float p[3]) {
+  cudaStream_t s = c->stream;
+  const vbx_esdf_config& cfg = c->ecfg;
+  std::memset(c->esdf_counters, 0, sizeof(c->esdf_counters));
+  uint64_t launches = 0;
+  const float radii[2] = {cfg.clear_sphere_radius, cfg.occupied_sphere_radius};
+  SphereParams S[2];
+  std::vector<float> xs[2];
+  for (int k = 0; k < 2; ++k) {
+    std::memset(&S[k], 0, sizeof(SphereParams));
+    const float rv = radii[k] / c->voxel_size;  // radius_in_voxels, planning_utils_inl.h:24
+    if (!(rv == rv) || rv > 320.0f) return fail(c, VBX_E_CAPACITY, "sphere radius above 320 voxels");
+    for (float x = -rv; x <= rv; x++) xs[k].push_back(x);  // planning_utils_inl.h:26
+    const I3 ci = grid_index(f3(p[0], p[1], p[2]), c->voxel_size_inv);
+    S[k].n = (int)xs[k].size();
+    S[k].cx = ci.x;
+    S[k].cy = ci.y;
+    S[k].cz = ci.z;
+    S[k].rv = rv;
+    S[k].default_distance = cfg.default_distance_m;
+    S[k].L = c->L;
+    S[k].outer = k;
+    S[k].cap = (uint32_t)c->frontier_cap;
+  }
+  // the per-axis lists ride in the seed-value scratch (floats; frontier_cap >> 1300 entries)
+  float* d_xs[2] = {c->esdf_seed_val, c->esdf_seed_val + xs[0].size()};
+  VBX_CUDA(c, cudaEventRecord(c->ev0, s));
+  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+  k_esdf_set_pending<<<1, 1, 0, s>>>(c->d_state, c->esdf_pending_raise, c->esdf_pending_open);
+  for (int k = 0; k < 2; ++k) {
+    if (S[k].n == 0) continue;
+    VBX_CUDA(c, cudaMemcpyAsync(d_xs[k], xs[k].data(), xs[k].size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    const uint64_t n3 = (uint64_t)S[k].n * S[k].n * S[k].n;
+    k_esdf_sphere_blocks<<<grid_for(n3, 256), 256, 0, s>>>(S[k], c->tab, d_xs[k], c->d_state);
+    launches += 1;
+  }
+  k_esdf_sphere_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, c->d_state);
+  launches += 2;
+  for (int k = 0; k < 2; ++k) {
+    if (S[k].n == 0) continue;
+    const uint64_t n3 = (uint64_t)S[k].n * S[k].n * S[k].n;
+    k_esdf_sphere_apply<<<grid_for(n3, 256), 256, 0, s>>>(S[k], c->tab, d_xs[k], c->raise_q[0], c->frontier[0], c->d_state);
+    launches += 1;
+  }
+  VBX_CUDA(c, cudaEventRecord(c->ev1, s));
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));  // (also keeps xs[] alive until the copies are done)
+  VBX_CUDA(c, cudaGetLastError());
+  VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  const ScanState& h = *c->h_state;
+  if (h.error & (kErrPoolFull | kErrHashFull)) return fail(c, VBX_E_CAPACITY, "block pool / hash full in addNewRobotPosition");
+  if (h.error & kErrCoordRange) return fail(c, VBX_E_INVALID, "robot position sphere outside the +-2^20 block range");
+  if (h.error & kErrUpdatesFull) return fail(c, VBX_E_CAPACITY, "ESDF wavefront queue capacity exceeded");
+  if (h.n_new) c->maybe_esdf_only = true;
+  if (int rc = set_n_blocks(c, h.n_blocks)) return rc;
+  c->esdf_pending_raise = h.raise_n[0];
+  c->esdf_pending_open = h.frontier_n[0];
+  c->esdf_counters[0] = h.n_new;          // ESDF blocks created
+  c->esdf_counters[1] = h.esdf_counts[1]; // voxels set free
+  c->esdf_counters[2] = h.esdf_counts[2]; // voxels set occupied
+  c->esdf_counters[4] = h.raise_n[0];     // queued: raise_
+  c->esdf_counters[5] = h.frontier_n[0];  // queued: open_
+  c->esdf_counters[7] = launches;
+  c->launches += launches;
+  return refresh_host_mirror(c);
+}
+
 int esdf_update(vbx_ctx* c, int batch, int clear_updated_flag) {
   return esdf_run(c, batch, batch ? 0 : 1, clear_updated_flag, nullptr, 0);
 }
@@ -507,10 +698,14 @@ int esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incremen
   if (int rc = refresh_host_mirror(c)) return rc;
   std::vector<uint32_t> slots;
   slots.reserve(m);
-  std::vector<uint8_t> seen(c->n_blocks, 0);
+  std::vector<uint8_t> seen(c->n_blocks, 0), upd(c->n_blocks, 0);
+  if (c->maybe_esdf_only && c->n_blocks) {
+    VBX_CUDA(c, cudaMemcpyAsync(upd.data(), c->tab.slot_updated, c->n_blocks, cudaMemcpyDeviceToHost, c->stream));
+    VBX_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   for (uint64_t i = 0; i < m; ++i) {
     auto it = c->host_key2slot.find(pack3(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
-    if (it == c->host_key2slot.end() || seen[it->second]) continue;
+    if (it == c->host_key2slot.end() || seen[it->second] || (upd[it->second] & kSlotNoTsdf)) continue;
     seen[it->second] = 1;
     slots.push_back((uint32_t)it->second);
   }
@@ -551,6 +746,19 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
     return VBX_OK;
   }
   if (batch) {
+    // the batch update wipes the ESDF layer (cc:95); queue entries of addNewRobotPosition would
+    // point into removed blocks (the reference CHECK-fails on them), so they are dropped
+    c->esdf_pending_raise = c->esdf_pending_open = 0;
+  }
+  // raise_ / open_ entries queued by addNewRobotPosition since the last update (they sit at the
+  // head of raise_q[0] / frontier[0]; this call's own entries are appended behind them)
+  const bool pending = c->esdf_pending_raise || c->esdf_pending_open;
+  if (pending) {
+    k_esdf_set_pending<<<1, 1, 0, s>>>(c->d_state, c->esdf_pending_raise, c->esdf_pending_open);
+    launches += 1;
+  }
+  c->esdf_pending_raise = c->esdf_pending_open = 0;
+  if (batch) {
     // esdf_layer_->removeAllBlocks() (cc:95): every ESDF block starts from scratch
     const size_t nvox = (size_t)c->n_blocks * c->vox_per_block;
     VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, nvox * sizeof(EsdfVoxel), s));
@@ -573,11 +781,13 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
     nb = c->h_state->esdf_counts[0];
   }
   launches += 1;
-  if (nb > 0) {
-    k_esdf_propagate<<<grid_for((uint64_t)nb * c->vox_per_block, 256), 256, 0, s>>>(
-        E, c->tab, c->esdf_block_list, nb, c->frontier[0], c->raise_q[0], c->esdf_seed_list, c->d_state);
-    launches += 1;
-    if (incremental) {
+  if (nb > 0 || pending) {
+    if (nb > 0) {
+      k_esdf_propagate<<<grid_for((uint64_t)nb * c->vox_per_block, 256), 256, 0, s>>>(
+          E, c->tab, c->esdf_block_list, nb, c->frontier[0], c->raise_q[0], c->esdf_seed_list, c->d_state);
+      launches += 1;
+    }
+    if (nb > 0 && incremental) {
       const unsigned int g = 148 * 8;
       k_esdf_seed<<<g, 256, 0, s>>>(E, c->tab, c->esdf_seed_list, c->frontier[0], c->esdf_seed_val, c->d_state);
       k_esdf_seed_commit<<<g, 256, 0, s>>>(E, c->tab, c->esdf_seed_list, c->esdf_seed_val, c->d_state);
@@ -585,7 +795,7 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
     }
     if (c->profiling) cudaEventRecord(c->sev[1], s);
     {
-      const int per_sm = nb <= 256 ? 1 : c->esdf_ctas_wide;
+      const int per_sm = (nb <= 256 && !pending) ? 1 : c->esdf_ctas_wide;
       c->esdf_grid_raise = c->esdf_grid_lower = c->esdf_sms * per_sm;
     }
     {
@@ -600,7 +810,7 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
     k_esdf_parents<<<148 * 8, 256, 0, s>>>(E, c->tab, c->esdf_touched, c->d_state);
     if (c->profiling) cudaEventRecord(c->sev[3], s);
     launches += 3;
-    if (!batch && clear_updated_flag) {
+    if (nb > 0 && !batch && clear_updated_flag) {
       k_esdf_clear_tsdf_flag<<<grid_for(nb, 256), 256, 0, s>>>(c->tab, c->esdf_block_list, c->d_state);
       launches += 1;
     }
@@ -610,7 +820,7 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
   VBX_CUDA(c, cudaStreamSynchronize(s));
   VBX_CUDA(c, cudaGetLastError());
   VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-  if (c->profiling && nb > 0) {
+  if (c->profiling && (nb > 0 || pending)) {
     for (int m = 0; m < 3; ++m) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, c->sev[m], c->sev[m + 1]) == cudaSuccess) {
