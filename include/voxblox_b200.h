@@ -157,7 +157,10 @@ VBX_API int vbx_tsdf_integrate_device(vbx_ctx* ctx, int kind, const float q_wxyz
  * [0] normal rays/bundles cast  [1] clearing rays/bundles cast  [2] ray-voxel updates
  * [3] distinct voxels touched   [4] distinct blocks touched     [5] blocks allocated
  * [6] valid points              [7] kernels launched            [8] kernels launched by all
- * integrate calls since vbx_create                               [9..15] reserved
+ * integrate calls since vbx_create   [9] / [10] bundles / points folded a second time with IEEE
+ * division (diagnostic)   [11] passes the call needed (> 1 when its update records exceed
+ * vbx_engine_options.max_updates_per_pass: the synchronous calls then emit and apply contiguous
+ * ray ranges one after the other, same result; [3] counts a voxel once per pass)  [12..15] reserved
  * After asynchronous submissions: the counters of the last scan collected (all, after vbx_sync). */
 VBX_API int vbx_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
 /* Device time (ms, CUDA events on the context's stream) of the last integrate /

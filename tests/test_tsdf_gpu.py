@@ -114,6 +114,37 @@ def test_far_clearing_points_use_wide_keys():
     _assert_parity(rep)
 
 
+@pytest.mark.parametrize("kind,order,cfg_kw", [
+    (1, po.ORDER_REFERENCE, {}), (2, po.ORDER_CANONICAL, {}),
+    (2, po.ORDER_CANONICAL, dict(enable_anti_grazing=1)), (1, po.ORDER_REFERENCE, dict(integration_order_mode=1))])
+def test_more_updates_than_one_pass_holds(kind, order, cfg_kw):
+    """K > max_updates_per_pass: the call is applied in passes over contiguous ray ranges and
+    must equal the one-pass result (= the oracle) bit for bit; a single ray that does not fit is
+    refused loudly."""
+    scans = _small_scans(2)
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1, **cfg_kw)
+    small = vb.EngineOptions(max_updates_per_pass=4096 if kind == 2 else 60000)
+    layer = vb.Layer(0.1, 16, engine_options=small)
+    integ = vb.TsdfIntegratorFactory.create(kind, cfg, layer)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4, integrator_threads=1,
+                                                           **cfg_kw), 0.1, 16)
+    for s in scans:
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(kind, s, order=order)
+        gc, oc = integ.counters(), omap.counters()
+        assert gc["passes"] > 1, gc
+        for k in ("rays", "clear_rays", "updates", "blocks_touched", "blocks_allocated"):
+            assert gc[k] == oc[k], (k, gc, oc)
+    rep = compare_tsdf(layer, omap)
+    print(rep, gc)
+    _assert_parity(rep)
+    assert rep["n_bit_exact"] == rep["n_voxels"], rep
+    tiny = vb.Layer(0.1, 16, engine_options=vb.EngineOptions(max_updates_per_pass=8))
+    integ2 = vb.TsdfIntegratorFactory.create(kind, cfg, tiny)
+    with pytest.raises(vb.VoxbloxError):
+        integ2.integratePointCloud((scans[0][2], scans[0][3]), scans[0][0], scans[0][1])
+
+
 def test_degenerate_clouds():
     cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4)
     layer = vb.Layer(0.1, 16)

@@ -567,7 +567,7 @@ class TsdfIntegratorBase:
                         "vbx_get_counters")
         names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
                  "blocks_allocated", "valid_points", "kernel_launches", "kernel_launches_total", "refolded_bundles",
-                 "refolded_points"]
+                 "refolded_points", "passes"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def lastDeviceMs(self) -> float:

@@ -235,6 +235,7 @@ struct vbx_ctx {
   uint32_t esdf_pending_raise = 0, esdf_pending_open = 0;  // raise_ / open_ entries queued by addNewRobotPosition
   bool maybe_esdf_only = false;                            // some slot may carry kSlotNoTsdf
   // reporting
+  uint32_t last_passes = 1;  // passes the last synchronous integrate call needed (K > max_updates_per_pass)
   uint64_t counters[16] = {0};
   uint64_t esdf_counters[16] = {0};
   uint64_t shard_front_counters[4] = {0};

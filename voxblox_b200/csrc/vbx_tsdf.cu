@@ -71,6 +71,9 @@ struct ScanParams {
   // the number of voxels a ray updates is known from its DDA set-up alone (no anti-grazing, not the
   // Fast integrator): one walk that creates blocks AND writes the update records
   int single_walk;
+  // a call whose update records do not fit max_updates_per_pass is emitted and applied in several
+  // passes over contiguous ray-slot ranges [emit_lo, emit_hi); emit_base = off[emit_lo]
+  uint32_t emit_lo, emit_hi, emit_base;
 };
 
 // MixedThreadSafeIndex::getNextIndexImpl, integrator_utils.cc:54-63
@@ -735,6 +738,16 @@ __global__ void k_set_total(const uint32_t* __restrict__ off, uint32_t n, uint64
   st->total_updates = total;
 }
 
+// A call that is applied in several passes (K > max_updates_per_pass): before each pass.  Blocks
+// created by earlier passes already own their slots; the apply work lists restart.
+__global__ void k_pass_begin(ScanState* st, unsigned long long pass_updates) {
+  st->error &= ~kErrUpdatesFull;
+  st->total_updates = st->error ? 0ull : pass_updates;
+  st->n_new = 0;
+  st->n_long = 0;
+  st->n_verify = 0;
+}
+
 // After the last walk that can create blocks: pool slots for the blocks created by this call
 // (updateLayerWithStoredBlocks, cc:137-147); a new block is born with all updated bits set (cc:128).
 __global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_t* __restrict__ nb_out, ScanState* st) {
@@ -768,6 +781,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
                                     uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t c = cnt[i];
   if (c == 0 || st->total_updates == 0) return;  // (a failed / to-be-redone call emits nothing)
+  if (i < P.emit_lo || i >= P.emit_hi) return;   // (not in this pass)
   const float4 rp = ray_p[i];
   const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
   const F3 point_G = f3(rp.x, rp.y, rp.z);
@@ -778,7 +792,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
   uint32_t emitted = 0;
   int lbx = INT_MIN, lby = INT_MIN, lbz = INT_MIN;
   uint32_t hp = 0;
-  const uint32_t base = off[i];
+  const uint32_t base = off[i] - P.emit_base;
   const int mask = (1 << P.L) - 1;
   const int lim = (kCoordBias - 1) << P.L;
   for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
@@ -870,7 +884,7 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
   for (uint32_t b = warp; b < n_rays; b += n_warps) {
     const uint32_t i = ray_list[b];
     const uint32_t c = cnt[i];
-    if (c == 0) continue;
+    if (c == 0 || i < P.emit_lo || i >= P.emit_hi) continue;
     const float4 rp = ray_p[i];
     const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
     Dda d;
@@ -924,7 +938,7 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
       continue;
     }
     // 3. records, 32 steps at a time
-    const uint32_t base = off[i];
+    const uint32_t base = off[i] - P.emit_base;
     int cbx = INT_MIN, cby = INT_MIN, cbz = INT_MIN;  // block of the previous chunk's last step
     uint32_t chp = 0u;
     for (unsigned int r0 = 0; r0 <= len; r0 += 32u) {
@@ -1641,6 +1655,39 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   return sort_and_apply(c, P, K, n_touched, mk, launches);
 }
 
+// The back half of a call whose K exceeds max_updates_per_pass, in passes (see integrate_device).
+template <typename KeyT>
+static int apply_in_passes(vbx_ctx* c, ScanParams P, const KeyT* keys, Marks& mk, uint64_t* launches) {
+  cudaStream_t s = c->stream;
+  const uint32_t n = P.n;
+  std::vector<uint32_t> off(n + 1);
+  VBX_CUDA(c, cudaMemcpyAsync(off.data(), c->off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  uint32_t lo = 0, passes = 0;
+  while (lo < n) {
+    // the longest slot range starting at lo whose records fit
+    const uint64_t room = (uint64_t)off[lo] + c->max_updates;
+    uint32_t hi = (uint32_t)(std::upper_bound(off.begin() + lo, off.end(), room,
+                                              [](uint64_t v, uint32_t o) { return v < (uint64_t)o; }) -
+                             off.begin());
+    hi = hi > 0 ? hi - 1 : 0;  // off[hi] <= room
+    if (hi <= lo) return fail(c, VBX_E_CAPACITY, "a single ray has more updates than max_updates_per_pass");
+    const unsigned long long kp = (unsigned long long)off[hi] - off[lo];
+    if (kp > 0) {
+      P.emit_lo = lo;
+      P.emit_hi = hi;
+      P.emit_base = off[lo];
+      k_pass_begin<<<1, 1, 0, s>>>(c->d_state, kp);
+      *launches += 1;
+      if (int rc = back_half<KeyT>(c, P, keys, kp, 0, mk, launches)) return rc;
+      ++passes;
+    }
+    lo = hi;
+  }
+  c->last_passes = passes;
+  return VBX_OK;
+}
+
 static void fill_params(vbx_ctx* c, int kind, const float q[4], const float t[3], uint32_t n, int freespace,
                         ScanParams& P) {
   const vbx_tsdf_config& cfg = c->cfg;
@@ -1704,6 +1751,9 @@ static void fill_params(vbx_ctx* c, int kind, const float q[4], const float t[3]
   P.slot_lo = 0;
   P.slot_hi = n;
   P.shard = 0;
+  P.emit_lo = 0;
+  P.emit_hi = 0xffffffffu;
+  P.emit_base = 0;
   P.single_walk = (kind != VBX_FAST && !(kind == VBX_MERGED && cfg.enable_anti_grazing)) ? 1 : 0;
 }
 
@@ -1747,7 +1797,8 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
     launches += 11;
   }
 
-  uint32_t new_blocks_first_attempt = 0;
+  uint32_t new_blocks_first_attempt = 0, chunk_blocks_before = 0;
+  bool chunked = false;
   const uint32_t* keys32 = nullptr;
   const uint64_t* keys64 = nullptr;
   unsigned long long K = 0;
@@ -1786,7 +1837,28 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
       VBX_CUDA(c, cudaEventRecord(c->ev1, s));
       VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
       VBX_CUDA(c, cudaStreamSynchronize(s));
-      if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+      if (c->h_state->error == kErrUpdatesFull) {
+        // More update records than one pass holds.  Nothing was emitted or applied; the per-ray
+        // tables, counts and offsets of the front half stand.  Apply the call in passes over
+        // contiguous ray-slot ranges: every voxel still sees its updates in ray-rank order, so
+        // the result is the one-pass result bit for bit.
+        chunk_blocks_before = c->n_blocks;
+        if (P.wide_keys) {
+          if (int rc = apply_in_passes<uint64_t>(c, P, keys64, mk, &launches)) return rc;
+        } else {
+          if (int rc = apply_in_passes<uint32_t>(c, P, keys32, mk, &launches)) return rc;
+        }
+        chunked = true;
+        VBX_CUDA(c, cudaEventRecord(c->ev1, s));
+        VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+        VBX_CUDA(c, cudaStreamSynchronize(s));
+      }
+      {
+        // (a call that must be redone with wide keys is redone first; its record count is judged then)
+        uint32_t err = c->h_state->error;
+        if (err & kNeedWideKeys) err &= ~kErrUpdatesFull;
+        if (int rc = check_state_errors(c, err)) return rc;
+      }
       c->n_blocks = c->h_state->n_blocks;
       if (!(c->h_state->error & kNeedWideKeys)) {
         K = c->h_state->total_found;
@@ -1816,7 +1888,9 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   c->counters[2] = K;
   c->counters[3] = c->h_state->n_voxels;
   c->counters[4] = n_touched;
-  c->counters[5] = (uint64_t)c->h_state->n_new + new_blocks_first_attempt;
+  c->counters[5] = chunked ? (uint64_t)(c->n_blocks - chunk_blocks_before)
+                           : (uint64_t)c->h_state->n_new + new_blocks_first_attempt;
+  c->counters[11] = chunked ? c->last_passes : 1;
   c->counters[9] = c->h_state->n_refold;
   c->counters[10] = c->h_state->refold_members;
   c->counters[6] = (kind == VBX_MERGED) ? c->h_state->n_valid_points
