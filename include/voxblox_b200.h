@@ -253,6 +253,26 @@ VBX_API int vbx_esdf_get_config(const vbx_ctx* ctx, vbx_esdf_config* out);
  * [4] voxels raised [5] wavefront relaxations R [6] wavefront sweeps [7] kernels */
 VBX_API int vbx_esdf_get_counters(const vbx_ctx* ctx, uint64_t out[16]);
 
+/* Meshing: MeshIntegrator<TsdfVoxel> (mesh/mesh_integrator.h) over the device map.
+ * MeshIntegratorConfig (mesh_integrator.h:46-66) minus integrator_threads. */
+typedef struct vbx_mesh_config {
+  int32_t use_color; /* true  */
+  float min_weight;  /* 1e-4  */
+} vbx_mesh_config;
+/* generateMesh(only_mesh_updated_blocks, clear_updated_flag) (mesh_integrator.h:132-160): marching cubes
+ * (mesh/marching_cubes.h:74-164) over every TSDF block, or over those whose Update::kMesh bit is set;
+ * clear_updated_flag resets that bit (:171-175).  The meshes stay in device memory until the next
+ * call; n_blocks / n_vertices report their size. */
+VBX_API int vbx_mesh_generate(vbx_ctx* ctx, const vbx_mesh_config* cfg, int only_mesh_updated_blocks,
+                              int clear_updated_flag, uint64_t* n_blocks, uint64_t* n_vertices);
+/* The result of the last vbx_mesh_generate: idx3 = 3*n_blocks block indices ascending by (x, y, z);
+ * block b owns vertices [first_vertex[b], first_vertex[b+1]) (n_blocks + 1 entries); vertices / normals
+ * = 3 floats per vertex in the reference's order (Mesh::vertices / normals, mesh/mesh.h:151-154), colors =
+ * r,g,b,a per vertex (only after use_color).  Mesh::indices is 0..n-1 per block
+ * (marching_cubes.h:97-99) and is not transferred.  Any pointer may be NULL. */
+VBX_API int vbx_mesh_download(vbx_ctx* ctx, int32_t* idx3, uint64_t* first_vertex, float* vertices, float* normals,
+                              uint8_t* colors);
+
 VBX_API int vbx_sync(vbx_ctx* ctx);
 
 /* Ray-range sharding over the GPUs of one box (BASELINE.json north_star).

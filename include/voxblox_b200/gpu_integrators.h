@@ -18,6 +18,8 @@
 #include <voxblox/core/layer.h>
 #include <voxblox/core/voxel.h>
 #include <voxblox/integrator/esdf_integrator.h>
+#include <voxblox/mesh/mesh_integrator.h>
+#include <voxblox/mesh/mesh_layer.h>
 #include <voxblox/integrator/tsdf_integrator.h>
 
 #include "../voxblox_b200.h"
@@ -261,6 +263,53 @@ class GpuEsdfIntegrator {
  private:
   vbx_ctx* ctx_;
   Layer<EsdfVoxel>* esdf_layer_;
+};
+
+/// MeshIntegrator<TsdfVoxel>::generateMesh (mesh/mesh_integrator.h:132-160) on the device map owned by
+/// a GpuTsdfIntegrator; the MeshLayer stays the caller's host object, as in the reference.
+class GpuMeshIntegrator {
+ public:
+  GpuMeshIntegrator(const MeshIntegratorConfig& config, GpuTsdfIntegrator* tsdf, MeshLayer* mesh_layer)
+      : config_(config), ctx_(CHECK_NOTNULL(tsdf)->context()), mesh_layer_(CHECK_NOTNULL(mesh_layer)) {}
+
+  void generateMesh(bool only_mesh_updated_blocks, bool clear_updated_flag) {
+    vbx_mesh_config pod;
+    pod.use_color = config_.use_color ? 1 : 0;
+    pod.min_weight = config_.min_weight;
+    uint64_t nb = 0, nv = 0;
+    gpu_detail::check(ctx_, vbx_mesh_generate(ctx_, &pod, only_mesh_updated_blocks ? 1 : 0, clear_updated_flag ? 1 : 0, &nb, &nv),
+                      "vbx_mesh_generate");
+    if (nb == 0) return;
+    std::vector<int32_t> idx(3 * nb);
+    std::vector<uint64_t> first(nb + 1);
+    std::vector<float> vertices(3 * nv), normals(3 * nv);
+    std::vector<uint8_t> colors(config_.use_color ? 4 * nv : 0);
+    gpu_detail::check(ctx_, vbx_mesh_download(ctx_, idx.data(), first.data(), vertices.data(), normals.data(),
+                                              (config_.use_color && nv) ? colors.data() : nullptr),
+                      "vbx_mesh_download");
+    for (uint64_t b = 0; b < nb; ++b) {
+      // allocateMeshPtrByIndex + updateMeshForBlock (mesh_integrator.h:146-149, :238-260)
+      Mesh::Ptr mesh = mesh_layer_->allocateMeshPtrByIndex(BlockIndex(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2]));
+      mesh->clear();
+      const uint64_t lo = first[b], n = first[b + 1] - first[b];
+      mesh->vertices.reserve(n);
+      mesh->normals.reserve(n);
+      mesh->indices.reserve(n);
+      if (config_.use_color) mesh->colors.reserve(n);
+      for (uint64_t i = lo; i < lo + n; ++i) {
+        mesh->vertices.emplace_back(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]);
+        mesh->normals.emplace_back(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+        mesh->indices.push_back(i - lo);
+        if (config_.use_color) mesh->colors.emplace_back(colors[4 * i], colors[4 * i + 1], colors[4 * i + 2], colors[4 * i + 3]);
+      }
+      mesh->updated = true;
+    }
+  }
+
+ private:
+  MeshIntegratorConfig config_;
+  vbx_ctx* ctx_;
+  MeshLayer* mesh_layer_;
 };
 
 }  // namespace voxblox

@@ -205,6 +205,54 @@ int main() {
                 a.size(), b.size(), same ? 1 : 0, diff, free_v, occ_v, gpu.syncLayer(0));
     if (!same || diff != 0 || free_v == 0 || occ_v == 0 || tsdf_g.getNumberOfAllocatedBlocks() != 0) ++failures;
   }
+  // Meshing through the adapter against the reference's own MeshIntegrator on the SAME host layer
+  // (the Simple integrator's device map is bit-identical to the CPU one, so every vertex must be too).
+  {
+    Layer<TsdfVoxel> cpu_layer(voxel_size, 16), gpu_layer(voxel_size, 16);
+    TsdfIntegratorBase::Ptr cpu = TsdfIntegratorFactory::create("simple", config, &cpu_layer);
+    GpuTsdfIntegrator gpu(TsdfIntegratorType::kSimple, config, &gpu_layer);
+    MeshLayer mesh_c(cpu_layer.block_size()), mesh_g(gpu_layer.block_size());
+    MeshIntegratorConfig mc;
+    mc.integrator_threads = 1;
+    MeshIntegrator<TsdfVoxel> cm(mc, &cpu_layer, &mesh_c);
+    GpuMeshIntegrator gm(mc, &gpu, &mesh_g);
+    size_t vertices = 0, diff = 0, blocks_differ = 0;
+    for (int k = 0; k < 3; ++k) {
+      Transformation T;
+      Pointcloud pts;
+      Colors cols;
+      makeScan(k, &T, &pts, &cols);
+      cpu->integratePointCloud(T, pts, cols);
+      gpu.integratePointCloud(T, pts, cols);
+      cm.generateMesh(true, true);
+      gm.generateMesh(true, true);
+    }
+    BlockIndexList a, b;
+    mesh_c.getAllAllocatedMeshes(&a);
+    mesh_g.getAllAllocatedMeshes(&b);
+    if (a.size() != b.size()) ++blocks_differ;
+    for (const BlockIndex& bi : a) {
+      Mesh::ConstPtr x = static_cast<const MeshLayer&>(mesh_c).getMeshPtrByIndex(bi);
+      Mesh::ConstPtr y = std::find(b.begin(), b.end(), bi) != b.end() ? static_cast<const MeshLayer&>(mesh_g).getMeshPtrByIndex(bi)
+                                                                       : Mesh::ConstPtr();
+      if (!y || x->vertices.size() != y->vertices.size() || x->colors.size() != y->colors.size() ||
+          x->indices.size() != y->indices.size()) {
+        ++blocks_differ;
+        continue;
+      }
+      vertices += x->vertices.size();
+      for (size_t i = 0; i < x->vertices.size(); ++i) {
+        const bool same = x->vertices[i] == y->vertices[i] && x->normals[i] == y->normals[i] &&
+                          x->indices[i] == y->indices[i] && x->colors[i].r == y->colors[i].r &&
+                          x->colors[i].g == y->colors[i].g && x->colors[i].b == y->colors[i].b &&
+                          x->colors[i].a == y->colors[i].a;
+        if (!same) ++diff;
+      }
+    }
+    std::printf("mesh: blocks cpu %zu gpu %zu, block mismatches %zu, vertices %zu, differing %zu\n", a.size(), b.size(),
+                blocks_differ, vertices, diff);
+    if (blocks_differ || diff || vertices == 0) ++failures;
+  }
   std::printf(failures ? "ADAPTER TEST FAILED\n" : "ADAPTER TEST OK\n");
   return failures ? 1 : 0;
 }

@@ -113,6 +113,16 @@ class OracleLib:
         lib.vbo_esdf_set_full_euclidean.argtypes = [C.c_void_p, C.c_int]
         lib.vbo_esdf_add_robot_position.restype = C.c_int
         lib.vbo_esdf_add_robot_position.argtypes = [C.c_void_p, C.c_void_p]
+        lib.vbo_mesh_generate.restype = C.c_int
+        lib.vbo_mesh_generate.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int]
+        lib.vbo_mesh_num_blocks.restype = C.c_uint64
+        lib.vbo_mesh_num_blocks.argtypes = [C.c_void_p]
+        lib.vbo_mesh_block_indices.argtypes = [C.c_void_p, C.c_void_p]
+        lib.vbo_mesh_get.restype = C.c_uint64
+        lib.vbo_mesh_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.vbo_mc_tables.restype = C.c_int
+        lib.vbo_mc_tables.argtypes = [C.c_void_p, C.c_void_p]
         self.lib = lib
         assert lib.vbo_impl_name().decode() == which
 
@@ -223,3 +233,32 @@ class OracleMap:
         rc = self.lib.vbo_esdf_add_robot_position(self.h, p.ctypes.data)
         if rc != 0:
             raise RuntimeError(f"vbo_esdf_add_robot_position rc={rc}")
+
+    # ---- MeshIntegrator<TsdfVoxel> (mesh/mesh_integrator.h) into the map's MeshLayer
+    def mesh_generate(self, use_color: bool = True, min_weight: float = 1e-4, only_mesh_updated_blocks: bool = False,
+                      clear_updated_flag: bool = True):
+        rc = self.lib.vbo_mesh_generate(self.h, int(use_color), float(min_weight), int(only_mesh_updated_blocks),
+                                        int(clear_updated_flag))
+        if rc != 0:
+            raise RuntimeError(f"vbo_mesh_generate rc={rc}")
+
+    def mesh_block_indices(self) -> np.ndarray:
+        n = int(self.lib.vbo_mesh_num_blocks(self.h))
+        out = np.zeros((n, 3), dtype=np.int32)
+        if n:
+            self.lib.vbo_mesh_block_indices(self.h, out.ctypes.data)
+        return out
+
+    def mesh_block(self, index):
+        """(vertices [n,3] f32, normals [n,3] f32, colors [n,4] u8 or None, updated) of one block mesh"""
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        n = int(self.lib.vbo_mesh_get(self.h, idx.ctypes.data, None, None, None, None, None))
+        if n >= 2 ** 63:
+            raise KeyError(tuple(int(v) for v in idx))
+        v = np.zeros((n, 3), dtype=np.float32)
+        nr = np.zeros((n, 3), dtype=np.float32)
+        col = np.zeros((n, 4), dtype=np.uint8)
+        has, upd = C.c_int(0), C.c_int(0)
+        self.lib.vbo_mesh_get(self.h, idx.ctypes.data, v.ctypes.data, nr.ctypes.data, col.ctypes.data,
+                              C.byref(has), C.byref(upd))
+        return v, nr, (col if has.value else None), bool(upd.value)

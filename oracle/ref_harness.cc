@@ -15,6 +15,9 @@
 #include "voxblox/core/voxel.h"
 #include "voxblox/integrator/esdf_integrator.h"
 #include "voxblox/integrator/tsdf_integrator.h"
+#include "voxblox/mesh/marching_cubes.h"
+#include "voxblox/mesh/mesh_integrator.h"
+#include "voxblox/mesh/mesh_layer.h"
 
 #include "vbo_api.h"
 
@@ -26,6 +29,7 @@ struct Handle {
   std::unique_ptr<voxblox::Layer<voxblox::EsdfVoxel>> esdf;
   voxblox::TsdfIntegratorBase::Ptr integrators[4];
   std::unique_ptr<voxblox::EsdfIntegrator> esdf_integrator;
+  std::unique_ptr<voxblox::MeshLayer> mesh;
   double last_seconds = 0.0;
 };
 
@@ -230,6 +234,86 @@ int vbo_esdf_add_robot_position(void* hv, const float p[3]) {
   Handle* h = static_cast<Handle*>(hv);
   if (!h->esdf_integrator) return 2;
   h->esdf_integrator->addNewRobotPosition(voxblox::Point(p[0], p[1], p[2]));
+  return 0;
+}
+
+
+int vbo_mesh_generate(void* hv, int use_color, float min_weight, int only_mesh_updated_blocks,
+                      int clear_updated_flag) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h->mesh) h->mesh.reset(new voxblox::MeshLayer(h->tsdf->block_size()));
+  voxblox::MeshIntegratorConfig cfg;
+  cfg.use_color = use_color != 0;
+  cfg.min_weight = min_weight;
+  cfg.integrator_threads = 1;
+  voxblox::MeshIntegrator<voxblox::TsdfVoxel> integrator(cfg, h->tsdf.get(), h->mesh.get());
+  const auto t0 = std::chrono::steady_clock::now();
+  integrator.generateMesh(only_mesh_updated_blocks != 0, clear_updated_flag != 0);
+  h->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+uint64_t vbo_mesh_num_blocks(void* hv) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h->mesh) return 0;
+  voxblox::BlockIndexList have;
+  h->mesh->getAllAllocatedMeshes(&have);
+  return have.size();
+}
+
+void vbo_mesh_block_indices(void* hv, int32_t* out) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h->mesh) return;
+  voxblox::BlockIndexList blocks;
+  h->mesh->getAllAllocatedMeshes(&blocks);
+  std::sort(blocks.begin(), blocks.end(), [](const voxblox::BlockIndex& a, const voxblox::BlockIndex& b) {
+    if (a.x() != b.x()) return a.x() < b.x();
+    if (a.y() != b.y()) return a.y() < b.y();
+    return a.z() < b.z();
+  });
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    out[3 * i + 0] = blocks[i].x();
+    out[3 * i + 1] = blocks[i].y();
+    out[3 * i + 2] = blocks[i].z();
+  }
+}
+
+uint64_t vbo_mesh_get(void* hv, const int32_t idx[3], float* vertices, float* normals, uint8_t* colors,
+                      int* has_colors, int* updated) {
+  Handle* h = static_cast<Handle*>(hv);
+  const voxblox::BlockIndex bi(idx[0], idx[1], idx[2]);
+  if (!h->mesh) return ~0ull;
+  voxblox::BlockIndexList have;
+  h->mesh->getAllAllocatedMeshes(&have);
+  if (std::find(have.begin(), have.end(), bi) == have.end()) return ~0ull;
+  voxblox::Mesh::ConstPtr m = static_cast<const voxblox::MeshLayer*>(h->mesh.get())->getMeshPtrByIndex(bi);
+  const size_t n = m->vertices.size();
+  for (size_t i = 0; i < n; ++i) {
+    if (m->indices[i] != i) return ~0ull - 1;  // (never: marching_cubes.h:97-99)
+    for (int k = 0; k < 3; ++k) {
+      if (vertices) vertices[3 * i + k] = m->vertices[i](k);
+      if (normals) normals[3 * i + k] = m->normals[i](k);
+    }
+    if (colors && m->colors.size() == n) {
+      colors[4 * i + 0] = m->colors[i].r;
+      colors[4 * i + 1] = m->colors[i].g;
+      colors[4 * i + 2] = m->colors[i].b;
+      colors[4 * i + 3] = m->colors[i].a;
+    }
+  }
+  if (has_colors) *has_colors = (n > 0 && m->colors.size() == n) ? 1 : 0;
+  if (updated) *updated = m->updated ? 1 : 0;
+  return n;
+}
+
+int vbo_mc_tables(int32_t tri[256 * 16], int32_t edges[12 * 2]) {
+  for (int i = 0; i < 256; ++i) {
+    for (int j = 0; j < 16; ++j) tri[16 * i + j] = voxblox::MarchingCubes::kTriangleTable[i][j];
+  }
+  for (int i = 0; i < 12; ++i) {
+    edges[2 * i] = voxblox::MarchingCubes::kEdgeIndexPairs[i][0];
+    edges[2 * i + 1] = voxblox::MarchingCubes::kEdgeIndexPairs[i][1];
+  }
   return 0;
 }
 

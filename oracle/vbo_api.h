@@ -111,6 +111,23 @@ int vbo_esdf_set_full_euclidean(void* h, int full_euclidean);
 /* EsdfIntegrator::addNewRobotPosition (esdf_integrator.cc:25-92) */
 int vbo_esdf_add_robot_position(void* h, const float p[3]);
 
+
+/* MeshIntegrator<TsdfVoxel>::generateMesh(only_mesh_updated_blocks, clear_updated_flag)
+ * (mesh/mesh_integrator.h:132-160) into the map's own MeshLayer (mesh/mesh_layer.h); marching
+ * cubes per mesh/marching_cubes.h:44-164, vertex colours per mesh_integrator.h:368-388. */
+int vbo_mesh_generate(void* h, int use_color, float min_weight, int only_mesh_updated_blocks,
+                      int clear_updated_flag);
+uint64_t vbo_mesh_num_blocks(void* h);           /* MeshLayer::getAllAllocatedMeshes */
+void vbo_mesh_block_indices(void* h, int32_t* out); /* 3*M int32, sorted by (x, y, z) */
+/* One block mesh: returns its vertex count (UINT64_MAX if there is no mesh at idx).  vertices /
+ * normals: 3 floats per vertex, colors: 4 bytes per vertex (written only when the mesh has
+ * colours); any pointer may be null.  Mesh::indices is always 0..n-1 (marching_cubes.h:97-99). */
+uint64_t vbo_mesh_get(void* h, const int32_t idx[3], float* vertices, float* normals, uint8_t* colors,
+                      int* has_colors, int* updated);
+/* MarchingCubes::kTriangleTable / kEdgeIndexPairs (src/mesh/marching_cubes.cc:33-293);
+ * returns 0 from the reference library, 1 from the restatement (which holds no second copy). */
+int vbo_mc_tables(int32_t tri[256 * 16], int32_t edges[12 * 2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "vbo_api.h"
+#include "../voxblox_b200/csrc/vbx_mc_tables.h"  // generated case table, pinned to the reference table by tests/test_mesh_cpu.py
 
 namespace {
 
@@ -326,6 +327,13 @@ struct Map {
   BucketQ open;
   std::queue<L3> raise;
   std::unordered_set<I3, HashI3> updated_blocks;
+  // MeshLayer (mesh/mesh_layer.h:22-310): block index -> Mesh (mesh/mesh.h:36-164)
+  struct MeshBlk {
+    std::vector<V3> vertices, normals;
+    std::vector<Rgba> colors;
+    bool updated = false;
+  };
+  std::unordered_map<I3, MeshBlk, HashI3> mesh;
   // bookkeeping
   double last_seconds = 0;
   uint64_t counters[8] = {0};
@@ -799,6 +807,156 @@ struct Map {
     }
   }
 
+  // ------------------------------------------------------------------ meshing
+  // Block::computeCoordinatesFromVoxelIndex (core/block.h:90-92): origin_ + centre, with
+  // origin_ = float(block index) * block_size (core/common.h:196-201, core/layer.h:133-140)
+  V3 blockOrigin(const I3& bi) const {
+    return V3{static_cast<float>(bi.x) * block_size, static_cast<float>(bi.y) * block_size,
+              static_cast<float>(bi.z) * block_size};
+  }
+  // utils/meshing_utils.h:16-24
+  static bool sdfIfValid(const TsdfVox& v, float min_weight, float* sdf) {
+    if (v.weight <= min_weight) return false;
+    *sdf = v.distance;
+    return true;
+  }
+  // mesh/marching_cubes.h:150-164
+  static V3 interpolateVertex(V3 v1, V3 v2, float sdf1, float sdf2) {
+    const float kMinSdfDifference = 1e-6f;
+    const float diff = sdf1 - sdf2;
+    if (std::abs(diff) >= kMinSdfDifference) {
+      const float t = sdf1 / diff;
+      return v1 + (v2 - v1) * t;
+    }
+    return (v1 + v2) * 0.5f;
+  }
+  // mesh/marching_cubes.h:74-113 (the Mesh overload) with :115-147
+  static void meshCube(const V3 corner[8], const float sdf[8], MeshBlk* out) {
+    static const uint64_t kTri[256] = {VBX_MC_TRIANGLE_WORDS};
+    static const int kPairs[12][2] = {VBX_MC_EDGE_PAIRS};
+    int index = 0;
+    for (int i = 0; i < 8; ++i) index |= (sdf[i] < 0 ? (1 << i) : 0);
+    if (index == 0) return;
+    V3 edge[12];
+    for (int i = 0; i < 12; ++i) {
+      const int a = kPairs[i][0], b = kPairs[i][1];
+      if ((sdf[a] < 0 && sdf[b] >= 0) || (sdf[a] >= 0 && sdf[b] < 0)) {
+        edge[i] = interpolateVertex(corner[a], corner[b], sdf[a], sdf[b]);
+      }
+    }
+    const uint64_t row = kTri[index];
+    for (int col = 0; col < 15 && ((row >> (4 * col)) & 0xF) != 0xF; col += 3) {
+      const V3 p0 = edge[(row >> (4 * (col + 2))) & 0xF];
+      const V3 p1 = edge[(row >> (4 * (col + 1))) & 0xF];
+      const V3 p2 = edge[(row >> (4 * col)) & 0xF];
+      out->vertices.push_back(p0);
+      out->vertices.push_back(p1);
+      out->vertices.push_back(p2);
+      const V3 n = unit3(cross3(p1 - p0, p2 - p0));
+      out->normals.push_back(n);
+      out->normals.push_back(n);
+      out->normals.push_back(n);
+    }
+  }
+  // mesh_integrator.h:262-290 (inside) and :292-366 (border): the cube whose lowest corner is voxel
+  // `vi` of block `bi`; corners outside the block come from the neighbouring blocks
+  void meshOneCube(const I3& bi, const Blk<TsdfVox>& blk, const I3& vi, float min_weight, MeshBlk* out) const {
+    static const int kOff[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
+                                   {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};  // cube_index_offsets_, :94-95
+    const V3 coords = blockOrigin(bi) + centerPoint(L3{vi.x, vi.y, vi.z}, voxel_size);
+    V3 corner[8];
+    float sdf[8];
+    for (int i = 0; i < 8; ++i) {
+      int cx = vi.x + kOff[i][0], cy = vi.y + kOff[i][1], cz = vi.z + kOff[i][2];
+      const Blk<TsdfVox>* src = &blk;
+      if (cx >= vps || cy >= vps || cz >= vps) {
+        I3 nb = bi;
+        if (cx >= vps) {
+          nb.x += 1;
+          cx -= vps;
+        }
+        if (cy >= vps) {
+          nb.y += 1;
+          cy -= vps;
+        }
+        if (cz >= vps) {
+          nb.z += 1;
+          cz -= vps;
+        }
+        auto it = tsdf.find(nb);
+        if (it == tsdf.end()) return;  // all_neighbors_observed = false, :358-361
+        src = it->second.get();
+      }
+      if (!sdfIfValid(src->vox[cx + vps * (cy + cz * vps)], min_weight, &sdf[i])) return;
+      const V3 off{static_cast<float>(kOff[i][0]) * voxel_size, static_cast<float>(kOff[i][1]) * voxel_size,
+                   static_cast<float>(kOff[i][2]) * voxel_size};
+      corner[i] = coords + off;
+    }
+    meshCube(corner, sdf, out);
+  }
+  // mesh_integrator.h:368-388
+  void meshColors(const I3& bi, const Blk<TsdfVox>& blk, float min_weight, MeshBlk* out) const {
+    out->colors.assign(out->vertices.size(), Rgba{0, 0, 0, 0});
+    const V3 origin = blockOrigin(bi);
+    const float block_size_inv = static_cast<float>(1.0 / block_size);
+    for (size_t i = 0; i < out->vertices.size(); ++i) {
+      const V3 v = out->vertices[i];
+      const L3 vi = gridIndex(v - origin, voxel_size_inv);  // computeVoxelIndexFromCoordinates, core/block.h:65-70
+      const TsdfVox* vox = nullptr;
+      if (vi.x >= 0 && vi.x < vps && vi.y >= 0 && vi.y < vps && vi.z >= 0 && vi.z < vps) {
+        vox = &blk.vox[vi.x + vps * (vi.y + vi.z * vps)];
+      } else {
+        const L3 nbl = gridIndex(v, block_size_inv);  // Layer::computeBlockIndexFromCoordinates, core/layer.h:128-131
+        const I3 nb{static_cast<int>(nbl.x), static_cast<int>(nbl.y), static_cast<int>(nbl.z)};
+        auto it = tsdf.find(nb);
+        if (it == tsdf.end()) continue;  // (the reference dereferences a null block pointer here)
+        // Block::getVoxelByCoordinates -> computeTruncatedVoxelIndexFromCoordinates, core/block_inl.h:29-40
+        const L3 t = gridIndex(v - blockOrigin(nb), voxel_size_inv);
+        const int64_t mx = vps - 1;
+        const int64_t tx = std::max<int64_t>(std::min(t.x, mx), 0), ty = std::max<int64_t>(std::min(t.y, mx), 0),
+                      tz = std::max<int64_t>(std::min(t.z, mx), 0);
+        vox = &it->second->vox[tx + vps * (ty + tz * vps)];
+      }
+      if (vox->weight > min_weight) out->colors[i] = vox->color;  // utils/meshing_utils.h:45-54
+    }
+  }
+  // MeshIntegrator::generateMesh (mesh_integrator.h:132-160) + updateMeshForBlock (:238-260) +
+  // extractBlockMesh (:179-236, the cube order of the four loops)
+  void generateMesh(bool use_color, float min_weight, bool only_updated, bool clear_flag) {
+    std::vector<I3> blocks;
+    for (const auto& kv : tsdf) {
+      if (!only_updated || (kv.second->updated & 2)) blocks.push_back(kv.first);
+    }
+    for (const I3& bi : blocks) {
+      MeshBlk& mb = mesh[bi];  // allocateMeshPtrByIndex
+      mb.vertices.clear();
+      mb.normals.clear();
+      mb.colors.clear();
+      Blk<TsdfVox>& blk = *tsdf.find(bi)->second;
+      I3 vi;
+      for (vi.x = 0; vi.x < vps - 1; ++vi.x) {
+        for (vi.y = 0; vi.y < vps - 1; ++vi.y) {
+          for (vi.z = 0; vi.z < vps - 1; ++vi.z) meshOneCube(bi, blk, vi, min_weight, &mb);
+        }
+      }
+      vi.x = vps - 1;  // max X plane
+      for (vi.z = 0; vi.z < vps; ++vi.z) {
+        for (vi.y = 0; vi.y < vps; ++vi.y) meshOneCube(bi, blk, vi, min_weight, &mb);
+      }
+      vi.y = vps - 1;  // max Y plane
+      for (vi.z = 0; vi.z < vps; ++vi.z) {
+        for (vi.x = 0; vi.x < vps - 1; ++vi.x) meshOneCube(bi, blk, vi, min_weight, &mb);
+      }
+      vi.z = vps - 1;  // max Z plane
+      for (vi.y = 0; vi.y < vps - 1; ++vi.y) {
+        for (vi.x = 0; vi.x < vps - 1; ++vi.x) meshOneCube(bi, blk, vi, min_weight, &mb);
+      }
+      if (use_color) meshColors(bi, blk, min_weight, &mb);
+      mb.updated = true;
+      if (clear_flag) blk.updated &= static_cast<uint8_t>(~2);  // updated().reset(Update::kMesh), :171-175
+    }
+  }
+
   // utils/planning_utils_inl.h:15-62 + esdf_integrator.cc:25-92
   typedef std::unordered_map<I3, std::vector<I3>, HashI3> HierMap;
   void sphereAround(V3 center, float radius, HierMap* out) {
@@ -1073,5 +1231,46 @@ int vbo_esdf_add_robot_position(void* hv, const float p[3]) {
   m->addRobotPosition(V3{p[0], p[1], p[2]});
   return 0;
 }
+
+
+int vbo_mesh_generate(void* hv, int use_color, float min_weight, int only_mesh_updated_blocks,
+                      int clear_updated_flag) {
+  Map* m = static_cast<Map*>(hv);
+  const auto t0 = std::chrono::steady_clock::now();
+  m->generateMesh(use_color != 0, min_weight, only_mesh_updated_blocks != 0, clear_updated_flag != 0);
+  m->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+uint64_t vbo_mesh_num_blocks(void* hv) { return static_cast<Map*>(hv)->mesh.size(); }
+void vbo_mesh_block_indices(void* hv, int32_t* out) {
+  Map* m = static_cast<Map*>(hv);
+  std::vector<I3> k;
+  for (const auto& kv : m->mesh) k.push_back(kv.first);
+  std::sort(k.begin(), k.end(), [](const I3& a, const I3& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  });
+  for (size_t i = 0; i < k.size(); ++i) {
+    out[3 * i] = k[i].x;
+    out[3 * i + 1] = k[i].y;
+    out[3 * i + 2] = k[i].z;
+  }
+}
+uint64_t vbo_mesh_get(void* hv, const int32_t idx[3], float* vertices, float* normals, uint8_t* colors,
+                      int* has_colors, int* updated) {
+  Map* m = static_cast<Map*>(hv);
+  auto it = m->mesh.find(I3{idx[0], idx[1], idx[2]});
+  if (it == m->mesh.end()) return ~0ull;
+  const Map::MeshBlk& mb = it->second;
+  const size_t n = mb.vertices.size();
+  if (vertices && n) std::memcpy(vertices, mb.vertices.data(), n * sizeof(V3));
+  if (normals && n) std::memcpy(normals, mb.normals.data(), n * sizeof(V3));
+  if (colors && mb.colors.size() == n && n) std::memcpy(colors, mb.colors.data(), n * sizeof(Rgba));
+  if (has_colors) *has_colors = (n > 0 && mb.colors.size() == n) ? 1 : 0;
+  if (updated) *updated = mb.updated ? 1 : 0;
+  return n;
+}
+int vbo_mc_tables(int32_t*, int32_t*) { return 1; }  // the restatement owns no second copy of the table
 
 }  // extern "C"

@@ -93,6 +93,14 @@ class EsdfIntegratorConfig(C.Structure):
         super().__init__(**d)
 
 
+class MeshIntegratorConfig(C.Structure):
+    """MeshIntegratorConfig (mesh/mesh_integrator.h:46-66); integrator_threads has no meaning here."""
+    _fields_ = [("use_color", C.c_int32), ("min_weight", C.c_float)]
+
+    def __init__(self, use_color: bool = True, min_weight: float = 1e-4):
+        super().__init__(use_color=int(bool(use_color)), min_weight=float(min_weight))
+
+
 class EngineOptions(C.Structure):
     """vbx_engine_options: device-side sizing (no reference counterpart)."""
     _fields_ = [("device", C.c_int32), ("max_blocks", C.c_uint32),
@@ -114,7 +122,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
            "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
-           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_esdf_add_robot_position", "vbx_esdf_clear", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_esdf_add_robot_position", "vbx_esdf_clear", "vbx_mesh_generate", "vbx_mesh_download", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
            "vbx_proto_encode_layer", "vbx_proto_encode_block", "vbx_proto_decode_block"]
 
 _lib = None
@@ -198,6 +206,10 @@ def load_library():
     lib.vbx_esdf_add_robot_position.argtypes = [vp, vp]
     lib.vbx_esdf_clear.restype = i32
     lib.vbx_esdf_clear.argtypes = [vp]
+    lib.vbx_mesh_generate.restype = i32
+    lib.vbx_mesh_generate.argtypes = [vp, C.POINTER(MeshIntegratorConfig), i32, i32, C.POINTER(u64), C.POINTER(u64)]
+    lib.vbx_mesh_download.restype = i32
+    lib.vbx_mesh_download.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.vbx_sync.restype = i32
     lib.vbx_sync.argtypes = [vp]
     lib.vbx_host_alloc.restype = i32
@@ -678,4 +690,96 @@ class EsdfIntegrator:
         ms = C.c_float(0)
         self._ctx.check(self._ctx.lib.vbx_last_device_ms(self._ctx.handle, C.byref(ms)),
                         "vbx_last_device_ms")
+        return float(ms.value)
+
+
+class Mesh:
+    """Mesh (mesh/mesh.h:36-164): the triangles of one block, three consecutive vertices each."""
+
+    def __init__(self, block_size: float, origin):
+        self.block_size = block_size
+        self.origin = np.asarray(origin, dtype=np.float32)
+        self.vertices = np.zeros((0, 3), np.float32)
+        self.normals = np.zeros((0, 3), np.float32)
+        self.colors = np.zeros((0, 4), np.uint8)
+        self.indices = np.zeros(0, np.uint64)
+        self.updated = False
+
+    def size(self) -> int:
+        return int(self.vertices.shape[0])
+
+
+class MeshLayer:
+    """MeshLayer (mesh/mesh_layer.h:22-310): block index -> Mesh, kept on the host like the
+    reference's (its consumers -- ROS publishing, PLY output -- read it there)."""
+
+    def __init__(self, block_size: float):
+        self._block_size = float(np.float32(block_size))
+        self._meshes: Dict[Tuple[int, int, int], Mesh] = {}
+
+    def block_size(self) -> float:
+        return self._block_size
+
+    def allocateMeshPtrByIndex(self, index) -> Mesh:  # mesh_layer.h:79-87, :108-121
+        key = tuple(int(v) for v in index)
+        m = self._meshes.get(key)
+        if m is None:
+            origin = np.asarray(key, dtype=np.float32) * np.float32(self._block_size)
+            m = self._meshes[key] = Mesh(self._block_size, origin)
+        return m
+
+    def getMeshPtrByIndex(self, index) -> Optional[Mesh]:
+        return self._meshes.get(tuple(int(v) for v in index))
+
+    def getAllAllocatedMeshes(self) -> np.ndarray:  # sorted by (x, y, z)
+        return np.array(sorted(self._meshes), dtype=np.int32).reshape(-1, 3)
+
+    def getAllUpdatedMeshes(self) -> np.ndarray:
+        return np.array(sorted(k for k, m in self._meshes.items() if m.updated), dtype=np.int32).reshape(-1, 3)
+
+    def getNumberOfAllocatedMeshes(self) -> int:
+        return len(self._meshes)
+
+
+class MeshIntegrator:
+    """MeshIntegrator<TsdfVoxel> (mesh/mesh_integrator.h:72-412) over the device map."""
+
+    def __init__(self, config: MeshIntegratorConfig, sdf_layer: Layer, mesh_layer: MeshLayer):
+        if sdf_layer is None or mesh_layer is None:  # CHECK_NOTNULL, mesh_integrator.h:89-91
+            raise VoxbloxError("Check failed: 'sdf_layer' / 'mesh_layer' Must be non NULL")
+        self.config_ = config
+        self.sdf_layer_ = sdf_layer
+        self.mesh_layer_ = mesh_layer
+
+    def generateMesh(self, only_mesh_updated_blocks: bool, clear_updated_flag: bool) -> None:  # :132-160
+        ctx = self.sdf_layer_._bound()
+        nb, nv = C.c_uint64(0), C.c_uint64(0)
+        ctx.check(ctx.lib.vbx_mesh_generate(ctx.handle, C.byref(self.config_), int(bool(only_mesh_updated_blocks)),
+                                            int(bool(clear_updated_flag)), C.byref(nb), C.byref(nv)), "generateMesh")
+        nb, nv = int(nb.value), int(nv.value)
+        self.last_blocks, self.last_vertices = nb, nv
+        if nb == 0:
+            return
+        idx = np.zeros((nb, 3), np.int32)
+        first = np.zeros(nb + 1, np.uint64)
+        vertices = np.zeros((nv, 3), np.float32)
+        normals = np.zeros((nv, 3), np.float32)
+        use_color = bool(self.config_.use_color)
+        colors = np.zeros((nv, 4), np.uint8)
+        ctx.check(ctx.lib.vbx_mesh_download(ctx.handle, idx.ctypes.data, first.ctypes.data, vertices.ctypes.data,
+                                            normals.ctypes.data, colors.ctypes.data if use_color and nv else None),
+                  "vbx_mesh_download")
+        for b in range(nb):
+            lo, hi = int(first[b]), int(first[b + 1])
+            m = self.mesh_layer_.allocateMeshPtrByIndex(idx[b])  # :146-149
+            m.vertices = vertices[lo:hi].copy()                   # updateMeshForBlock: clear + refill, :238-260
+            m.normals = normals[lo:hi].copy()
+            m.colors = colors[lo:hi].copy() if use_color else np.zeros((0, 4), np.uint8)
+            m.indices = np.arange(hi - lo, dtype=np.uint64)       # marching_cubes.h:97-99
+            m.updated = True
+
+    def lastDeviceMs(self) -> float:
+        ctx = self.sdf_layer_._bound()
+        ms = C.c_float(0)
+        ctx.check(ctx.lib.vbx_last_device_ms(ctx.handle, C.byref(ms)), "vbx_last_device_ms")
         return float(ms.value)

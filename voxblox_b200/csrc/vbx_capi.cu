@@ -412,6 +412,7 @@ void vbx_destroy(vbx_ctx* c) {
   select_lane(c, 0);
   c->stream = c->stream_main;
   esdf_destroy(c);
+  mesh_destroy(c);
   Tables& t = c->tab;
   void* ptrs[] = {t.hkeys,        t.hslot,       t.htouch_epoch, t.htouch_rank, t.new_list, t.touched_list,
                   t.slot_key,     t.slot_updated, t.slot_esdf_updated, t.slot_has_esdf, t.tsdf, c->d_xyz,
@@ -818,6 +819,21 @@ int vbx_esdf_update_blocks(vbx_ctx* c, const int32_t* idx3, uint64_t m, int incr
   VBX_DRAIN(c);
   if (!c->has_esdf) return fail(c, VBX_E_STATE, "vbx_esdf_update_blocks before vbx_esdf_create");
   return esdf_update_blocks(c, idx3, m, incremental);
+}
+
+int vbx_mesh_generate(vbx_ctx* c, const vbx_mesh_config* cfg, int only_mesh_updated_blocks, int clear_updated_flag,
+                      uint64_t* n_blocks, uint64_t* n_vertices) {
+  if (!c || !cfg) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  return mesh_generate(c, cfg, only_mesh_updated_blocks, clear_updated_flag, n_blocks, n_vertices);
+}
+
+int vbx_mesh_download(vbx_ctx* c, int32_t* idx3, uint64_t* first_vertex, float* vertices, float* normals,
+                      uint8_t* colors) {
+  if (!c) return VBX_E_INVALID;
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  return mesh_download(c, idx3, first_vertex, vertices, normals, colors);
 }
 
 int vbx_esdf_add_robot_position(vbx_ctx* c, const float position[3]) {

@@ -234,6 +234,18 @@ struct vbx_ctx {
   int esdf_grid_raise = 0, esdf_grid_lower = 0, esdf_sms = 0, esdf_ctas_wide = 1;
   uint32_t esdf_pending_raise = 0, esdf_pending_open = 0;  // raise_ / open_ entries queued by addNewRobotPosition
   bool maybe_esdf_only = false;                            // some slot may carry kSlotNoTsdf
+  // mesher (vbx_mesh.cu): the result of the last vbx_mesh_generate stays on the device until the next one
+  uint32_t* mesh_slots = nullptr;
+  uint16_t* mesh_cube_off = nullptr;
+  uint32_t* mesh_block_nv = nullptr;
+  unsigned long long* mesh_first = nullptr;
+  float* mesh_vertices = nullptr;
+  float* mesh_normals = nullptr;
+  uint32_t* mesh_colors = nullptr;
+  uint64_t mesh_cap_blocks = 0, mesh_cap_vertices = 0, mesh_launches = 0;
+  std::vector<int32_t> mesh_idx;
+  std::vector<uint64_t> mesh_first_host = std::vector<uint64_t>(1, 0);
+  bool mesh_use_color = false;
   // reporting
   uint32_t last_passes = 1;  // passes the last synchronous integrate call needed (K > max_updates_per_pass)
   uint64_t counters[16] = {0};
@@ -256,6 +268,10 @@ int refresh_host_mirror(vbx_ctx* c);
 int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int32_t* idx3, void* voxels,
                    uint8_t* updated_bits, uint64_t cap, uint64_t* n, int serialized);
 int esdf_destroy(vbx_ctx* c);
+void mesh_destroy(vbx_ctx* c);
+int mesh_generate(vbx_ctx* c, const vbx_mesh_config* cfg, int only_updated, int clear_flag, uint64_t* n_blocks_out,
+                  uint64_t* n_vertices_out);
+int mesh_download(vbx_ctx* c, int32_t* idx3, uint64_t* first_vertex, float* vertices, float* normals, uint8_t* colors);
 int esdf_add_robot_position(vbx_ctx* c, const float p[3]);
 int esdf_clear_state(vbx_ctx* c);
 int ensure_async(vbx_ctx* c);          // allocate the extra hand-off sets / front lanes
