@@ -427,6 +427,38 @@ def run_ours(args, rank, world):
         omap.integrate(2, s, order=po.ORDER_CANONICAL)
     rep = compare_tsdf(layer4, omap)
 
+    # ---- (6) the callers either side of the path: ESDF update and
+    # incremental mesh after every scan; device time per call, not part of `value`
+    downstream = None
+    try:
+        layer5, integ5 = fresh()
+        esdf5 = vb.Layer(VOXEL_SIZE, 16, voxel_type="esdf")
+        e5 = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(max_distance_m=2.0, default_distance_m=2.0,
+                                                       min_distance_m=TRUNC / 2, min_diff_m=1e-3), layer5, esdf5)
+        mesh5 = vb.MeshLayer(layer5.block_size())
+        m5 = vb.MeshIntegrator(vb.MeshIntegratorConfig(), layer5, mesh5)
+        t_ms5, e_ms5, m_ms5, m_wall5 = [], [], [], []
+        k5 = min(n_total, 12)
+        for i in range(k5):
+            integ5.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+            t_ms5.append(integ5.lastDeviceMs())
+            e5.updateFromTsdfLayer(True)
+            e_ms5.append(e5.lastDeviceMs())
+            t0 = time.perf_counter()
+            m5.generateMesh(True, True)
+            m_wall5.append((time.perf_counter() - t0) * 1e3)
+            m_ms5.append(m5.lastDeviceMs())
+        w = slice(min(3, k5 - 1), None)
+        downstream = {"scans": k5, "tsdf_sync_device_ms": float(np.mean(t_ms5[w])),
+                      "esdf_incremental_device_ms": float(np.mean(e_ms5[w])),
+                      "mesh_incremental_device_ms": float(np.mean(m_ms5[w])),
+                      "mesh_incremental_wall_ms_incl_download": float(np.mean(m_wall5[w])),
+                      "mesh_vertices_last_call": int(m5.last_vertices), "mesh_blocks_last_call": int(m5.last_blocks),
+                      "note": "Merged + EsdfIntegrator::updateFromTsdfLayer(true) + MeshIntegrator::generateMesh(true, true) "
+                              "after every scan (config C4 + N3); CPU reference: scripts/esdf_bench.py, scripts/mesh_bench.py"}
+    except Exception as exc:  # never lose the headline line to an optional section
+        downstream = {"error": repr(exc)}
+
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
@@ -454,6 +486,7 @@ def run_ours(args, rank, world):
                    "bit_exact_voxels": rep.get("n_bit_exact"), "voxels": rep.get("n_voxels"),
                    "color_mismatch": rep.get("color_mismatch")},
         "last_counters": last_counters,
+        "downstream": downstream,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -248,3 +248,93 @@ def test_save_and_load_layer_file(tmp_path):
     vb.TsdfIntegratorFactory.create("merged", cfg, other)
     with pytest.raises(vb.VoxbloxError):
         other.loadBlocksFromFile(path)
+
+
+def test_esdf_only_blocks_stay_out_of_the_tsdf_layer():
+    """Blocks inserted into the ESDF layer at indices the TSDF layer does not hold (what
+    addNewRobotPosition and loading an ESDF map do) occupy pool slots of their own: the TSDF
+    layer's listings, downloads, mirror, serialisation and block count do not see them, the
+    clear-updated call leaves them alone, and the first TSDF integration into such an index
+    starts from an empty block like the reference's allocateBlockPtrByIndex."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    scans = scenes.c3_room_sequence(n_scans=1, width=96, height=72)
+    s = scans[0]
+    # what the scan alone produces
+    ref_layer = vb.Layer(0.1, 16)
+    vb.TsdfIntegratorFactory.create("merged", cfg, ref_layer).integratePointCloud((s[2], s[3]), s[0], s[1])
+    want_idx, want_vox, want_upd = _snapshot(ref_layer)
+    # same scan into a map that first received ESDF-only blocks: two at indices the scan will
+    # touch, one far away
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    esdf = vb.Layer(0.1, 16, voxel_type="esdf")
+    vb.EsdfIntegrator(vb.EsdfIntegratorConfig(min_distance_m=0.2), layer, esdf)
+    eidx = np.concatenate([want_idx[:2], np.array([[40, -40, 7]], np.int32)])
+    evox = np.zeros((3, 4096), vb.ESDF_DTYPE)
+    evox["distance"] = 1.25
+    evox["observed"] = 1
+    esdf.insertBlocks(eidx, evox)
+    assert layer.getNumberOfAllocatedBlocks() == 0 and len(layer.getAllAllocatedBlocks()) == 0
+    assert layer.mirrorUpdated(0, 0)[0].shape[0] == 0
+    assert esdf.getNumberOfAllocatedBlocks() == 3
+    got_e, _ = esdf.getBlocks(esdf.getAllAllocatedBlocks())
+    assert (got_e["distance"] == 1.25).all()
+    with pytest.raises(vb.VoxbloxError):
+        layer.getBlocks(eidx[:1])                  # not a TSDF block
+    layer.clearUpdated(7)                          # must not disturb the internal marks
+    assert layer.getNumberOfAllocatedBlocks() == 0
+    integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    got_idx, got_vox, got_upd = _snapshot(layer)
+    assert (got_idx == want_idx).all()
+    assert got_vox.tobytes() == want_vox.tobytes() and (got_upd == want_upd).all()
+    assert layer.getNumberOfAllocatedBlocks() == len(want_idx)
+    assert esdf.getNumberOfAllocatedBlocks() == 3   # the ESDF blocks are still there, untouched
+    got_e, _ = esdf.getBlocks(esdf.getAllAllocatedBlocks())
+    assert (got_e["distance"] == 1.25).all()
+
+
+def test_layers_are_removed_independently():
+    """Layer::removeBlock / removeAllBlocks act on ONE layer (core/layer.h:163-164): removing TSDF
+    blocks keeps the ESDF blocks at those indices and vice versa; a pool slot is recycled once both
+    are gone, and integration afterwards starts from empty blocks."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    scans = scenes.c3_room_sequence(n_scans=2, width=96, height=72)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    esdf = vb.Layer(0.1, 16, voxel_type="esdf")
+    eint = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(min_distance_m=0.2), layer, esdf)
+    s = scans[0]
+    integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    eint.updateFromTsdfLayer(True)
+    idx, vox, _ = _snapshot(layer)
+    eidx, evox, _ = _snapshot(esdf)
+    assert (idx == eidx).all()
+    kill = idx[::2]
+    keep = np.array([i for i in range(len(idx)) if i % 2 == 1])
+    layer.removeBlocks(kill)
+    i2, v2, _ = _snapshot(layer)
+    assert (i2 == idx[keep]).all() and v2.tobytes() == vox[keep].tobytes()
+    e2, ev2, _ = _snapshot(esdf)                       # the ESDF layer is untouched
+    assert (e2 == eidx).all() and ev2.tobytes() == evox.tobytes()
+    esdf.removeBlocks(kill[:1])                        # now that slot is free in both layers
+    e3, ev3, _ = _snapshot(esdf)
+    assert (e3 == eidx[1:]).all() and ev3.tobytes() == evox[1:].tobytes()
+    esdf.removeBlocks(idx[keep][:1])                   # ESDF gone, TSDF stays
+    i4, v4, _ = _snapshot(layer)
+    assert (i4 == idx[keep]).all() and v4.tobytes() == vox[keep].tobytes()
+    assert esdf.getNumberOfAllocatedBlocks() == len(eidx) - 2
+    # removeAllBlocks on the TSDF layer keeps the remaining ESDF blocks
+    esdf_before = _snapshot(esdf)
+    layer.removeAllBlocks()
+    assert layer.getNumberOfAllocatedBlocks() == 0
+    esdf_after = _snapshot(esdf)
+    assert (esdf_after[0] == esdf_before[0]).all() and esdf_after[1].tobytes() == esdf_before[1].tobytes()
+    # integrating again: the result equals a fresh map's (the freed / ESDF-only slots read as new blocks)
+    s1 = scans[1]
+    integ.integratePointCloud((s1[2], s1[3]), s1[0], s1[1])
+    fresh = vb.Layer(0.1, 16)
+    vb.TsdfIntegratorFactory.create("merged", cfg, fresh).integratePointCloud((s1[2], s1[3]), s1[0], s1[1])
+    a, b = _snapshot(layer), _snapshot(fresh)
+    assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
+    esdf.removeAllBlocks()
+    assert esdf.getNumberOfAllocatedBlocks() == 0 and layer.getNumberOfAllocatedBlocks() == len(b[0])

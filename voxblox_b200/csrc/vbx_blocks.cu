@@ -220,23 +220,31 @@ int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const 
   return refresh_host_mirror(c);
 }
 
+int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m);
+
+// Layer::removeAllBlocks (core/layer.h:164) of ONE layer; the other layer keeps its blocks
 int clear_layer(vbx_ctx* c, int layer) {
   cudaStream_t s = c->stream;
-  const size_t used = (size_t)c->n_blocks * c->vox_per_block;
-  if (layer == VBX_LAYER_ESDF) {
-    if (!c->has_esdf) return VBX_OK;
-    c->esdf_pending_raise = c->esdf_pending_open = 0;
-    VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, used * sizeof(EsdfVoxel), s));
-    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf, 0, c->tab.max_blocks, s));
-    VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated, 0, c->tab.max_blocks, s));
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    return VBX_OK;
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
+  if (c->has_esdf && c->n_blocks) {
+    // the layers share pool slots: remove this layer's block from every slot (slots that end up
+    // empty are given back)
+    if (int rc = refresh_host_mirror(c)) return rc;
+    std::vector<int32_t> idx(3 * (size_t)c->n_blocks);
+    for (uint32_t sl = 0; sl < c->n_blocks; ++sl) {
+      int x, y, z;
+      unpack3(c->host_slot_key[sl], &x, &y, &z);
+      idx[3 * sl] = x;
+      idx[3 * sl + 1] = y;
+      idx[3 * sl + 2] = z;
+    }
+    return remove_blocks(c, layer, idx.data(), c->n_blocks);
   }
+  // no ESDF layer: reset the whole map
+  const size_t used = (size_t)c->n_blocks * c->vox_per_block;
   c->esdf_pending_raise = c->esdf_pending_open = 0;
   c->maybe_esdf_only = false;
-  // removing every TSDF block also empties the ESDF layer's storage (the two layers share slots)
   VBX_CUDA(c, cudaMemsetAsync(c->tab.tsdf, 0, used * sizeof(TsdfVoxel), s));
-  if (c->has_esdf) VBX_CUDA(c, cudaMemsetAsync(c->tab.esdf, 0, used * sizeof(EsdfVoxel), s));
   VBX_CUDA(c, cudaMemsetAsync(c->tab.hkeys, 0xff, (size_t)c->hcap * sizeof(uint64_t), s));
   VBX_CUDA(c, cudaMemsetAsync(c->tab.hslot, 0xff, (size_t)c->hcap * sizeof(int32_t), s));
   VBX_CUDA(c, cudaMemsetAsync(c->tab.htouch_epoch, 0, (size_t)c->hcap * sizeof(uint32_t), s));
@@ -263,20 +271,40 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
   victims.erase(std::unique(victims.begin(), victims.end()), victims.end());
   if (victims.empty()) return VBX_OK;
   const size_t tb = sizeof(TsdfVoxel) * c->vox_per_block, eb = sizeof(EsdfVoxel) * c->vox_per_block;
-  if (layer == VBX_LAYER_ESDF) {
-    if (!c->has_esdf) return VBX_OK;
-    c->esdf_pending_raise = c->esdf_pending_open = 0;
-    for (int32_t v : victims) {
+  if (layer == VBX_LAYER_ESDF && !c->has_esdf) return VBX_OK;
+  // The two layers are independent in the reference (Layer::removeBlock = block_map_.erase, core/layer.h:163)
+  // but share pool slots here: a slot is given back only when NEITHER layer holds a block in it.
+  std::vector<uint8_t> upd(c->n_blocks), has(c->n_blocks, 0);
+  VBX_CUDA(c, cudaMemcpyAsync(upd.data(), c->tab.slot_updated, c->n_blocks, cudaMemcpyDeviceToHost, s));
+  if (c->has_esdf) VBX_CUDA(c, cudaMemcpyAsync(has.data(), c->tab.slot_has_esdf, c->n_blocks, cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  // queue entries of addNewRobotPosition address voxels by slot: they are dropped
+  c->esdf_pending_raise = c->esdf_pending_open = 0;
+  std::vector<int32_t> drop;  // slots that become free
+  const uint8_t no_tsdf = kSlotNoTsdf;
+  for (int32_t v : victims) {
+    if (layer == VBX_LAYER_ESDF) {
+      if (!has[v]) continue;  // erasing a missing block is a no-op
       VBX_CUDA(c, cudaMemsetAsync(reinterpret_cast<char*>(c->tab.esdf) + (size_t)v * eb, 0, eb, s));
       VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_has_esdf + v, 0, 1, s));
       VBX_CUDA(c, cudaMemsetAsync(c->tab.slot_esdf_updated + v, 0, 1, s));
+      if (upd[v] & kSlotNoTsdf) drop.push_back(v);
+    } else {
+      if (upd[v] & kSlotNoTsdf) continue;  // the TSDF layer holds no block here
+      if (has[v]) {
+        // the ESDF block stays; the slot's TSDF half reads as never allocated from now on
+        VBX_CUDA(c, cudaMemsetAsync(reinterpret_cast<char*>(c->tab.tsdf) + (size_t)v * tb, 0, tb, s));
+        VBX_CUDA(c, cudaMemcpyAsync(c->tab.slot_updated + v, &no_tsdf, 1, cudaMemcpyHostToDevice, s));
+        c->maybe_esdf_only = true;
+      } else {
+        drop.push_back(v);
+      }
     }
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    return VBX_OK;
   }
-  // TSDF: swap-remove in the pool (highest victim first), then rebuild the hash from slot_key.
-  // Queue entries of addNewRobotPosition address voxels by slot: they are dropped.
-  c->esdf_pending_raise = c->esdf_pending_open = 0;
+  VBX_CUDA(c, cudaStreamSynchronize(s));  // (no_tsdf lives on this stack frame)
+  if (drop.empty()) return VBX_OK;
+  victims.swap(drop);
+  // swap-remove in the pool (highest victim first), then rebuild the hash from slot_key
   uint32_t n = c->n_blocks;
   for (auto it = victims.rbegin(); it != victims.rend(); ++it) {
     const uint32_t v = (uint32_t)*it, last = n - 1;

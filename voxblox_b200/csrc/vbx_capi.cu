@@ -80,6 +80,7 @@ void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S) {
   c->counters[5] = h.n_new;
   c->counters[6] = S.kind == VBX_MERGED ? h.n_valid_points : (uint64_t)h.n_rays + h.n_clear_rays;
   c->counters[7] = S.launches;
+  c->counters[11] = 1;
   if (h.error & kNeedWideKeys) c->force_wide_keys = true;  // later submissions use full-width keys
   if (h.error && !c->deferred_rc) {
     c->deferred_rc = VBX_E_CAPACITY;

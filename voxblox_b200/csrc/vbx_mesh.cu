@@ -40,7 +40,7 @@ struct MeshParams {
   int use_color;
 };
 
-constexpr int kMeshThreads = 256;
+constexpr int kMeshThreads = 1024;  // 4 cubes per thread at vps 16: the per-cube work is a latency chain, so more threads per block
 
 // position of cube (x, y, z) in the order extractBlockMesh visits the cubes (mesh_integrator.h:186-235),
 // and its inverse
