@@ -63,7 +63,7 @@ def _meshed_map(which, use_color=True, incremental=True):
     for k, s in enumerate(scans):
         m.integrate(2, s)
         if incremental:
-            # mesh the blocks the scan dirtied, clearing their kMesh bit (tsdf_server.cc:509-512)
+            # mesh the blocks the scan dirtied, clearing their kMesh bit (tsdf_server.cc:494-501)
             m.mesh_generate(use_color, 1e-4, only_mesh_updated_blocks=True, clear_updated_flag=True)
     if not incremental:
         m.mesh_generate(use_color, 1e-4, only_mesh_updated_blocks=False, clear_updated_flag=False)

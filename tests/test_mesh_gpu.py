@@ -48,7 +48,7 @@ def _setup(voxel_size, trunc, vps=16):
 @pytest.mark.parametrize("use_color", [True, False])
 def test_incremental_mesh_matches_oracle(use_color):
     """generateMesh(only_mesh_updated_blocks=true, clear_updated_flag=true) after every scan, as
-    TsdfServer::updateMesh does (voxblox_ros/src/tsdf_server.cc:509-512)."""
+    TsdfServer::updateMesh does (voxblox_ros/src/tsdf_server.cc:494-501)."""
     scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
     layer, integ, omap = _setup(0.1, 0.4)
     mesh_layer = vb.MeshLayer(layer.block_size())
