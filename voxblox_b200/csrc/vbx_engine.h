@@ -59,7 +59,8 @@ struct ScanState {
   unsigned long long total_updates;  // K the back half runs on (0 when the call failed / is redone)
   unsigned long long total_found;    // K as counted
   // ESDF
-  uint32_t esdf_counts[8];
+  uint32_t esdf_counts[7];
+  uint32_t raise_n2;         // third raise-level counter (see esdf_cnt: the counters rotate mod 3)
   uint32_t frontier_n[2];
   uint32_t raise_n[2];
   uint32_t seed_n;           // ESDF: new free voxels waiting for updateVoxelFromNeighbors
@@ -69,8 +70,9 @@ struct ScanState {
   uint32_t n_verify;         // work items of k_apply_verify
   uint32_t n_refold;         // bundles folded a second time with IEEE division (diagnostic)
   uint32_t refold_members;   // ... and the points they hold
-  uint32_t pad_[1];
+  uint32_t frontier_n2;      // third wavefront counter
 };
+static_assert(sizeof(ScanState) == 128, "the status block the host reads back is 128 bytes");
 
 // The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
 // core/layer.h:30-32,292).
@@ -231,7 +233,7 @@ struct vbx_ctx {
   uint32_t* esdf_seed_list = nullptr;
   float* esdf_seed_val = nullptr;
   uint32_t* esdf_touched = nullptr;
-  int esdf_grid_raise = 0, esdf_grid_lower = 0, esdf_sms = 0, esdf_ctas_wide = 1;
+  int esdf_grid_raise = 0, esdf_grid_lower = 0, esdf_sms = 0, esdf_ctas_wide = 1, esdf_ctas_small = 1;
   uint32_t esdf_pending_raise = 0, esdf_pending_open = 0;  // raise_ / open_ entries queued by addNewRobotPosition
   bool maybe_esdf_only = false;                            // some slot may carry kSlotNoTsdf
   // mesher (vbx_mesh.cu): the result of the last vbx_mesh_generate stays on the device until the next one

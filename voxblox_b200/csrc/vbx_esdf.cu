@@ -118,6 +118,16 @@ __device__ __forceinline__ void push(uint32_t* list, uint32_t* count, uint32_t c
   }
 }
 
+// The level-synchronous kernels below keep THREE counters per queue and rotate through them: sweep k
+// reads counter k % 3, appends to counter (k + 1) % 3 and zeroes counter (k + 2) % 3 (last read one
+// sweep ago, next written one sweep ahead), so a sweep needs a single grid-wide barrier.
+__device__ __forceinline__ uint32_t* frontier_cnt(ScanState* st, uint32_t k) {
+  return k % 3u == 2u ? &st->frontier_n2 : &st->frontier_n[k % 3u];
+}
+__device__ __forceinline__ uint32_t* raise_cnt(ScanState* st, uint32_t k) {
+  return k % 3u == 2u ? &st->raise_n2 : &st->raise_n[k % 3u];
+}
+
 // Step (1), esdf_integrator.cc:136-287: one thread per voxel of every listed block.
 // esdf_counts: [1] lower [2] raise [3] new
 __global__ void k_esdf_propagate(EsdfParams E, Tables tab, const uint32_t* __restrict__ block_list, uint32_t n_blocks,
@@ -255,12 +265,13 @@ __global__ void k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  int cur = 0;
-  while (true) {
-    uint32_t* in = cur ? raise_b : raise_a;
-    uint32_t* out = cur ? raise_a : raise_b;
-    const uint32_t n = min(__ldcg(&st->raise_n[cur]), E.cap);
+  for (uint32_t level = 0;; ++level) {
+    uint32_t* in = (level & 1u) ? raise_b : raise_a;
+    uint32_t* out = (level & 1u) ? raise_a : raise_b;
+    const uint32_t n = min(__ldcg(raise_cnt(st, level)), E.cap);
     if (n == 0) break;
+    uint32_t* out_n = raise_cnt(st, level + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *raise_cnt(st, level + 2) = 0;
     for (uint32_t q = warp; q < n; q += n_warps) {
       const uint32_t ref = __ldcg(&in[q]);
       if (lane == 0) atomicAdd(&st->esdf_counts[4], 1u);
@@ -279,7 +290,7 @@ __global__ void k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32
             if (is_parent) {
               np->distance = (float)signum_d(np->distance) * E.default_distance;
               np->px = np->py = np->pz = 0;
-              push(out, &st->raise_n[cur ^ 1], E.cap, nref, st);
+              push(out, out_n, E.cap, nref, st);
             } else if (!(atomicOr(&np->flags, kBitInQueue) & kFlagInQueue)) {
               push(open_list, &st->frontier_n[0], E.cap, nref, st);
             }
@@ -288,44 +299,47 @@ __global__ void k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32
       }
     }
     grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->raise_n[cur] = 0;
-    cur ^= 1;
-    grid.sync();
   }
 }
 
 // Step (3), processOpenSet cc:371-496: wavefront relaxation.  One warp per frontier voxel, one
 // lane per neighbour; a lowered neighbour joins the next frontier (once: the in_queue flag).
+// A voxel leaves the queue (voxel->in_queue = false, cc:384) when its warp starts on it: the flag is
+// cleared BEFORE the distance is read, so a neighbour that lowers this voxel either still sees the
+// flag (then its lower value is the one read here) or re-queues the voxel for the next sweep.
 __global__ void k_esdf_lower(EsdfParams E, Tables tab, uint32_t* front_a, uint32_t* front_b, uint32_t* touched_list,
                              ScanState* st) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  int cur = 0;
-  while (true) {
-    uint32_t* in = cur ? front_b : front_a;
-    uint32_t* out = cur ? front_a : front_b;
-    const uint32_t n = min(__ldcg(&st->frontier_n[cur]), E.cap);
+  for (uint32_t sweep = 0;; ++sweep) {
+    uint32_t* in = (sweep & 1u) ? front_b : front_a;
+    uint32_t* out = (sweep & 1u) ? front_a : front_b;
+    const uint32_t n = min(__ldcg(frontier_cnt(st, sweep)), E.cap);
     if (n == 0) break;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->esdf_counts[6], 1u);
-    // pass A: leave the queue (voxel->in_queue = false, cc:384)
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-      atomicAnd(&(reinterpret_cast<EsdfWords*>(tab.esdf) + __ldcg(&in[i]))->flags, ~kBitInQueue);
+    uint32_t* out_n = frontier_cnt(st, sweep + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *frontier_cnt(st, sweep + 2) = 0;
+      atomicAdd(&st->esdf_counts[6], 1u);
     }
-    grid.sync();
-    // pass B: relax the 26-neighbourhood
     for (uint32_t q = warp; q < n; q += n_warps) {
       const uint32_t ref = __ldcg(&in[q]);
-      const EsdfWords* vp = reinterpret_cast<const EsdfWords*>(tab.esdf) + ref;
+      EsdfWords* vpm = reinterpret_cast<EsdfWords*>(tab.esdf) + ref;
+      if (lane == 0) {
+        atomicAnd(&vpm->flags, ~kBitInQueue);
+        __threadfence();
+      }
+      __syncwarp();
+      const EsdfWords* vp = vpm;
       const float vd = *reinterpret_cast<const volatile float*>(&vp->distance);
-      const uint32_t vf = vp->flags;
+      const uint32_t vf = *reinterpret_cast<const volatile uint32_t*>(&vp->flags);
       if (!(vf & kFlagObserved) || vd >= E.max_distance || vd <= -E.max_distance) continue;  // cc:387-390
       if (lane >= 26) continue;
       const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
       if (nref == 0xffffffffu) continue;
       EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
-      const uint32_t nf = np->flags;
+      const uint32_t nf = *reinterpret_cast<const volatile uint32_t*>(&np->flags);
       if (!(nf & kFlagObserved) || (nf & kFlagFixed)) continue;  // cc:407-411
       float dist = nbr_dist(E, lane);
       if (E.full_euclidean) {  // cc:414-426
@@ -373,14 +387,12 @@ __global__ void k_esdf_lower(EsdfParams E, Tables tab, uint32_t* front_a, uint32
           np->py = -kOff[lane][1];
           np->pz = -kOff[lane][2];
         }
+        __threadfence();  // the lowered distance is visible before the queue flag is tested
         const uint32_t old = atomicOr(&np->flags, kBitInQueue | kBitLowered);
         if (!(old & kBitLowered)) push(touched_list, &st->lowered_n, E.cap, nref, st);
-        if (E.multi_queue || !(old & kFlagInQueue)) push(out, &st->frontier_n[cur ^ 1], E.cap, nref, st);
+        if (E.multi_queue || !(old & kFlagInQueue)) push(out, out_n, E.cap, nref, st);
       }
     }
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->frontier_n[cur] = 0;
-    cur ^= 1;
     grid.sync();
   }
 }
@@ -795,7 +807,8 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
     }
     if (c->profiling) cudaEventRecord(c->sev[1], s);
     {
-      const int per_sm = (nb <= 256 && !pending) ? 1 : c->esdf_ctas_wide;
+      int per_sm = (nb <= 256 && !pending) ? c->esdf_ctas_small : c->esdf_ctas_wide;
+      if (const char* e = std::getenv("VBX_ESDF_CTAS")) per_sm = std::max(1, std::min(std::atoi(e), c->esdf_ctas_wide));  // (tuning aid)
       c->esdf_grid_raise = c->esdf_grid_lower = c->esdf_sms * per_sm;
     }
     {
