@@ -134,7 +134,7 @@ __global__ void k_esdf_propagate(EsdfParams E, Tables tab, const uint32_t* __res
                                  uint32_t* open_list, uint32_t* raise_list, uint32_t* seed_list, ScanState* st) {
   const uint32_t vpb = 1u << (3 * E.L);
   const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (uint64_t)n_blocks * vpb) return;
+  if (gid >= (uint64_t)min(n_blocks, st->esdf_counts[0]) * vpb) return;  // (n_blocks is the launch's upper bound)
   const uint32_t slot = block_list[gid >> (3 * E.L)];
   const uint32_t lin = (uint32_t)(gid & (vpb - 1));
   const uint32_t ref = (slot << (3 * E.L)) | lin;
@@ -787,10 +787,11 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
       VBX_CUDA(c, cudaStreamSynchronize(s));  // the two host sources above are stack / vector memory
     }
   } else {
+    // the list and its length (esdf_counts[0]) stay on the device: no host round trip in the middle of
+    // the call; the launches below are sized for the upper bound (every slot) and the kernels stop at
+    // the real count
     k_esdf_block_list<<<grid_for(c->n_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks, batch, c->esdf_block_list, c->d_state);
-    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    nb = c->h_state->esdf_counts[0];
+    nb = c->n_blocks;
   }
   launches += 1;
   if (nb > 0 || pending) {
