@@ -112,6 +112,10 @@ def test_port_mesh_matches_reference(name):
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_port_mesh_matches_committed_golden(name):
+    from tests.golden import make_golden as mg
+    inputs = json.load(open(os.path.join(HERE, "golden", "digests.json")))["inputs"]
+    if mg.scans_digest("room") != inputs["room"]:
+        pytest.skip("scan generator output differs on this machine (numpy / libm): inputs not comparable")
     gold = json.load(open(GOLD_PATH))
     use_color, incremental = CASES[name]
     got = _mesh_digest(_meshed_map("port", use_color, incremental))
