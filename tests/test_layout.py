@@ -81,3 +81,29 @@ def test_operator_interface_mirrors_reference_errors():
     e = vb.EsdfIntegratorConfig()
     assert e.max_distance_m == 2.0 and abs(e.min_diff_m - 0.001) < 1e-9 and e.num_buckets == 20
     assert vb.TSDF_DTYPE.itemsize == 12 and vb.ESDF_DTYPE.itemsize == 20
+
+
+def test_mesh_host_mirror_matches_reference_defaults_and_layout():
+    """MeshIntegratorConfig defaults (mesh/mesh_integrator.h:49-52), the C struct layout of
+    vbx_mesh_config, and MeshLayer::allocateMeshPtrByIndex's origin = index * block_size
+    (mesh/mesh_layer.h:108-121)."""
+    import ctypes as C
+
+    import numpy as np
+
+    cfg = vb.MeshIntegratorConfig()
+    assert cfg.use_color == 1 and abs(cfg.min_weight - 1e-4) < 1e-10
+    assert C.sizeof(vb.MeshIntegratorConfig) == 8
+    text = open(os.path.join(ROOT, "include", "voxblox_b200.h")).read()
+    body = re.search(r"typedef struct vbx_mesh_config \{(.*?)\} vbx_mesh_config;", text, re.S).group(1)
+    assert re.findall(r"\b(int32_t|float)\s+(\w+);", body) == [("int32_t", "use_color"), ("float", "min_weight")]
+    ml = vb.MeshLayer(0.8)
+    m = ml.allocateMeshPtrByIndex((1, -2, 3))
+    assert m is ml.allocateMeshPtrByIndex(np.array([1, -2, 3]))          # same mesh on the second call
+    assert np.allclose(m.origin, np.float32(0.8) * np.array([1, -2, 3], np.float32)) and m.size() == 0 and not m.updated
+    assert ml.getNumberOfAllocatedMeshes() == 1 and ml.getMeshPtrByIndex((0, 0, 0)) is None
+    ml.allocateMeshPtrByIndex((0, 0, 0)).updated = True
+    assert ml.getAllAllocatedMeshes().tolist() == [[0, 0, 0], [1, -2, 3]]
+    assert ml.getAllUpdatedMeshes().tolist() == [[0, 0, 0]]
+    with pytest.raises(vb.VoxbloxError):
+        vb.MeshIntegrator(cfg, None, ml)     # CHECK_NOTNULL(sdf_layer), mesh_integrator.h:89
