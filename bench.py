@@ -27,19 +27,61 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "integrated points/sec (640x480 scan, 0.05 m voxel)"
-VOXEL_SIZE = 0.05
-TRUNC = 0.2  # 4 voxels (voxblox_ros ros_params.h:66-67, cow_and_lady_dataset.launch)
-WORKLOAD = "merged_640x480_room_sequence_0.05m"
+
+# The workloads of BASELINE.json / SURVEY.md section 8(d).  "bench" is the configuration the metric is
+# quoted on (Merged, 640x480, 0.05 m voxels, truncation 4 voxels: the C3 / C4 cloud stream through the
+# Merged integrator) and the only one the driver runs; the others are selected with --config and are
+# what BASELINE.md's table is filled from.
+CONFIGS = {
+    "bench": dict(workload="merged_640x480_room_sequence_0.05m", kind="merged", voxel=0.05, scan="c3_room_scan",
+                  cfg=dict(default_truncation_distance=0.2), opts=dict(max_blocks=16384, max_points_per_scan=1 << 19,
+                                                                       max_updates_per_pass=1 << 24),
+                  scan_text="640x480 pinhole, box room + 4 objects, 15% dropouts, 30 Hz handheld trajectory"),
+    "C1": dict(workload="C1_simple_64x48_planar_wall_0.20m", kind="simple", voxel=0.2, scan="c1_planar_wall",
+               cfg=dict(default_truncation_distance=0.8), opts=dict(max_blocks=4096, max_points_per_scan=1 << 16,
+                                                                    max_updates_per_pass=1 << 22),
+               scan_text="64x48 pinhole, planar wall at 3 m (the same scan every step)"),
+    "C2": dict(workload="C2_merged_640x480_sphere_room_0.10m", kind="merged", voxel=0.1, scan="c2_sphere_scan",
+               cfg=dict(default_truncation_distance=0.4), opts=dict(max_blocks=16384, max_points_per_scan=1 << 19,
+                                                                    max_updates_per_pass=1 << 24),
+               scan_text="640x480 pinhole inside a 3 m sphere, 300-scan orbit (truncation 4 voxels; --trunc 4.0 for the literal 4 m)"),
+    "C3": dict(workload="C3_fast_640x480_room_sequence_0.05m", kind="fast", voxel=0.05, scan="c3_room_scan",
+               cfg=dict(default_truncation_distance=0.2), opts=dict(max_blocks=16384, max_points_per_scan=1 << 19,
+                                                                    max_updates_per_pass=1 << 26),
+               scan_text="640x480 pinhole, box room + 4 objects, 15% dropouts, 30 Hz handheld trajectory"),
+    "C4": dict(workload="C4_merged_plus_esdf_640x480_0.05m", kind="merged", voxel=0.05, scan="c3_room_scan", esdf=True,
+               cfg=dict(default_truncation_distance=0.2), opts=dict(max_blocks=16384, max_points_per_scan=1 << 19,
+                                                                    max_updates_per_pass=1 << 24),
+               scan_text="as bench, EsdfIntegrator::updateFromTsdfLayer(true) after every scan (ROS defaults)"),
+    "C5": dict(workload="C5_merged_lidar_2048x128_0.05m", kind="merged", voxel=0.05, scan="c5_lidar_scan",
+               cfg=dict(default_truncation_distance=0.2, max_ray_length_m=10.0, use_const_weight=1),
+               opts=dict(max_blocks=16384, max_points_per_scan=1 << 19, max_updates_per_pass=1 << 25),
+               scan_text="2048x128 spinning LiDAR in a 9x9x4 m hall with pillars, ~13 M voxel updates per scan"),
+}
+KIND_ID = {"simple": 1, "merged": 2, "fast": 3}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_scans(n, start=0):
+def make_scans(conf, n, start=0):
     from voxblox_b200 import scenes
 
-    return scenes.generate_parallel(scenes.c3_room_scan, range(start, start + n))
+    if conf["scan"] == "c1_planar_wall":
+        s = scenes.c1_planar_wall()
+        return [s for _ in range(n)]
+    return scenes.generate_parallel(getattr(scenes, conf["scan"]), range(start, start + n))
+
+
+def config_dict(conf, scans_timed):
+    """The `config` object of the JSON line: identical in our arm and in the reference arm."""
+    n_mean = float(np.mean([int(s[0].shape[0]) for s in scans_timed])) if scans_timed else 0.0
+    return {"workload": conf["workload"], "integrator": conf["kind"], "voxel_size_m": conf["voxel"],
+            "truncation_m": conf["cfg"]["default_truncation_distance"], "voxels_per_side": 16,
+            "scan": conf["scan_text"], "points_per_scan_mean": n_mean,
+            "l2": "every step integrates a different scan (cloud set > L2); the map's voxel blocks stay hot across "
+                  "steps as they do in a mapping session"}
 
 
 # ------------------------------------------------------------------------- clocks
@@ -163,24 +205,31 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------- CPU baseline
-def time_reference(scans, threads, kind=2, which=None):
+def time_reference(conf, scans, threads, which=None, esdf=False):
     """Seconds inside integratePointCloud per scan (stopwatch placed like
     voxblox_ros/src/tsdf_server.cc:305-307) for the CPU implementation."""
     from oracle import pyoracle as po
 
     which = which or ("reference" if po.available("reference") else "port")
     lib = po.OracleLib(which)
-    cfg = po.TsdfConfig(default_truncation_distance=TRUNC, integrator_threads=threads)
-    m = po.OracleMap(lib, cfg, VOXEL_SIZE, 16)
+    cfg = po.TsdfConfig(integrator_threads=threads, **conf["cfg"])
+    m = po.OracleMap(lib, cfg, conf["voxel"], 16)
+    if esdf:
+        m.esdf_create(po.EsdfConfig(max_distance_m=2.0, default_distance_m=2.0,
+                                    min_distance_m=conf["cfg"]["default_truncation_distance"] / 2, min_diff_m=1e-3))
     secs = []
     for s in scans:
-        m.integrate(kind, s)
-        secs.append(m.last_seconds())
+        m.integrate(KIND_ID[conf["kind"]], s)
+        t = m.last_seconds()
+        if esdf:
+            m.esdf_update(batch=False, clear_updated_flag=True)
+            t += m.last_seconds()
+        secs.append(t)
     m.close()
     return which, secs
 
 
-def calibrate_threads(scans):
+def calibrate_threads(conf, scans):
     """The reference defaults to hardware_concurrency threads (tsdf_integrator.h:70) but
     its per-call std::thread fan-out often loses to fewer threads; give it the best."""
     ncpu = os.cpu_count() or 1
@@ -190,7 +239,7 @@ def calibrate_threads(scans):
     for t in cands:
         if t > ncpu:
             continue
-        _, secs = time_reference(scans, t)
+        _, secs = time_reference(conf, scans, t)
         v = float(np.mean(secs[1:])) if len(secs) > 1 else secs[0]
         detail[str(t)] = round(v * 1e3, 3)
         if best is None or v < best[1]:
@@ -198,14 +247,14 @@ def calibrate_threads(scans):
     return best[0], detail
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, conf, rank):
+    """The reference's own CPU implementation of the path (oracle/_ref: its translation units compiled
+    where they lie) on this box's host cores; none of the engine is loaded in this process."""
     if rank != 0:
         return
-    from oracle import pyoracle as po
-
-    scans = make_scans(args.warmup + args.steps)
-    threads, detail = calibrate_threads(scans[:3])
-    which, secs = time_reference(scans, threads)
+    scans = make_scans(conf, args.warmup + args.steps)
+    threads, detail = calibrate_threads(conf, scans[:3])
+    which, secs = time_reference(conf, scans, threads, esdf=bool(conf.get("esdf")))
     timed = secs[args.warmup:]
     pts = sum(int(s[0].shape[0]) for s in scans[args.warmup:])
     total = float(sum(timed))
@@ -213,12 +262,10 @@ def run_reference_arm(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(timed)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "integrator": "merged", "voxel_size_m": VOXEL_SIZE,
-                   "truncation_m": TRUNC, "scan": "640x480 pinhole, box room + 4 objects, 15% dropouts",
-                   "points_per_scan_mean": pts / max(1, len(timed))},
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(conf, scans[args.warmup:]),
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": which,
-                         "sample": f"{len(timed)} scans of the workload; MergedTsdfIntegrator, integrator_threads={threads} "
+                         "sample": f"{len(timed)} scans of the workload; {conf['kind']} integrator, integrator_threads={threads} "
                                    f"(fastest of {detail} ms/scan; host has {os.cpu_count()} logical cores)"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,12 +273,97 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------- DRAM traffic (ncu)
+NCU_METRICS = "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
+
+
+def traffic_child(conf):
+    """Run under `ncu` by measure_traffic(): a few synchronous scans, nothing else."""
+    import torch
+
+    import voxblox_b200 as vb
+
+    scans = make_scans(conf, 5)
+    layer = vb.Layer(conf["voxel"], 16, engine_options=vb.EngineOptions(**conf["opts"]))
+    integ = vb.TsdfIntegratorFactory.create(conf["kind"], vb.TsdfIntegratorConfig(**conf["cfg"]), layer)
+    d = [(torch.from_numpy(s[0]).cuda(), torch.from_numpy(s[1]).cuda()) for s in scans]
+    for s, (x, c) in zip(scans, d):
+        integ.integratePointCloudDevice((s[2], s[3]), x.data_ptr(), c.data_ptr(), int(s[0].shape[0]))
+    print(json.dumps({"scans": len(scans)}), flush=True)
+
+
+def measure_traffic(conf_name, timeout_s=300):
+    """dram__bytes_read.sum + dram__bytes_write.sum per kernel, measured NOW on this box by running a
+    5-scan child of this script under ncu (cache control at its default: every kernel starts with
+    cold caches, so the figures are upper bounds for the steady state in which the map's blocks stay
+    in the 126 MB L2).  Returns bytes per scan per kernel name, or {"unavailable": why}."""
+    import csv
+    import shutil
+    import tempfile
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"unavailable": "ncu not found"}
+    with tempfile.TemporaryDirectory() as td:
+        logf = os.path.join(td, "ncu.csv")
+        cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "--print-units", "base", "--csv",
+               "--log-file", logf, sys.executable, os.path.abspath(__file__), "--traffic-child", "--config", conf_name]
+        try:
+            env = dict(os.environ)
+            env.pop("RANK", None)
+            env.pop("WORLD_SIZE", None)
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s, env=env)
+        except Exception as exc:
+            return {"unavailable": f"ncu run failed: {exc!r}"}
+        if p.returncode != 0 or not os.path.exists(logf):
+            return {"unavailable": f"ncu exit code {p.returncode}: {p.stderr[-300:]}"}
+        n_scans = 5
+        per = {}
+        with open(logf, newline="") as f:
+            rows = [r for r in csv.reader(f) if len(r) > 10]
+        if not rows:
+            return {"unavailable": "ncu wrote no rows"}
+        hdr = None
+        for r in rows:
+            if "Kernel Name" in r and "Metric Name" in r:
+                hdr = r
+                continue
+            if hdr is None:
+                continue
+            rec = dict(zip(hdr, r))
+            name = rec.get("Kernel Name", "").split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
+            try:
+                val = float(rec.get("Metric Value", "0").replace(",", ""))
+            except ValueError:
+                continue
+            d = per.setdefault(name, {"dram_bytes": 0.0, "ns": 0.0, "launches": 0})
+            m = rec.get("Metric Name", "")
+            if m.startswith("dram__bytes"):
+                d["dram_bytes"] += val
+            elif m.startswith("gpu__time_duration"):
+                d["ns"] += val
+                d["launches"] += 1
+        out = {k: {"dram_bytes_per_scan": v["dram_bytes"] / n_scans, "us_per_scan_under_ncu": v["ns"] / n_scans / 1e3,
+                   "launches_per_scan": v["launches"] / n_scans} for k, v in per.items()}
+        return {"per_kernel": out, "total_dram_bytes_per_scan": sum(v["dram_bytes"] for v in per.values()) / n_scans,
+                "scans": n_scans, "how": "ncu --metrics " + NCU_METRICS + " (cold caches per kernel), run inside this bench"}
+
+
 # --------------------------------------------------------------------------- ours
-def run_ours(args, rank, world):
+STAGE_OF_KERNEL = {  # stage name (Layer.stageMs) -> kernels that run in it
+    "point_keys": ("k_point_bounds", "k_point_keys"), "point_sort": ("k_sort_prepare", "k_sort_pass", "k_sort_to_a"),
+    "bundle_order": ("k_heads", "k_bundle_order"), "bundle_merge": ("k_merge",), "scan": ("k_exclusive_scan", "k_set_total"),
+    "ray_emit": ("k_rays_emit_warp", "k_rays_emit", "k_rays_count"), "assign": ("k_assign",),
+    "apply": ("k_apply_short", "k_apply_verify", "k_apply_long", "k_apply_block"),
+}
+
+
+def run_ours(args, conf, rank, world):
     import torch
     import torch.distributed as dist
 
     import voxblox_b200 as vb
+    from voxblox_b200 import sharded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
@@ -242,82 +374,103 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
 
     n_total = args.warmup + args.steps
-    # weak scaling: every rank integrates its own stream of scans (a different stretch of
-    # the trajectory) into its own map -- see DESIGN.md "multi-GPU" for the sharded mode.
-    scans = make_scans(n_total, start=rank * n_total)
+    # N > 1: ONE map, sharded over the ranks by block ownership; every rank receives every scan
+    # (identical, seeded) -- strong scaling.  DESIGN.md "multi-GPU".
+    scans = make_scans(conf, n_total)
     npts = [int(s[0].shape[0]) for s in scans]
-    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=TRUNC)
-    opts = vb.EngineOptions(device=local, max_blocks=16384, max_points_per_scan=1 << 19,
-                            max_updates_per_pass=1 << 24)
+    cfg = vb.TsdfIntegratorConfig(**conf["cfg"])
+    kind = conf["kind"]
+    do_esdf = bool(conf.get("esdf"))
 
-    def fresh():
-        layer = vb.Layer(VOXEL_SIZE, 16, engine_options=opts)
-        return layer, vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    def fresh(rank_=rank, world_=world):
+        opts = vb.EngineOptions(device=local, rank=rank_, world_size=world_, **conf["opts"])
+        layer = vb.Layer(conf["voxel"], 16, engine_options=opts)
+        return layer, vb.TsdfIntegratorFactory.create(kind, cfg, layer)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- (1) value: inputs resident in HBM, device-timed over the K steps -----------------
+    def reduce_max(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
     h_xyz = [torch.from_numpy(s[0]).pin_memory() for s in scans]
     h_rgba = [torch.from_numpy(s[1]).pin_memory() for s in scans]
     d_xyz = [torch.from_numpy(s[0]).to(dev) for s in scans]
     d_rgba = [torch.from_numpy(s[1]).to(dev) for s in scans]
-    # (1a) the synchronous call: returns when the scan is in the map (one host round trip per scan)
+    pts_timed = float(sum(npts[args.warmup:]))
+    steps = max(1, args.steps)
+
+    # ---- (1a) the synchronous call: returns when the scan is in the map (one host round trip per scan)
     layer, integ = fresh()
-    launches = 0
-    for i in range(args.warmup):
+    esdf_int = None
+    if do_esdf:
+        esdf_layer = vb.Layer(conf["voxel"], 16, voxel_type="esdf")
+        esdf_int = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(max_distance_m=2.0, default_distance_m=2.0,
+                                                              min_distance_m=conf["cfg"]["default_truncation_distance"] / 2,
+                                                              min_diff_m=1e-3), layer, esdf_layer)
+
+    def sync_step(i):
         integ.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+        if esdf_int is not None:
+            esdf_int.updateFromTsdfLayer(True)
+
+    for i in range(args.warmup):
+        sync_step(i)
     barrier()
     layer.timerStart()
+    U = B = K = 0
     for i in range(args.warmup, n_total):
-        integ.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-        launches += integ.counters()["kernel_launches"]
+        sync_step(i)
+        c = integ.counters()
+        U += c["voxels_touched"]
+        B += c["blocks_touched"]
+        K += c["updates"]
     sync_ms = layer.timerStopMs()
     barrier()
-    del layer, integ
-    # (1b) headline: the same K scans submitted back to back (vbx_tsdf_integrate_async): the front
-    # half of scan i+1 overlaps the back half of scan i; timed until the last scan is in the map
-    layer, integ = fresh()
+    del layer, integ, esdf_int
+    # ---- (1b) headline: the same K scans submitted back to back (vbx_tsdf_integrate_async): stages of
+    # neighbouring scans overlap; timed on the device until the last scan is in the map.  With the ESDF
+    # update after every scan (C4) the calls are synchronous by nature: (1a) is the number.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for i in range(args.warmup):
-        integ.integratePointCloudAsync((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-    layer.sync()
-    barrier()
-    launches_before = integ.counters()["kernel_launches_total"]
-    sampler.mark_begin()
-    layer.timerStart()
-    t0 = time.perf_counter()
-    for i in range(args.warmup, n_total):
-        integ.integratePointCloudAsync((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-    dev_ms = layer.timerStopMs()  # drains both streams first
-    sampler.mark_end()
-    barrier()
-    launches = integ.counters()["kernel_launches_total"] - launches_before
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    last_counters = integ.counters()
-    n_blocks = layer.getNumberOfAllocatedBlocks()
-    pts_timed = sum(npts[args.warmup:])
-    t_ms = torch.tensor([dev_ms, wall_ms, sync_ms], dtype=torch.float64, device=dev)
-    tot_pts = torch.tensor([float(pts_timed)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot_pts, op=dist.ReduceOp.SUM)
-    dev_ms, wall_ms, sync_ms = float(t_ms[0]), float(t_ms[1]), float(t_ms[2])
-    all_pts = float(tot_pts[0])
-    value = all_pts / (dev_ms * 1e-3)
-
-    # ---- (2) e2e: the reference-facing call with HOST buffers (pinned), H2D inside -------
-    layer2, integ2 = fresh()
-    for rep_ in range(4):  # the GPU idled while the host set up this pass: bring the clocks back up
+    if do_esdf:
+        dev_ms, wall_ms, launches, last_counters, n_blocks = sync_ms, sync_ms, 0, {}, 0
+        sampler.mark_begin()
+        time.sleep(0.05)
+        sampler.mark_end()
+    else:
+        layer, integ = fresh()
         for i in range(args.warmup):
-            integ.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+            integ.integratePointCloudAsync((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+        layer.sync()
+        barrier()
+        launches_before = integ.counters()["kernel_launches_total"]
+        sampler.mark_begin()
+        layer.timerStart()
+        t0 = time.perf_counter()
+        for i in range(args.warmup, n_total):
+            integ.integratePointCloudAsync((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+        dev_ms = layer.timerStopMs()  # drains the pipeline first
+        sampler.mark_end()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        last_counters = integ.counters()
+        launches = last_counters["kernel_launches_total"] - launches_before
+        n_blocks = layer.getNumberOfAllocatedBlocks()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms, wall_ms, sync_ms = reduce_max(dev_ms, wall_ms, sync_ms)
+    value = pts_timed / (dev_ms * 1e-3)
+
+    # ---- (2) e2e: the reference-facing call with HOST buffers, H2D inside the timed region ----
     hx = [t.numpy() for t in h_xyz]
     hc = [t.numpy() for t in h_rgba]
+    layer2, integ2 = fresh()
     for i in range(args.warmup):
         integ2.integratePointCloud((scans[i][2], scans[i][3]), hx[i], hc[i])
     barrier()
@@ -329,7 +482,7 @@ def run_ours(args, rank, world):
     barrier()
     del layer2, integ2
     # headline e2e: host (page-locked) clouds submitted back to back; every step's H2D copy and the
-    # D2H read of its result block (128 B of counters / status) are inside the pipeline
+    # D2H read of its result block (192 B of counters / status) are inside the pipeline
     layer2, integ2 = fresh()
     for i in range(args.warmup):
         integ2.integratePointCloudAsync((scans[i][2], scans[i][3]), hx[i], hc[i])
@@ -352,318 +505,197 @@ def run_ours(args, rank, world):
     e2e_pageable_ms = layer2b.timerStopMs()
     barrier()
     del layer2b, integ2b
-    t_e = torch.tensor([e2e_ms, e2e_sync_ms, e2e_pageable_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = all_pts / (float(t_e[0]) * 1e-3)
+    e2e_ms, e2e_sync_ms, e2e_pageable_ms = reduce_max(e2e_ms, e2e_sync_ms, e2e_pageable_ms)
+    e2e_value = pts_timed / (e2e_ms * 1e-3)
     h2d = int(np.mean([16 * n for n in npts[args.warmup:]]))
+
+    # ---- N > 1: the union of the shards must be the single-GPU map; cost of read replicas -------
+    shard_info = None
+    if world > 1:
+        import hashlib
+
+        sl = sharded.ShardedLayer(layer2)
+        gathered = sl.gather()
+        t0 = time.perf_counter()
+        n_recv = sl.sync_replicas()
+        torch.cuda.synchronize()
+        sync_replica_ms = (time.perf_counter() - t0) * 1e3
+        if rank == 0:
+            ls, isg = fresh(0, 1)
+            for i in range(n_total):
+                isg.integratePointCloud((scans[i][2], scans[i][3]), hx[i], hc[i])
+            single = ls.blocks()
+
+            def dig(b):
+                hsh = hashlib.sha256()
+                for k in sorted(b):
+                    hsh.update(np.asarray(k, np.int32).tobytes())
+                    hsh.update(b[k].tobytes())
+                return hsh.hexdigest()[:16]
+
+            shard_info = {"union_of_shards_digest": dig(gathered), "single_gpu_digest": dig(single),
+                          "union_equals_single_gpu_map": dig(gathered) == dig(single), "blocks": len(single),
+                          "blocks_owned_by_rank0": int(sum(1 for k in gathered if sharded.block_owner([k], world)[0] == 0)),
+                          "sync_replicas_all_blocks_wall_ms": sync_replica_ms, "blocks_received_rank0": n_recv}
+            del ls, isg
+        barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- (3) per-stage device time (profiling pass) and the roofline of the top kernel ---
-    layer3, integ3 = fresh()
-    U = B = K = 0
+    # ---- (3) per-stage device time (profiling pass), roofline ---------------------------------
+    layer3, integ3 = fresh(0, 1)
     for i in range(n_total):
         if i == args.warmup:
             layer3.setStageProfiling(True)
         integ3.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-        if i >= args.warmup:
-            c = integ3.counters()
-            U += c["voxels_touched"]
-            B += c["blocks_touched"]
-            K += c["updates"]
     stages = {k: v for k, v in layer3.stageMs().items() if v[1] > 0}
-    top = max(stages, key=lambda k: stages[k][0])
-    steps = max(1, args.steps)
+    del layer3, integ3
     n_mean, u_mean, b_mean, k_mean = pts_timed / steps, U / steps, B / steps, K / steps
-    # algorithmic bytes per launch of each stage: SURVEY.md 8(d)'s per-scan
-    # figure 16 N + 24 U + 20 B, plus what each stage of THIS design must read and write once.
-    alg = {"point_keys": 12 * n_mean + 8 * n_mean, "point_sort": 2 * 8 * n_mean,
-           "bundle_merge": (16 + 8) * n_mean, "ray_count": 16 * n_mean, "scan": 8 * n_mean,
-           "ray_emit": 8 * k_mean + 20 * b_mean, "assign": 20 * b_mean, "update_sort": 2 * 8 * k_mean,
-           "apply": 24 * u_mean + 16 * k_mean}
-    # DRAM traffic of the dominant kernels from `ncu --set full` captures (profiles/), per launch
-    traffic = {"bundle_merge": 6.35e6, "apply": 4.66e6 + 1.32e6, "ray_emit": 1.18e6}
+    # algorithmic bytes per scan = 16 N + 24 U + 20 B; each stage owns the part of
+    # it that it must move (the cloud is algorithmically read once: by the stages up to the bundle fold;
+    # block keys / slab pointers by the ray walk; the touched voxels by the apply).  Update records, sort
+    # traffic and the per-ray tables are this design's own overhead and count for nothing here.
+    alg = {"point_keys": 12 * n_mean, "bundle_merge": 16 * n_mean, "ray_emit": 20 * b_mean, "apply": 24 * u_mean,
+           "point_sort": 0.0, "bundle_order": 0.0, "scan": 0.0, "update_sort": 0.0, "assign": 0.0, "ray_count": 0.0}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    top_ms = stages[top][0] / stages[top][1]
-    achieved = alg[top] / (top_ms * 1e-3) / 1e9
     scan_alg = 16 * n_mean + 24 * u_mean + 20 * b_mean
-    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic.get(top),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "alg_bytes_per_launch": alg[top], "avg_launch_ms": top_ms,
-                "whole_scan": {"alg_bytes": scan_alg, "ms": dev_ms / steps,
-                               "achieved": scan_alg / (dev_ms / steps * 1e-3) / 1e9,
-                               "frac": scan_alg / (dev_ms / steps * 1e-3) / 1e9 / peak},
-                "stage_ms_per_scan": {k: round(v[0] / steps, 5) for k, v in stages.items()}}
+    traffic = measure_traffic(args.config) if args.traffic else {"unavailable": "--no-traffic"}
+    top = max(stages, key=lambda k: stages[k][0]) if stages else None
+    top_ms = stages[top][0] / stages[top][1] if top else None
+    dom = None
+    if top:
+        t_bytes = None
+        if "per_kernel" in traffic:
+            t_bytes = sum(v["dram_bytes_per_scan"] for k, v in traffic["per_kernel"].items()
+                          if k in STAGE_OF_KERNEL.get(top, ()))
+        dom = {"stage": top, "kernels": list(STAGE_OF_KERNEL.get(top, ())), "avg_ms": top_ms,
+               "alg_bytes_per_launch": alg.get(top, 0.0),
+               "achieved": alg.get(top, 0.0) / (top_ms * 1e-3) / 1e9, "frac": alg.get(top, 0.0) / (top_ms * 1e-3) / 1e9 / peak,
+               "traffic": t_bytes}
+    ms_per_step = dev_ms / steps
+    roofline = {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650",
+                # headline: SURVEY 8(d)'s whole-scan bytes over the measured time per scan
+                "alg_bytes_per_launch": scan_alg, "alg_bytes_formula": "16*N + 24*U + 20*B (SURVEY.md 8d)",
+                "achieved": scan_alg / (ms_per_step * 1e-3) / 1e9, "frac": scan_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+                "traffic": traffic.get("total_dram_bytes_per_scan"), "traffic_detail": traffic,
+                "synchronous_call_frac": scan_alg / (sync_ms / steps * 1e-3) / 1e9 / peak,
+                "dominant_kernel": dom,
+                "stage_ms_per_scan": {k: round(v[0] / steps, 5) for k, v in stages.items()},
+                "why_small": "a scan moves ~5 MB (1 us at HBM speed); every stage is a latency chain "
+                             "(dependent loads, ordered per-voxel update chains), not a bandwidth stream"}
 
     # ---- (4) CPU baseline on this box's host cores, bounded sample ------------------------
     from oracle import pyoracle as po
 
-    sample = scans[:min(len(scans), 12)]
-    threads, detail = calibrate_threads(sample[:3])
-    which, secs = time_reference(sample, threads)
+    sample = scans[:min(len(scans), 12 if conf["scan"] != "c5_lidar_scan" else 5)]
+    threads, detail = calibrate_threads(conf, sample[:3])
+    which, secs = time_reference(conf, sample, threads, esdf=do_esdf)
     cpu_pts = sum(int(s[0].shape[0]) for s in sample[2:])
     cpu_value = cpu_pts / float(sum(secs[2:]))
     cpu = {"value": cpu_value, "unit": "points/s", "cores": threads, "kind": which,
-           "sample": f"{len(sample) - 2} scans of the workload after 2 warm-up scans; MergedTsdfIntegrator "
+           "sample": f"{len(sample) - 2} scans of the workload after 2 warm-up scans; {kind} integrator "
                      f"with integrator_threads={threads} (fastest of {detail} ms/scan; {os.cpu_count()} logical cores)"}
+    try:  # the same translation units at -O3 -march=x86-64-v3: a faster-than-stock build, for context
+        if po.available("reference_o3"):
+            _, secs3 = time_reference(conf, sample, threads, which="reference_o3", esdf=do_esdf)
+            cpu["o3_x86_64_v3"] = {"value": cpu_pts / float(sum(secs3[2:])), "cores": threads}
+    except Exception as exc:
+        cpu["o3_x86_64_v3"] = {"error": repr(exc)}
 
-    # ---- (5) parity spot check against the oracle on the same scans -----------------------
-    from tests.parity import compare_tsdf
+    # ---- (5) parity against the reference itself (one thread) on the first scans -----------
+    parity = None
+    if kind != "fast":
+        from tests.parity import compare_tsdf
 
-    layer4, integ4 = fresh()
-    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=TRUNC), VOXEL_SIZE, 16)
-    for s in scans[:3]:
-        integ4.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
-    rep = compare_tsdf(layer4, omap)
+        layer4, integ4 = fresh(0, 1)
+        pw = "reference" if po.available("reference") else "port"
+        omap = po.OracleMap(po.OracleLib(pw), po.TsdfConfig(integrator_threads=1, **conf["cfg"]), conf["voxel"], 16)
+        for s in scans[:3]:
+            integ4.integratePointCloud((s[2], s[3]), s[0], s[1])
+            omap.integrate(KIND_ID[kind], s)
+        rep = compare_tsdf(layer4, omap)
+        parity = {"against": pw + " (integrator_threads=1)", "scans": 3, "blocks_equal": rep["blocks_equal"],
+                  "max_rel_err": rep.get("max_rel_err"), "bit_exact_voxels": rep.get("n_bit_exact"),
+                  "voxels": rep.get("n_voxels"), "color_mismatch": rep.get("color_mismatch")}
+        del layer4, integ4
 
     # ---- (6) the callers either side of the path: ESDF update and
     # incremental mesh after every scan; device time per call, not part of `value`
     downstream = None
-    try:
-        layer5, integ5 = fresh()
-        esdf5 = vb.Layer(VOXEL_SIZE, 16, voxel_type="esdf")
-        e5 = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(max_distance_m=2.0, default_distance_m=2.0,
-                                                       min_distance_m=TRUNC / 2, min_diff_m=1e-3), layer5, esdf5)
-        mesh5 = vb.MeshLayer(layer5.block_size())
-        m5 = vb.MeshIntegrator(vb.MeshIntegratorConfig(), layer5, mesh5)
-        t_ms5, e_ms5, m_ms5, m_wall5 = [], [], [], []
-        k5 = min(n_total, 12)
-        for i in range(k5):
-            integ5.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-            t_ms5.append(integ5.lastDeviceMs())
-            e5.updateFromTsdfLayer(True)
-            e_ms5.append(e5.lastDeviceMs())
-            t0 = time.perf_counter()
-            m5.generateMesh(True, True)
-            m_wall5.append((time.perf_counter() - t0) * 1e3)
-            m_ms5.append(m5.lastDeviceMs())
-        w = slice(min(3, k5 - 1), None)
-        downstream = {"scans": k5, "tsdf_sync_device_ms": float(np.mean(t_ms5[w])),
-                      "esdf_incremental_device_ms": float(np.mean(e_ms5[w])),
-                      "mesh_incremental_device_ms": float(np.mean(m_ms5[w])),
-                      "mesh_incremental_wall_ms_incl_download": float(np.mean(m_wall5[w])),
-                      "mesh_vertices_last_call": int(m5.last_vertices), "mesh_blocks_last_call": int(m5.last_blocks),
-                      "note": "Merged + EsdfIntegrator::updateFromTsdfLayer(true) + MeshIntegrator::generateMesh(true, true) "
-                              "after every scan (config C4 + N3); CPU reference: scripts/esdf_bench.py, scripts/mesh_bench.py"}
-    except Exception as exc:  # never lose the headline line to an optional section
-        downstream = {"error": repr(exc)}
+    if args.config == "bench":
+        try:
+            layer5, integ5 = fresh(0, 1)
+            esdf5 = vb.Layer(conf["voxel"], 16, voxel_type="esdf")
+            e5 = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(max_distance_m=2.0, default_distance_m=2.0,
+                                                           min_distance_m=0.1, min_diff_m=1e-3), layer5, esdf5)
+            mesh5 = vb.MeshLayer(layer5.block_size())
+            m5 = vb.MeshIntegrator(vb.MeshIntegratorConfig(), layer5, mesh5)
+            t_ms5, e_ms5, m_ms5, m_wall5 = [], [], [], []
+            k5 = min(n_total, 12)
+            for i in range(k5):
+                integ5.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
+                t_ms5.append(integ5.lastDeviceMs())
+                e5.updateFromTsdfLayer(True)
+                e_ms5.append(e5.lastDeviceMs())
+                t0 = time.perf_counter()
+                m5.generateMesh(True, True)
+                m_wall5.append((time.perf_counter() - t0) * 1e3)
+                m_ms5.append(m5.lastDeviceMs())
+            w = slice(min(3, k5 - 1), None)
+            ec = e5.counters()
+            downstream = {"scans": k5, "tsdf_sync_device_ms": float(np.mean(t_ms5[w])),
+                          "esdf_incremental_device_ms": float(np.mean(e_ms5[w])),
+                          "mesh_incremental_device_ms": float(np.mean(m_ms5[w])),
+                          "mesh_incremental_wall_ms_incl_download": float(np.mean(m_wall5[w])),
+                          "mesh_vertices_last_call": int(m5.last_vertices), "mesh_blocks_last_call": int(m5.last_blocks),
+                          "esdf_last_counters": ec,
+                          "esdf_roofline": {"alg_bytes_formula": "(12+20+20)*4096*B_upd + 40*R (SURVEY.md 8d)",
+                                            "alg_bytes": 52 * 4096 * ec.get("blocks", 0) + 40 * ec.get("relaxations", 0),
+                                            "frac": (52 * 4096 * ec.get("blocks", 0) + 40 * ec.get("relaxations", 0)) /
+                                                    max(1e-9, e_ms5[-1] * 1e-3) / 1e9 / peak},
+                          "note": "Merged + EsdfIntegrator::updateFromTsdfLayer(true) + MeshIntegrator::generateMesh(true, true) "
+                                  "after every scan (config C4 + N3)"}
+        except Exception as exc:  # never lose the headline line to an optional section
+            downstream = {"error": repr(exc)}
 
+    config = config_dict(conf, scans[args.warmup:])
+    config.update({"updates_per_scan_mean": k_mean, "voxels_touched_per_scan_mean": u_mean,
+                   "blocks_touched_per_scan_mean": b_mean, "map_blocks_after_run": n_blocks,
+                   "parallelism": ("single GPU" if world == 1 else
+                                   f"own{world}: ONE map sharded over {world} GPUs by block ownership; every rank receives "
+                                   "every scan, folds and walks all rays, applies only the voxels of its own blocks; no "
+                                   "collective while integrating")})
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "integrator": "merged", "voxel_size_m": VOXEL_SIZE,
-                   "truncation_m": TRUNC, "voxels_per_side": 16,
-                   "scan": "640x480 pinhole, box room + 4 objects, 15% dropouts, 30 Hz handheld trajectory",
-                   "points_per_scan_mean": n_mean, "updates_per_scan_mean": k_mean,
-                   "voxels_touched_per_scan_mean": u_mean, "blocks_touched_per_scan_mean": b_mean,
-                   "map_blocks_after_run": n_blocks,
-                   "l2": "every step integrates a different scan (cloud set > L2); the map's voxel blocks stay "
-                         "hot across steps as they do in a mapping session",
-                   "parallelism": "one map per GPU" if world > 1 else "single GPU"},
-        "clocks": clocks, "wall_ms_per_step": wall_ms / steps,
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 128,
-                "ms_per_step": float(t_e[0]) / steps, "submission": "vbx_tsdf_integrate_async, page-locked host clouds",
-                "synchronous_call": {"value": all_pts / (float(t_e[1]) * 1e-3), "ms_per_step": float(t_e[1]) / steps},
-                "pageable_host_memory": {"value": all_pts / (float(t_e[2]) * 1e-3), "ms_per_step": float(t_e[2]) / steps}},
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config, "clocks": clocks, "wall_ms_per_step": wall_ms / steps,
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 192 * world,
+                "ms_per_step": e2e_ms / steps, "submission": "vbx_tsdf_integrate_async, page-locked host clouds"
+                + (" (every rank copies the whole cloud over its own PCIe link)" if world > 1 else ""),
+                "synchronous_call": {"value": pts_timed / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / steps},
+                "pageable_host_memory": {"value": pts_timed / (e2e_pageable_ms * 1e-3), "ms_per_step": e2e_pageable_ms / steps}},
         "submission": "vbx_tsdf_integrate_async: scans queued back to back, timed until the last one is in the map",
-        "synchronous_call": {"value": all_pts / (sync_ms * 1e-3), "ms_per_step": sync_ms / steps,
-                             "note": "vbx_tsdf_integrate_device, returns when the scan is in the map"},
-        "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
-        "parity": {"scans": 3, "blocks_equal": rep["blocks_equal"], "max_rel_err": rep.get("max_rel_err"),
-                   "bit_exact_voxels": rep.get("n_bit_exact"), "voxels": rep.get("n_voxels"),
-                   "color_mismatch": rep.get("color_mismatch")},
-        "last_counters": last_counters,
-        "downstream": downstream,
+        "synchronous_call": {"value": pts_timed / (sync_ms * 1e-3), "ms_per_step": sync_ms / steps,
+                             "note": "vbx_tsdf_integrate_device, returns when the scan is in the map"
+                             + (" + EsdfIntegrator::updateFromTsdfLayer(true)" if do_esdf else "")},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "last_counters": last_counters, "downstream": downstream,
     }
+    if shard_info is not None:
+        line["sharded_map"] = shard_info
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def run_sharded(args, rank, world):
-    """N > 1.  Headline: the scans are the units and they shard across ranks -- every rank integrates
-    its own scan stream into its own map, no collective on the data path (weak scaling).  Also
-    measured and reported beside it: the within-scan design of the north_star -- one map, every
-    scan sharded over the ranks by contiguous ray ranges with one NCCL all-gather of update records
-    per scan (strong scaling; DESIGN.md "multi-GPU")."""
-    import torch
-    import torch.distributed as dist
-
-    import voxblox_b200 as vb
-    from voxblox_b200 import sharded
-
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    n_total = args.warmup + args.steps
-    scans = make_scans(n_total)  # identical on every rank (seeded)
-    npts = [int(s[0].shape[0]) for s in scans]
-    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=TRUNC)
-
-    def fresh(rank_, world_):
-        opts = vb.EngineOptions(device=local, max_blocks=16384, max_points_per_scan=1 << 19,
-                                max_updates_per_pass=1 << 24, rank=rank_, world_size=world_)
-        layer = vb.Layer(VOXEL_SIZE, 16, engine_options=opts)
-        return layer, vb.TsdfIntegratorFactory.create("merged", cfg, layer)
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    d_xyz = [torch.from_numpy(s[0]).to(dev) for s in scans]
-    d_rgba = [torch.from_numpy(s[1]).to(dev) for s in scans]
-    h_xyz = [torch.from_numpy(s[0]).pin_memory() for s in scans]
-    h_rgba = [torch.from_numpy(s[1]).pin_memory() for s in scans]
-
-    # ---- value: inputs resident in HBM on every rank
-    layer, integ = fresh(rank, world)
-    sh = sharded.ShardedTsdfIntegrator(integ, record_capacity=(1 << 24) // world)
-    for i in range(args.warmup):
-        sh.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    sampler.mark_begin()
-    layer.timerStart()
-    launches = 0
-    xbytes = 0
-    for i in range(args.warmup, n_total):
-        sh.integratePointCloudDevice((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-        launches += integ.counters()["kernel_launches"]
-        xbytes += sh.last_exchange_bytes
-    dev_ms = layer.timerStopMs()
-    sampler.mark_end()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    dev_ms = float(t_ms[0])
-    pts_timed = float(sum(npts[args.warmup:]))
-    value = pts_timed / (dev_ms * 1e-3)
-
-    # ---- e2e: host buffers, H2D of the cloud on every rank inside the timed region
-    layer2, integ2 = fresh(rank, world)
-    sh2 = sharded.ShardedTsdfIntegrator(integ2, record_capacity=(1 << 24) // world)
-    stage_xyz = torch.empty((max(npts), 3), dtype=torch.float32, device=dev)
-    stage_rgba = torch.empty((max(npts), 4), dtype=torch.uint8, device=dev)
-
-    def e2e_step(i):
-        stage_xyz[:npts[i]].copy_(h_xyz[i], non_blocking=True)
-        stage_rgba[:npts[i]].copy_(h_rgba[i], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        sh2.integratePointCloudDevice((scans[i][2], scans[i][3]), stage_xyz.data_ptr(), stage_rgba.data_ptr(), npts[i])
-        return integ2.counters()
-
-    for i in range(args.warmup):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.warmup, n_total):
-        e2e_step(i)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = pts_timed / (float(t_e[0]) * 1e-3)
-
-    # ---- replicas (weak scaling, for context): every rank integrates its own scan stream
-    layer3, integ3 = fresh(0, 1)
-    sampler3 = ClockSampler(local)
-    if rank == 0:
-        sampler3.start()
-    for i in range(args.warmup):
-        integ3.integratePointCloudAsync((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-    layer3.sync()
-    barrier()
-    l3 = integ3.counters()["kernel_launches_total"]
-    sampler3.mark_begin()
-    layer3.timerStart()
-    for i in range(args.warmup, n_total):
-        integ3.integratePointCloudAsync((scans[i][2], scans[i][3]), d_xyz[i].data_ptr(), d_rgba[i].data_ptr(), npts[i])
-    rep_ms = layer3.timerStopMs()
-    sampler3.mark_end()
-    barrier()
-    rep_launches = integ3.counters()["kernel_launches_total"] - l3
-    clocks = sampler3.stop() if rank == 0 else None
-    t_r = torch.tensor([rep_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
-    replicas_value = world * pts_timed / (float(t_r[0]) * 1e-3)
-
-    # all replicas must hold the same map: compare a digest of rank 0's blocks with every rank's
-    import hashlib
-
-    idx = layer.getAllAllocatedBlocks()
-    vox, _ = layer.getBlocks(idx)
-    digest = int.from_bytes(hashlib.sha256(idx.tobytes() + vox.tobytes()).digest()[:7], "little")
-    dg = torch.tensor([digest], dtype=torch.int64, device=dev)
-    allg = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(allg, dg)
-    replicas_identical = bool((allg == allg[0]).all())
-
-    # ---- replicas, e2e: every rank feeds its own map from pinned host buffers
-    layer4, integ4 = fresh(0, 1)
-    hx = [t.numpy() for t in h_xyz]
-    hc = [t.numpy() for t in h_rgba]
-    for i in range(args.warmup):
-        integ4.integratePointCloudAsync((scans[i][2], scans[i][3]), hx[i], hc[i])
-    layer4.sync()
-    barrier()
-    layer4.timerStart()
-    for i in range(args.warmup, n_total):
-        integ4.integratePointCloudAsync((scans[i][2], scans[i][3]), hx[i], hc[i])
-    rep_e2e_ms = layer4.timerStopMs()
-    barrier()
-    t_re = torch.tensor([rep_e2e_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t_re, op=dist.ReduceOp.MAX)
-    replicas_e2e = world * pts_timed / (float(t_re[0]) * 1e-3)
-    n_l = torch.tensor([rep_launches], dtype=torch.int64, device=dev)
-    dist.all_reduce(n_l, op=dist.ReduceOp.SUM)
-
-    if rank == 0:
-        steps = max(1, args.steps)
-        line = {
-            "metric": METRIC, "value": replicas_value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": float(t_r[0]) / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "integrator": "merged", "voxel_size_m": VOXEL_SIZE,
-                       "truncation_m": TRUNC, "voxels_per_side": 16,
-                       "scan": "640x480 pinhole, box room + 4 objects, 15% dropouts, 30 Hz handheld trajectory",
-                       "points_per_scan_mean": pts_timed / steps,
-                       "parallelism": f"{world} replicas: one map and one scan stream per GPU, scans sharded across "
-                                      "ranks, no collective on the data path (a 0.6 ms scan is too small to shard "
-                                      "internally; see ray_range_sharded)",
-                       "l2": "every step integrates a different scan; the map's blocks stay hot"},
-            "clocks": clocks,
-            "e2e": {"value": replicas_e2e, "unit": "points/s", "h2d_bytes_per_step": int(16 * pts_timed / steps),
-                    "d2h_bytes_per_step": 128, "ms_per_step": float(t_re[0]) / steps,
-                    "submission": "vbx_tsdf_integrate_async, page-locked host clouds"},
-            "submission": "vbx_tsdf_integrate_async: scans queued back to back, timed until the last one is in the map",
-            "gpu_launches": int(n_l[0]),
-            # the north_star's within-scan design: ONE map, every scan sharded by contiguous ray ranges,
-            # one NCCL all-gather of update records per scan; replicas bit-identical.  Strong scaling.
-            "ray_range_sharded": {"value": value, "unit": "points/s", "scaling": "strong",
-                                  "ms_per_step": dev_ms / steps,
-                                  "e2e": {"value": e2e_value, "ms_per_step": float(t_e[0]) / steps},
-                                  "exchange_bytes_per_scan": xbytes / steps, "gpu_launches": int(launches),
-                                  "replicas_identical": replicas_identical},
-        }
-        print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
 
 
 def main():
@@ -672,26 +704,36 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="bench", choices=sorted(CONFIGS))
+    ap.add_argument("--trunc", type=float, default=None, help="override default_truncation_distance (C2: 4.0 = the literal '4 m')")
+    ap.add_argument("--no-traffic", dest="traffic", action="store_false", help="skip the ncu DRAM-traffic pass")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    conf = dict(CONFIGS[args.config])
+    if args.trunc is not None:
+        conf["cfg"] = dict(conf["cfg"], default_truncation_distance=args.trunc)
+        conf["workload"] += f"_trunc{args.trunc:g}"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import __graft_entry__ as g
 
     if rank == 0:
-        with open(os.devnull, "w") as devnull:
-            old = sys.stdout
-            sys.stdout = sys.stderr
-            try:
+        old = sys.stdout
+        sys.stdout = sys.stderr
+        try:
+            if args.impl == "reference":
+                g.build_oracle()  # the reference arm loads nothing of the engine
+            else:
                 g.build()
-            finally:
-                sys.stdout = old
-    if args.impl == "reference":
-        run_reference_arm(args, rank)
-    elif world > 1:
-        run_sharded(args, rank, world)
+        finally:
+            sys.stdout = old
+    if args.traffic_child:
+        traffic_child(conf)
+    elif args.impl == "reference":
+        run_reference_arm(args, conf, rank)
     else:
-        run_ours(args, rank, world)
+        run_ours(args, conf, rank, world)
 
 
 if __name__ == "__main__":

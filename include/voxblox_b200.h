@@ -110,7 +110,7 @@ typedef struct vbx_engine_options {
   uint32_t max_points_per_scan;   /* [1 << 20]                                        */
   uint64_t max_updates_per_pass;  /* ray-voxel update records per pass [1 << 26]      */
   int32_t rank;                   /* this process' rank in the group [0]              */
-  int32_t world_size;             /* number of ray-range shards [1]                   */
+  int32_t world_size;             /* block-ownership shards of ONE map [1], see below */
 } vbx_engine_options;
 
 /* Layer<TsdfVoxel>(voxel_size, voxels_per_side) + TsdfIntegratorBase(config, layer)
@@ -275,37 +275,17 @@ VBX_API int vbx_mesh_download(vbx_ctx* ctx, int32_t* idx3, uint64_t* first_verte
 
 VBX_API int vbx_sync(vbx_ctx* ctx);
 
-/* Ray-range sharding over the GPUs of one box (BASELINE.json north_star).
- * Every rank holds a full replica of the map and receives the full cloud.  A scan is integrated
- * in three steps per rank (vbx_engine_options.rank / world_size):
- *   1. vbx_shard_front: transform + bundle the WHOLE cloud (cheap, identical on every rank so
- *      that all ranks agree on the bundles), then merge and ray-cast only this rank's contiguous
- *      range of ray slots [rank*slice, (rank+1)*slice).  Writes this rank's update records
- *      (global voxel key, ray slot) and its slice of the per-ray tables into `d_pack` (device
- *      memory, vbx_shard_layout.pack_bytes bytes) and returns the record count.
- *   2. the caller all-gathers the counts and then the used prefix of every rank's pack
- *      (NCCL, torch.distributed), rank order.
- *   3. vbx_shard_back: every rank allocates the blocks of all gathered records on its replica
- *      and applies them in ray order -- the same per-voxel update order as one GPU, so all
- *      replicas (and the single-GPU result) are bit-identical.
- * Supported for the Simple and Merged integrators. */
-typedef struct vbx_shard_layout {
-  uint64_t record_capacity; /* update records per rank the pack can hold            */
-  uint64_t slice;           /* ray slots per rank = ceil(n / world_size)             */
-  uint64_t pack_bytes;      /* size of one rank's pack                               */
-  uint64_t off_ray_a, off_ray_c, off_records; /* byte offsets inside a pack: per-ray tables
-                                               * first, then 16-byte update records, so that
-                                               * a prefix of the pack is enough to exchange   */
-} vbx_shard_layout;
-VBX_API int vbx_shard_layout_for(vbx_ctx* ctx, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out);
-VBX_API int vbx_shard_front(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3], const float* d_xyz,
-                    const uint8_t* d_rgba, uint64_t n, int freespace, const vbx_shard_layout* layout,
-                    void* d_pack, uint64_t* count_out);
-/* d_gathered holds world_size pack prefixes, pack_stride bytes apart (>= off_records + 16 * max
- * count); counts = the world_size record counts (host memory). */
-VBX_API int vbx_shard_back(vbx_ctx* ctx, int kind, const float q_wxyz[4], const float t[3], uint64_t n,
-                   const vbx_shard_layout* layout, const void* d_gathered, uint64_t pack_stride,
-                   const uint64_t* counts);
+/* One map over the GPUs of one box: block-ownership sharding (BASELINE.json north_star; SURVEY.md
+ * section 8e "alternative: block-hash ownership (sharded map)"; DESIGN.md "multi-GPU").
+ * With vbx_engine_options.world_size = W > 1 every rank receives EVERY scan through the ordinary
+ * vbx_tsdf_integrate* calls.  Bundling, the bundle order, the merge and the ray walk are the same
+ * deterministic computation on every rank; a rank creates only the blocks it owns
+ * (vbx_block_owner(index) == rank) and applies only their voxel updates.  TsdfVoxel updates are
+ * order dependent and not associative (tsdf_integrator.cc:205-208), so the shards exchange
+ * nothing while integrating: the union of the W shards IS the single-GPU map, bit for bit, and
+ * every voxel keeps the reference's one-thread update order.  Consumers either work per shard or
+ * gather the blocks they need (vbx_mirror_updated / vbx_upload_blocks on the owner / reader). */
+VBX_API int vbx_block_owner(const vbx_ctx* ctx, const int32_t block_index[3], int32_t* owner);
 
 /* Measurement aids (the reference's counterpart is timing::Timer, utils/timing.h:132-199).
  * vbx_timer_start / vbx_timer_stop_ms bracket any number of calls with two CUDA events
@@ -329,6 +309,11 @@ VBX_API int vbx_host_copy_ms(vbx_ctx* ctx, const void* src, size_t bytes, float*
 VBX_API int vbx_debug_sort(vbx_ctx* ctx, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
                    uint32_t* perm_out);
 VBX_API int vbx_debug_scan(vbx_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out);
+/* Test hook for the Merged integrator's bundle order (the iteration order of the reference's
+ * unordered_map voxel_map, tsdf_integrator.cc:318-322, :436-456): element e is the e-th inserted key
+ * with LongIndexHash hashes[e]; out[p] = the element at iteration position p.  force_global != 0 uses
+ * the global-memory tables even when the shared-memory ones would fit. */
+VBX_API int vbx_debug_bundle_order(vbx_ctx* ctx, const uint32_t* hashes, uint32_t n, int force_global, uint32_t* out);
 VBX_API int vbx_timer_start(vbx_ctx* ctx);
 VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms);
 VBX_API int vbx_set_stage_profiling(vbx_ctx* ctx, int enabled);

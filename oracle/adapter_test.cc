@@ -96,8 +96,9 @@ int main() {
     std::printf("type %d (%s): blocks cpu %zu gpu %zu same %d, voxels %zu bit-exact %zu, rmse %.3g\n", type,
                 type == 1 ? "simple" : "merged", a.size(), b.size(), same_blocks ? 1 : 0, n, exact, rmse);
     if (!same_blocks) ++failures;
-    if (type == 1 && exact != n) ++failures;                 // same update order: bit-identical
-    if (type == 2 && !(rmse < 0.25 * voxel_size)) ++failures;  // CPU order = hash-map iteration order
+    // Simple: point order.  Merged: the device reproduces the iteration order of the reference's
+    // unordered_map (one integrator thread).  Both: bit-identical.
+    if (exact != n) ++failures;
   }
   // Pipelined adapter, and an adapter started from a non-empty layer: both must reproduce the
   // plain adapter bit for bit.

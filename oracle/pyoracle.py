@@ -18,6 +18,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libvbx_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libvbx_ref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "libvbx_ref_o3.so")  # timing-only build (-O3 -march=x86-64-v3)
+_PATHS = {"port": PORT_SO, "reference": REF_SO, "reference_o3": REF_O3_SO}
 
 TSDF_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4"), ("color", "u1", (4,))])
 ESDF_DTYPE = np.dtype([("distance", "<f4"), ("observed", "u1"), ("hallucinated", "u1"),
@@ -25,7 +27,7 @@ ESDF_DTYPE = np.dtype([("distance", "<f4"), ("observed", "u1"), ("hallucinated",
 assert TSDF_DTYPE.itemsize == 12 and ESDF_DTYPE.itemsize == 20
 
 SIMPLE, MERGED, FAST = 1, 2, 3
-ORDER_REFERENCE, ORDER_CANONICAL = 0, 1
+ORDER_REFERENCE = 0
 LAYER_TSDF, LAYER_ESDF = 0, 1
 
 
@@ -72,12 +74,12 @@ class EsdfConfig(C.Structure):
 
 
 def available(which: str) -> bool:
-    return os.path.exists(REF_SO if which == "reference" else PORT_SO)
+    return os.path.exists(_PATHS[which])
 
 
 class OracleLib:
     def __init__(self, which: str = "port"):
-        path = REF_SO if which == "reference" else PORT_SO
+        path = _PATHS[which]
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle` (or __graft_entry__.build())")
         self.which = which
@@ -121,10 +123,20 @@ class OracleLib:
         lib.vbo_mesh_get.restype = C.c_uint64
         lib.vbo_mesh_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.vbo_umap_order.restype = None
+        lib.vbo_umap_order.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         lib.vbo_mc_tables.restype = C.c_int
         lib.vbo_mc_tables.argtypes = [C.c_void_p, C.c_void_p]
         self.lib = lib
-        assert lib.vbo_impl_name().decode() == which
+        assert lib.vbo_impl_name().decode() == which.split("_")[0]
+
+
+def umap_order(lib: "OracleLib", hashes: np.ndarray) -> np.ndarray:
+    """Keys 0..n-1 (hash(key) = hashes[key]) in the iteration order of a std::unordered_map filled by operator[]."""
+    h = np.ascontiguousarray(hashes, dtype=np.uint32)
+    out = np.zeros(h.size, dtype=np.uint32)
+    lib.lib.vbo_umap_order(h.ctypes.data, h.size, out.ctypes.data)
+    return out
 
 
 class OracleMap:

@@ -317,4 +317,21 @@ int vbo_mc_tables(int32_t tri[256 * 16], int32_t edges[12 * 2]) {
   return 0;
 }
 
+
+}  // extern "C"
+namespace {
+const uint32_t* g_preset_hashes = nullptr;
+struct PresetHash {
+  size_t operator()(uint32_t key) const { return static_cast<size_t>(g_preset_hashes[key]); }
+};
+}  // namespace
+extern "C" void vbo_umap_order(const uint32_t* hashes, uint64_t n, uint32_t* out) {
+  g_preset_hashes = hashes;
+  std::unordered_map<uint32_t, int, PresetHash> m;  // default-constructed like tsdf_integrator.cc:318-322
+  for (uint64_t i = 0; i < n; ++i) m[static_cast<uint32_t>(i)] = 0;
+  uint64_t p = 0;
+  for (const auto& kv : m) out[p++] = kv.first;
+}
+
+extern "C" {
 }  // extern "C"

@@ -54,14 +54,11 @@ typedef struct vbo_esdf_config {
   float occupied_sphere_radius;
 } vbo_esdf_config;
 
-/* bundle_order for the Merged integrator:
- *   0  reference order: libstdc++ unordered_map iteration order, as
- *      integrateVoxels walks it (tsdf_integrator.cc:434-457)
- *   1  canonical order: bundles ascending by (z, y, x) of their voxel index,
- *      normal bundles before clearing bundles.  Only the restatement offers it
- *      (the reference leaves the cross-ray update order to its thread schedule).
- */
-enum { VBO_ORDER_REFERENCE = 0, VBO_ORDER_CANONICAL = 1 };
+/* bundle_order for the Merged integrator: only the reference's own order exists --
+ * libstdc++ unordered_map iteration order, as integrateVoxels walks it with one thread
+ * (tsdf_integrator.cc:434-457).  (Round 1 also had a "canonical" order; it is gone: the device
+ * reproduces the reference order.) */
+enum { VBO_ORDER_REFERENCE = 0 };
 enum { VBO_SIMPLE = 1, VBO_MERGED = 2, VBO_FAST = 3 }; /* TsdfIntegratorType */
 enum { VBO_LAYER_TSDF = 0, VBO_LAYER_ESDF = 1 };
 
@@ -127,6 +124,12 @@ uint64_t vbo_mesh_get(void* h, const int32_t idx[3], float* vertices, float* nor
 /* MarchingCubes::kTriangleTable / kEdgeIndexPairs (src/mesh/marching_cubes.cc:33-293);
  * returns 0 from the reference library, 1 from the restatement (which holds no second copy). */
 int vbo_mc_tables(int32_t tri[256 * 16], int32_t edges[12 * 2]);
+
+/* Iteration order of a std::unordered_map<key, ...> with hash(key) = hashes[i] (as size_t) after
+ * inserting keys 0..n-1 one by one with operator[], exactly as bundleRays fills voxel_map
+ * (tsdf_integrator.cc:340-371): out[p] = the key at iteration position p.  Checks the device's
+ * k_bundle_order against the C++ library itself. */
+void vbo_umap_order(const uint32_t* hashes, uint64_t n, uint32_t* out);
 
 #ifdef __cplusplus
 }

@@ -502,8 +502,7 @@ struct Map {
     }
   }
 
-  void integrateMerged(const Pose& T, const float* xyz, const uint8_t* rgba, size_t n, bool freespace,
-                       int bundle_order) {
+  void integrateMerged(const Pose& T, const float* xyz, const uint8_t* rgba, size_t n, bool freespace) {
     BundleMap voxel_map, clear_map;
     for (size_t idx : pointOrder(xyz, n)) {  // bundleRays, cc:340-371
       const V3 p{xyz[3 * idx], xyz[3 * idx + 1], xyz[3 * idx + 2]};
@@ -515,20 +514,8 @@ struct Map {
     }
     for (int pass = 0; pass < 2; ++pass) {  // integrateRays(false) then (true), cc:323-335
       const BundleMap& m = pass ? clear_map : voxel_map;
-      if (bundle_order == VBO_ORDER_CANONICAL) {
-        std::vector<const BundleMap::value_type*> v;
-        v.reserve(m.size());
-        for (const auto& kv : m) v.push_back(&kv);
-        std::sort(v.begin(), v.end(), [](const BundleMap::value_type* a, const BundleMap::value_type* b) {
-          if (a->first.z != b->first.z) return a->first.z < b->first.z;
-          if (a->first.y != b->first.y) return a->first.y < b->first.y;
-          return a->first.x < b->first.x;
-        });
-        for (const auto* kv : v) castBundle(T, xyz, rgba, pass == 1, kv->first, kv->second, voxel_map);
-      } else {
-        // one thread visits every map entry in iteration order (cc:434-457 with threads == 1)
-        for (const auto& kv : m) castBundle(T, xyz, rgba, pass == 1, kv.first, kv.second, voxel_map);
-      }
+      // one thread visits every map entry in iteration order (cc:434-457 with threads == 1)
+      for (const auto& kv : m) castBundle(T, xyz, rgba, pass == 1, kv.first, kv.second, voxel_map);
       commitTemp();  // cc:482-485
     }
   }
@@ -1060,7 +1047,8 @@ int vbo_integrate(void* hv, int kind, const float q[4], const float t[3], const 
   if (kind == VBO_SIMPLE) {
     m->integrateSimple(T, xyz, rgba, n, freespace != 0);
   } else if (kind == VBO_MERGED) {
-    m->integrateMerged(T, xyz, rgba, n, freespace != 0, bundle_order);
+    if (bundle_order != VBO_ORDER_REFERENCE) return 3;  // one order: the reference's
+    m->integrateMerged(T, xyz, rgba, n, freespace != 0);
   } else {
     m->integrateFast(T, xyz, rgba, n, freespace != 0);
   }
@@ -1273,4 +1261,21 @@ uint64_t vbo_mesh_get(void* hv, const int32_t idx[3], float* vertices, float* no
 }
 int vbo_mc_tables(int32_t*, int32_t*) { return 1; }  // the restatement owns no second copy of the table
 
+
+}  // extern "C"
+namespace {
+const uint32_t* g_preset_hashes = nullptr;
+struct PresetHash {
+  size_t operator()(uint32_t key) const { return static_cast<size_t>(g_preset_hashes[key]); }
+};
+}  // namespace
+extern "C" void vbo_umap_order(const uint32_t* hashes, uint64_t n, uint32_t* out) {
+  g_preset_hashes = hashes;
+  std::unordered_map<uint32_t, int, PresetHash> m;  // default-constructed like tsdf_integrator.cc:318-322
+  for (uint64_t i = 0; i < n; ++i) m[static_cast<uint32_t>(i)] = 0;
+  uint64_t p = 0;
+  for (const auto& kv : m) out[p++] = kv.first;
+}
+
+extern "C" {
 }  // extern "C"

@@ -9,7 +9,7 @@ from voxblox_b200 import scenes
 scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
 tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
 for s in scans:
-    integ.integratePointCloud((s[2], s[3]), s[0], s[1]); omap.integrate(2, s, order=po.ORDER_CANONICAL)
+    integ.integratePointCloud((s[2], s[3]), s[0], s[1]); omap.integrate(2, s, order=po.ORDER_REFERENCE)
 eint.updateFromTsdfLayerBatch(); omap.esdf_update(batch=True)
 rep = compare_esdf(esdf, omap, 4.0)
 for k, v in rep.items(): print(k, v)

@@ -44,6 +44,26 @@ def compare_tsdf(layer, omap, dist_floor: float = None) -> Dict:
     return rep
 
 
+def compare_oracles(a, b) -> Dict:
+    """Two oracle maps (e.g. the reference at 4 threads against the reference at 1 thread)."""
+    ai, bi = a.block_indices(), b.block_indices()
+    rep = {"blocks_equal": ai.shape == bi.shape and bool((ai == bi).all())}
+    if not rep["blocks_equal"]:
+        return rep
+    av = np.stack([a.block(i)[0] for i in ai])
+    bv = np.stack([b.block(i)[0] for i in bi])
+    obs = bv["weight"] > 0
+    de = rel_err(av["distance"], bv["distance"], 1e-3 * b.voxel_size)
+    we = rel_err(av["weight"], bv["weight"], 1e-12)
+    rep.update({"voxels_observed": int(obs.sum()),
+                "frac_over_1e-4": float(((de > 1e-4) | (we > 1e-4))[obs].mean()) if obs.any() else 0.0,
+                "max_abs_dist_diff": float(np.abs(av["distance"].astype(np.float64) - bv["distance"]).max()),
+                "color_mismatch_frac": float((av["color"] != bv["color"]).any(axis=-1)[obs].mean()) if obs.any() else 0.0,
+                "n_bit_exact": int(((av["distance"] == bv["distance"]) & (av["weight"] == bv["weight"])).sum()),
+                "n_voxels": int(av.size)})
+    return rep
+
+
 def compare_esdf(layer, omap, max_distance: float) -> Dict:
     """GPU ESDF Layer against the oracle's ESDF layer (layer id 1)."""
     gi = layer.getAllAllocatedBlocks()

@@ -128,7 +128,7 @@ def test_serialized_blocks_match_reference_format():
     omap.esdf_create(po.EsdfConfig(**ekw))
     for s in scenes.c3_room_sequence(n_scans=2, width=96, height=72):
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
     eint.updateFromTsdfLayer(False)
     # TSDF: the device map is bit-identical to the oracle's, so the words must be too
     idx, words, upd = layer.serializeUpdated(0, 0)

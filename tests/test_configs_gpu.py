@@ -35,7 +35,7 @@ def test_c2_merged_sphere_room_full_size(trunc):
         s = scenes.c2_sphere_scan(i)
         assert s[0].shape[0] == 640 * 480
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
         gc, oc = integ.counters(), omap.counters()
         for k in ("rays", "clear_rays", "updates", "voxels_touched", "blocks_touched", "blocks_allocated"):
             assert gc[k] == oc[k], (k, gc, oc)
@@ -76,7 +76,7 @@ def test_c4_merged_plus_esdf_every_scan_full_size():
     for i in range(2):
         s = scenes.c3_room_scan(i)
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
         eint.updateFromTsdfLayer(True)
         omap.esdf_update(batch=False, clear_updated_flag=True)
     _exact(compare_tsdf(layer, omap))
@@ -96,7 +96,7 @@ def test_c5_merged_lidar_full_size():
         s = scenes.c5_lidar_scan(i)
         assert s[0].shape[0] == 2048 * 128
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
         gc, oc = integ.counters(), omap.counters()
         for k in ("rays", "clear_rays", "updates", "voxels_touched", "blocks_touched", "blocks_allocated"):
             assert gc[k] == oc[k], (k, gc, oc)

@@ -30,7 +30,7 @@ def test_esdf_batch_matches_oracle():
     tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
     for s in scans:
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
     assert compare_tsdf(tsdf, omap)["max_rel_err"] == 0.0
     eint.updateFromTsdfLayerBatch()
     omap.esdf_update(batch=True)
@@ -62,7 +62,7 @@ def test_esdf_batch_exact_without_sign_conflicts():
     tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
     for s in _wall_scans():
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
     eint.updateFromTsdfLayerBatch()
     omap.esdf_update(batch=True)
     rep = compare_esdf(esdf, omap, 4.0)
@@ -76,7 +76,7 @@ def test_esdf_incremental_tracks_oracle():
     tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
     for s in scans:
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
         eint.updateFromTsdfLayer(True)
         omap.esdf_update(batch=False, clear_updated_flag=True)
         rep = compare_esdf(esdf, omap, 4.0)
@@ -96,7 +96,7 @@ def test_update_from_tsdf_blocks_and_setters():
     tsdf, integ, esdf, eint, omap = _setup(0.1, 0.4, EKW)
     for s in _wall_scans():
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
     blocks = tsdf.getAllAllocatedBlocks()
     subset = np.concatenate([blocks[::2], blocks[:1], np.array([[900, 900, 900]], np.int32)])
     eint.updateFromTsdfBlocks(subset)
@@ -156,7 +156,7 @@ def test_add_new_robot_position_matches_oracle():
             eint.addNewRobotPosition(s[3])
             omap.esdf_add_robot_position(s[3])
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
         assert compare_tsdf(tsdf, omap)["max_rel_err"] == 0.0
         eint.updateFromTsdfLayer(True)
         omap.esdf_update(batch=False, clear_updated_flag=True)

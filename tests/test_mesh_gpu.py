@@ -55,7 +55,7 @@ def test_incremental_mesh_matches_oracle(use_color):
     mesher = vb.MeshIntegrator(vb.MeshIntegratorConfig(use_color=use_color), layer, mesh_layer)
     for s in scans:
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
         mesher.generateMesh(True, True)
         omap.mesh_generate(use_color, 1e-4, True, True)
         assert len(layer.getAllUpdatedBlocks(1)) == 0   # kMesh bits cleared
@@ -76,7 +76,7 @@ def test_full_mesh_small_blocks_and_second_call_is_empty():
     mesher = vb.MeshIntegrator(vb.MeshIntegratorConfig(min_weight=0.5), layer, mesh_layer)
     for s in scans:
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
     mesher.generateMesh(False, False)
     omap.mesh_generate(True, 0.5, False, False)
     rep = _compare(mesh_layer, omap)

@@ -1,30 +1,35 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: ray-slot partition, count exchange,
-prefix-of-pack all-gather and the global record order the device back half relies on."""
+"""Host-side logic of the block-ownership sharding (voxblox_b200/sharded.py) on CPU: the ownership
+function, and the variable-size block all-gather under gloo with world_size 2."""
 import os
 import socket
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from voxblox_b200 import sharded
+from voxblox_b200.api import TSDF_DTYPE
 
 
-def test_slot_ranges_partition_the_scan():
-    for n in (0, 1, 7, 1024, 261119, 307200):
-        for world in (1, 2, 3, 4, 8):
-            r = [sharded.slot_range(n, k, world) for k in range(world)]
-            assert r[0][0] == 0 and r[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
-            assert all(hi - lo <= (n + world - 1) // world for lo, hi in r)
-
-
-def test_exchange_size_and_prefix():
-    assert sharded.exchange_bytes(512, [0, 0]) == 512
-    assert sharded.exchange_bytes(512, [1, 4097]) == 512 + 16 * 8192
-    assert sharded.record_prefix([3, 0, 5]) == [0, 3, 3, 8]
+def test_block_owner_partitions_space():
+    rng = np.random.default_rng(0)
+    idx = rng.integers(-50, 50, size=(5000, 3)).astype(np.int32)
+    for world in (1, 2, 3, 4, 8):
+        o = sharded.block_owner(idx, world)
+        assert o.min() >= 0 and o.max() < world
+        # every rank owns a fair share, and face neighbours along x never share an owner (world > 1)
+        counts = np.bincount(o, minlength=world)
+        assert counts.min() > 0.5 * len(idx) / world
+        if world > 1:
+            nb = idx.copy()
+            nb[:, 0] += 1
+            assert (sharded.block_owner(nb, world) != o).all()
+    # the 2 x 2 x 2 brick of 8 ranks: the eight blocks around a corner all have different owners
+    corner = np.array([[x, y, z] for z in (-1, 0) for y in (-1, 0) for x in (-1, 0)], np.int32)
+    assert sorted(sharded.block_owner(corner, 8).tolist()) == list(range(8))
+    # negative coordinates: non-negative modulo like the device's block_owner()
+    assert sharded.block_owner([[-1, 0, 0]], 8)[0] == 7 and sharded.block_owner([[0, 0, -1]], 8)[0] == 4
 
 
 def _free_port():
@@ -33,45 +38,39 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _blocks_of(rank):
+    rng = np.random.default_rng(100 + rank)
+    m = 3 + 4 * rank  # ranks hold different numbers of blocks
+    idx = rng.integers(-9, 9, size=(m, 3)).astype(np.int32)
+    vox = np.zeros((m, 8), dtype=TSDF_DTYPE)
+    vox["distance"] = rng.normal(size=(m, 8)).astype(np.float32)
+    vox["weight"] = rank + 1
+    vox["color"] = rng.integers(0, 255, size=(m, 8, 4))
+    return idx, vox
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n = 1000
-        lo, hi = sharded.slot_range(n, rank, world)
-        rng = np.random.default_rng(rank)
-        count = 5000 + 3000 * rank  # ranks hold different numbers of records
-        off_records = 256
-        cap = 16384
-        pack = torch.zeros(off_records + cap * 16, dtype=torch.uint8)
-        rec = np.zeros((count, 4), dtype=np.uint32)
-        rec[:, 0] = rng.integers(0, 2 ** 32, count)
-        rec[:, 2] = np.sort(rng.integers(lo, hi, count))  # ray slots of this rank, ascending
-        pack[off_records:off_records + count * 16] = torch.from_numpy(rec.view(np.uint8).reshape(-1))
-        pack[:8] = torch.from_numpy(np.array([rank + 1], dtype=np.int64).view(np.uint8))  # fake ray table
-        counts = sharded.gather_counts(count)
-        assert counts == [5000 + 3000 * r for r in range(world)]
-        nbytes = sharded.exchange_bytes(off_records, counts)
-        gathered = torch.zeros(world * pack.numel(), dtype=torch.uint8)
-        got = sharded.gather_packs(pack, nbytes, gathered).numpy().reshape(world, nbytes)
-        start = sharded.record_prefix(counts)
-        slots = []
+        idx, vox = _blocks_of(rank)
+        all_idx, all_vox, counts = sharded.all_gather_blocks(idx, vox)
+        assert counts.tolist() == [3 + 4 * r for r in range(world)]
+        at = 0
         for r in range(world):
-            assert int(got[r, :8].view(np.int64)[0]) == r + 1
-            rr = got[r, off_records:off_records + counts[r] * 16].view(np.uint32).reshape(-1, 4)
-            slots.append(rr[:, 2])
-            if r == rank:
-                assert (rr == rec).all()
-        allslots = np.concatenate(slots)
-        assert len(allslots) == start[-1]
-        # rank order == ascending ray slots: the order in which the back half applies updates
-        assert (np.diff(allslots.astype(np.int64)) >= 0).all()
+            ri, rv = _blocks_of(r)
+            assert (all_idx[at:at + len(ri)] == ri).all()
+            assert all_vox[at:at + len(ri)].tobytes() == rv.tobytes()
+            at += len(ri)
+        # a rank with nothing to send
+        e_idx, e_vox, e_counts = sharded.all_gather_blocks(idx[:0] if rank == 0 else idx, vox[:0] if rank == 0 else vox)
+        assert e_counts[0] == 0 and len(e_idx) == sum(e_counts)
         out[rank] = 1
     finally:
         dist.destroy_process_group()
 
 
-def test_exchange_plumbing_world2_gloo():
+def test_block_all_gather_world2_gloo():
     world = 2
     ctx = mp.get_context("spawn")
     out = ctx.Array("i", world)

@@ -42,12 +42,12 @@ def test_c1_simple_planar_wall():
 
 
 def test_c1_merged_planar_wall():
-    rep = _run(2, [scenes.c1_planar_wall()], 0.2, 0.8, po.ORDER_CANONICAL)
+    rep = _run(2, [scenes.c1_planar_wall()], 0.2, 0.8, po.ORDER_REFERENCE)
     print(rep)
     _assert_parity(rep)
 
 
-@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_CANONICAL)])
+@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_REFERENCE)])
 def test_room_sequence_small(kind, order):
     scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
     rep = _run(kind, scans, 0.1, 0.4, order)
@@ -60,7 +60,7 @@ def _small_scans(n=2, w=96, h=72):
     return scenes.c3_room_sequence(n_scans=n, width=w, height=h)
 
 
-@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_CANONICAL)])
+@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_REFERENCE)])
 @pytest.mark.parametrize("cfg_kw", [
     dict(use_const_weight=1),
     dict(voxel_carving_enabled=0),
@@ -82,12 +82,12 @@ def test_config_variants(kind, order, cfg_kw):
 
 
 def test_merged_anti_grazing():
-    rep = _run(2, _small_scans(), 0.1, 0.4, po.ORDER_CANONICAL, enable_anti_grazing=1)
+    rep = _run(2, _small_scans(), 0.1, 0.4, po.ORDER_REFERENCE, enable_anti_grazing=1)
     print(rep)
     _assert_parity(rep)
 
 
-@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_CANONICAL)])
+@pytest.mark.parametrize("kind,order", [(1, po.ORDER_REFERENCE), (2, po.ORDER_REFERENCE)])
 def test_freespace_points(kind, order):
     """freespace_points=true: every ray is a clearing ray (tsdf_integrator.h:96-99)."""
     cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
@@ -102,21 +102,22 @@ def test_freespace_points(kind, order):
     _assert_parity(rep)
 
 
-def test_far_clearing_points_use_wide_keys():
-    """Points far beyond max_ray_length fall outside the compact bundle-key range: the call is
-    redone with full-width keys and must still match."""
+def test_far_clearing_points():
+    """Points far beyond max_ray_length become clearing bundles keyed by voxels thousands of voxels
+    away: the bundle keys are packed relative to the scan's own bounding box, so they simply use
+    more key bits."""
     s = _small_scans(1)[0]
     pts = s[0].copy()
     pts[::7] *= 40.0      # ~100 m away: clearing rays whose end voxels are thousands of voxels off
     scan = (pts, s[1], s[2], s[3])
-    rep = _run(2, [scan], 0.1, 0.4, po.ORDER_CANONICAL)
+    rep = _run(2, [scan], 0.1, 0.4, po.ORDER_REFERENCE)
     print(rep)
     _assert_parity(rep)
 
 
 @pytest.mark.parametrize("kind,order,cfg_kw", [
-    (1, po.ORDER_REFERENCE, {}), (2, po.ORDER_CANONICAL, {}),
-    (2, po.ORDER_CANONICAL, dict(enable_anti_grazing=1)), (1, po.ORDER_REFERENCE, dict(integration_order_mode=1))])
+    (1, po.ORDER_REFERENCE, {}), (2, po.ORDER_REFERENCE, {}),
+    (2, po.ORDER_REFERENCE, dict(enable_anti_grazing=1)), (1, po.ORDER_REFERENCE, dict(integration_order_mode=1))])
 def test_more_updates_than_one_pass_holds(kind, order, cfg_kw):
     """K > max_updates_per_pass: the call is applied in passes over contiguous ray ranges and
     must equal the one-pass result (= the oracle) bit for bit; a single ray that does not fit is
@@ -177,7 +178,7 @@ def test_voxels_per_side_8():
     omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 8)
     for s in _small_scans():
         integ.integratePointCloud((s[2], s[3]), s[0], s[1])
-        omap.integrate(2, s, order=po.ORDER_CANONICAL)
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
     gi, oi = layer.getAllAllocatedBlocks(), omap.block_indices()
     assert gi.shape == oi.shape and (gi == oi).all()
     gv, _ = layer.getBlocks(gi)
@@ -246,10 +247,9 @@ def test_async_submission_equals_synchronous(kind, pageable):
     assert _layer_bytes(la) == _layer_bytes(ls)
 
 
-def test_async_far_points_are_reported_not_silently_dropped():
-    """A scan whose clearing points overflow the compact bundle keys cannot be redone once later
-    scans are queued behind it: the error surfaces at the next synchronising call, and later
-    submissions switch to full-width keys."""
+def test_async_far_points_are_integrated():
+    """Round 1 dropped an asynchronously submitted scan whose clearing points overflowed the compact
+    bundle keys.  Keys are now packed relative to the scan's bounding box: nothing overflows."""
     cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
     layer = vb.Layer(0.1, 16)
     integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
@@ -257,15 +257,66 @@ def test_async_far_points_are_reported_not_silently_dropped():
     pts = s[0].copy()
     pts[::7] *= 40.0
     integ.integratePointCloudAsync((s[2], s[3]), pts, s[1])
-    with pytest.raises(vb.VoxbloxError):
-        layer.sync()
-    assert layer.getNumberOfAllocatedBlocks() == 0
-    integ.integratePointCloudAsync((s[2], s[3]), pts, s[1])   # now with full-width keys
+    integ.integratePointCloudAsync((s[2], s[3]), pts, s[1])
     layer.sync()
     ref = vb.Layer(0.1, 16)
     r = vb.TsdfIntegratorFactory.create("merged", cfg, ref)
     r.integratePointCloud((s[2], s[3]), pts, s[1])
+    r.integratePointCloud((s[2], s[3]), pts, s[1])
     assert _layer_bytes(layer) == _layer_bytes(ref)
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_async_scan_with_more_updates_than_one_pass_is_redone_not_dropped(kind):
+    """An asynchronously submitted scan whose update records exceed max_updates_per_pass cannot be
+    chunked on the device.  It raises the hold flag; the scans queued behind it skip their back
+    halves; the host then redoes all of them synchronously (in passes), in submission order.  The map
+    must equal the all-synchronous map and no error may surface."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    small = lambda: vb.EngineOptions(max_updates_per_pass=6000 if kind == 2 else 100000)
+    la, ls = vb.Layer(0.1, 16, engine_options=small()), vb.Layer(0.1, 16, engine_options=small())
+    ia, isync = vb.TsdfIntegratorFactory.create(kind, cfg, la), vb.TsdfIntegratorFactory.create(kind, cfg, ls)
+    scans = scenes.c3_room_sequence(n_scans=9, width=96, height=72)
+    keep = []
+    for s in scans:   # more scans than hand-off sets: the recovery also runs when a set is reused
+        isync.integratePointCloud((s[2], s[3]), s[0], s[1])
+        p, c = np.ascontiguousarray(s[0]), np.ascontiguousarray(s[1])
+        keep.append((p, c))
+        ia.integratePointCloudAsync((s[2], s[3]), p, c)
+    la.sync()
+    assert isync.counters()["passes"] > 1
+    assert ia.counters()["async_redone_total"] >= len(scans) - 1
+    assert _layer_bytes(la) == _layer_bytes(ls)
+
+
+def test_pool_overflow_is_reported_and_does_not_poison_later_calls():
+    """a call that runs out of pool slots left hash entries without a slot behind; a later
+    call found them and wrote out of bounds.  Now the failing call reports VBX_E_CAPACITY, the hash
+    is rebuilt from the slots that exist, and the map keeps working (here: after blocks are removed)."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16, engine_options=vb.EngineOptions(max_blocks=8))
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    s = _small_scans(1)[0]
+    with pytest.raises(vb.VoxbloxError):
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    assert layer.getNumberOfAllocatedBlocks() <= 8
+    with pytest.raises(vb.VoxbloxError):   # still full: fails again, cleanly
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+    vox, _ = layer.getBlocks(layer.getAllAllocatedBlocks())
+    assert np.isfinite(vox["distance"]).all()
+    # asynchronous submissions behind a failing scan must not write through slot-less entries either
+    for _ in range(4):
+        integ.integratePointCloudAsync((s[2], s[3]), np.ascontiguousarray(s[0]), np.ascontiguousarray(s[1]))
+    with pytest.raises(vb.VoxbloxError):
+        layer.sync()
+    layer.removeAllBlocks()
+    assert layer.getNumberOfAllocatedBlocks() == 0
+    few = (s[0][:1], s[1][:1], s[2], s[3])    # one ray: a handful of blocks fits
+    integ.integratePointCloud((few[2], few[3]), few[0], few[1])
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, 16)
+    omap.integrate(2, few)
+    rep = compare_tsdf(layer, omap)
+    assert rep["blocks_equal"] and rep["n_bit_exact"] == rep["n_voxels"], rep
 
 
 def test_async_falls_back_for_map_dependent_front_halves():

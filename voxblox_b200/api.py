@@ -120,8 +120,8 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_upload_blocks", "vbx_remove_blocks", "vbx_clear", "vbx_clear_updated",
            "vbx_esdf_create", "vbx_esdf_update", "vbx_esdf_get_counters", "vbx_sync",
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
-           "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_shard_layout_for", "vbx_shard_front",
-           "vbx_shard_back", "vbx_debug_sort", "vbx_debug_scan", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
+           "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_block_owner",
+           "vbx_debug_sort", "vbx_debug_scan", "vbx_debug_bundle_order", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
            "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_esdf_add_robot_position", "vbx_esdf_clear", "vbx_mesh_generate", "vbx_mesh_download", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
            "vbx_proto_encode_layer", "vbx_proto_encode_block", "vbx_proto_decode_block"]
 
@@ -212,6 +212,8 @@ def load_library():
     lib.vbx_mesh_download.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.vbx_sync.restype = i32
     lib.vbx_sync.argtypes = [vp]
+    lib.vbx_block_owner.restype = i32
+    lib.vbx_block_owner.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     lib.vbx_host_alloc.restype = i32
     lib.vbx_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.vbx_host_free.restype = i32
@@ -457,7 +459,7 @@ class Layer:
         ctx.check(ctx.lib.vbx_set_stage_profiling(ctx.handle, int(enabled)), "vbx_set_stage_profiling")
 
     STAGE_NAMES = ("point_keys", "point_sort", "ray_count", "scan", "assign", "ray_emit",
-                   "update_sort", "apply", "bundle_merge", "esdf_propagate", "esdf_raise", "esdf_lower")
+                   "update_sort", "apply", "bundle_merge", "esdf_propagate", "esdf_raise", "esdf_lower", "bundle_order")
 
     def stageMs(self):
         ctx = self._bound()
@@ -579,7 +581,7 @@ class TsdfIntegratorBase:
                         "vbx_get_counters")
         names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
                  "blocks_allocated", "valid_points", "kernel_launches", "kernel_launches_total", "refolded_bundles",
-                 "refolded_points", "passes"]
+                 "refolded_points", "passes", "bundle_key_bits", "async_redone_total"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def lastDeviceMs(self) -> float:

@@ -62,6 +62,19 @@ __global__ void k_rebuild_hash(Tables tab, uint32_t n_blocks) {
 
 static inline unsigned int grid_for(uint64_t n, int block) { return (unsigned int)((n + block - 1) / block); }
 
+// The block hash rebuilt from slot_key: after removals, and after a call that ran out of pool slots
+// (its surplus hash entries have no slot and must not be found by later calls).
+int rebuild_hash(vbx_ctx* c) {
+  cudaStream_t s = c->stream;
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.hkeys, 0xff, (size_t)c->hcap * sizeof(uint64_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.hslot, 0xff, (size_t)c->hcap * sizeof(int32_t), s));
+  VBX_CUDA(c, cudaMemsetAsync(c->tab.htouch_epoch, 0, (size_t)c->hcap * sizeof(uint32_t), s));
+  if (c->n_blocks) k_rebuild_hash<<<grid_for(c->n_blocks, 256), 256, 0, s>>>(c->tab, c->n_blocks);
+  VBX_CUDA(c, cudaStreamSynchronize(s));
+  VBX_CUDA(c, cudaGetLastError());
+  return VBX_OK;
+}
+
 // ---- serialised block payloads, voxblox/src/core/block.cc:
 //   TsdfVoxel -> 3 words: distance bits, weight bits, a | b<<8 | g<<16 | r<<24      (cc:159-183, :65-90)
 //   EsdfVoxel -> 2 words: distance bits, parent x,y,z as int8 in bytes 3,2,1 | flag byte
@@ -329,12 +342,7 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
     --n;
   }
   if (int rc = set_n_blocks(c, n)) return rc;
-  VBX_CUDA(c, cudaMemsetAsync(c->tab.hkeys, 0xff, (size_t)c->hcap * sizeof(uint64_t), s));
-  VBX_CUDA(c, cudaMemsetAsync(c->tab.hslot, 0xff, (size_t)c->hcap * sizeof(int32_t), s));
-  VBX_CUDA(c, cudaMemsetAsync(c->tab.htouch_epoch, 0, (size_t)c->hcap * sizeof(uint32_t), s));
-  if (n) k_rebuild_hash<<<grid_for(n, 256), 256, 0, s>>>(c->tab, n);
-  VBX_CUDA(c, cudaStreamSynchronize(s));
-  VBX_CUDA(c, cudaGetLastError());
+  if (int rc = rebuild_hash(c)) return rc;
   c->host_slot_key.clear();
   c->host_key2slot.clear();
   return refresh_host_mirror(c);

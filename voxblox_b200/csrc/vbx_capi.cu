@@ -14,14 +14,10 @@ namespace vbx {
 int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
                      const uint8_t* d_rgba, uint64_t n, int freespace);
 size_t cub_temp_bytes(uint32_t max_points, uint64_t max_updates);
-int shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out);
-int shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz, const uint8_t* d_rgba,
-                uint64_t n, int freespace, const vbx_shard_layout* lay, void* d_pack, uint64_t* count_out);
-int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n, const vbx_shard_layout* lay,
-               const void* d_gathered, uint64_t pack_stride, const uint64_t* counts);
 int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
                uint32_t* vals_out);
 int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out);
+int debug_bundle_order(vbx_ctx* c, const uint32_t* hashes, uint32_t n, int force_global, uint32_t* out);
 int upload_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m, const void* voxels,
                   const uint8_t* updated_bits, int serialized);
 int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m);
@@ -81,12 +77,49 @@ void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S) {
   c->counters[6] = S.kind == VBX_MERGED ? h.n_valid_points : (uint64_t)h.n_rays + h.n_clear_rays;
   c->counters[7] = S.launches;
   c->counters[11] = 1;
-  if (h.error & kNeedWideKeys) c->force_wide_keys = true;  // later submissions use full-width keys
-  if (h.error && !c->deferred_rc) {
+  const uint32_t fatal = h.error & kFatalErrors & ~kErrUpdatesFull;
+  if (!fatal && (h.error & (kErrUpdatesFull | kSkipped))) {
+    // more update records than one pass holds (or queued behind such a scan): nothing was applied;
+    // recover_async redoes it synchronously, in passes, in submission order
+    S.redo = true;
+    return;
+  }
+  if (fatal & kErrPoolFull) c->hash_dirty = true;  // surplus hash entries without a pool slot
+  if (fatal && !c->deferred_rc) {
     c->deferred_rc = VBX_E_CAPACITY;
     c->deferred_msg = "an asynchronously submitted scan failed on the device (error bits " + std::to_string(h.error) +
-                      (h.error & kNeedWideKeys ? ": a point lies outside the compact bundle-key range; that scan was NOT integrated" : "") + ")";
+                      (fatal & kErrPoolFull ? ": block pool full, raise vbx_engine_options.max_blocks" : "") + ")";
   }
+}
+
+// Every queued scan has been waited for.  Scans that could not be applied asynchronously (and the
+// scans queued behind them, which skipped their back halves) are redone synchronously from their
+// retained inputs, in submission order -- no scan is lost and the update order is the callers'.
+static int recover_async(vbx_ctx* c) {
+  if (c->hash_dirty) {
+    c->hash_dirty = false;
+    if (int rc = rebuild_hash(c)) return rc;
+  }
+  std::vector<vbx_ctx::ScratchSet*> todo;
+  for (int k = 0; k < vbx_ctx::kSets; ++k) {
+    if (c->set[k].redo) todo.push_back(&c->set[k]);
+  }
+  if (todo.empty()) return VBX_OK;
+  std::sort(todo.begin(), todo.end(), [](const vbx_ctx::ScratchSet* a, const vbx_ctx::ScratchSet* b) { return a->seq < b->seq; });
+  VBX_CUDA(c, cudaMemsetAsync(c->d_hold, 0, sizeof(uint32_t), c->stream_main));
+  int first_rc = VBX_OK;
+  std::string first_msg;
+  for (vbx_ctx::ScratchSet* S : todo) {
+    S->redo = false;
+    const int rc = integrate_device(c, S->kind, S->q, S->t, S->in_xyz, S->in_rgba, S->n, S->freespace);
+    c->async_redone += 1;
+    if (rc != VBX_OK && first_rc == VBX_OK) {
+      first_rc = rc;
+      first_msg = c->err;
+    }
+  }
+  if (first_rc != VBX_OK) c->err = first_msg;
+  return first_rc;
 }
 
 void select_set(vbx_ctx* c, int k) {
@@ -112,6 +145,9 @@ void select_set(vbx_ctx* c, int k) {
 
 void select_lane(vbx_ctx* c, int l) {
   const vbx_ctx::FrontLane& F = c->lane[l];
+  c->head_list = F.head_list;
+  c->first_bits = F.first_bits;
+  c->order_scratch = F.order_scratch;
   c->pkeys[1] = F.pkeys1;
   c->pvals[0] = F.pvals[0];
   c->pvals[1] = F.pvals[1];
@@ -133,6 +169,9 @@ int drain_async(vbx_ctx* c) {
   c->stream = c->stream_main;
   c->apply_stream = nullptr;
   c->sort_stream = nullptr;
+  if (int rc = recover_async(c)) {
+    if (!c->deferred_rc) return rc;
+  }
   if (c->deferred_rc) {
     const int rc = c->deferred_rc;
     c->err = c->deferred_msg;
@@ -145,6 +184,36 @@ int drain_async(vbx_ctx* c) {
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+// k_bundle_order's tables for one front lane (vbx_order.cuh)
+int alloc_order_scratch(vbx_ctx* c, OrderScratch* g, uint32_t** head_list, uint32_t** first_bits) {
+  const size_t np = c->max_points;
+  std::memset(g, 0, sizeof(*g));
+  g->cap = (uint32_t)np;
+  // the bucket count after np insertions
+  uint32_t buckets = 1;
+  for (int k = 0; k < c->rehash.count && c->rehash.m[k] < np; ++k) buckets = c->rehash.n[k];
+  g->bucket_cap = buckets;
+  VBX_CUDA(c, dmalloc(&g->h, np));
+  VBX_CUDA(c, dmalloc(&g->tau, np));
+  VBX_CUDA(c, dmalloc(&g->tau2, np));
+  VBX_CUDA(c, dmalloc(&g->next, np));
+  VBX_CUDA(c, dmalloc(&g->A, np));
+  VBX_CUDA(c, dmalloc(&g->bhead, (size_t)buckets));
+  VBX_CUDA(c, dmalloc(&g->head_of, np));
+  VBX_CUDA(c, dmalloc(&g->wp, np / 32 + 2));
+  VBX_CUDA(c, dmalloc(head_list, np));
+  VBX_CUDA(c, dmalloc(first_bits, 2 * (np / 32 + 2)));
+  VBX_CUDA(c, cudaMemsetAsync(*first_bits, 0, 2 * (np / 32 + 2) * sizeof(uint32_t), c->stream_main));
+  return VBX_OK;
+}
+void free_order_scratch(OrderScratch* g, uint32_t* head_list, uint32_t* first_bits) {
+  void* ptrs[] = {g->h, g->tau, g->tau2, g->next, g->A, g->bhead, g->head_of, g->wp, head_list, first_bits};
+  for (void* p : ptrs) {
+    if (p) cudaFree(p);
+  }
+  std::memset(g, 0, sizeof(*g));
 }
 
 }  // namespace vbx
@@ -203,7 +272,12 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   c->max_updates = std::min<uint64_t>(o.max_updates_per_pass, 0x7fffffffull);
   int rb = 0;
   for (uint32_t v = o.max_blocks; v; v >>= 1) ++rb;
-  if (rb + 1 + 3 * c->L > 32) {  // an update record's key = (hash position, voxel in block) in 32 bits
+  // an update record's key = (hash position, voxel in block) in 32 bits, 0xffffffff reserved
+  if (rb + 1 + 3 * c->L > 32 || (rb + 1 + 3 * c->L == 32 && (o.max_blocks & (o.max_blocks - 1)))) {
+    delete c;
+    return VBX_E_INVALID;
+  }
+  if (o.world_size > 1 && (o.rank < 0 || o.rank >= o.world_size)) {
     delete c;
     return VBX_E_INVALID;
   }
@@ -265,7 +339,10 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     CK(dmalloc(&c->cvals[i], (size_t)c->max_updates));
   }
   CK(dmalloc(&c->order, np));
+  CK(dmalloc(&c->order_inv, np));
   CK(dmalloc(&c->ray_list, np));
+  if (int rc = init_bundle_order(c)) return rc;
+  if (int rc = alloc_order_scratch(c, &c->order_scratch, &c->head_list, &c->first_bits)) return rc;
   CK(dmalloc(&c->long_list, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->long_end, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->long_state, (size_t)(c->max_updates / 32 + 1)));
@@ -302,6 +379,8 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_state), sizeof(ScanState)));
   CK(dmalloc(&c->d_nblocks, 2));
   CK(cudaMemsetAsync(c->d_nblocks, 0, 2 * sizeof(uint32_t), c->stream));
+  CK(dmalloc(&c->d_hold, 1));
+  CK(cudaMemsetAsync(c->d_hold, 0, sizeof(uint32_t), c->stream));
   {
     // hand-off set 0 / front lane 0 are the buffers above; the others are allocated by ensure_async
     vbx_ctx::ScratchSet& a = c->set[0];
@@ -329,6 +408,9 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     f.sort_plan0 = c->sort_plan[0];
     f.sort_status0 = c->sort_status[0];
     f.scan_status = c->scan_status;
+    f.head_list = c->head_list;
+    f.first_bits = c->first_bits;
+    f.order_scratch = c->order_scratch;
   }
   CK(cudaStreamSynchronize(c->stream));
 #undef CK
@@ -361,6 +443,7 @@ int ensure_async(vbx_ctx* c) {
     CK(dmalloc(&F.sort_plan0, 1));
     CK(dmalloc(&F.sort_status0, (size_t)8 * c->sort_tiles_cap[0] * kRadix));
     CK(dmalloc(&F.scan_status, (np + 1) / kScanTile + 4));
+    if (int rc = alloc_order_scratch(c, &F.order_scratch, &F.head_list, &F.first_bits)) return rc;
   }
   for (int k = 0; k < vbx_ctx::kSets; ++k) {
     vbx_ctx::ScratchSet& S = c->set[k];
@@ -422,7 +505,7 @@ void vbx_destroy(vbx_ctx* c) {
                   c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
                   c->ray_list,    c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
                   c->sort_status[0], c->sort_status[1], c->scan_status, c->long_end, c->long_state,
-                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w, c->d_nblocks};
+                  c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w, c->d_nblocks, c->order_inv, c->d_hold};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }
@@ -454,6 +537,7 @@ void vbx_destroy(vbx_ctx* c) {
         if (p) cudaFree(p);
       }
     }
+    free_order_scratch(&F.order_scratch, F.head_list, F.first_bits);
     if (F.stream) cudaStreamDestroy(F.stream);
   }
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -506,28 +590,10 @@ int vbx_tsdf_integrate_async(vbx_ctx* c, int kind, const float q[4], const float
   return integrate_async(c, kind, q, t, xyz, rgba, n, freespace, inputs_on_device);
 }
 
-int vbx_shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out) {
-  if (!c || !out) return VBX_E_INVALID;
-  return shard_layout_for(c, n, record_capacity, out);
-}
-
-int vbx_shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
-                    const uint8_t* d_rgba, uint64_t n, int freespace, const vbx_shard_layout* lay, void* d_pack,
-                    uint64_t* count_out) {
-  if (!c || !q || !t || !lay || !d_pack || !count_out || (n && (!d_xyz || !d_rgba))) {
-    return fail(c, VBX_E_INVALID, "null argument");
-  }
-  VBX_CUDA(c, cudaSetDevice(c->device));
-  VBX_DRAIN(c);
-  return shard_front(c, kind, q, t, d_xyz, d_rgba, n, freespace, lay, d_pack, count_out);
-}
-
-int vbx_shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n, const vbx_shard_layout* lay,
-                   const void* d_gathered, uint64_t pack_stride, const uint64_t* counts) {
-  if (!c || !q || !t || !lay || !d_gathered || !counts) return fail(c, VBX_E_INVALID, "null argument");
-  VBX_CUDA(c, cudaSetDevice(c->device));
-  VBX_DRAIN(c);
-  return shard_back(c, kind, q, t, n, lay, d_gathered, pack_stride, counts);
+int vbx_block_owner(const vbx_ctx* c, const int32_t block_index[3], int32_t* owner) {
+  if (!c || !block_index || !owner) return VBX_E_INVALID;
+  *owner = c->opt.world_size > 1 ? block_owner(block_index[0], block_index[1], block_index[2], c->opt.world_size) : 0;
+  return VBX_OK;
 }
 
 int vbx_debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
@@ -545,10 +611,18 @@ int vbx_debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {
   return debug_scan(c, in, n, out);
 }
 
+int vbx_debug_bundle_order(vbx_ctx* c, const uint32_t* hashes, uint32_t n, int force_global, uint32_t* out) {
+  if (!c || (n && (!hashes || !out))) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  return debug_bundle_order(c, hashes, n, force_global, out);
+}
+
 int vbx_get_counters(const vbx_ctx* c, uint64_t out[16]) {
   if (!c || !out) return VBX_E_INVALID;
   std::memcpy(out, c->counters, sizeof(c->counters));
   out[8] = c->launches;  // kernels launched by TSDF integration since vbx_create
+  out[13] = c->async_redone;  // asynchronously submitted scans that were redone synchronously (see vbx_tsdf_integrate_async)
   return VBX_OK;
 }
 

@@ -11,6 +11,7 @@
 
 #include "../../include/voxblox_b200.h"
 #include "vbx_math.cuh"
+#include "vbx_order.cuh"
 
 namespace vbx {
 struct SortPlan;
@@ -43,7 +44,7 @@ enum : uint32_t {
   kErrCoordRange = 4u,      // |voxel coordinate| >= 2^20 * vps
   kErrUpdatesFull = 8u,     // ray-voxel updates exceed max_updates_per_pass
   kFatalErrors = 15u,       // any of the above
-  kNeedWideKeys = 16u,      // not an error: a clearing point fell outside the compact bundle-key range
+  kSkipped = 32u,           // not an error: the scan was queued behind a scan that must be redone (vbx_capi.cu)
 };
 
 // Device-resident per-call state; the host reads it back through pinned memory.
@@ -71,8 +72,15 @@ struct ScanState {
   uint32_t n_refold;         // bundles folded a second time with IEEE division (diagnostic)
   uint32_t refold_members;   // ... and the points they hold
   uint32_t frontier_n2;      // third wavefront counter
+  // Merged: bounding box of the valid points' voxels, both ends atomicMax'ed (so that an all-zero
+  // block means "no valid point"): kb_max = v + 2^30, kb_min = 0xffffffff - (v + 2^30); the bundle
+  // keys are packed relative to it (vbx_tsdf.cu, KeyLayout)
+  uint32_t kb_max[3];
+  uint32_t kb_min[3];
+  uint32_t key_bits;         // bits a bundle key uses
+  uint32_t reserved[9];
 };
-static_assert(sizeof(ScanState) == 128, "the status block the host reads back is 128 bytes");
+static_assert(sizeof(ScanState) == 192, "the status block the host reads back is 192 bytes");
 
 // The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
 // core/layer.h:30-32,292).
@@ -101,6 +109,11 @@ __host__ __device__ inline void unpack3(uint64_t k, int* x, int* y, int* z) {
   *x = (int)(k & 0x1fffffu) - kCoordBias;
   *y = (int)((k >> 21) & 0x1fffffu) - kCoordBias;
   *z = (int)((k >> 42) & 0x1fffffu) - kCoordBias;
+}
+// block-ownership sharding: the rank that owns a block (2 x 2 x 2 brick pattern for 8 ranks)
+__host__ __device__ inline int block_owner(int bx, int by, int bz, int world) {
+  const int a = (bx + 2 * by + 4 * bz) % world;
+  return a < 0 ? a + world : a;
 }
 __host__ __device__ inline uint32_t hash64(uint64_t k) {
   k ^= k >> 33;
@@ -134,7 +147,13 @@ struct vbx_ctx {
   uint64_t* pkeys[2] = {nullptr, nullptr};
   uint32_t* pvals[2] = {nullptr, nullptr};
   uint32_t* order = nullptr;
-  uint32_t* ray_list = nullptr;            // [max_points] dense list of bundle heads
+  uint32_t* order_inv = nullptr;           // [max_points] inverse of `order` ("sorted" integration order)
+  uint32_t* ray_list = nullptr;            // [max_points] Merged: ray slot (rank in the reference's bundle order) -> head
+  uint32_t* head_list = nullptr;           // [max_points] bundle heads, unordered (front-lane private)
+  uint32_t* first_bits = nullptr;          // [2][max_points / 32 + 1] first-occurrence bitmaps (front-lane private)
+  vbx::OrderScratch order_scratch{};         // k_bundle_order's global tables (front-lane private)
+  vbx::RehashSchedule rehash{};            // libstdc++'s unordered_map growth schedule (vbx_create)
+  size_t order_smem_bytes = 0;             // dynamic shared memory of k_bundle_order
   unsigned long long* long_list = nullptr; // [max_updates / 32 + 1] starts of long voxel runs
   unsigned long long* long_end = nullptr;
   uint32_t* long_state = nullptr;
@@ -194,6 +213,15 @@ struct vbx_ctx {
     bool in_flight = false;
     int kind = 0;
     uint64_t launches = 0;
+    // what the scan was submitted with, kept until it is known to be in the map: a scan that cannot
+    // be applied asynchronously is redone from here (recover_async)
+    uint64_t seq = 0;
+    bool redo = false;
+    float q[4] = {1, 0, 0, 0}, t[3] = {0, 0, 0};
+    uint64_t n = 0;
+    int freespace = 0;
+    const float* in_xyz = nullptr;
+    const uint8_t* in_rgba = nullptr;
   } set[kSets];
   struct FrontLane {  // scratch private to one front-half stream
     cudaStream_t stream = nullptr;
@@ -202,6 +230,9 @@ struct vbx_ctx {
     vbx::SortPlan* sort_plan0 = nullptr;
     uint32_t* sort_status0 = nullptr;
     uint32_t* scan_status = nullptr;
+    uint32_t* head_list = nullptr;
+    uint32_t* first_bits = nullptr;
+    vbx::OrderScratch order_scratch{};
   } lane[kLanes];
   bool async_ready = false;
   int prio_lo = 0, prio_hi = 0;  // stream priority range of the device
@@ -212,8 +243,10 @@ struct vbx_ctx {
   cudaStream_t apply_stream = nullptr;  // ... and the apply kernels here
   cudaEvent_t sorted_event = nullptr;   // ... after this event
   uint64_t async_seq = 0;
+  uint32_t* d_hold = nullptr;           // device flag: a queued scan must be redone, later scans skip their back half
+  uint64_t async_redone = 0;            // scans redone synchronously since vbx_create (reporting)
+  bool hash_dirty = false;              // an asynchronous scan ran out of pool slots: rebuild the hash at the next drain
   int deferred_rc = 0;
-  bool force_wide_keys = false;  // set once an asynchronous scan overflowed the compact bundle keys
   std::string deferred_msg;
   // incremental device -> host mirror (vbx_mirror_updated): gather staging on both sides
   void* mirror_dev = nullptr;
@@ -281,6 +314,10 @@ void select_set(vbx_ctx* c, int k);     // point the context's scratch fields at
 void select_lane(vbx_ctx* c, int l);
 int drain_async(vbx_ctx* c);           // wait for every asynchronously submitted scan, collect its results
 int set_n_blocks(vbx_ctx* c, uint32_t n);
+int alloc_order_scratch(vbx_ctx* c, vbx::OrderScratch* g, uint32_t** head_list, uint32_t** first_bits);
+void free_order_scratch(vbx::OrderScratch* g, uint32_t* head_list, uint32_t* first_bits);
+int init_bundle_order(vbx_ctx* c);     // rehash schedule + shared-memory opt-in of k_bundle_order
+int rebuild_hash(vbx_ctx* c);          // block hash rebuilt from slot_key (after removals / a pool overflow)
 void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S);  // collect a finished asynchronous scan's results
 }  // namespace vbx
 

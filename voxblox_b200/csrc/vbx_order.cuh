@@ -1,0 +1,162 @@
+// The Merged integrator's bundle order: the iteration order of the reference's
+//   LongIndexHashMapType<AlignedVector<size_t>>::type voxel_map / clear_map
+// (tsdf_integrator.cc:318-322), which integrateVoxels walks with one thread
+// (tsdf_integrator.cc:436-456).  That map is a libstdc++ std::unordered_map filled by bundleRays
+// (cc:340-371) in point order, so its iteration order is a pure function of
+//   (a) the sequence of DISTINCT voxel keys in first-occurrence order,
+//   (b) LongIndexHash of each key (core/block_hash.h:52-64), and
+//   (c) libstdc++'s insertion / rehash rules (bits/hashtable.h _M_insert_bucket_begin,
+//       _M_rehash_aux; bits/hashtable_policy.h _Prime_rehash_policy):
+//       - a node whose bucket is non-empty goes to the FRONT of that bucket's group of nodes;
+//       - a node whose bucket is empty goes to the FRONT of the whole list (a new group);
+//       - a rehash re-inserts every node, in list order, into the new bucket array by the same
+//         two rules;
+//       - the bucket count grows along the policy's prime table when the element count would
+//         exceed it (max_load_factor 1).
+// Hence after any sequence of insertions into a table of n buckets the list is: groups in
+// descending order of their creation time, nodes of a group in descending insertion time -- so
+//   position(b) = #nodes in groups created later than b's group + #nodes of b's group inserted later
+// which is data parallel: a chain per bucket (atomicExch), the group's creation time and size by
+// walking the chain, a suffix sum over creation times.  A rehash is the same computation with
+// "insertion time" = position in the list before the rehash.  The schedule of rehashes (element
+// count at which it happens, new bucket count) depends on the number of insertions only and is
+// computed on the host from the very policy class the C++ library ships (vbx_create), so the
+// device follows the libstdc++ the engine is built with.
+//
+// Checked against a real std::unordered_map on the host by tests/umap_order_check.cc (same code,
+// compiled for the host), and end to end by every Merged parity test (bit-exact against the
+// reference's own MergedTsdfIntegrator with one thread).
+#pragma once
+
+#include <stdint.h>
+
+namespace vbx {
+
+struct RehashSchedule {  // event k: when the map holds m[k] elements the bucket count becomes n[k]
+  int count;
+  uint32_t m[30];
+  uint32_t n[30];
+};
+
+struct OrderScratch {     // global-memory fallback when a map's tables do not fit shared memory
+  uint32_t* h;            // [cap] LongIndexHash per element (insertion order)
+  uint32_t* tau;          // [cap] current insertion time
+  uint32_t* tau2;         // [cap]
+  uint32_t* next;         // [cap] bucket chain
+  uint32_t* A;            // [cap] group sizes by creation time -> suffix sums
+  uint32_t* bhead;        // [bucket_cap]
+  uint32_t* head_of;      // [cap] element -> sorted position of its bundle head
+  uint32_t* wp;           // [cap / 32 + 1] popcount prefix of the first-occurrence bitmap
+  uint32_t cap, bucket_cap;
+};
+
+constexpr uint32_t kOrderNil = 0xffffffffu;
+constexpr int kOrderThreads = 1024;
+
+#if defined(__CUDACC__)
+// exclusive scan of one value per thread over the 1024-thread block; *total = block sum
+__device__ __forceinline__ uint32_t order_block_scan(uint32_t v, uint32_t* warp_sums /* [33] shared */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) warp_sums[32] = winc;
+  }
+  __syncthreads();
+  const uint32_t r = warp_sums[warp] + inc - v;
+  *total = warp_sums[32];
+  __syncthreads();  // warp_sums may be reused right away
+  return r;
+}
+
+// List positions of elements [0, m) with insertion times tau[] in a table of n buckets.
+// Result in tau_out[]; A, next, bhead are scratch.
+__device__ inline void order_positions(const uint32_t* h, const uint32_t* tau, uint32_t* tau_out, uint32_t* next,
+                                       uint32_t* A, uint32_t* bhead, uint32_t m, uint32_t n, uint32_t* warp_sums) {
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t j = tid; j < n; j += kOrderThreads) bhead[j] = kOrderNil;
+  for (uint32_t t = tid; t < m; t += kOrderThreads) A[t] = 0u;
+  __syncthreads();
+  for (uint32_t b = tid; b < m; b += kOrderThreads) next[b] = atomicExch(&bhead[h[b] % n], b);
+  __syncthreads();
+  // the group's creator (smallest time) publishes the group size at its creation time
+  for (uint32_t b = tid; b < m; b += kOrderThreads) {
+    const uint32_t tb = tau[b];
+    uint32_t cmin = kOrderNil, size = 0;
+    for (uint32_t c = bhead[h[b] % n]; c != kOrderNil; c = next[c]) {
+      cmin = min(cmin, tau[c]);
+      ++size;
+    }
+    if (cmin == tb) A[tb] = size;
+  }
+  __syncthreads();
+  // A[t] <- number of elements in groups created after time t (exclusive suffix sum), top chunk first
+  {
+    uint32_t carry = 0;
+    const uint32_t chunks = (m + kOrderThreads - 1) / kOrderThreads;
+    for (uint32_t c = chunks; c-- > 0;) {
+      const uint32_t t = c * kOrderThreads + (kOrderThreads - 1 - tid);  // thread 0 holds the highest time
+      const uint32_t v = t < m ? A[t] : 0u;
+      uint32_t total;
+      const uint32_t ex = order_block_scan(v, warp_sums, &total);
+      if (t < m) A[t] = carry + ex;
+      carry += total;
+    }
+  }
+  __syncthreads();
+  for (uint32_t b = tid; b < m; b += kOrderThreads) {
+    const uint32_t tb = tau[b];
+    uint32_t cmin = kOrderNil, later = 0;
+    for (uint32_t c = bhead[h[b] % n]; c != kOrderNil; c = next[c]) {
+      const uint32_t tc = tau[c];
+      cmin = min(cmin, tc);
+      later += tc > tb ? 1u : 0u;
+    }
+    tau_out[b] = A[cmin] + later;
+  }
+  __syncthreads();
+}
+
+// All rehash stages + the final listing for B elements already loaded into h[] (insertion order).
+// On return pos[] (= one of tau / tau2, returned) holds every element's position in the iteration order.
+__device__ inline uint32_t* order_run(const RehashSchedule& rs, uint32_t B, const uint32_t* h, uint32_t* tau, uint32_t* tau2,
+                                      uint32_t* next, uint32_t* A, uint32_t* bhead, uint32_t* warp_sums) {
+  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) tau[e] = e;
+  __syncthreads();
+  uint32_t n_cur = 1;
+  uint32_t* cur = tau;
+  uint32_t* oth = tau2;
+  for (int k = 0; k < rs.count; ++k) {
+    const uint32_t mk = rs.m[k];
+    if (mk >= B) break;  // the map never reaches this size
+    if (mk > 0) {
+      order_positions(h, cur, oth, next, A, bhead, mk, n_cur, warp_sums);
+      // elements inserted after the rehash keep their insertion index as time
+      for (uint32_t e = mk + threadIdx.x; e < B; e += kOrderThreads) oth[e] = e;
+      __syncthreads();
+      uint32_t* t = cur;
+      cur = oth;
+      oth = t;
+    }
+    n_cur = rs.n[k];
+  }
+  order_positions(h, cur, oth, next, A, bhead, B, n_cur, warp_sums);
+  return oth;
+}
+#endif  // __CUDACC__
+
+}  // namespace vbx

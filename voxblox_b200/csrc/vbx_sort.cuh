@@ -66,7 +66,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_prepare(const KeyT* __restrict__ keys, const unsigned long long* d_n, uint32_t n_fixed, int passes,
-               SortPlan* plan, uint32_t* status, uint32_t tiles_cap) {
+               const uint32_t* d_key_bits, SortPlan* plan, uint32_t* status, uint32_t tiles_cap) {
+  // the number of key bits in use may be known on the device only: passes beyond them are not even histogrammed
+  if (d_key_bits) passes = min(passes, (int)((*d_key_bits + 7u) / 8u));
   __shared__ uint32_t hist[kMaxPasses][kRadix];
   __shared__ uint32_t is_last;
   const uint32_t n = d_n ? (uint32_t)min(*d_n, (unsigned long long)tiles_cap * kSortTile) : n_fixed;
@@ -106,8 +108,8 @@ k_sort_prepare(const KeyT* __restrict__ keys, const unsigned long long* d_n, uin
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t buf = 0;
-    for (int p = 0; p < passes; ++p) {
-      const uint32_t act = (n > 1 && !uniform[p]) ? 1u : 0u;
+    for (int p = 0; p < kMaxPasses; ++p) {  // (passes beyond the bits in use stay inactive)
+      const uint32_t act = (p < passes && n > 1 && !uniform[p]) ? 1u : 0u;
       plan->active[p] = act;
       plan->src_buf[p] = buf;
       if (act) buf ^= 1u;

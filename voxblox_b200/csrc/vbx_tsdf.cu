@@ -24,18 +24,21 @@
 // Update order.  The reference applies a voxel's updates in whatever order its
 // threads reach the voxel's mutex (cc:186); with one thread that is point order for
 // Simple / Fast and unordered_map iteration order for Merged.  The device applies
-// them in ray-rank order: point order (integration_order_mode) for Simple / Fast,
-// and ascending (z, y, x) of the bundle voxel for Merged, normal bundles before
-// clearing bundles (cc:323-335).  See DESIGN.md "update order".
+// them in ray-rank order, and the rank IS the reference's one-thread order: point
+// order (integration_order_mode) for Simple / Fast; for Merged the iteration order
+// of the reference's libstdc++ unordered_map (k_bundle_order, vbx_order.cuh), normal
+// bundles before clearing bundles (cc:323-335).  See DESIGN.md "update order".
 #include <cub/cub.cuh>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <unordered_map>  // std::__detail::_Prime_rehash_policy: the growth schedule the reference's map follows
 
 #include "vbx_engine.h"
 #include "vbx_hash.cuh"
 #include "vbx_sort.cuh"
+#include "vbx_order.cuh"
 
 namespace vbx {
 
@@ -58,16 +61,10 @@ struct ScanParams {
   uint32_t set_epoch;  // generation tag of the Fast integrator's approximate sets
   uint32_t epoch;      // call id
   uint64_t max_updates;
-  // bundle keys: voxel coordinates relative to (origin voxel - key_radius), key_bits per
-  // axis; wide = full 21-bit absolute coordinates (fallback for far clearing points)
-  int ovx, ovy, ovz;
-  int key_radius;
-  int key_bits;
-  int wide_keys;
-  // ray-range sharding (multi-GPU): this rank casts the rays whose slot lies in
-  // [slot_lo, slot_hi); shard != 0 defers all block-hash work to vbx_shard_back
-  uint32_t slot_lo, slot_hi;
-  int shard;
+  // block-ownership sharding (multi-GPU, one map over the GPUs of a box): this rank applies the
+  // updates of the voxels in blocks it owns (block_owner() == own_rank) and creates only those
+  // blocks; everything before the apply is identical on all ranks
+  int own_world, own_rank;
   // the number of voxels a ray updates is known from its DDA set-up alone (no anti-grazing, not the
   // Fast integrator): one walk that creates blocks AND writes the update records
   int single_walk;
@@ -90,35 +87,115 @@ __device__ __forceinline__ uint32_t load_color(const uint8_t* rgba, uint32_t idx
   return __ldg(reinterpret_cast<const uint32_t*>(rgba) + idx);
 }
 
+// ------------------------------------------------------- block ownership (multi-GPU)
+// One map over the GPUs of a box: rank r owns the blocks with block_owner() == r -- a 2 x 2 x 2
+// brick pattern for 8 ranks, so the blocks around the sensor (where most updates land) spread
+// over all ranks.  See DESIGN.md "multi-GPU".
+__device__ __forceinline__ bool owns_block(const ScanParams& P, int bx, int by, int bz) {
+  return P.own_world <= 1 || block_owner(bx, by, bz, P.own_world) == P.own_rank;
+}
+// An update record's key: (hash position of the block, voxel inside the block).  Records of blocks
+// another rank owns keep their place in the ray's record range (offsets are fixed before the walk)
+// under the key 0xffffffff, which sorts behind every real key and is skipped by the apply.
+constexpr uint32_t kNotOwned = 0xfffffffeu;
+constexpr uint32_t kSkipRecord = 0xffffffffu;
+__device__ __forceinline__ uint32_t record_key(uint32_t hp, uint32_t lin, int L) {
+  return hp >= kNotOwned ? kSkipRecord : ((hp << (3 * L)) | lin);
+}
+
 // ------------------------------------------------------------------ bundle keys
-// key = [clearing | z | y | x]; ascending key order = (clearing, z, y, x).
-__device__ __forceinline__ uint64_t make_point_key(const ScanParams& P, I3 v, bool clearing, bool* in_range) {
-  if (P.wide_keys) {
-    const int lim = kCoordBias - 1;
-    *in_range = !(v.x < -lim || v.x > lim || v.y < -lim || v.y > lim || v.z < -lim || v.z > lim);
-    return pack3(v.x, v.y, v.z) | ((uint64_t)clearing << 63);
-  }
-  const int rx = v.x - P.ovx + P.key_radius, ry = v.y - P.ovy + P.key_radius, rz = v.z - P.ovz + P.key_radius;
-  const int span = 2 * P.key_radius;
-  *in_range = !(rx < 0 || rx > span || ry < 0 || ry > span || rz < 0 || rz > span);
-  return (uint64_t)rx | ((uint64_t)ry << P.key_bits) | ((uint64_t)rz << (2 * P.key_bits)) |
-         ((uint64_t)clearing << (3 * P.key_bits));
+// key = [clearing | z | y | x] with the voxel coordinates taken relative to the bounding box of
+// the scan's valid points' voxels (k_point_bounds), each axis in exactly the bits its extent
+// needs.  Any scan fits 64 bits (|voxel coordinate| < 2^20: at most 21 bits per axis + 1), a
+// 640 x 480 room scan needs ~22 -- and the sort only runs the radix passes those bits span.
+// Ascending key order = (clearing, z, y, x).
+constexpr uint32_t kBoundBias = 1u << 30;
+struct KeyLayout {
+  int minx, miny, minz;
+  int bx, by, bz;  // bits per axis
+  bool any;        // the scan has at least one valid point
+};
+__device__ __forceinline__ int bits_of(uint32_t extent) { return 32 - __clz(extent); }
+__device__ __forceinline__ KeyLayout key_layout(const ScanState* st) {
+  KeyLayout k;
+  const uint32_t mx = st->kb_max[0];
+  k.any = mx != 0u;
+  k.minx = (int)(0xffffffffu - st->kb_min[0] - kBoundBias);
+  k.miny = (int)(0xffffffffu - st->kb_min[1] - kBoundBias);
+  k.minz = (int)(0xffffffffu - st->kb_min[2] - kBoundBias);
+  k.bx = k.any ? bits_of((uint32_t)((int)(mx - kBoundBias) - k.minx)) : 0;
+  k.by = k.any ? bits_of((uint32_t)((int)(st->kb_max[1] - kBoundBias) - k.miny)) : 0;
+  k.bz = k.any ? bits_of((uint32_t)((int)(st->kb_max[2] - kBoundBias) - k.minz)) : 0;
+  return k;
+}
+__device__ __forceinline__ uint64_t make_point_key(const KeyLayout& k, I3 v, bool clearing, bool* in_range) {
+  const int rx = v.x - k.minx, ry = v.y - k.miny, rz = v.z - k.minz;
+  *in_range = k.any && rx >= 0 && ry >= 0 && rz >= 0 && (rx >> k.bx) == 0 && (ry >> k.by) == 0 && (rz >> k.bz) == 0;
+  return (uint64_t)(uint32_t)rx | ((uint64_t)(uint32_t)ry << k.bx) | ((uint64_t)(uint32_t)rz << (k.bx + k.by)) |
+         ((uint64_t)clearing << (k.bx + k.by + k.bz));
 }
 // the key a NORMAL bundle ending in voxel v would have (anti-grazing lookup)
-__device__ __forceinline__ uint64_t normal_key_of(const ScanParams& P, int x, int y, int z, bool* in_range) {
-  return make_point_key(P, i3(x, y, z), false, in_range);
+__device__ __forceinline__ uint64_t normal_key_of(const KeyLayout& k, int x, int y, int z, bool* in_range) {
+  return make_point_key(k, i3(x, y, z), false, in_range);
 }
-__device__ __forceinline__ bool key_is_clearing(const ScanParams& P, uint64_t key) {
-  return ((key >> (P.wide_keys ? 63 : 3 * P.key_bits)) & 1ull) != 0;
+__device__ __forceinline__ bool key_is_clearing(const KeyLayout& k, uint64_t key) {
+  return ((key >> (k.bx + k.by + k.bz)) & 1ull) != 0;
+}
+// the voxel a bundle key stands for
+__device__ __forceinline__ I3 key_voxel(const KeyLayout& k, uint64_t key) {
+  return i3((int)(key & ((1ull << k.bx) - 1ull)) + k.minx, (int)((key >> k.bx) & ((1ull << k.by) - 1ull)) + k.miny,
+            (int)((key >> (k.bx + k.by)) & ((1ull << k.bz) - 1ull)) + k.minz);
 }
 
 // ------------------------------------------------------------------- kernels
-// Merged: key every point by its end voxel (bundleRays, cc:340-371).
+// Merged, pass 1 over the cloud: the bounding box of the valid points' voxels (and their count).
+__global__ void k_point_bounds(ScanParams P, const float* __restrict__ xyz, const uint32_t* __restrict__ order,
+                               uint32_t* __restrict__ first_bits, ScanState* st) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < 2u * ((P.n + 31u) >> 5)) first_bits[s] = 0u;  // the first-occurrence bitmaps k_heads fills
+  bool valid = false;
+  I3 v = i3(0, 0, 0);
+  if (s < P.n) {
+    const F3 p = load_point(xyz, s);  // (the bounding box does not depend on the point order)
+    if (classify_point(p, P.min_ray, P.max_ray, P.allow_clear != 0, P.freespace != 0) != 0) {
+      v = grid_index(transform(P.T, p), P.voxel_size_inv);
+      const int lim = kCoordBias - 1;
+      if (v.x < -lim || v.x > lim || v.y < -lim || v.y > lim || v.z < -lim || v.z > lim) {
+        atomicOr(&st->error, kErrCoordRange);
+      } else {
+        valid = true;
+      }
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, valid);
+  if (b) {
+    // encoded so that the zero-initialised status block means "empty": both ends are atomicMax'ed
+    const uint32_t hi_x = valid ? (uint32_t)v.x + kBoundBias : 0u, lo_x = valid ? 0xffffffffu - ((uint32_t)v.x + kBoundBias) : 0u;
+    const uint32_t hi_y = valid ? (uint32_t)v.y + kBoundBias : 0u, lo_y = valid ? 0xffffffffu - ((uint32_t)v.y + kBoundBias) : 0u;
+    const uint32_t hi_z = valid ? (uint32_t)v.z + kBoundBias : 0u, lo_z = valid ? 0xffffffffu - ((uint32_t)v.z + kBoundBias) : 0u;
+    const uint32_t r0 = __reduce_max_sync(0xffffffffu, hi_x), r1 = __reduce_max_sync(0xffffffffu, hi_y),
+                   r2 = __reduce_max_sync(0xffffffffu, hi_z), r3 = __reduce_max_sync(0xffffffffu, lo_x),
+                   r4 = __reduce_max_sync(0xffffffffu, lo_y), r5 = __reduce_max_sync(0xffffffffu, lo_z);
+    if ((threadIdx.x & 31) == 0) {
+      if (r0 > st->kb_max[0]) atomicMax(&st->kb_max[0], r0);
+      if (r1 > st->kb_max[1]) atomicMax(&st->kb_max[1], r1);
+      if (r2 > st->kb_max[2]) atomicMax(&st->kb_max[2], r2);
+      if (r3 > st->kb_min[0]) atomicMax(&st->kb_min[0], r3);
+      if (r4 > st->kb_min[1]) atomicMax(&st->kb_min[1], r4);
+      if (r5 > st->kb_min[2]) atomicMax(&st->kb_min[2], r5);
+      atomicAdd(&st->n_valid_points, (uint32_t)__popc(b));
+    }
+  }
+}
+
+// Merged, pass 2: key every point by its end voxel (bundleRays, cc:340-371), in the reference's
+// point order (position s of that order holds point point_order(s)).
 template <typename KeyT>
 __global__ void k_point_keys(ScanParams P, const float* __restrict__ xyz, const uint32_t* __restrict__ order,
                              KeyT* __restrict__ keys, uint32_t* __restrict__ vals, ScanState* st) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = false;
+  const KeyLayout kl = key_layout(st);
+  if (s == 0) st->key_bits = (uint32_t)(kl.bx + kl.by + kl.bz + 1);
   if (s < P.n) {
     const uint32_t idx = point_order(P, order, s);
     const F3 p = load_point(xyz, idx);
@@ -127,19 +204,12 @@ __global__ void k_point_keys(ScanParams P, const float* __restrict__ xyz, const 
     if (cls != 0) {
       const I3 v = grid_index(transform(P.T, p), P.voxel_size_inv);
       bool in_range;
-      const uint64_t k = make_point_key(P, v, cls == 2, &in_range);
-      if (in_range) {
-        key = (KeyT)k;
-        valid = true;
-      } else {
-        atomicOr(&st->error, P.wide_keys ? kErrCoordRange : kNeedWideKeys);
-      }
+      const uint64_t k = make_point_key(kl, v, cls == 2, &in_range);
+      if (in_range) key = (KeyT)k;  // (out of range only beyond +-2^20 voxels: flagged by k_point_bounds)
     }
     keys[s] = key;
     vals[s] = idx;
   }
-  const unsigned b = __ballot_sync(0xffffffffu, valid);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->n_valid_points, (uint32_t)__popc(b));
 }
 
 // "sorted" integration order: key = |p|^2 (float, widened to double like
@@ -154,16 +224,40 @@ __global__ void k_sqnorm_keys(uint32_t n, const float* __restrict__ xyz, uint64_
   vals[i] = i;
 }
 
-// Dense (unordered) list of bundle heads; a ray's rank stays its sorted position.
+// point index -> its position in the reference's point order (the inverse of point_order)
+__device__ __forceinline__ uint32_t point_order_inv(const ScanParams& P, const uint32_t* order_inv, uint32_t idx) {
+  if (P.order_mode == 1) return order_inv[idx];
+  if (P.n_groups * 1024u <= idx) return idx;
+  return (idx % 1024u) * P.n_groups + idx / 1024u;
+}
+__global__ void k_invert_order(uint32_t n, const uint32_t* __restrict__ order, uint32_t* __restrict__ order_inv) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) order_inv[order[s]] = s;
+}
+
+// Dense (unordered) list of bundle heads, and the first-occurrence bitmaps: bit t of map m
+// (0 normal, 1 clearing) is set when the point at position t of the reference's point order is the
+// first of its bundle, i.e. the point whose operator[] inserts the bundle's key into the reference's
+// voxel_map / clear_map (bundleRays, cc:340-371).  k_bundle_order turns them into the maps'
+// iteration order.
 template <typename KeyT>
-__global__ void k_heads(uint32_t n, uint32_t slot_lo, uint32_t slot_hi, const KeyT* __restrict__ keys,
-                        uint32_t* __restrict__ ray_list, uint32_t* __restrict__ cnt, ScanState* st) {
+__global__ void k_heads(ScanParams P, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+                        const uint32_t* __restrict__ order_inv, uint32_t* __restrict__ head_list,
+                        uint32_t* __restrict__ first_bits, uint32_t* __restrict__ cnt, ScanState* st) {
+  const uint32_t n = P.n;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const KeyLayout kl = key_layout(st);
   bool head = false;
   if (i <= n) cnt[i] = 0;
   if (i < n) {
     const KeyT key = keys[i];
-    head = key != (KeyT)~(KeyT)0 && (i == 0 || keys[i - 1] != key) && i >= slot_lo && i < slot_hi;
+    head = key != (KeyT)~(KeyT)0 && (i == 0 || keys[i - 1] != key);
+    if (head) {
+      // the stable sort keeps point order inside a bundle: its first member is its first occurrence
+      const uint32_t t0 = point_order_inv(P, order_inv, vals[i]);
+      const uint32_t words = (n + 31u) >> 5;
+      atomicOr(first_bits + (key_is_clearing(kl, (uint64_t)key) ? words : 0u) + (t0 >> 5), 1u << (t0 & 31u));
+    }
   }
   const unsigned b = __ballot_sync(0xffffffffu, head);
   if (b) {
@@ -171,7 +265,82 @@ __global__ void k_heads(uint32_t n, uint32_t slot_lo, uint32_t slot_hi, const Ke
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&st->n_ray_list, (uint32_t)__popc(b));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (head) ray_list[base + __popc(b & ((1u << lane) - 1u))] = i;
+    if (head) head_list[base + __popc(b & ((1u << lane) - 1u))] = i;
+  }
+}
+
+// LongIndexHash, core/block_hash.h:52-64 (32-bit wrap of x + 17191 y + 17191^2 z)
+__device__ __forceinline__ uint32_t long_index_hash(int x, int y, int z) {
+  return (uint32_t)x + (uint32_t)y * 17191u + (uint32_t)z * 295530481u;
+}
+// The reference's bundle order (vbx_order.cuh): ONE thread block ranks the bundles of the normal map,
+// then those of the clearing map, and writes ray_list[rank] = sorted position of the bundle's head.
+// Ranks are dense: normal bundles 0 .. B0-1 in voxel_map's iteration order, clearing bundles
+// B0 .. B0+B1-1 in clear_map's (integrateRays(false) runs before integrateRays(true), cc:323-335).
+// Tables live in shared memory when they fit (a few thousand bundles), else in global scratch.
+template <typename KeyT>
+__global__ void __launch_bounds__(kOrderThreads)
+k_bundle_order(ScanParams P, RehashSchedule rs, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+               const uint32_t* __restrict__ order_inv, const uint32_t* __restrict__ head_list,
+               const uint32_t* __restrict__ first_bits, OrderScratch g, uint32_t smem_words,
+               uint32_t* __restrict__ ray_list, ScanState* st) {
+  extern __shared__ uint32_t order_smem[];
+  __shared__ uint32_t warp_sums[33];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t words = (P.n + 31u) >> 5;
+  const uint32_t n_heads = st->n_ray_list;
+  const KeyLayout kl = key_layout(st);
+  uint32_t base_rank = 0;
+  for (int mp = 0; mp < 2; ++mp) {
+    const uint32_t* bits = first_bits + (mp ? words : 0u);
+    // popcount prefix of the bitmap: insertion index of a bundle = number of earlier first occurrences
+    uint32_t B = 0;
+    for (uint32_t c = 0; c < words; c += kOrderThreads) {
+      const uint32_t w = c + tid;
+      const uint32_t v = w < words ? (uint32_t)__popc(bits[w]) : 0u;
+      uint32_t total;
+      const uint32_t ex = order_block_scan(v, warp_sums, &total);
+      if (w < words) g.wp[w] = B + ex;
+      B += total;
+    }
+    if (mp == 0 && tid == 0) st->n_rays = B;
+    if (mp == 1 && tid == 0) st->n_clear_rays = B;
+    __syncthreads();
+    if (B == 0) continue;
+    if (B > g.cap) {  // cannot happen: cap = max_points_per_scan
+      if (tid == 0) atomicOr(&st->error, kErrUpdatesFull);
+      continue;
+    }
+    // bucket count after B insertions
+    uint32_t n_final = 1;
+    for (int k = 0; k < rs.count && rs.m[k] < B; ++k) n_final = rs.n[k];
+    uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *A = g.A, *bhead = g.bhead;
+    if (5u * B + n_final <= smem_words) {
+      h = order_smem;
+      tau = h + B;
+      tau2 = tau + B;
+      next = tau2 + B;
+      A = next + B;
+      bhead = A + B;
+    } else if (n_final > g.bucket_cap) {
+      if (tid == 0) atomicOr(&st->error, kErrUpdatesFull);
+      continue;
+    }
+    for (uint32_t j = tid; j < n_heads; j += kOrderThreads) {
+      const uint32_t i = head_list[j];
+      const uint64_t key = (uint64_t)keys[i];
+      if ((key_is_clearing(kl, key) ? 1 : 0) != mp) continue;
+      const uint32_t t0 = point_order_inv(P, order_inv, vals[i]);
+      const uint32_t e = g.wp[t0 >> 5] + (uint32_t)__popc(bits[t0 >> 5] & ((1u << (t0 & 31u)) - 1u));
+      const I3 v = key_voxel(kl, key);
+      h[e] = long_index_hash(v.x, v.y, v.z);
+      g.head_of[e] = i;
+    }
+    __syncthreads();
+    const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, A, bhead, warp_sums);
+    for (uint32_t e = tid; e < B; e += kOrderThreads) ray_list[base_rank + pos[e]] = g.head_of[e];
+    __syncthreads();
+    base_rank += B;
   }
 }
 
@@ -224,10 +393,10 @@ __device__ __forceinline__ float fold_step(float state, float4 abcd, bool is_mea
 template <typename KeyT, bool kIeee>
 __device__ bool fold_bundle(const ScanParams& P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
                             const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t i,
-                            float4* stage_warp, F3* out_mp, float* out_mw, uint32_t* out_col) {
+                            float4* stage_warp, F3* out_mp, float* out_mw, uint32_t* out_col, const ScanState* st) {
   const int lane = threadIdx.x & 31;
   const KeyT key = keys[i];
-  const bool clearing = key_is_clearing(P, (uint64_t)key);
+  const bool clearing = key_is_clearing(key_layout(st), (uint64_t)key);
   float mw = 0.0f;
   bool done = false;
   bool suspect = false;
@@ -363,6 +532,7 @@ __device__ __forceinline__ void store_ray(const ScanParams& P, uint32_t i, F3 po
 struct ChunkDesc {
   uint32_t live;   // members that carry weight, in list order
   uint32_t head;   // sorted position of the bundle's first member
+  uint32_t slot;   // the bundle's ray slot = its rank in the reference's bundle order
   uint32_t flags;
   float mw;        // merged weight after this chunk (final on the bundle's last chunk)
 };
@@ -404,12 +574,13 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
   const uint32_t pair = blockIdx.x * 2u + (uint32_t)pair_in_block;
   const uint32_t n_pairs = gridDim.x * 2u;
   const uint32_t n_bundles = st->n_ray_list;
+  const KeyLayout kl = key_layout(st);
   uint32_t seq = 0;
   if (producer) {
     for (uint32_t b = pair; b < n_bundles; b += n_pairs) {
       const uint32_t i = ray_list[b];
       const KeyT key = keys[i];
-      const bool clearing = key_is_clearing(P, (uint64_t)key);
+      const bool clearing = key_is_clearing(kl, (uint64_t)key);
       float mw = 0.0f;
       bool done = false, first = true;
       uint32_t j0 = i;
@@ -500,6 +671,7 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
           ChunkDesc d;
           d.live = live;
           d.head = i;
+          d.slot = b;
           d.flags = (first ? kChunkFirst : 0u) | (done ? kChunkLast : 0u) | (any_bad ? kChunkSuspect : 0u);
           d.mw = mw_run;
           desc[pair_in_block][slot] = d;
@@ -514,6 +686,7 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
       ChunkDesc d;
       d.live = 0u;
       d.head = 0u;
+      d.slot = 0u;
       d.flags = kChunkEnd;
       d.mw = 0.f;
       desc[pair_in_block][seq & 1u] = d;
@@ -561,7 +734,7 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
         if (__any_sync(0xffffffffu, suspect)) {
           // the fast division met an operand it does not trust: fold this bundle again with the
           // IEEE division (one warp, the slot just consumed as its staging area)
-          fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage[pair_in_block][slot], &mp, &mw, &mcol);
+          fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage[pair_in_block][slot], &mp, &mw, &mcol, st);
           if (lane == 0) {
             atomicAdd(&st->n_refold, 1u);
             uint32_t lo = i, hi = P.n;  // first sorted position with a larger key
@@ -581,14 +754,13 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
                  (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 6) & 0xffu) << 24);
         }
         if (lane == 0) {
-          const bool clearing = key_is_clearing(P, (uint64_t)keys[i]);
+          const bool clearing = key_is_clearing(kl, (uint64_t)keys[i]);
           const F3 pg = transform(P.T, mp);
-          store_ray(P, i, pg, mw, mcol, clearing, ray_p, ray_a, ray_c);
+          store_ray(P, d.slot, pg, mw, mcol, clearing, ray_p, ray_a, ray_c);
           if (P.single_walk) {
             Dda dd;
             dda_setup(dd, P.origin, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc, true);
-            cnt[i] = dd.len + 1u;  // RayCaster emits ray_length_in_steps_ + 1 voxels (integrator_utils.cc:111-125)
-            atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
+            cnt[d.slot] = dd.len + 1u;  // RayCaster emits ray_length_in_steps_ + 1 voxels (integrator_utils.cc:111-125)
           }
         }
       }
@@ -613,19 +785,15 @@ __device__ bool bundle_exists(const KeyT* keys, uint32_t n, KeyT key) {
 }
 
 template <typename KeyT>
-__device__ __forceinline__ bool grazing_skip(const ScanParams& P, const KeyT* keys, KeyT own, bool clearing,
-                                             int x, int y, int z) {
+__device__ __forceinline__ bool grazing_skip(const ScanParams& P, const KeyLayout& kl, const KeyT* keys, KeyT own,
+                                             bool clearing, int x, int y, int z) {
   bool in_range;
-  const KeyT vkey = (KeyT)normal_key_of(P, x, y, z, &in_range);
+  const KeyT vkey = (KeyT)normal_key_of(kl, x, y, z, &in_range);
   if (!in_range) return false;
   const KeyT own_normal = clearing ? (KeyT)~(KeyT)0 : own;
   return (clearing || vkey != own_normal) && bundle_exists<KeyT>(keys, P.n, vkey);
 }
 
-// LongIndexHash, core/block_hash.h:52-64 (32-bit wrap of x + 17191 y + 17191^2 z)
-__device__ __forceinline__ uint32_t long_index_hash(int x, int y, int z) {
-  return (uint32_t)x + (uint32_t)y * 17191u + (uint32_t)z * 295530481u;
-}
 // ApproxHashSet::replaceHash, utils/approx_hash_array.h:125-134.  The generation tag in
 // the upper word plays the role of the reference's sliding offset (h:155-168).
 __device__ __forceinline__ bool replace_hash(unsigned long long* set, uint32_t h, uint32_t epoch) {
@@ -651,15 +819,15 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   KeyT own = 0;
   if (P.kind == VBX_MERGED) {
     if (t >= st->n_ray_list) return;
-    i = ray_list[t];
+    i = t;  // ray slot = rank in the reference's bundle order; ray_list[t] = sorted position of the head
     const float4 rp = ray_p[i];
     point_G = f3(rp.x, rp.y, rp.z);
     clearing = (__float_as_uint(rp.w) & 1u) != 0;
-    own = keys[i];
+    own = keys[ray_list[t]];
   } else {
     i = t;
     if (i > P.n) return;
-    if (i == P.n || i < P.slot_lo || i >= P.slot_hi) {
+    if (i == P.n) {
       cnt[i] = 0;
       return;
     }
@@ -683,7 +851,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
     store_ray(P, i, point_G, point_weight(p.z, P.use_const_weight != 0), load_color(rgba, idx), clearing, ray_p,
               ray_a, ray_c);
   }
-  atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);
+  if (P.kind != VBX_MERGED) atomicAdd(clearing ? &st->n_clear_rays : &st->n_rays, 1u);  // (Merged: k_bundle_order)
 
   Dda d;
   dda_setup(d, P.origin, point_G, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
@@ -698,7 +866,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   const int lim = (kCoordBias - 1) << P.L;
   for (unsigned int s = 0; s <= d.len; ++s, dda_advance(d)) {
     if (P.kind == VBX_MERGED && P.anti_grazing) {
-      if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
+      if (grazing_skip<KeyT>(P, key_layout(st), keys, own, clearing, d.cx, d.cy, d.cz)) continue;
     }
     if (P.kind == VBX_FAST) {
       // cc:531-543: stop once the ray runs through voxels other rays already observed
@@ -714,14 +882,14 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
       break;
     }
     const int bx = d.cx >> P.L, by = d.cy >> P.L, bz = d.cz >> P.L;
-    if (!P.shard && (bx != lbx || by != lby || bz != lbz)) {
+    if ((bx != lbx || by != lby || bz != lbz) && owns_block(P, bx, by, bz)) {
       const uint32_t hp = ensure_block(tab, pack3(bx, by, bz), st);
       if (hp == 0xffffffffu) break;
       mark_touched(tab, hp, P.epoch, st);
-      lbx = bx;
-      lby = by;
-      lbz = bz;
     }
+    lbx = bx;
+    lby = by;
+    lbz = bz;
     ++count;
   }
   cnt[i] = count;
@@ -746,6 +914,16 @@ __global__ void k_pass_begin(ScanState* st, unsigned long long pass_updates) {
   st->n_new = 0;
   st->n_long = 0;
   st->n_verify = 0;
+}
+
+// First kernel of an asynchronously submitted scan's back half (walk stream: submission order).
+__global__ void k_back_begin(ScanState* st, uint32_t* hold) {
+  if (*hold) {
+    st->error |= kSkipped;  // queued behind a scan that must be redone: do nothing, the host redoes both in order
+    st->total_updates = 0;
+  } else if (st->error & kErrUpdatesFull) {
+    *hold = 1u;
+  }
 }
 
 // After the last walk that can create blocks: pool slots for the blocks created by this call
@@ -776,7 +954,7 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_
 // with allocateStorageAndGetVoxelPtr's find-or-create per block change (cc:91-134).
 template <typename KeyT>
 __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, const KeyT* __restrict__ keys, uint32_t i,
-                                    const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
+                                    uint32_t head_pos, const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
                                     const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
                                     uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t c = cnt[i];
@@ -788,7 +966,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
   Dda d;
   dda_setup(d, P.origin, point_G, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
             P.kind != VBX_FAST);
-  const KeyT own = (P.kind == VBX_MERGED) ? keys[i] : (KeyT)0;
+  const KeyT own = (P.kind == VBX_MERGED) ? keys[head_pos] : (KeyT)0;
   uint32_t emitted = 0;
   int lbx = INT_MIN, lby = INT_MIN, lbz = INT_MIN;
   uint32_t hp = 0;
@@ -797,11 +975,13 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
   const int lim = (kCoordBias - 1) << P.L;
   for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
     if (P.kind == VBX_MERGED && P.anti_grazing) {
-      if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
+      if (grazing_skip<KeyT>(P, key_layout(st), keys, own, clearing, d.cx, d.cy, d.cz)) continue;
     }
     const int bx = d.cx >> P.L, by = d.cy >> P.L, bz = d.cz >> P.L;
     if (bx != lbx || by != lby || bz != lbz) {
-      if (P.single_walk) {
+      if (!owns_block(P, bx, by, bz)) {
+        hp = kNotOwned;  // another rank's block: the record keeps its place and is skipped by the apply
+      } else if (P.single_walk) {
         // the only walk of this ray: allocateStorageAndGetVoxelPtr's find-or-create, cc:91-134
         if (d.cx < -lim || d.cx > lim || d.cy < -lim || d.cy > lim || d.cz < -lim || d.cz > lim) {
           atomicOr(&st->error, kErrCoordRange);
@@ -813,7 +993,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
       } else {
         hp = find_block(tab, pack3(bx, by, bz));
       }
-      if (hp != 0xffffffffu) {
+      if (hp != 0xffffffffu && hp != kNotOwned) {
         const int32_t slot = tab.hslot[hp];
         if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
       }
@@ -826,7 +1006,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
     // a record = (hash position of the block, voxel inside the block) -> ray.  A ray whose block
     // could not be created still fills its slots so that offsets stay valid; the error flag set
     // above stops the apply kernels.
-    ckeys[base + emitted] = (hp << (3 * P.L)) | lin;
+    ckeys[base + emitted] = record_key(hp, lin, P.L);
     cvals[base + emitted] = i;
     ++emitted;
   }
@@ -840,14 +1020,16 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
                             uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t i;
+  uint32_t head_pos = 0;
   if (P.kind == VBX_MERGED) {
     if (t >= st->n_ray_list) return;
-    i = ray_list[t];
+    i = t;
+    head_pos = ray_list[t];
   } else {
     i = t;
     if (i >= P.n) return;
   }
-  emit_ray_sequential<KeyT>(P, tab, keys, i, ray_p, cnt, off, ckeys, cvals, st);
+  emit_ray_sequential<KeyT>(P, tab, keys, i, head_pos, ray_p, cnt, off, ckeys, cvals, st);
 }
 
 // The same walk cast by a WARP per ray (single-walk modes of the Merged integrator: a few thousand
@@ -882,7 +1064,7 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
   const int mask = (1 << P.L) - 1;
   const int lim = (kCoordBias - 1) << P.L;
   for (uint32_t b = warp; b < n_rays; b += n_warps) {
-    const uint32_t i = ray_list[b];
+    const uint32_t i = b;  // ray slot = rank in the reference's bundle order
     const uint32_t c = cnt[i];
     if (c == 0 || i < P.emit_lo || i >= P.emit_hi) continue;
     const float4 rp = ray_p[i];
@@ -933,7 +1115,7 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
       __syncwarp();
     }
     if (!merge_ok) {
-      if (lane == 0) emit_ray_sequential<KeyT>(P, tab, keys, i, ray_p, cnt, off, ckeys, cvals, st);
+      if (lane == 0) emit_ray_sequential<KeyT>(P, tab, keys, i, ray_list[b], ray_p, cnt, off, ckeys, cvals, st);
       __syncwarp();
       continue;
     }
@@ -960,14 +1142,16 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
       uint32_t hp = 0u;
       if (head) {
         // the first step inside a block: allocateStorageAndGetVoxelPtr's find-or-create, cc:91-134
-        if (vx < -lim || vx > lim || vy < -lim || vy > lim || vz < -lim || vz > lim) {
+        if (!owns_block(P, bx, by, bz)) {
+          hp = kNotOwned;
+        } else if (vx < -lim || vx > lim || vy < -lim || vy > lim || vz < -lim || vz > lim) {
           atomicOr(&st->error, kErrCoordRange);
           hp = 0xffffffffu;
         } else {
           hp = ensure_block(tab, pack3(bx, by, bz), st);
           if (hp != 0xffffffffu) mark_touched(tab, hp, P.epoch, st);
         }
-        if (hp != 0xffffffffu) {
+        if (hp != 0xffffffffu && hp != kNotOwned) {
           const int32_t slot = tab.hslot[hp];
           if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
         }
@@ -979,7 +1163,7 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
       const uint32_t hp_l = below ? hp_run : chp;
       if (valid) {
         const uint32_t lin = (uint32_t)(vx & mask) | ((uint32_t)(vy & mask) << P.L) | ((uint32_t)(vz & mask) << (2 * P.L));
-        ckeys[base + r] = (hp_l << (3 * P.L)) | lin;
+        ckeys[base + r] = record_key(hp_l, lin, P.L);
         cvals[base + r] = i;
       }
       // carry the last step's block into the next chunk (a full chunk whenever there is a next one)
@@ -990,109 +1174,6 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
     }
     __syncwarp();  // the walk list is reused by this warp's next ray
   }
-}
-
-// ------------------------------------------------------------- ray-range sharding
-// Multi-GPU: a rank's rays emit records keyed by GLOBAL voxel coordinates (17 bits per block
-// axis + 3L bits inside the block) so that every rank can apply every rank's records to its own
-// replica of the map.
-constexpr int kShardBias = 1 << 16;
-__device__ __forceinline__ bool shard_key(int bx, int by, int bz, uint32_t lin, int L, uint64_t* key) {
-  const int lim = kShardBias - 1;
-  if (bx < -lim || bx > lim || by < -lim || by > lim || bz < -lim || bz > lim) return false;
-  *key = ((((uint64_t)(uint32_t)(bz + kShardBias) << 34) | ((uint64_t)(uint32_t)(by + kShardBias) << 17) |
-           (uint64_t)(uint32_t)(bx + kShardBias))
-          << (3 * L)) |
-         lin;
-  return true;
-}
-__device__ __forceinline__ uint64_t shard_key_block(uint64_t key, int L) {
-  const uint64_t b = key >> (3 * L);
-  return pack3((int)(b & 0x1ffffu) - kShardBias, (int)((b >> 17) & 0x1ffffu) - kShardBias,
-               (int)((b >> 34) & 0x1ffffu) - kShardBias);
-}
-
-template <typename KeyT>
-__global__ void k_rays_emit_global(ScanParams P, const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
-                                   const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
-                                   const uint32_t* __restrict__ off, uint4* __restrict__ grec, uint64_t cap,
-                                   ScanState* st) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t i;
-  if (P.kind == VBX_MERGED) {
-    if (t >= st->n_ray_list) return;
-    i = ray_list[t];
-  } else {
-    i = t;
-    if (i >= P.n) return;
-  }
-  const uint32_t c = cnt[i];
-  if (c == 0) return;
-  const uint32_t base = off[i];
-  if ((uint64_t)base + c > cap) {
-    atomicOr(&st->error, kErrUpdatesFull);
-    return;
-  }
-  const float4 rp = ray_p[i];
-  const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
-  Dda d;
-  dda_setup(d, P.origin, f3(rp.x, rp.y, rp.z), clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc,
-            P.kind != VBX_FAST);
-  const KeyT own = (P.kind == VBX_MERGED) ? keys[i] : (KeyT)0;
-  uint32_t emitted = 0;
-  const int mask = (1 << P.L) - 1;
-  for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
-    if (P.kind == VBX_MERGED && P.anti_grazing) {
-      if (grazing_skip<KeyT>(P, keys, own, clearing, d.cx, d.cy, d.cz)) continue;
-    }
-    const uint32_t lin = (uint32_t)(d.cx & mask) | ((uint32_t)(d.cy & mask) << P.L) |
-                         ((uint32_t)(d.cz & mask) << (2 * P.L));
-    uint64_t key = ~0ull;
-    if (!shard_key(d.cx >> P.L, d.cy >> P.L, d.cz >> P.L, lin, P.L, &key)) atomicOr(&st->error, kErrCoordRange);
-    grec[base + emitted] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), i, 0u);  // 16-byte record
-    ++emitted;
-  }
-}
-
-// the gathered records of all ranks, rank after rank (= ascending ray slots)
-struct ShardSegments {
-  const uint4* rec[8];  // (key lo, key hi, ray slot, pad)
-  unsigned long long start[9];  // prefix of the per-rank record counts
-  int world;
-};
-
-// find-or-create the block of every gathered record on THIS rank's replica
-__global__ void k_localize_blocks(ShardSegments seg, Tables tab, int L, uint32_t epoch, uint32_t* __restrict__ hp_of,
-                                  ScanState* st) {
-  const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= seg.start[seg.world]) return;
-  int r = 0;
-  while (p >= seg.start[r + 1]) ++r;
-  const uint4 rec = seg.rec[r][p - seg.start[r]];
-  const uint64_t key = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-  const uint32_t hp = ensure_block(tab, shard_key_block(key, L), st);
-  if (hp != 0xffffffffu) mark_touched(tab, hp, epoch, st);
-  hp_of[p] = hp;
-}
-
-__global__ void k_localize_keys(ShardSegments seg, Tables tab, int L, const uint32_t* __restrict__ hp_of,
-                                uint32_t* __restrict__ ckeys, uint32_t* __restrict__ cvals) {
-  const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= seg.start[seg.world]) return;
-  int r = 0;
-  while (p >= seg.start[r + 1]) ++r;
-  const unsigned long long j = p - seg.start[r];
-  const uint32_t hp = hp_of[p];
-  if (hp == 0xffffffffu) {
-    ckeys[p] = 0xffffffffu;
-    cvals[p] = 0;
-    return;
-  }
-  const uint4 rec = seg.rec[r][j];
-  const uint32_t lin = rec.x & ((1u << (3 * L)) - 1u);
-  ckeys[p] = (hp << (3 * L)) | lin;
-  cvals[p] = rec.z;
-  tab.slot_updated[tab.hslot[hp]] = 7;  // (*last_block)->updated().set(), cc:128
 }
 
 // ----------------------------------------------------------------------- apply
@@ -1111,7 +1192,9 @@ __device__ __forceinline__ VoxelRef locate_voxel(const ScanParams& P, const Tabl
   const int vy = (by << P.L) + (int)((lin >> P.L) & mask);
   const int vz = (bz << P.L) + (int)(lin >> (2 * P.L));
   VoxelRef r;
-  r.ptr = tab.tsdf + (((size_t)tab.hslot[hp]) << (3 * P.L)) + lin;
+  // (a block that found no pool slot -- kErrPoolFull -- has hslot < 0: nothing to update)
+  const int32_t slot = tab.hslot[hp];
+  r.ptr = slot >= 0 ? tab.tsdf + (((size_t)slot) << (3 * P.L)) + lin : nullptr;
   const F3 c = f3(center_coord(vx, P.voxel_size), center_coord(vy, P.voxel_size), center_coord(vz, P.voxel_size));
   r.vo = sub3(c, P.origin);
   return r;
@@ -1218,8 +1301,8 @@ k_apply_short(ScanParams P, Tables tab, RecordView rv, const float4* __restrict_
     VoxelRef vr;
     vr.ptr = nullptr;
     vr.vo = f3(0.f, 0.f, 0.f);
-    if (e < total) {
-      key = ckeys[e];
+    if (e < total) key = ckeys[e];
+    if (key != kSkipRecord) {  // (records of blocks this rank does not own sort to the end and are skipped)
       head = (e == 0) || (ckeys[e - 1] != key);
       const uint32_t r = cvals[e];
       const float4 ra = ray_a[r];
@@ -1235,6 +1318,7 @@ k_apply_short(ScanParams P, Tables tab, RecordView rv, const float4* __restrict_
     }
     s_key[threadIdx.x] = key;
     __syncthreads();
+    head = head && vr.ptr != nullptr;
     if (head) {
       TsdfVoxel v = *vr.ptr;
       unsigned long long j = e;
@@ -1421,6 +1505,41 @@ __global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const floa
 }
 
 // --------------------------------------------------------------------- host side
+// The growth schedule of a default-constructed std::unordered_map (max_load_factor 1) under
+// one-by-one insertion, taken from the C++ library's own policy object: operator[] asks
+// _M_need_rehash(bucket_count, element_count, 1) before every insertion of a new key
+// (bits/hashtable.h _M_insert_unique_node).
+int init_bundle_order(vbx_ctx* c) {
+  RehashSchedule& rs = c->rehash;
+  std::memset(&rs, 0, sizeof(rs));
+  std::__detail::_Prime_rehash_policy pol;
+  size_t buckets = 1;
+  size_t e = 0;
+  const size_t limit = (size_t)c->max_points + 1;
+  while (e < limit && rs.count < 30) {
+    const auto r = pol._M_need_rehash(buckets, e, 1);
+    if (r.first) {
+      buckets = r.second;
+      rs.m[rs.count] = (uint32_t)e;
+      rs.n[rs.count] = (uint32_t)buckets;
+      ++rs.count;
+    }
+    // no rehash can happen before the element count exceeds the policy's next threshold
+    const size_t next = (size_t)pol._M_next_resize;
+    e = std::max(e + 1, next);
+  }
+  if (e < limit) return fail(c, VBX_E_INVALID, "unordered_map growth schedule longer than expected");
+  int dev = 0, max_optin = 0;
+  VBX_CUDA(c, cudaGetDevice(&dev));
+  VBX_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  c->order_smem_bytes = (size_t)std::max(0, max_optin - 2048) & ~(size_t)15;
+  VBX_CUDA(c, cudaFuncSetAttribute(k_bundle_order<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)c->order_smem_bytes));
+  VBX_CUDA(c, cudaFuncSetAttribute(k_bundle_order<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)c->order_smem_bytes));
+  return VBX_OK;
+}
+
 static inline unsigned int grid_for(uint64_t n, int block) { return (unsigned int)((n + block - 1) / block); }
 
 static int bits_for(uint64_t v) {
@@ -1433,8 +1552,13 @@ static int bits_for(uint64_t v) {
 }
 
 static int check_state_errors(vbx_ctx* c, uint32_t err) {
-  err &= ~kNeedWideKeys;
+  err &= kFatalErrors;
   if (!err) return VBX_OK;
+  if (err & kErrPoolFull) {
+    // the surplus hash entries of this call have no pool slot: drop them, or later calls would find them
+    if (c->h_state->n_blocks) c->n_blocks = c->h_state->n_blocks;
+    rebuild_hash(c);
+  }
   std::string m = "device reported:";
   if (err & kErrPoolFull) m += " block pool full (raise vbx_engine_options.max_blocks);";
   if (err & kErrHashFull) m += " block hash full;";
@@ -1473,7 +1597,8 @@ struct Marks {
 // The engine's own stable radix sort (vbx_sort.cuh).  n lives on the device (d_n) or is n_fixed.
 template <typename KeyT>
 static int own_sort(vbx_ctx* c, int which, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                    const unsigned long long* d_n, uint32_t n_fixed, int key_bits, uint64_t* launches) {
+                    const unsigned long long* d_n, uint32_t n_fixed, int key_bits, uint64_t* launches,
+                    const uint32_t* d_key_bits = nullptr) {
   cudaStream_t s = c->stream;
   const int passes = std::min(kMaxPasses, (key_bits + 7) / 8);
   SortPlan* plan = c->sort_plan[which];
@@ -1481,7 +1606,7 @@ static int own_sort(vbx_ctx* c, int which, KeyT* keys_a, uint32_t* vals_a, KeyT*
   const uint32_t tiles_cap = c->sort_tiles_cap[which];
   VBX_CUDA(c, cudaMemsetAsync(plan, 0, sizeof(SortPlan), s));
   const unsigned int grid = std::min<uint32_t>(tiles_cap, 148 * 4);
-  k_sort_prepare<KeyT><<<grid, kSortThreads, 0, s>>>(keys_a, d_n, n_fixed, passes, plan, status, tiles_cap);
+  k_sort_prepare<KeyT><<<grid, kSortThreads, 0, s>>>(keys_a, d_n, n_fixed, passes, d_key_bits, plan, status, tiles_cap);
   for (int p = 0; p < passes; ++p) {
     k_sort_pass<KeyT><<<grid, kSortThreads, 0, s>>>(p, keys_a, vals_a, keys_b, vals_b, plan, status, tiles_cap);
   }
@@ -1513,9 +1638,10 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
   if (P.kind == VBX_MERGED) {
     KeyT* k0 = reinterpret_cast<KeyT*>(c->pkeys[0]);
     KeyT* k1 = reinterpret_cast<KeyT*>(c->pkeys[1]);
+    k_point_bounds<<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, c->first_bits, c->d_state);
     k_point_keys<KeyT><<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, k0, c->pvals[0], c->d_state);
     mk.mark(0);
-    const int end_bit = P.wide_keys ? 64 : 3 * P.key_bits + 1;
+    const int end_bit = 8 * (int)sizeof(KeyT);  // the bits in use are known on the device only (ScanState::key_bits)
     if (c->use_cub) {
       cub::DoubleBuffer<KeyT> kb(k0, k1);
       cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
@@ -1524,18 +1650,27 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
       keys = kb.Current();
       vals = vb.Current();
     } else {
-      if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, end_bit, launches)) return rc;
+      if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, end_bit, launches,
+                                  &c->d_state->key_bits)) {
+        return rc;
+      }
       k_sort_to_a<KeyT><<<148, 256, 0, s>>>(k0, c->pvals[0], k1, c->pvals[1], c->sort_plan[0]);
       keys = k0;
       vals = c->pvals[0];
     }
     mk.mark(1);
-    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(n, P.slot_lo, P.slot_hi, keys, c->ray_list, c->cnt,
-                                                               c->d_state);
+    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(P, keys, vals, c->order_inv, c->head_list, c->first_bits,
+                                                               c->cnt, c->d_state);
+    // the reference's bundle order: ray_list[rank] = head (vbx_order.cuh)
+    k_bundle_order<KeyT><<<1, kOrderThreads, c->order_smem_bytes, s>>>(P, c->rehash, keys, vals, c->order_inv, c->head_list,
+                                                                       c->first_bits, c->order_scratch,
+                                                                       (uint32_t)(c->order_smem_bytes / 4), c->ray_list,
+                                                                       c->d_state);
+    mk.mark(12);
     k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_a, c->ray_c,
                                            c->cnt, c->d_state);
     mk.mark(8);
-    *launches += c->use_cub ? 4 + (end_bit + 7) / 8 : 4;
+    *launches += c->use_cub ? 6 + (end_bit + 7) / 8 : 6;
     if (!P.single_walk) {
       // the bundle count is only known on the device: launch for the worst case (every
       // point its own bundle); surplus threads exit on the first load
@@ -1567,7 +1702,7 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
   return VBX_OK;
 }
 
-// update-record sort + the two apply kernels (shared by the single-GPU and the sharded path)
+// update-record sort + the apply kernels
 static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K, uint32_t n_touched, Marks& mk,
                           uint64_t* launches) {
   cudaStream_t s = c->stream;
@@ -1732,25 +1867,8 @@ static void fill_params(vbx_ctx* c, int kind, const float q[4], const float t[3]
     }
   }
   P.set_epoch = c->set_epoch;
-  // compact bundle keys: every non-clearing point lies within max_ray_length of the sensor,
-  // so its voxel is within key_radius voxels of the origin's voxel on every axis
-  {
-    const I3 ov = grid_index(P.origin, P.voxel_size_inv);
-    P.ovx = ov.x;
-    P.ovy = ov.y;
-    P.ovz = ov.z;
-    const double r = (double)cfg.max_ray_length_m * (double)c->voxel_size_inv;
-    P.key_radius = (r < 2.0e5) ? (int)std::ceil(r) + 3 : (1 << 20);
-    // ... widened to what still fits a 31-bit key (10 bits per axis: +-511 voxels), so that
-    // clearing points up to 511 voxels away never need the full-width fallback
-    if (P.key_radius < 511) P.key_radius = 511;
-    P.key_bits = bits_for((uint64_t)(2 * (int64_t)P.key_radius));
-    P.wide_keys = (3 * P.key_bits + 1 > 32 || c->force_wide_keys) ? 1 : 0;
-  }
-
-  P.slot_lo = 0;
-  P.slot_hi = n;
-  P.shard = 0;
+  P.own_world = c->opt.world_size > 1 ? c->opt.world_size : 1;
+  P.own_rank = c->opt.rank;
   P.emit_lo = 0;
   P.emit_hi = 0xffffffffu;
   P.emit_base = 0;
@@ -1788,93 +1906,55 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   if (cfg.integration_order_mode == 1) {
     // SortedThreadSafeIndex: ascending |p|^2 (stable here; std::sort leaves ties unspecified)
     k_sqnorm_keys<<<grid_for(n, TB), TB, 0, s>>>(n, d_xyz, c->pkeys[0], c->pvals[0]);
-    cub::DoubleBuffer<uint64_t> kb(c->pkeys[0], c->pkeys[1]);
-    cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
-    size_t tmp = c->cub_tmp_bytes;
-    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, 64, s));
-    VBX_CUDA(c, cudaMemcpyAsync(c->order, vb.Current(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    if (int rc = own_sort<uint64_t>(c, 0, c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], nullptr, n, 64, &launches)) {
+      return rc;
+    }
+    k_sort_to_a<uint64_t><<<148, 256, 0, s>>>(c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], c->sort_plan[0]);
+    VBX_CUDA(c, cudaMemcpyAsync(c->order, c->pvals[0], n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    k_invert_order<<<grid_for(n, TB), TB, 0, s>>>(n, c->order, c->order_inv);
     order = c->order;
-    launches += 11;
+    launches += 3;
   }
 
-  uint32_t new_blocks_first_attempt = 0, chunk_blocks_before = 0;
+  uint32_t chunk_blocks_before = 0;
   bool chunked = false;
-  const uint32_t* keys32 = nullptr;
   const uint64_t* keys64 = nullptr;
   unsigned long long K = 0;
   uint32_t n_touched = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if (P.wide_keys) {
-      if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
-    } else {
-      if (int rc = front_half<uint32_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys32)) return rc;
+  if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
+  if (c->use_cub) {
+    // the library sort needs K on the host: one stream synchronisation in the middle of the call
+    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+    c->n_blocks = c->h_state->n_blocks;
+    K = c->h_state->total_updates;
+    n_touched = c->h_state->n_touched;
+    if (K > 0) {
+      if (int rc = back_half<uint64_t>(c, P, keys64, K, n_touched, mk, &launches)) return rc;
     }
-    if (c->use_cub) {
-      // the library sort needs K on the host: one stream synchronisation in the middle of the call
-      VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-      VBX_CUDA(c, cudaStreamSynchronize(s));
-      if (int rc = check_state_errors(c, c->h_state->error)) return rc;
-      c->n_blocks = c->h_state->n_blocks;
-      if (!(c->h_state->error & kNeedWideKeys)) {
-        K = c->h_state->total_updates;
-        n_touched = c->h_state->n_touched;
-        if (K > 0) {
-          if (P.wide_keys) {
-            if (int rc = back_half<uint64_t>(c, P, keys64, K, n_touched, mk, &launches)) return rc;
-          } else {
-            if (int rc = back_half<uint32_t>(c, P, keys32, K, n_touched, mk, &launches)) return rc;
-          }
-        }
-        break;
-      }
-    } else {
-      // own sort: K stays on the device, the whole call is enqueued without a host round trip
-      if (P.wide_keys) {
-        if (int rc = back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches)) return rc;
-      } else {
-        if (int rc = back_half<uint32_t>(c, P, keys32, 0, 0, mk, &launches)) return rc;
-      }
+  } else {
+    // own sort: K stays on the device, the whole call is enqueued without a host round trip
+    if (int rc = back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches)) return rc;
+    VBX_CUDA(c, cudaEventRecord(c->ev1, s));
+    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+    VBX_CUDA(c, cudaStreamSynchronize(s));
+    if (c->h_state->error == kErrUpdatesFull) {
+      // More update records than one pass holds.  Nothing was emitted or applied; the per-ray
+      // tables, counts and offsets of the front half stand.  Apply the call in passes over
+      // contiguous ray-slot ranges: every voxel still sees its updates in ray-rank order, so
+      // the result is the one-pass result bit for bit.
+      chunk_blocks_before = c->n_blocks;
+      if (int rc = apply_in_passes<uint64_t>(c, P, keys64, mk, &launches)) return rc;
+      chunked = true;
       VBX_CUDA(c, cudaEventRecord(c->ev1, s));
       VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
       VBX_CUDA(c, cudaStreamSynchronize(s));
-      if (c->h_state->error == kErrUpdatesFull) {
-        // More update records than one pass holds.  Nothing was emitted or applied; the per-ray
-        // tables, counts and offsets of the front half stand.  Apply the call in passes over
-        // contiguous ray-slot ranges: every voxel still sees its updates in ray-rank order, so
-        // the result is the one-pass result bit for bit.
-        chunk_blocks_before = c->n_blocks;
-        if (P.wide_keys) {
-          if (int rc = apply_in_passes<uint64_t>(c, P, keys64, mk, &launches)) return rc;
-        } else {
-          if (int rc = apply_in_passes<uint32_t>(c, P, keys32, mk, &launches)) return rc;
-        }
-        chunked = true;
-        VBX_CUDA(c, cudaEventRecord(c->ev1, s));
-        VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-        VBX_CUDA(c, cudaStreamSynchronize(s));
-      }
-      {
-        // (a call that must be redone with wide keys is redone first; its record count is judged then)
-        uint32_t err = c->h_state->error;
-        if (err & kNeedWideKeys) err &= ~kErrUpdatesFull;
-        if (int rc = check_state_errors(c, err)) return rc;
-      }
-      c->n_blocks = c->h_state->n_blocks;
-      if (!(c->h_state->error & kNeedWideKeys)) {
-        K = c->h_state->total_found;
-        n_touched = c->h_state->n_touched;
-        break;
-      }
     }
-    // A clearing point landed outside the compact key range.  The rays cast so far are
-    // a correct SUBSET of the call's rays (block allocation is monotone), so keep the
-    // blocks they created and redo the call with full-width keys under a fresh call id
-    // (touch marks restart).  Nothing was applied: k_assign zeroes K for such a call.
-    new_blocks_first_attempt = c->h_state->n_new;
-    VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
-    c->epoch += 1;
-    P.epoch = c->epoch;
-    P.wide_keys = 1;
+    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
+    c->n_blocks = c->h_state->n_blocks;
+    K = c->h_state->total_found;
+    n_touched = c->h_state->n_touched;
   }
   VBX_CUDA(c, cudaEventRecord(c->ev1, s));
   VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
@@ -1888,11 +1968,11 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   c->counters[2] = K;
   c->counters[3] = c->h_state->n_voxels;
   c->counters[4] = n_touched;
-  c->counters[5] = chunked ? (uint64_t)(c->n_blocks - chunk_blocks_before)
-                           : (uint64_t)c->h_state->n_new + new_blocks_first_attempt;
+  c->counters[5] = chunked ? (uint64_t)(c->n_blocks - chunk_blocks_before) : (uint64_t)c->h_state->n_new;
   c->counters[11] = chunked ? c->last_passes : 1;
   c->counters[9] = c->h_state->n_refold;
   c->counters[10] = c->h_state->refold_members;
+  c->counters[12] = c->h_state->key_bits;
   c->counters[6] = (kind == VBX_MERGED) ? c->h_state->n_valid_points
                                         : (uint64_t)c->h_state->n_rays + c->h_state->n_clear_rays;
   c->counters[7] = launches;
@@ -1939,6 +2019,10 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   if (S.in_flight) {  // bounded run-ahead: wait for the scan that used this hand-off set
     VBX_CUDA(c, cudaEventSynchronize(S.back_done));
     harvest_async(c, S);
+    if (S.redo) {
+      // it (and every scan queued behind it) did not run its back half: redo them now, in order
+      if (int rc = drain_async(c)) return rc;
+    }
   }
   select_set(c, k);
   select_lane(c, (int)(c->async_seq % vbx_ctx::kLanes));
@@ -1968,14 +2052,12 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     dx = S.d_xyz;
     dr = S.d_rgba;
   }
-  const uint32_t* keys32 = nullptr;
   const uint64_t* keys64 = nullptr;
   if (rc == VBX_OK && cudaMemsetAsync(S.d_state, 0, sizeof(ScanState), F.stream) != cudaSuccess) {
     rc = fail(c, VBX_E_CUDA, "cudaMemsetAsync");
   }
   if (rc == VBX_OK) {
-    rc = P.wide_keys ? front_half<uint64_t>(c, P, dx, dr, nullptr, mk, &launches, &keys64)
-                     : front_half<uint32_t>(c, P, dx, dr, nullptr, mk, &launches, &keys32);
+    rc = front_half<uint64_t>(c, P, dx, dr, nullptr, mk, &launches, &keys64);
   }
   if (rc == VBX_OK && cudaEventRecord(S.front_done, F.stream) != cudaSuccess) rc = fail(c, VBX_E_CUDA, "cudaEventRecord");
   // ---- walk + record sort on stream_e, apply on the main stream
@@ -1989,8 +2071,15 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     rc = fail(c, VBX_E_CUDA, "cudaStreamWaitEvent");
   }
   if (rc == VBX_OK) {
-    rc = P.wide_keys ? back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches)
-                     : back_half<uint32_t>(c, P, keys32, 0, 0, mk, &launches);
+    // Scans run their map-touching stages in submission order on this stream.  A scan that cannot be
+    // applied asynchronously (more update records than one pass holds) raises the context's hold
+    // flag here; every scan queued behind it then skips its back half, and the host redoes all of
+    // them synchronously, in order, from the retained inputs (recover_async, vbx_capi.cu).
+    if (rc == VBX_OK) {
+      k_back_begin<<<1, 1, 0, c->stream_e>>>(S.d_state, c->d_hold);
+      launches += 1;
+      rc = back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches);
+    }
   }
   if (rc == VBX_OK && (cudaMemcpyAsync(S.h_state, S.d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->stream_main) != cudaSuccess ||
                        cudaEventRecord(S.back_done, c->stream_main) != cudaSuccess)) {
@@ -2004,6 +2093,14 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   S.in_flight = true;
   S.kind = kind;
   S.launches = launches;
+  S.seq = c->async_seq;
+  S.redo = false;
+  std::memcpy(S.q, q, sizeof(S.q));
+  std::memcpy(S.t, t, sizeof(S.t));
+  S.n = n64;
+  S.freespace = freespace;
+  S.in_xyz = dx;   // (the set's private copy of a host cloud, or the caller's device buffers)
+  S.in_rgba = dr;
   c->launches += launches;
   c->async_seq += 1;
   if (c->deferred_rc) {
@@ -2015,178 +2112,47 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   return VBX_OK;
 }
 
-// ------------------------------------------------------------- ray-range sharding, host side
-static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
-
-int shard_layout_for(vbx_ctx* c, uint64_t n, uint64_t record_capacity, vbx_shard_layout* out) {
-  const uint64_t world = (uint64_t)c->opt.world_size;
-  if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
-  if (record_capacity == 0 || record_capacity * world > c->max_updates) {
-    return fail(c, VBX_E_CAPACITY, "record_capacity * world_size exceeds max_updates_per_pass");
+// ------------------------------------------------------------------ test hooks
+// k_bundle_order's core on caller-supplied hashes (element e = e-th inserted key, hash h_in[e]):
+// out[p] = the element at iteration position p.  tests/test_order_gpu.py compares it with a real
+// std::unordered_map.
+__global__ void __launch_bounds__(kOrderThreads)
+k_debug_order(RehashSchedule rs, const uint32_t* __restrict__ h_in, uint32_t B, OrderScratch g, uint32_t smem_words,
+              int force_global, uint32_t* __restrict__ out) {
+  extern __shared__ uint32_t order_smem[];
+  __shared__ uint32_t warp_sums[33];
+  uint32_t n_final = 1;
+  for (int k = 0; k < rs.count && rs.m[k] < B; ++k) n_final = rs.n[k];
+  uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *A = g.A, *bhead = g.bhead;
+  if (!force_global && 5u * B + n_final <= smem_words) {
+    h = order_smem;
+    tau = h + B;
+    tau2 = tau + B;
+    next = tau2 + B;
+    A = next + B;
+    bhead = A + B;
   }
-  out->record_capacity = record_capacity;
-  out->slice = (n + world - 1) / world;
-  out->off_ray_a = 0;
-  out->off_ray_c = out->slice * 16;
-  out->off_records = round_up(out->slice * 24, 256);
-  out->pack_bytes = out->off_records + record_capacity * 16;
-  return VBX_OK;
+  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) h[e] = h_in[e];
+  __syncthreads();
+  const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, A, bhead, warp_sums);
+  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) out[pos[e]] = e;
 }
 
-int shard_front(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz, const uint8_t* d_rgba,
-                uint64_t n64, int freespace, const vbx_shard_layout* lay, void* d_pack, uint64_t* count_out) {
-  if (kind != VBX_SIMPLE && kind != VBX_MERGED) {
-    return fail(c, VBX_E_INVALID, "ray-range sharding supports the simple and merged integrators");
-  }
-  if (n64 > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
-  const uint32_t n = (uint32_t)n64;
+int debug_bundle_order(vbx_ctx* c, const uint32_t* hashes, uint32_t n, int force_global, uint32_t* out) {
   cudaStream_t s = c->stream;
-  uint64_t launches = 0;
-  ScanParams P;
-  fill_params(c, kind, q, t, n, freespace, P);
-  P.shard = 1;
-  P.slot_lo = (uint32_t)std::min<uint64_t>((uint64_t)c->opt.rank * lay->slice, n);
-  P.slot_hi = (uint32_t)std::min<uint64_t>((uint64_t)(c->opt.rank + 1) * lay->slice, n);
-  *count_out = 0;
-  VBX_CUDA(c, cudaEventRecord(c->ev0, s));
-  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
-  if (n == 0) {
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    return VBX_OK;
-  }
-  Marks mk;
-  mk.c = c;
-  mk.s = s;
-  mk.begin();
-  const uint32_t* order = nullptr;
-  if (c->cfg.integration_order_mode == 1) {
-    k_sqnorm_keys<<<grid_for(n, 256), 256, 0, s>>>(n, d_xyz, c->pkeys[0], c->pvals[0]);
-    cub::DoubleBuffer<uint64_t> kb(c->pkeys[0], c->pkeys[1]);
-    cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
-    size_t tmp = c->cub_tmp_bytes;
-    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, 64, s));
-    VBX_CUDA(c, cudaMemcpyAsync(c->order, vb.Current(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    order = c->order;
-  }
-  const uint32_t* keys32 = nullptr;
-  const uint64_t* keys64 = nullptr;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if (P.wide_keys) {
-      if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
-    } else {
-      if (int rc = front_half<uint32_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys32)) return rc;
-    }
-    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
-    if (!(c->h_state->error & kNeedWideKeys)) break;
-    VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
-    P.wide_keys = 1;
-  }
-  const unsigned long long K = c->h_state->total_updates;
-  if (K > lay->record_capacity) return fail(c, VBX_E_CAPACITY, "this rank's update records exceed record_capacity");
-  char* pack = static_cast<char*>(d_pack);
-  if (K > 0) {
-    uint4* grec = reinterpret_cast<uint4*>(pack + lay->off_records);
-    if (P.wide_keys) {
-      k_rays_emit_global<uint64_t><<<grid_for(n, 128), 128, 0, s>>>(P, keys64, c->ray_list, c->ray_p, c->cnt, c->off,
-                                                                     grec, lay->record_capacity, c->d_state);
-    } else {
-      k_rays_emit_global<uint32_t><<<grid_for(n, 128), 128, 0, s>>>(P, keys32, c->ray_list, c->ray_p, c->cnt, c->off,
-                                                                     grec, lay->record_capacity, c->d_state);
-    }
-    launches += 1;
-  }
-  const uint32_t len = P.slot_hi - P.slot_lo;
-  if (len > 0) {
-    VBX_CUDA(c, cudaMemcpyAsync(pack + lay->off_ray_a, c->ray_a + P.slot_lo, (size_t)len * sizeof(float4),
-                                cudaMemcpyDeviceToDevice, s));
-    VBX_CUDA(c, cudaMemcpyAsync(pack + lay->off_ray_c, c->ray_c + P.slot_lo, (size_t)len * sizeof(uint2),
-                                cudaMemcpyDeviceToDevice, s));
-  }
-  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-  VBX_CUDA(c, cudaStreamSynchronize(s));
-  if (int rc = check_state_errors(c, c->h_state->error)) return rc;
-  mk.collect();
-  c->launches += launches;
-  c->shard_front_counters[0] = c->h_state->n_rays;
-  c->shard_front_counters[1] = c->h_state->n_clear_rays;
-  c->shard_front_counters[2] = c->h_state->n_valid_points;
-  c->shard_front_counters[3] = launches;
-  *count_out = K;
-  return VBX_OK;
-}
-
-int shard_back(vbx_ctx* c, int kind, const float q[4], const float t[3], uint64_t n64, const vbx_shard_layout* lay,
-               const void* d_gathered, uint64_t pack_stride, const uint64_t* counts) {
-  const int world = c->opt.world_size;
-  if (world > 8) return fail(c, VBX_E_INVALID, "at most 8 ranks");
-  const uint32_t n = (uint32_t)n64;
-  cudaStream_t s = c->stream;
-  uint64_t launches = 0;
-  std::memset(c->counters, 0, sizeof(c->counters));
-  ScanParams P;
-  fill_params(c, kind, q, t, n, 0, P);
-  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
-  ShardSegments seg;
-  std::memset(&seg, 0, sizeof(seg));
-  seg.world = world;
-  const char* base = static_cast<const char*>(d_gathered);
-  for (int r = 0; r < world; ++r) {
-    const char* pack = base + (size_t)r * pack_stride;
-    seg.rec[r] = reinterpret_cast<const uint4*>(pack + lay->off_records);
-    if (counts[r] > lay->record_capacity || lay->off_records + counts[r] * 16 > pack_stride) {
-      return fail(c, VBX_E_INVALID, "count exceeds the gathered pack");
-    }
-    seg.start[r + 1] = seg.start[r] + counts[r];
-    const uint64_t lo = std::min<uint64_t>((uint64_t)r * lay->slice, n), hi = std::min<uint64_t>((uint64_t)(r + 1) * lay->slice, n);
-    if (hi > lo) {
-      VBX_CUDA(c, cudaMemcpyAsync(c->ray_a + lo, pack + lay->off_ray_a, (hi - lo) * sizeof(float4),
-                                  cudaMemcpyDeviceToDevice, s));
-      VBX_CUDA(c, cudaMemcpyAsync(c->ray_c + lo, pack + lay->off_ray_c, (hi - lo) * sizeof(uint2),
-                                  cudaMemcpyDeviceToDevice, s));
-    }
-  }
-  const unsigned long long K = seg.start[world];
-  if (K > c->max_updates) return fail(c, VBX_E_CAPACITY, "gathered update records exceed max_updates_per_pass");
-  Marks mk;
-  mk.c = c;
-  mk.s = s;
-  mk.begin();
-  uint32_t n_touched = 0;
-  if (K > 0) {
-    uint32_t* hp_of = c->cvals[1];
-    k_localize_blocks<<<grid_for(K, 256), 256, 0, s>>>(seg, c->tab, c->L, P.epoch, hp_of, c->d_state);
-    k_set_total<<<1, 1, 0, s>>>(nullptr, 0, c->max_updates, c->d_state, K);
-    k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->d_nblocks + c->nb_cur, c->d_nblocks + (c->nb_cur ^ 1),
-                                                            c->d_state);
-  c->nb_cur ^= 1;
-    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
-    c->n_blocks = c->h_state->n_blocks;
-    n_touched = c->h_state->n_touched;
-    k_localize_keys<<<grid_for(K, 256), 256, 0, s>>>(seg, c->tab, c->L, hp_of, c->ckeys[0], c->cvals[0]);
-    mk.mark(5);
-    launches += 3;
-    if (int rc = sort_and_apply(c, P, K, n_touched, mk, &launches)) return rc;
-  }
-  VBX_CUDA(c, cudaEventRecord(c->ev1, s));
-  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
+  if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "debug_bundle_order: n > max_points_per_scan");
+  if (n == 0) return VBX_OK;
+  VBX_CUDA(c, cudaFuncSetAttribute(k_debug_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->order_smem_bytes));
+  VBX_CUDA(c, cudaMemcpyAsync(c->pvals[0], hashes, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  k_debug_order<<<1, kOrderThreads, c->order_smem_bytes, s>>>(c->rehash, c->pvals[0], n, c->order_scratch,
+                                                               (uint32_t)(c->order_smem_bytes / 4), force_global,
+                                                               c->pvals[1]);
+  VBX_CUDA(c, cudaMemcpyAsync(out, c->pvals[1], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   VBX_CUDA(c, cudaGetLastError());
-  VBX_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-  mk.collect();
-  c->launches += launches;
-  c->counters[2] = K;
-  c->counters[3] = c->h_state->n_voxels;
-  c->counters[4] = n_touched;
-  c->counters[5] = c->h_state->n_new;
-  c->counters[7] = launches + c->shard_front_counters[3];
   return VBX_OK;
 }
 
-// ------------------------------------------------------------------ test hooks
 __global__ void k_iota(uint32_t* v, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
 }

@@ -1,144 +1,130 @@
-"""Ray-range sharding of one scan over the GPUs of a box (BASELINE.json north_star, SURVEY.md
-section 8e): one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the one
-exchange step, the C-ABI's vbx_shard_front / vbx_shard_back for the device work.
+"""One map over the GPUs of a box: block-ownership sharding (BASELINE.json north_star, SURVEY.md
+section 8e; DESIGN.md "multi-GPU").  One process per GPU, torch.distributed for the plumbing.
 
-Every rank keeps a full replica of the map and is handed the full cloud.  All ranks bundle the
-whole cloud (so they agree on the bundles), then rank r merges and ray-casts only the ray slots
-[r*S, (r+1)*S), S = ceil(n / world).  The ranks all-gather their update records (16 B each:
-global voxel key + ray slot) and their slices of the per-ray tables; every rank then applies ALL
-records in ray order to its replica.  The per-voxel update order is the single-GPU order, so the
-replicas and the single-GPU map are bit-identical (tests/test_sharded_gpu.py).
+Every rank is handed EVERY scan and runs the ordinary integrators; the engine (created with
+EngineOptions(rank=r, world_size=W)) applies only the voxel updates of the blocks rank r owns and
+creates only those blocks.  Bundling, the reference's bundle order, the merge and the ray walk are
+the same deterministic computation on every rank, so the ranks need no exchange while integrating:
+the union of the W shards is the single-GPU map bit for bit (tests/test_sharded_gpu.py), every voxel
+keeping the reference's one-thread update order.
 
-The reference has no multi-device path; its closest semantic model is the layer merge of
-voxblox/src/utils/voxel_utils.cc:9-22, which is associative only because it averages -- the
-integrator's clamp-after-every-update (tsdf_integrator.cc:205-208) is not, which is why the
-exchange carries update records rather than partial sums.
+Why no reduce: the reference's closest multi-map model is the layer merge of
+voxblox/src/utils/voxel_utils.cc:9-22, which is associative only because it averages; the
+integrator's clamp after every update (tsdf_integrator.cc:205-208) is not, so partial TSDF sums
+from different ray ranges cannot be combined into the reference's result.  Ownership sharding keeps
+every voxel's update chain on one GPU instead.
+
+This module holds the host-side logic: the ownership function (mirrors vbx_block_owner), gathering
+the shards into one block dictionary, and keeping read-only replicas of the other ranks' dirty blocks
+(`sync_replicas`, one all-gather of the blocks dirtied since the last call).
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-from .api import TsdfIntegratorBase, VoxbloxError, _as_pose
-
-
-class ShardLayout(C.Structure):
-    """vbx_shard_layout"""
-    _fields_ = [("record_capacity", C.c_uint64), ("slice", C.c_uint64), ("pack_bytes", C.c_uint64),
-                ("off_ray_a", C.c_uint64), ("off_ray_c", C.c_uint64), ("off_records", C.c_uint64)]
-
-
-RECORD_BYTES = 16
-RECORD_GRANULE = 4096  # the exchanged prefix grows in steps of 4096 records
+from .api import EngineOptions, Layer, VoxbloxError
 
 
 # ------------------------------------------------------------------ host logic (CPU-testable)
-def slot_range(n: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous ray-slot range of a rank: [rank*S, (rank+1)*S) clipped to n, S = ceil(n/world)."""
-    s = (n + world - 1) // world
-    return min(rank * s, n), min((rank + 1) * s, n)
+def block_owner(index, world: int) -> np.ndarray:
+    """vbx_block_owner: rank owning block (bx, by, bz) = (bx + 2 by + 4 bz) mod world (non-negative)."""
+    idx = np.asarray(index, dtype=np.int64).reshape(-1, 3)
+    return ((idx[:, 0] + 2 * idx[:, 1] + 4 * idx[:, 2]) % int(world)).astype(np.int32)
 
 
-def exchange_bytes(off_records: int, counts: Sequence[int]) -> int:
-    """Bytes of each rank's pack that must travel: the per-ray tables plus the longest record
-    list, rounded up to the record granule (all ranks must send the same length)."""
-    m = max(int(c) for c in counts) if len(counts) else 0
-    m = (m + RECORD_GRANULE - 1) // RECORD_GRANULE * RECORD_GRANULE
-    return int(off_records) + RECORD_BYTES * m
+def shard_options(rank: int, world: int, **kw) -> EngineOptions:
+    """EngineOptions for rank `rank` of a `world`-way sharded map."""
+    if not 0 <= rank < world:
+        raise VoxbloxError("rank outside [0, world_size)")
+    return EngineOptions(rank=rank, world_size=world, **kw)
 
 
-def record_prefix(counts: Sequence[int]) -> List[int]:
-    """Start of every rank's records in the global (ray-ordered) record sequence."""
-    out = [0]
-    for c in counts:
-        out.append(out[-1] + int(c))
-    return out
+def pack_blocks(indices: np.ndarray, voxels: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """(M, 3) int32 indices and (M, vps^3) voxel records -> two contiguous byte arrays."""
+    idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+    vox = np.ascontiguousarray(voxels)
+    return idx.view(np.uint8).reshape(-1), vox.view(np.uint8).reshape(-1)
 
 
-def gather_counts(count: int, group=None):
-    """All ranks' record counts (one small all-gather; gloo on CPU, NCCL on GPU)."""
+def all_gather_blocks(indices: np.ndarray, voxels: np.ndarray, group=None):
+    """All ranks' (indices, voxels), rank after rank.  Variable block counts per rank: the counts
+    travel first, then one padded all-gather (gloo on CPU tensors, NCCL on CUDA tensors)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    mine = torch.tensor([int(count)], dtype=torch.int64, device=dev)
-    out = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(out, mine, group=group)
-    return [int(v) for v in out.cpu().tolist()]
+    nccl = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    idx_b, vox_b = pack_blocks(indices, voxels)
+    m = int(np.asarray(indices).reshape(-1, 3).shape[0])
+    per_block = int(vox_b.size // m) if m else int(voxels.dtype.itemsize * (voxels.shape[-1] if voxels.ndim > 1 else 0))
+    meta = torch.tensor([m, per_block], dtype=torch.int64, device=dev)
+    metas = torch.zeros(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas = metas.cpu().numpy().reshape(world, 2)
+    counts = metas[:, 0]
+    per_block = int(metas[:, 1].max())
+    cap = int(counts.max())
+    out_idx, out_vox = [], []
+    if cap == 0:
+        return np.zeros((0, 3), np.int32), np.zeros((0,), np.uint8), counts
+    send = torch.zeros(cap * (12 + per_block), dtype=torch.uint8, device=dev)
+    if m:
+        send[: m * 12] = torch.from_numpy(idx_b.copy()).to(dev)
+        send[cap * 12: cap * 12 + m * per_block] = torch.from_numpy(vox_b.copy()).to(dev)
+    recv = torch.zeros(world * send.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy().reshape(world, -1)
+    for r in range(world):
+        c = int(counts[r])
+        out_idx.append(recv[r, : c * 12].view(np.int32).reshape(c, 3))
+        out_vox.append(recv[r, cap * 12: cap * 12 + c * per_block].reshape(c, per_block))
+    return np.concatenate(out_idx), np.concatenate(out_vox), counts
 
 
-def gather_packs(pack, nbytes: int, gathered, group=None):
-    """All-gather the first nbytes of every rank's pack into gathered[:world * nbytes]."""
-    import torch.distributed as dist
+class ShardedLayer:
+    """The block-sharded map as its callers see it.
 
-    world = dist.get_world_size(group)
-    dist.all_gather_into_tensor(gathered[: world * nbytes], pack[:nbytes], group=group)
-    return gathered[: world * nbytes]
+    `layer` is this rank's shard (a Layer whose engine was created with shard_options)."""
 
-
-# ------------------------------------------------------------------------------ device path
-class ShardedTsdfIntegrator:
-    """integratePointCloud for one scan shared by all ranks of a torch.distributed group.
-
-    Wraps a Simple or Merged integrator created on a Layer whose EngineOptions carry this
-    process' rank and world_size."""
-
-    def __init__(self, integrator: TsdfIntegratorBase, record_capacity: int = 1 << 21, group=None):
-        import torch
+    def __init__(self, layer: Layer, group=None):
         import torch.distributed as dist
 
-        if integrator.kind not in (1, 2):
-            raise VoxbloxError("ray-range sharding supports the simple and merged integrators")
-        self.integ = integrator
-        self.ctx = integrator._ctx
+        self.layer = layer
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.record_capacity = int(record_capacity)
-        self.lib = self.ctx.lib
-        self.lib.vbx_shard_layout_for.restype = C.c_int
-        self.lib.vbx_shard_layout_for.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ShardLayout)]
-        self.lib.vbx_shard_front.restype = C.c_int
-        self.lib.vbx_shard_front.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                             C.c_uint64, C.c_int, C.POINTER(ShardLayout), C.c_void_p,
-                                             C.POINTER(C.c_uint64)]
-        self.lib.vbx_shard_back.restype = C.c_int
-        self.lib.vbx_shard_back.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
-                                            C.POINTER(ShardLayout), C.c_void_p, C.c_uint64, C.c_void_p]
-        self._torch = torch
-        self._pack = None
-        self._gathered = None
-        self.last_exchange_bytes = 0
 
-    def _buffers(self, lay: ShardLayout):
-        torch = self._torch
-        if self._pack is None or self._pack.numel() < lay.pack_bytes:
-            dev = torch.device("cuda", torch.cuda.current_device())
-            self._pack = torch.empty(int(lay.pack_bytes), dtype=torch.uint8, device=dev)
-            self._gathered = torch.empty(int(lay.pack_bytes) * self.world, dtype=torch.uint8, device=dev)
-        return self._pack, self._gathered
+    def owned(self, indices) -> np.ndarray:
+        return block_owner(indices, self.world) == self.rank
 
-    def integratePointCloudDevice(self, T_G_C, d_xyz: int, d_rgba: int, n: int, freespace_points: bool = False):
-        q, t = _as_pose(T_G_C)
-        lay = ShardLayout()
-        self.ctx.check(self.lib.vbx_shard_layout_for(self.ctx.handle, n, self.record_capacity, C.byref(lay)),
-                       "vbx_shard_layout_for")
-        pack, gathered = self._buffers(lay)
-        count = C.c_uint64(0)
-        self.ctx.check(self.lib.vbx_shard_front(self.ctx.handle, self.integ.kind, q.ctypes.data, t.ctypes.data,
-                                                d_xyz, d_rgba, n, int(bool(freespace_points)), C.byref(lay),
-                                                pack.data_ptr(), C.byref(count)), "vbx_shard_front")
-        # vbx_shard_front returns after its stream has drained, so the pack is complete
-        counts = gather_counts(int(count.value), self.group)
-        nbytes = exchange_bytes(int(lay.off_records), counts)
-        got = gather_packs(pack, nbytes, gathered, self.group)
-        self._torch.cuda.current_stream().synchronize()
-        self.last_exchange_bytes = nbytes * self.world
-        carr = np.asarray(counts, dtype=np.uint64)
-        self.ctx.check(self.lib.vbx_shard_back(self.ctx.handle, self.integ.kind, q.ctypes.data, t.ctypes.data, n,
-                                               C.byref(lay), got.data_ptr(), nbytes, carr.ctypes.data),
-                       "vbx_shard_back")
-        return counts
+    def gather(self) -> Dict[Tuple[int, int, int], np.ndarray]:
+        """Every block of the map (all shards), as {index: voxels} on every rank."""
+        idx = self.layer.getAllAllocatedBlocks()
+        vox, _ = self.layer.getBlocks(idx)
+        if len(idx):
+            mine = self.owned(idx)
+            idx, vox = idx[mine], vox[mine]
+        all_idx, all_vox, _ = all_gather_blocks(idx, vox, self.group)
+        dt = vox.dtype
+        return {tuple(int(v) for v in i): all_vox[k].view(dt) for k, i in enumerate(all_idx)}
+
+    def sync_replicas(self, updated_mask: int = 1) -> int:
+        """Make every rank's map a full replica for READING: all-gather the owned blocks dirtied since
+        the last call (Update::kMap bit by default, cleared on the owner) and upload the other ranks'
+        blocks as read-only copies (the integrators never touch blocks this rank does not own).
+        Returns the number of blocks received."""
+        idx, vox, _ = self.layer.mirrorUpdated(updated_mask, clear_mask=updated_mask)
+        if len(idx):
+            mine = self.owned(idx)
+            idx, vox = idx[mine], vox[mine]
+        all_idx, all_vox, counts = all_gather_blocks(idx, vox, self.group)
+        if not len(all_idx):
+            return 0
+        theirs = ~self.owned(all_idx)
+        if theirs.any():
+            self.layer.insertBlocks(all_idx[theirs], all_vox[theirs].view(vox.dtype).reshape(int(theirs.sum()), -1),
+                                    updated_bits=np.zeros(int(theirs.sum()), np.uint8))
+        return int(theirs.sum())
