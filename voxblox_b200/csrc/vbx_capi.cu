@@ -13,7 +13,6 @@ namespace vbx {
 
 int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], const float* d_xyz,
                      const uint8_t* d_rgba, uint64_t n, int freespace);
-size_t cub_temp_bytes(uint32_t max_points, uint64_t max_updates);
 int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
                uint32_t* vals_out);
 int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out);
@@ -128,6 +127,8 @@ void select_set(vbx_ctx* c, int k) {
   c->ray_a = S.ray_a;
   c->ray_c = S.ray_c;
   c->ray_list = S.ray_list;
+  c->head_list = S.head_list;
+  c->tab.touched_list = S.touched_list;
   c->cnt = S.cnt;
   c->off = S.off;
   c->d_state = S.d_state;
@@ -145,9 +146,12 @@ void select_set(vbx_ctx* c, int k) {
 
 void select_lane(vbx_ctx* c, int l) {
   const vbx_ctx::FrontLane& F = c->lane[l];
-  c->head_list = F.head_list;
+  c->big_list = F.big_list;
   c->first_bits = F.first_bits;
   c->order_scratch = F.order_scratch;
+  c->side_stream = F.side;
+  c->ev_fork = F.ev_fork;
+  c->ev_join = F.ev_join;
   c->pkeys[1] = F.pkeys1;
   c->pvals[0] = F.pvals[0];
   c->pvals[1] = F.pvals[1];
@@ -187,7 +191,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 }
 
 // k_bundle_order's tables for one front lane (vbx_order.cuh)
-int alloc_order_scratch(vbx_ctx* c, OrderScratch* g, uint32_t** head_list, uint32_t** first_bits) {
+int alloc_order_scratch(vbx_ctx* c, OrderScratch* g, uint32_t** big_list, uint32_t** first_bits) {
   const size_t np = c->max_points;
   std::memset(g, 0, sizeof(*g));
   g->cap = (uint32_t)np;
@@ -199,17 +203,18 @@ int alloc_order_scratch(vbx_ctx* c, OrderScratch* g, uint32_t** head_list, uint3
   VBX_CUDA(c, dmalloc(&g->tau, np));
   VBX_CUDA(c, dmalloc(&g->tau2, np));
   VBX_CUDA(c, dmalloc(&g->next, np));
+  VBX_CUDA(c, dmalloc(&g->bkt, np));
   VBX_CUDA(c, dmalloc(&g->A, np));
   VBX_CUDA(c, dmalloc(&g->bhead, (size_t)buckets));
   VBX_CUDA(c, dmalloc(&g->head_of, np));
   VBX_CUDA(c, dmalloc(&g->wp, np / 32 + 2));
-  VBX_CUDA(c, dmalloc(head_list, np));
+  VBX_CUDA(c, dmalloc(big_list, np / 256 + 2));
   VBX_CUDA(c, dmalloc(first_bits, 2 * (np / 32 + 2)));
   VBX_CUDA(c, cudaMemsetAsync(*first_bits, 0, 2 * (np / 32 + 2) * sizeof(uint32_t), c->stream_main));
   return VBX_OK;
 }
-void free_order_scratch(OrderScratch* g, uint32_t* head_list, uint32_t* first_bits) {
-  void* ptrs[] = {g->h, g->tau, g->tau2, g->next, g->A, g->bhead, g->head_of, g->wp, head_list, first_bits};
+void free_order_scratch(OrderScratch* g, uint32_t* big_list, uint32_t* first_bits) {
+  void* ptrs[] = {g->h, g->tau, g->tau2, g->next, g->bkt, g->A, g->bhead, g->head_of, g->wp, big_list, first_bits};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }
@@ -272,8 +277,9 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   c->max_updates = std::min<uint64_t>(o.max_updates_per_pass, 0x7fffffffull);
   int rb = 0;
   for (uint32_t v = o.max_blocks; v; v >>= 1) ++rb;
-  // an update record's key = (hash position, voxel in block) in 32 bits, 0xffffffff reserved
-  if (rb + 1 + 3 * c->L > 32 || (rb + 1 + 3 * c->L == 32 && (o.max_blocks & (o.max_blocks - 1)))) {
+  // an update record's key = (touched id, voxel in block) in 32 bits with 0xffffffff reserved: a single
+  // call may touch up to 2^(32 - 3L) - 1 blocks; the pool itself is only bounded by memory
+  if (rb > 30) {
     delete c;
     return VBX_E_INVALID;
   }
@@ -311,10 +317,12 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   t.max_blocks = o.max_blocks;
   CK(dmalloc(&t.hkeys, hcap));
   CK(dmalloc(&t.hslot, hcap));
-  CK(dmalloc(&t.htouch_epoch, hcap));
-  CK(dmalloc(&t.htouch_rank, hcap));
+  CK(dmalloc(&t.htouch, hcap));
   CK(dmalloc(&t.new_list, o.max_blocks));
-  CK(dmalloc(&t.touched_list, o.max_blocks));
+  // ids lost to first-touch races stay unused (vbx_hash.cuh); (id, voxel) must fit a 32-bit record key
+  t.touched_cap = (uint32_t)std::min<uint64_t>((uint64_t)o.max_blocks + 65536u, (0xffffffffull >> (3 * c->L)) - 1);
+  t.vox_per_block = c->vox_per_block;
+  CK(dmalloc(&t.touched_list, t.touched_cap));
   CK(dmalloc(&t.slot_key, o.max_blocks));
   CK(dmalloc(&t.slot_updated, o.max_blocks));
   CK(dmalloc(&t.slot_esdf_updated, o.max_blocks));
@@ -322,8 +330,7 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&t.tsdf, (size_t)o.max_blocks * c->vox_per_block));
   CK(cudaMemsetAsync(t.hkeys, 0xff, (size_t)hcap * sizeof(uint64_t), c->stream));
   CK(cudaMemsetAsync(t.hslot, 0xff, (size_t)hcap * sizeof(int32_t), c->stream));
-  CK(cudaMemsetAsync(t.htouch_epoch, 0, (size_t)hcap * sizeof(uint32_t), c->stream));
-  CK(cudaMemsetAsync(t.htouch_rank, 0, (size_t)hcap * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(t.htouch, 0, (size_t)hcap * sizeof(unsigned long long), c->stream));
   CK(cudaMemsetAsync(t.slot_updated, 0, o.max_blocks, c->stream));
   CK(cudaMemsetAsync(t.slot_esdf_updated, 0, o.max_blocks, c->stream));
   CK(cudaMemsetAsync(t.slot_has_esdf, 0, o.max_blocks, c->stream));
@@ -342,7 +349,13 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->order_inv, np));
   CK(dmalloc(&c->ray_list, np));
   if (int rc = init_bundle_order(c)) return rc;
-  if (int rc = alloc_order_scratch(c, &c->order_scratch, &c->head_list, &c->first_bits)) return rc;
+  CK(dmalloc(&c->head_list, np));
+  if (int rc = alloc_order_scratch(c, &c->order_scratch, &c->big_list, &c->first_bits)) return rc;
+  for (int l = 0; l < vbx_ctx::kLanes; ++l) {
+    CK(cudaStreamCreateWithPriority(&c->lane[l].side, cudaStreamNonBlocking, prio_lo));
+    CK(cudaEventCreateWithFlags(&c->lane[l].ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->lane[l].ev_join, cudaEventDisableTiming));
+  }
   CK(dmalloc(&c->long_list, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->long_end, (size_t)(c->max_updates / 32 + 1)));
   CK(dmalloc(&c->long_state, (size_t)(c->max_updates / 32 + 1)));
@@ -356,9 +369,7 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   CK(dmalloc(&c->cnt, np + 1));
   CK(dmalloc(&c->off, np + 1));
   {
-    // own sort / scan state; VBX_USE_CUB=1 selects the library sort (A/B measurements)
-    const char* env = std::getenv("VBX_USE_CUB");
-    c->use_cub = env && env[0] == '1';
+    // own sort / scan state
     c->sort_tiles_cap[0] = (uint32_t)((np + kSortTile - 1) / kSortTile);
     c->sort_tiles_cap[1] = (uint32_t)((c->max_updates + kSortTile - 1) / kSortTile);
     for (int i = 0; i < 2; ++i) {
@@ -368,8 +379,6 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     }
     CK(dmalloc(&c->scan_status, (np + 1) / kScanTile + 4));
   }
-  c->cub_tmp_bytes = cub_temp_bytes(c->max_points, c->max_updates);
-  CK(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
   CK(dmalloc(&c->set_start, 1u << 20));
   CK(dmalloc(&c->set_observed, 1u << 20));
   CK(cudaMemsetAsync(c->set_start, 0, sizeof(unsigned long long) << 20, c->stream));
@@ -388,6 +397,8 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     a.ray_a = c->ray_a;
     a.ray_c = c->ray_c;
     a.ray_list = c->ray_list;
+    a.head_list = c->head_list;
+    a.touched_list = c->tab.touched_list;
     a.cnt = c->cnt;
     a.off = c->off;
     a.d_state = c->d_state;
@@ -408,9 +419,10 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     f.sort_plan0 = c->sort_plan[0];
     f.sort_status0 = c->sort_status[0];
     f.scan_status = c->scan_status;
-    f.head_list = c->head_list;
+    f.big_list = c->big_list;
     f.first_bits = c->first_bits;
     f.order_scratch = c->order_scratch;
+    select_lane(c, 0);
   }
   CK(cudaStreamSynchronize(c->stream));
 #undef CK
@@ -443,7 +455,7 @@ int ensure_async(vbx_ctx* c) {
     CK(dmalloc(&F.sort_plan0, 1));
     CK(dmalloc(&F.sort_status0, (size_t)8 * c->sort_tiles_cap[0] * kRadix));
     CK(dmalloc(&F.scan_status, (np + 1) / kScanTile + 4));
-    if (int rc = alloc_order_scratch(c, &F.order_scratch, &F.head_list, &F.first_bits)) return rc;
+    if (int rc = alloc_order_scratch(c, &F.order_scratch, &F.big_list, &F.first_bits)) return rc;
   }
   for (int k = 0; k < vbx_ctx::kSets; ++k) {
     vbx_ctx::ScratchSet& S = c->set[k];
@@ -457,6 +469,8 @@ int ensure_async(vbx_ctx* c) {
     CK(dmalloc(&S.ray_a, np));
     CK(dmalloc(&S.ray_c, np));
     CK(dmalloc(&S.ray_list, np));
+    CK(dmalloc(&S.head_list, np));
+    CK(dmalloc(&S.touched_list, c->tab.touched_cap));
     CK(dmalloc(&S.cnt, np + 1));
     CK(dmalloc(&S.off, np + 1));
     CK(dmalloc(&S.d_state, 1));
@@ -498,12 +512,12 @@ void vbx_destroy(vbx_ctx* c) {
   esdf_destroy(c);
   mesh_destroy(c);
   Tables& t = c->tab;
-  void* ptrs[] = {t.hkeys,        t.hslot,       t.htouch_epoch, t.htouch_rank, t.new_list, t.touched_list,
+  void* ptrs[] = {t.hkeys,        t.hslot,       t.htouch, t.new_list, t.touched_list,
                   t.slot_key,     t.slot_updated, t.slot_esdf_updated, t.slot_has_esdf, t.tsdf, c->d_xyz,
                   c->d_rgba,      c->pkeys[0],   c->pkeys[1],    c->pvals[0],   c->pvals[1], c->ckeys[0],
                   c->ckeys[1],    c->cvals[0],   c->cvals[1],    c->order,      c->ray_p,    c->ray_c,
-                  c->cnt,         c->off,        c->cub_tmp,     c->set_start,  c->set_observed, c->d_state,
-                  c->ray_list,    c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
+                  c->cnt,         c->off,        c->set_start,  c->set_observed, c->d_state,
+                  c->ray_list,    c->head_list,  c->long_list,  c->ray_a,      c->sort_plan[0], c->sort_plan[1],
                   c->sort_status[0], c->sort_status[1], c->scan_status, c->long_end, c->long_state,
                   c->verify_run,  c->verify_start, c->rec_sdf, c->rec_w, c->d_nblocks, c->order_inv, c->d_hold};
   for (void* p : ptrs) {
@@ -516,7 +530,7 @@ void vbx_destroy(vbx_ctx* c) {
   for (int k = 0; k < vbx_ctx::kSets; ++k) {
     vbx_ctx::ScratchSet& S = c->set[k];
     if (k > 0) {
-      void* sp[] = {S.ray_p, S.ray_a, S.ray_c, S.ray_list, S.cnt, S.off, S.d_state, S.d_xyz, S.d_rgba, S.pkeys0,
+      void* sp[] = {S.ray_p, S.ray_a, S.ray_c, S.ray_list, S.head_list, S.touched_list, S.cnt, S.off, S.d_state, S.d_xyz, S.d_rgba, S.pkeys0,
                     S.ckeys[0], S.ckeys[1], S.cvals[0], S.cvals[1], S.sort_plan1, S.sort_status1};
       for (void* p : sp) {
         if (p) cudaFree(p);
@@ -537,7 +551,13 @@ void vbx_destroy(vbx_ctx* c) {
         if (p) cudaFree(p);
       }
     }
-    free_order_scratch(&F.order_scratch, F.head_list, F.first_bits);
+    free_order_scratch(&F.order_scratch, F.big_list, F.first_bits);
+    if (F.side) {
+      cudaStreamSynchronize(F.side);
+      cudaStreamDestroy(F.side);
+    }
+    if (F.ev_fork) cudaEventDestroy(F.ev_fork);
+    if (F.ev_join) cudaEventDestroy(F.ev_join);
     if (F.stream) cudaStreamDestroy(F.stream);
   }
   if (c->ev0) cudaEventDestroy(c->ev0);

@@ -78,7 +78,11 @@ struct ScanState {
   uint32_t kb_max[3];
   uint32_t kb_min[3];
   uint32_t key_bits;         // bits a bundle key uses
-  uint32_t reserved[9];
+  uint32_t n_big;            // Merged: bundles of at least kBigBundle members (folded first)
+  uint32_t merge_ticket;     // Merged: work hand-out counter of k_merge
+  uint32_t n_touch_ids;      // touched-block ids handed out (>= n_touched: ids lost to a race stay unused)
+  uint32_t rec_key_bits;     // bits an update-record key uses: voxel-in-block bits + bits of the touched ids
+  uint32_t reserved[5];
 };
 static_assert(sizeof(ScanState) == 192, "the status block the host reads back is 192 bytes");
 
@@ -87,12 +91,13 @@ static_assert(sizeof(ScanState) == 192, "the status block the host reads back is
 struct Tables {
   uint64_t* hkeys;        // [hcap] packed block index, kEmptyKey when free
   int32_t* hslot;         // [hcap] pool slot
-  uint32_t* htouch_epoch; // [hcap] call id of the last call that touched the block
-  uint32_t* htouch_rank;  // [hcap] dense id among the blocks touched by that call
+  unsigned long long* htouch;  // [hcap] (call id << 32 | touched id) of the last call that touched the block
   uint32_t hmask;         // hcap - 1
   uint32_t max_blocks;
+  uint32_t vox_per_block;
   uint32_t* new_list;     // [max_blocks] hash positions created by this call
-  uint32_t* touched_list; // [max_blocks] hash positions touched by this call
+  uint32_t* touched_list; // [touched_cap] touched id -> hash position (0xffffffff: unused id); hand-off set private
+  uint32_t touched_cap;
   uint64_t* slot_key;     // [max_blocks] packed block index per pool slot
   uint8_t* slot_updated;  // [max_blocks] TSDF Block::updated() bits
   uint8_t* slot_esdf_updated;  // [max_blocks] ESDF Block::updated() bits
@@ -149,7 +154,10 @@ struct vbx_ctx {
   uint32_t* order = nullptr;
   uint32_t* order_inv = nullptr;           // [max_points] inverse of `order` ("sorted" integration order)
   uint32_t* ray_list = nullptr;            // [max_points] Merged: ray slot (rank in the reference's bundle order) -> head
-  uint32_t* head_list = nullptr;           // [max_points] bundle heads, unordered (front-lane private)
+  uint32_t* head_list = nullptr;           // [max_points] bundle heads, unordered (hand-off set private)
+  uint32_t* big_list = nullptr;            // [max_points / 256 + 1] ids of the big bundles (front-lane private)
+  cudaStream_t side_stream = nullptr;      // k_bundle_order runs here, beside k_merge (front-lane private)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t* first_bits = nullptr;          // [2][max_points / 32 + 1] first-occurrence bitmaps (front-lane private)
   vbx::OrderScratch order_scratch{};         // k_bundle_order's global tables (front-lane private)
   vbx::RehashSchedule rehash{};            // libstdc++'s unordered_map growth schedule (vbx_create)
@@ -169,13 +177,10 @@ struct vbx_ctx {
   uint32_t* ckeys[2] = {nullptr, nullptr};
   uint32_t* cvals[2] = {nullptr, nullptr};
   // the engine's own radix sort / scan (vbx_sort.cuh): [0] point keys, [1] update records
-  bool use_cub = false;
   vbx::SortPlan* sort_plan[2] = {nullptr, nullptr};
   uint32_t* sort_status[2] = {nullptr, nullptr};
   uint32_t sort_tiles_cap[2] = {0, 0};
   uint32_t* scan_status = nullptr;
-  void* cub_tmp = nullptr;
-  size_t cub_tmp_bytes = 0;
   unsigned long long* set_start = nullptr;  // Fast integrator approximate sets
   unsigned long long* set_observed = nullptr;
   uint32_t set_epoch = 1;
@@ -192,12 +197,14 @@ struct vbx_ctx {
   // the main stream -- so up to kSets scans are in flight, each owning one set of hand-off
   // buffers.  Map-touching stages run in submission order.  Set 0 / lane 0 are the buffers the
   // synchronous calls use; the others are allocated on the first asynchronous submission.
-  static constexpr int kSets = 6, kLanes = 3, kSortStreams = 2;
+  static constexpr int kSets = 10, kLanes = 6, kSortStreams = 2;
   struct ScratchSet {
     float4* ray_p = nullptr;
     float4* ray_a = nullptr;
     uint2* ray_c = nullptr;
     uint32_t* ray_list = nullptr;
+    uint32_t* head_list = nullptr;   // bundle id -> sorted position of its head (read again by the ray walk)
+    uint32_t* touched_list = nullptr;  // touched id -> hash position (written by the walk, read by the apply)
     uint32_t* cnt = nullptr;
     uint32_t* off = nullptr;
     vbx::ScanState* d_state = nullptr;
@@ -230,9 +237,11 @@ struct vbx_ctx {
     vbx::SortPlan* sort_plan0 = nullptr;
     uint32_t* sort_status0 = nullptr;
     uint32_t* scan_status = nullptr;
-    uint32_t* head_list = nullptr;
+    uint32_t* big_list = nullptr;
     uint32_t* first_bits = nullptr;
     vbx::OrderScratch order_scratch{};
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   } lane[kLanes];
   bool async_ready = false;
   int prio_lo = 0, prio_hi = 0;  // stream priority range of the device
@@ -314,8 +323,8 @@ void select_set(vbx_ctx* c, int k);     // point the context's scratch fields at
 void select_lane(vbx_ctx* c, int l);
 int drain_async(vbx_ctx* c);           // wait for every asynchronously submitted scan, collect its results
 int set_n_blocks(vbx_ctx* c, uint32_t n);
-int alloc_order_scratch(vbx_ctx* c, vbx::OrderScratch* g, uint32_t** head_list, uint32_t** first_bits);
-void free_order_scratch(vbx::OrderScratch* g, uint32_t* head_list, uint32_t* first_bits);
+int alloc_order_scratch(vbx_ctx* c, vbx::OrderScratch* g, uint32_t** big_list, uint32_t** first_bits);
+void free_order_scratch(vbx::OrderScratch* g, uint32_t* big_list, uint32_t* first_bits);
 int init_bundle_order(vbx_ctx* c);     // rehash schedule + shared-memory opt-in of k_bundle_order
 int rebuild_hash(vbx_ctx* c);          // block hash rebuilt from slot_key (after removals / a pool overflow)
 void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S);  // collect a finished asynchronous scan's results

@@ -46,14 +46,29 @@ __device__ __forceinline__ uint32_t find_block(const Tables& t, uint64_t key) {
   return 0xffffffffu;
 }
 
-__device__ __forceinline__ void mark_touched(const Tables& t, uint32_t hp, uint32_t epoch, ScanState* st) {
-  if (*reinterpret_cast<volatile uint32_t*>(t.htouch_epoch + hp) != epoch) {
-    const uint32_t old = atomicExch(t.htouch_epoch + hp, epoch);
-    if (old != epoch) {
-      const uint32_t j = atomicAdd(&st->n_touched, 1u);
-      if (j < t.max_blocks) t.touched_list[j] = hp;
-    }
+// Blocks touched by the current call get dense ids 0, 1, 2, ... (update records are keyed by
+// (touched id, voxel in block): a handful of bits instead of a hash position).  The per-position
+// word packs (call id, touched id); the first toucher of a block in this call installs it with one
+// CAS.  A thread that loses the CAS race has drawn an id nobody uses: it is marked as a hole in
+// touched_list (0xffffffff) -- ids stay dense enough, n_touched counts the blocks exactly.
+__device__ __forceinline__ uint32_t touch_block(const Tables& t, uint32_t hp, uint32_t epoch, ScanState* st) {
+  unsigned long long* w = t.htouch + hp;
+  const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(w);
+  if ((uint32_t)(cur >> 32) == epoch) return (uint32_t)cur;
+  const uint32_t id = atomicAdd(&st->n_touch_ids, 1u);
+  if (id >= t.touched_cap) {
+    atomicOr(&st->error, kErrPoolFull);
+    return 0u;
   }
+  const unsigned long long want = ((unsigned long long)epoch << 32) | id;
+  const unsigned long long old = atomicCAS(w, cur, want);
+  if (old == cur) {
+    t.touched_list[id] = hp;
+    atomicAdd(&st->n_touched, 1u);
+    return id;
+  }
+  t.touched_list[id] = 0xffffffffu;  // a hole
+  return (uint32_t)old;              // (only this call's walk writes these words: the winner carries this call's id)
 }
 
 }  // namespace vbx

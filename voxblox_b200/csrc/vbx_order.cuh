@@ -43,6 +43,7 @@ struct OrderScratch {     // global-memory fallback when a map's tables do not f
   uint32_t* tau;          // [cap] current insertion time
   uint32_t* tau2;         // [cap]
   uint32_t* next;         // [cap] bucket chain
+  uint32_t* bkt;          // [cap] bucket of the element in the current table
   uint32_t* A;            // [cap] group sizes by creation time -> suffix sums
   uint32_t* bhead;        // [bucket_cap]
   uint32_t* head_of;      // [cap] element -> sorted position of its bundle head
@@ -84,44 +85,56 @@ __device__ __forceinline__ uint32_t order_block_scan(uint32_t v, uint32_t* warp_
 }
 
 // List positions of elements [0, m) with insertion times tau[] in a table of n buckets.
-// Result in tau_out[]; A, next, bhead are scratch.
+// Result in tau_out[]; A, next, bkt, bhead are scratch.  `tag` (distinct per call, < 2^12) marks the
+// bucket heads written by this call, so the bucket array needs no clearing between calls:
+// bhead[j] = tag << 20 | element, anything with another tag reads as "empty" (elements < 2^20).
 __device__ inline void order_positions(const uint32_t* h, const uint32_t* tau, uint32_t* tau_out, uint32_t* next,
-                                       uint32_t* A, uint32_t* bhead, uint32_t m, uint32_t n, uint32_t* warp_sums) {
+                                       uint32_t* bkt, uint32_t* A, uint32_t* bhead, uint32_t m, uint32_t n, uint32_t tag,
+                                       uint32_t* warp_sums) {
   const uint32_t tid = threadIdx.x;
-  for (uint32_t j = tid; j < n; j += kOrderThreads) bhead[j] = kOrderNil;
-  for (uint32_t t = tid; t < m; t += kOrderThreads) A[t] = 0u;
+  const uint32_t tg = tag << 20;
+  // chains: next[b] = the element that headed b's bucket before b (kOrderNil: none)
+  for (uint32_t b = tid; b < m; b += kOrderThreads) {
+    const uint32_t g = h[b] % n;
+    bkt[b] = g;
+    const uint32_t old = atomicExch(&bhead[g], tg | b);
+    next[b] = (old >> 20) == tag ? (old & 0xfffffu) : kOrderNil;
+  }
   __syncthreads();
-  for (uint32_t b = tid; b < m; b += kOrderThreads) next[b] = atomicExch(&bhead[h[b] % n], b);
-  __syncthreads();
-  // the group's creator (smallest time) publishes the group size at its creation time
+  // the group's creator (smallest time) publishes the group size at its creation time; every time in
+  // [0, m) belongs to exactly one element, so A needs no clearing either
   for (uint32_t b = tid; b < m; b += kOrderThreads) {
     const uint32_t tb = tau[b];
     uint32_t cmin = kOrderNil, size = 0;
-    for (uint32_t c = bhead[h[b] % n]; c != kOrderNil; c = next[c]) {
+    for (uint32_t c = bhead[bkt[b]] & 0xfffffu; c != kOrderNil; c = next[c]) {
       cmin = min(cmin, tau[c]);
       ++size;
     }
-    if (cmin == tb) A[tb] = size;
+    A[tb] = cmin == tb ? size : 0u;
   }
   __syncthreads();
-  // A[t] <- number of elements in groups created after time t (exclusive suffix sum), top chunk first
+  // A[t] <- number of elements in groups created after time t (exclusive suffix sum): every thread owns
+  // a contiguous run of times, one block-wide scan over the run totals
   {
-    uint32_t carry = 0;
-    const uint32_t chunks = (m + kOrderThreads - 1) / kOrderThreads;
-    for (uint32_t c = chunks; c-- > 0;) {
-      const uint32_t t = c * kOrderThreads + (kOrderThreads - 1 - tid);  // thread 0 holds the highest time
-      const uint32_t v = t < m ? A[t] : 0u;
-      uint32_t total;
-      const uint32_t ex = order_block_scan(v, warp_sums, &total);
-      if (t < m) A[t] = carry + ex;
-      carry += total;
+    const uint32_t per = (m + kOrderThreads - 1) / kOrderThreads;
+    // thread 0 owns the HIGHEST times
+    const uint32_t hi = m > tid * per ? m - tid * per : 0u;          // one past my highest time
+    const uint32_t lo = hi > per ? hi - per : 0u;
+    uint32_t sum = 0;
+    for (uint32_t t = lo; t < hi; ++t) sum += A[t];
+    uint32_t total;
+    uint32_t run = order_block_scan(sum, warp_sums, &total);          // elements at times above my run
+    for (uint32_t t = hi; t-- > lo;) {
+      const uint32_t v = A[t];
+      A[t] = run;
+      run += v;
     }
   }
   __syncthreads();
   for (uint32_t b = tid; b < m; b += kOrderThreads) {
     const uint32_t tb = tau[b];
     uint32_t cmin = kOrderNil, later = 0;
-    for (uint32_t c = bhead[h[b] % n]; c != kOrderNil; c = next[c]) {
+    for (uint32_t c = bhead[bkt[b]] & 0xfffffu; c != kOrderNil; c = next[c]) {
       const uint32_t tc = tau[c];
       cmin = min(cmin, tc);
       later += tc > tb ? 1u : 0u;
@@ -133,18 +146,23 @@ __device__ inline void order_positions(const uint32_t* h, const uint32_t* tau, u
 
 // All rehash stages + the final listing for B elements already loaded into h[] (insertion order).
 // On return pos[] (= one of tau / tau2, returned) holds every element's position in the iteration order.
+// bhead must not hold values with tags 1.. from an earlier run: the caller clears it once (or uses a
+// fresh shared-memory array and clears that).
 __device__ inline uint32_t* order_run(const RehashSchedule& rs, uint32_t B, const uint32_t* h, uint32_t* tau, uint32_t* tau2,
-                                      uint32_t* next, uint32_t* A, uint32_t* bhead, uint32_t* warp_sums) {
+                                      uint32_t* next, uint32_t* bkt, uint32_t* A, uint32_t* bhead, uint32_t n_final,
+                                      uint32_t* warp_sums) {
   for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) tau[e] = e;
+  for (uint32_t j = threadIdx.x; j < n_final; j += kOrderThreads) bhead[j] = 0u;  // tag 0 = never used
   __syncthreads();
   uint32_t n_cur = 1;
+  uint32_t tag = 1;
   uint32_t* cur = tau;
   uint32_t* oth = tau2;
   for (int k = 0; k < rs.count; ++k) {
     const uint32_t mk = rs.m[k];
     if (mk >= B) break;  // the map never reaches this size
     if (mk > 0) {
-      order_positions(h, cur, oth, next, A, bhead, mk, n_cur, warp_sums);
+      order_positions(h, cur, oth, next, bkt, A, bhead, mk, n_cur, tag++, warp_sums);
       // elements inserted after the rehash keep their insertion index as time
       for (uint32_t e = mk + threadIdx.x; e < B; e += kOrderThreads) oth[e] = e;
       __syncthreads();
@@ -154,7 +172,7 @@ __device__ inline uint32_t* order_run(const RehashSchedule& rs, uint32_t B, cons
     }
     n_cur = rs.n[k];
   }
-  order_positions(h, cur, oth, next, A, bhead, B, n_cur, warp_sums);
+  order_positions(h, cur, oth, next, bkt, A, bhead, B, n_cur, tag, warp_sums);
   return oth;
 }
 #endif  // __CUDACC__

@@ -220,12 +220,15 @@ k_sort_pass(int pass, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* va
   }
 }
 
-// Exclusive prefix sum of n uint32 (n known on the host), chained scan over tiles of 2048.
+// Exclusive prefix sum of n uint32 (n known on the host), chained scan over tiles of 2048.  With a
+// permutation the summand at position i is in[perm[i]] for i < *d_limit and 0 beyond (the record
+// offsets of the Merged integrator: counts are stored per bundle id, offsets are needed in rank order).
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kSortThreads * kScanItems;
 static __global__ void __launch_bounds__(kSortThreads)
-k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* status,
-                 uint32_t* tile_counter) {
+k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ d_limit,
+                 uint32_t* __restrict__ out, uint32_t n, uint32_t* status, uint32_t* tile_counter) {
+  const uint32_t limit = d_limit ? *d_limit : 0xffffffffu;
   __shared__ uint32_t warp_sums[kSortWarps];
   __shared__ uint32_t cur_tile, tile_base;
   const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
@@ -240,7 +243,8 @@ k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, ui
     uint32_t sum = 0;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-      v[j] = (base + j < n) ? in[base + j] : 0u;
+      const uint32_t e = base + j;
+      v[j] = (e < n && e < limit) ? in[perm ? perm[e] : e] : 0u;
       sum += v[j];
     }
     const uint32_t excl_in_tile = block_exclusive_scan_256(sum, warp_sums);

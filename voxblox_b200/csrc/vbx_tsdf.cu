@@ -28,8 +28,6 @@
 // order (integration_order_mode) for Simple / Fast; for Merged the iteration order
 // of the reference's libstdc++ unordered_map (k_bundle_order, vbx_order.cuh), normal
 // bundles before clearing bundles (cc:323-335).  See DESIGN.md "update order".
-#include <cub/cub.cuh>
-
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -94,13 +92,15 @@ __device__ __forceinline__ uint32_t load_color(const uint8_t* rgba, uint32_t idx
 __device__ __forceinline__ bool owns_block(const ScanParams& P, int bx, int by, int bz) {
   return P.own_world <= 1 || block_owner(bx, by, bz, P.own_world) == P.own_rank;
 }
-// An update record's key: (hash position of the block, voxel inside the block).  Records of blocks
-// another rank owns keep their place in the ray's record range (offsets are fixed before the walk)
-// under the key 0xffffffff, which sorts behind every real key and is skipped by the apply.
+// An update record's key: (touched id of the block in this call, voxel inside the block) -- e.g.
+// 6 + 12 bits when a scan touches ~50 blocks, so the record sort runs three 8-bit passes whatever
+// the size of the map.  Records of blocks another rank owns keep their place in the ray's record
+// range (offsets are fixed before the walk) under the key 0xffffffff, which sorts behind every
+// real key and is skipped by the apply.
 constexpr uint32_t kNotOwned = 0xfffffffeu;
 constexpr uint32_t kSkipRecord = 0xffffffffu;
-__device__ __forceinline__ uint32_t record_key(uint32_t hp, uint32_t lin, int L) {
-  return hp >= kNotOwned ? kSkipRecord : ((hp << (3 * L)) | lin);
+__device__ __forceinline__ uint32_t record_key(uint32_t touched_id, uint32_t lin, int L) {
+  return touched_id >= kNotOwned ? kSkipRecord : ((touched_id << (3 * L)) | lin);
 }
 
 // ------------------------------------------------------------------ bundle keys
@@ -149,43 +149,55 @@ __device__ __forceinline__ I3 key_voxel(const KeyLayout& k, uint64_t key) {
 
 // ------------------------------------------------------------------- kernels
 // Merged, pass 1 over the cloud: the bounding box of the valid points' voxels (and their count).
-__global__ void k_point_bounds(ScanParams P, const float* __restrict__ xyz, const uint32_t* __restrict__ order,
-                               uint32_t* __restrict__ first_bits, ScanState* st) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < 2u * ((P.n + 31u) >> 5)) first_bits[s] = 0u;  // the first-occurrence bitmaps k_heads fills
-  bool valid = false;
-  I3 v = i3(0, 0, 0);
-  if (s < P.n) {
+// Grid-stride over the points, one set of atomics per thread block.
+__global__ void __launch_bounds__(256)
+k_point_bounds(ScanParams P, const float* __restrict__ xyz, uint32_t* __restrict__ first_bits, ScanState* st) {
+  __shared__ uint32_t s_red[7];
+  if (threadIdx.x < 7) s_red[threadIdx.x] = 0u;
+  const uint32_t words2 = 2u * ((P.n + 31u) >> 5);
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words2; w += gridDim.x * blockDim.x) {
+    first_bits[w] = 0u;  // the first-occurrence bitmaps k_heads fills
+  }
+  __syncthreads();
+  // both ends encoded so that the zero-initialised status block means "empty" and atomicMax serves both
+  uint32_t hi_x = 0, hi_y = 0, hi_z = 0, lo_x = 0, lo_y = 0, lo_z = 0, n_valid = 0;
+  const int lim = kCoordBias - 1;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n; s += gridDim.x * blockDim.x) {
     const F3 p = load_point(xyz, s);  // (the bounding box does not depend on the point order)
-    if (classify_point(p, P.min_ray, P.max_ray, P.allow_clear != 0, P.freespace != 0) != 0) {
-      v = grid_index(transform(P.T, p), P.voxel_size_inv);
-      const int lim = kCoordBias - 1;
-      if (v.x < -lim || v.x > lim || v.y < -lim || v.y > lim || v.z < -lim || v.z > lim) {
-        atomicOr(&st->error, kErrCoordRange);
-      } else {
-        valid = true;
-      }
+    if (classify_point(p, P.min_ray, P.max_ray, P.allow_clear != 0, P.freespace != 0) == 0) continue;
+    const I3 v = grid_index(transform(P.T, p), P.voxel_size_inv);
+    if (v.x < -lim || v.x > lim || v.y < -lim || v.y > lim || v.z < -lim || v.z > lim) {
+      atomicOr(&st->error, kErrCoordRange);
+      continue;
     }
+    ++n_valid;
+    hi_x = max(hi_x, (uint32_t)v.x + kBoundBias);
+    hi_y = max(hi_y, (uint32_t)v.y + kBoundBias);
+    hi_z = max(hi_z, (uint32_t)v.z + kBoundBias);
+    lo_x = max(lo_x, 0xffffffffu - ((uint32_t)v.x + kBoundBias));
+    lo_y = max(lo_y, 0xffffffffu - ((uint32_t)v.y + kBoundBias));
+    lo_z = max(lo_z, 0xffffffffu - ((uint32_t)v.z + kBoundBias));
   }
-  const unsigned b = __ballot_sync(0xffffffffu, valid);
-  if (b) {
-    // encoded so that the zero-initialised status block means "empty": both ends are atomicMax'ed
-    const uint32_t hi_x = valid ? (uint32_t)v.x + kBoundBias : 0u, lo_x = valid ? 0xffffffffu - ((uint32_t)v.x + kBoundBias) : 0u;
-    const uint32_t hi_y = valid ? (uint32_t)v.y + kBoundBias : 0u, lo_y = valid ? 0xffffffffu - ((uint32_t)v.y + kBoundBias) : 0u;
-    const uint32_t hi_z = valid ? (uint32_t)v.z + kBoundBias : 0u, lo_z = valid ? 0xffffffffu - ((uint32_t)v.z + kBoundBias) : 0u;
-    const uint32_t r0 = __reduce_max_sync(0xffffffffu, hi_x), r1 = __reduce_max_sync(0xffffffffu, hi_y),
-                   r2 = __reduce_max_sync(0xffffffffu, hi_z), r3 = __reduce_max_sync(0xffffffffu, lo_x),
-                   r4 = __reduce_max_sync(0xffffffffu, lo_y), r5 = __reduce_max_sync(0xffffffffu, lo_z);
-    if ((threadIdx.x & 31) == 0) {
-      if (r0 > st->kb_max[0]) atomicMax(&st->kb_max[0], r0);
-      if (r1 > st->kb_max[1]) atomicMax(&st->kb_max[1], r1);
-      if (r2 > st->kb_max[2]) atomicMax(&st->kb_max[2], r2);
-      if (r3 > st->kb_min[0]) atomicMax(&st->kb_min[0], r3);
-      if (r4 > st->kb_min[1]) atomicMax(&st->kb_min[1], r4);
-      if (r5 > st->kb_min[2]) atomicMax(&st->kb_min[2], r5);
-      atomicAdd(&st->n_valid_points, (uint32_t)__popc(b));
-    }
+  hi_x = __reduce_max_sync(0xffffffffu, hi_x);
+  hi_y = __reduce_max_sync(0xffffffffu, hi_y);
+  hi_z = __reduce_max_sync(0xffffffffu, hi_z);
+  lo_x = __reduce_max_sync(0xffffffffu, lo_x);
+  lo_y = __reduce_max_sync(0xffffffffu, lo_y);
+  lo_z = __reduce_max_sync(0xffffffffu, lo_z);
+  n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&s_red[0], hi_x);
+    atomicMax(&s_red[1], hi_y);
+    atomicMax(&s_red[2], hi_z);
+    atomicMax(&s_red[3], lo_x);
+    atomicMax(&s_red[4], lo_y);
+    atomicMax(&s_red[5], lo_z);
+    atomicAdd(&s_red[6], n_valid);
   }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_red[threadIdx.x]) atomicMax(&st->kb_max[threadIdx.x], s_red[threadIdx.x]);
+  if (threadIdx.x >= 3 && threadIdx.x < 6 && s_red[threadIdx.x]) atomicMax(&st->kb_min[threadIdx.x - 3], s_red[threadIdx.x]);
+  if (threadIdx.x == 6 && s_red[6]) atomicAdd(&st->n_valid_points, s_red[6]);
 }
 
 // Merged, pass 2: key every point by its end voxel (bundleRays, cc:340-371), in the reference's
@@ -235,6 +247,11 @@ __global__ void k_invert_order(uint32_t n, const uint32_t* __restrict__ order, u
   if (s < n) order_inv[order[s]] = s;
 }
 
+// A bundle's id is its position j in head_list (unordered, dense): the per-ray tables (ray_p / ray_a /
+// ray_c / cnt) are indexed by j, update records carry j, and ray_list[rank] = j gives the order.
+constexpr uint32_t kBigBundle = 256;         // members from which a bundle is folded before the others
+constexpr uint32_t kHeadBig = 0x80000000u;   // head_list entry: sorted position of the head | this flag
+
 // Dense (unordered) list of bundle heads, and the first-occurrence bitmaps: bit t of map m
 // (0 normal, 1 clearing) is set when the point at position t of the reference's point order is the
 // first of its bundle, i.e. the point whose operator[] inserts the bundle's key into the reference's
@@ -243,7 +260,8 @@ __global__ void k_invert_order(uint32_t n, const uint32_t* __restrict__ order, u
 template <typename KeyT>
 __global__ void k_heads(ScanParams P, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
                         const uint32_t* __restrict__ order_inv, uint32_t* __restrict__ head_list,
-                        uint32_t* __restrict__ first_bits, uint32_t* __restrict__ cnt, ScanState* st) {
+                        uint32_t* __restrict__ big_list, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ cnt,
+                        ScanState* st) {
   const uint32_t n = P.n;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const KeyLayout kl = key_layout(st);
@@ -265,7 +283,13 @@ __global__ void k_heads(ScanParams P, const KeyT* __restrict__ keys, const uint3
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&st->n_ray_list, (uint32_t)__popc(b));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (head) head_list[base + __popc(b & ((1u << lane) - 1u))] = i;
+    if (head) {
+      // the fold of a bundle is one dependent chain: the long ones are started first (k_merge)
+      const bool big = i + kBigBundle < n && keys[i + kBigBundle] == keys[i];
+      const uint32_t j = base + __popc(b & ((1u << lane) - 1u));
+      head_list[j] = i | (big ? kHeadBig : 0u);
+      if (big) big_list[atomicAdd(&st->n_big, 1u)] = j;
+    }
   }
 }
 
@@ -274,7 +298,7 @@ __device__ __forceinline__ uint32_t long_index_hash(int x, int y, int z) {
   return (uint32_t)x + (uint32_t)y * 17191u + (uint32_t)z * 295530481u;
 }
 // The reference's bundle order (vbx_order.cuh): ONE thread block ranks the bundles of the normal map,
-// then those of the clearing map, and writes ray_list[rank] = sorted position of the bundle's head.
+// then those of the clearing map, and writes ray_list[rank] = bundle id j.
 // Ranks are dense: normal bundles 0 .. B0-1 in voxel_map's iteration order, clearing bundles
 // B0 .. B0+B1-1 in clear_map's (integrateRays(false) runs before integrateRays(true), cc:323-335).
 // Tables live in shared memory when they fit (a few thousand bundles), else in global scratch.
@@ -307,37 +331,38 @@ k_bundle_order(ScanParams P, RehashSchedule rs, const KeyT* __restrict__ keys, c
     if (mp == 1 && tid == 0) st->n_clear_rays = B;
     __syncthreads();
     if (B == 0) continue;
-    if (B > g.cap) {  // cannot happen: cap = max_points_per_scan
+    if (B > g.cap || B > (1u << 20)) {  // cap = max_points_per_scan; bucket heads pack the element into 20 bits
       if (tid == 0) atomicOr(&st->error, kErrUpdatesFull);
       continue;
     }
     // bucket count after B insertions
     uint32_t n_final = 1;
     for (int k = 0; k < rs.count && rs.m[k] < B; ++k) n_final = rs.n[k];
-    uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *A = g.A, *bhead = g.bhead;
-    if (5u * B + n_final <= smem_words) {
+    uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *bkt = g.bkt, *A = g.A, *bhead = g.bhead;
+    if (6u * B + n_final <= smem_words) {
       h = order_smem;
       tau = h + B;
       tau2 = tau + B;
       next = tau2 + B;
-      A = next + B;
+      bkt = next + B;
+      A = bkt + B;
       bhead = A + B;
     } else if (n_final > g.bucket_cap) {
       if (tid == 0) atomicOr(&st->error, kErrUpdatesFull);
       continue;
     }
     for (uint32_t j = tid; j < n_heads; j += kOrderThreads) {
-      const uint32_t i = head_list[j];
+      const uint32_t i = head_list[j] & ~kHeadBig;
       const uint64_t key = (uint64_t)keys[i];
       if ((key_is_clearing(kl, key) ? 1 : 0) != mp) continue;
       const uint32_t t0 = point_order_inv(P, order_inv, vals[i]);
       const uint32_t e = g.wp[t0 >> 5] + (uint32_t)__popc(bits[t0 >> 5] & ((1u << (t0 & 31u)) - 1u));
       const I3 v = key_voxel(kl, key);
       h[e] = long_index_hash(v.x, v.y, v.z);
-      g.head_of[e] = i;
+      g.head_of[e] = j;
     }
     __syncthreads();
-    const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, A, bhead, warp_sums);
+    const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, bkt, A, bhead, n_final, warp_sums);
     for (uint32_t e = tid; e < B; e += kOrderThreads) ray_list[base_rank + pos[e]] = g.head_of[e];
     __syncthreads();
     base_rank += B;
@@ -561,7 +586,8 @@ __device__ __forceinline__ void pair_barrier(int pair_in_block) {
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
 k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
-        const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ray_list,
+        const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ head_list,
+        const uint32_t* __restrict__ big_list,
         float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c, uint32_t* __restrict__ cnt,
         ScanState* st) {
   __shared__ float4 stage[2][2][32 * kStageStride];  // [pair in block][slot][member][role]
@@ -571,14 +597,28 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
   const int pair_in_block = warp_in_block >> 1;
   const bool producer = (warp_in_block & 1) == 0;
   const int bar_id = pair_in_block;
-  const uint32_t pair = blockIdx.x * 2u + (uint32_t)pair_in_block;
-  const uint32_t n_pairs = gridDim.x * 2u;
   const uint32_t n_bundles = st->n_ray_list;
+  const uint32_t n_big = st->n_big;
   const KeyLayout kl = key_layout(st);
   uint32_t seq = 0;
   if (producer) {
-    for (uint32_t b = pair; b < n_bundles; b += n_pairs) {
-      const uint32_t i = ray_list[b];
+    // Work is handed out by ticket: first the big bundles (their chains bound the kernel's duration, so
+    // they start at once), then every other bundle in head_list order.
+    while (true) {
+      uint32_t ticket = 0;
+      if (lane == 0) ticket = atomicAdd(&st->merge_ticket, 1u);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      if (ticket >= n_big + n_bundles) break;
+      uint32_t b, hl;
+      if (ticket < n_big) {
+        b = big_list[ticket];
+        hl = head_list[b];
+      } else {
+        b = ticket - n_big;
+        hl = head_list[b];
+        if (hl & kHeadBig) continue;  // folded through the big list
+      }
+      const uint32_t i = hl & ~kHeadBig;
       const KeyT key = keys[i];
       const bool clearing = key_is_clearing(kl, (uint64_t)key);
       float mw = 0.0f;
@@ -808,7 +848,7 @@ __device__ __forceinline__ bool replace_hash(unsigned long long* set, uint32_t h
 template <typename KeyT>
 __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__ xyz,
                              const uint8_t* __restrict__ rgba, const uint32_t* __restrict__ order,
-                             const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
+                             const KeyT* __restrict__ keys, const uint32_t* __restrict__ head_list,
                              float4* __restrict__ ray_p, float4* __restrict__ ray_a, uint2* __restrict__ ray_c,
                              uint32_t* __restrict__ cnt,
                              unsigned long long* set_start, unsigned long long* set_observed, ScanState* st) {
@@ -819,11 +859,11 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   KeyT own = 0;
   if (P.kind == VBX_MERGED) {
     if (t >= st->n_ray_list) return;
-    i = t;  // ray slot = rank in the reference's bundle order; ray_list[t] = sorted position of the head
+    i = t;  // bundle id j (the count does not depend on the order); head_list[j] = sorted position of its head
     const float4 rp = ray_p[i];
     point_G = f3(rp.x, rp.y, rp.z);
     clearing = (__float_as_uint(rp.w) & 1u) != 0;
-    own = keys[ray_list[t]];
+    own = keys[head_list[t] & ~kHeadBig];
   } else {
     i = t;
     if (i > P.n) return;
@@ -885,7 +925,7 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
     if ((bx != lbx || by != lby || bz != lbz) && owns_block(P, bx, by, bz)) {
       const uint32_t hp = ensure_block(tab, pack3(bx, by, bz), st);
       if (hp == 0xffffffffu) break;
-      mark_touched(tab, hp, P.epoch, st);
+      touch_block(tab, hp, P.epoch, st);
     }
     lbx = bx;
     lby = by;
@@ -947,6 +987,10 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_
     const uint32_t after = min(n_blocks_before + st->n_new, tab.max_blocks);
     st->n_blocks = after;
     *nb_out = after;
+    // what the record sort has to look at: voxel bits + the bits of the touched ids handed out
+    uint32_t vb = 0;
+    while ((tab.vox_per_block >> vb) > 1u) ++vb;
+    st->rec_key_bits = vb + (uint32_t)(32 - __clz(st->n_touch_ids));
   }
 }
 
@@ -954,12 +998,13 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_
 // with allocateStorageAndGetVoxelPtr's find-or-create per block change (cc:91-134).
 template <typename KeyT>
 __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, const KeyT* __restrict__ keys, uint32_t i,
-                                    uint32_t head_pos, const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
+                                    uint32_t rank, uint32_t head_pos, const float4* __restrict__ ray_p,
+                                    const uint32_t* __restrict__ cnt,
                                     const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
                                     uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t c = cnt[i];
   if (c == 0 || st->total_updates == 0) return;  // (a failed / to-be-redone call emits nothing)
-  if (i < P.emit_lo || i >= P.emit_hi) return;   // (not in this pass)
+  if (rank < P.emit_lo || rank >= P.emit_hi) return;   // (not in this pass)
   const float4 rp = ray_p[i];
   const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
   const F3 point_G = f3(rp.x, rp.y, rp.z);
@@ -969,8 +1014,8 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
   const KeyT own = (P.kind == VBX_MERGED) ? keys[head_pos] : (KeyT)0;
   uint32_t emitted = 0;
   int lbx = INT_MIN, lby = INT_MIN, lbz = INT_MIN;
-  uint32_t hp = 0;
-  const uint32_t base = off[i] - P.emit_base;
+  uint32_t hp = 0, tid = 0;
+  const uint32_t base = off[rank] - P.emit_base;
   const int mask = (1 << P.L) - 1;
   const int lim = (kCoordBias - 1) << P.L;
   for (unsigned int s = 0; s <= d.len && emitted < c; ++s, dda_advance(d)) {
@@ -988,12 +1033,13 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
           hp = 0xffffffffu;
         } else {
           hp = ensure_block(tab, pack3(bx, by, bz), st);
-          if (hp != 0xffffffffu) mark_touched(tab, hp, P.epoch, st);
         }
       } else {
         hp = find_block(tab, pack3(bx, by, bz));
       }
+      tid = hp;  // (the two sentinels pass through)
       if (hp != 0xffffffffu && hp != kNotOwned) {
+        tid = touch_block(tab, hp, P.epoch, st);
         const int32_t slot = tab.hslot[hp];
         if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
       }
@@ -1006,7 +1052,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
     // a record = (hash position of the block, voxel inside the block) -> ray.  A ray whose block
     // could not be created still fills its slots so that offsets stay valid; the error flag set
     // above stops the apply kernels.
-    ckeys[base + emitted] = record_key(hp, lin, P.L);
+    ckeys[base + emitted] = record_key(tid, lin, P.L);
     cvals[base + emitted] = i;
     ++emitted;
   }
@@ -1014,8 +1060,8 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
 
 template <typename KeyT>
 __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ keys,
-                            const uint32_t* __restrict__ ray_list, const float4* __restrict__ ray_p,
-                            const uint32_t* __restrict__ cnt,
+                            const uint32_t* __restrict__ ray_list, const uint32_t* __restrict__ head_list,
+                            const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt,
                             const uint32_t* __restrict__ off, uint32_t* __restrict__ ckeys,
                             uint32_t* __restrict__ cvals, ScanState* st) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1023,13 +1069,13 @@ __global__ void k_rays_emit(ScanParams P, Tables tab, const KeyT* __restrict__ k
   uint32_t head_pos = 0;
   if (P.kind == VBX_MERGED) {
     if (t >= st->n_ray_list) return;
-    i = t;
-    head_pos = ray_list[t];
+    i = ray_list[t];  // rank t -> bundle id
+    head_pos = head_list[i] & ~kHeadBig;
   } else {
     i = t;
     if (i >= P.n) return;
   }
-  emit_ray_sequential<KeyT>(P, tab, keys, i, head_pos, ray_p, cnt, off, ckeys, cvals, st);
+  emit_ray_sequential<KeyT>(P, tab, keys, i, t, head_pos, ray_p, cnt, off, ckeys, cvals, st);
 }
 
 // The same walk cast by a WARP per ray (single-walk modes of the Merged integrator: a few thousand
@@ -1051,7 +1097,7 @@ constexpr int kWalkCap = 3 * kChainCap;
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
 k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const uint32_t* __restrict__ ray_list,
-                 const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
+                 const uint32_t* __restrict__ head_list, const float4* __restrict__ ray_p, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
                  uint32_t* __restrict__ ckeys, uint32_t* __restrict__ cvals, ScanState* st) {
   __shared__ float chain_s[4][3][kChainCap];
   __shared__ uint32_t walk_s[4][kWalkCap];
@@ -1064,9 +1110,9 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
   const int mask = (1 << P.L) - 1;
   const int lim = (kCoordBias - 1) << P.L;
   for (uint32_t b = warp; b < n_rays; b += n_warps) {
-    const uint32_t i = b;  // ray slot = rank in the reference's bundle order
+    const uint32_t i = ray_list[b];  // rank b in the reference's bundle order -> bundle id
     const uint32_t c = cnt[i];
-    if (c == 0 || i < P.emit_lo || i >= P.emit_hi) continue;
+    if (c == 0 || b < P.emit_lo || b >= P.emit_hi) continue;
     const float4 rp = ray_p[i];
     const bool clearing = (__float_as_uint(rp.w) & 1u) != 0;
     Dda d;
@@ -1115,12 +1161,14 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
       __syncwarp();
     }
     if (!merge_ok) {
-      if (lane == 0) emit_ray_sequential<KeyT>(P, tab, keys, i, ray_list[b], ray_p, cnt, off, ckeys, cvals, st);
+      if (lane == 0) {
+        emit_ray_sequential<KeyT>(P, tab, keys, i, b, head_list[i] & ~kHeadBig, ray_p, cnt, off, ckeys, cvals, st);
+      }
       __syncwarp();
       continue;
     }
     // 3. records, 32 steps at a time
-    const uint32_t base = off[i] - P.emit_base;
+    const uint32_t base = off[b] - P.emit_base;
     int cbx = INT_MIN, cby = INT_MIN, cbz = INT_MIN;  // block of the previous chunk's last step
     uint32_t chp = 0u;
     for (unsigned int r0 = 0; r0 <= len; r0 += 32u) {
@@ -1149,11 +1197,11 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
           hp = 0xffffffffu;
         } else {
           hp = ensure_block(tab, pack3(bx, by, bz), st);
-          if (hp != 0xffffffffu) mark_touched(tab, hp, P.epoch, st);
         }
         if (hp != 0xffffffffu && hp != kNotOwned) {
           const int32_t slot = tab.hslot[hp];
           if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
+          hp = touch_block(tab, hp, P.epoch, st);      // from here on: the block's touched id
         }
       }
       const unsigned int heads = __ballot_sync(0xffffffffu, head);
@@ -1183,7 +1231,7 @@ struct VoxelRef {
 };
 
 __device__ __forceinline__ VoxelRef locate_voxel(const ScanParams& P, const Tables& tab, uint32_t key) {
-  const uint32_t hp = key >> (3 * P.L);
+  const uint32_t hp = tab.touched_list[key >> (3 * P.L)];  // touched id -> hash position
   const uint32_t lin = key & ((1u << (3 * P.L)) - 1u);
   int bx, by, bz;
   unpack3(tab.hkeys[hp], &bx, &by, &bz);
@@ -1635,65 +1683,67 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
   const int TB = 256;
   const KeyT* keys = nullptr;
   const uint32_t* vals = nullptr;
+  const uint32_t* scan_perm = nullptr;
+  const uint32_t* scan_limit = nullptr;
   if (P.kind == VBX_MERGED) {
     KeyT* k0 = reinterpret_cast<KeyT*>(c->pkeys[0]);
     KeyT* k1 = reinterpret_cast<KeyT*>(c->pkeys[1]);
-    k_point_bounds<<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, c->first_bits, c->d_state);
+    k_point_bounds<<<std::min<unsigned int>(grid_for(n, TB), 148 * 4), TB, 0, s>>>(P, d_xyz, c->first_bits, c->d_state);
     k_point_keys<KeyT><<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, k0, c->pvals[0], c->d_state);
     mk.mark(0);
-    const int end_bit = 8 * (int)sizeof(KeyT);  // the bits in use are known on the device only (ScanState::key_bits)
-    if (c->use_cub) {
-      cub::DoubleBuffer<KeyT> kb(k0, k1);
-      cub::DoubleBuffer<uint32_t> vb(c->pvals[0], c->pvals[1]);
-      size_t tmp = c->cub_tmp_bytes;
-      VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)n, 0, end_bit, s));
-      keys = kb.Current();
-      vals = vb.Current();
-    } else {
-      if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, end_bit, launches,
-                                  &c->d_state->key_bits)) {
-        return rc;
-      }
-      k_sort_to_a<KeyT><<<148, 256, 0, s>>>(k0, c->pvals[0], k1, c->pvals[1], c->sort_plan[0]);
-      keys = k0;
-      vals = c->pvals[0];
+    // the bits in use are known on the device only (ScanState::key_bits): passes beyond them exit at once
+    if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, 8 * (int)sizeof(KeyT), launches,
+                                &c->d_state->key_bits)) {
+      return rc;
     }
+    k_sort_to_a<KeyT><<<148, 256, 0, s>>>(k0, c->pvals[0], k1, c->pvals[1], c->sort_plan[0]);
+    keys = k0;
+    vals = c->pvals[0];
     mk.mark(1);
-    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(P, keys, vals, c->order_inv, c->head_list, c->first_bits,
-                                                               c->cnt, c->d_state);
-    // the reference's bundle order: ray_list[rank] = head (vbx_order.cuh)
-    k_bundle_order<KeyT><<<1, kOrderThreads, c->order_smem_bytes, s>>>(P, c->rehash, keys, vals, c->order_inv, c->head_list,
-                                                                       c->first_bits, c->order_scratch,
-                                                                       (uint32_t)(c->order_smem_bytes / 4), c->ray_list,
-                                                                       c->d_state);
+    k_heads<KeyT><<<grid_for((uint64_t)n + 1, TB), TB, 0, s>>>(P, keys, vals, c->order_inv, c->head_list, c->big_list,
+                                                               c->first_bits, c->cnt, c->d_state);
+    // The reference's bundle order (ray_list[rank] = bundle id, vbx_order.cuh) is one thread block's work
+    // and the fold (k_merge) does not need it: the two run side by side.  (With stage profiling on they
+    // run one after the other so that each gets its own time.)
+    cudaStream_t so = c->profiling ? s : c->side_stream;
+    if (so != s) {
+      VBX_CUDA(c, cudaEventRecord(c->ev_fork, s));
+      VBX_CUDA(c, cudaStreamWaitEvent(so, c->ev_fork, 0));
+    }
+    k_bundle_order<KeyT><<<1, kOrderThreads, c->order_smem_bytes, so>>>(P, c->rehash, keys, vals, c->order_inv, c->head_list,
+                                                                        c->first_bits, c->order_scratch,
+                                                                        (uint32_t)(c->order_smem_bytes / 4), c->ray_list,
+                                                                        c->d_state);
+    if (so != s) VBX_CUDA(c, cudaEventRecord(c->ev_join, so));
     mk.mark(12);
-    k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->ray_list, c->ray_p, c->ray_a, c->ray_c,
-                                           c->cnt, c->d_state);
+    k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
+                                           c->ray_c, c->cnt, c->d_state);
     mk.mark(8);
-    *launches += c->use_cub ? 6 + (end_bit + 7) / 8 : 6;
+    *launches += 7;
     if (!P.single_walk) {
       // the bundle count is only known on the device: launch for the worst case (every
       // point its own bundle); surplus threads exit on the first load
-      k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->ray_list,
+      k_rays_count<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys, c->head_list,
                                                            c->ray_p, c->ray_a, c->ray_c, c->cnt, c->set_start,
                                                            c->set_observed, c->d_state);
       *launches += 1;
     }
+    if (so != s) VBX_CUDA(c, cudaStreamWaitEvent(s, c->ev_join, 0));
+    // record offsets in RANK order: off[rank] = sum of cnt[ray_list[r]] over r < rank
+    scan_perm = c->ray_list;
+    scan_limit = &c->d_state->n_ray_list;
   } else {
     k_rays_count<KeyT><<<grid_for((uint64_t)n + 1, 128), 128, 0, s>>>(P, c->tab, d_xyz, d_rgba, order, keys,
-                                                                       c->ray_list, c->ray_p, c->ray_a, c->ray_c, c->cnt,
+                                                                       c->head_list, c->ray_p, c->ray_a, c->ray_c, c->cnt,
                                                                        c->set_start, c->set_observed, c->d_state);
     *launches += 1;
   }
   mk.mark(2);
-  if (c->use_cub) {
-    size_t tmp = c->cub_tmp_bytes;
-    VBX_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp, tmp, c->cnt, c->off, (int)(n + 1), s));
-  } else {
+  {
     const uint32_t tiles = (n + 1 + kScanTile - 1) / kScanTile;
     VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
-    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, c->off, n + 1, c->scan_status + 1,
-                                                                               c->scan_status);
+    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, scan_perm, scan_limit, c->off, n + 1,
+                                                                               c->scan_status + 1, c->scan_status);
   }
   k_set_total<<<1, 1, 0, s>>>(c->off, n, c->max_updates, c->d_state, 0);
   mk.mark(3);
@@ -1707,22 +1757,10 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
                           uint64_t* launches) {
   cudaStream_t s = c->stream;
   RecordView rv;
-  if (c->use_cub) {
-    cub::DoubleBuffer<uint32_t> kb(c->ckeys[0], c->ckeys[1]);
-    cub::DoubleBuffer<uint32_t> vb(c->cvals[0], c->cvals[1]);
-    size_t tmp = c->cub_tmp_bytes;
-    const int key_bits = 3 * c->L + bits_for(c->hcap - 1);
-    VBX_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, kb, vb, (int)K, 0, key_bits, s));
-    rv.keys[0] = rv.keys[1] = kb.Current();
-    rv.vals[0] = rv.vals[1] = vb.Current();
-    rv.plan = nullptr;
-    rv.d_total = nullptr;
-    rv.total_fixed = K;
-    *launches += 1 + (key_bits + 7) / 8;
-  } else {
+  {
     // K and the number of touched blocks are only known on the device: sort on every bit a
     // record key can have; passes whose digit is uniform are skipped on the device
-    const int key_bits = 3 * c->L + bits_for(c->hcap - 1);
+    const int key_bits = 32;
     if (c->sort_stream) {
       // pipelined submission: the record sort works on buffers private to this scan, so it leaves
       // the walk stream (which the next scan's ray walk is waiting for)
@@ -1732,7 +1770,7 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
       c->stream = s;
     }
     if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
-                                     &c->d_state->total_updates, 0, key_bits, launches)) {
+                                     &c->d_state->total_updates, 0, key_bits, launches, &c->d_state->rec_key_bits)) {
       return rc;
     }
     rv.keys[0] = c->ckeys[0];
@@ -1751,7 +1789,7 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
     VBX_CUDA(c, cudaStreamWaitEvent(c->apply_stream, c->sorted_event, 0));
     s = c->apply_stream;
   }
-  const unsigned int g_short = c->use_cub ? grid_for(K, 256) : 148 * 8;
+  const unsigned int g_short = 148 * 8;
   LongRuns lr;
   lr.start = c->long_list;
   lr.end = c->long_end;
@@ -1775,10 +1813,10 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   const uint32_t n = P.n;
   if (P.kind == VBX_MERGED && P.single_walk) {
     // a few thousand bundles of 100-300 steps: one warp per ray
-    k_rays_emit_warp<KeyT><<<148 * 8, 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off, c->ckeys[0],
-                                                   c->cvals[0], c->d_state);
+    k_rays_emit_warp<KeyT><<<148 * 8, 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->head_list, c->ray_p, c->cnt, c->off,
+                                                   c->ckeys[0], c->cvals[0], c->d_state);
   } else {
-    k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->ray_p, c->cnt, c->off,
+    k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->head_list, c->ray_p, c->cnt, c->off,
                                                         c->ckeys[0], c->cvals[0], c->d_state);
   }
   mk.mark(5);
@@ -1922,18 +1960,7 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   unsigned long long K = 0;
   uint32_t n_touched = 0;
   if (int rc = front_half<uint64_t>(c, P, d_xyz, d_rgba, order, mk, &launches, &keys64)) return rc;
-  if (c->use_cub) {
-    // the library sort needs K on the host: one stream synchronisation in the middle of the call
-    VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
-    VBX_CUDA(c, cudaStreamSynchronize(s));
-    if (int rc = check_state_errors(c, c->h_state->error)) return rc;
-    c->n_blocks = c->h_state->n_blocks;
-    K = c->h_state->total_updates;
-    n_touched = c->h_state->n_touched;
-    if (K > 0) {
-      if (int rc = back_half<uint64_t>(c, P, keys64, K, n_touched, mk, &launches)) return rc;
-    }
-  } else {
+  {
     // own sort: K stays on the device, the whole call is enqueued without a host round trip
     if (int rc = back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches)) return rc;
     VBX_CUDA(c, cudaEventRecord(c->ev1, s));
@@ -1996,7 +2023,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   if (kind < VBX_SIMPLE || kind > VBX_FAST) return fail(c, VBX_E_INVALID, "Unknown TSDF integrator type");
   if (n64 > c->max_points) return fail(c, VBX_E_CAPACITY, "cloud larger than max_points_per_scan");
   const vbx_tsdf_config& cfg = c->cfg;
-  const bool overlappable = kind != VBX_FAST && !(kind == VBX_MERGED && cfg.enable_anti_grazing) && !c->use_cub &&
+  const bool overlappable = kind != VBX_FAST && !(kind == VBX_MERGED && cfg.enable_anti_grazing) &&
                             cfg.integration_order_mode == 0 && n64 > 0;
   if (!overlappable) {
     // configurations whose front half touches the map or the Fast integrator's sets run in order
@@ -2123,18 +2150,19 @@ k_debug_order(RehashSchedule rs, const uint32_t* __restrict__ h_in, uint32_t B, 
   __shared__ uint32_t warp_sums[33];
   uint32_t n_final = 1;
   for (int k = 0; k < rs.count && rs.m[k] < B; ++k) n_final = rs.n[k];
-  uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *A = g.A, *bhead = g.bhead;
-  if (!force_global && 5u * B + n_final <= smem_words) {
+  uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *bkt = g.bkt, *A = g.A, *bhead = g.bhead;
+  if (!force_global && 6u * B + n_final <= smem_words) {
     h = order_smem;
     tau = h + B;
     tau2 = tau + B;
     next = tau2 + B;
-    A = next + B;
+    bkt = next + B;
+    A = bkt + B;
     bhead = A + B;
   }
   for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) h[e] = h_in[e];
   __syncthreads();
-  const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, A, bhead, warp_sums);
+  const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, bkt, A, bhead, n_final, warp_sums);
   for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) out[pos[e]] = e;
 }
 
@@ -2205,23 +2233,13 @@ int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {
   const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
   VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
   if (n) {
-    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, c->off, n, c->scan_status + 1,
-                                                                               c->scan_status);
+    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, nullptr, nullptr, c->off, n,
+                                                                               c->scan_status + 1, c->scan_status);
   }
   VBX_CUDA(c, cudaMemcpyAsync(out, c->off, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   VBX_CUDA(c, cudaGetLastError());
   return VBX_OK;
-}
-
-size_t cub_temp_bytes(uint32_t max_points, uint64_t max_updates) {
-  size_t a = 0, b = 0, d = 0;
-  cub::DoubleBuffer<uint64_t> k64(nullptr, nullptr);
-  cub::DoubleBuffer<uint32_t> k32(nullptr, nullptr), v32(nullptr, nullptr);
-  cub::DeviceRadixSort::SortPairs(nullptr, a, k64, v32, (int)max_points, 0, 64);
-  cub::DeviceRadixSort::SortPairs(nullptr, b, k32, v32, (int)std::min<uint64_t>(max_updates, 0x7fffffffull), 0, 32);
-  cub::DeviceScan::ExclusiveSum(nullptr, d, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_points + 1);
-  return std::max(a, std::max(b, d)) + 256;
 }
 
 }  // namespace vbx
