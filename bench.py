@@ -716,6 +716,13 @@ def main():
         conf["workload"] += f"_trunc{args.trunc:g}"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Exactly ONE line goes to stdout: the JSON.  Libraries (NCCL's version banner, make) write to file
+    # descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line is
+    # written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     import __graft_entry__ as g
 
     if rank == 0:

@@ -199,22 +199,23 @@ int alloc_order_scratch(vbx_ctx* c, OrderScratch* g, uint32_t** big_list, uint32
   uint32_t buckets = 1;
   for (int k = 0; k < c->rehash.count && c->rehash.m[k] < np; ++k) buckets = c->rehash.n[k];
   g->bucket_cap = buckets;
-  VBX_CUDA(c, dmalloc(&g->h, np));
+  VBX_CUDA(c, dmalloc(&g->h, 2 * np));
   VBX_CUDA(c, dmalloc(&g->tau, np));
   VBX_CUDA(c, dmalloc(&g->tau2, np));
   VBX_CUDA(c, dmalloc(&g->next, np));
   VBX_CUDA(c, dmalloc(&g->bkt, np));
   VBX_CUDA(c, dmalloc(&g->A, np));
   VBX_CUDA(c, dmalloc(&g->bhead, (size_t)buckets));
-  VBX_CUDA(c, dmalloc(&g->head_of, np));
-  VBX_CUDA(c, dmalloc(&g->wp, np / 32 + 2));
+  VBX_CUDA(c, dmalloc(&g->head_of, 2 * np));
+  VBX_CUDA(c, dmalloc(&g->wp, 2 * (np / 32 + 2)));
+  VBX_CUDA(c, dmalloc(&g->cta_tot, 64));
   VBX_CUDA(c, dmalloc(big_list, np / 256 + 2));
   VBX_CUDA(c, dmalloc(first_bits, 2 * (np / 32 + 2)));
   VBX_CUDA(c, cudaMemsetAsync(*first_bits, 0, 2 * (np / 32 + 2) * sizeof(uint32_t), c->stream_main));
   return VBX_OK;
 }
 void free_order_scratch(OrderScratch* g, uint32_t* big_list, uint32_t* first_bits) {
-  void* ptrs[] = {g->h, g->tau, g->tau2, g->next, g->bkt, g->A, g->bhead, g->head_of, g->wp, big_list, first_bits};
+  void* ptrs[] = {g->h, g->tau, g->tau2, g->next, g->bkt, g->A, g->bhead, g->head_of, g->wp, g->cta_tot, big_list, first_bits};
   for (void* p : ptrs) {
     if (p) cudaFree(p);
   }

@@ -128,90 +128,216 @@ __device__ __forceinline__ uint32_t* raise_cnt(ScanState* st, uint32_t k) {
   return k % 3u == 2u ? &st->raise_n2 : &st->raise_n[k % 3u];
 }
 
-// Step (1), esdf_integrator.cc:136-287: one thread per voxel of every listed block.
-// esdf_counts: [1] lower [2] raise [3] new
-__global__ void k_esdf_propagate(EsdfParams E, Tables tab, const uint32_t* __restrict__ block_list, uint32_t n_blocks,
-                                 uint32_t* open_list, uint32_t* raise_list, uint32_t* seed_list, ScanState* st) {
-  const uint32_t vpb = 1u << (3 * E.L);
-  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (uint64_t)min(n_blocks, st->esdf_counts[0]) * vpb) return;  // (n_blocks is the launch's upper bound)
-  const uint32_t slot = block_list[gid >> (3 * E.L)];
-  const uint32_t lin = (uint32_t)(gid & (vpb - 1));
-  const uint32_t ref = (slot << (3 * E.L)) | lin;
-  const TsdfVoxel tv = tab.tsdf[(size_t)slot * vpb + lin];
-  EsdfWords* ep = reinterpret_cast<EsdfWords*>(tab.esdf) + (size_t)slot * vpb + lin;
+// Step (1), esdf_integrator.cc:136-287, for ONE voxel: the stored ESDF voxel `ev` against its TSDF voxel `tv`.
+// Returns false when the voxel is left alone (unobserved in the TSDF, cc:153-164); otherwise ev holds the new
+// voxel and the flags say which queues it joins.  kind: 0 none, 1 lower, 2 raise, 3 new (the VLOG counters).
+struct EsdfClass {
+  bool to_open, to_raise, to_seed;
+  int kind;
+};
+__device__ __forceinline__ bool esdf_classify(const EsdfParams& E, const TsdfVoxel& tv, EsdfWords& ev, EsdfClass& k) {
+  k.to_open = k.to_raise = k.to_seed = false;
+  k.kind = 0;
   if (tv.weight < E.min_weight) {  // unobserved in the TSDF, cc:153-164
     if (!E.incremental && E.add_occupied_crust) {
-      ep->distance = -E.default_distance;
-      ep->flags = (ep->flags & ~(kFlagObserved | kFlagHallucinated | kFlagFixed)) | kBitObserved | kBitHallucinated;
+      ev.distance = -E.default_distance;
+      ev.flags = (ev.flags & ~(kFlagObserved | kFlagHallucinated | kFlagFixed)) | kBitObserved | kBitHallucinated;
+      return true;
     }
-    return;
+    return false;
   }
-  EsdfWords ev = *ep;
   const bool observed = (ev.flags & kFlagObserved) != 0, halluc = (ev.flags & kFlagHallucinated) != 0;
   bool fixed = (ev.flags & kFlagFixed) != 0, in_queue = (ev.flags & kFlagInQueue) != 0;
   const bool tfixed = fabsf(tv.distance) < E.min_distance;  // isFixed, esdf_integrator.h:131-133
   const float sgn_default = (float)signum_d(tv.distance) * E.default_distance;
   const float md = E.min_diff;
-  bool to_open = false, to_raise = false, to_seed = false, reset_parent = false;
+  bool reset_parent = false;
   if (!observed || halluc) {  // nothing there before, cc:174-200
-    if (halluc) to_raise = true;
+    if (halluc) k.to_raise = true;
     if (tfixed) {
       ev.distance = tv.distance;
       fixed = true;
-      to_open = true;
+      k.to_open = true;
     } else {
       ev.distance = sgn_default;
       fixed = false;
-      if (E.incremental) to_seed = true;
+      if (E.incremental) k.to_seed = true;
     }
     reset_parent = true;
-    atomicAdd(&st->esdf_counts[3], 1u);
+    k.kind = 3;
   } else if (tfixed || fixed) {  // cc:211-262
     if (!tfixed) {
       ev.distance = sgn_default;
       reset_parent = true;
       fixed = false;
-      to_raise = true;
-      to_open = true;
-      atomicAdd(&st->esdf_counts[2], 1u);
+      k.to_raise = true;
+      k.to_open = true;
+      k.kind = 2;
     } else if ((ev.distance > 0.0f && tv.distance + md < ev.distance) ||
                (ev.distance <= 0.0f && tv.distance - md > ev.distance)) {
       fixed = tfixed;
       ev.distance = fixed ? tv.distance : sgn_default;
       reset_parent = true;
-      to_open = true;
-      atomicAdd(&st->esdf_counts[1], 1u);
+      k.to_open = true;
+      k.kind = 1;
     } else if ((ev.distance > 0.0f && tv.distance - md > ev.distance) ||
                (ev.distance <= 0.0f && tv.distance + md < ev.distance)) {
       fixed = tfixed;
       ev.distance = fixed ? tv.distance : sgn_default;
       reset_parent = true;
-      to_raise = true;
-      to_open = true;
-      atomicAdd(&st->esdf_counts[2], 1u);
+      k.to_raise = true;
+      k.to_open = true;
+      k.kind = 2;
     }
   } else if (signum_d(tv.distance) != signum_d(ev.distance)) {  // cc:263-282
     if (tv.distance < ev.distance) {
       ev.distance = sgn_default;
       reset_parent = true;
-      to_open = true;
-      atomicAdd(&st->esdf_counts[1], 1u);
+      k.to_open = true;
+      k.kind = 1;
     } else {
       ev.distance = sgn_default;
       reset_parent = true;
-      to_raise = true;
-      atomicAdd(&st->esdf_counts[2], 1u);
+      k.to_raise = true;
+      k.kind = 2;
     }
   }
-  if (to_open) in_queue = true;
+  if (k.to_open) in_queue = true;
   if (reset_parent) ev.px = ev.py = ev.pz = 0;
   // esdf_voxel.observed = true; hallucinated = false, cc:285-286
   ev.flags = kBitObserved | (in_queue ? kBitInQueue : 0u) | (fixed ? kBitFixed : 0u);
-  *ep = ev;
-  if (to_open) push(open_list, &st->frontier_n[0], E.cap, ref, st);
-  if (to_raise) push(raise_list, &st->raise_n[0], E.cap, ref, st);
-  if (to_seed) push(seed_list, &st->seed_n, E.cap, ref, st);
+  return true;
+}
+
+// one queue append per warp instead of one per voxel
+__device__ __forceinline__ void push_warp(bool want, uint32_t* list, uint32_t* count, uint32_t cap, uint32_t ref, ScanState* st) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (want) {
+    const uint32_t j = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    if (j < cap) {
+      list[j] = ref;
+    } else {
+      atomicOr(&st->error, kErrUpdatesFull);
+    }
+  }
+}
+
+// ---- TMA helpers (PTX: mbarrier + cp.async.bulk, the bulk-copy path of the tensor memory accelerator)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared, completion signalled on the mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void tma_store_bulk(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Step (1) over every listed block: "HOT LOOP 1" of SURVEY.md 3.3 -- a stream of whole blocks, 12 B in and
+// 20 B in/out per voxel.  One thread block per voxel block: the TSDF slab (48 KiB at 16^3) and the ESDF slab
+// (80 KiB) are staged into shared memory by two TMA bulk copies, classified from there (every thread a few
+// voxels), and the ESDF slab goes back with one bulk store.  Queue appends are warp-aggregated, the VLOG
+// counters block-aggregated.  esdf_counts: [1] lower [2] raise [3] new.
+__global__ void __launch_bounds__(1024)
+k_esdf_propagate(EsdfParams E, Tables tab, const uint32_t* __restrict__ block_list, uint32_t n_blocks,
+                 uint32_t* open_list, uint32_t* raise_list, uint32_t* seed_list, ScanState* st) {
+  extern __shared__ __align__(128) unsigned char slab[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_cnt[4];
+  const uint32_t vpb = 1u << (3 * E.L);
+  if (blockIdx.x >= min(n_blocks, st->esdf_counts[0])) return;  // (n_blocks is the launch's upper bound)
+  const uint32_t slot = block_list[blockIdx.x];
+  TsdfVoxel* s_tsdf = reinterpret_cast<TsdfVoxel*>(slab);
+  EsdfWords* s_esdf = reinterpret_cast<EsdfWords*>(slab + (size_t)vpb * sizeof(TsdfVoxel));
+  EsdfWords* g_esdf = reinterpret_cast<EsdfWords*>(tab.esdf) + (size_t)slot * vpb;
+  const uint32_t tsdf_bytes = vpb * (uint32_t)sizeof(TsdfVoxel), esdf_bytes = vpb * (uint32_t)sizeof(EsdfVoxel);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_async_smem();
+  }
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const bool bulk = (tsdf_bytes & 15u) == 0u && (esdf_bytes & 15u) == 0u;  // (not for one-voxel blocks)
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, tsdf_bytes + esdf_bytes);
+      tma_load_bulk(s_tsdf, tab.tsdf + (size_t)slot * vpb, tsdf_bytes, &bar);
+      tma_load_bulk(s_esdf, g_esdf, esdf_bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (uint32_t lin = threadIdx.x; lin < vpb; lin += blockDim.x) {
+      s_tsdf[lin] = tab.tsdf[(size_t)slot * vpb + lin];
+      s_esdf[lin] = g_esdf[lin];
+    }
+    __syncthreads();
+  }
+  uint32_t n_kind[4] = {0, 0, 0, 0};
+  for (uint32_t lin0 = 0; lin0 < vpb; lin0 += blockDim.x) {
+    const uint32_t lin = lin0 + threadIdx.x;
+    EsdfClass k;
+    k.to_open = k.to_raise = k.to_seed = false;
+    k.kind = 0;
+    if (lin < vpb) {
+      EsdfWords ev = s_esdf[lin];
+      if (esdf_classify(E, s_tsdf[lin], ev, k)) s_esdf[lin] = ev;
+      n_kind[k.kind] += 1;
+    }
+    const uint32_t ref = (slot << (3 * E.L)) | lin;
+    push_warp(k.to_open, open_list, &st->frontier_n[0], E.cap, ref, st);
+    push_warp(k.to_raise, raise_list, &st->raise_n[0], E.cap, ref, st);
+    push_warp(k.to_seed, seed_list, &st->seed_n, E.cap, ref, st);
+  }
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    const uint32_t w = __reduce_add_sync(0xffffffffu, n_kind[q]);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[q], w);
+  }
+  fence_async_smem();  // the slab written through the generic proxy is read by the bulk store (async proxy)
+  __syncthreads();
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      tma_store_bulk(g_esdf, s_esdf, esdf_bytes);
+      tma_store_commit_and_wait();
+    }
+  } else {
+    for (uint32_t lin = threadIdx.x; lin < vpb; lin += blockDim.x) g_esdf[lin] = s_esdf[lin];
+  }
+  if (threadIdx.x >= 1 && threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&st->esdf_counts[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // updateVoxelFromNeighbors (cc:498-530) for the new free-space voxels of an incremental update:
@@ -601,6 +727,8 @@ int esdf_create(vbx_ctx* c, const vbx_esdf_config* cfg) {
   VBX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->esdf_touched), c->frontier_cap * sizeof(uint32_t)));
   int dev = c->device, sms = 0, per_sm_r = 0, per_sm_l = 0;
   VBX_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  VBX_CUDA(c, cudaFuncSetAttribute(k_esdf_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)c->vox_per_block * (sizeof(TsdfVoxel) + sizeof(EsdfVoxel)))));
   VBX_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, k_esdf_raise, 256, 0));
   VBX_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, k_esdf_lower, 256, 0));
   // persistent grids: the wavefront is a chain of grid-wide barriers over small frontiers, so the
@@ -796,7 +924,9 @@ static int esdf_run(vbx_ctx* c, int batch, int incremental, int clear_updated_fl
   launches += 1;
   if (nb > 0 || pending) {
     if (nb > 0) {
-      k_esdf_propagate<<<grid_for((uint64_t)nb * c->vox_per_block, 256), 256, 0, s>>>(
+      // one thread block per voxel block, both slabs staged by the TMA
+      const size_t slab_bytes = (size_t)c->vox_per_block * (sizeof(TsdfVoxel) + sizeof(EsdfVoxel));
+      k_esdf_propagate<<<nb, (unsigned int)std::max<uint32_t>(32u, std::min<uint32_t>(1024u, c->vox_per_block)), slab_bytes, s>>>(
           E, c->tab, c->esdf_block_list, nb, c->frontier[0], c->raise_q[0], c->esdf_seed_list, c->d_state);
       launches += 1;
     }

@@ -38,16 +38,17 @@ struct RehashSchedule {  // event k: when the map holds m[k] elements the bucket
   uint32_t n[30];
 };
 
-struct OrderScratch {     // global-memory fallback when a map's tables do not fit shared memory
-  uint32_t* h;            // [cap] LongIndexHash per element (insertion order)
+struct OrderScratch {     // global tables (the clearing map's h / head_of / wp follow the normal map's)
+  uint32_t* h;            // [2 * cap] LongIndexHash per element (insertion order)
   uint32_t* tau;          // [cap] current insertion time
   uint32_t* tau2;         // [cap]
   uint32_t* next;         // [cap] bucket chain
   uint32_t* bkt;          // [cap] bucket of the element in the current table
   uint32_t* A;            // [cap] group sizes by creation time -> suffix sums
   uint32_t* bhead;        // [bucket_cap]
-  uint32_t* head_of;      // [cap] element -> sorted position of its bundle head
-  uint32_t* wp;           // [cap / 32 + 1] popcount prefix of the first-occurrence bitmap
+  uint32_t* head_of;      // [2 * cap] element -> bundle id
+  uint32_t* wp;           // [2 * (cap / 32 + 2)] popcount prefixes of the first-occurrence bitmaps
+  uint32_t* cta_tot;      // [64] per-block totals of the grid-wide suffix sum
   uint32_t cap, bucket_cap;
 };
 

@@ -33,10 +33,14 @@
 #include <cstring>
 #include <unordered_map>  // std::__detail::_Prime_rehash_policy: the growth schedule the reference's map follows
 
+#include <cooperative_groups.h>
+
 #include "vbx_engine.h"
 #include "vbx_hash.cuh"
 #include "vbx_sort.cuh"
 #include "vbx_order.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace vbx {
 
@@ -297,74 +301,236 @@ __global__ void k_heads(ScanParams P, const KeyT* __restrict__ keys, const uint3
 __device__ __forceinline__ uint32_t long_index_hash(int x, int y, int z) {
   return (uint32_t)x + (uint32_t)y * 17191u + (uint32_t)z * 295530481u;
 }
-// The reference's bundle order (vbx_order.cuh): ONE thread block ranks the bundles of the normal map,
-// then those of the clearing map, and writes ray_list[rank] = bundle id j.
-// Ranks are dense: normal bundles 0 .. B0-1 in voxel_map's iteration order, clearing bundles
-// B0 .. B0+B1-1 in clear_map's (integrateRays(false) runs before integrateRays(true), cc:323-335).
-// Tables live in shared memory when they fit (a few thousand bundles), else in global scratch.
-template <typename KeyT>
+// ---- The reference's bundle order (vbx_order.cuh) in three kernels:
+//   k_order_prefix  per-word popcount prefixes of the two first-occurrence bitmaps (one thread block);
+//                   the bundle counts B0 (normal map) and B1 (clearing map)
+//   k_order_heads   one thread per bundle: its insertion index e into the reference's map (= number of
+//                   earlier first occurrences), LongIndexHash of its voxel -> h[map][e], head_of[map][e]
+//   k_bundle_order  the iteration order of each map; writes ray_list[rank] = bundle id.  Ranks are
+//                   dense: normal bundles 0 .. B0-1 in voxel_map's iteration order, clearing bundles
+//                   B0 .. B0+B1-1 in clear_map's (integrateRays(false) runs before integrateRays(true),
+//                   cc:323-335).  A cooperative launch: when a map's tables fit shared memory (a few
+//                   thousand bundles: 640 x 480 scans) block 0 does everything alone and the others
+//                   leave at once; larger maps (LiDAR: ~50 k bundles) run their late rehash stages
+//                   grid-wide on global tables, the early (small) stages still in block 0's shared memory.
+// The clearing map's arrays follow the normal map's at offset g.cap.
 __global__ void __launch_bounds__(kOrderThreads)
-k_bundle_order(ScanParams P, RehashSchedule rs, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
-               const uint32_t* __restrict__ order_inv, const uint32_t* __restrict__ head_list,
-               const uint32_t* __restrict__ first_bits, OrderScratch g, uint32_t smem_words,
-               uint32_t* __restrict__ ray_list, ScanState* st) {
-  extern __shared__ uint32_t order_smem[];
+k_order_prefix(uint32_t n, const uint32_t* __restrict__ first_bits, OrderScratch g, ScanState* st) {
   __shared__ uint32_t warp_sums[33];
   const uint32_t tid = threadIdx.x;
+  const uint32_t words = (n + 31u) >> 5;
+  const uint32_t per = (words + kOrderThreads - 1) / kOrderThreads;
+  const uint32_t lo = min(tid * per, words), hi = min(lo + per, words);
+  for (int mp = 0; mp < 2; ++mp) {
+    const uint32_t* bits = first_bits + (mp ? words : 0u);
+    uint32_t* wp = g.wp + (mp ? words : 0u);
+    uint32_t sum = 0;
+    for (uint32_t w = lo; w < hi; ++w) sum += (uint32_t)__popc(bits[w]);  // (independent loads: all in flight together)
+    uint32_t total;
+    uint32_t run = order_block_scan(sum, warp_sums, &total);
+    for (uint32_t w = lo; w < hi; ++w) {
+      wp[w] = run;
+      run += (uint32_t)__popc(bits[w]);
+    }
+    if (tid == 0) {
+      if (mp == 0) st->n_rays = total; else st->n_clear_rays = total;
+    }
+  }
+}
+
+template <typename KeyT>
+__global__ void k_order_heads(ScanParams P, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+                              const uint32_t* __restrict__ order_inv, const uint32_t* __restrict__ head_list,
+                              const uint32_t* __restrict__ first_bits, OrderScratch g, const ScanState* st) {
   const uint32_t words = (P.n + 31u) >> 5;
   const uint32_t n_heads = st->n_ray_list;
   const KeyLayout kl = key_layout(st);
-  uint32_t base_rank = 0;
-  for (int mp = 0; mp < 2; ++mp) {
-    const uint32_t* bits = first_bits + (mp ? words : 0u);
-    // popcount prefix of the bitmap: insertion index of a bundle = number of earlier first occurrences
-    uint32_t B = 0;
-    for (uint32_t c = 0; c < words; c += kOrderThreads) {
-      const uint32_t w = c + tid;
-      const uint32_t v = w < words ? (uint32_t)__popc(bits[w]) : 0u;
-      uint32_t total;
-      const uint32_t ex = order_block_scan(v, warp_sums, &total);
-      if (w < words) g.wp[w] = B + ex;
-      B += total;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_heads; j += gridDim.x * blockDim.x) {
+    const uint32_t i = head_list[j] & ~kHeadBig;
+    const uint64_t key = (uint64_t)keys[i];
+    const uint32_t mp = key_is_clearing(kl, key) ? 1u : 0u;
+    const uint32_t t0 = point_order_inv(P, order_inv, vals[i]);
+    const uint32_t w = (mp ? words : 0u) + (t0 >> 5);
+    const uint32_t e = g.wp[w] + (uint32_t)__popc(first_bits[w] & ((1u << (t0 & 31u)) - 1u));
+    if (e >= g.cap) continue;  // (cannot happen: cap = max_points_per_scan)
+    const I3 v = key_voxel(kl, key);
+    g.h[mp * g.cap + e] = long_index_hash(v.x, v.y, v.z);
+    g.head_of[mp * g.cap + e] = j;
+  }
+}
+
+// grid-wide version of order_positions (vbx_order.cuh) on global tables; every block of the cooperative
+// grid calls it.  cta_tot: one word per block.
+__device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, const uint32_t* tau, uint32_t* tau_out,
+                                     uint32_t* next, uint32_t* bkt, uint32_t* A, uint32_t* bhead, uint32_t m, uint32_t n,
+                                     uint32_t tag, uint32_t B, uint32_t* cta_tot, uint32_t* warp_sums) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t tg = tag << 20;
+  for (uint32_t b = gtid; b < m; b += gthreads) {
+    const uint32_t gb = h[b] % n;
+    bkt[b] = gb;
+    const uint32_t old = atomicExch(&bhead[gb], tg | b);
+    next[b] = (old >> 20) == tag ? (old & 0xfffffu) : kOrderNil;
+  }
+  grid.sync();
+  for (uint32_t b = gtid; b < m; b += gthreads) {
+    const uint32_t tb = __ldcg(&tau[b]);
+    uint32_t cmin = kOrderNil, size = 0;
+    for (uint32_t c = __ldcg(&bhead[bkt[b]]) & 0xfffffu; c != kOrderNil; c = __ldcg(&next[c])) {
+      cmin = min(cmin, __ldcg(&tau[c]));
+      ++size;
     }
-    if (mp == 0 && tid == 0) st->n_rays = B;
-    if (mp == 1 && tid == 0) st->n_clear_rays = B;
-    __syncthreads();
-    if (B == 0) continue;
-    if (B > g.cap || B > (1u << 20)) {  // cap = max_points_per_scan; bucket heads pack the element into 20 bits
-      if (tid == 0) atomicOr(&st->error, kErrUpdatesFull);
+    A[tb] = cmin == tb ? size : 0u;
+  }
+  grid.sync();
+  // exclusive suffix sum of A over times: block c owns a contiguous range of times (block 0 the highest),
+  // thread t of it a contiguous run inside
+  {
+    const uint32_t per_cta = (m + gridDim.x - 1) / gridDim.x;
+    const uint32_t chi = m > blockIdx.x * per_cta ? m - blockIdx.x * per_cta : 0u;
+    const uint32_t clo = chi > per_cta ? chi - per_cta : 0u;
+    const uint32_t per = (per_cta + kOrderThreads - 1) / kOrderThreads;
+    const uint32_t hi = chi > clo + threadIdx.x * per ? chi - threadIdx.x * per : clo;
+    const uint32_t lo = hi > clo + per ? hi - per : clo;
+    uint32_t sum = 0;
+    for (uint32_t t = lo; t < hi; ++t) sum += __ldcg(&A[t]);
+    uint32_t total;
+    uint32_t run = order_block_scan(sum, warp_sums, &total);
+    if (threadIdx.x == 0) cta_tot[blockIdx.x] = total;
+    grid.sync();
+    uint32_t above = 0;  // elements at times above this block's range
+    for (uint32_t c = 0; c < blockIdx.x; ++c) above += __ldcg(&cta_tot[c]);
+    run += above;
+    for (uint32_t t = hi; t-- > lo;) {
+      const uint32_t v = __ldcg(&A[t]);
+      A[t] = run;
+      run += v;
+    }
+  }
+  grid.sync();
+  for (uint32_t b = gtid; b < B; b += gthreads) {
+    if (b >= m) {  // inserted after this rehash: the insertion index stays its time
+      tau_out[b] = b;
       continue;
     }
-    // bucket count after B insertions
-    uint32_t n_final = 1;
-    for (int k = 0; k < rs.count && rs.m[k] < B; ++k) n_final = rs.n[k];
-    uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *bkt = g.bkt, *A = g.A, *bhead = g.bhead;
-    if (6u * B + n_final <= smem_words) {
-      h = order_smem;
+    const uint32_t tb = __ldcg(&tau[b]);
+    uint32_t cmin = kOrderNil, later = 0;
+    for (uint32_t c = __ldcg(&bhead[bkt[b]]) & 0xfffffu; c != kOrderNil; c = __ldcg(&next[c])) {
+      const uint32_t tc = __ldcg(&tau[c]);
+      cmin = min(cmin, tc);
+      later += tc > tb ? 1u : 0u;
+    }
+    tau_out[b] = __ldcg(&A[cmin]) + later;
+  }
+  grid.sync();
+}
+
+__global__ void __launch_bounds__(kOrderThreads)
+k_bundle_order(RehashSchedule rs, OrderScratch g, uint32_t smem_words, uint32_t* __restrict__ ray_list, uint32_t* cta_tot,
+               ScanState* st) {
+  extern __shared__ uint32_t order_smem[];
+  __shared__ uint32_t warp_sums[33];
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t tid = threadIdx.x;
+  const uint32_t B_of[2] = {st->n_rays, st->n_clear_rays};
+  uint32_t n_of[2];
+  bool small = true, bad = false;
+  for (int mp = 0; mp < 2; ++mp) {
+    uint32_t nf = 1;
+    for (int k = 0; k < rs.count && rs.m[k] < B_of[mp]; ++k) nf = rs.n[k];
+    n_of[mp] = nf;
+    if (6u * B_of[mp] + nf > smem_words) small = false;
+    // bucket heads pack the element into 20 bits; cap = max_points_per_scan
+    if (B_of[mp] > g.cap || B_of[mp] > (1u << 20) || nf > g.bucket_cap) bad = true;
+  }
+  if (bad) {
+    if (blockIdx.x == 0 && tid == 0) atomicOr(&st->error, kErrUpdatesFull);
+    return;
+  }
+  if (small && blockIdx.x != 0) return;  // (every block takes the same decision: nobody waits at a grid barrier)
+  uint32_t base_rank = 0;
+  for (int mp = 0; mp < 2; ++mp) {
+    const uint32_t B = B_of[mp], n_final = n_of[mp];
+    if (B == 0) continue;
+    const uint32_t* gh = g.h + mp * g.cap;
+    const uint32_t* head_of = g.head_of + mp * g.cap;
+    uint32_t *h = order_smem, *tau = h, *tau2 = h, *next = h, *bkt = h, *A = h, *bhead = h;
+    if (small) {
       tau = h + B;
       tau2 = tau + B;
       next = tau2 + B;
       bkt = next + B;
       A = bkt + B;
       bhead = A + B;
-    } else if (n_final > g.bucket_cap) {
-      if (tid == 0) atomicOr(&st->error, kErrUpdatesFull);
+      for (uint32_t e = tid; e < B; e += kOrderThreads) h[e] = gh[e];
+      __syncthreads();
+      const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, bkt, A, bhead, n_final, warp_sums);
+      for (uint32_t e = tid; e < B; e += kOrderThreads) ray_list[base_rank + pos[e]] = head_of[e];
+      __syncthreads();
+      base_rank += B;
       continue;
     }
-    for (uint32_t j = tid; j < n_heads; j += kOrderThreads) {
-      const uint32_t i = head_list[j] & ~kHeadBig;
-      const uint64_t key = (uint64_t)keys[i];
-      if ((key_is_clearing(kl, key) ? 1 : 0) != mp) continue;
-      const uint32_t t0 = point_order_inv(P, order_inv, vals[i]);
-      const uint32_t e = g.wp[t0 >> 5] + (uint32_t)__popc(bits[t0 >> 5] & ((1u << (t0 & 31u)) - 1u));
-      const I3 v = key_voxel(kl, key);
-      h[e] = long_index_hash(v.x, v.y, v.z);
-      g.head_of[e] = j;
+    // ---- a large map.  Stages whose tables fit shared memory run in block 0 alone ...
+    int k_small = 0;       // rehash events [0, k_small) are handled in shared memory
+    uint32_t m_small = 0;  // elements present at the last of them
+    uint32_t n_small = 1;  // bucket count after it
+    for (int k = 0; k < rs.count && rs.m[k] < B; ++k) {
+      if (6u * rs.m[k] + (k > 0 ? rs.n[k - 1] : 1u) > smem_words) break;
+      k_small = k + 1;
+      m_small = rs.m[k];
+      n_small = rs.n[k];
     }
-    __syncthreads();
-    const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, bkt, A, bhead, n_final, warp_sums);
-    for (uint32_t e = tid; e < B; e += kOrderThreads) ray_list[base_rank + pos[e]] = g.head_of[e];
-    __syncthreads();
+    uint32_t* cur = g.tau;   // global arrays of the grid-wide stages
+    uint32_t* oth = g.tau2;
+    if (blockIdx.x == 0) {
+      // the first m_small elements through rehash events 0 .. k_small-1: order_run's loop on a prefix
+      h = order_smem;
+      tau = h + m_small;
+      tau2 = tau + m_small;
+      next = tau2 + m_small;
+      bkt = next + m_small;
+      A = bkt + m_small;
+      bhead = A + m_small;
+      for (uint32_t e = tid; e < m_small; e += kOrderThreads) {
+        h[e] = gh[e];
+        tau[e] = e;
+      }
+      const uint32_t n_clear = k_small > 1 ? rs.n[k_small - 2] : 1u;
+      for (uint32_t j = tid; j < n_clear; j += kOrderThreads) bhead[j] = 0u;
+      __syncthreads();
+      uint32_t n_cur = 1, tag = 1;
+      uint32_t* c0 = tau;
+      uint32_t* c1 = tau2;
+      for (int k = 0; k < k_small; ++k) {
+        const uint32_t mk = rs.m[k];
+        if (mk > 0) {
+          order_positions(h, c0, c1, next, bkt, A, bhead, mk, n_cur, tag++, warp_sums);
+          for (uint32_t e = mk + tid; e < m_small; e += kOrderThreads) c1[e] = e;
+          __syncthreads();
+          uint32_t* t = c0;
+          c0 = c1;
+          c1 = t;
+        }
+        n_cur = rs.n[k];
+      }
+      for (uint32_t e = tid; e < m_small; e += kOrderThreads) cur[e] = c0[e];
+    }
+    // ... the rest grid-wide.  Times of elements not yet inserted = their insertion index.
+    const uint32_t gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
+    for (uint32_t e = m_small + gtid; e < B; e += gthreads) cur[e] = e;
+    for (uint32_t j = gtid; j < n_final; j += gthreads) g.bhead[j] = 0u;
+    grid.sync();
+    uint32_t n_cur = n_small, tag = 1;
+    for (int k = k_small; k < rs.count && rs.m[k] < B; ++k) {
+      order_positions_grid(grid, gh, cur, oth, g.next, g.bkt, g.A, g.bhead, rs.m[k], n_cur, tag++, B, cta_tot, warp_sums);
+      uint32_t* t = cur;
+      cur = oth;
+      oth = t;
+      n_cur = rs.n[k];
+    }
+    order_positions_grid(grid, gh, cur, oth, g.next, g.bkt, g.A, g.bhead, B, n_cur, tag, B, cta_tot, warp_sums);
+    for (uint32_t e = gtid; e < B; e += gthreads) ray_list[base_rank + __ldcg(&oth[e])] = head_of[e];
+    grid.sync();  // the arrays are reused by the other map
     base_rank += B;
   }
 }
@@ -1581,10 +1747,7 @@ int init_bundle_order(vbx_ctx* c) {
   VBX_CUDA(c, cudaGetDevice(&dev));
   VBX_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   c->order_smem_bytes = (size_t)std::max(0, max_optin - 2048) & ~(size_t)15;
-  VBX_CUDA(c, cudaFuncSetAttribute(k_bundle_order<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)c->order_smem_bytes));
-  VBX_CUDA(c, cudaFuncSetAttribute(k_bundle_order<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)c->order_smem_bytes));
+  VBX_CUDA(c, cudaFuncSetAttribute(k_bundle_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->order_smem_bytes));
   return VBX_OK;
 }
 
@@ -1674,6 +1837,25 @@ __global__ void k_sort_to_a(KeyT* keys_a, uint32_t* vals_a, const KeyT* keys_b, 
   }
 }
 
+// k_order_prefix, k_order_heads, k_bundle_order on stream `so` (see the kernels).
+constexpr int kOrderGrid = 32;  // blocks of the cooperative k_bundle_order launch (only large maps use more than one)
+template <typename KeyT>
+static int launch_bundle_order(vbx_ctx* c, cudaStream_t so, const ScanParams& P, const KeyT* keys, const uint32_t* vals,
+                               uint32_t smem_words) {
+  k_order_prefix<<<1, kOrderThreads, 0, so>>>(P.n, c->first_bits, c->order_scratch, c->d_state);
+  k_order_heads<KeyT><<<std::min<unsigned int>(grid_for(P.n, 256), 148 * 2), 256, 0, so>>>(
+      P, keys, vals, c->order_inv, c->head_list, c->first_bits, c->order_scratch, c->d_state);
+  RehashSchedule rs = c->rehash;
+  OrderScratch g = c->order_scratch;
+  uint32_t* ray_list = c->ray_list;
+  uint32_t* cta_tot = c->order_scratch.cta_tot;
+  ScanState* st = c->d_state;
+  void* args[] = {&rs, &g, &smem_words, &ray_list, &cta_tot, &st};
+  VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_bundle_order, dim3(kOrderGrid), dim3(kOrderThreads), args,
+                                          c->order_smem_bytes, so));
+  return VBX_OK;
+}
+
 // Stages up to and including k_assign: everything that decides WHICH voxels are updated.
 template <typename KeyT>
 static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8_t* d_rgba, const uint32_t* order,
@@ -1710,16 +1892,13 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
       VBX_CUDA(c, cudaEventRecord(c->ev_fork, s));
       VBX_CUDA(c, cudaStreamWaitEvent(so, c->ev_fork, 0));
     }
-    k_bundle_order<KeyT><<<1, kOrderThreads, c->order_smem_bytes, so>>>(P, c->rehash, keys, vals, c->order_inv, c->head_list,
-                                                                        c->first_bits, c->order_scratch,
-                                                                        (uint32_t)(c->order_smem_bytes / 4), c->ray_list,
-                                                                        c->d_state);
+    if (int rc = launch_bundle_order<KeyT>(c, so, P, keys, vals, (uint32_t)(c->order_smem_bytes / 4))) return rc;
     if (so != s) VBX_CUDA(c, cudaEventRecord(c->ev_join, so));
     mk.mark(12);
     k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
                                            c->ray_c, c->cnt, c->d_state);
     mk.mark(8);
-    *launches += 7;
+    *launches += 9;
     if (!P.single_walk) {
       // the bundle count is only known on the device: launch for the worst case (every
       // point its own bundle); surplus threads exit on the first load
@@ -2140,44 +2319,39 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
 }
 
 // ------------------------------------------------------------------ test hooks
-// k_bundle_order's core on caller-supplied hashes (element e = e-th inserted key, hash h_in[e]):
-// out[p] = the element at iteration position p.  tests/test_order_gpu.py compares it with a real
-// std::unordered_map.
-__global__ void __launch_bounds__(kOrderThreads)
-k_debug_order(RehashSchedule rs, const uint32_t* __restrict__ h_in, uint32_t B, OrderScratch g, uint32_t smem_words,
-              int force_global, uint32_t* __restrict__ out) {
-  extern __shared__ uint32_t order_smem[];
-  __shared__ uint32_t warp_sums[33];
-  uint32_t n_final = 1;
-  for (int k = 0; k < rs.count && rs.m[k] < B; ++k) n_final = rs.n[k];
-  uint32_t *h = g.h, *tau = g.tau, *tau2 = g.tau2, *next = g.next, *bkt = g.bkt, *A = g.A, *bhead = g.bhead;
-  if (!force_global && 6u * B + n_final <= smem_words) {
-    h = order_smem;
-    tau = h + B;
-    tau2 = tau + B;
-    next = tau2 + B;
-    bkt = next + B;
-    A = bkt + B;
-    bhead = A + B;
+// k_bundle_order on caller-supplied hashes (element e = e-th inserted key, hash hashes[e]): out[p] = the
+// element at iteration position p.  tests/test_order_gpu.py compares it with a real std::unordered_map.
+// force_global: pretend there is no shared memory, i.e. run every stage grid-wide on the global tables.
+__global__ void k_debug_order_setup(OrderScratch g, uint32_t n, ScanState* st) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) g.head_of[e] = e;
+  if (e == 0) {
+    st->n_rays = n;
+    st->n_clear_rays = 0;
   }
-  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) h[e] = h_in[e];
-  __syncthreads();
-  const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, bkt, A, bhead, n_final, warp_sums);
-  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) out[pos[e]] = e;
 }
 
 int debug_bundle_order(vbx_ctx* c, const uint32_t* hashes, uint32_t n, int force_global, uint32_t* out) {
   cudaStream_t s = c->stream;
   if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "debug_bundle_order: n > max_points_per_scan");
   if (n == 0) return VBX_OK;
-  VBX_CUDA(c, cudaFuncSetAttribute(k_debug_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->order_smem_bytes));
-  VBX_CUDA(c, cudaMemcpyAsync(c->pvals[0], hashes, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  k_debug_order<<<1, kOrderThreads, c->order_smem_bytes, s>>>(c->rehash, c->pvals[0], n, c->order_scratch,
-                                                               (uint32_t)(c->order_smem_bytes / 4), force_global,
-                                                               c->pvals[1]);
-  VBX_CUDA(c, cudaMemcpyAsync(out, c->pvals[1], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaMemsetAsync(c->d_state, 0, sizeof(ScanState), s));
+  VBX_CUDA(c, cudaMemcpyAsync(c->order_scratch.h, hashes, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  k_debug_order_setup<<<grid_for(n, 256), 256, 0, s>>>(c->order_scratch, n, c->d_state);
+  RehashSchedule rs = c->rehash;
+  OrderScratch g = c->order_scratch;
+  uint32_t smem_words = force_global ? 0u : (uint32_t)(c->order_smem_bytes / 4);
+  uint32_t* ray_list = c->ray_list;
+  uint32_t* cta_tot = c->order_scratch.cta_tot;
+  ScanState* st = c->d_state;
+  void* args[] = {&rs, &g, &smem_words, &ray_list, &cta_tot, &st};
+  VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_bundle_order, dim3(kOrderGrid), dim3(kOrderThreads), args,
+                                          c->order_smem_bytes, s));
+  VBX_CUDA(c, cudaMemcpyAsync(out, c->ray_list, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  VBX_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
   VBX_CUDA(c, cudaGetLastError());
+  if (c->h_state->error) return fail(c, VBX_E_CAPACITY, "debug_bundle_order: table capacity");
   return VBX_OK;
 }
 
