@@ -60,6 +60,11 @@ extern "C" {
 #define VBX_UPDATED_MAP 1
 #define VBX_UPDATED_MESH 2
 #define VBX_UPDATED_ESDF 4
+/* Not a voxblox bit: the engine's own "changed since it was last mirrored" mark, set by every TSDF / ESDF
+ * update of a block next to Block::updated().  Accepted in the updated_mask / clear_mask of
+ * vbx_mirror_updated and vbx_serialize_updated (never reported back), so that an incremental host mirror
+ * does not depend on -- or disturb -- the three bits above, which belong to their consumers. */
+#define VBX_UPDATED_MIRROR 8
 
 typedef struct vbx_ctx vbx_ctx;
 

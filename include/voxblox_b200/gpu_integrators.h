@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include <voxblox/core/layer.h>
@@ -78,9 +79,24 @@ inline vbx_esdf_config toPod(const EsdfIntegrator::Config& c) {
 inline void check(vbx_ctx* ctx, int rc, const char* what) {
   if (rc != VBX_OK) LOG(FATAL) << what << " failed (" << rc << "): " << vbx_last_error(ctx);
 }
-// device -> host: refresh (or create) the host blocks listed by the device
+// TSDF layer -> the engine context that holds it (registered by GpuTsdfIntegrator): lets
+// GpuEsdfIntegrator / GpuMeshIntegrator be constructed from the reference's own constructor
+// arguments (layer pointers), e.g. inside voxblox_ros's EsdfServer, without handing a
+// GpuTsdfIntegrator around.  Like the reference's integrators, not thread safe.
+inline std::map<const void*, vbx_ctx*>& contextOfLayer() {
+  static std::map<const void*, vbx_ctx*> m;
+  return m;
+}
+inline vbx_ctx* lookupContext(const void* tsdf_layer) {
+  auto it = contextOfLayer().find(tsdf_layer);
+  CHECK(it != contextOfLayer().end()) << "no GpuTsdfIntegrator is attached to this Layer<TsdfVoxel>";
+  return it->second;
+}
+// device -> host: refresh (or create) the host blocks listed by the device.  clear_mask: updated()
+// bits cleared ON THE DEVICE for the mirrored blocks -- the host block carries them from then on, so
+// the next call with the same mask transfers only what changed since (core/layer.h:194-203 protocol).
 template <typename VoxelType>
-inline size_t downloadBlocks(vbx_ctx* ctx, int layer_id, int updated_mask, Layer<VoxelType>* layer) {
+inline size_t downloadBlocks(vbx_ctx* ctx, int layer_id, int updated_mask, Layer<VoxelType>* layer, int clear_mask = 0) {
   // one call: dirty-block list + payloads (gathered on the device, one copy out)
   uint64_t n = 0;
   check(ctx, vbx_num_blocks(ctx, layer_id, &n), "vbx_num_blocks");
@@ -94,7 +110,8 @@ inline size_t downloadBlocks(vbx_ctx* ctx, int layer_id, int updated_mask, Layer
     idx.resize(3 * cap);
     vox.resize(vpb * cap);
     upd.resize(cap);
-    check(ctx, vbx_mirror_updated(ctx, layer_id, updated_mask, /*clear_mask=*/0, idx.data(), vox.data(), upd.data(), cap, &n),
+    // (a call whose buffer is too small delivers nothing and clears nothing: grow and retry)
+    check(ctx, vbx_mirror_updated(ctx, layer_id, updated_mask, clear_mask, idx.data(), vox.data(), upd.data(), cap, &n),
           "vbx_mirror_updated");
     if (n <= cap) break;
     cap = n;
@@ -118,13 +135,43 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
 
   GpuTsdfIntegrator(TsdfIntegratorType type, const Config& config, Layer<TsdfVoxel>* layer,
                     const vbx_engine_options* options = nullptr)
-      : TsdfIntegratorBase(config, layer), type_(type), ctx_(nullptr), pipelined_(false) {
+      : TsdfIntegratorBase(config, layer), type_(type), ctx_(nullptr), pipelined_(false), auto_sync_(false) {
     const vbx_tsdf_config pod = gpu_detail::toPod(config_);
     const int rc = vbx_create(&pod, voxel_size_, static_cast<int>(voxels_per_side_), options, &ctx_);
     if (rc != VBX_OK) LOG(FATAL) << "vbx_create failed (" << rc << "): " << vbx_last_error(ctx_);
     uploadLayer();  // a layer loaded from a file / built by another integrator becomes the device map
+    gpu_detail::contextOfLayer()[layer_] = ctx_;
   }
-  ~GpuTsdfIntegrator() { vbx_destroy(ctx_); }
+  ~GpuTsdfIntegrator() {
+    gpu_detail::contextOfLayer().erase(layer_);
+    vbx_destroy(ctx_);
+  }
+
+  /// TsdfIntegratorBase::setLayer (tsdf_integrator.cc:68-80): the device map is re-targeted too -- it is
+  /// emptied and `layer`'s blocks become its content.  (The base class method is not virtual: call it on
+  /// the adapter type.  voxel_size / voxels_per_side of the new layer must equal the old ones, which the
+  /// engine was sized for; the reference has no such restriction.)
+  void setLayer(Layer<TsdfVoxel>* layer) {
+    CHECK_NOTNULL(layer);
+    CHECK_EQ(layer->voxel_size(), voxel_size_);
+    CHECK_EQ(layer->voxels_per_side(), voxels_per_side_);
+    gpu_detail::contextOfLayer().erase(layer_);
+    TsdfIntegratorBase::setLayer(layer);
+    gpu_detail::check(ctx_, vbx_clear(ctx_, VBX_LAYER_TSDF), "vbx_clear");
+    uploadLayer();
+    gpu_detail::contextOfLayer()[layer_] = ctx_;
+  }
+
+  /// Auto-sync mode for UNMODIFIED host consumers of the layer: every integratePointCloud() ends by
+  /// mirroring the blocks it changed into the host Layer and setting their updated() bits there
+  /// (Block::updated().set(), tsdf_integrator.cc:128), so code that reads layer_ right after the call --
+  /// the reference's own MeshIntegrator, EsdfIntegrator, io::SaveLayer -- sees what it would see after
+  /// the reference's call.  The transfer is incremental through the engine's own dirty mark
+  /// (VBX_UPDATED_MIRROR); the three updated() bits on the device stay with the device-side consumers.
+  void setAutoSync(bool on) {
+    auto_sync_ = on;
+    if (on) pipelined_ = false;
+  }
 
   void integratePointCloud(const Transformation& T_G_C, const Pointcloud& points_C, const Colors& colors,
                            const bool freespace_points = false) override {
@@ -148,6 +195,7 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
                                            freespace_points ? 1 : 0),
                         "vbx_tsdf_integrate");
     }
+    if (auto_sync_) gpu_detail::downloadBlocks(ctx_, VBX_LAYER_TSDF, VBX_UPDATED_MIRROR, layer_, VBX_UPDATED_MIRROR);
   }
 
   /// Pipelined mode: integratePointCloud() enqueues the scan and returns; the transform / bundle
@@ -200,7 +248,12 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
   /// Bring the host Layer<TsdfVoxel> up to date: downloads every block whose updated() bits
   /// match `updated_mask` (0 = all blocks).  Call it before host code reads the layer (meshing,
   /// saving, interpolation); like the reference, clearing the bits is the consumer's job.
-  size_t syncLayer(int updated_mask = 0) { return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_TSDF, updated_mask, layer_); }
+  /// `clear_mask` (default: the mirrored bits themselves): cleared on the device for the blocks delivered, so
+  /// that the host block owns them from then on and the next syncLayer(mask) transfers only newer changes.
+  /// Pass 0 to leave the device bits alone (e.g. when the device-side ESDF / mesher consume them too).
+  size_t syncLayer(int updated_mask = 0, int clear_mask = -1) {
+    return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_TSDF, updated_mask, layer_, clear_mask < 0 ? updated_mask : clear_mask);
+  }
 
   vbx_ctx* context() { return ctx_; }
 
@@ -208,21 +261,43 @@ class GpuTsdfIntegrator : public TsdfIntegratorBase {
   TsdfIntegratorType type_;
   vbx_ctx* ctx_;
   bool pipelined_;
+  bool auto_sync_;
 };
 
 /// EsdfIntegrator's update entry points (esdf_integrator.h:101-106) on the device map owned by a
 /// GpuTsdfIntegrator.
 class GpuEsdfIntegrator {
  public:
+  typedef EsdfIntegrator::Config Config;
   GpuEsdfIntegrator(const EsdfIntegrator::Config& config, GpuTsdfIntegrator* tsdf, Layer<EsdfVoxel>* esdf_layer)
-      : ctx_(CHECK_NOTNULL(tsdf)->context()), esdf_layer_(CHECK_NOTNULL(esdf_layer)) {
+      : ctx_(CHECK_NOTNULL(tsdf)->context()), esdf_layer_(CHECK_NOTNULL(esdf_layer)), auto_sync_(false) {
     const vbx_esdf_config pod = gpu_detail::toPod(config);
     gpu_detail::check(ctx_, vbx_esdf_create(ctx_, &pod), "vbx_esdf_create");
   }
+  /// EsdfIntegrator's own constructor signature (esdf_integrator.h:80-82): the TSDF layer must be the one a
+  /// GpuTsdfIntegrator is attached to.  With this, `std::unique_ptr<EsdfIntegrator> esdf_integrator_`
+  /// (voxblox_ros/include/voxblox_ros/esdf_server.h:107) becomes `std::unique_ptr<GpuEsdfIntegrator>` and the
+  /// construction line stays as it is; auto-sync is on so that the server's host readers of the
+  /// ESDF layer (publishing, planning) need no further edits.
+  GpuEsdfIntegrator(const EsdfIntegrator::Config& config, Layer<TsdfVoxel>* tsdf_layer, Layer<EsdfVoxel>* esdf_layer)
+      : ctx_(gpu_detail::lookupContext(CHECK_NOTNULL(tsdf_layer))), esdf_layer_(CHECK_NOTNULL(esdf_layer)), auto_sync_(true) {
+    const vbx_esdf_config pod = gpu_detail::toPod(config);
+    gpu_detail::check(ctx_, vbx_esdf_create(ctx_, &pod), "vbx_esdf_create");
+  }
+  /// mirror the ESDF blocks an update changed into the host Layer<EsdfVoxel> right after the update
+  void setAutoSync(bool on) { auto_sync_ = on; }
+  /// every ESDF block changed since the last call of this function (incl. the blocks the wavefront reached)
+  size_t syncChanged() {
+    return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_ESDF, VBX_UPDATED_MIRROR, esdf_layer_, VBX_UPDATED_MIRROR);
+  }
   void updateFromTsdfLayer(bool clear_updated_flag) {
     gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 0, clear_updated_flag ? 1 : 0), "vbx_esdf_update");
+    if (auto_sync_) syncChanged();
   }
-  void updateFromTsdfLayerBatch() { gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 1, 0), "vbx_esdf_update"); }
+  void updateFromTsdfLayerBatch() {
+    gpu_detail::check(ctx_, vbx_esdf_update(ctx_, 1, 0), "vbx_esdf_update");
+    if (auto_sync_) syncChanged();
+  }
   void updateFromTsdfBlocks(const BlockIndexList& tsdf_blocks, bool incremental = false) {
     std::vector<int32_t> idx(3 * tsdf_blocks.size());
     for (size_t b = 0; b < tsdf_blocks.size(); ++b) {
@@ -232,6 +307,7 @@ class GpuEsdfIntegrator {
     }
     gpu_detail::check(ctx_, vbx_esdf_update_blocks(ctx_, idx.data(), tsdf_blocks.size(), incremental ? 1 : 0),
                       "vbx_esdf_update_blocks");
+    if (auto_sync_) syncChanged();
   }
   /// esdf_integrator.cc:25-92: free sphere / occupied shell around the robot, queued for the next update
   void addNewRobotPosition(const Point& position) {
@@ -256,13 +332,14 @@ class GpuEsdfIntegrator {
   void setFullEuclidean(bool full_euclidean) {
     gpu_detail::check(ctx_, vbx_esdf_set_full_euclidean(ctx_, full_euclidean ? 1 : 0), "vbx_esdf_set_full_euclidean");
   }
-  size_t syncLayer(int updated_mask = 0) {
-    return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_ESDF, updated_mask, esdf_layer_);
+  size_t syncLayer(int updated_mask = 0, int clear_mask = -1) {
+    return gpu_detail::downloadBlocks(ctx_, VBX_LAYER_ESDF, updated_mask, esdf_layer_, clear_mask < 0 ? updated_mask : clear_mask);
   }
 
  private:
   vbx_ctx* ctx_;
   Layer<EsdfVoxel>* esdf_layer_;
+  bool auto_sync_;
 };
 
 /// MeshIntegrator<TsdfVoxel>::generateMesh (mesh/mesh_integrator.h:132-160) on the device map owned by
@@ -271,6 +348,9 @@ class GpuMeshIntegrator {
  public:
   GpuMeshIntegrator(const MeshIntegratorConfig& config, GpuTsdfIntegrator* tsdf, MeshLayer* mesh_layer)
       : config_(config), ctx_(CHECK_NOTNULL(tsdf)->context()), mesh_layer_(CHECK_NOTNULL(mesh_layer)) {}
+  /// MeshIntegrator<TsdfVoxel>'s own constructor signature (mesh/mesh_integrator.h:75-90; tsdf_server.cc:110-112)
+  GpuMeshIntegrator(const MeshIntegratorConfig& config, Layer<TsdfVoxel>* tsdf_layer, MeshLayer* mesh_layer)
+      : config_(config), ctx_(gpu_detail::lookupContext(CHECK_NOTNULL(tsdf_layer))), mesh_layer_(CHECK_NOTNULL(mesh_layer)) {}
 
   void generateMesh(bool only_mesh_updated_blocks, bool clear_updated_flag) {
     vbx_mesh_config pod;

@@ -166,6 +166,64 @@ int main() {
     std::printf("esdf blocks %zu (tsdf %zu)\n", nb, gpu.syncLayer(0));
     if (nb == 0 || esdf.getNumberOfAllocatedBlocks() != tsdf.getNumberOfAllocatedBlocks()) ++failures;
   }
+  // The drop-in shapes: GpuEsdfIntegrator built from the REFERENCE's constructor arguments (layer pointers,
+  // esdf_integrator.h:80-82 / esdf_server.cc) with auto-sync, the TSDF adapter in auto-sync mode feeding the
+  // reference's OWN host-side MeshIntegrator without any syncLayer() call, and setLayer().
+  {
+    Layer<TsdfVoxel> tsdf(voxel_size, 16), tsdf_plain(voxel_size, 16);
+    Layer<EsdfVoxel> esdf(voxel_size, 16);
+    GpuTsdfIntegrator gpu(TsdfIntegratorType::kMerged, config, &tsdf);
+    GpuTsdfIntegrator plain(TsdfIntegratorType::kMerged, config, &tsdf_plain);
+    gpu.setAutoSync(true);  // every block an integratePointCloud call changes is mirrored into `tsdf`
+    EsdfIntegrator::Config ec;
+    ec.min_distance_m = 0.2f;
+    GpuEsdfIntegrator ge(ec, &tsdf, &esdf);  // <- the reference's signature; finds the engine through the layer
+    MeshLayer mesh_host(tsdf.block_size()), mesh_ref(tsdf_plain.block_size());
+    MeshIntegratorConfig mc;
+    mc.integrator_threads = 1;
+    MeshIntegrator<TsdfVoxel> host_mesher(mc, &tsdf, &mesh_host);       // the reference's mesher on the mirrored layer
+    MeshIntegrator<TsdfVoxel> ref_mesher(mc, &tsdf_plain, &mesh_ref);  // ... and on an explicitly synced layer
+    Transformation T;
+    Pointcloud pts;
+    Colors cols;
+    size_t esdf_blocks = 0;
+    for (int k = 0; k < 3; ++k) {
+      makeScan(k, &T, &pts, &cols);
+      gpu.integratePointCloud(T, pts, cols);
+      plain.integratePointCloud(T, pts, cols);
+      ge.updateFromTsdfLayer(true);  // auto-sync: the ESDF blocks it touched are in `esdf` when it returns
+      host_mesher.generateMesh(true, true);
+      plain.syncLayer(0, 0);
+      ref_mesher.generateMesh(false, true);
+      esdf_blocks = esdf.getNumberOfAllocatedBlocks();
+    }
+    BlockIndexList ma, mb;
+    mesh_host.getAllAllocatedMeshes(&ma);
+    mesh_ref.getAllAllocatedMeshes(&mb);
+    size_t va = 0, vb = 0;
+    for (const BlockIndex& bi : ma) va += mesh_host.getMeshByIndex(bi).vertices.size();
+    for (const BlockIndex& bi : mb) vb += mesh_ref.getMeshByIndex(bi).vertices.size();
+    // setLayer: the device map follows the new host layer
+    Layer<TsdfVoxel> other(voxel_size, 16);
+    gpu.setLayer(&other);
+    makeScan(0, &T, &pts, &cols);
+    gpu.integratePointCloud(T, pts, cols);
+    Layer<TsdfVoxel> fresh(voxel_size, 16);
+    GpuTsdfIntegrator fresh_gpu(TsdfIntegratorType::kMerged, config, &fresh);
+    fresh_gpu.integratePointCloud(T, pts, cols);
+    fresh_gpu.syncLayer(0);
+    const std::vector<BlockIndex> oa = sortedBlocks(other), ob = sortedBlocks(fresh);
+    bool set_layer_ok = oa.size() == ob.size() && !oa.empty();
+    for (size_t i = 0; set_layer_ok && i < oa.size(); ++i) {
+      set_layer_ok = oa[i] == ob[i] &&
+                     std::memcmp(&other.getBlockByIndex(oa[i]).getVoxelByLinearIndex(0),
+                                 &fresh.getBlockByIndex(ob[i]).getVoxelByLinearIndex(0), 4096 * sizeof(TsdfVoxel)) == 0;
+    }
+    std::printf("drop-in shapes: esdf blocks %zu tsdf blocks %zu, host mesher on the auto-synced layer %zu vertices "
+                "(explicit sync %zu), setLayer ok %d\n",
+                esdf_blocks, tsdf.getNumberOfAllocatedBlocks(), va, vb, set_layer_ok ? 1 : 0);
+    if (esdf_blocks == 0 || esdf_blocks != tsdf.getNumberOfAllocatedBlocks() || va == 0 || va != vb || !set_layer_ok) ++failures;
+  }
   // addNewRobotPosition through the adapter against the reference's own EsdfIntegrator on an empty
   // map (test_clear_spheres.cc:135-136): the hallucinated free sphere / occupied shell is deterministic,
   // so both ESDF layers must agree voxel for voxel.

@@ -151,7 +151,7 @@ __global__ void k_scatter_blocks(int layer, int serialized, const uint32_t* __re
     for (int k = 0; k < 5; ++k) dst[k] = v[k];
   }
   if (i == 0) {
-    flags[slot] = upd_in ? (uint8_t)(upd_in[b] & 0x7f) : (uint8_t)0;  // (bit 7 is the engine's own; a TSDF upload clears kSlotNoTsdf)
+    flags[slot] = upd_in ? (uint8_t)(upd_in[b] & 0x07) : (uint8_t)0;  // (bit 7 is the engine's own; a TSDF upload clears kSlotNoTsdf)
     if (has_esdf) has_esdf[slot] = 1;
   }
 }
@@ -385,7 +385,7 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
   VBX_CUDA(c, cudaStreamSynchronize(s));
   for (uint32_t sl = 0; sl < c->n_blocks; ++sl) {
     if (layer == VBX_LAYER_TSDF && (upd[sl] & kSlotNoTsdf)) has[sl] = 0;  // an ESDF-only slot
-    upd[sl] &= 0x7f;
+    upd[sl] &= 0x7f;  // (bit 3, the mirror mark, may be selected by updated_mask; it is not reported)
   }
   struct Item {
     int x, y, z;
@@ -420,7 +420,7 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
       idx3[3 * i + 1] = items[i].y;
       idx3[3 * i + 2] = items[i].z;
     }
-    if (updated_bits) updated_bits[i] = upd[items[i].slot];
+    if (updated_bits) updated_bits[i] = upd[items[i].slot] & 0x07;
   }
   VBX_CUDA(c, cudaMemcpyAsync(c->mirror_slots, slots.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   const char* pool = (layer == VBX_LAYER_TSDF) ? reinterpret_cast<const char*>(c->tab.tsdf)

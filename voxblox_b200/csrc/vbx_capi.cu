@@ -742,7 +742,7 @@ static int fetch_flags(vbx_ctx* c, int layer, std::vector<uint8_t>* upd, std::ve
   VBX_CUDA(c, cudaStreamSynchronize(c->stream));
   for (uint32_t s = 0; s < c->n_blocks; ++s) {
     if (layer == VBX_LAYER_TSDF && ((*upd)[s] & kSlotNoTsdf)) (*has)[s] = 0;
-    (*upd)[s] &= 0x7f;  // kSlotNoTsdf / kEsdfPending are internal
+    (*upd)[s] &= 0x07;  // kSlotNoTsdf / kEsdfPending / the mirror mark are internal
   }
   return VBX_OK;
 }

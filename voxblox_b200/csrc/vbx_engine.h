@@ -29,6 +29,10 @@ constexpr int kCoordBias = 1 << 20;  // block / voxel coordinates are packed 21 
 //     that starts from zeroed voxels, exactly like a freshly allocated one.
 //   slot_esdf_updated bit 7: member of EsdfIntegrator::updated_blocks_ (esdf_integrator.h:172-175).
 constexpr uint8_t kSlotNoTsdf = 0x80, kEsdfPending = 0x80;
+//   bit 3 of both flag bytes (VBX_UPDATED_MIRROR): the block changed since a vbx_mirror_updated /
+//     vbx_serialize_updated call last cleared this bit -- the engine's own dirty mark for the incremental
+//     host mirror, independent of the three Block::updated() bits (which their consumers clear).
+constexpr uint8_t kTouchedBits = 0x0F;  // what a TSDF update writes: Block::updated().set() + the mirror mark
 
 struct EsdfVoxel {  // core/voxel.h:18-37
   float distance;

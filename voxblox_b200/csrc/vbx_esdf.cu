@@ -109,6 +109,13 @@ __device__ __forceinline__ uint32_t neighbor_ref(const Tables& tab, int L, uint3
   return (nslot << (3 * L)) | (uint32_t)(x | (y << L) | (z << (2 * L)));
 }
 
+// the wavefront changed a voxel of this block: mark it for the incremental host mirror (the reference flags only
+// the blocks it propagates, cc:147; the blocks its queues reach stay unflagged there)
+__device__ __forceinline__ void mark_mirror(const Tables& tab, int L, uint32_t ref) {
+  uint8_t* f = tab.slot_esdf_updated + (ref >> (3 * L));
+  if (!(*f & 8)) *f |= 8;  // (every concurrent writer stores the same bit)
+}
+
 __device__ __forceinline__ void push(uint32_t* list, uint32_t* count, uint32_t cap, uint32_t ref, ScanState* st) {
   const uint32_t j = atomicAdd(count, 1u);
   if (j < cap) {
@@ -416,6 +423,7 @@ __global__ void k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32
             if (is_parent) {
               np->distance = (float)signum_d(np->distance) * E.default_distance;
               np->px = np->py = np->pz = 0;
+              mark_mirror(tab, E.L, nref);
               push(out, out_n, E.cap, nref, st);
             } else if (!(atomicOr(&np->flags, kBitInQueue) & kFlagInQueue)) {
               push(open_list, &st->frontier_n[0], E.cap, nref, st);
@@ -501,6 +509,7 @@ __global__ void k_esdf_lower(EsdfParams E, Tables tab, uint32_t* front_a, uint32
       }
       if (changed) {
         atomicAdd(&st->esdf_counts[5], 1u);
+        mark_mirror(tab, E.L, nref);
         // neighbor_voxel->parent = new_parent (cc:436,450,470,481).  Written unguarded: when two
         // sources lower the same voxel in one sweep the last writer wins; k_esdf_parents then
         // re-derives the parent from the converged distances (quasi-Euclidean mode).
@@ -570,7 +579,7 @@ __global__ void k_esdf_block_list(Tables tab, uint32_t n_slots, int batch, uint3
   if (batch || (u & VBX_UPDATED_ESDF) || (eu & kEsdfPending)) {
     block_list[atomicAdd(&st->esdf_counts[0], 1u)] = s;
     tab.slot_has_esdf[s] = 1;  // allocateBlockPtrByIndex in the ESDF layer, cc:143-146
-    tab.slot_esdf_updated[s] = (tab.slot_esdf_updated[s] & kEsdfPending) | 1;  // esdf_block->set_updated(true): bitset(1) = kMap only, cc:147
+    tab.slot_esdf_updated[s] = (tab.slot_esdf_updated[s] & kEsdfPending) | 9;  // esdf_block->set_updated(true): bitset(1) = kMap only, cc:147 (+ the mirror mark)
   }
 }
 
@@ -580,7 +589,7 @@ __global__ void k_esdf_mark_listed(Tables tab, const uint32_t* __restrict__ bloc
   if (i >= nb) return;
   const uint32_t s = block_list[i];
   tab.slot_has_esdf[s] = 1;
-  tab.slot_esdf_updated[s] = (tab.slot_esdf_updated[s] & kEsdfPending) | 1;
+  tab.slot_esdf_updated[s] = (tab.slot_esdf_updated[s] & kEsdfPending) | 9;
 }
 
 // ------------------------------------------------------------------ addNewRobotPosition
@@ -675,7 +684,9 @@ __global__ void k_esdf_sphere_apply(SphereParams S, Tables tab, const float* __r
   if (changed) {
     ep->flags = f | kBitObserved | kBitHallucinated;
     ep->px = ep->py = ep->pz = 0;
-    if (!(tab.slot_esdf_updated[slot] & kEsdfPending)) tab.slot_esdf_updated[slot] |= kEsdfPending;  // updated_blocks_.insert
+    if ((tab.slot_esdf_updated[slot] & (kEsdfPending | 8)) != (kEsdfPending | 8)) {
+      tab.slot_esdf_updated[slot] |= (uint8_t)(kEsdfPending | 8);  // updated_blocks_.insert (+ the mirror mark)
+    }
     atomicAdd(&st->esdf_counts[S.outer ? 2 : 1], 1u);
   }
 }

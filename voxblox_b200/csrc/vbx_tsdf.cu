@@ -1144,7 +1144,7 @@ __global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_
       const uint32_t hp = tab.new_list[j];
       tab.hslot[hp] = (int32_t)slot;
       tab.slot_key[slot] = tab.hkeys[hp];
-      tab.slot_updated[slot] = 7;
+      tab.slot_updated[slot] = kTouchedBits;
     } else {
       atomicOr(&st->error, kErrPoolFull);
     }
@@ -1207,7 +1207,7 @@ __device__ void emit_ray_sequential(const ScanParams& P, const Tables& tab, cons
       if (hp != 0xffffffffu && hp != kNotOwned) {
         tid = touch_block(tab, hp, P.epoch, st);
         const int32_t slot = tab.hslot[hp];
-        if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
+        if (slot >= 0) tab.slot_updated[slot] = kTouchedBits;  // (*last_block)->updated().set(), cc:128
       }
       lbx = bx;
       lby = by;
@@ -1366,7 +1366,7 @@ k_rays_emit_warp(ScanParams P, Tables tab, const KeyT* __restrict__ keys, const 
         }
         if (hp != 0xffffffffu && hp != kNotOwned) {
           const int32_t slot = tab.hslot[hp];
-          if (slot >= 0) tab.slot_updated[slot] = 7;  // (*last_block)->updated().set(), cc:128
+          if (slot >= 0) tab.slot_updated[slot] = kTouchedBits;  // (*last_block)->updated().set(), cc:128
           hp = touch_block(tab, hp, P.epoch, st);      // from here on: the block's touched id
         }
       }
