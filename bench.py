@@ -583,7 +583,7 @@ def run_ours(args, conf, rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     scan_alg = 16 * n_mean + 24 * u_mean + 20 * b_mean
-    traffic = measure_traffic(args.config) if args.traffic else {"unavailable": "--no-traffic"}
+    traffic = measure_traffic(args.config) if (args.traffic and world == 1) else {"unavailable": "--no-traffic or N > 1"}
     top = max(stages, key=lambda k: stages[k][0]) if stages else None
     top_ms = stages[top][0] / stages[top][1] if top else None
     dom = None
@@ -613,7 +613,12 @@ def run_ours(args, conf, rank, world):
     from oracle import pyoracle as po
 
     sample = scans[:min(len(scans), 12 if conf["scan"] != "c5_lidar_scan" else 5)]
-    threads, detail = calibrate_threads(conf, sample[:3])
+    if world > 1:
+        # (N > 1: the other ranks' GPUs idle while rank 0 measures the CPU: one thread, as calibrated at N = 1)
+        sample = sample[:6]
+        threads, detail = 1, {"1": "not calibrated at N > 1"}
+    else:
+        threads, detail = calibrate_threads(conf, sample[:3])
     which, secs = time_reference(conf, sample, threads, esdf=do_esdf)
     cpu_pts = sum(int(s[0].shape[0]) for s in sample[2:])
     cpu_value = cpu_pts / float(sum(secs[2:]))
@@ -647,7 +652,7 @@ def run_ours(args, conf, rank, world):
     # ---- (6) the callers either side of the path: ESDF update and
     # incremental mesh after every scan; device time per call, not part of `value`
     downstream = None
-    if args.config == "bench":
+    if args.config == "bench" and world == 1:
         try:
             layer5, integ5 = fresh(0, 1)
             esdf5 = vb.Layer(conf["voxel"], 16, voxel_type="esdf")
