@@ -88,3 +88,15 @@ def test_merge_form_of_the_ray_walk_equals_the_sequential_walk(tmp_path):
     assert stats["mismatches"] == 0 and stats["regular"] > 0.7 * stats["rays"]
     per_regime = [int(v) for v in out.stdout.splitlines()[1].split(":")[1].split()]
     assert per_regime[0] == 0 and per_regime[1] == 0 and per_regime[6] == 0   # camera-like and clearing rays
+
+
+def test_bundle_order_formulation_equals_unordered_map(tmp_path):
+    """The Merged integrator's bundle order (voxblox_b200/csrc/vbx_order.cuh) is computed as one
+    data-parallel position formula per rehash along libstdc++'s growth schedule.  tests/umap_order_check.cc
+    runs that formulation on the host against a real std::unordered_map (the container the reference's
+    voxel_map is, tsdf_integrator.cc:318-322).  The device kernels themselves are checked against the same
+    container on the GPU (tests/test_order_gpu.py)."""
+    exe = str(tmp_path / "umap_order_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(HERE, "umap_order_check.cc"), "-o", exe])
+    out = subprocess.check_output([exe]).decode()
+    assert " 0 failures" in out, out

@@ -303,6 +303,7 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
   c->prio_hi = prio_hi;
   CK(cudaStreamCreateWithPriority(&c->stream_main, cudaStreamNonBlocking, prio_hi));
   CK(cudaStreamCreateWithFlags(&c->stream_c, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream_c2, cudaStreamNonBlocking));
   c->stream = c->stream_main;
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -499,6 +500,7 @@ void vbx_destroy(vbx_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream_main) cudaStreamSynchronize(c->stream_main);
   if (c->stream_c) cudaStreamSynchronize(c->stream_c);
+  if (c->stream_c2) cudaStreamSynchronize(c->stream_c2);
   if (c->stream_e) cudaStreamSynchronize(c->stream_e);
   for (int i = 0; i < vbx_ctx::kSortStreams; ++i) {
     if (c->stream_s[i]) cudaStreamSynchronize(c->stream_s[i]);
@@ -574,6 +576,7 @@ void vbx_destroy(vbx_ctx* c) {
     if (c->stream_s[i]) cudaStreamDestroy(c->stream_s[i]);
   }
   if (c->stream_c) cudaStreamDestroy(c->stream_c);
+  if (c->stream_c2) cudaStreamDestroy(c->stream_c2);
   delete c;
 }
 

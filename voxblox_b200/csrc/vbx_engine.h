@@ -140,6 +140,7 @@ struct vbx_ctx {
   cudaStream_t stream = nullptr;      // the stream the next launch goes to (main, or a pipeline stage's stream while one is enqueued)
   cudaStream_t stream_main = nullptr; // back halves, ESDF, block management, synchronous calls
   cudaStream_t stream_c = nullptr;    // host-to-device cloud copies of asynchronously submitted scans
+  cudaStream_t stream_c2 = nullptr;   // ... alternating with this one
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   vbx_tsdf_config cfg;
   vbx_engine_options opt;

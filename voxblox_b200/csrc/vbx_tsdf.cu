@@ -575,6 +575,21 @@ __device__ __forceinline__ float fold_step(float state, float4 abcd, bool is_mea
   return is_mean ? quot : rnd;
 }
 
+// The two halves of fold_step as separate chains (k_merge runs them in separate warps, so that neither
+// pays for the other's instructions): the running mean's  state = (state*A + B) / C  with the
+// three-operation division, and a colour channel's  state = round(state*A + B).
+__device__ __forceinline__ float fold_step_mean(float state, float4 abcd, bool* suspect) {
+  const float tt = fadd(fmul(state, abcd.x), abcd.y);
+  const float q = __fmul_rn(tt, abcd.w);
+  *suspect |= !exact_div_operand_ok(tt);
+  return __fmaf_rn(__fmaf_rn(-q, abcd.z, tt), abcd.w, q);
+}
+__device__ __forceinline__ float fold_step_colour(float state, float4 abcd) {
+  const float tt = fadd(fmul(state, abcd.x), abcd.y);
+  const float m = fadd(fadd(tt, 8388608.0f), -8388608.0f);
+  return (fsub(tt, m) == 0.5f) ? fadd(m, 1.0f) : m;
+}
+
 // Fold one bundle (a run of equal keys starting at sorted position i) with one warp.
 // Members are loaded 32 at a time (keys coalesced, points gathered, next chunk prefetched) and
 // folded in list order with the reference's running weighted mean
@@ -729,28 +744,38 @@ struct ChunkDesc {
 };
 constexpr uint32_t kChunkFirst = 1u, kChunkLast = 2u, kChunkSuspect = 4u, kChunkEnd = 8u;
 
-// named barrier of one warp pair (ids 1 and 2; 0 is __syncthreads'); literal ids so that ptxas
-// reserves three barriers, not all sixteen
-__device__ __forceinline__ void pair_barrier(int pair_in_block) {
-  if (pair_in_block == 0) {
-    asm volatile("bar.sync 1, 64;" ::: "memory");
+// named barriers of one warp triple (producer, mean consumer, colour consumer): ids 1 / 2 = the chunk
+// hand-over of triple 0 / 1 (96 threads), ids 3 / 4 = the two consumers among themselves (64 threads);
+// 0 is __syncthreads'.  Literal ids so that ptxas reserves five barriers, not all sixteen.
+__device__ __forceinline__ void pair_barrier(int triple_in_block) {
+  if (triple_in_block == 0) {
+    asm volatile("bar.sync 1, 96;" ::: "memory");
   } else {
-    asm volatile("bar.sync 2, 64;" ::: "memory");
+    asm volatile("bar.sync 2, 96;" ::: "memory");
+  }
+}
+__device__ __forceinline__ void consumer_barrier(int triple_in_block) {
+  if (triple_in_block == 0) {
+    asm volatile("bar.sync 3, 64;" ::: "memory");
+  } else {
+    asm volatile("bar.sync 4, 64;" ::: "memory");
   }
 }
 
 // The merge of integrateVoxel (cc:384-407): every bundle's points folded in list order.  The fold
 // is one dependent chain per bundle, so the kernel's duration is the largest bundle's chain (up to
-// ~3000 points on this workload).  Warps work in PAIRS on a stream of 32-member chunks:
-//   producer  loads the members (three-deep load pipeline), walks the weight chain W <- W + w
-//             (the only thing a chunk needs from its predecessor besides the running state),
-//             computes everything else that does not depend on the running mean -- p*w, W+w,
-//             RN(1/(W+w)), blendTwoColors' normalised weights -- and stages it per role
-//   consumer  runs the dependent chain state = (state*A + B) / C  over the staged operands
-// so the preparation of chunk c+1 overlaps the chain of chunk c (two shared-memory slots, one
-// named barrier per chunk), also across bundle boundaries.
+// ~3000 points on this workload).  Warps work in TRIPLES on a stream of 32-member chunks:
+//   producer         loads the members (three-deep load pipeline), walks the weight chain W <- W + w
+//                    (the only thing a chunk needs from its predecessor besides the running state),
+//                    computes everything else that does not depend on the running mean -- p*w, W+w,
+//                    RN(1/(W+w)), blendTwoColors' normalised weights -- and stages it per role
+//   mean consumer    runs the dependent chain state = (state*A + B) / C over the staged operands (lanes 0-2: x, y, z)
+//   colour consumer  runs state = round(state*A + B) (lanes 0-3: r, g, b, a)
+// so the preparation of chunk c+1 overlaps the chains of chunk c (two shared-memory slots, one
+// named barrier per chunk), also across bundle boundaries, and each chain issues only its own
+// instructions (~5 dependent operations per member for the mean, ~7 for a colour channel).
 template <typename KeyT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(192)
 k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__ rgba,
         const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ head_list,
         const uint32_t* __restrict__ big_list,
@@ -759,9 +784,11 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
   __shared__ float4 stage[2][2][32 * kStageStride];  // [pair in block][slot][member][role]
   __shared__ ChunkDesc desc[2][2];
   const int lane = threadIdx.x & 31;
+  __shared__ uint32_t s_col[2];
   const int warp_in_block = threadIdx.x >> 5;
-  const int pair_in_block = warp_in_block >> 1;
-  const bool producer = (warp_in_block & 1) == 0;
+  const int pair_in_block = warp_in_block / 3;  // (the triple this warp belongs to)
+  const int warp_role = warp_in_block % 3;      // 0 producer, 1 mean consumer, 2 colour consumer
+  const bool producer = warp_role == 0;
   const int bar_id = pair_in_block;
   const uint32_t n_bundles = st->n_ray_list;
   const uint32_t n_big = st->n_big;
@@ -898,9 +925,47 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
       desc[pair_in_block][seq & 1u] = d;
     }
     pair_barrier(bar_id);
+  } else if (warp_role == 2) {
+    // ---- colour consumer: lanes 0-3 carry r, g, b, a (floats holding exact integers 0..255)
+    const int role = 3 + (lane < 4 ? lane : 3);
+    float state = 0.f;
+    for (;; ++seq) {
+      pair_barrier(bar_id);
+      const int slot = (int)(seq & 1u);
+      const ChunkDesc d = desc[pair_in_block][slot];
+      if (d.flags & kChunkEnd) break;
+      if (d.flags & kChunkFirst) state = 0.f;
+      const float4* st_col = stage[pair_in_block][slot] + role;
+      if (d.live == 0xffffffffu) {
+        float4 cur = st_col[0];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float4 nxt = st_col[((k + 1) & 31) * kStageStride];
+          state = fold_step_colour(state, cur);
+          cur = nxt;
+        }
+      } else if (d.live) {
+        unsigned m = d.live;
+        float4 cur = st_col[(__ffs(m) - 1) * kStageStride];
+        while (m) {
+          m &= m - 1;
+          const float4 nxt = st_col[(m ? __ffs(m) - 1 : 0) * kStageStride];
+          state = fold_step_colour(state, cur);
+          cur = nxt;
+        }
+      }
+      if (d.flags & kChunkLast) {
+        const uint32_t mcol = ((uint32_t)(int)__shfl_sync(0xffffffffu, state, 0) & 0xffu) |
+                              (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 1) & 0xffu) << 8) |
+                              (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 2) & 0xffu) << 16) |
+                              (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 3) & 0xffu) << 24);
+        if (lane == 0) s_col[pair_in_block] = mcol;
+        consumer_barrier(pair_in_block);  // the mean consumer picks the colour up and finishes the bundle
+      }
+    }
   } else {
-    const int role = lane < 7 ? lane : 7;  // lanes 7.. mirror a benign slot
-    const bool is_mean = lane < 3;
+    // ---- mean consumer: lanes 0-2 carry x, y, z of the running mean; it also finishes every bundle
+    const int role = lane < 3 ? lane : 2;
     float state = 0.f;
     bool suspect = false;
     for (;; ++seq) {
@@ -919,7 +984,7 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const float4 nxt = st_col[((k + 1) & 31) * kStageStride];
-          state = fold_step<false>(state, cur, is_mean, &suspect);
+          state = fold_step_mean(state, cur, &suspect);
           cur = nxt;
         }
       } else if (d.live) {
@@ -928,18 +993,19 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
         while (m) {
           m &= m - 1;
           const float4 nxt = st_col[(m ? __ffs(m) - 1 : 0) * kStageStride];  // the next operand's load overlaps the step
-          state = fold_step<false>(state, cur, is_mean, &suspect);
+          state = fold_step_mean(state, cur, &suspect);
           cur = nxt;
         }
       }
       if (d.flags & kChunkLast) {
+        consumer_barrier(pair_in_block);  // the colour consumer is done with this slot and has published the colour
         const uint32_t i = d.head;
         F3 mp;
         float mw = d.mw;
-        uint32_t mcol;
+        uint32_t mcol = s_col[pair_in_block];
         if (__any_sync(0xffffffffu, suspect)) {
           // the fast division met an operand it does not trust: fold this bundle again with the
-          // IEEE division (one warp, the slot just consumed as its staging area)
+          // IEEE division (this warp alone, the slot just consumed as its staging area)
           fold_bundle<KeyT, true>(P, xyz, rgba, keys, vals, i, stage[pair_in_block][slot], &mp, &mw, &mcol, st);
           if (lane == 0) {
             atomicAdd(&st->n_refold, 1u);
@@ -954,10 +1020,6 @@ k_merge(ScanParams P, const float* __restrict__ xyz, const uint8_t* __restrict__
         } else {
           mp = f3(__shfl_sync(0xffffffffu, state, 0), __shfl_sync(0xffffffffu, state, 1),
                   __shfl_sync(0xffffffffu, state, 2));
-          mcol = ((uint32_t)(int)__shfl_sync(0xffffffffu, state, 3) & 0xffu) |
-                 (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 4) & 0xffu) << 8) |
-                 (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 5) & 0xffu) << 16) |
-                 (((uint32_t)(int)__shfl_sync(0xffffffffu, state, 6) & 0xffu) << 24);
         }
         if (lane == 0) {
           const bool clearing = key_is_clearing(kl, (uint64_t)keys[i]);
@@ -1895,7 +1957,7 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     if (int rc = launch_bundle_order<KeyT>(c, so, P, keys, vals, (uint32_t)(c->order_smem_bytes / 4))) return rc;
     if (so != s) VBX_CUDA(c, cudaEventRecord(c->ev_join, so));
     mk.mark(12);
-    k_merge<KeyT><<<148 * 4, 128, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
+    k_merge<KeyT><<<148 * 4, 192, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
                                            c->ray_c, c->cnt, c->d_state);
     mk.mark(8);
     *launches += 9;
@@ -2249,9 +2311,11 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   const uint8_t* dr = rgba;
   if (!on_device) {
     // the copy engine works ahead of the front half on a stream of its own
-    if (cudaMemcpyAsync(S.d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream_c) != cudaSuccess ||
-        cudaMemcpyAsync(S.d_rgba, rgba, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream_c) != cudaSuccess ||
-        cudaEventRecord(S.copy_done, c->stream_c) != cudaSuccess ||
+    // (two copy streams alternate, so two scans' clouds can be in flight on the copy engines at once)
+    cudaStream_t sc = (c->async_seq & 1u) ? c->stream_c2 : c->stream_c;
+    if (cudaMemcpyAsync(S.d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, sc) != cudaSuccess ||
+        cudaMemcpyAsync(S.d_rgba, rgba, (size_t)n * 4, cudaMemcpyHostToDevice, sc) != cudaSuccess ||
+        cudaEventRecord(S.copy_done, sc) != cudaSuccess ||
         cudaStreamWaitEvent(F.stream, S.copy_done, 0) != cudaSuccess) {
       rc = fail(c, VBX_E_CUDA, "asynchronous host-to-device copy failed");
     }
