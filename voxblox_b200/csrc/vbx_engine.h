@@ -86,9 +86,10 @@ struct ScanState {
   uint32_t merge_ticket;     // Merged: work hand-out counter of k_merge
   uint32_t n_touch_ids;      // touched-block ids handed out (>= n_touched: ids lost to a race stay unused)
   uint32_t rec_key_bits;     // bits an update-record key uses: voxel-in-block bits + bits of the touched ids
-  uint32_t reserved[5];
+  uint32_t esdf_ticket[6];   // ESDF queue kernels: work hand-out counters, rotating like the queue counters ([0..2] raise, [3..5] lower)
+  uint32_t reserved[15];
 };
-static_assert(sizeof(ScanState) == 192, "the status block the host reads back is 192 bytes");
+static_assert(sizeof(ScanState) == 256, "the status block the host reads back is 256 bytes");
 
 // The GPU-resident block hash + voxel pools (the device mirror of Layer<T>::block_map_,
 // core/layer.h:30-32,292).
