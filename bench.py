@@ -22,6 +22,11 @@ import time
 
 import numpy as np
 
+# The pipelined path keeps ~18 CUDA streams busy (front lanes, their side streams, walk, sorts, apply, copies).
+# By default a process gets 8 hardware work queues and streams beyond that share them, which serialises
+# kernels that could overlap; the variable must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

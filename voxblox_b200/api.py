@@ -133,6 +133,9 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    # more hardware work queues for the pipelined path's streams (effective only if CUDA is not initialised yet
+    # in this process; see bench.py / INTEGRATION.md)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     if not os.path.exists(LIB_PATH):
         raise VoxbloxError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ "
                            "as g; g.build()'` (there is no CPU fallback)")

@@ -295,6 +295,11 @@ int vbx_create(const vbx_tsdf_config* cfg, float voxel_size, int voxels_per_side
     if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
   } while (0)
   CK(cudaSetDevice(c->device));
+  {
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) == cudaSuccess && sms > 0) c->grid_sms = (unsigned int)sms;
+    if (const char* e = std::getenv("VBX_GRID_SMS")) c->grid_sms = (unsigned int)std::max(1, std::atoi(e));
+  }
   // stream priorities for the pipelined path: the stages that run in submission order (apply, then
   // the ray walk) are the pipeline's bottleneck, so their thread blocks go first
   int prio_lo = 0, prio_hi = 0;

@@ -149,6 +149,7 @@ struct vbx_ctx {
   int vps = 16, L = 4;         // voxels per side and log2
   uint32_t vox_per_block = 4096;
   uint32_t hcap = 0;
+  unsigned int grid_sms = 148;  // persistent-kernel grids are multiples of this (the SM count; VBX_GRID_SMS overrides: tuning aid)
   vbx::Tables tab;
   // scratch
   uint32_t max_points = 0;

@@ -389,211 +389,144 @@ __global__ void k_esdf_seed_commit(EsdfParams E, Tables tab, const uint32_t* __r
   }
 }
 
-// ---- block-local wavefronts.  Both queue kernels below are persistent cooperative kernels.  A grid-wide
-// sweep hands its queue out in batches of one item per warp (atomic ticket); what a thread block's warps
-// push goes to a list in the block's OWN shared memory and is processed by the same block in the next
-// local round (a __syncthreads apart), so a block follows its part of the wavefront level after level
-// without leaving the SM; only what overflows the local list goes to the global queue of the next
-// grid-wide sweep.  A grid barrier therefore advances the wavefront by as many levels as the local
-// lists hold (typically all of them: 1-3 sweeps instead of one per level -- 17-40 before).
-constexpr uint32_t kLocalCap = 2048;
-struct LocalQueue {
-  uint32_t list[2][kLocalCap];
-  uint32_t n[2];
-  uint32_t take;
-};
-__device__ __forceinline__ void push_local(LocalQueue& lq, int nxt, uint32_t ref, uint32_t* spill, uint32_t* spill_n,
-                                           uint32_t cap, ScanState* st) {
-  const uint32_t j = atomicAdd(&lq.n[nxt], 1u);
-  if (j < kLocalCap) {
-    lq.list[nxt][j] = ref;
-  } else {
-    push(spill, spill_n, cap, ref, st);
-  }
-}
-__device__ __forceinline__ uint32_t* raise_ticket(ScanState* st, uint32_t k) { return &st->esdf_ticket[k % 3u]; }
-__device__ __forceinline__ uint32_t* lower_ticket(ScanState* st, uint32_t k) { return &st->esdf_ticket[3u + k % 3u]; }
-
-// Step (2), processRaiseSet cc:305-369.  One warp per raised voxel, one lane per neighbour.  A neighbour
-// whose parent points back at the raised voxel is reset and raised in turn; any other observed,
-// non-fixed neighbour joins the open set.
-__device__ __forceinline__ void raise_one(const EsdfParams& E, const Tables& tab, uint32_t ref, int lane, LocalQueue& lq, int nxt,
-                                          uint32_t* out, uint32_t* out_n, uint32_t* open_list, ScanState* st) {
-  if (lane == 0) atomicAdd(&st->esdf_counts[4], 1u);
-  if (lane >= 26) return;
-  const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
-  if (nref == 0xffffffffu) return;
-  EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
-  const uint32_t nf = np->flags;
-  if (!(nf & kFlagObserved) || (nf & kFlagFixed)) return;
-  bool is_parent = np->px == -kOff[lane][0] && np->py == -kOff[lane][1] && np->pz == -kOff[lane][2];
-  if (E.full_euclidean) {  // cc:339-347
-    const F3 pd = unit3(f3((float)np->px, (float)np->py, (float)np->pz));
-    is_parent = (int)roundf(pd.x) == -kOff[lane][0] && (int)roundf(pd.y) == -kOff[lane][1] &&
-                (int)roundf(pd.z) == -kOff[lane][2];
-  }
-  if (is_parent) {
-    np->distance = (float)signum_d(np->distance) * E.default_distance;
-    np->px = np->py = np->pz = 0;
-    mark_mirror(tab, E.L, nref);
-    push_local(lq, nxt, nref, out, out_n, E.cap, st);
-  } else if (!(atomicOr(&np->flags, kBitInQueue) & kFlagInQueue)) {
-    push(open_list, &st->frontier_n[0], E.cap, nref, st);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32_t* raise_b, uint32_t* open_list, ScanState* st) {
+// Step (2), processRaiseSet cc:305-369: level-synchronous BFS.  One warp per raised voxel, one
+// lane per neighbour.  A neighbour whose parent points back at the raised voxel is reset and
+// raised in turn; any other observed, non-fixed neighbour joins the open set.
+__global__ void k_esdf_raise(EsdfParams E, Tables tab, uint32_t* raise_a, uint32_t* raise_b, uint32_t* open_list,
+                             ScanState* st) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ LocalQueue lq;
   const int lane = threadIdx.x & 31;
-  const uint32_t w = threadIdx.x >> 5, n_w = blockDim.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t level = 0;; ++level) {
     uint32_t* in = (level & 1u) ? raise_b : raise_a;
     uint32_t* out = (level & 1u) ? raise_a : raise_b;
     const uint32_t n = min(__ldcg(raise_cnt(st, level)), E.cap);
     if (n == 0) break;
     uint32_t* out_n = raise_cnt(st, level + 1);
-    uint32_t* ticket = raise_ticket(st, level);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      *raise_cnt(st, level + 2) = 0;
-      *raise_ticket(st, level + 2) = 0;
-    }
-    if (threadIdx.x == 0) lq.n[0] = lq.n[1] = 0;
-    __syncthreads();
-    int cur = 0;
-    while (true) {
-      const uint32_t nl = min(lq.n[cur], kLocalCap);
-      if (nl == 0) {
-        if (threadIdx.x == 0) lq.take = atomicAdd(ticket, n_w);
-        __syncthreads();
-        const uint32_t base = lq.take;
-        if (base >= n) break;
-        if (base + w < n) raise_one(E, tab, __ldcg(&in[base + w]), lane, lq, cur ^ 1, out, out_n, open_list, st);
-      } else {
-        for (uint32_t i = w; i < nl; i += n_w) raise_one(E, tab, lq.list[cur][i], lane, lq, cur ^ 1, out, out_n, open_list, st);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *raise_cnt(st, level + 2) = 0;
+    for (uint32_t q = warp; q < n; q += n_warps) {
+      const uint32_t ref = __ldcg(&in[q]);
+      if (lane == 0) atomicAdd(&st->esdf_counts[4], 1u);
+      if (lane < 26) {
+        const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
+        if (nref != 0xffffffffu) {
+          EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
+          const uint32_t nf = np->flags;
+          if ((nf & kFlagObserved) && !(nf & kFlagFixed)) {
+            bool is_parent = np->px == -kOff[lane][0] && np->py == -kOff[lane][1] && np->pz == -kOff[lane][2];
+            if (E.full_euclidean) {  // cc:339-347
+              const F3 pd = unit3(f3((float)np->px, (float)np->py, (float)np->pz));
+              is_parent = (int)roundf(pd.x) == -kOff[lane][0] && (int)roundf(pd.y) == -kOff[lane][1] &&
+                          (int)roundf(pd.z) == -kOff[lane][2];
+            }
+            if (is_parent) {
+              np->distance = (float)signum_d(np->distance) * E.default_distance;
+              np->px = np->py = np->pz = 0;
+              mark_mirror(tab, E.L, nref);
+              push(out, out_n, E.cap, nref, st);
+            } else if (!(atomicOr(&np->flags, kBitInQueue) & kFlagInQueue)) {
+              push(open_list, &st->frontier_n[0], E.cap, nref, st);
+            }
+          }
+        }
       }
-      __syncthreads();
-      if (threadIdx.x == 0) lq.n[cur] = 0;
-      cur ^= 1;
-      __syncthreads();
     }
     grid.sync();
   }
 }
 
 // Step (3), processOpenSet cc:371-496: wavefront relaxation.  One warp per frontier voxel, one
-// lane per neighbour; a lowered neighbour joins the next (local) frontier (once: the in_queue flag).
+// lane per neighbour; a lowered neighbour joins the next frontier (once: the in_queue flag).
 // A voxel leaves the queue (voxel->in_queue = false, cc:384) when its warp starts on it: the flag is
 // cleared BEFORE the distance is read, so a neighbour that lowers this voxel either still sees the
-// flag (then its lower value is the one read here) or re-queues the voxel.
-__device__ __forceinline__ void lower_one(const EsdfParams& E, const Tables& tab, uint32_t ref, int lane, LocalQueue& lq, int nxt,
-                                          uint32_t* out, uint32_t* out_n, uint32_t* touched_list, ScanState* st) {
-  EsdfWords* vpm = reinterpret_cast<EsdfWords*>(tab.esdf) + ref;
-  if (lane == 0) {
-    atomicAnd(&vpm->flags, ~kBitInQueue);
-    __threadfence();
-  }
-  __syncwarp();
-  const EsdfWords* vp = vpm;
-  const float vd = *reinterpret_cast<const volatile float*>(&vp->distance);
-  const uint32_t vf = *reinterpret_cast<const volatile uint32_t*>(&vp->flags);
-  if (!(vf & kFlagObserved) || vd >= E.max_distance || vd <= -E.max_distance) return;  // cc:387-390
-  if (lane >= 26) return;
-  const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
-  if (nref == 0xffffffffu) return;
-  EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
-  const uint32_t nf = *reinterpret_cast<const volatile uint32_t*>(&np->flags);
-  if (!(nf & kFlagObserved) || (nf & kFlagFixed)) return;  // cc:407-411
-  float dist = nbr_dist(E, lane);
-  if (E.full_euclidean) {  // cc:414-426
-    const F3 npar = f3((float)(vp->px - kOff[lane][0]), (float)(vp->py - kOff[lane][1]), (float)(vp->pz - kOff[lane][2]));
-    dist = fmul(E.voxel_size, fsub(norm3(npar), norm3(f3((float)vp->px, (float)vp->py, (float)vp->pz))));
-    if (dist < 0.0f) return;
-  }
-  const float nd = *reinterpret_cast<const volatile float*>(&np->distance);
-  bool changed = false;
-  int* nbits = reinterpret_cast<int*>(&np->distance);
-  if (vd > 0.0f && nd > 0.0f) {  // both outside, cc:429-443
-    if (fadd(fadd(vd, dist), E.min_diff) < nd) {
-      const float cand = fadd(vd, dist);
-      changed = atomicMin(nbits, __float_as_int(cand)) > __float_as_int(cand);
-    }
-  } else if (vd <= 0.0f && nd <= 0.0f) {  // both inside, cc:444-457
-    if (fsub(fsub(vd, dist), E.min_diff) > nd) {
-      const float cand = fsub(vd, dist);
-      changed = atomicMin(nbits, __float_as_int(cand)) > __float_as_int(cand);
-    }
-  } else {  // signs differ, cc:458-488 (incl. the sign-vs-distance comparison of cc:464)
-    const float pot = fsub(vd, fmul((float)signum_d(vd), dist));
-    if (fabsf(fsub(pot, nd)) > dist) {
-      // The reference ASSIGNS sign(n) * dist here, so its result depends on which source it
-      // pops first.  The device keeps the candidate nearest the surface (order free): the
-      // assignment is applied only when it lowers |distance|.
-      const float nv = ((float)signum_d(pot) == nd) ? pot : fmul((float)signum_d(nd), dist);
-      if ((nv > 0.0f) == (nd > 0.0f)) {
-        changed = atomicMin(nbits, __float_as_int(nv)) > __float_as_int(nv);
-      }
-    }
-  }
-  if (changed) {
-    atomicAdd(&st->esdf_counts[5], 1u);
-    mark_mirror(tab, E.L, nref);
-    // neighbor_voxel->parent = new_parent (cc:436,450,470,481).  Written unguarded: when two
-    // sources lower the same voxel at once the last writer wins; k_esdf_parents then
-    // re-derives the parent from the converged distances (quasi-Euclidean mode).
-    if (E.full_euclidean) {
-      np->px = vp->px - kOff[lane][0];
-      np->py = vp->py - kOff[lane][1];
-      np->pz = vp->pz - kOff[lane][2];
-    } else {
-      np->px = -kOff[lane][0];
-      np->py = -kOff[lane][1];
-      np->pz = -kOff[lane][2];
-    }
-    __threadfence();  // the lowered distance is visible before the queue flag is tested
-    const uint32_t old = atomicOr(&np->flags, kBitInQueue | kBitLowered);
-    if (!(old & kBitLowered)) push(touched_list, &st->lowered_n, E.cap, nref, st);
-    if (E.multi_queue || !(old & kFlagInQueue)) push_local(lq, nxt, nref, out, out_n, E.cap, st);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_esdf_lower(EsdfParams E, Tables tab, uint32_t* front_a, uint32_t* front_b, uint32_t* touched_list, ScanState* st) {
+// flag (then its lower value is the one read here) or re-queues the voxel for the next sweep.
+__global__ void k_esdf_lower(EsdfParams E, Tables tab, uint32_t* front_a, uint32_t* front_b, uint32_t* touched_list,
+                             ScanState* st) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ LocalQueue lq;
   const int lane = threadIdx.x & 31;
-  const uint32_t w = threadIdx.x >> 5, n_w = blockDim.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t sweep = 0;; ++sweep) {
     uint32_t* in = (sweep & 1u) ? front_b : front_a;
     uint32_t* out = (sweep & 1u) ? front_a : front_b;
     const uint32_t n = min(__ldcg(frontier_cnt(st, sweep)), E.cap);
     if (n == 0) break;
     uint32_t* out_n = frontier_cnt(st, sweep + 1);
-    uint32_t* ticket = lower_ticket(st, sweep);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       *frontier_cnt(st, sweep + 2) = 0;
-      *lower_ticket(st, sweep + 2) = 0;
       atomicAdd(&st->esdf_counts[6], 1u);
     }
-    if (threadIdx.x == 0) lq.n[0] = lq.n[1] = 0;
-    __syncthreads();
-    int cur = 0;
-    while (true) {
-      const uint32_t nl = min(lq.n[cur], kLocalCap);
-      if (nl == 0) {
-        if (threadIdx.x == 0) lq.take = atomicAdd(ticket, n_w);
-        __syncthreads();
-        const uint32_t base = lq.take;
-        if (base >= n) break;
-        if (base + w < n) lower_one(E, tab, __ldcg(&in[base + w]), lane, lq, cur ^ 1, out, out_n, touched_list, st);
-      } else {
-        for (uint32_t i = w; i < nl; i += n_w) lower_one(E, tab, lq.list[cur][i], lane, lq, cur ^ 1, out, out_n, touched_list, st);
+    for (uint32_t q = warp; q < n; q += n_warps) {
+      const uint32_t ref = __ldcg(&in[q]);
+      EsdfWords* vpm = reinterpret_cast<EsdfWords*>(tab.esdf) + ref;
+      if (lane == 0) {
+        atomicAnd(&vpm->flags, ~kBitInQueue);
+        __threadfence();
       }
-      __syncthreads();
-      if (threadIdx.x == 0) lq.n[cur] = 0;
-      cur ^= 1;
-      __syncthreads();
+      __syncwarp();
+      const EsdfWords* vp = vpm;
+      const float vd = *reinterpret_cast<const volatile float*>(&vp->distance);
+      const uint32_t vf = *reinterpret_cast<const volatile uint32_t*>(&vp->flags);
+      if (!(vf & kFlagObserved) || vd >= E.max_distance || vd <= -E.max_distance) continue;  // cc:387-390
+      if (lane >= 26) continue;
+      const uint32_t nref = neighbor_ref(tab, E.L, ref, lane);
+      if (nref == 0xffffffffu) continue;
+      EsdfWords* np = reinterpret_cast<EsdfWords*>(tab.esdf) + nref;
+      const uint32_t nf = *reinterpret_cast<const volatile uint32_t*>(&np->flags);
+      if (!(nf & kFlagObserved) || (nf & kFlagFixed)) continue;  // cc:407-411
+      float dist = nbr_dist(E, lane);
+      if (E.full_euclidean) {  // cc:414-426
+        const F3 npar = f3((float)(vp->px - kOff[lane][0]), (float)(vp->py - kOff[lane][1]),
+                           (float)(vp->pz - kOff[lane][2]));
+        dist = fmul(E.voxel_size, fsub(norm3(npar), norm3(f3((float)vp->px, (float)vp->py, (float)vp->pz))));
+        if (dist < 0.0f) continue;
+      }
+      const float nd = *reinterpret_cast<const volatile float*>(&np->distance);
+      bool changed = false;
+      int* nbits = reinterpret_cast<int*>(&np->distance);
+      if (vd > 0.0f && nd > 0.0f) {  // both outside, cc:429-443
+        if (fadd(fadd(vd, dist), E.min_diff) < nd) {
+          const float cand = fadd(vd, dist);
+          changed = atomicMin(nbits, __float_as_int(cand)) > __float_as_int(cand);
+        }
+      } else if (vd <= 0.0f && nd <= 0.0f) {  // both inside, cc:444-457
+        if (fsub(fsub(vd, dist), E.min_diff) > nd) {
+          const float cand = fsub(vd, dist);
+          changed = atomicMin(nbits, __float_as_int(cand)) > __float_as_int(cand);
+        }
+      } else {  // signs differ, cc:458-488 (incl. the sign-vs-distance comparison of cc:464)
+        const float pot = fsub(vd, fmul((float)signum_d(vd), dist));
+        if (fabsf(fsub(pot, nd)) > dist) {
+          // The reference ASSIGNS sign(n) * dist here, so its result depends on which source it
+          // pops first.  The device keeps the candidate nearest the surface (order free): the
+          // assignment is applied only when it lowers |distance|.
+          const float nv = ((float)signum_d(pot) == nd) ? pot : fmul((float)signum_d(nd), dist);
+          if ((nv > 0.0f) == (nd > 0.0f)) {
+            changed = atomicMin(nbits, __float_as_int(nv)) > __float_as_int(nv);
+          }
+        }
+      }
+      if (changed) {
+        atomicAdd(&st->esdf_counts[5], 1u);
+        mark_mirror(tab, E.L, nref);
+        // neighbor_voxel->parent = new_parent (cc:436,450,470,481).  Written unguarded: when two
+        // sources lower the same voxel in one sweep the last writer wins; k_esdf_parents then
+        // re-derives the parent from the converged distances (quasi-Euclidean mode).
+        if (E.full_euclidean) {
+          np->px = vp->px - kOff[lane][0];
+          np->py = vp->py - kOff[lane][1];
+          np->pz = vp->pz - kOff[lane][2];
+        } else {
+          np->px = -kOff[lane][0];
+          np->py = -kOff[lane][1];
+          np->pz = -kOff[lane][2];
+        }
+        __threadfence();  // the lowered distance is visible before the queue flag is tested
+        const uint32_t old = atomicOr(&np->flags, kBitInQueue | kBitLowered);
+        if (!(old & kBitLowered)) push(touched_list, &st->lowered_n, E.cap, nref, st);
+        if (E.multi_queue || !(old & kFlagInQueue)) push(out, out_n, E.cap, nref, st);
+      }
     }
     grid.sync();
   }

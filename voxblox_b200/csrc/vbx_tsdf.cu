@@ -1957,7 +1957,7 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     if (int rc = launch_bundle_order<KeyT>(c, so, P, keys, vals, (uint32_t)(c->order_smem_bytes / 4))) return rc;
     if (so != s) VBX_CUDA(c, cudaEventRecord(c->ev_join, so));
     mk.mark(12);
-    k_merge<KeyT><<<148 * 4, 192, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
+    k_merge<KeyT><<<c->grid_sms * 4, 192, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
                                            c->ray_c, c->cnt, c->d_state);
     mk.mark(8);
     *launches += 9;
@@ -2030,7 +2030,7 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
     VBX_CUDA(c, cudaStreamWaitEvent(c->apply_stream, c->sorted_event, 0));
     s = c->apply_stream;
   }
-  const unsigned int g_short = 148 * 8;
+  const unsigned int g_short = c->grid_sms * 8;
   LongRuns lr;
   lr.start = c->long_list;
   lr.end = c->long_end;
@@ -2040,8 +2040,8 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
   lr.rec_sdf = c->rec_sdf;
   lr.rec_w = c->rec_w;
   k_apply_short<<<g_short, 256, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
-  k_apply_verify<<<148 * 8, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
-  k_apply_long<<<148 * 4, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
+  k_apply_verify<<<c->grid_sms * 8, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
+  k_apply_long<<<c->grid_sms * 4, 128, 0, s>>>(P, c->tab, rv, c->ray_a, c->ray_c, lr, c->d_state);
   mk.mark(7);
   *launches += 3;
   return VBX_OK;
@@ -2054,7 +2054,7 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
   const uint32_t n = P.n;
   if (P.kind == VBX_MERGED && P.single_walk) {
     // a few thousand bundles of 100-300 steps: one warp per ray
-    k_rays_emit_warp<KeyT><<<148 * 8, 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->head_list, c->ray_p, c->cnt, c->off,
+    k_rays_emit_warp<KeyT><<<c->grid_sms * 8, 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->head_list, c->ray_p, c->cnt, c->off,
                                                    c->ckeys[0], c->cvals[0], c->d_state);
   } else {
     k_rays_emit<KeyT><<<grid_for(n, 128), 128, 0, s>>>(P, c->tab, keys, c->ray_list, c->head_list, c->ray_p, c->cnt, c->off,
