@@ -700,18 +700,18 @@ def run_ours(args, conf, rank, world):
         except Exception as exc:  # never lose the headline line to an optional section
             downstream = {"error": repr(exc)}
 
-    config = config_dict(conf, scans[args.warmup:])
-    config.update({"updates_per_scan_mean": k_mean, "voxels_touched_per_scan_mean": u_mean,
-                   "blocks_touched_per_scan_mean": b_mean, "map_blocks_after_run": n_blocks,
-                   "parallelism": ("single GPU" if world == 1 else
-                                   f"own{world}: ONE map sharded over {world} GPUs by block ownership; every rank receives "
-                                   "every scan, folds and walks all rays, applies only the voxels of its own blocks; no "
-                                   "collective while integrating")})
+    config = config_dict(conf, scans[args.warmup:])  # (exactly the reference arm's object)
+    workload_stats = {"updates_per_scan_mean": k_mean, "voxels_touched_per_scan_mean": u_mean,
+                      "blocks_touched_per_scan_mean": b_mean, "map_blocks_after_run": n_blocks}
+    parallelism = ("single GPU" if world == 1 else
+                   f"own{world}: ONE map sharded over {world} GPUs by block ownership; every rank receives every scan, "
+                   "folds and walks all rays, applies only the voxels of its own blocks; no collective while integrating")
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config, "clocks": clocks, "wall_ms_per_step": wall_ms / steps,
+        "config": config, "workload_stats": workload_stats, "parallelism": parallelism, "clocks": clocks,
+        "wall_ms_per_step": wall_ms / steps,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 256 * world,
                 "ms_per_step": e2e_ms / steps, "submission": "vbx_tsdf_integrate_async, page-locked host clouds (vbx_host_alloc)"
                 + (" (every rank copies the whole cloud over its own PCIe link)" if world > 1 else ""),
