@@ -192,3 +192,30 @@ def test_esdf_clear_drops_robot_position_queue():
     eint.updateFromTsdfLayer(True)
     c = eint.counters()
     assert c["blocks"] == 0 and c["relaxations"] == 0 and c["raised_voxels"] == 0, c
+
+
+@pytest.mark.parametrize("vps", [8, 4])
+def test_esdf_other_block_sizes(vps):
+    """voxels_per_side 8 and 4: the propagation kernel stages 6 KiB + 10 KiB (768 B + 1280 B) slabs with the same
+    TMA bulk copies as the 48 KiB + 80 KiB ones of the default block size."""
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    tsdf = vb.Layer(0.1, vps)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, tsdf)
+    esdf = vb.Layer(0.1, vps, voxel_type="esdf")
+    eint = vb.EsdfIntegrator(vb.EsdfIntegratorConfig(**EKW), tsdf, esdf)
+    omap = po.OracleMap(po.OracleLib("port"), po.TsdfConfig(default_truncation_distance=0.4), 0.1, vps)
+    omap.esdf_create(po.EsdfConfig(**EKW))
+    for s in _wall_scans():
+        integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+        omap.integrate(2, s, order=po.ORDER_REFERENCE)
+        eint.updateFromTsdfLayer(True)
+        omap.esdf_update(batch=False, clear_updated_flag=True)
+    gi, oi = esdf.getAllAllocatedBlocks(), omap.block_indices(1)
+    assert gi.shape == oi.shape and (gi == oi).all()
+    gv, _ = esdf.getBlocks(gi)
+    ov = np.stack([omap.block(i, 1)[0] for i in oi])
+    obs = ov["observed"] != 0
+    assert ((gv["observed"] != 0) == obs).all() and (gv["fixed"][obs] == ov["fixed"][obs]).all()
+    exact = (gv["distance"][obs] == ov["distance"][obs]).mean()
+    print("vps", vps, "observed", int(obs.sum()), "bit-exact fraction", exact)
+    assert exact >= 0.995

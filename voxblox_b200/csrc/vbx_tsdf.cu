@@ -1815,15 +1815,6 @@ int init_bundle_order(vbx_ctx* c) {
 
 static inline unsigned int grid_for(uint64_t n, int block) { return (unsigned int)((n + block - 1) / block); }
 
-static int bits_for(uint64_t v) {
-  int b = 0;
-  while (v > 0) {
-    ++b;
-    v >>= 1;
-  }
-  return b;
-}
-
 static int check_state_errors(vbx_ctx* c, uint32_t err) {
   err &= kFatalErrors;
   if (!err) return VBX_OK;
