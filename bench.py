@@ -297,11 +297,13 @@ def traffic_child(conf):
     print(json.dumps({"scans": len(scans)}), flush=True)
 
 
-def measure_traffic(conf_name, timeout_s=300):
+def measure_traffic(conf_name, timeout_s=300, cache_control="all"):
     """dram__bytes_read.sum + dram__bytes_write.sum per kernel, measured NOW on this box by running a
-    5-scan child of this script under ncu (cache control at its default: every kernel starts with
-    cold caches, so the figures are upper bounds for the steady state in which the map's blocks stay
-    in the 126 MB L2).  Returns bytes per scan per kernel name, or {"unavailable": why}."""
+    5-scan child of this script under ncu.  cache_control "all" (ncu's default) flushes the caches before
+    every kernel: an upper bound in which every intermediate buffer (sort ping-pong, records, ray tables)
+    is charged as DRAM traffic although the pipeline hands it from kernel to kernel through the 126 MB L2;
+    "none" leaves the caches alone, so a kernel finds what the previous kernel wrote where the real run
+    finds it.  Returns bytes per scan per kernel name, or {"unavailable": why}."""
     import csv
     import shutil
     import tempfile
@@ -311,8 +313,8 @@ def measure_traffic(conf_name, timeout_s=300):
         return {"unavailable": "ncu not found"}
     with tempfile.TemporaryDirectory() as td:
         logf = os.path.join(td, "ncu.csv")
-        cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "--print-units", "base", "--csv",
-               "--log-file", logf, sys.executable, os.path.abspath(__file__), "--traffic-child", "--config", conf_name]
+        cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "--cache-control", cache_control,
+               "--print-units", "base", "--csv", "--log-file", logf, sys.executable, os.path.abspath(__file__), "--traffic-child", "--config", conf_name]
         try:
             env = dict(os.environ)
             env.pop("RANK", None)
@@ -351,7 +353,9 @@ def measure_traffic(conf_name, timeout_s=300):
         out = {k: {"dram_bytes_per_scan": v["dram_bytes"] / n_scans, "us_per_scan_under_ncu": v["ns"] / n_scans / 1e3,
                    "launches_per_scan": v["launches"] / n_scans} for k, v in per.items()}
         return {"per_kernel": out, "total_dram_bytes_per_scan": sum(v["dram_bytes"] for v in per.values()) / n_scans,
-                "scans": n_scans, "how": "ncu --metrics " + NCU_METRICS + " (cold caches per kernel), run inside this bench"}
+                "scans": n_scans, "how": "ncu --metrics " + NCU_METRICS + " --cache-control " + cache_control +
+                ("  (caches flushed before every kernel)" if cache_control == "all" else
+                 "  (caches left as the previous kernel left them, as in the real run)") + ", run inside this bench"}
 
 
 # --------------------------------------------------------------------------- ours
@@ -595,7 +599,11 @@ def run_ours(args, conf, rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     scan_alg = 16 * n_mean + 24 * u_mean + 20 * b_mean
-    traffic = measure_traffic(args.config) if (args.traffic and world == 1) else {"unavailable": "--no-traffic or N > 1"}
+    if args.traffic and world == 1:
+        traffic = measure_traffic(args.config, cache_control="none")
+        traffic_cold = measure_traffic(args.config, cache_control="all")
+    else:
+        traffic = traffic_cold = {"unavailable": "--no-traffic or N > 1"}
     top = max(stages, key=lambda k: stages[k][0]) if stages else None
     top_ms = stages[top][0] / stages[top][1] if top else None
     dom = None
@@ -614,7 +622,9 @@ def run_ours(args, conf, rank, world):
                 # headline: SURVEY 8(d)'s whole-scan bytes over the measured time per scan
                 "alg_bytes_per_launch": scan_alg, "alg_bytes_formula": "16*N + 24*U + 20*B (SURVEY.md 8d)",
                 "achieved": scan_alg / (ms_per_step * 1e-3) / 1e9, "frac": scan_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+                # DRAM bytes per scan, all kernels of the scan: caches as the run leaves them / flushed per kernel
                 "traffic": traffic.get("total_dram_bytes_per_scan"), "traffic_detail": traffic,
+                "traffic_cold_cache": traffic_cold.get("total_dram_bytes_per_scan"), "traffic_cold_cache_detail": traffic_cold,
                 "synchronous_call_frac": scan_alg / (sync_ms / steps * 1e-3) / 1e9 / peak,
                 "dominant_kernel": dom,
                 "stage_ms_per_scan": {k: round(v[0] / steps, 5) for k, v in stages.items()},

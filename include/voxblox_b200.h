@@ -278,6 +278,37 @@ VBX_API int vbx_mesh_generate(vbx_ctx* ctx, const vbx_mesh_config* cfg, int only
 VBX_API int vbx_mesh_download(vbx_ctx* ctx, int32_t* idx3, uint64_t* first_vertex, float* vertices, float* normals,
                               uint8_t* colors);
 
+/* ICP pose refinement: voxblox::ICP (alignment/icp.h:72-233, src/alignment/icp.cc),
+ * the optional step in front of integratePointCloud (voxblox_ros/src/tsdf_server.cc:254-299).
+ * ICP::Config (icp.h:76-108), field names as spelled there.  num_threads: the reference starts that many
+ * racing host threads; the device runs them as `num_threads` warps of one thread block under the
+ * round-robin schedule (every round: warp w = 0..T-1 takes the next mini batch, matches it against the
+ * pose it saw at its own last successful fusion, fusions applied in warp order) -- one of the schedules
+ * the reference's threads can produce, and THE schedule for num_threads = 1.  1 <= num_threads <= 32. */
+typedef struct vbx_icp_config {
+  int32_t refine_roll_pitch;          /* false */
+  int32_t mini_batch_size;            /* 20    */
+  float min_match_ratio;              /* 0.8   */
+  float subsample_keep_ratio;         /* 0.5   */
+  float inital_translation_weighting; /* 100   */
+  float inital_rotation_weighting;    /* 100   */
+  int32_t num_threads;                /* hardware_concurrency() in the reference */
+  int32_t reserved;
+} vbx_icp_config;
+/* ICP::runICP(tsdf_layer, points, inital_T_tsdf_sensor, &refined_T_tsdf_sensor, seed) (icp.h:118-123,
+ * icp.cc:219-259) against the device map: points_C = 3*n floats (host memory), the pose as quaternion
+ * (w, x, y, z) + translation.  The point order is randomised exactly as the reference does it
+ * (std::shuffle with std::default_random_engine(seed) from the C++ library the engine is built with).
+ * *num_updates = the number of mini batches that were fused (the reference's return value).
+ * Queued asynchronous scans are drained first: the match runs against the map they produce. */
+VBX_API int vbx_icp_run(vbx_ctx* ctx, const vbx_icp_config* cfg, const float* points_C, uint64_t n,
+                        const float q_wxyz[4], const float t[3], uint32_t seed, float out_q_wxyz[4], float out_t[3],
+                        uint64_t* num_updates);
+/* the same with the cloud already in device memory */
+VBX_API int vbx_icp_run_device(vbx_ctx* ctx, const vbx_icp_config* cfg, const float* d_points_C, uint64_t n,
+                               const float q_wxyz[4], const float t[3], uint32_t seed, float out_q_wxyz[4],
+                               float out_t[3], uint64_t* num_updates);
+
 VBX_API int vbx_sync(vbx_ctx* ctx);
 
 /* One map over the GPUs of one box: block-ownership sharding (BASELINE.json north_star; SURVEY.md

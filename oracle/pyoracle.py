@@ -73,6 +73,20 @@ class EsdfConfig(C.Structure):
         super().__init__(**d)
 
 
+class IcpConfig(C.Structure):
+    """vbo_icp_config; defaults = ICP::Config (alignment/icp.h:76-108) except num_threads, which is
+    hardware_concurrency() there (its threads race; 1 is the deterministic setting)."""
+    _fields_ = [("refine_roll_pitch", C.c_int32), ("mini_batch_size", C.c_int32), ("min_match_ratio", C.c_float),
+                ("subsample_keep_ratio", C.c_float), ("inital_translation_weighting", C.c_float),
+                ("inital_rotation_weighting", C.c_float), ("num_threads", C.c_int32)]
+
+    def __init__(self, **kw):
+        d = dict(refine_roll_pitch=0, mini_batch_size=20, min_match_ratio=0.8, subsample_keep_ratio=0.5,
+                 inital_translation_weighting=100.0, inital_rotation_weighting=100.0, num_threads=1)
+        d.update(kw)
+        super().__init__(**d)
+
+
 def available(which: str) -> bool:
     return os.path.exists(_PATHS[which])
 
@@ -125,6 +139,11 @@ class OracleLib:
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.vbo_umap_order.restype = None
         lib.vbo_umap_order.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.vbo_icp_run.restype = C.c_int
+        lib.vbo_icp_run.argtypes = [C.c_void_p, C.POINTER(IcpConfig), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                    C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.vbo_icp_shuffle.restype = None
+        lib.vbo_icp_shuffle.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
         lib.vbo_mc_tables.restype = C.c_int
         lib.vbo_mc_tables.argtypes = [C.c_void_p, C.c_void_p]
         self.lib = lib
@@ -167,6 +186,18 @@ class OracleMap:
                                     cols.ctypes.data, pts.shape[0], int(freespace), order)
         if rc != 0:
             raise RuntimeError(f"vbo_integrate rc={rc}")
+
+    def icp(self, cfg: "IcpConfig", points, q_wxyz, t, seed: int):
+        """ICP::runICP against this map's TSDF layer -> (q_wxyz, t, num_updates)."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        q = np.ascontiguousarray(q_wxyz, dtype=np.float32)
+        tt = np.ascontiguousarray(t, dtype=np.float32)
+        oq, ot, nu = np.zeros(4, np.float32), np.zeros(3, np.float32), C.c_uint64(0)
+        rc = self.lib.vbo_icp_run(self.h, C.byref(cfg), pts.ctypes.data, pts.shape[0], q.ctypes.data, tt.ctypes.data,
+                                  int(seed) & 0xffffffff, oq.ctypes.data, ot.ctypes.data, C.byref(nu))
+        if rc != 0:
+            raise RuntimeError(f"vbo_icp_run rc={rc}")
+        return oq, ot, int(nu.value)
 
     def last_seconds(self) -> float:
         return float(self.lib.vbo_last_seconds(self.h))

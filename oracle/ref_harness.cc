@@ -11,6 +11,10 @@
 #include <memory>
 #include <vector>
 
+#include <numeric>
+#include <random>
+
+#include "voxblox/alignment/icp.h"
 #include "voxblox/core/layer.h"
 #include "voxblox/core/voxel.h"
 #include "voxblox/integrator/esdf_integrator.h"
@@ -335,3 +339,38 @@ extern "C" void vbo_umap_order(const uint32_t* hashes, uint64_t n, uint32_t* out
 
 extern "C" {
 }  // extern "C"
+
+// ---------------------------------------------------------------- ICP (src/alignment/icp.cc)
+extern "C" int vbo_icp_run(void* hv, const vbo_icp_config* c, const float* xyz, uint64_t n, const float q[4],
+                           const float t[3], uint32_t seed, float out_q[4], float out_t[3], uint64_t* num_updates) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (c->num_threads != 1) return 3;  // the reference's threads race: only one thread is a function of its input
+  voxblox::ICP::Config cfg;
+  cfg.refine_roll_pitch = c->refine_roll_pitch != 0;
+  cfg.mini_batch_size = c->mini_batch_size;
+  cfg.min_match_ratio = c->min_match_ratio;
+  cfg.subsample_keep_ratio = c->subsample_keep_ratio;
+  cfg.inital_translation_weighting = c->inital_translation_weighting;
+  cfg.inital_rotation_weighting = c->inital_rotation_weighting;
+  cfg.num_threads = static_cast<size_t>(c->num_threads);
+  voxblox::ICP icp(cfg);
+  voxblox::Pointcloud points(n);
+  for (uint64_t i = 0; i < n; ++i) points[i] = voxblox::Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  const voxblox::Transformation T_init(voxblox::Rotation(q[0], q[1], q[2], q[3]), voxblox::Point(t[0], t[1], t[2]));
+  voxblox::Transformation T_out;
+  const auto t0 = std::chrono::steady_clock::now();
+  const size_t updates = icp.runICP(*h->tsdf, points, T_init, &T_out, seed);
+  h->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  out_q[0] = T_out.getRotation().w();
+  out_q[1] = T_out.getRotation().x();
+  out_q[2] = T_out.getRotation().y();
+  out_q[3] = T_out.getRotation().z();
+  for (int i = 0; i < 3; ++i) out_t[i] = T_out.getPosition()[i];
+  if (num_updates) *num_updates = updates;
+  return 0;
+}
+
+extern "C" void vbo_icp_shuffle(uint64_t n, uint32_t seed, uint32_t* out) {
+  std::iota(out, out + n, 0u);
+  std::shuffle(out, out + n, std::default_random_engine(seed));
+}

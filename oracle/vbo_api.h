@@ -125,6 +125,29 @@ uint64_t vbo_mesh_get(void* h, const int32_t idx[3], float* vertices, float* nor
  * returns 0 from the reference library, 1 from the restatement (which holds no second copy). */
 int vbo_mc_tables(int32_t tri[256 * 16], int32_t edges[12 * 2]);
 
+/* POD mirror of ICP::Config (voxblox/include/voxblox/alignment/icp.h:76-108; field names as spelled there). */
+typedef struct vbo_icp_config {
+  int32_t refine_roll_pitch;
+  int32_t mini_batch_size;
+  float min_match_ratio;
+  float subsample_keep_ratio;
+  float inital_translation_weighting;
+  float inital_rotation_weighting;
+  int32_t num_threads;
+} vbo_icp_config;
+/* ICP::runICP(tsdf_layer, points, inital_T_tsdf_sensor, &refined_T_tsdf_sensor, seed) (icp.h:118-123,
+ * icp.cc:219-259) against the map's TSDF layer; returns 0 and the number of successful mini batches.
+ * The reference library runs the reference's own class: deterministic only with num_threads = 1 (its
+ * threads race for batches and for the pose).  The restatement also accepts num_threads = T > 1 and
+ * then follows ONE legal schedule of those T threads, the round-robin one: in every round thread
+ * w = 0..T-1 takes the next batch (atomic_idx_ order), matches it against the pose snapshot it took at
+ * its own last successful fusion, and the fusions of the round are applied in the order w = 0..T-1. */
+int vbo_icp_run(void* h, const vbo_icp_config* cfg, const float* xyz, uint64_t n, const float q_wxyz[4],
+                const float t[3], uint32_t seed, float out_q_wxyz[4], float out_t[3], uint64_t* num_updates);
+/* std::shuffle(first, last, std::default_random_engine(seed)) of n elements (icp.cc:229-233):
+ * out[i] = original position of the element that ends at position i. */
+void vbo_icp_shuffle(uint64_t n, uint32_t seed, uint32_t* out);
+
 /* Iteration order of a std::unordered_map<key, ...> with hash(key) = hashes[i] (as size_t) after
  * inserting keys 0..n-1 one by one with operator[], exactly as bundleRays fills voxel_map
  * (tsdf_integrator.cc:340-371): out[p] = the key at iteration position p.  Checks the device's

@@ -24,7 +24,9 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <numeric>
 #include <queue>
+#include <random>
 #include <unordered_map>
 #include <unordered_set>
 #include <utility>
@@ -1279,3 +1281,383 @@ extern "C" void vbo_umap_order(const uint32_t* hashes, uint64_t n, uint32_t* out
 
 extern "C" {
 }  // extern "C"
+
+// =====================================================================================
+// ICP pose refinement (src/alignment/icp.cc, include/voxblox/alignment/icp.h,
+// interpolator/interpolator_inl.h -- the nearest-voxel paths icp.cc:126-128 selects).
+// Third-party arithmetic (Eigen JacobiSVD / quaternion conversions, minkindr log / exp) is
+// restated from the published algorithms; the ICP parity bound is a float tolerance.
+// =====================================================================================
+namespace {
+
+struct Quat {
+  float w, x, y, z;
+};
+inline Quat qmul(const Quat& a, const Quat& b) {  // Eigen quat_product, scalar path
+  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+inline V3 qrot(const Quat& q, V3 p) {  // QuaternionBase::_transformVector
+  const V3 qv{q.x, q.y, q.z};
+  V3 uv = cross3(qv, p);
+  uv = uv + uv;
+  return (p + uv * q.w) + cross3(qv, uv);
+}
+inline Quat qconj(const Quat& q) { return {q.w, -q.x, -q.y, -q.z}; }
+struct SE3 {
+  Quat q;
+  V3 t;
+};
+inline SE3 se3mul(const SE3& a, const SE3& b) { return {qmul(a.q, b.q), a.t + qrot(a.q, b.t)}; }
+inline SE3 se3inv(const SE3& a) {
+  const Quat qi = qconj(a.q);
+  const V3 r = qrot(qi, a.t);
+  return {qi, V3{-r.x, -r.y, -r.z}};
+}
+// Eigen: quaternion <- rotation matrix (m[r][c])
+inline Quat quatFromMatrix(const float m[3][3]) {
+  Quat q;
+  float t = m[0][0] + m[1][1] + m[2][2];
+  if (t > 0.0f) {
+    t = std::sqrt(t + 1.0f);
+    q.w = 0.5f * t;
+    t = 0.5f / t;
+    q.x = (m[2][1] - m[1][2]) * t;
+    q.y = (m[0][2] - m[2][0]) * t;
+    q.z = (m[1][0] - m[0][1]) * t;
+  } else {
+    int i = 0;
+    if (m[1][1] > m[0][0]) i = 1;
+    if (m[2][2] > m[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    float v[3];
+    t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0f);
+    v[i] = 0.5f * t;
+    t = 0.5f / t;
+    q.w = (m[k][j] - m[j][k]) * t;
+    v[j] = (m[j][i] + m[i][j]) * t;
+    v[k] = (m[k][i] + m[i][k]) * t;
+    q.x = v[0];
+    q.y = v[1];
+    q.z = v[2];
+  }
+  return q;
+}
+// minkindr RotationQuaternion::log / exp (see oracle/shim/kindr/minimal/quat-transformation.h)
+inline V3 quatLog(const Quat& q) {
+  const V3 a{q.x, q.y, q.z};
+  const float na = norm3(a), eta = q.w;
+  float scale;
+  if (std::fabs(eta) < na) {
+    scale = eta >= 0.0f ? std::acos(eta) / na : -std::acos(-eta) / na;
+  } else {
+    const float s = std::fabs(na) < std::pow(std::numeric_limits<float>::epsilon(), 0.25f)
+                        ? 1.0f + na * na * float(1.0 / 6.0)
+                        : std::asin(na) / na;
+    scale = eta > 0.0f ? s : -s;
+  }
+  return a * (2.0f * scale);
+}
+inline Quat quatExp(V3 d) {
+  const double x = d.x, y = d.y, z = d.z;
+  const double theta = std::sqrt(x * x + y * y + z * z);
+  const double na = theta < std::pow(std::numeric_limits<double>::epsilon(), 0.25) ? 0.5 + (theta * theta) * (1.0 / 48.0)
+                                                                                  : std::sin(theta * 0.5) / theta;
+  return {static_cast<float>(std::cos(theta * 0.5)), static_cast<float>(x * na), static_cast<float>(y * na),
+          static_cast<float>(z * na)};
+}
+
+// 3 x 3 proper rotation maximising trace(R H) (= V diag(1, 1, det) U^T of H = U S V^T, icp.h:160-177), by
+// the eigen-decomposition of H^T H in double (cyclic Jacobi); returns false on non-finite input.
+inline bool rotationFromH3(const float hf[3][3], float r[3][3]) {
+  double a[3][3], b[3][3], v[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = hf[i][j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += a[k][i] * a[k][j];
+      b[i][j] = s;
+      v[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) (i == j ? diag : off) += b[i][j] * b[i][j];
+    if (!(off > 1e-60) || off <= 1e-32 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (b[p][q] == 0.0) continue;
+        const double theta = (b[q][q] - b[p][p]) / (2.0 * b[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double bkp = b[k][p], bkq = b[k][q];
+          b[k][p] = c * bkp - sn * bkq;
+          b[k][q] = sn * bkp + c * bkq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double bpk = b[p][k], bqk = b[q][k];
+          b[p][k] = c * bpk - sn * bqk;
+          b[q][k] = sn * bpk + c * bqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - sn * vkq;
+          v[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (b[order[j]][order[j]] > b[order[i]][order[i]]) std::swap(order[i], order[j]);
+  double u[3][3], vs[3][3], sv[3];
+  for (int c = 0; c < 3; ++c) {
+    sv[c] = std::sqrt(b[order[c]][order[c]] > 0 ? b[order[c]][order[c]] : 0.0);
+    for (int k = 0; k < 3; ++k) vs[k][c] = v[k][order[c]];
+  }
+  int good = 0;
+  for (int c = 0; c < 3; ++c) {
+    if (sv[c] > 1e-12 * (sv[0] > 0 ? sv[0] : 1.0) && sv[c] > 0) {
+      for (int i = 0; i < 3; ++i) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += a[i][k] * vs[k][c];
+        u[i][c] = s / sv[c];
+      }
+      good = c + 1;
+    } else {
+      break;
+    }
+  }
+  for (int c = good; c < 3; ++c)
+    for (int e = 0; e < 3; ++e) {
+      double w[3] = {e == 0 ? 1.0 : 0.0, e == 1 ? 1.0 : 0.0, e == 2 ? 1.0 : 0.0};
+      for (int p = 0; p < c; ++p) {
+        double dp = 0;
+        for (int i = 0; i < 3; ++i) dp += w[i] * u[i][p];
+        for (int i = 0; i < 3; ++i) w[i] -= dp * u[i][p];
+      }
+      const double nn = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+      if (nn > 0.1) {
+        for (int i = 0; i < 3; ++i) u[i][c] = w[i] / std::sqrt(nn);
+        break;
+      }
+    }
+  float uf[3][3], vf[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      uf[i][j] = static_cast<float>(u[i][j]);
+      vf[i][j] = static_cast<float>(vs[i][j]);
+    }
+  auto det3 = [](const float m[3][3]) {
+    return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+           m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+  };
+  if (det3(uf) * det3(vf) < 0.0f)
+    for (int i = 0; i < 3; ++i) vf[i][2] = vf[i][2] * -1.0f;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[i][j] = vf[i][0] * uf[j][0] + vf[i][1] * uf[j][1] + vf[i][2] * uf[j][2];
+  return true;
+}
+
+struct IcpStep {
+  bool ok = false;
+  SE3 delta{};
+  float info[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct IcpRunner {
+  const Map& m;
+  vbo_icp_config cfg;
+  float block_size_inv;
+
+  IcpRunner(const Map& map, const vbo_icp_config& c) : m(map), cfg(c) {
+    block_size_inv = static_cast<float>(1.0 / m.block_size);  // Layer ctor, core/layer.h:41
+  }
+
+  // Interpolator::getNearestDistance (interpolator_inl.h:330-345): Layer::getBlockPtrByCoordinates,
+  // Block::getVoxelByCoordinates (truncated voxel index, block_inl.h:30-40), observed = weight > 1e-6
+  bool nearestDistance(V3 p, float* d, bool* has_block) const {
+    const L3 bi = gridIndex(p, block_size_inv);
+    auto it = m.tsdf.find(I3{static_cast<int>(bi.x), static_cast<int>(bi.y), static_cast<int>(bi.z)});
+    if (it == m.tsdf.end()) {
+      *has_block = false;
+      return false;
+    }
+    *has_block = true;
+    const V3 origin{static_cast<float>(static_cast<int>(bi.x)) * m.block_size, static_cast<float>(static_cast<int>(bi.y)) * m.block_size,
+                    static_cast<float>(static_cast<int>(bi.z)) * m.block_size};
+    const L3 vi = gridIndex(p - origin, m.voxel_size_inv);
+    const int mx = m.vps - 1;
+    const int x = std::max(std::min(static_cast<int>(vi.x), mx), 0), y = std::max(std::min(static_cast<int>(vi.y), mx), 0),
+              z = std::max(std::min(static_cast<int>(vi.z), mx), 0);
+    const TsdfVox& v = it->second->vox[static_cast<size_t>(x + m.vps * (y + m.vps * z))];
+    *d = v.distance;
+    return static_cast<double>(v.weight) > 1e-6;
+  }
+  // Interpolator::getGradient, interpolate = false (interpolator_inl.h:48-77)
+  bool gradient(V3 p, V3* g) const {
+    float d;
+    bool has_block;
+    nearestDistance(p, &d, &has_block);
+    if (!has_block) return false;
+    float gr[3] = {0.0f, 0.0f, 0.0f};
+    for (int i = 0; i < 3; ++i)
+      for (int sign = -1; sign <= 1; sign += 2) {
+        V3 q = p;
+        const float off = static_cast<float>(sign) * m.voxel_size;
+        (i == 0 ? q.x : i == 1 ? q.y : q.z) += off;
+        float od;
+        bool hb;
+        if (!nearestDistance(q, &od, &hb)) return false;
+        gr[i] = gr[i] + od * static_cast<float>(sign);
+      }
+    const float den = 2 * m.voxel_size;
+    *g = V3{gr[0] / den, gr[1] / den, gr[2] / den};
+    return true;
+  }
+
+  // ICP::stepICP = matchPoints + getTransformFromMatchedPoints (icp.cc:104-169, :50-80, icp.h:146-187)
+  IcpStep step(const std::vector<V3>& pts, size_t start, const SE3& T) const {
+    IcpStep out;
+    const size_t mb = static_cast<size_t>(cfg.mini_batch_size);
+    std::vector<V3> src, tgt;
+    float info[6];
+    for (float& v : info) v = kEps;
+    const Pose pose{T.q.w, T.q.x, T.q.y, T.q.z, T.t};
+    for (size_t i = start; i < std::min(pts.size(), start + mb); ++i) {
+      const V3 p = pose.apply(pts[i]);
+      const L3 vidx = gridIndex(p, m.voxel_size_inv);
+      float dist;
+      bool hb;
+      V3 g;
+      if (nearestDistance(p, &dist, &hb) && gradient(p, &g) && sqnorm3(g) > 0.1f) {
+        g = unit3(g);
+        const V3 q = p - T.t;  // addNormalizedPointInfo (icp.cc:82-102)
+        info[0] = info[0] + 2.0f * (g.x * g.x);
+        info[1] = info[1] + 2.0f * (g.y * g.y);
+        info[2] = info[2] + 2.0f * (g.z * g.z);
+        info[3] = info[3] + 2.0f * (q.y * q.y * g.z * g.z + q.z * q.z * g.y * g.y);
+        info[4] = info[4] + 2.0f * (q.x * q.x * g.z * g.z + q.z * q.z * g.x * g.x);
+        info[5] = info[5] + 2.0f * (q.x * q.x * g.y * g.y + q.y * q.y * g.x * g.x);
+        const V3 centre = centerPoint(vidx, m.voxel_size);
+        dist = dist + dot3(g, p - centre);
+        src.push_back(p);
+        tgt.push_back(p - g * dist);
+      }
+    }
+    for (int k = 0; k < 6; ++k) out.info[k] = info[k];
+    const int n = static_cast<int>(src.size());
+    if (n < std::max(3, static_cast<int>(cfg.mini_batch_size * cfg.min_match_ratio))) return out;
+    V3 sc = src[0], tc = tgt[0];
+    for (int i = 1; i < n; ++i) {
+      sc = sc + src[i];
+      tc = tc + tgt[i];
+    }
+    sc = sc / static_cast<float>(n);
+    tc = tc / static_cast<float>(n);
+    const int dim = cfg.refine_roll_pitch ? 3 : 2;
+    float h[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < n; ++k) {
+      const V3 s = src[k] - sc, t = tgt[k] - tc;
+      const float sv[3] = {s.x, s.y, s.z}, tv[3] = {t.x, t.y, t.z};
+      for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j) h[i][j] = h[i][j] + sv[i] * tv[j];
+    }
+    float r[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (dim == 2) {
+      // the proper rotation V diag(1, det) U^T of the 2 x 2 SVD maximises trace(R H): closed form
+      const float a = h[0][0] + h[1][1], b = h[0][1] - h[1][0];
+      const float nrm = std::sqrt(a * a + b * b);
+      const float c = a / nrm, s = b / nrm;
+      r[0][0] = c;
+      r[0][1] = -s;
+      r[1][0] = s;
+      r[1][1] = c;
+    } else if (!rotationFromH3(h, r)) {
+      return out;
+    }
+    float sum = 0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) sum += r[i][j];
+    if (!std::isfinite(sum)) return out;
+    out.delta.q = quatFromMatrix(r);
+    out.delta.t = tc - qrot(out.delta.q, sc);
+    out.ok = true;
+    return out;
+  }
+};
+
+}  // namespace
+
+extern "C" void vbo_icp_shuffle(uint64_t n, uint32_t seed, uint32_t* out) {
+  std::iota(out, out + n, 0u);
+  std::shuffle(out, out + n, std::default_random_engine(seed));  // the C++ library's own, as icp.cc:231-233 calls it
+}
+
+extern "C" int vbo_icp_run(void* hv, const vbo_icp_config* c, const float* xyz, uint64_t n, const float q[4],
+                           const float t[3], uint32_t seed, float out_q[4], float out_t[3], uint64_t* num_updates) {
+  Map& m = *static_cast<Map*>(hv);
+  if (c->num_threads < 1 || c->mini_batch_size < 1) return 2;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<uint32_t> perm(n);
+  vbo_icp_shuffle(n, seed, perm.data());
+  std::vector<V3> pts(n);
+  for (uint64_t i = 0; i < n; ++i) pts[i] = V3{xyz[3 * perm[i]], xyz[3 * perm[i] + 1], xyz[3 * perm[i] + 2]};
+  IcpRunner run(m, *c);
+  SE3 cur{Quat{q[0], q[1], q[2], q[3]}, V3{t[0], t[1], t[2]}};
+  float base[6] = {c->inital_translation_weighting, c->inital_translation_weighting, c->inital_translation_weighting,
+                   c->inital_rotation_weighting,    c->inital_rotation_weighting,    c->inital_rotation_weighting};
+  const int T = c->num_threads;
+  std::vector<SE3> snapshot(T, cur);  // runThread's current_thread_T_tsdf_sensor (icp.cc:178-182)
+  std::vector<char> alive(T, 1);
+  size_t next_idx = 0, updates = 0;
+  const size_t mb = static_cast<size_t>(c->mini_batch_size);
+  for (;;) {
+    // one round of the round-robin schedule: fetch_add in thread order, match, fuse in thread order
+    std::vector<std::pair<int, size_t>> jobs;
+    for (int w = 0; w < T; ++w) {
+      if (!alive[w]) continue;
+      const size_t start = next_idx;
+      next_idx += mb;
+      if (static_cast<float>(start) > c->subsample_keep_ratio * static_cast<float>(n)) {  // icp.cc:186-188
+        alive[w] = 0;
+        continue;
+      }
+      jobs.emplace_back(w, start);
+    }
+    if (jobs.empty()) break;
+    std::vector<IcpStep> res(jobs.size());
+    for (size_t k = 0; k < jobs.size(); ++k) res[k] = run.step(pts, jobs[k].second, snapshot[jobs[k].first]);
+    for (size_t k = 0; k < jobs.size(); ++k) {
+      if (!res[k].ok) continue;
+      // icp.cc:195-213
+      const SE3 t_temp = se3mul(res[k].delta, cur);
+      SE3 d = se3mul(se3inv(cur), t_temp);
+      const V3 w3 = quatLog(d.q);
+      const float lg[6] = {d.t.x, d.t.y, d.t.z, w3.x, w3.y, w3.z};
+      float wl[6];
+      for (int i = 0; i < 6; ++i) {
+        const float weight = res[k].info[i] / (base[i] + res[k].info[i]);
+        wl[i] = weight * lg[i];
+      }
+      d = SE3{quatExp(V3{wl[3], wl[4], wl[5]}), V3{wl[0], wl[1], wl[2]}};
+      for (int i = 0; i < 6; ++i) base[i] = base[i] + res[k].info[i];
+      cur = se3mul(cur, d);
+      snapshot[jobs[k].first] = cur;
+      ++updates;
+    }
+  }
+  out_q[0] = cur.q.w;
+  out_q[1] = cur.q.x;
+  out_q[2] = cur.q.y;
+  out_q[3] = cur.q.z;
+  out_t[0] = cur.t.x;
+  out_t[1] = cur.t.y;
+  out_t[2] = cur.t.z;
+  if (num_updates) *num_updates = updates;
+  m.last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+

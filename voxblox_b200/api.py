@@ -101,6 +101,20 @@ class MeshIntegratorConfig(C.Structure):
         super().__init__(use_color=int(bool(use_color)), min_weight=float(min_weight))
 
 
+class ICPConfig(C.Structure):
+    """ICP::Config (alignment/icp.h:76-108), field names as spelled there.  num_threads defaults to 1 (the
+    reference default, hardware_concurrency(), makes its result depend on thread timing); 1..32 here."""
+    _fields_ = [("refine_roll_pitch", C.c_int32), ("mini_batch_size", C.c_int32), ("min_match_ratio", C.c_float),
+                ("subsample_keep_ratio", C.c_float), ("inital_translation_weighting", C.c_float),
+                ("inital_rotation_weighting", C.c_float), ("num_threads", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, **kw):
+        d = dict(refine_roll_pitch=0, mini_batch_size=20, min_match_ratio=0.8, subsample_keep_ratio=0.5,
+                 inital_translation_weighting=100.0, inital_rotation_weighting=100.0, num_threads=1, reserved=0)
+        d.update(kw)
+        super().__init__(**d)
+
+
 class EngineOptions(C.Structure):
     """vbx_engine_options: device-side sizing (no reference counterpart)."""
     _fields_ = [("device", C.c_int32), ("max_blocks", C.c_uint32),
@@ -122,7 +136,7 @@ EXPORTS = ["vbx_create", "vbx_destroy", "vbx_last_error", "vbx_version", "vbx_ge
            "vbx_timer_start", "vbx_timer_stop_ms", "vbx_set_stage_profiling", "vbx_get_stage_ms",
            "vbx_host_alloc", "vbx_host_free", "vbx_host_copy_ms", "vbx_block_owner",
            "vbx_debug_sort", "vbx_debug_scan", "vbx_debug_bundle_order", "vbx_tsdf_integrate_async", "vbx_esdf_update_blocks", "vbx_esdf_set_max_distance",
-           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_esdf_add_robot_position", "vbx_esdf_clear", "vbx_mesh_generate", "vbx_mesh_download", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
+           "vbx_esdf_set_full_euclidean", "vbx_esdf_get_config", "vbx_esdf_add_robot_position", "vbx_esdf_clear", "vbx_mesh_generate", "vbx_mesh_download", "vbx_icp_run", "vbx_icp_run_device", "vbx_mirror_updated", "vbx_serialize_updated", "vbx_deserialize_blocks", "vbx_save_layer", "vbx_load_layer",
            "vbx_proto_encode_layer", "vbx_proto_encode_block", "vbx_proto_decode_block"]
 
 _lib = None
@@ -209,6 +223,10 @@ def load_library():
     lib.vbx_esdf_add_robot_position.argtypes = [vp, vp]
     lib.vbx_esdf_clear.restype = i32
     lib.vbx_esdf_clear.argtypes = [vp]
+    for name in ("vbx_icp_run", "vbx_icp_run_device"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [vp, C.POINTER(ICPConfig), vp, u64, vp, vp, C.c_uint32, vp, vp, C.POINTER(u64)]
     lib.vbx_mesh_generate.restype = i32
     lib.vbx_mesh_generate.argtypes = [vp, C.POINTER(MeshIntegratorConfig), i32, i32, C.POINTER(u64), C.POINTER(u64)]
     lib.vbx_mesh_download.restype = i32
@@ -744,6 +762,36 @@ class MeshLayer:
 
     def getNumberOfAllocatedMeshes(self) -> int:
         return len(self._meshes)
+
+
+class ICP:
+    """voxblox::ICP (alignment/icp.h:72-233): point-to-TSDF pose refinement against the device map."""
+
+    def __init__(self, config: ICPConfig):
+        self.config_ = config
+
+    def refiningRollPitch(self) -> bool:  # icp.h:125
+        return bool(self.config_.refine_roll_pitch)
+
+    def runICP(self, tsdf_layer: "Layer", points, inital_T_tsdf_sensor, seed: int):
+        """runICP(tsdf_layer, points, inital_T_tsdf_sensor, &refined_T_tsdf_sensor, seed) (icp.h:118-123):
+        returns (number of successful mini batches, (q_wxyz, t) refined)."""
+        return self._run(tsdf_layer, np.ascontiguousarray(points, dtype=np.float32).ctypes.data, int(len(points)),
+                         inital_T_tsdf_sensor, seed, device=False)
+
+    def runICPDevice(self, tsdf_layer: "Layer", d_points_ptr: int, n: int, inital_T_tsdf_sensor, seed: int):
+        """The same with the cloud (3n floats) already in device memory."""
+        return self._run(tsdf_layer, d_points_ptr, n, inital_T_tsdf_sensor, seed, device=True)
+
+    def _run(self, tsdf_layer, ptr, n, T, seed, device):
+        ctx = tsdf_layer._bound()
+        q = np.ascontiguousarray(T[0], dtype=np.float32)
+        t = np.ascontiguousarray(T[1], dtype=np.float32)
+        oq, ot, nu = np.zeros(4, np.float32), np.zeros(3, np.float32), C.c_uint64(0)
+        f = ctx.lib.vbx_icp_run_device if device else ctx.lib.vbx_icp_run
+        ctx.check(f(ctx.handle, C.byref(self.config_), ptr, n, q.ctypes.data, t.ctypes.data, int(seed) & 0xffffffff,
+                    oq.ctypes.data, ot.ctypes.data, C.byref(nu)), "runICP")
+        return int(nu.value), (oq, ot)
 
 
 class MeshIntegrator:

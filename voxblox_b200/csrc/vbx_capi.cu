@@ -519,6 +519,7 @@ void vbx_destroy(vbx_ctx* c) {
   c->stream = c->stream_main;
   esdf_destroy(c);
   mesh_destroy(c);
+  icp_destroy(c);
   Tables& t = c->tab;
   void* ptrs[] = {t.hkeys,        t.hslot,       t.htouch, t.new_list, t.touched_list,
                   t.slot_key,     t.slot_updated, t.slot_esdf_updated, t.slot_has_esdf, t.tsdf, c->d_xyz,
@@ -931,6 +932,22 @@ int vbx_mesh_generate(vbx_ctx* c, const vbx_mesh_config* cfg, int only_mesh_upda
   VBX_CUDA(c, cudaSetDevice(c->device));
   VBX_DRAIN(c);
   return mesh_generate(c, cfg, only_mesh_updated_blocks, clear_updated_flag, n_blocks, n_vertices);
+}
+
+int vbx_icp_run(vbx_ctx* c, const vbx_icp_config* cfg, const float* points_C, uint64_t n, const float q_wxyz[4],
+                const float t[3], uint32_t seed, float out_q_wxyz[4], float out_t[3], uint64_t* num_updates) {
+  if (!c || !cfg || (n && !points_C) || !q_wxyz || !t || !out_q_wxyz || !out_t) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  return icp_run(c, cfg, points_C, 0, n, q_wxyz, t, seed, out_q_wxyz, out_t, num_updates);
+}
+
+int vbx_icp_run_device(vbx_ctx* c, const vbx_icp_config* cfg, const float* d_points_C, uint64_t n, const float q_wxyz[4],
+                       const float t[3], uint32_t seed, float out_q_wxyz[4], float out_t[3], uint64_t* num_updates) {
+  if (!c || !cfg || (n && !d_points_C) || !q_wxyz || !t || !out_q_wxyz || !out_t) return fail(c, VBX_E_INVALID, "null argument");
+  VBX_CUDA(c, cudaSetDevice(c->device));
+  VBX_DRAIN(c);
+  return icp_run(c, cfg, d_points_C, 1, n, q_wxyz, t, seed, out_q_wxyz, out_t, num_updates);
 }
 
 int vbx_mesh_download(vbx_ctx* c, int32_t* idx3, uint64_t* first_vertex, float* vertices, float* normals,

@@ -297,6 +297,13 @@ struct vbx_ctx {
   std::vector<int32_t> mesh_idx;
   std::vector<uint64_t> mesh_first_host = std::vector<uint64_t>(1, 0);
   bool mesh_use_color = false;
+  // ICP (vbx_icp.cu): shuffled point order (host page-locked + device), host-cloud staging, result block
+  uint32_t* icp_perm_dev = nullptr;
+  uint32_t* icp_perm_host = nullptr;
+  float* icp_points_dev = nullptr;
+  float* icp_out_dev = nullptr;
+  float* icp_out_host = nullptr;
+  uint64_t icp_cap = 0;
   // reporting
   uint32_t last_passes = 1;  // passes the last synchronous integrate call needed (K > max_updates_per_pass)
   uint64_t counters[16] = {0};
@@ -320,6 +327,9 @@ int mirror_updated(vbx_ctx* c, int layer, int updated_mask, int clear_mask, int3
                    uint8_t* updated_bits, uint64_t cap, uint64_t* n, int serialized);
 int esdf_destroy(vbx_ctx* c);
 void mesh_destroy(vbx_ctx* c);
+void icp_destroy(vbx_ctx* c);
+int icp_run(vbx_ctx* c, const vbx_icp_config* cfg, const float* points, int on_device, uint64_t n, const float q[4],
+            const float t[3], uint32_t seed, float out_q[4], float out_t[3], uint64_t* num_updates);
 int mesh_generate(vbx_ctx* c, const vbx_mesh_config* cfg, int only_updated, int clear_flag, uint64_t* n_blocks_out,
                   uint64_t* n_vertices_out);
 int mesh_download(vbx_ctx* c, int32_t* idx3, uint64_t* first_vertex, float* vertices, float* normals, uint8_t* colors);
