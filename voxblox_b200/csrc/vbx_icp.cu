@@ -19,7 +19,7 @@
 //   * fusion: thread 0 applies the fusions of the round in warp order.
 //
 // Arithmetic: float32 with one rounding per operation (the library is built with -fmad=false), in the
-// operation order of the reference's Eigen / minkindr expressions (oracle/shim restates those).  The 2-D
+// operation order of the reference's Eigen / minkindr expressions.  The 2-D
 // Procrustes rotation (refine_roll_pitch = false) uses the closed form atan2(h01 - h10, h00 + h11) of
 // V diag(1, det) U^T; the 3-D one an SVD by Jacobi rotations on H^T H in double.
 #include <algorithm>
