@@ -16,6 +16,7 @@
 #include <map>
 #include <vector>
 
+#include <voxblox/alignment/icp.h>
 #include <voxblox/core/layer.h>
 #include <voxblox/core/voxel.h>
 #include <voxblox/integrator/esdf_integrator.h>
@@ -390,6 +391,50 @@ class GpuMeshIntegrator {
   MeshIntegratorConfig config_;
   vbx_ctx* ctx_;
   MeshLayer* mesh_layer_;
+};
+
+/// voxblox::ICP (alignment/icp.h:72-233) against the device map: same constructor and runICP signature, so
+/// `icp_.reset(new ICP(getICPConfigFromRosParam(nh_private)))` in TsdfServer (voxblox_ros/src/tsdf_server.cc:114)
+/// and the call at tsdf_server.cc:259-262 only change the TYPE.  The TSDF layer argument selects the engine
+/// context a GpuTsdfIntegrator registered for it; scans still queued by pipelined submission are drained first.
+/// Config::num_threads racing host threads become that many warps under a fixed round-robin schedule
+/// (include/voxblox_b200.h), i.e. the result is deterministic where the reference's (num_threads > 1) is not.
+class GpuICP {
+ public:
+  explicit GpuICP(const ICP::Config& config) : config_(config) {}
+
+  size_t runICP(const Layer<TsdfVoxel>& tsdf_layer, const Pointcloud& points, const Transformation& inital_T_tsdf_sensor,
+                Transformation* refined_T_tsdf_sensor,
+                const unsigned seed = std::chrono::system_clock::now().time_since_epoch().count()) {
+    CHECK_NOTNULL(refined_T_tsdf_sensor);
+    vbx_ctx* ctx = gpu_detail::lookupContext(&tsdf_layer);
+    vbx_icp_config pod;
+    std::memset(&pod, 0, sizeof(pod));
+    pod.refine_roll_pitch = config_.refine_roll_pitch ? 1 : 0;
+    pod.mini_batch_size = config_.mini_batch_size;
+    pod.min_match_ratio = config_.min_match_ratio;
+    pod.subsample_keep_ratio = config_.subsample_keep_ratio;
+    pod.inital_translation_weighting = config_.inital_translation_weighting;
+    pod.inital_rotation_weighting = config_.inital_rotation_weighting;
+    pod.num_threads = static_cast<int32_t>(std::max<size_t>(1, std::min<size_t>(config_.num_threads, 32)));
+    const float q[4] = {inital_T_tsdf_sensor.getRotation().w(), inital_T_tsdf_sensor.getRotation().x(),
+                        inital_T_tsdf_sensor.getRotation().y(), inital_T_tsdf_sensor.getRotation().z()};
+    const Point p = inital_T_tsdf_sensor.getPosition();
+    const float t[3] = {p.x(), p.y(), p.z()};
+    float oq[4], ot[3];
+    uint64_t num_updates = 0;
+    gpu_detail::check(ctx,
+                      vbx_icp_run(ctx, &pod, points.empty() ? nullptr : reinterpret_cast<const float*>(points.data()), points.size(), q, t,
+                                  static_cast<uint32_t>(seed), oq, ot, &num_updates),
+                      "vbx_icp_run");
+    *refined_T_tsdf_sensor = Transformation(Rotation(oq[0], oq[1], oq[2], oq[3]), Point(ot[0], ot[1], ot[2]));
+    return static_cast<size_t>(num_updates);
+  }
+
+  bool refiningRollPitch() { return config_.refine_roll_pitch; }
+
+ private:
+  ICP::Config config_;
 };
 
 }  // namespace voxblox

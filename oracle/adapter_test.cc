@@ -3,6 +3,7 @@
 // classes, next to the reference's CPU integrators, the way test/test_sdf_integrators.cc does.
 // Simple must agree voxel for voxel (same update order); Merged is compared on the block set
 // and statistically (its CPU order is unordered_map iteration order).  Exit code 0 = pass.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -311,6 +312,45 @@ int main() {
     std::printf("mesh: blocks cpu %zu gpu %zu, block mismatches %zu, vertices %zu, differing %zu\n", a.size(), b.size(),
                 blocks_differ, vertices, diff);
     if (blocks_differ || diff || vertices == 0) ++failures;
+  }
+  // ICP through the adapter: the reference's own voxblox::ICP on the host layer next to GpuICP
+  // on the device map, same constructor / runICP signature, num_threads = 1 (the reference's deterministic
+  // setting), same seed.  The maps are bit identical (Merged); the refined poses agree to the float tolerance
+  // (a chain of SE(3) log / exp with library functions, tests/test_icp_gpu.py), the fused-batch counts exactly.
+  {
+    Layer<TsdfVoxel> tsdf_c(voxel_size, 16), tsdf_g(voxel_size, 16);
+    TsdfIntegratorBase::Ptr cpu = TsdfIntegratorFactory::create(TsdfIntegratorType::kMerged, config, &tsdf_c);
+    GpuTsdfIntegrator gpu(TsdfIntegratorType::kMerged, config, &tsdf_g);
+    Transformation T;
+    Pointcloud pts;
+    Colors cols;
+    for (int k = 0; k < 3; ++k) {
+      makeScan(k, &T, &pts, &cols);
+      cpu->integratePointCloud(T, pts, cols);
+      gpu.integratePointCloud(T, pts, cols);
+    }
+    makeScan(1, &T, &pts, &cols);
+    const Transformation guess(T.getRotation(), T.getPosition() + Point(0.03f, -0.02f, 0.01f));
+    size_t bad = 0;
+    for (int roll_pitch = 0; roll_pitch < 2; ++roll_pitch) {
+      ICP::Config ic;
+      ic.num_threads = 1;
+      ic.refine_roll_pitch = roll_pitch != 0;
+      ICP ref_icp(ic);
+      GpuICP gpu_icp(ic);  // <- the reference's constructor
+      Transformation Tc, Tg;
+      const size_t nc = ref_icp.runICP(tsdf_c, pts, guess, &Tc, 7u);
+      const size_t ng = gpu_icp.runICP(tsdf_g, pts, guess, &Tg, 7u);  // <- the reference's call
+      const float dq = std::max(std::max(std::fabs(Tc.getRotation().w() - Tg.getRotation().w()),
+                                         std::fabs(Tc.getRotation().x() - Tg.getRotation().x())),
+                                std::max(std::fabs(Tc.getRotation().y() - Tg.getRotation().y()),
+                                         std::fabs(Tc.getRotation().z() - Tg.getRotation().z())));
+      const float dt = (Tc.getPosition() - Tg.getPosition()).norm();
+      std::printf("icp (refine_roll_pitch %d): fused batches cpu %zu gpu %zu, |dq| %.3g, |dt| %.3g m, moved %.3g m\n", roll_pitch,
+                  nc, ng, dq, dt, (Tg.getPosition() - guess.getPosition()).norm());
+      if (nc != ng || nc == 0 || !(dq < 1e-4f) || !(dt < 1e-4f) || gpu_icp.refiningRollPitch() != ref_icp.refiningRollPitch()) ++bad;
+    }
+    if (bad) ++failures;
   }
   std::printf(failures ? "ADAPTER TEST FAILED\n" : "ADAPTER TEST OK\n");
   return failures ? 1 : 0;

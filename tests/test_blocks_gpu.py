@@ -250,6 +250,93 @@ def test_save_and_load_layer_file(tmp_path):
         other.loadBlocksFromFile(path)
 
 
+def test_loaded_file_with_duplicate_blocks_and_has_data(tmp_path):
+    """io::LoadBlocksFromFile with kReplace (io/layer_io_inl.h:71-73): a block listed twice keeps the LAST
+    payload; BlockProto.has_data (core/block_inl.h:73-109) survives a load -> save round trip, blocks the
+    integrator makes keep has_data = false, and removing a block forgets the flag."""
+    from tests.test_proto_io import _encode_block, _messages
+    import ctypes as C
+
+    lib = vb.load_library()
+    BlockProto, LayerProto = _messages()
+    vs, vps = float(np.float32(0.1)), 16
+    bs = float(np.float32(0.1) * np.float32(16))
+    rng = np.random.default_rng(5)
+    n_words = 3 * vps ** 3
+
+    def payload():
+        w = np.zeros((vps ** 3, 3), dtype=np.uint32)
+        w[:, 0] = rng.uniform(-0.4, 0.4, vps ** 3).astype(np.float32).view(np.uint32)
+        w[:, 1] = rng.uniform(0.5, 9.0, vps ** 3).astype(np.float32).view(np.uint32)
+        w[:, 2] = rng.integers(0, 2 ** 32, vps ** 3, dtype=np.uint32)
+        return w.reshape(-1)
+    first, second, third = payload(), payload(), payload()
+    blocks = [((1, 0, 0), True, first), ((0, 2, -1), False, second), ((1, 0, 0), True, third)]  # (1,0,0) twice
+
+    def varint_bytes(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+    n = C.c_uint64(0)
+    hdr = np.zeros(64, dtype=np.uint8)
+    assert lib.vbx_proto_encode_layer(vs, vps, b"tsdf", hdr.ctypes.data, hdr.size, C.byref(n)) == 0
+    data = varint_bytes(1 + len(blocks)) + varint_bytes(n.value) + hdr[:n.value].tobytes()
+    for idx, has, w in blocks:
+        msg = _encode_block(lib, vps, vs, [i * bs for i in idx], has, w)
+        data += varint_bytes(len(msg)) + msg
+    path = str(tmp_path / "dup.vxblx")
+    open(path, "wb").write(data)
+
+    cfg = vb.TsdfIntegratorConfig(default_truncation_distance=0.4, integrator_threads=1)
+    layer = vb.Layer(0.1, 16)
+    integ = vb.TsdfIntegratorFactory.create("merged", cfg, layer)
+    assert layer.loadBlocksFromFile(path) == 2
+    idx, words, _ = layer.serializeUpdated(0, 0)
+    got = {tuple(int(v) for v in idx[k]): words[k] for k in range(idx.shape[0])}
+    assert set(got) == {(1, 0, 0), (0, 2, -1)}
+    assert got[(1, 0, 0)].tobytes() == third.tobytes()       # the last payload, whole
+    assert got[(0, 2, -1)].tobytes() == second.tobytes()
+    # the integrator adds blocks of its own: has_data stays false on them
+    s = scenes.c3_room_sequence(n_scans=1, width=64, height=48)[0]
+    integ.integratePointCloud((s[2], s[3]), s[0], s[1])
+
+    def saved_flags(p):
+        layer.saveToFile(p, True)
+        raw = open(p, "rb").read()
+
+        def varint(pos):
+            v, shift = 0, 0
+            while True:
+                b = raw[pos]
+                pos += 1
+                v |= (b & 0x7F) << shift
+                shift += 7
+                if not b & 0x80:
+                    return v, pos
+        count, pos = varint(0)
+        size, pos = varint(pos)
+        pos += size
+        flags = {}
+        for _ in range(count - 1):
+            size, pos = varint(pos)
+            bm = BlockProto()
+            bm.ParseFromString(raw[pos:pos + size])
+            pos += size
+            flags[tuple(int(round(v / bs)) for v in (bm.origin_x, bm.origin_y, bm.origin_z))] = bool(bm.has_data)
+        return flags
+    flags = saved_flags(str(tmp_path / "resaved.vxblx"))
+    assert flags[(1, 0, 0)] is True and flags[(0, 2, -1)] is False
+    assert sum(flags.values()) == 1 and len(flags) > 2
+    # Layer::removeBlock + a new block at the same index: a fresh Block, has_data false
+    layer.removeBlock((1, 0, 0))
+    layer.insertBlocks(np.array([[1, 0, 0]], dtype=np.int32), layer.getBlocks(np.array([[0, 2, -1]], dtype=np.int32))[0])
+    assert saved_flags(str(tmp_path / "resaved2.vxblx"))[(1, 0, 0)] is False
+
+
 def test_esdf_only_blocks_stay_out_of_the_tsdf_layer():
     """Blocks inserted into the ESDF layer at indices the TSDF layer does not hold (what
     addNewRobotPosition and loading an ESDF map do) occupy pool slots of their own: the TSDF

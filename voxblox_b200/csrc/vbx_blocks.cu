@@ -253,6 +253,8 @@ int clear_layer(vbx_ctx* c, int layer) {
     }
     return remove_blocks(c, layer, idx.data(), c->n_blocks);
   }
+  c->has_data_keys[0].clear();
+  c->has_data_keys[1].clear();
   // no ESDF layer: reset the whole map
   const size_t used = (size_t)c->n_blocks * c->vox_per_block;
   c->esdf_pending_raise = c->esdf_pending_open = 0;
@@ -277,6 +279,7 @@ int remove_blocks(vbx_ctx* c, int layer, const int32_t* idx3, uint64_t m) {
   if (int rc = refresh_host_mirror(c)) return rc;
   std::vector<int32_t> victims;
   for (uint64_t i = 0; i < m; ++i) {
+    c->has_data_keys[layer == VBX_LAYER_ESDF ? 1 : 0].erase(pack3(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
     auto it = c->host_key2slot.find(pack3(idx3[3 * i], idx3[3 * i + 1], idx3[3 * i + 2]));
     if (it != c->host_key2slot.end()) victims.push_back(it->second);  // erasing a missing block is a no-op
   }

@@ -7,6 +7,7 @@
 
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/voxblox_b200.h"
@@ -272,6 +273,9 @@ struct vbx_ctx {
   // host mirror of slot_key (refreshed lazily)
   std::vector<uint64_t> host_slot_key;
   std::unordered_map<uint64_t, int32_t> host_key2slot;
+  // Block::has_data_ (core/block.h:206): never set by the integrators, carried by BlockProto; blocks loaded
+  // from a .vxblx file with has_data = true are remembered per layer so that a re-save writes the flag back
+  std::unordered_set<uint64_t> has_data_keys[2];
   // ESDF
   bool has_esdf = false;
   vbx_esdf_config ecfg;

@@ -208,8 +208,9 @@ int save_layer(vbx_ctx* c, int layer, const char* path, int clear_file) {
     // Block origin = getOriginPointFromGridIndex(index, block_size) in float (core/common.h:196-201)
     const double origin[3] = {(double)((float)idx[3 * b] * block_size), (double)((float)idx[3 * b + 1] * block_size),
                               (double)((float)idx[3 * b + 2] * block_size)};
-    encode_block_proto(&msg, (int32_t)(1u << c->L), (double)c->voxel_size, origin, /*has_data=*/false,
-                       words.data() + b * wpb, wpb);
+    // has_data_: false for every block the integrators made; true only where a loaded file said so
+    const bool has_data = c->has_data_keys[layer == VBX_LAYER_ESDF ? 1 : 0].count(pack3(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2])) != 0;
+    encode_block_proto(&msg, (int32_t)(1u << c->L), (double)c->voxel_size, origin, has_data, words.data() + b * wpb, wpb);
     out.clear();
     put_varint(&out, msg.size());
     ok = std::fwrite(out.data(), 1, out.size(), f) == out.size() && std::fwrite(msg.data(), 1, msg.size(), f) == msg.size();
@@ -255,6 +256,7 @@ int load_layer(vbx_ctx* c, int layer, const char* path, uint64_t* n_loaded) {
                             lm.vps == (1u << c->L) && lm.type == layer_type(layer);
     std::vector<int32_t> idx;
     std::vector<uint32_t> words;
+    std::vector<uint8_t> has_data;
     BlockMsg bm;
     for (uint64_t b = 0; b + 1 < num_protos; ++b) {
       const uint64_t bsize = r.varint();
@@ -271,16 +273,45 @@ int load_layer(vbx_ctx* c, int layer, const char* path, uint64_t* n_loaded) {
         // getGridIndexFromOriginPoint<BlockIndex>(origin, block_size_inv), core/common.h:171-177
         for (int a = 0; a < 3; ++a) idx.push_back((int32_t)std::round((float)bm.origin[a] * block_size_inv));
         words.insert(words.end(), bm.words.begin(), bm.words.end());
+        has_data.push_back(bm.has_data ? 1 : 0);
       }
       r.p += bsize;
     }
     if (compatible) {
       layer_found = true;
-      const uint64_t m = idx.size() / 3;
-      // kReplace: a block listed twice keeps the last payload, like block_map_[index] = block
+      uint64_t m = idx.size() / 3;
+      // kReplace: a block listed twice keeps the LAST payload, like block_map_[index] = block
+      // (io/layer_io_inl.h:71-73).  One upload scatters all blocks concurrently, so earlier duplicates are
+      // dropped here, on the host.
+      {
+        std::unordered_map<uint64_t, uint64_t> last;
+        for (uint64_t b = 0; b < m; ++b) last[pack3(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2])] = b;
+        if (last.size() != m) {
+          uint64_t w = 0;
+          for (uint64_t b = 0; b < m; ++b) {
+            if (last[pack3(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2])] != b) continue;
+            if (w != b) {
+              std::copy(idx.begin() + 3 * b, idx.begin() + 3 * b + 3, idx.begin() + 3 * w);
+              std::copy(words.begin() + b * wpb, words.begin() + (b + 1) * wpb, words.begin() + w * wpb);
+              has_data[w] = has_data[b];
+            }
+            ++w;
+          }
+          m = w;
+        }
+      }
       std::vector<uint8_t> upd(m, (uint8_t)7);  // updated().set(), core/layer_inl.h:227
       if (m) {
         if (int rc = upload_blocks(c, layer, idx.data(), m, words.data(), upd.data(), 1)) return rc;
+      }
+      std::unordered_set<uint64_t>& hd = c->has_data_keys[layer == VBX_LAYER_ESDF ? 1 : 0];
+      for (uint64_t b = 0; b < m; ++b) {
+        const uint64_t key = pack3(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2]);
+        if (has_data[b]) {
+          hd.insert(key);
+        } else {
+          hd.erase(key);
+        }
       }
       *n_loaded = m;
     }
