@@ -6,7 +6,7 @@ library built by oracle/Makefile (oracle/_ref/libvbx_ref.so, vbo_mc_tables) and 
 64-bit word per case, nibble k = k-th edge index of the row, 0xF = end of row.
 tests/test_mesh_cpu.py pins the committed header to the reference's table.
 
-    python scripts/gen_mc_tables.py
+    python oracle/gen_mc_tables.py
 """
 import ctypes as C
 import os
@@ -40,7 +40,7 @@ def main():
         n = row.index(-1)
         assert n % 3 == 0 and n <= 15 and all(v == -1 for v in row[n:]) and all(0 <= v < 12 for v in row[:n])
     with open(OUT, "w") as f:
-        f.write("// GENERATED by scripts/gen_mc_tables.py -- do not edit.\n"
+        f.write("// GENERATED (gen_mc_tables.py, kept with the test infrastructure) -- do not edit.\n"
                 "// Marching-cubes case table in voxblox's corner / edge numbering (MarchingCubes::kTriangleTable,\n"
                 "// kEdgeIndexPairs; voxblox/src/mesh/marching_cubes.cc:33-293), packed: one 64-bit word per case,\n"
                 "// nibble k = k-th edge index of the row, 0xF = end of row.  Pinned to the reference's table by\n"

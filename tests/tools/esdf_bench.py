@@ -1,7 +1,7 @@
 """C4: MergedTsdfIntegrator + EsdfIntegrator::updateFromTsdfLayer(true) after every scan, 640x480,
 0.05 m voxels; device time per ESDF update next to the reference's on the host."""
 import os, sys, json, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import voxblox_b200 as vb
 from oracle import pyoracle as po

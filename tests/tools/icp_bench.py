@@ -2,7 +2,7 @@
 per call on the GPU (host cloud, and cloud already on the device) for num_threads = 1, 8, 32, next to the
 reference's own ICP on the host (one thread: its deterministic setting)."""
 import os, sys, json, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import voxblox_b200 as vb
 from oracle import pyoracle as po

@@ -1,7 +1,7 @@
 """C5: MergedTsdfIntegrator on 2048x128 spinning-LiDAR scans, 0.05 m voxels, const weight,
 max_ray_length 10 m.  Single GPU, or ray-range sharded when launched under torchrun."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import voxblox_b200 as vb
 from voxblox_b200 import scenes, sharded

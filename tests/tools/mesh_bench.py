@@ -4,7 +4,7 @@
   (b) one C5 LiDAR map (~730+ blocks at 0.05 m): all blocks in one call
 Prints one JSON line."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import voxblox_b200 as vb
 from voxblox_b200 import scenes

@@ -1,4 +1,4 @@
-// GENERATED by scripts/gen_mc_tables.py -- do not edit.
+// GENERATED (gen_mc_tables.py, kept with the test infrastructure) -- do not edit.
 // Marching-cubes case table in voxblox's corner / edge numbering (MarchingCubes::kTriangleTable,
 // kEdgeIndexPairs; voxblox/src/mesh/marching_cubes.cc:33-293), packed: one 64-bit word per case,
 // nibble k = k-th edge index of the row, 0xF = end of row.  Pinned to the reference's table by
