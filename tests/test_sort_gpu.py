@@ -46,6 +46,19 @@ def test_radix_sort_is_a_stable_sort(ctx, dtype, bits, n):
     assert (perm == want).all()
 
 
+def test_radix_sort_more_tiles_than_thread_blocks(ctx):
+    """1024 tiles on a grid of at most two thread blocks per SM: every block takes several tickets per pass and
+    waits for the other blocks' tiles between the passes (the whole sort is one launch)."""
+    n = (1 << 22) - 5
+    rng = np.random.default_rng(11)
+    keys = rng.integers(0, (1 << 22) - 1, size=n, dtype=np.uint32)
+    keys[: n // 4] &= np.uint32(0x3FF)
+    got_k, perm = _sort(ctx, keys, 32)
+    want = np.argsort(keys, kind="stable").astype(np.uint32)
+    assert (got_k == keys[want]).all()
+    assert (perm == want).all()
+
+
 def test_radix_sort_skips_uniform_digits(ctx):
     # keys that only differ in bits 8..15: three of the four passes are identity permutations
     rng = np.random.default_rng(7)

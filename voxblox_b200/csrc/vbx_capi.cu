@@ -70,6 +70,7 @@ void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S) {
   c->counters[0] = h.n_rays;
   c->counters[1] = h.n_clear_rays;
   c->counters[2] = h.total_found;
+  if (h.total_found) c->record_hint = h.total_found;
   c->counters[3] = h.n_voxels;
   c->counters[4] = h.n_touched;
   c->counters[5] = h.n_new;

@@ -155,6 +155,7 @@ struct vbx_ctx {
   // scratch
   uint32_t max_points = 0;
   uint64_t max_updates = 0;
+  uint64_t record_hint = 1u << 20;  // update records of the most recent scan whose count reached the host: sizes the record sort's grid
   float* d_xyz = nullptr;
   uint8_t* d_rgba = nullptr;
   uint64_t* pkeys[2] = {nullptr, nullptr};

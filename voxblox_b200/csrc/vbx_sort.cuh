@@ -1,7 +1,7 @@
 // Hand-written device primitives for the integration pipeline: a stable LSD radix sort of
 // (key, value) pairs whose element count lives in DEVICE memory, and an exclusive prefix sum.
 //
-// Both are single-pass "chained scan" designs (one kernel per radix pass, one kernel for the
+// Both are single-pass "chained scan" designs (ONE kernel for the whole sort, one kernel for the
 // scan): a tile publishes its local aggregate, looks back over its predecessors' status words
 // until it meets an inclusive prefix, publishes its own inclusive prefix and scatters.  Tiles are
 // handed out through an atomic ticket, so every predecessor of a running tile is itself running
@@ -31,15 +31,26 @@ struct SortPlan {  // device resident; zeroed by the host before every sort
   uint32_t n;
   uint32_t n_tiles;
   uint32_t final_buf;                 // 0: sorted data is in buffer A (the input), 1: in buffer B
-  uint32_t done_blocks;
+  uint32_t hist_ticket;               // histogram phase: tiles handed out / tiles finished
+  uint32_t hist_done;
+  uint32_t plan_ready;                // set (after a fence) by the block that finished the last histogram tile
   uint32_t active[kMaxPasses];
   uint32_t src_buf[kMaxPasses];
-  uint32_t tile_counter[kMaxPasses];
+  uint32_t tile_counter[kMaxPasses];  // radix passes: tiles handed out / tiles scattered
+  uint32_t tiles_done[kMaxPasses];
   uint32_t hist[kMaxPasses][kRadix];  // global digit histograms
 };
 
 __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+// thread 0 of the block waits until *p reaches `want`; every thread returns with the writers' data visible
+__device__ __forceinline__ void block_wait_for(const uint32_t* p, uint32_t want) {
+  if (threadIdx.x == 0) {
+    while (ld_status(p) < want) __nanosleep(40);
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 // exclusive scan of one value per thread over a 256-thread block; returns the exclusive prefix
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* warp_sums /* [8] shared */) {
@@ -61,161 +72,201 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
   return base + inc - v;
 }
 
-// Kernel 1: digit histograms of every pass in one read of the keys, status words of the used
-// tiles cleared, and (last block) the plan: which passes are needed, which buffer feeds each.
+// The whole sort in ONE launch: digit histograms of every pass (one read of the keys), the plan
+// (which passes are needed, which buffer feeds each), the radix passes, and the final copy back
+// into buffer A for callers that want the result there.  Phases are separated by counters in
+// device memory instead of kernel boundaries.  That is deadlock free for any grid size because
+// ALL work is handed out by ticket: a block only ever waits for tiles whose tickets were taken by
+// blocks that are already running (look-back inside a pass, "all tiles of the previous phase
+// done" between phases); a block that is scheduled late finds the tickets gone and walks through.
+// Data written by one phase is read by the next on other SMs: loads go through L2 (__ldcg), the
+// writers fence before they count themselves done.
+// Stable: tiles, warps inside a tile and items inside a warp are all ranked in element order.
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
-k_sort_prepare(const KeyT* __restrict__ keys, const unsigned long long* d_n, uint32_t n_fixed, int passes,
-               const uint32_t* d_key_bits, SortPlan* plan, uint32_t* status, uint32_t tiles_cap) {
-  // the number of key bits in use may be known on the device only: passes beyond them are not even histogrammed
-  if (d_key_bits) passes = min(passes, (int)((*d_key_bits + 7u) / 8u));
-  __shared__ uint32_t hist[kMaxPasses][kRadix];
-  __shared__ uint32_t is_last;
-  const uint32_t n = d_n ? (uint32_t)min(*d_n, (unsigned long long)tiles_cap * kSortTile) : n_fixed;
-  const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
-  for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
-  __syncthreads();
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    for (int p = 0; p < passes; ++p) status[((size_t)p * tiles_cap + tile) * kRadix + threadIdx.x] = 0;
-    const uint32_t base = tile * kSortTile;
-#pragma unroll 4
-    for (int j = 0; j < kSortItems; ++j) {
-      const uint32_t e = base + j * kSortThreads + threadIdx.x;
-      if (e < n) {
-        const KeyT k = keys[e];
-        for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(uint32_t)(k >> (8 * p)) & 0xffu], 1u);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) {
-    const uint32_t v = (&hist[0][0])[i];
-    if (v) atomicAdd(&plan->hist[0][0] + i, v);
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(&plan->done_blocks, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // a pass whose digit is identical for all keys is the identity permutation: skip it
-  __shared__ uint32_t uniform[kMaxPasses];
-  if (threadIdx.x < kMaxPasses) uniform[threadIdx.x] = 0;
-  __syncthreads();
-  for (int p = 0; p < passes; ++p) {
-    if (ld_status(&plan->hist[p][threadIdx.x]) == n) uniform[p] = 1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t buf = 0;
-    for (int p = 0; p < kMaxPasses; ++p) {  // (passes beyond the bits in use stay inactive)
-      const uint32_t act = (p < passes && n > 1 && !uniform[p]) ? 1u : 0u;
-      plan->active[p] = act;
-      plan->src_buf[p] = buf;
-      if (act) buf ^= 1u;
-    }
-    plan->final_buf = buf;
-    plan->n = n;
-    plan->n_tiles = n_tiles;
-  }
-}
-
-// Kernel 2: one radix pass.  Stable: tiles, warps inside a tile and items inside a warp are all
-// ranked in element order.
-template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
-k_sort_pass(int pass, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, SortPlan* plan,
-            uint32_t* status_all, uint32_t tiles_cap) {
-  if (!plan->active[pass]) return;
+__global__ void __launch_bounds__(kSortThreads, 2)
+k_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, const unsigned long long* d_n, uint32_t n_fixed,
+       int passes, const uint32_t* d_key_bits, SortPlan* plan, uint32_t* status_all, uint32_t tiles_cap, int result_in_a) {
   __shared__ uint32_t digit_base[kRadix];             // global exclusive prefix of the digit counts
-  __shared__ uint32_t warp_hist[kSortWarps][kRadix];  // per-warp digit counts -> exclusive warp offsets
+  __shared__ uint32_t warp_hist[kSortWarps][kRadix];  // phase 1: digit counts of all passes; passes: per-warp counts
   __shared__ uint32_t tile_excl[kRadix];
   __shared__ uint32_t warp_sums[kSortWarps];
-  __shared__ uint32_t cur_tile;
-  const uint32_t n = plan->n, n_tiles = plan->n_tiles;
-  const bool from_a = plan->src_buf[pass] == 0;
-  const KeyT* src_k = from_a ? keys_a : keys_b;
-  const uint32_t* src_v = from_a ? vals_a : vals_b;
-  KeyT* dst_k = from_a ? keys_b : keys_a;
-  uint32_t* dst_v = from_a ? vals_b : vals_a;
-  uint32_t* status = status_all + (size_t)pass * tiles_cap * kRadix;
+  __shared__ uint32_t cur_tile, s_flag;
+  static_assert(kSortWarps == kMaxPasses, "the histogram phase reuses warp_hist as hist[pass][digit]");
+  // the number of key bits in use may be known on the device only: passes beyond them are not even histogrammed
+  if (d_key_bits) passes = min(passes, (int)((*d_key_bits + 7u) / 8u));
+  const uint32_t n = d_n ? (uint32_t)min(*d_n, (unsigned long long)tiles_cap * kSortTile) : n_fixed;
+  const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
+  if (n_tiles == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      plan->n = 0;
+      plan->n_tiles = 0;
+      plan->final_buf = 0;
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+
+  // ---- phase 1: histograms (ticketed tiles), status words of the used tiles cleared
   {
-    const uint32_t h = plan->hist[pass][threadIdx.x];
-    const uint32_t ex = block_exclusive_scan_256(h, warp_sums);
-    digit_base[threadIdx.x] = ex;
+    uint32_t(*hist)[kRadix] = warp_hist;
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
+    uint32_t mine = 0;
+    while (true) {
+      __syncthreads();
+      if (threadIdx.x == 0) cur_tile = atomicAdd(&plan->hist_ticket, 1u);
+      __syncthreads();
+      const uint32_t tile = cur_tile;
+      if (tile >= n_tiles) break;
+      ++mine;
+      for (int p = 0; p < passes; ++p) status_all[((size_t)p * tiles_cap + tile) * kRadix + threadIdx.x] = 0;
+      const uint32_t base = tile * kSortTile;
+#pragma unroll 4
+      for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t e = base + j * kSortThreads + threadIdx.x;
+        if (e < n) {
+          const KeyT k = keys_a[e];
+          for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(uint32_t)(k >> (8 * p)) & 0xffu], 1u);
+        }
+      }
+    }
+    if (mine) {  // (uniform over the block)
+      for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) {
+        const uint32_t v = (&hist[0][0])[i];
+        if (v) atomicAdd(&plan->hist[0][0] + i, v);
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_flag = (atomicAdd(&plan->hist_done, mine) + mine == n_tiles) ? 1u : 0u;
+      __syncthreads();
+      if (s_flag) {
+        // this block finished the last tile: it writes the plan.  A pass whose digit is identical for
+        // all keys is the identity permutation and is skipped.
+        __threadfence();
+        __shared__ uint32_t uniform[kMaxPasses];
+        if (threadIdx.x < kMaxPasses) uniform[threadIdx.x] = 0;
+        __syncthreads();
+        for (int p = 0; p < passes; ++p) {
+          if (ld_status(&plan->hist[p][threadIdx.x]) == n) uniform[p] = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          uint32_t buf = 0;
+          for (int p = 0; p < kMaxPasses; ++p) {  // (passes beyond the bits in use stay inactive)
+            const uint32_t act = (p < passes && n > 1 && !uniform[p]) ? 1u : 0u;
+            plan->active[p] = act;
+            plan->src_buf[p] = buf;
+            if (act) buf ^= 1u;
+          }
+          plan->final_buf = buf;
+          plan->n = n;
+          plan->n_tiles = n_tiles;
+          __threadfence();
+          st_status(&plan->plan_ready, 1u);
+        }
+      }
+    }
+    block_wait_for(&plan->plan_ready, 1u);
   }
-  while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) cur_tile = atomicAdd(&plan->tile_counter[pass], 1u);
-    for (int w = 0; w < kSortWarps; ++w) warp_hist[w][threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t tile = cur_tile;
-    if (tile >= n_tiles) break;
-    const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
-    KeyT key[kSortItems];
-    uint32_t val[kSortItems];
-    uint32_t rank[kSortItems];
-#pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      const uint32_t e = base + j * 32 + lane;
-      key[j] = e < n ? src_k[e] : (KeyT)0;
-      val[j] = e < n ? src_v[e] : 0u;
+
+  // ---- phase 2: the radix passes
+  for (int pass = 0; pass < passes; ++pass) {
+    if (!ld_status(&plan->active[pass])) continue;
+    const bool from_a = ld_status(&plan->src_buf[pass]) == 0;
+    const KeyT* src_k = from_a ? keys_a : keys_b;
+    const uint32_t* src_v = from_a ? vals_a : vals_b;
+    KeyT* dst_k = from_a ? keys_b : keys_a;
+    uint32_t* dst_v = from_a ? vals_b : vals_a;
+    uint32_t* status = status_all + (size_t)pass * tiles_cap * kRadix;
+    {
+      const uint32_t h = ld_status(&plan->hist[pass][threadIdx.x]);
+      const uint32_t ex = block_exclusive_scan_256(h, warp_sums);
+      digit_base[threadIdx.x] = ex;
     }
+    while (true) {
+      __syncthreads();
+      if (threadIdx.x == 0) cur_tile = atomicAdd(&plan->tile_counter[pass], 1u);
+      for (int w = 0; w < kSortWarps; ++w) warp_hist[w][threadIdx.x] = 0;
+      __syncthreads();
+      const uint32_t tile = cur_tile;
+      if (tile >= n_tiles) break;
+      const uint32_t base = tile * kSortTile + warp * (32 * kSortItems);
+      KeyT key[kSortItems];
+      uint32_t val[kSortItems];
+      uint32_t rank[kSortItems];
 #pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      const uint32_t e = base + j * 32 + lane;
-      const uint32_t d = e < n ? ((uint32_t)(key[j] >> (8 * pass)) & 0xffu) : 0xffffffffu;
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
-      const int leader = __ffs(peers) - 1;
-      uint32_t before = 0;
-      if (lane == leader && d != 0xffffffffu) {
-        before = warp_hist[warp][d];
-        warp_hist[warp][d] = before + (uint32_t)__popc(peers);
+      for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t e = base + j * 32 + lane;
+        key[j] = e < n ? __ldcg(&src_k[e]) : (KeyT)0;
+        val[j] = e < n ? __ldcg(&src_v[e]) : 0u;
       }
-      before = __shfl_sync(0xffffffffu, before, leader);
-      rank[j] = before + (uint32_t)__popc(peers & lt_mask);
-      __syncwarp();
-    }
-    __syncthreads();
-    // thread d: exclusive offsets of digit d over the warps of this tile, and the tile total
-    uint32_t total = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t c = warp_hist[w][threadIdx.x];
-      warp_hist[w][threadIdx.x] = total;
-      total += c;
-    }
-    // chained scan over the tiles, one digit per thread
-    uint32_t* mine = status + (size_t)tile * kRadix + threadIdx.x;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      st_status(mine, kFlagPrefix | total);
-    } else {
-      st_status(mine, kFlagAggregate | total);
-      for (uint32_t t = tile; t-- > 0;) {
-        const uint32_t* theirs = status + (size_t)t * kRadix + threadIdx.x;
-        uint32_t v;
-        do {
-          v = ld_status(theirs);
-        } while ((v & ~kValueMask) == 0u);
-        excl += v & kValueMask;
-        if (v & kFlagPrefix) break;
+      for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t e = base + j * 32 + lane;
+        const uint32_t d = e < n ? ((uint32_t)(key[j] >> (8 * pass)) & 0xffu) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if (lane == leader && d != 0xffffffffu) {
+          before = warp_hist[warp][d];
+          warp_hist[warp][d] = before + (uint32_t)__popc(peers);
+        }
+        before = __shfl_sync(0xffffffffu, before, leader);
+        rank[j] = before + (uint32_t)__popc(peers & lt_mask);
+        __syncwarp();
       }
-      st_status(mine, kFlagPrefix | (excl + total));
-    }
-    tile_excl[threadIdx.x] = excl;
-    __syncthreads();
+      __syncthreads();
+      // thread d: exclusive offsets of digit d over the warps of this tile, and the tile total
+      uint32_t total = 0;
 #pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      const uint32_t e = base + j * 32 + lane;
-      if (e < n) {
-        const uint32_t d = (uint32_t)(key[j] >> (8 * pass)) & 0xffu;
-        const uint32_t pos = digit_base[d] + tile_excl[d] + warp_hist[warp][d] + rank[j];
-        dst_k[pos] = key[j];
-        dst_v[pos] = val[j];
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = warp_hist[w][threadIdx.x];
+        warp_hist[w][threadIdx.x] = total;
+        total += c;
       }
+      // chained scan over the tiles, one digit per thread
+      uint32_t* mine = status + (size_t)tile * kRadix + threadIdx.x;
+      uint32_t excl = 0;
+      if (tile == 0) {
+        st_status(mine, kFlagPrefix | total);
+      } else {
+        st_status(mine, kFlagAggregate | total);
+        for (uint32_t t = tile; t-- > 0;) {
+          const uint32_t* theirs = status + (size_t)t * kRadix + threadIdx.x;
+          uint32_t v;
+          do {
+            v = ld_status(theirs);
+          } while ((v & ~kValueMask) == 0u);
+          excl += v & kValueMask;
+          if (v & kFlagPrefix) break;
+        }
+        st_status(mine, kFlagPrefix | (excl + total));
+      }
+      tile_excl[threadIdx.x] = excl;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t e = base + j * 32 + lane;
+        if (e < n) {
+          const uint32_t d = (uint32_t)(key[j] >> (8 * pass)) & 0xffu;
+          const uint32_t pos = digit_base[d] + tile_excl[d] + warp_hist[warp][d] + rank[j];
+          dst_k[pos] = key[j];
+          dst_v[pos] = val[j];
+        }
+      }
+      // this tile is scattered: visible to every SM before it is counted
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(&plan->tiles_done[pass], 1u);
+    }
+    block_wait_for(&plan->tiles_done[pass], n_tiles);
+  }
+
+  // ---- phase 3: callers that read buffer A get the result there (nobody waits for this phase)
+  if (result_in_a && ld_status(&plan->final_buf) != 0) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      keys_a[i] = __ldcg(&keys_b[i]);
+      vals_a[i] = __ldcg(&vals_b[i]);
     }
   }
 }

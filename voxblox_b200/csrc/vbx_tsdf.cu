@@ -1707,8 +1707,96 @@ __global__ void k_apply_long(ScanParams P, Tables tab, RecordView rv, const floa
           w_n[g] = in_n[g] ? lr.rec_w[j] : 0.f;
         }
       }
+      // The common long run -- free space far in front of any surface, the voxel already at +T -- is decided
+      // for all kG chunks at once: ONE exact in-order weight chain over the step's records, then every
+      // lane checks that its updates map +T onto +T, one vote.  (Same arithmetic as the per-chunk path
+      // below, which remains for everything else and redoes the step from the unchanged voxel if a
+      // check fails.)
+      bool step_done = false;
+      {
+        bool ff = true;
+        float wl[kG];
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+          ff = ff && (!in_c[g] || sdf_c[g] >= T);
+          wl[g] = in_c[g] ? w_c[g] : 0.f;
+        }
+        if (__all_sync(0xffffffffu, ff) && v.distance == T) {
+          float ws = (wl[0] + wl[1]) + (wl[2] + wl[3]);  // any-order sum, used only as a bound
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+          const bool saturated = v.weight == P.up.max_weight && P.up.max_weight >= VBX_EPS;
+          const bool no_clamp = v.weight >= VBX_EPS && (v.weight + ws) * 1.0001f < P.up.max_weight;
+          float mb[kG];
+          float w_end = v.weight;
+          bool have = true;
+          if (saturated) {
+            // W + w >= max_weight for every w >= 0: the clamp returns max_weight at every step
+#pragma unroll
+            for (int g = 0; g < kG; ++g) mb[g] = v.weight;
+          } else if (no_clamp) {
+            // neither the 1e-6 guard nor the max_weight clamp can fire: the chain is plain in-order addition
+            bool ints = v.weight == truncf(v.weight) && (v.weight + ws) < 16777216.0f;
+#pragma unroll
+            for (int g = 0; g < kG; ++g) ints = ints && wl[g] == truncf(wl[g]);
+            if (__all_sync(0xffffffffu, ints)) {
+              // integer-valued weights (use_const_weight: a bundle's weight is its point count) on an
+              // integer-valued W, everything below 2^24: every partial sum is exact, so any order gives
+              // the in-order chain -- a warp scan per chunk
+              float base = v.weight;
+#pragma unroll
+              for (int g = 0; g < kG; ++g) {
+                float inc = wl[g];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const float t = __shfl_up_sync(0xffffffffu, inc, o);
+                  if (lane >= o) inc += t;
+                }
+                mb[g] = base + (inc - wl[g]);
+                base = base + __shfl_sync(0xffffffffu, inc, 31);
+              }
+              w_end = base;
+            } else {
+              float base = v.weight;
+#pragma unroll
+              for (int g = 0; g < kG; ++g) {
+                float before = base;
+#pragma unroll
+                for (int k = 0; k < 31; ++k) {
+                  const float wk = __shfl_sync(0xffffffffu, wl[g], k);
+                  if (k < lane) before = fadd(before, wk);
+                }
+                mb[g] = before;
+                base = __shfl_sync(0xffffffffu, fadd(before, wl[g]), 31);
+              }
+              w_end = base;
+            }
+          } else {
+            have = false;
+          }
+          if (have) {
+            bool keeps_T = true;
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+              if (in_c[g]) {
+                const float nw = fadd(mb[g], w_c[g]);
+                if (!(nw < VBX_EPS)) {
+                  const float ns = fdiv(fadd(fmul(sdf_c[g], w_c[g]), fmul(T, mb[g])), nw);
+                  const float clamped = (ns > 0.0f) ? ((ns < T) ? ns : T) : ((-T < ns) ? ns : -T);
+                  keeps_T = keeps_T && (clamped == T);
+                }
+              }
+            }
+            if (__all_sync(0xffffffffu, keeps_T)) {
+              v.weight = w_end;
+              step_done = true;
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int g = 0; g < kG; ++g) {
+        if (step_done) break;
         const bool in = in_c[g];
         const float sdf = sdf_c[g], w = w_c[g];
         const int cnt = __popc(__ballot_sync(0xffffffffu, in));
@@ -1858,36 +1946,25 @@ struct Marks {
 };
 }  // namespace
 
-// The engine's own stable radix sort (vbx_sort.cuh).  n lives on the device (d_n) or is n_fixed.
+// The engine's own stable radix sort (vbx_sort.cuh): one launch.  n lives on the device (d_n) or is n_fixed;
+// n_hint sizes the grid (tiles are handed out by ticket, so any grid sorts any n).  result_in_a: the sorted
+// pairs end in buffer A whatever the number of passes (otherwise SortPlan::final_buf says where they are).
 template <typename KeyT>
 static int own_sort(vbx_ctx* c, int which, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                    const unsigned long long* d_n, uint32_t n_fixed, int key_bits, uint64_t* launches,
-                    const uint32_t* d_key_bits = nullptr) {
+                    const unsigned long long* d_n, uint32_t n_fixed, uint64_t n_hint, int key_bits, bool result_in_a,
+                    uint64_t* launches, const uint32_t* d_key_bits = nullptr) {
   cudaStream_t s = c->stream;
   const int passes = std::min(kMaxPasses, (key_bits + 7) / 8);
   SortPlan* plan = c->sort_plan[which];
   uint32_t* status = c->sort_status[which];
   const uint32_t tiles_cap = c->sort_tiles_cap[which];
   VBX_CUDA(c, cudaMemsetAsync(plan, 0, sizeof(SortPlan), s));
-  const unsigned int grid = std::min<uint32_t>(tiles_cap, 148 * 4);
-  k_sort_prepare<KeyT><<<grid, kSortThreads, 0, s>>>(keys_a, d_n, n_fixed, passes, d_key_bits, plan, status, tiles_cap);
-  for (int p = 0; p < passes; ++p) {
-    k_sort_pass<KeyT><<<grid, kSortThreads, 0, s>>>(p, keys_a, vals_a, keys_b, vals_b, plan, status, tiles_cap);
-  }
-  *launches += 1 + passes;
+  const uint64_t tiles_hint = std::max<uint64_t>(1, (n_hint + kSortTile - 1) / kSortTile);
+  const unsigned int grid = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(tiles_cap, tiles_hint), (uint64_t)c->grid_sms * 2);
+  k_sort<KeyT><<<grid, kSortThreads, 0, s>>>(keys_a, vals_a, keys_b, vals_b, d_n, n_fixed, passes, d_key_bits, plan, status,
+                                              tiles_cap, result_in_a ? 1 : 0);
+  *launches += 1;
   return VBX_OK;
-}
-
-// after a sort whose consumers want the result in buffer A
-template <typename KeyT>
-__global__ void k_sort_to_a(KeyT* keys_a, uint32_t* vals_a, const KeyT* keys_b, const uint32_t* vals_b,
-                            const SortPlan* plan) {
-  if (plan->final_buf == 0) return;
-  const uint32_t n = plan->n;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    keys_a[i] = keys_b[i];
-    vals_a[i] = vals_b[i];
-  }
 }
 
 // k_order_prefix, k_order_heads, k_bundle_order on stream `so` (see the kernels).
@@ -1927,11 +2004,10 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     k_point_keys<KeyT><<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, k0, c->pvals[0], c->d_state);
     mk.mark(0);
     // the bits in use are known on the device only (ScanState::key_bits): passes beyond them exit at once
-    if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, 8 * (int)sizeof(KeyT), launches,
+    if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, n, 8 * (int)sizeof(KeyT), true, launches,
                                 &c->d_state->key_bits)) {
       return rc;
     }
-    k_sort_to_a<KeyT><<<148, 256, 0, s>>>(k0, c->pvals[0], k1, c->pvals[1], c->sort_plan[0]);
     keys = k0;
     vals = c->pvals[0];
     mk.mark(1);
@@ -1951,7 +2027,7 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
     k_merge<KeyT><<<c->grid_sms * 4, 192, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
                                            c->ray_c, c->cnt, c->d_state);
     mk.mark(8);
-    *launches += 9;
+    *launches += 8;
     if (!P.single_walk) {
       // the bundle count is only known on the device: launch for the worst case (every
       // point its own bundle); surplus threads exit on the first load
@@ -2001,8 +2077,8 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
       s = c->sort_stream;
       c->stream = s;
     }
-    if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
-                                     &c->d_state->total_updates, 0, key_bits, launches, &c->d_state->rec_key_bits)) {
+    if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1], &c->d_state->total_updates,
+                                     0, c->record_hint, key_bits, false, launches, &c->d_state->rec_key_bits)) {
       return rc;
     }
     rv.keys[0] = c->ckeys[0];
@@ -2176,14 +2252,13 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   if (cfg.integration_order_mode == 1) {
     // SortedThreadSafeIndex: ascending |p|^2 (stable here; std::sort leaves ties unspecified)
     k_sqnorm_keys<<<grid_for(n, TB), TB, 0, s>>>(n, d_xyz, c->pkeys[0], c->pvals[0]);
-    if (int rc = own_sort<uint64_t>(c, 0, c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], nullptr, n, 64, &launches)) {
+    if (int rc = own_sort<uint64_t>(c, 0, c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], nullptr, n, n, 64, true, &launches)) {
       return rc;
     }
-    k_sort_to_a<uint64_t><<<148, 256, 0, s>>>(c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], c->sort_plan[0]);
     VBX_CUDA(c, cudaMemcpyAsync(c->order, c->pvals[0], n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     k_invert_order<<<grid_for(n, TB), TB, 0, s>>>(n, c->order, c->order_inv);
     order = c->order;
-    launches += 3;
+    launches += 2;
   }
 
   uint32_t chunk_blocks_before = 0;
@@ -2225,6 +2300,7 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   c->counters[0] = c->h_state->n_rays;
   c->counters[1] = c->h_state->n_clear_rays;
   c->counters[2] = K;
+  if (K) c->record_hint = K;
   c->counters[3] = c->h_state->n_voxels;
   c->counters[4] = n_touched;
   c->counters[5] = chunked ? (uint64_t)(c->n_blocks - chunk_blocks_before) : (uint64_t)c->h_state->n_new;
@@ -2429,21 +2505,19 @@ int debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int key_
     const unsigned long long nn = n;
     VBX_CUDA(c, cudaMemcpyAsync(&c->d_state->total_updates, &nn, sizeof(nn), cudaMemcpyHostToDevice, s));
     if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1],
-                                     &c->d_state->total_updates, 0, key_bits, &launches)) {
+                                     &c->d_state->total_updates, 0, n, key_bits, true, &launches)) {
       return rc;
     }
-    k_sort_to_a<uint32_t><<<148, 256, 0, s>>>(c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1], c->sort_plan[1]);
     VBX_CUDA(c, cudaMemcpyAsync(keys_out, c->ckeys[0], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     VBX_CUDA(c, cudaMemcpyAsync(vals_out, c->cvals[0], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   } else if (key_bytes == 8) {
     if (n > c->max_points) return fail(c, VBX_E_CAPACITY, "debug_sort: n > max_points_per_scan");
     VBX_CUDA(c, cudaMemcpyAsync(c->pkeys[0], keys, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     k_iota<<<148, 256, 0, s>>>(c->pvals[0], n);
-    if (int rc = own_sort<uint64_t>(c, 0, c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], nullptr, n, key_bits,
+    if (int rc = own_sort<uint64_t>(c, 0, c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], nullptr, n, n, key_bits, true,
                                      &launches)) {
       return rc;
     }
-    k_sort_to_a<uint64_t><<<148, 256, 0, s>>>(c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], c->sort_plan[0]);
     VBX_CUDA(c, cudaMemcpyAsync(keys_out, c->pkeys[0], (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     VBX_CUDA(c, cudaMemcpyAsync(vals_out, c->pvals[0], (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   } else {
