@@ -345,6 +345,12 @@ VBX_API int vbx_host_copy_ms(vbx_ctx* ctx, const void* src, size_t bytes, float*
 VBX_API int vbx_debug_sort(vbx_ctx* ctx, const void* keys, int key_bytes, uint32_t n, int key_bits, void* keys_out,
                    uint32_t* perm_out);
 VBX_API int vbx_debug_scan(vbx_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out);
+/* Diagnostic for the pipelined path (vbx_tsdf_integrate_async): with the environment variable
+ * VBX_ASYNC_TIMELINE set before the first asynchronous submission, the hand-off events keep timestamps.
+ * For each of the (at most cap_sets, 10 exist) hand-off sets: seq[k] = submission number of the last scan
+ * that used it, ms[5k .. 5k+4] = when its front half started / ended, its ray walk ended, its record sort
+ * ended and its apply ended, in ms since the pipeline was created (-1: not recorded).  Call after vbx_sync. */
+VBX_API int vbx_debug_async_timeline(vbx_ctx* ctx, uint64_t* seq, float* ms, int cap_sets);
 /* Test hook for the Merged integrator's bundle order (the iteration order of the reference's
  * unordered_map voxel_map, tsdf_integrator.cc:318-322, :436-456): element e is the e-th inserted key
  * with LongIndexHash hashes[e]; out[p] = the element at iteration position p.  force_global != 0 uses

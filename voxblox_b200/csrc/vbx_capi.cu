@@ -71,6 +71,7 @@ void harvest_async(vbx_ctx* c, vbx_ctx::ScratchSet& S) {
   c->counters[1] = h.n_clear_rays;
   c->counters[2] = h.total_found;
   if (h.total_found) c->record_hint = h.total_found;
+  if (S.kind == VBX_MERGED && !(h.error & kFatalErrors)) c->bundle_hint = std::max(h.n_rays, h.n_clear_rays);
   c->counters[3] = h.n_voxels;
   c->counters[4] = h.n_touched;
   c->counters[5] = h.n_new;
@@ -465,13 +466,21 @@ int ensure_async(vbx_ctx* c) {
     CK(dmalloc(&F.scan_status, (np + 1) / kScanTile + 4));
     if (int rc = alloc_order_scratch(c, &F.order_scratch, &F.big_list, &F.first_bits)) return rc;
   }
+  // diagnostic: with VBX_ASYNC_TIMELINE set the hand-off events keep timestamps (vbx_debug_async_timeline)
+  c->timeline = std::getenv("VBX_ASYNC_TIMELINE") != nullptr;
+  const unsigned int evf = c->timeline ? cudaEventDefault : cudaEventDisableTiming;
+  if (c->timeline) {
+    CK(cudaEventCreate(&c->timeline_ref));
+    CK(cudaEventRecord(c->timeline_ref, c->stream_main));
+  }
   for (int k = 0; k < vbx_ctx::kSets; ++k) {
     vbx_ctx::ScratchSet& S = c->set[k];
-    CK(cudaEventCreateWithFlags(&S.copy_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&S.front_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&S.walked, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&S.sorted, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&S.back_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.copy_done, evf));
+    CK(cudaEventCreateWithFlags(&S.front_done, evf));
+    CK(cudaEventCreateWithFlags(&S.walked, evf));
+    CK(cudaEventCreateWithFlags(&S.sorted, evf));
+    CK(cudaEventCreateWithFlags(&S.back_done, evf));
+    if (c->timeline) CK(cudaEventCreate(&S.front_start));
     if (k == 0) continue;
     CK(dmalloc(&S.ray_p, np));
     CK(dmalloc(&S.ray_a, np));
@@ -552,6 +561,7 @@ void vbx_destroy(vbx_ctx* c) {
     if (S.walked) cudaEventDestroy(S.walked);
     if (S.sorted) cudaEventDestroy(S.sorted);
     if (S.back_done) cudaEventDestroy(S.back_done);
+    if (S.front_start) cudaEventDestroy(S.front_start);
   }
   for (int l = 0; l < vbx_ctx::kLanes; ++l) {
     vbx_ctx::FrontLane& F = c->lane[l];
@@ -570,6 +580,7 @@ void vbx_destroy(vbx_ctx* c) {
     if (F.ev_join) cudaEventDestroy(F.ev_join);
     if (F.stream) cudaStreamDestroy(F.stream);
   }
+  if (c->timeline_ref) cudaEventDestroy(c->timeline_ref);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->tev0) cudaEventDestroy(c->tev0);
@@ -633,6 +644,25 @@ int vbx_debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int 
   VBX_CUDA(c, cudaSetDevice(c->device));
   VBX_DRAIN(c);
   return debug_sort(c, keys, key_bytes, n, key_bits, keys_out, vals_out);
+}
+
+int vbx_debug_async_timeline(vbx_ctx* c, uint64_t* seq, float* ms, int cap_sets) {
+  if (!c || !seq || !ms) return VBX_E_INVALID;
+  if (!c->async_ready || !c->timeline) return fail(c, VBX_E_STATE, "set VBX_ASYNC_TIMELINE before the first asynchronous submission");
+  for (int k = 0; k < vbx_ctx::kSets && k < cap_sets; ++k) {
+    vbx_ctx::ScratchSet& S = c->set[k];
+    seq[k] = S.seq;
+    cudaEvent_t ev[5] = {S.front_start, S.front_done, S.walked, S.sorted, S.back_done};
+    for (int j = 0; j < 5; ++j) {
+      float t = -1.f;
+      if (cudaEventSynchronize(ev[j]) != cudaSuccess || cudaEventElapsedTime(&t, c->timeline_ref, ev[j]) != cudaSuccess) {
+        t = -1.f;
+        cudaGetLastError();
+      }
+      ms[5 * k + j] = t;
+    }
+  }
+  return VBX_OK;
 }
 
 int vbx_debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {

@@ -155,6 +155,9 @@ struct vbx_ctx {
   // scratch
   uint32_t max_points = 0;
   uint64_t max_updates = 0;
+  bool timeline = false;            // VBX_ASYNC_TIMELINE: the hand-off events carry timestamps
+  cudaEvent_t timeline_ref = nullptr;
+  uint32_t bundle_hint = 0;         // bundles (the larger of the two maps) of the most recent Merged scan whose counters reached the host
   uint64_t record_hint = 1u << 20;  // update records of the most recent scan whose count reached the host: sizes the record sort's grid
   float* d_xyz = nullptr;
   uint8_t* d_rgba = nullptr;
@@ -226,6 +229,7 @@ struct vbx_ctx {
     vbx::SortPlan* sort_plan1 = nullptr;
     uint32_t* sort_status1 = nullptr;
     cudaEvent_t copy_done = nullptr, front_done = nullptr, walked = nullptr, sorted = nullptr, back_done = nullptr;
+    cudaEvent_t front_start = nullptr;  // only with VBX_ASYNC_TIMELINE (vbx_debug_async_timeline)
     bool in_flight = false;
     int kind = 0;
     uint64_t launches = 0;

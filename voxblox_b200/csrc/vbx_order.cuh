@@ -89,29 +89,33 @@ __device__ __forceinline__ uint32_t order_block_scan(uint32_t v, uint32_t* warp_
 // Result in tau_out[]; A, next, bkt, bhead are scratch.  `tag` (distinct per call, < 2^12) marks the
 // bucket heads written by this call, so the bucket array needs no clearing between calls:
 // bhead[j] = tag << 20 | element, anything with another tag reads as "empty" (elements < 2^20).
-__device__ inline void order_positions(const uint32_t* h, const uint32_t* tau, uint32_t* tau_out, uint32_t* next,
-                                       uint32_t* bkt, uint32_t* A, uint32_t* bhead, uint32_t m, uint32_t n, uint32_t tag,
-                                       uint32_t* warp_sums) {
+// IdxT: uint32_t, or uint16_t when m < 65535 and n <= 65535 (times, chain links, bucket numbers and the
+// suffix sums all fit 16 bits then): the tables of a few thousand bundles take half the shared memory.
+// h may live in shared or in global memory (it is read once per element and call).
+template <typename IdxT>
+__device__ inline void order_positions(const uint32_t* h, const IdxT* tau, IdxT* tau_out, IdxT* next, IdxT* bkt, IdxT* A,
+                                       uint32_t* bhead, uint32_t m, uint32_t n, uint32_t tag, uint32_t* warp_sums) {
+  constexpr uint32_t nil = (uint32_t)(IdxT)~(IdxT)0;
   const uint32_t tid = threadIdx.x;
   const uint32_t tg = tag << 20;
-  // chains: next[b] = the element that headed b's bucket before b (kOrderNil: none)
+  // chains: next[b] = the element that headed b's bucket before b (nil: none)
   for (uint32_t b = tid; b < m; b += kOrderThreads) {
     const uint32_t g = h[b] % n;
-    bkt[b] = g;
+    bkt[b] = (IdxT)g;
     const uint32_t old = atomicExch(&bhead[g], tg | b);
-    next[b] = (old >> 20) == tag ? (old & 0xfffffu) : kOrderNil;
+    next[b] = (old >> 20) == tag ? (IdxT)(old & 0xfffffu) : (IdxT)nil;
   }
   __syncthreads();
   // the group's creator (smallest time) publishes the group size at its creation time; every time in
   // [0, m) belongs to exactly one element, so A needs no clearing either
   for (uint32_t b = tid; b < m; b += kOrderThreads) {
     const uint32_t tb = tau[b];
-    uint32_t cmin = kOrderNil, size = 0;
-    for (uint32_t c = bhead[bkt[b]] & 0xfffffu; c != kOrderNil; c = next[c]) {
-      cmin = min(cmin, tau[c]);
+    uint32_t cmin = 0xffffffffu, size = 0;
+    for (uint32_t c = bhead[bkt[b]] & 0xfffffu; c != nil; c = next[c]) {
+      cmin = min(cmin, (uint32_t)tau[c]);
       ++size;
     }
-    A[tb] = cmin == tb ? size : 0u;
+    A[tb] = (IdxT)(cmin == tb ? size : 0u);
   }
   __syncthreads();
   // A[t] <- number of elements in groups created after time t (exclusive suffix sum): every thread owns
@@ -127,54 +131,62 @@ __device__ inline void order_positions(const uint32_t* h, const uint32_t* tau, u
     uint32_t run = order_block_scan(sum, warp_sums, &total);          // elements at times above my run
     for (uint32_t t = hi; t-- > lo;) {
       const uint32_t v = A[t];
-      A[t] = run;
+      A[t] = (IdxT)run;
       run += v;
     }
   }
   __syncthreads();
   for (uint32_t b = tid; b < m; b += kOrderThreads) {
     const uint32_t tb = tau[b];
-    uint32_t cmin = kOrderNil, later = 0;
-    for (uint32_t c = bhead[bkt[b]] & 0xfffffu; c != kOrderNil; c = next[c]) {
+    uint32_t cmin = 0xffffffffu, later = 0;
+    for (uint32_t c = bhead[bkt[b]] & 0xfffffu; c != nil; c = next[c]) {
       const uint32_t tc = tau[c];
       cmin = min(cmin, tc);
       later += tc > tb ? 1u : 0u;
     }
-    tau_out[b] = A[cmin] + later;
+    tau_out[b] = (IdxT)((uint32_t)A[cmin] + later);
   }
   __syncthreads();
 }
 
-// All rehash stages + the final listing for B elements already loaded into h[] (insertion order).
+// All rehash stages + the final listing for B elements with hashes h[] (insertion order).
 // On return pos[] (= one of tau / tau2, returned) holds every element's position in the iteration order.
-// bhead must not hold values with tags 1.. from an earlier run: the caller clears it once (or uses a
-// fresh shared-memory array and clears that).
-__device__ inline uint32_t* order_run(const RehashSchedule& rs, uint32_t B, const uint32_t* h, uint32_t* tau, uint32_t* tau2,
-                                      uint32_t* next, uint32_t* bkt, uint32_t* A, uint32_t* bhead, uint32_t n_final,
-                                      uint32_t* warp_sums) {
-  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) tau[e] = e;
+// bhead must not hold values with tags 1.. from an earlier run: it is cleared here (n_final entries).
+template <typename IdxT>
+__device__ inline IdxT* order_run(const RehashSchedule& rs, uint32_t B, const uint32_t* h, IdxT* tau, IdxT* tau2, IdxT* next,
+                                  IdxT* bkt, IdxT* A, uint32_t* bhead, uint32_t n_final, uint32_t* warp_sums) {
+  for (uint32_t e = threadIdx.x; e < B; e += kOrderThreads) tau[e] = (IdxT)e;
   for (uint32_t j = threadIdx.x; j < n_final; j += kOrderThreads) bhead[j] = 0u;  // tag 0 = never used
   __syncthreads();
   uint32_t n_cur = 1;
   uint32_t tag = 1;
-  uint32_t* cur = tau;
-  uint32_t* oth = tau2;
+  IdxT* cur = tau;
+  IdxT* oth = tau2;
   for (int k = 0; k < rs.count; ++k) {
     const uint32_t mk = rs.m[k];
     if (mk >= B) break;  // the map never reaches this size
     if (mk > 0) {
-      order_positions(h, cur, oth, next, bkt, A, bhead, mk, n_cur, tag++, warp_sums);
+      order_positions<IdxT>(h, cur, oth, next, bkt, A, bhead, mk, n_cur, tag++, warp_sums);
       // elements inserted after the rehash keep their insertion index as time
-      for (uint32_t e = mk + threadIdx.x; e < B; e += kOrderThreads) oth[e] = e;
+      for (uint32_t e = mk + threadIdx.x; e < B; e += kOrderThreads) oth[e] = (IdxT)e;
       __syncthreads();
-      uint32_t* t = cur;
+      IdxT* t = cur;
       cur = oth;
       oth = t;
     }
     n_cur = rs.n[k];
   }
-  order_positions(h, cur, oth, next, bkt, A, bhead, B, n_cur, tag, warp_sums);
+  order_positions<IdxT>(h, cur, oth, next, bkt, A, bhead, B, n_cur, tag, warp_sums);
   return oth;
+}
+
+// Shared-memory words the single-block form needs for B elements in n_final buckets: five 16-bit index
+// tables and the bucket heads (0xffffffff: too many elements for 16-bit tables -- such a map would not fit
+// one SM's shared memory with 32-bit tables either).  Host and device use the same formula.
+__host__ __device__ inline uint32_t order_smem_words_needed(uint32_t B, uint32_t n_final) {
+  if (B >= 65535u || n_final > 65535u) return 0xffffffffu;
+  const uint32_t pad = (B + 1u) & ~1u;  // (keeps every 16-bit table 4-byte aligned)
+  return 5u * pad / 2u + n_final;
 }
 #endif  // __CUDACC__
 

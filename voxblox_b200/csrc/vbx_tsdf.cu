@@ -439,7 +439,7 @@ k_bundle_order(RehashSchedule rs, OrderScratch g, uint32_t smem_words, uint32_t*
     uint32_t nf = 1;
     for (int k = 0; k < rs.count && rs.m[k] < B_of[mp]; ++k) nf = rs.n[k];
     n_of[mp] = nf;
-    if (6u * B_of[mp] + nf > smem_words) small = false;
+    if (order_smem_words_needed(B_of[mp], nf) > smem_words) small = false;
     // bucket heads pack the element into 20 bits; cap = max_points_per_scan
     if (B_of[mp] > g.cap || B_of[mp] > (1u << 20) || nf > g.bucket_cap) bad = true;
   }
@@ -456,15 +456,12 @@ k_bundle_order(RehashSchedule rs, OrderScratch g, uint32_t smem_words, uint32_t*
     const uint32_t* head_of = g.head_of + mp * g.cap;
     uint32_t *h = order_smem, *tau = h, *tau2 = h, *next = h, *bkt = h, *A = h, *bhead = h;
     if (small) {
-      tau = h + B;
-      tau2 = tau + B;
-      next = tau2 + B;
-      bkt = next + B;
-      A = bkt + B;
-      bhead = A + B;
-      for (uint32_t e = tid; e < B; e += kOrderThreads) h[e] = gh[e];
-      __syncthreads();
-      const uint32_t* pos = order_run(rs, B, h, tau, tau2, next, bkt, A, bhead, n_final, warp_sums);
+      // one block, 16-bit tables in shared memory (the hashes are read from global memory, once per stage)
+      const uint32_t pad = (B + 1u) & ~1u;
+      uint16_t* t16 = reinterpret_cast<uint16_t*>(order_smem);
+      bhead = order_smem + 5u * pad / 2u;
+      const uint16_t* pos = order_run<uint16_t>(rs, B, gh, t16, t16 + pad, t16 + 2u * pad, t16 + 3u * pad, t16 + 4u * pad, bhead,
+                                                n_final, warp_sums);
       for (uint32_t e = tid; e < B; e += kOrderThreads) ray_list[base_rank + pos[e]] = head_of[e];
       __syncthreads();
       base_rank += B;
@@ -504,7 +501,7 @@ k_bundle_order(RehashSchedule rs, OrderScratch g, uint32_t smem_words, uint32_t*
       for (int k = 0; k < k_small; ++k) {
         const uint32_t mk = rs.m[k];
         if (mk > 0) {
-          order_positions(h, c0, c1, next, bkt, A, bhead, mk, n_cur, tag++, warp_sums);
+          order_positions<uint32_t>(h, c0, c1, next, bkt, A, bhead, mk, n_cur, tag++, warp_sums);
           for (uint32_t e = mk + tid; e < m_small; e += kOrderThreads) c1[e] = e;
           __syncthreads();
           uint32_t* t = c0;
@@ -1969,20 +1966,36 @@ static int own_sort(vbx_ctx* c, int which, KeyT* keys_a, uint32_t* vals_a, KeyT*
 
 // k_order_prefix, k_order_heads, k_bundle_order on stream `so` (see the kernels).
 constexpr int kOrderGrid = 32;  // blocks of the cooperative k_bundle_order launch (only large maps use more than one)
+// The shared memory asked for is what the bundle count of recent scans needs (plus a margin), not the whole
+// SM: a block that wants 200 KB can only start on an SM that holds nothing else, and in the pipelined path
+// -- every SM busy with other scans' kernels -- it waits for one to drain.  A scan with more bundles than the
+// request covers is still ordered correctly: the kernel falls back to its global-memory stages.
 template <typename KeyT>
-static int launch_bundle_order(vbx_ctx* c, cudaStream_t so, const ScanParams& P, const KeyT* keys, const uint32_t* vals,
-                               uint32_t smem_words) {
+static int launch_bundle_order(vbx_ctx* c, cudaStream_t so, const ScanParams& P, const KeyT* keys, const uint32_t* vals) {
   k_order_prefix<<<1, kOrderThreads, 0, so>>>(P.n, c->first_bits, c->order_scratch, c->d_state);
   k_order_heads<KeyT><<<std::min<unsigned int>(grid_for(P.n, 256), 148 * 2), 256, 0, so>>>(
       P, keys, vals, c->order_inv, c->head_list, c->first_bits, c->order_scratch, c->d_state);
   RehashSchedule rs = c->rehash;
+  size_t smem_bytes = c->order_smem_bytes;
+  unsigned int grid = kOrderGrid;
+  if (c->bundle_hint) {
+    const uint32_t B = (uint32_t)std::min<uint64_t>(c->bundle_hint + c->bundle_hint / 4 + 512, P.n);
+    uint32_t nf = 1;
+    for (int k = 0; k < rs.count && rs.m[k] < B; ++k) nf = rs.n[k];
+    const uint32_t words = order_smem_words_needed(B, nf);
+    const size_t need = ((size_t)words * 4 + 1023) & ~(size_t)1023;
+    if (words != 0xffffffffu && need <= c->order_smem_bytes) {
+      smem_bytes = need;
+      grid = 1;  // the single-block form; block 0 is the only one that would work
+    }
+  }
   OrderScratch g = c->order_scratch;
+  uint32_t smem_words = (uint32_t)(smem_bytes / 4);
   uint32_t* ray_list = c->ray_list;
   uint32_t* cta_tot = c->order_scratch.cta_tot;
   ScanState* st = c->d_state;
   void* args[] = {&rs, &g, &smem_words, &ray_list, &cta_tot, &st};
-  VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_bundle_order, dim3(kOrderGrid), dim3(kOrderThreads), args,
-                                          c->order_smem_bytes, so));
+  VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_bundle_order, dim3(grid), dim3(kOrderThreads), args, smem_bytes, so));
   return VBX_OK;
 }
 
@@ -2021,7 +2034,7 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
       VBX_CUDA(c, cudaEventRecord(c->ev_fork, s));
       VBX_CUDA(c, cudaStreamWaitEvent(so, c->ev_fork, 0));
     }
-    if (int rc = launch_bundle_order<KeyT>(c, so, P, keys, vals, (uint32_t)(c->order_smem_bytes / 4))) return rc;
+    if (int rc = launch_bundle_order<KeyT>(c, so, P, keys, vals)) return rc;
     if (so != s) VBX_CUDA(c, cudaEventRecord(c->ev_join, so));
     mk.mark(12);
     k_merge<KeyT><<<c->grid_sms * 4, 192, 0, s>>>(P, d_xyz, d_rgba, keys, vals, c->head_list, c->big_list, c->ray_p, c->ray_a,
@@ -2298,6 +2311,7 @@ int integrate_device(vbx_ctx* c, int kind, const float q[4], const float t[3], c
   mk.collect();
   c->launches += launches;
   c->counters[0] = c->h_state->n_rays;
+  if (kind == VBX_MERGED) c->bundle_hint = std::max(c->h_state->n_rays, c->h_state->n_clear_rays);
   c->counters[1] = c->h_state->n_clear_rays;
   c->counters[2] = K;
   if (K) c->record_hint = K;
@@ -2393,6 +2407,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   if (rc == VBX_OK && cudaMemsetAsync(S.d_state, 0, sizeof(ScanState), F.stream) != cudaSuccess) {
     rc = fail(c, VBX_E_CUDA, "cudaMemsetAsync");
   }
+  if (rc == VBX_OK && c->timeline) cudaEventRecord(S.front_start, F.stream);
   if (rc == VBX_OK) {
     rc = front_half<uint64_t>(c, P, dx, dr, nullptr, mk, &launches, &keys64);
   }
