@@ -163,8 +163,8 @@ void select_lane(vbx_ctx* c, int l) {
 }
 
 int drain_async(vbx_ctx* c) {
-  for (int k = 0; k < vbx_ctx::kSets; ++k) {
-    vbx_ctx::ScratchSet& S = c->set[(c->async_seq + k) % vbx_ctx::kSets];  // oldest submission first
+  for (int k = 0; k < c->sets_in_use; ++k) {
+    vbx_ctx::ScratchSet& S = c->set[(c->async_seq + k) % c->sets_in_use];  // oldest submission first
     if (!S.in_flight) continue;
     VBX_CUDA(c, cudaEventSynchronize(S.back_done));
     harvest_async(c, S);
@@ -449,12 +449,15 @@ int ensure_async(vbx_ctx* c) {
     cudaError_t _e = (expr);                               \
     if (_e != cudaSuccess) return cuda_fail(c, _e, #expr); \
   } while (0)
+  if (const char* e = std::getenv("VBX_ASYNC_SETS")) c->sets_in_use = std::max(2, std::min(std::atoi(e), (int)vbx_ctx::kSets));
+  if (const char* e = std::getenv("VBX_ASYNC_LANES")) c->lanes_in_use = std::max(1, std::min(std::atoi(e), (int)vbx_ctx::kLanes));
   const size_t np = c->max_points;
+  CK(cudaStreamCreateWithFlags(&c->stream_h, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithPriority(&c->stream_e, cudaStreamNonBlocking, std::min(c->prio_lo, c->prio_hi + 1)));
   for (int i = 0; i < vbx_ctx::kSortStreams; ++i) {
     CK(cudaStreamCreateWithPriority(&c->stream_s[i], cudaStreamNonBlocking, std::min(c->prio_lo, c->prio_hi + 2)));
   }
-  for (int l = 0; l < vbx_ctx::kLanes; ++l) {
+  for (int l = 0; l < c->lanes_in_use; ++l) {
     vbx_ctx::FrontLane& F = c->lane[l];
     CK(cudaStreamCreateWithPriority(&F.stream, cudaStreamNonBlocking, c->prio_lo));
     if (l == 0) continue;
@@ -473,13 +476,14 @@ int ensure_async(vbx_ctx* c) {
     CK(cudaEventCreate(&c->timeline_ref));
     CK(cudaEventRecord(c->timeline_ref, c->stream_main));
   }
-  for (int k = 0; k < vbx_ctx::kSets; ++k) {
+  for (int k = 0; k < c->sets_in_use; ++k) {
     vbx_ctx::ScratchSet& S = c->set[k];
     CK(cudaEventCreateWithFlags(&S.copy_done, evf));
     CK(cudaEventCreateWithFlags(&S.front_done, evf));
     CK(cudaEventCreateWithFlags(&S.walked, evf));
     CK(cudaEventCreateWithFlags(&S.sorted, evf));
     CK(cudaEventCreateWithFlags(&S.back_done, evf));
+    CK(cudaEventCreateWithFlags(&S.applied, evf));
     if (c->timeline) CK(cudaEventCreate(&S.front_start));
     if (k == 0) continue;
     CK(dmalloc(&S.ray_p, np));
@@ -516,6 +520,7 @@ void vbx_destroy(vbx_ctx* c) {
   if (c->stream_main) cudaStreamSynchronize(c->stream_main);
   if (c->stream_c) cudaStreamSynchronize(c->stream_c);
   if (c->stream_c2) cudaStreamSynchronize(c->stream_c2);
+  if (c->stream_h) cudaStreamSynchronize(c->stream_h);
   if (c->stream_e) cudaStreamSynchronize(c->stream_e);
   for (int i = 0; i < vbx_ctx::kSortStreams; ++i) {
     if (c->stream_s[i]) cudaStreamSynchronize(c->stream_s[i]);
@@ -561,6 +566,7 @@ void vbx_destroy(vbx_ctx* c) {
     if (S.walked) cudaEventDestroy(S.walked);
     if (S.sorted) cudaEventDestroy(S.sorted);
     if (S.back_done) cudaEventDestroy(S.back_done);
+    if (S.applied) cudaEventDestroy(S.applied);
     if (S.front_start) cudaEventDestroy(S.front_start);
   }
   for (int l = 0; l < vbx_ctx::kLanes; ++l) {
@@ -595,6 +601,7 @@ void vbx_destroy(vbx_ctx* c) {
   }
   if (c->stream_c) cudaStreamDestroy(c->stream_c);
   if (c->stream_c2) cudaStreamDestroy(c->stream_c2);
+  if (c->stream_h) cudaStreamDestroy(c->stream_h);
   delete c;
 }
 
@@ -649,10 +656,14 @@ int vbx_debug_sort(vbx_ctx* c, const void* keys, int key_bytes, uint32_t n, int 
 int vbx_debug_async_timeline(vbx_ctx* c, uint64_t* seq, float* ms, int cap_sets) {
   if (!c || !seq || !ms) return VBX_E_INVALID;
   if (!c->async_ready || !c->timeline) return fail(c, VBX_E_STATE, "set VBX_ASYNC_TIMELINE before the first asynchronous submission");
-  for (int k = 0; k < vbx_ctx::kSets && k < cap_sets; ++k) {
+  for (int k = 0; k < cap_sets; ++k) {
+    if (k >= c->sets_in_use) {
+      seq[k] = ~0ull;
+      continue;
+    }
     vbx_ctx::ScratchSet& S = c->set[k];
     seq[k] = S.seq;
-    cudaEvent_t ev[5] = {S.front_start, S.front_done, S.walked, S.sorted, S.back_done};
+    cudaEvent_t ev[5] = {S.front_start, S.front_done, S.walked, S.sorted, S.applied};
     for (int j = 0; j < 5; ++j) {
       float t = -1.f;
       if (cudaEventSynchronize(ev[j]) != cudaSuccess || cudaEventElapsedTime(&t, c->timeline_ref, ev[j]) != cudaSuccess) {

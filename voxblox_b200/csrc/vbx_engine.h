@@ -143,6 +143,7 @@ struct vbx_ctx {
   cudaStream_t stream_main = nullptr; // back halves, ESDF, block management, synchronous calls
   cudaStream_t stream_c = nullptr;    // host-to-device cloud copies of asynchronously submitted scans
   cudaStream_t stream_c2 = nullptr;   // ... alternating with this one
+  cudaStream_t stream_h = nullptr;    // read-back of a queued scan's status block (keeps the copy engine out of the apply stream)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   vbx_tsdf_config cfg;
   vbx_engine_options opt;
@@ -209,7 +210,8 @@ struct vbx_ctx {
   // the main stream -- so up to kSets scans are in flight, each owning one set of hand-off
   // buffers.  Map-touching stages run in submission order.  Set 0 / lane 0 are the buffers the
   // synchronous calls use; the others are allocated on the first asynchronous submission.
-  static constexpr int kSets = 10, kLanes = 6, kSortStreams = 2;
+  static constexpr int kSets = 16, kLanes = 8, kSortStreams = 2;  // upper bounds
+  int sets_in_use = 10, lanes_in_use = 6;  // (tuning aids: VBX_ASYNC_SETS, VBX_ASYNC_LANES)
   struct ScratchSet {
     float4* ray_p = nullptr;
     float4* ray_a = nullptr;
@@ -229,6 +231,7 @@ struct vbx_ctx {
     vbx::SortPlan* sort_plan1 = nullptr;
     uint32_t* sort_status1 = nullptr;
     cudaEvent_t copy_done = nullptr, front_done = nullptr, walked = nullptr, sorted = nullptr, back_done = nullptr;
+    cudaEvent_t applied = nullptr;      // the apply kernels are done (the status read-back follows on stream_h)
     cudaEvent_t front_start = nullptr;  // only with VBX_ASYNC_TIMELINE (vbx_debug_async_timeline)
     bool in_flight = false;
     int kind = 0;

@@ -52,6 +52,35 @@ __device__ __forceinline__ void block_wait_for(const uint32_t* p, uint32_t want)
   __syncthreads();
 }
 
+// Decoupled look-back of tile `tile` (> 0): the sum of the predecessors' aggregates back to (and including) the
+// nearest inclusive prefix.  base[t * stride] is tile t's status word.  The words of kLookBatch predecessors
+// are requested together -- independent loads, one L2 round trip for the batch instead of one per tile --
+// and then consumed in order; a word that is not published yet is polled.
+constexpr int kLookBatch = 8;
+__device__ __forceinline__ uint32_t look_back(const uint32_t* base, uint32_t stride, uint32_t tile) {
+  uint32_t excl = 0;
+  uint32_t t = tile;  // predecessors t-1, t-2, ... 0
+  while (t > 0) {
+    uint32_t v[kLookBatch];
+    const uint32_t nb = t < (uint32_t)kLookBatch ? t : (uint32_t)kLookBatch;
+#pragma unroll
+    for (int i = 0; i < kLookBatch; ++i) {
+      if ((uint32_t)i < nb) v[i] = ld_status(base + (size_t)(t - 1u - (uint32_t)i) * stride);
+    }
+#pragma unroll
+    for (int i = 0; i < kLookBatch; ++i) {
+      if ((uint32_t)i < nb) {
+        uint32_t x = v[i];
+        while ((x & ~kValueMask) == 0u) x = ld_status(base + (size_t)(t - 1u - (uint32_t)i) * stride);
+        excl += x & kValueMask;
+        if (x & kFlagPrefix) return excl;
+      }
+    }
+    t -= nb;
+  }
+  return excl;  // (not reached: tile 0 always publishes a prefix)
+}
+
 // exclusive scan of one value per thread over a 256-thread block; returns the exclusive prefix
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* warp_sums /* [8] shared */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,15 +260,7 @@ k_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, const uns
         st_status(mine, kFlagPrefix | total);
       } else {
         st_status(mine, kFlagAggregate | total);
-        for (uint32_t t = tile; t-- > 0;) {
-          const uint32_t* theirs = status + (size_t)t * kRadix + threadIdx.x;
-          uint32_t v;
-          do {
-            v = ld_status(theirs);
-          } while ((v & ~kValueMask) == 0u);
-          excl += v & kValueMask;
-          if (v & kFlagPrefix) break;
-        }
+        excl = look_back(status + threadIdx.x, kRadix, tile);
         st_status(mine, kFlagPrefix | (excl + total));
       }
       tile_excl[threadIdx.x] = excl;
@@ -306,14 +327,7 @@ k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ p
         st_status(status, kFlagPrefix | total);
       } else {
         st_status(status + tile, kFlagAggregate | total);
-        for (uint32_t t = tile; t-- > 0;) {
-          uint32_t s;
-          do {
-            s = ld_status(status + t);
-          } while ((s & ~kValueMask) == 0u);
-          excl += s & kValueMask;
-          if (s & kFlagPrefix) break;
-        }
+        excl = look_back(status, 1, tile);
         st_status(status + tile, kFlagPrefix | (excl + total));
       }
       tile_base = excl;

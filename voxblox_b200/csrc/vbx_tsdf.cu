@@ -2362,9 +2362,9 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   }
   if (int rc = ensure_async(c)) return rc;
   const uint32_t n = (uint32_t)n64;
-  const int k = (int)(c->async_seq % vbx_ctx::kSets);
+  const int k = (int)(c->async_seq % c->sets_in_use);
   vbx_ctx::ScratchSet& S = c->set[k];
-  vbx_ctx::FrontLane& F = c->lane[c->async_seq % vbx_ctx::kLanes];
+  vbx_ctx::FrontLane& F = c->lane[c->async_seq % c->lanes_in_use];
   if (S.in_flight) {  // bounded run-ahead: wait for the scan that used this hand-off set
     VBX_CUDA(c, cudaEventSynchronize(S.back_done));
     harvest_async(c, S);
@@ -2374,7 +2374,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
     }
   }
   select_set(c, k);
-  select_lane(c, (int)(c->async_seq % vbx_ctx::kLanes));
+  select_lane(c, (int)(c->async_seq % c->lanes_in_use));
   ScanParams P;
   fill_params(c, kind, q, t, n, freespace, P);
   uint64_t launches = 0;
@@ -2433,8 +2433,12 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
       rc = back_half<uint64_t>(c, P, keys64, 0, 0, mk, &launches);
     }
   }
-  if (rc == VBX_OK && (cudaMemcpyAsync(S.h_state, S.d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->stream_main) != cudaSuccess ||
-                       cudaEventRecord(S.back_done, c->stream_main) != cudaSuccess)) {
+  // the status block travels on a stream of its own: a copy between two scans' apply kernels would make the
+  // apply stream (the pace setter of the pipeline) hop between the compute and the copy engine for every scan
+  if (rc == VBX_OK && (cudaEventRecord(S.applied, c->stream_main) != cudaSuccess ||
+                       cudaStreamWaitEvent(c->stream_h, S.applied, 0) != cudaSuccess ||
+                       cudaMemcpyAsync(S.h_state, S.d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->stream_h) != cudaSuccess ||
+                       cudaEventRecord(S.back_done, c->stream_h) != cudaSuccess)) {
     rc = fail(c, VBX_E_CUDA, "enqueueing the result read-back failed");
   }
   c->profiling = profiling;
