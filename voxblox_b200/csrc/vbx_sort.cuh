@@ -294,16 +294,20 @@ k_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, const uns
 
 // Exclusive prefix sum of n uint32 (n known on the host), chained scan over tiles of 2048.  With a
 // permutation the summand at position i is in[perm[i]] for i < *d_limit and 0 beyond (the record
-// offsets of the Merged integrator: counts are stored per bundle id, offsets are needed in rank order).
+// offsets of the Merged integrator: counts are stored per bundle id, offsets are needed in rank order;
+// a few thousand bundles out of a launch sized for every point its own bundle).
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kSortThreads * kScanItems;
 static __global__ void __launch_bounds__(kSortThreads)
 k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ d_limit,
                  uint32_t* __restrict__ out, uint32_t n, uint32_t* status, uint32_t* tile_counter) {
   const uint32_t limit = d_limit ? *d_limit : 0xffffffffu;
+  // with a limit only positions [0, limit] are scanned (position `limit` holds the total: its summand is 0);
+  // the total is also stored at out[n - 1], where the callers read it -- positions in between are not written
+  const uint32_t n_eff = (d_limit && limit < n - 1u) ? limit + 1u : n;
   __shared__ uint32_t warp_sums[kSortWarps];
   __shared__ uint32_t cur_tile, tile_base;
-  const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  const uint32_t n_tiles = (n_eff + kScanTile - 1) / kScanTile;
   while (true) {
     __syncthreads();
     if (threadIdx.x == 0) cur_tile = atomicAdd(tile_counter, 1u);
@@ -316,7 +320,7 @@ k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ p
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
       const uint32_t e = base + j;
-      v[j] = (e < n && e < limit) ? in[perm ? perm[e] : e] : 0u;
+      v[j] = (e < n_eff && e < limit) ? in[perm ? perm[e] : e] : 0u;
       sum += v[j];
     }
     const uint32_t excl_in_tile = block_exclusive_scan_256(sum, warp_sums);
@@ -336,7 +340,8 @@ k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ p
     uint32_t run = tile_base + excl_in_tile;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-      if (base + j < n) out[base + j] = run;
+      if (base + j < n_eff) out[base + j] = run;
+      if (n_eff < n && base + j == n_eff - 1u) out[n - 1u] = run;
       run += v[j];
     }
   }

@@ -2157,6 +2157,11 @@ static int apply_in_passes(vbx_ctx* c, ScanParams P, const KeyT* keys, Marks& mk
   std::vector<uint32_t> off(n + 1);
   VBX_CUDA(c, cudaMemcpyAsync(off.data(), c->off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
+  if (P.kind == VBX_MERGED) {
+    // the scan wrote the offsets of the bundles and, at [n], the total; ranks past the last bundle hold nothing
+    const uint32_t nr = std::min(c->h_state->n_ray_list, n);
+    for (uint32_t i = nr + 1; i < n; ++i) off[i] = off[n];
+  }
   uint32_t lo = 0, passes = 0;
   while (lo < n) {
     // the longest slot range starting at lo whose records fit
