@@ -120,6 +120,11 @@ k_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, const uns
   __shared__ uint32_t tile_excl[kRadix];
   __shared__ uint32_t warp_sums[kSortWarps];
   __shared__ uint32_t cur_tile, s_flag;
+  // staging of one tile in digit order (32-bit keys only; a one-element dummy otherwise)
+  constexpr int kStage = sizeof(KeyT) == 4 ? kSortTile : 1;
+  __shared__ uint32_t stage_k[kStage];
+  __shared__ uint32_t stage_v[kStage];
+  __shared__ uint32_t digit_base_tile[sizeof(KeyT) == 4 ? kRadix : 1];
   static_assert(kSortWarps == kMaxPasses, "the histogram phase reuses warp_hist as hist[pass][digit]");
   // the number of key bits in use may be known on the device only: passes beyond them are not even histogrammed
   if (d_key_bits) passes = min(passes, (int)((*d_key_bits + 7u) / 8u));
@@ -263,16 +268,48 @@ k_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, const uns
         excl = look_back(status + threadIdx.x, kRadix, tile);
         st_status(mine, kFlagPrefix | (excl + total));
       }
-      tile_excl[threadIdx.x] = excl;
-      __syncthreads();
+      if constexpr (sizeof(KeyT) == 4) {
+        // 32-bit keys (the update records: up to millions per scan): the tile is first put in digit order
+        // in shared memory, then written out by consecutive threads -- every digit's elements leave as one
+        // contiguous run instead of 32 scattered sectors per store instruction
+        const uint32_t tstart = block_exclusive_scan_256(total, warp_sums);  // digit's first position inside the tile
+        tile_excl[threadIdx.x] = digit_base[threadIdx.x] + excl - tstart;    // global position of tile position q: + q
+        digit_base_tile[threadIdx.x] = tstart;
+        __syncthreads();
 #pragma unroll
-      for (int j = 0; j < kSortItems; ++j) {
-        const uint32_t e = base + j * 32 + lane;
-        if (e < n) {
-          const uint32_t d = (uint32_t)(key[j] >> (8 * pass)) & 0xffu;
-          const uint32_t pos = digit_base[d] + tile_excl[d] + warp_hist[warp][d] + rank[j];
-          dst_k[pos] = key[j];
-          dst_v[pos] = val[j];
+        for (int j = 0; j < kSortItems; ++j) {
+          const uint32_t e = base + j * 32 + lane;
+          if (e < n) {
+            const uint32_t d = (uint32_t)(key[j] >> (8 * pass)) & 0xffu;
+            const uint32_t p = digit_base_tile[d] + warp_hist[warp][d] + rank[j];
+            stage_k[p] = (uint32_t)key[j];
+            stage_v[p] = val[j];
+          }
+        }
+        __syncthreads();
+        const uint32_t in_tile = min((uint32_t)kSortTile, n - tile * kSortTile);
+#pragma unroll 4
+        for (int i = 0; i < kSortItems; ++i) {
+          const uint32_t q = i * kSortThreads + threadIdx.x;
+          if (q < in_tile) {
+            const uint32_t k = stage_k[q];
+            const uint32_t pos = tile_excl[(k >> (8 * pass)) & 0xffu] + q;
+            dst_k[pos] = (KeyT)k;
+            dst_v[pos] = stage_v[q];
+          }
+        }
+      } else {
+        tile_excl[threadIdx.x] = excl;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSortItems; ++j) {
+          const uint32_t e = base + j * 32 + lane;
+          if (e < n) {
+            const uint32_t d = (uint32_t)(key[j] >> (8 * pass)) & 0xffu;
+            const uint32_t pos = digit_base[d] + tile_excl[d] + warp_hist[warp][d] + rank[j];
+            dst_k[pos] = key[j];
+            dst_v[pos] = val[j];
+          }
         }
       }
       // this tile is scattered: visible to every SM before it is counted

@@ -359,6 +359,15 @@ __global__ void k_order_heads(ScanParams P, const KeyT* __restrict__ keys, const
   }
 }
 
+// A one-block grid needs no cooperative launch: its grid barrier is the block barrier.
+__device__ __forceinline__ void order_grid_sync(cg::grid_group& grid) {
+  if (gridDim.x == 1) {
+    __syncthreads();
+  } else {
+    grid.sync();
+  }
+}
+
 // grid-wide version of order_positions (vbx_order.cuh) on global tables; every block of the cooperative
 // grid calls it.  cta_tot: one word per block.
 __device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, const uint32_t* tau, uint32_t* tau_out,
@@ -372,7 +381,7 @@ __device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, co
     const uint32_t old = atomicExch(&bhead[gb], tg | b);
     next[b] = (old >> 20) == tag ? (old & 0xfffffu) : kOrderNil;
   }
-  grid.sync();
+  order_grid_sync(grid);
   for (uint32_t b = gtid; b < m; b += gthreads) {
     const uint32_t tb = __ldcg(&tau[b]);
     uint32_t cmin = kOrderNil, size = 0;
@@ -382,7 +391,7 @@ __device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, co
     }
     A[tb] = cmin == tb ? size : 0u;
   }
-  grid.sync();
+  order_grid_sync(grid);
   // exclusive suffix sum of A over times: block c owns a contiguous range of times (block 0 the highest),
   // thread t of it a contiguous run inside
   {
@@ -397,7 +406,7 @@ __device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, co
     uint32_t total;
     uint32_t run = order_block_scan(sum, warp_sums, &total);
     if (threadIdx.x == 0) cta_tot[blockIdx.x] = total;
-    grid.sync();
+    order_grid_sync(grid);
     uint32_t above = 0;  // elements at times above this block's range
     for (uint32_t c = 0; c < blockIdx.x; ++c) above += __ldcg(&cta_tot[c]);
     run += above;
@@ -407,7 +416,7 @@ __device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, co
       run += v;
     }
   }
-  grid.sync();
+  order_grid_sync(grid);
   for (uint32_t b = gtid; b < B; b += gthreads) {
     if (b >= m) {  // inserted after this rehash: the insertion index stays its time
       tau_out[b] = b;
@@ -422,7 +431,7 @@ __device__ void order_positions_grid(cg::grid_group& grid, const uint32_t* h, co
     }
     tau_out[b] = __ldcg(&A[cmin]) + later;
   }
-  grid.sync();
+  order_grid_sync(grid);
 }
 
 __global__ void __launch_bounds__(kOrderThreads)
@@ -516,7 +525,7 @@ k_bundle_order(RehashSchedule rs, OrderScratch g, uint32_t smem_words, uint32_t*
     const uint32_t gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
     for (uint32_t e = m_small + gtid; e < B; e += gthreads) cur[e] = e;
     for (uint32_t j = gtid; j < n_final; j += gthreads) g.bhead[j] = 0u;
-    grid.sync();
+    order_grid_sync(grid);
     uint32_t n_cur = n_small, tag = 1;
     for (int k = k_small; k < rs.count && rs.m[k] < B; ++k) {
       order_positions_grid(grid, gh, cur, oth, g.next, g.bkt, g.A, g.bhead, rs.m[k], n_cur, tag++, B, cta_tot, warp_sums);
@@ -527,7 +536,7 @@ k_bundle_order(RehashSchedule rs, OrderScratch g, uint32_t smem_words, uint32_t*
     }
     order_positions_grid(grid, gh, cur, oth, g.next, g.bkt, g.A, g.bhead, B, n_cur, tag, B, cta_tot, warp_sums);
     for (uint32_t e = gtid; e < B; e += gthreads) ray_list[base_rank + __ldcg(&oth[e])] = head_of[e];
-    grid.sync();  // the arrays are reused by the other map
+    order_grid_sync(grid);  // the arrays are reused by the other map
     base_rank += B;
   }
 }
@@ -1995,7 +2004,12 @@ static int launch_bundle_order(vbx_ctx* c, cudaStream_t so, const ScanParams& P,
   uint32_t* cta_tot = c->order_scratch.cta_tot;
   ScanState* st = c->d_state;
   void* args[] = {&rs, &g, &smem_words, &ray_list, &cta_tot, &st};
-  VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_bundle_order, dim3(grid), dim3(kOrderThreads), args, smem_bytes, so));
+  if (grid == 1) {
+    // an ordinary launch: nothing about it has to be co-scheduled
+    k_bundle_order<<<1, kOrderThreads, smem_bytes, so>>>(rs, g, smem_words, ray_list, cta_tot, st);
+  } else {
+    VBX_CUDA(c, cudaLaunchCooperativeKernel((void*)k_bundle_order, dim3(grid), dim3(kOrderThreads), args, smem_bytes, so));
+  }
   return VBX_OK;
 }
 
