@@ -337,7 +337,9 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kSortThreads * kScanItems;
 static __global__ void __launch_bounds__(kSortThreads)
 k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ d_limit,
-                 uint32_t* __restrict__ out, uint32_t n, uint32_t* status, uint32_t* tile_counter) {
+                 uint32_t* __restrict__ out, uint32_t n, uint32_t* status, uint32_t* tile_counter,
+                 unsigned long long* total_out, unsigned long long* total_ok_out, uint32_t* error_word,
+                 unsigned long long total_max, uint32_t error_bit) {
   const uint32_t limit = d_limit ? *d_limit : 0xffffffffu;
   // with a limit only positions [0, limit] are scanned (position `limit` holds the total: its summand is 0);
   // the total is also stored at out[n - 1], where the callers read it -- positions in between are not written
@@ -378,7 +380,19 @@ k_exclusive_scan(const uint32_t* __restrict__ in, const uint32_t* __restrict__ p
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
       if (base + j < n_eff) out[base + j] = run;
-      if (n_eff < n && base + j == n_eff - 1u) out[n - 1u] = run;
+      if (base + j == n_eff - 1u) {
+        // the last scanned position: its exclusive prefix is the sum of everything (its own summand is 0 by
+        // the callers' construction).  What the integration pipeline does with the total (its update-record
+        // count): too many for one pass is an error, and nothing downstream runs on a failed call.
+        if (n_eff < n) out[n - 1u] = run;
+        if (total_out) {
+          unsigned long long total = run;
+          if (total > total_max) atomicOr(error_word, error_bit);
+          *total_out = total;
+          if (*reinterpret_cast<volatile uint32_t*>(error_word) != 0u || total > total_max) total = 0;
+          *total_ok_out = total;
+        }
+      }
       run += v[j];
     }
   }

@@ -155,13 +155,20 @@ __device__ __forceinline__ I3 key_voxel(const KeyLayout& k, uint64_t key) {
 // Merged, pass 1 over the cloud: the bounding box of the valid points' voxels (and their count).
 // Grid-stride over the points, one set of atomics per thread block.
 __global__ void __launch_bounds__(256)
-k_point_bounds(ScanParams P, const float* __restrict__ xyz, uint32_t* __restrict__ first_bits, ScanState* st) {
+k_point_bounds(ScanParams P, const float* __restrict__ xyz, uint32_t* __restrict__ first_bits, SortPlan* plan,
+               uint32_t* __restrict__ scan_status, uint32_t scan_words, ScanState* st) {
   __shared__ uint32_t s_red[7];
   if (threadIdx.x < 7) s_red[threadIdx.x] = 0u;
   const uint32_t words2 = 2u * ((P.n + 31u) >> 5);
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words2; w += gridDim.x * blockDim.x) {
     first_bits[w] = 0u;  // the first-occurrence bitmaps k_heads fills
   }
+  // (the first kernel of the front half also clears what later kernels of its lane count in: the point sort's
+  // plan and the status words of the offset scan)
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < (uint32_t)(sizeof(SortPlan) / 4); w += gridDim.x * blockDim.x) {
+    reinterpret_cast<uint32_t*>(plan)[w] = 0u;
+  }
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < scan_words; w += gridDim.x * blockDim.x) scan_status[w] = 0u;
   __syncthreads();
   // both ends encoded so that the zero-initialised status block means "empty" and atomicMax serves both
   uint32_t hi_x = 0, hi_y = 0, hi_z = 0, lo_x = 0, lo_y = 0, lo_z = 0, n_valid = 0;
@@ -1169,17 +1176,6 @@ __global__ void k_rays_count(ScanParams P, Tables tab, const float* __restrict__
   cnt[i] = count;
 }
 
-// After the scan: the call's update count, and whether anything downstream may run at all.
-__global__ void k_set_total(const uint32_t* __restrict__ off, uint32_t n, uint64_t max_updates, ScanState* st,
-                            unsigned long long total_if_no_off) {
-  unsigned long long total = off ? (unsigned long long)off[n] : total_if_no_off;
-  if (total > max_updates) atomicOr(&st->error, kErrUpdatesFull);
-  st->total_found = total;
-  // nothing downstream may run on a call that failed or must be redone with wide keys
-  if (st->error != 0 || total > max_updates) total = 0;
-  st->total_updates = total;
-}
-
 // A call that is applied in several passes (K > max_updates_per_pass): before each pass.  Blocks
 // created by earlier passes already own their slots; the apply work lists restart.
 __global__ void k_pass_begin(ScanState* st, unsigned long long pass_updates) {
@@ -1202,8 +1198,10 @@ __global__ void k_back_begin(ScanState* st, uint32_t* hold) {
 
 // After the last walk that can create blocks: pool slots for the blocks created by this call
 // (updateLayerWithStoredBlocks, cc:137-147); a new block is born with all updated bits set (cc:128).
-__global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_t* __restrict__ nb_out, ScanState* st) {
+__global__ void k_assign(Tables tab, const uint32_t* __restrict__ nb_in, uint32_t* __restrict__ nb_out, SortPlan* record_plan,
+                         ScanState* st) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < (uint32_t)(sizeof(SortPlan) / 4)) reinterpret_cast<uint32_t*>(record_plan)[j] = 0u;  // for the record sort that follows
   const uint32_t n_blocks_before = *nb_in;
   const uint32_t n_new = min(st->n_new, tab.max_blocks);
   if (j < n_new) {
@@ -1958,13 +1956,13 @@ struct Marks {
 template <typename KeyT>
 static int own_sort(vbx_ctx* c, int which, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
                     const unsigned long long* d_n, uint32_t n_fixed, uint64_t n_hint, int key_bits, bool result_in_a,
-                    uint64_t* launches, const uint32_t* d_key_bits = nullptr) {
+                    uint64_t* launches, const uint32_t* d_key_bits = nullptr, bool plan_cleared = false) {
   cudaStream_t s = c->stream;
   const int passes = std::min(kMaxPasses, (key_bits + 7) / 8);
   SortPlan* plan = c->sort_plan[which];
   uint32_t* status = c->sort_status[which];
   const uint32_t tiles_cap = c->sort_tiles_cap[which];
-  VBX_CUDA(c, cudaMemsetAsync(plan, 0, sizeof(SortPlan), s));
+  if (!plan_cleared) VBX_CUDA(c, cudaMemsetAsync(plan, 0, sizeof(SortPlan), s));  // (else: an earlier kernel of the stream did)
   const uint64_t tiles_hint = std::max<uint64_t>(1, (n_hint + kSortTile - 1) / kSortTile);
   const unsigned int grid = (unsigned int)std::min<uint64_t>(std::min<uint64_t>(tiles_cap, tiles_hint), (uint64_t)c->grid_sms * 2);
   k_sort<KeyT><<<grid, kSortThreads, 0, s>>>(keys_a, vals_a, keys_b, vals_b, d_n, n_fixed, passes, d_key_bits, plan, status,
@@ -2027,12 +2025,13 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
   if (P.kind == VBX_MERGED) {
     KeyT* k0 = reinterpret_cast<KeyT*>(c->pkeys[0]);
     KeyT* k1 = reinterpret_cast<KeyT*>(c->pkeys[1]);
-    k_point_bounds<<<std::min<unsigned int>(grid_for(n, TB), 148 * 4), TB, 0, s>>>(P, d_xyz, c->first_bits, c->d_state);
+    k_point_bounds<<<std::min<unsigned int>(grid_for(n, TB), 148 * 4), TB, 0, s>>>(
+        P, d_xyz, c->first_bits, c->sort_plan[0], c->scan_status, (n + 1 + kScanTile - 1) / kScanTile + 1, c->d_state);
     k_point_keys<KeyT><<<grid_for(n, TB), TB, 0, s>>>(P, d_xyz, order, k0, c->pvals[0], c->d_state);
     mk.mark(0);
     // the bits in use are known on the device only (ScanState::key_bits): passes beyond them exit at once
     if (int rc = own_sort<KeyT>(c, 0, k0, c->pvals[0], k1, c->pvals[1], nullptr, n, n, 8 * (int)sizeof(KeyT), true, launches,
-                                &c->d_state->key_bits)) {
+                                &c->d_state->key_bits, /*plan_cleared=*/true)) {
       return rc;
     }
     keys = k0;
@@ -2075,14 +2074,16 @@ static int front_half(vbx_ctx* c, ScanParams& P, const float* d_xyz, const uint8
   }
   mk.mark(2);
   {
+    // record offsets; the scan's last position also settles the call's update count (total_found, total_updates,
+    // kErrUpdatesFull: too many for one pass; nothing downstream runs on a call that failed)
     const uint32_t tiles = (n + 1 + kScanTile - 1) / kScanTile;
-    VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
-    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, scan_perm, scan_limit, c->off, n + 1,
-                                                                               c->scan_status + 1, c->scan_status);
+    if (P.kind != VBX_MERGED) VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));  // (Merged: k_point_bounds did)
+    k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(
+        c->cnt, scan_perm, scan_limit, c->off, n + 1, c->scan_status + 1, c->scan_status, &c->d_state->total_found,
+        &c->d_state->total_updates, &c->d_state->error, (unsigned long long)c->max_updates, kErrUpdatesFull);
   }
-  k_set_total<<<1, 1, 0, s>>>(c->off, n, c->max_updates, c->d_state, 0);
   mk.mark(3);
-  *launches += 2;
+  *launches += 1;
   *keys_out = keys;
   return VBX_OK;
 }
@@ -2105,7 +2106,8 @@ static int sort_and_apply(vbx_ctx* c, const ScanParams& P, unsigned long long K,
       c->stream = s;
     }
     if (int rc = own_sort<uint32_t>(c, 1, c->ckeys[0], c->cvals[0], c->ckeys[1], c->cvals[1], &c->d_state->total_updates,
-                                     0, c->record_hint, key_bits, false, launches, &c->d_state->rec_key_bits)) {
+                                     0, c->record_hint, key_bits, false, launches, &c->d_state->rec_key_bits,
+                                     /*plan_cleared=*/true)) {
       return rc;
     }
     rv.keys[0] = c->ckeys[0];
@@ -2155,8 +2157,8 @@ static int back_half(vbx_ctx* c, const ScanParams& P, const KeyT* keys, unsigned
                                                         c->ckeys[0], c->cvals[0], c->d_state);
   }
   mk.mark(5);
-  k_assign<<<grid_for(c->tab.max_blocks, 256), 256, 0, s>>>(c->tab, c->d_nblocks + c->nb_cur, c->d_nblocks + (c->nb_cur ^ 1),
-                                                            c->d_state);
+  k_assign<<<grid_for(std::max<uint32_t>(c->tab.max_blocks, 1024), 256), 256, 0, s>>>(
+      c->tab, c->d_nblocks + c->nb_cur, c->d_nblocks + (c->nb_cur ^ 1), c->sort_plan[1], c->d_state);
   c->nb_cur ^= 1;
   mk.mark(4);
   *launches += 2;
@@ -2575,7 +2577,8 @@ int debug_scan(vbx_ctx* c, const uint32_t* in, uint32_t n, uint32_t* out) {
   VBX_CUDA(c, cudaMemsetAsync(c->scan_status, 0, (size_t)(tiles + 1) * sizeof(uint32_t), s));
   if (n) {
     k_exclusive_scan<<<std::min<uint32_t>(tiles, 148 * 4), kSortThreads, 0, s>>>(c->cnt, nullptr, nullptr, c->off, n,
-                                                                               c->scan_status + 1, c->scan_status);
+                                                                               c->scan_status + 1, c->scan_status, nullptr,
+                                                                               nullptr, nullptr, 0ull, 0u);
   }
   VBX_CUDA(c, cudaMemcpyAsync(out, c->off, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   VBX_CUDA(c, cudaStreamSynchronize(s));
