@@ -361,9 +361,10 @@ def measure_traffic(conf_name, timeout_s=300, cache_control="all"):
 # --------------------------------------------------------------------------- ours
 STAGE_OF_KERNEL = {  # stage name (Layer.stageMs) -> kernels that run in it
     "point_keys": ("k_point_bounds", "k_point_keys"), "point_sort": ("k_sort",),
-    "bundle_order": ("k_heads", "k_bundle_order"), "bundle_merge": ("k_merge",), "scan": ("k_exclusive_scan", "k_set_total"),
+    "update_sort": ("k_sort",), "bundle_order": ("k_order_prefix", "k_order_heads", "k_bundle_order"),
+    "bundle_merge": ("k_merge",), "scan": ("k_exclusive_scan",),
     "ray_emit": ("k_rays_emit_warp", "k_rays_emit", "k_rays_count"), "assign": ("k_assign",),
-    "apply": ("k_apply_short", "k_apply_verify", "k_apply_long", "k_apply_block"),
+    "apply": ("k_apply_short", "k_apply_verify", "k_apply_long"),
 }
 
 
