@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import voxblox_b200 as vb
 from voxblox_b200 import scenes
 
-n = 85
+n = 205
 scans = scenes.generate_parallel(scenes.c3_room_scan, range(n))
 dev = torch.device("cuda", 0)
 d_xyz = [torch.from_numpy(s[0]).to(dev) for s in scans]
@@ -27,7 +27,9 @@ t1 = time.perf_counter()
 layer.sync()
 t2 = time.perf_counter()
 per = np.array(per) * 1e3
-print(json.dumps({"scans": n - 5, "submit_ms_per_scan_mean": float(per.mean()), "submit_ms_per_scan_median": float(np.median(per)),
+cn = integ.counters()
+print(json.dumps({"scans": n - 5, "host_wait_for_free_set_ms_per_scan": cn["async_wait_ns_total"] / 1e6 / n,
+                  "host_in_submission_calls_ms_per_scan_incl_wait": cn["async_submit_ns_total"] / 1e6 / n, "submit_ms_per_scan_mean": float(per.mean()), "submit_ms_per_scan_median": float(np.median(per)),
                   "submit_ms_first10": [round(float(v), 3) for v in per[:10]],
                   "loop_ms_per_scan": (t1 - t0) * 1e3 / (n - 5), "total_ms_per_scan": (t2 - t0) * 1e3 / (n - 5),
                   "drain_ms": (t2 - t1) * 1e3}))

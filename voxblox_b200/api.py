@@ -602,7 +602,7 @@ class TsdfIntegratorBase:
                         "vbx_get_counters")
         names = ["rays", "clear_rays", "updates", "voxels_touched", "blocks_touched",
                  "blocks_allocated", "valid_points", "kernel_launches", "kernel_launches_total", "refolded_bundles",
-                 "refolded_points", "passes", "bundle_key_bits", "async_redone_total"]
+                 "refolded_points", "passes", "bundle_key_bits", "async_redone_total", "async_wait_ns_total", "async_submit_ns_total"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def lastDeviceMs(self) -> float:

@@ -695,6 +695,8 @@ int vbx_get_counters(const vbx_ctx* c, uint64_t out[16]) {
   std::memcpy(out, c->counters, sizeof(c->counters));
   out[8] = c->launches;  // kernels launched by TSDF integration since vbx_create
   out[13] = c->async_redone;  // asynchronously submitted scans that were redone synchronously (see vbx_tsdf_integrate_async)
+  out[14] = c->async_wait_ns;    // host time asynchronous submissions spent waiting for a free hand-off set ...
+  out[15] = c->async_submit_ns;  // ... and enqueueing (cumulative, ns)
   return VBX_OK;
 }
 

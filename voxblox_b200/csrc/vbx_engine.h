@@ -319,6 +319,7 @@ struct vbx_ctx {
   // reporting
   uint32_t last_passes = 1;  // passes the last synchronous integrate call needed (K > max_updates_per_pass)
   uint64_t counters[16] = {0};
+  uint64_t async_wait_ns = 0, async_submit_ns = 0;  // host time of vbx_tsdf_integrate_async: waiting for a hand-off set / enqueueing
   uint64_t esdf_counters[16] = {0};
   uint64_t shard_front_counters[4] = {0};
   float last_ms = 0.f;

@@ -29,6 +29,7 @@
 // of the reference's libstdc++ unordered_map (k_bundle_order, vbx_order.cuh), normal
 // bundles before clearing bundles (cc:323-335).  See DESIGN.md "update order".
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <unordered_map>  // std::__detail::_Prime_rehash_policy: the growth schedule the reference's map follows
@@ -2386,8 +2387,10 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   const int k = (int)(c->async_seq % c->sets_in_use);
   vbx_ctx::ScratchSet& S = c->set[k];
   vbx_ctx::FrontLane& F = c->lane[c->async_seq % c->lanes_in_use];
+  const auto t_enter = std::chrono::steady_clock::now();
   if (S.in_flight) {  // bounded run-ahead: wait for the scan that used this hand-off set
     VBX_CUDA(c, cudaEventSynchronize(S.back_done));
+    c->async_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_enter).count();
     harvest_async(c, S);
     if (S.redo) {
       // it (and every scan queued behind it) did not run its back half: redo them now, in order
@@ -2478,6 +2481,7 @@ int integrate_async(vbx_ctx* c, int kind, const float q[4], const float t[3], co
   S.freespace = freespace;
   S.in_xyz = dx;   // (the set's private copy of a host cloud, or the caller's device buffers)
   S.in_rgba = dr;
+  c->async_submit_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_enter).count();
   c->launches += launches;
   c->async_seq += 1;
   if (c->deferred_rc) {
