@@ -317,10 +317,11 @@ __device__ __forceinline__ uint32_t long_index_hash(int x, int y, int z) {
 //   k_bundle_order  the iteration order of each map; writes ray_list[rank] = bundle id.  Ranks are
 //                   dense: normal bundles 0 .. B0-1 in voxel_map's iteration order, clearing bundles
 //                   B0 .. B0+B1-1 in clear_map's (integrateRays(false) runs before integrateRays(true),
-//                   cc:323-335).  A cooperative launch: when a map's tables fit shared memory (a few
-//                   thousand bundles: 640 x 480 scans) block 0 does everything alone and the others
-//                   leave at once; larger maps (LiDAR: ~50 k bundles) run their late rehash stages
-//                   grid-wide on global tables, the early (small) stages still in block 0's shared memory.
+//                   cc:323-335).  When a map's tables fit shared memory (16-bit tables: up to ~18 k
+//                   bundles; 640 x 480 scans have a few thousand) one block does everything alone -- an
+//                   ordinary one-block launch when recent scans say so, see launch_bundle_order; larger
+//                   maps (LiDAR: ~50 k bundles) run their late rehash stages grid-wide on global tables
+//                   (cooperative launch), the early (small) stages still in block 0's shared memory.
 // The clearing map's arrays follow the normal map's at offset g.cap.
 __global__ void __launch_bounds__(kOrderThreads)
 k_order_prefix(uint32_t n, const uint32_t* __restrict__ first_bits, OrderScratch g, ScanState* st) {
