@@ -51,6 +51,18 @@ def test_product_never_references_the_oracle():
         assert "pyoracle" not in open(os.path.join(ROOT, f)).read()
 
 
+def test_dev_scripts_outside_the_test_tree_do_not_touch_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU-baseline legs may load the checkers: the measurement / probe scripts
+    under scripts/ drive the product alone (the ones that compare against the oracle live under tests/tools/)."""
+    bad = []
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "scripts", f), errors="ignore").read()
+            if re.search(r"from oracle|import oracle|pyoracle|libvbx_ref|libvbx_oracle", text):
+                bad.append(f)
+    assert not bad, bad
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a machine without CUDA the engine must refuse loudly, never compute on the host."""
     import torch
