@@ -142,14 +142,6 @@ def cmp(G, d, obs, name):
                             "max_err": round(float(err.max()), 4), "rmse": round(float(np.sqrt((err**2).mean())), 5)}), flush=True)
     return err
 
-if __name__ == "__main__":
-    md, mq = (0.0, 1) if len(sys.argv) < 2 or sys.argv[1] == "test" else (1e-3, 0)
-    scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
-    m = build(0.1, 0.4, scans, md, mq)
-    G = Grid(m, 0.1, 0.4, md)
-    d, obs, pops = run_ref(G, mq); print("pops", pops); cmp(G, d, obs, "sim_ref(sorted blocks) vs reference")
-    d2, obs2, sw = run_dev(G, mq); print("sweeps", sw); cmp(G, d2, obs2, "sim_dev(level-sync,min) vs reference")
-    d3, obs3, sw = run_dev(G, mq, 'ref'); print("sweeps", sw); cmp(G, d3, obs3, "sim_dev(level-sync,assign) vs reference")
 
 def run_bucket(G, mq, policy, nb=20, shuffle=None):
     """bucket-synchronous: the whole content of the lowest non-empty bucket is one parallel sweep"""
@@ -182,3 +174,76 @@ def run_bucket(G, mq, policy, nb=20, shuffle=None):
                     if mq or not inq[q]:
                         buckets[bidx(nv)].append(q); inq[q] = True
     return d, obs, sweeps
+
+
+
+def run_jacobi(G, mq, rule, nb=20, bucketed=True, shuffle=None):
+    d, obs, fixed, open_list = G.init_batch()
+    inq = np.zeros(G.dims, bool)
+    buckets = [[] for _ in range(nb)]
+    def bidx(v):
+        if not bucketed: return 0
+        v = float(v)
+        if v > 2.0: v = 2.0
+        return min(int(np.floor(abs(v) / 2.0 * (nb - 1))), nb - 1)
+    for p in open_list:
+        inq[p] = True; buckets[bidx(d[p])].append(p)
+    sweeps = 0
+    while True:
+        b = next((i for i in range(nb) if buckets[i]), None)
+        if b is None: break
+        front = buckets[b]; buckets[b] = []
+        if shuffle is not None: shuffle.shuffle(front)
+        sweeps += 1
+        d0 = d.copy()
+        cand_same = {}; cand_mixed = {}
+        for p in front:
+            inq[p] = False
+            vd = d0[p]
+            if not obs[p] or vd >= G.maxd or vd <= -G.maxd: continue
+            for i, o in enumerate(OFF):
+                q = (p[0]+o[0], p[1]+o[1], p[2]+o[2])
+                if not G.exists[q] or not obs[q] or fixed[q]: continue
+                nd = d0[q]; dist = G.dist[i]
+                if (vd > 0 and nd > 0) or (vd <= 0 and nd <= 0):
+                    nv = relax_pair(G, vd, nd, dist, 'ref')
+                    if nv is not None:
+                        if q not in cand_same or abs(nv) < abs(cand_same[q]): cand_same[q] = nv
+                else:
+                    nv = relax_pair(G, vd, nd, dist, 'ref')
+                    if nv is not None: cand_mixed.setdefault(q, []).append(nv)
+        for q in set(cand_same) | set(cand_mixed):
+            new = d0[q]
+            if q in cand_mixed:
+                c = cand_mixed[q]
+                if rule == 'min': mv = min(c, key=lambda x: abs(x))
+                elif rule == 'max': mv = max(c, key=lambda x: abs(x))
+                elif rule == 'min_lower_only':
+                    mv = min(c, key=lambda x: abs(x))
+                    if abs(mv) >= abs(new): mv = new
+                new = mv
+            if q in cand_same and abs(cand_same[q]) < abs(new): new = cand_same[q]
+            if new != d0[q]:
+                d[q] = new
+                if mq or not inq[q]:
+                    buckets[bidx(new)].append(q); inq[q] = True
+    return d, obs, sweeps
+
+
+
+if __name__ == "__main__":
+    import random
+    md, mq = (0.0, 1) if len(sys.argv) < 2 or sys.argv[1] == "test" else (1e-3, 0)
+    scans = scenes.c3_room_sequence(n_scans=4, width=160, height=120)
+    m = build(0.1, 0.4, scans, md, mq)
+    G = Grid(m, 0.1, 0.4, md)
+    print("room scene, 4 scans of 160x120, voxel 0.1 m, batch update, min_diff", md, "multi_queue", mq)
+    d, obs, pops = run_ref(G, mq); cmp(G, d, obs, f"sequential replay of the bucket queue, blocks in sorted order ({pops} pops)")
+    d, obs, sw = run_dev(G, mq); cmp(G, d, obs, f"level-synchronous in place, nearest candidate wins, list order ({sw} sweeps)")
+    d, obs, sw = run_dev(G, mq, 'ref'); cmp(G, d, obs, f"level-synchronous in place, assignment, list order ({sw} sweeps)")
+    for pol in ("ref", "dev"):
+        d, obs, sw = run_bucket(G, mq, pol); cmp(G, d, obs, f"bucket by bucket, FIFO inside a bucket, policy {pol} ({sw} sweeps)")
+        for seed in (1, 2):
+            d, obs, sw = run_bucket(G, mq, pol, shuffle=random.Random(seed)); cmp(G, d, obs, f"bucket by bucket, arbitrary order inside a sweep (seed {seed}), policy {pol}")
+    for rule in ("min", "max"):
+        d, obs, sw = run_jacobi(G, mq, rule); cmp(G, d, obs, f"bucket by bucket, Jacobi sweeps, conflict rule {rule} ({sw} sweeps)")
