@@ -231,6 +231,56 @@ def run_jacobi(G, mq, rule, nb=20, bucketed=True, shuffle=None):
 
 
 
+def replay_dependency_depth(G, mq, nb=20):
+    """How parallel could an EXACT replay be?  Two pops commute iff their 3x3x3 footprints are disjoint; the
+    longest chain of non-commuting pops (in the reference's pop order) is the number of dependent steps any
+    schedule that reproduces the sequential result needs."""
+    d, obs, fixed, open_list = G.init_batch()
+    inq = np.zeros(G.dims, bool)
+    buckets = [collections.deque() for _ in range(nb)]
+    state = {"last": 0, "n": 0}
+
+    def push(p, v):
+        v = min(float(v), 2.0)
+        bi = min(int(np.floor(abs(v) / 2.0 * (nb - 1))), nb - 1)
+        state["last"] = min(state["last"], bi)
+        buckets[bi].append(p)
+        state["n"] += 1
+    for p in open_list:
+        inq[p] = True
+        push(p, d[p])
+    last = np.zeros(tuple(np.array(G.dims) + 2), np.int32)
+    depth = pops = 0
+    while state["n"]:
+        while not buckets[state["last"]]:
+            state["last"] += 1
+        p = buckets[state["last"]].popleft()
+        state["n"] -= 1
+        pops += 1
+        inq[p] = False
+        vd = d[p]
+        x, y, z = p[0] + 1, p[1] + 1, p[2] + 1
+        if not obs[p] or vd >= G.maxd or vd <= -G.maxd:
+            last[x, y, z] += 1
+            depth = max(depth, int(last[x, y, z]))
+            continue
+        sl = (slice(x - 1, x + 2), slice(y - 1, y + 2), slice(z - 1, z + 2))
+        dj = int(last[sl].max()) + 1
+        last[sl] = np.maximum(last[sl], dj)
+        depth = max(depth, dj)
+        for i, o in enumerate(OFF):
+            q = (p[0]+o[0], p[1]+o[1], p[2]+o[2])
+            if not G.exists[q] or not obs[q] or fixed[q]:
+                continue
+            nv = relax_pair(G, d[p], d[q], G.dist[i], 'ref')
+            if nv is not None:
+                d[q] = nv
+                if mq or not inq[q]:
+                    push(q, nv)
+                    inq[q] = True
+    return pops, depth
+
+
 if __name__ == "__main__":
     import random
     md, mq = (0.0, 1) if len(sys.argv) < 2 or sys.argv[1] == "test" else (1e-3, 0)
@@ -247,3 +297,5 @@ if __name__ == "__main__":
             d, obs, sw = run_bucket(G, mq, pol, shuffle=random.Random(seed)); cmp(G, d, obs, f"bucket by bucket, arbitrary order inside a sweep (seed {seed}), policy {pol}")
     for rule in ("min", "max"):
         d, obs, sw = run_jacobi(G, mq, rule); cmp(G, d, obs, f"bucket by bucket, Jacobi sweeps, conflict rule {rule} ({sw} sweeps)")
+    pops, depth = replay_dependency_depth(G, mq)
+    print(f"an exact replay: {pops} pops, longest chain of non-commuting pops {depth} (mean {pops / depth:.1f} pops per dependent step)")
